@@ -1,0 +1,304 @@
+"""ctypes binding of the C-ABI declared in include/xnb_hotpath.h.
+
+This is the same stub a maintainer of the reference would write to call the library from Python (INTEGRATION.md shows the
+C++ one).  It computes nothing itself: every method forwards to libxnb_hotpath.so, and loading fails loudly when the
+library is absent (no CPU fallback)."""
+import ctypes as C
+import os
+import numpy as np
+
+from . import buildlib as _build
+
+XNB_OK = 0
+ERRORS = {1: "XNB_ERR_NO_DEVICE", 2: "XNB_ERR_INVALID", 3: "XNB_ERR_CUDA", 4: "XNB_ERR_CAPACITY", 5: "XNB_ERR_LOST_PARTICLE", 6: "XNB_ERR_NCCL"}
+
+# every symbol include/xnb_hotpath.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
+SYMBOLS = [
+    "xnb_create", "xnb_destroy", "xnb_last_error", "xnb_version", "xnb_set_domain", "xnb_init_rcb_grid", "xnb_set_nbh_dist",
+    "xnb_set_type_mass", "xnb_set_sub_grid_density", "xnb_set_nccl_comm", "xnb_nccl_unique_id", "xnb_nccl_init_rank",
+    "xnb_set_particles", "xnb_num_inner", "xnb_num_total", "xnb_get_particles", "xnb_upload_rv", "xnb_download_rvf",
+    "xnb_get_grid_info", "xnb_get_cells", "xnb_move_particles", "xnb_rebuild_amr", "xnb_backup_r", "xnb_ghost_comm_scheme",
+    "xnb_ghost_update_all", "xnb_ghost_update_r", "xnb_chunk_neighbors", "xnb_zero_particle_force", "xnb_lennard_jones_force",
+    "xnb_divide_force_by_mass", "xnb_push_f_v_r", "xnb_push_f_v", "xnb_particle_displ_over", "xnb_verlet_first_half",
+    "xnb_read_displ_over", "xnb_force_and_second_half", "xnb_run_steps", "xnb_first_iteration", "xnb_energy_virial",
+    "xnb_view_chunk_neighbors", "xnb_stream_pool_u16", "xnb_get_streams", "xnb_get_amr", "xnb_get_backup",
+    "xnb_rebuild_count", "xnb_kernel_launches", "xnb_timing_enable", "xnb_timing_read", "xnb_measure_dfma_peak",
+    "xnb_host_lattice_fcc",
+]
+
+
+class XnbGridInfo(C.Structure):
+    _fields_ = [("dims", C.c_int64 * 3), ("offset", C.c_int64 * 3), ("ghost_layers", C.c_int64), ("n_cells", C.c_int64),
+                ("block_start", C.c_int64 * 3), ("block_end", C.c_int64 * 3)]
+
+
+class XnbLatticeCfg(C.Structure):
+    _fields_ = [("bounds_min", C.c_double * 3), ("bounds_max", C.c_double * 3), ("cell_size", C.c_double), ("grid_dims", C.c_int64 * 3),
+                ("lattice_a", C.c_double), ("noise_sigma", C.c_double), ("vel_sigma", C.c_double),
+                ("n_spheres", C.c_int32), ("sphere_rmin", C.c_double), ("sphere_rmax", C.c_double), ("drift_speed", C.c_double)]
+
+
+class XnbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s: %s" % (ERRORS.get(code, code), msg))
+        self.code = code
+
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load():
+    """dlopen libxnb_hotpath.so (built in-tree by exanbody_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError("libxnb_hotpath.so is not built (%s): run `python -m exanbody_b200.buildlib`; there is no CPU fallback" % path)
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    P, I, D, I64 = C.c_void_p, C.c_int, C.c_double, C.c_int64
+    sig = {
+        "xnb_create": (I, [C.POINTER(P), I]), "xnb_destroy": (None, [P]), "xnb_last_error": (C.c_char_p, [P]), "xnb_version": (C.c_char_p, []),
+        "xnb_set_domain": (I, [P, P, P, D, P, P]), "xnb_init_rcb_grid": (I, [P, I, I]), "xnb_set_nbh_dist": (I, [P, D, D]),
+        "xnb_set_type_mass": (I, [P, P, I]), "xnb_set_sub_grid_density": (I, [P, D]), "xnb_set_nccl_comm": (I, [P, P]),
+        "xnb_nccl_unique_id": (I, [P]), "xnb_nccl_init_rank": (I, [P, P, I, I]),
+        "xnb_set_particles": (I, [P, I64] + [P] * 8), "xnb_num_inner": (I64, [P]), "xnb_num_total": (I64, [P]),
+        "xnb_get_particles": (I, [P, I64, I64] + [P] * 12), "xnb_upload_rv": (I, [P] * 8), "xnb_download_rvf": (I, [P] * 12),
+        "xnb_get_grid_info": (I, [P, C.POINTER(XnbGridInfo)]), "xnb_get_cells": (I, [P, P, P]),
+        "xnb_move_particles": (I, [P, P]), "xnb_rebuild_amr": (I, [P, P]), "xnb_backup_r": (I, [P, P]), "xnb_ghost_comm_scheme": (I, [P, P]),
+        "xnb_ghost_update_all": (I, [P, P]), "xnb_ghost_update_r": (I, [P, P]), "xnb_chunk_neighbors": (I, [P, P]),
+        "xnb_zero_particle_force": (I, [P, I, P]), "xnb_lennard_jones_force": (I, [P, D, D, D, I, P]), "xnb_divide_force_by_mass": (I, [P, P]),
+        "xnb_push_f_v_r": (I, [P, D, D, P]), "xnb_push_f_v": (I, [P, D, D, P]), "xnb_particle_displ_over": (I, [P, P, P]),
+        "xnb_verlet_first_half": (I, [P, D, P]), "xnb_read_displ_over": (I, [P, P, P]), "xnb_force_and_second_half": (I, [P, D, D, D, D, P]),
+        "xnb_run_steps": (I, [P, I, D, D, D, D, P, P]), "xnb_first_iteration": (I, [P, D, D, D, P]),
+        "xnb_energy_virial": (I, [P, D, D, D, P, P, P, P]),
+        "xnb_view_chunk_neighbors": (I, [P, P, P, P]), "xnb_stream_pool_u16": (I64, [P]), "xnb_get_streams": (I, [P, P, P]),
+        "xnb_get_amr": (I64, [P, P, P]), "xnb_get_backup": (I, [P, P]), "xnb_rebuild_count": (I64, [P]), "xnb_kernel_launches": (I64, [P]),
+        "xnb_host_lattice_fcc": (I64, [C.POINTER(XnbLatticeCfg), I64] + [P] * 8),
+        "xnb_timing_enable": (I, [P, I]), "xnb_timing_read": (I, [P, P, P, P, P, I]), "xnb_measure_dfma_peak": (I, [I, P]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))   # raw address (e.g. pinned torch tensor data_ptr)
+
+
+class Context:
+    """One sub-domain on one GPU (xnb_ctx)."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.xnb_create(C.byref(h), device)
+        if rc != XNB_OK:
+            raise XnbError(rc, self.L.xnb_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.xnb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != XNB_OK:
+            raise XnbError(rc, self.L.xnb_last_error(self.h).decode())
+
+    # ---- configuration
+    def set_domain(self, bounds_min, bounds_max, cell_size, grid_dims, periodic=(1, 1, 1)):
+        a = np.asarray(bounds_min, np.float64); b = np.asarray(bounds_max, np.float64)
+        d = np.asarray(grid_dims, np.int64); p = np.asarray(periodic, np.int32)
+        self._ck(self.L.xnb_set_domain(self.h, _p(a), _p(b), float(cell_size), _p(d), _p(p)))
+
+    def init_rcb_grid(self, rank=0, nranks=1): self._ck(self.L.xnb_init_rcb_grid(self.h, rank, nranks))
+    def set_nbh_dist(self, rcut_max, rcut_inc): self._ck(self.L.xnb_set_nbh_dist(self.h, float(rcut_max), float(rcut_inc)))
+
+    def set_type_mass(self, masses):
+        m = np.ascontiguousarray(masses, np.float64)
+        self._ck(self.L.xnb_set_type_mass(self.h, _p(m), len(m)))
+
+    def set_sub_grid_density(self, d): self._ck(self.L.xnb_set_sub_grid_density(self.h, float(d)))
+
+    def nccl_unique_id(self):
+        b = np.zeros(128, np.uint8)
+        rc = self.L.xnb_nccl_unique_id(_p(b))
+        if rc != XNB_OK:
+            raise XnbError(rc, "ncclGetUniqueId failed")
+        return b
+
+    def nccl_init_rank(self, uid, rank, nranks):
+        b = np.ascontiguousarray(uid, np.uint8)
+        self._ck(self.L.xnb_nccl_init_rank(self.h, _p(b), rank, nranks))
+
+    # ---- particles
+    def set_particles(self, rx, ry, rz, vx=None, vy=None, vz=None, id=None, type=None):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float64)
+        rx, ry, rz, vx, vy, vz = map(f, (rx, ry, rz, vx, vy, vz))
+        ids = None if id is None else np.ascontiguousarray(id, np.uint64)
+        ty = None if type is None else np.ascontiguousarray(type, np.uint8)
+        self._ck(self.L.xnb_set_particles(self.h, len(rx), _p(rx), _p(ry), _p(rz), _p(vx), _p(vy), _p(vz), _p(ids), _p(ty)))
+
+    @property
+    def n_inner(self): return self.L.xnb_num_inner(self.h)
+    @property
+    def n_total(self): return self.L.xnb_num_total(self.h)
+
+    def get_particles(self, first=0, n=None, fields=("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz", "id", "type", "cell")):
+        if n is None:
+            n = self.n_total - first
+        names = ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz", "id", "type", "cell")
+        dt = dict(id=np.uint64, type=np.uint8, cell=np.uint32)
+        out = {k: np.zeros(n, dt.get(k, np.float64)) for k in names if k in fields}
+        self._ck(self.L.xnb_get_particles(self.h, first, n, *[_p(out.get(k)) for k in names]))
+        return out
+
+    def upload_rv(self, rx, ry, rz, vx, vy, vz, stream=None):
+        self._ck(self.L.xnb_upload_rv(self.h, _p(rx), _p(ry), _p(rz), _p(vx), _p(vy), _p(vz), _p(stream)))
+
+    def download_rvf(self, rx, ry, rz, vx, vy, vz, fx, fy, fz, id=None, stream=None):
+        self._ck(self.L.xnb_download_rvf(self.h, _p(rx), _p(ry), _p(rz), _p(vx), _p(vy), _p(vz), _p(fx), _p(fy), _p(fz), _p(id), _p(stream)))
+
+    def grid_info(self):
+        gi = XnbGridInfo()
+        self._ck(self.L.xnb_get_grid_info(self.h, C.byref(gi)))
+        return dict(dims=np.array(gi.dims[:]), offset=np.array(gi.offset[:]), ghost_layers=gi.ghost_layers, n_cells=gi.n_cells,
+                    block_start=np.array(gi.block_start[:]), block_end=np.array(gi.block_end[:]))
+
+    def cells(self):
+        nc = self.grid_info()["n_cells"]
+        s = np.zeros(nc, np.uint32); c = np.zeros(nc, np.uint32)
+        self._ck(self.L.xnb_get_cells(self.h, _p(s), _p(c)))
+        return s, c
+
+    # ---- operators
+    def move_particles(self, stream=None): self._ck(self.L.xnb_move_particles(self.h, _p(stream)))
+    def rebuild_amr(self, stream=None): self._ck(self.L.xnb_rebuild_amr(self.h, _p(stream)))
+    def backup_r(self, stream=None): self._ck(self.L.xnb_backup_r(self.h, _p(stream)))
+    def ghost_comm_scheme(self, stream=None): self._ck(self.L.xnb_ghost_comm_scheme(self.h, _p(stream)))
+    def ghost_update_all(self, stream=None): self._ck(self.L.xnb_ghost_update_all(self.h, _p(stream)))
+    def ghost_update_r(self, stream=None): self._ck(self.L.xnb_ghost_update_r(self.h, _p(stream)))
+    def chunk_neighbors(self, stream=None): self._ck(self.L.xnb_chunk_neighbors(self.h, _p(stream)))
+    def zero_particle_force(self, ghost=True, stream=None): self._ck(self.L.xnb_zero_particle_force(self.h, int(ghost), _p(stream)))
+    def lennard_jones_force(self, epsilon, sigma, rcut, ghost=False, stream=None):
+        self._ck(self.L.xnb_lennard_jones_force(self.h, epsilon, sigma, rcut, int(ghost), _p(stream)))
+    def divide_force_by_mass(self, stream=None): self._ck(self.L.xnb_divide_force_by_mass(self.h, _p(stream)))
+    def push_f_v_r(self, dt, dt_scale=1.0, stream=None): self._ck(self.L.xnb_push_f_v_r(self.h, dt, dt_scale, _p(stream)))
+    def push_f_v(self, dt, dt_scale=0.5, stream=None): self._ck(self.L.xnb_push_f_v(self.h, dt, dt_scale, _p(stream)))
+
+    def particle_displ_over(self, stream=None):
+        v = C.c_uint64()
+        self._ck(self.L.xnb_particle_displ_over(self.h, C.addressof(v), _p(stream)))
+        return v.value
+
+    def verlet_first_half(self, dt, stream=None): self._ck(self.L.xnb_verlet_first_half(self.h, dt, _p(stream)))
+
+    def read_displ_over(self, stream=None):
+        v = C.c_uint64()
+        self._ck(self.L.xnb_read_displ_over(self.h, C.addressof(v), _p(stream)))
+        return v.value
+
+    def force_and_second_half(self, epsilon, sigma, rcut, dt_half_kick, stream=None):
+        self._ck(self.L.xnb_force_and_second_half(self.h, epsilon, sigma, rcut, dt_half_kick, _p(stream)))
+
+    def run_steps(self, nsteps, dt, epsilon, sigma, rcut, stream=None):
+        r = C.c_int()
+        self._ck(self.L.xnb_run_steps(self.h, nsteps, dt, epsilon, sigma, rcut, _p(stream), C.addressof(r)))
+        return r.value
+
+    def first_iteration(self, epsilon, sigma, rcut, stream=None): self._ck(self.L.xnb_first_iteration(self.h, epsilon, sigma, rcut, _p(stream)))
+
+    def update_particles_full(self, stream=None):
+        """parallel_update_particles of data/config/update-particles.msp:47-53 (after move_particles)"""
+        self.rebuild_amr(stream); self.backup_r(stream); self.ghost_comm_scheme(stream); self.ghost_update_all(stream); self.chunk_neighbors(stream)
+
+    def energy_virial(self, epsilon, sigma, rcut, stream=None):
+        e = C.c_double(); k = C.c_double(); w = np.zeros(6)
+        self._ck(self.L.xnb_energy_virial(self.h, epsilon, sigma, rcut, C.addressof(e), _p(w), C.addressof(k), _p(stream)))
+        return e.value, w, k.value
+
+    # ---- derived data
+    def streams(self):
+        nc = self.grid_info()["n_cells"]
+        sz = np.zeros(nc, np.uint32)
+        self._ck(self.L.xnb_get_streams(self.h, _p(sz), None))
+        data = np.zeros(int(sz.sum()), np.uint16)
+        self._ck(self.L.xnb_get_streams(self.h, _p(sz), _p(data)))
+        return sz, data
+
+    def view_chunk_neighbors(self):
+        ps = C.c_void_p(); pb = C.c_void_p(); mx = C.c_uint32()
+        self._ck(self.L.xnb_view_chunk_neighbors(self.h, C.addressof(ps), C.addressof(pb), C.addressof(mx)))
+        return ps.value, pb.value, mx.value
+
+    def stream_pool_u16(self): return self.L.xnb_stream_pool_u16(self.h)
+
+    def amr_tables(self):
+        nc = self.grid_info()["n_cells"]
+        sgs = np.zeros(nc + 1, np.int64)
+        n = self.L.xnb_get_amr(self.h, _p(sgs), None)
+        sgc = np.zeros(max(n, 0), np.uint32)
+        if n > 0:
+            self.L.xnb_get_amr(self.h, None, _p(sgc))
+        return sgs, sgc
+
+    def backup(self):
+        b = np.zeros(3 * self.n_inner, np.uint32)
+        self._ck(self.L.xnb_get_backup(self.h, _p(b)))
+        return b
+
+    def rebuild_count(self): return self.L.xnb_rebuild_count(self.h)
+    def kernel_launches(self): return self.L.xnb_kernel_launches(self.h)
+    def timing_enable(self, on=True): self._ck(self.L.xnb_timing_enable(self.h, int(on)))
+
+    def timing_read(self, reset=True):
+        f = C.c_double(); fl = C.c_int64(); n = C.c_double(); nl = C.c_int64()
+        self._ck(self.L.xnb_timing_read(self.h, C.addressof(f), C.addressof(fl), C.addressof(n), C.addressof(nl), int(reset)))
+        return dict(force_ms=f.value, force_launches=fl.value, nbh_ms=n.value, nbh_launches=nl.value)
+
+
+def measure_dfma_peak(device=0):
+    L = load()
+    v = C.c_double()
+    rc = L.xnb_measure_dfma_peak(device, C.addressof(v))
+    if rc != XNB_OK:
+        raise XnbError(rc, "DFMA probe failed")
+    return v.value
+
+
+def lattice_fcc(bounds_max, cell_size, grid_dims, lattice_a, noise_sigma=0.0, vel_sigma=0.0, bounds_min=(0., 0., 0.),
+                n_spheres=0, sphere_rmin=0., sphere_rmax=0., drift_speed=0.):
+    """ops `lattice` + `gaussian_noise_r` (host side, deterministic): returns dict of numpy arrays in domain-cell order"""
+    L = load()
+    cfg = XnbLatticeCfg()
+    cfg.bounds_min[:] = bounds_min; cfg.bounds_max[:] = bounds_max; cfg.cell_size = cell_size; cfg.grid_dims[:] = grid_dims
+    cfg.lattice_a = lattice_a; cfg.noise_sigma = noise_sigma; cfg.vel_sigma = vel_sigma
+    cfg.n_spheres = n_spheres; cfg.sphere_rmin = sphere_rmin; cfg.sphere_rmax = sphere_rmax; cfg.drift_speed = drift_speed
+    cap = 4
+    for d in range(3):
+        cap *= int(np.ceil((bounds_max[d] - bounds_min[d]) / lattice_a)) + 1
+    out = {k: np.zeros(cap, np.float64) for k in ("rx", "ry", "rz", "vx", "vy", "vz")}
+    out["id"] = np.zeros(cap, np.uint64); out["type"] = np.zeros(cap, np.uint8)
+    n = L.xnb_host_lattice_fcc(C.byref(cfg), cap, *[_p(out[k]) for k in ("rx", "ry", "rz", "vx", "vy", "vz", "id", "type")])
+    if n < 0:
+        raise XnbError(4, "lattice capacity")
+    return {k: v[:n].copy() for k, v in out.items()}

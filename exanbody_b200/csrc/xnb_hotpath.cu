@@ -1,0 +1,1154 @@
+// xnb_hotpath.cu -- C-ABI (include/xnb_hotpath.h) and host-side orchestration of the sm_100a kernels.
+// One xnb_ctx = one sub-domain on one GPU.  No CPU compute path exists here: without a CUDA device every entry fails.
+#include "../../include/xnb_hotpath.h"
+#include "xnb_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+using namespace xnb;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// NCCL through dlsym: the library is resolved from the process (torch loads its bundled libnccl) or dlopen'ed; there is
+// no link-time dependency so the C-ABI loads on a box without NCCL/GPU.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+typedef void* ncclComm_t;
+typedef int ncclResult_t;
+enum { nccl_uint8 = 1, nccl_uint32 = 3, nccl_uint64 = 5, nccl_float64 = 8 };
+enum { nccl_sum = 0 };
+struct NcclApi
+{
+  bool loaded = false, ok = false;
+  ncclResult_t (*GetUniqueId)(void*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, /* ncclUniqueId by value: 128 bytes */ struct Id128, int) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+struct Id128 { char b[128]; };
+NcclApi g_nccl;
+
+bool nccl_load()
+{
+  if (g_nccl.loaded) return g_nccl.ok;
+  g_nccl.loaded = true;
+  void* h = RTLD_DEFAULT;
+  if (!dlsym(h, "ncclSend"))
+  {
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+  }
+#define XNB_SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) return false;
+  XNB_SYM(GetUniqueId, "ncclGetUniqueId") XNB_SYM(CommInitRank, "ncclCommInitRank") XNB_SYM(GroupStart, "ncclGroupStart")
+  XNB_SYM(GroupEnd, "ncclGroupEnd") XNB_SYM(Send, "ncclSend") XNB_SYM(Recv, "ncclRecv") XNB_SYM(AllReduce, "ncclAllReduce")
+  XNB_SYM(AllGather, "ncclAllGather") XNB_SYM(CommDestroy, "ncclCommDestroy") XNB_SYM(GetErrorString, "ncclGetErrorString")
+#undef XNB_SYM
+  g_nccl.ok = true;
+  return true;
+}
+
+std::string g_create_error;
+
+template <class T>
+struct DBuf
+{
+  T* p = nullptr; size_t cap = 0;
+  ~DBuf() { if (p) cudaFree(p); }
+  // grow to hold n elements; keep: preserve the first `keep` elements
+  cudaError_t ensure(size_t n, size_t keep = 0, double slack = 1.0)
+  {
+    if (n <= cap) return cudaSuccess;
+    size_t ncap = (size_t)((double)n * slack) + 16;
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (p && keep) { e = cudaMemcpy(q, p, std::min(keep, cap) * sizeof(T), cudaMemcpyDeviceToDevice); if (e != cudaSuccess) { cudaFree(q); return e; } }
+    if (p) cudaFree(p);
+    p = q; cap = ncap;
+    return cudaSuccess;
+  }
+};
+
+struct Block { int64_t s[3], e[3]; };
+
+// reference src/core/lib/simple_block_rcb.cpp:27-59 : recursive bisection, longest axis first (ties: i, then j)
+Block simple_block_rcb(Block b, size_t n_parts, size_t part)
+{
+  while (n_parts > 1)
+  {
+    const size_t pivot = n_parts / 2;
+    const bool side = part >= pivot;
+    const int64_t d[3] = {b.e[0] - b.s[0], b.e[1] - b.s[1], b.e[2] - b.s[2]};
+    int ax = 2;
+    if (d[0] >= d[1] && d[0] >= d[2]) ax = 0; else if (d[1] >= d[0] && d[1] >= d[2]) ax = 1;
+    if (side) b.s[ax] = b.s[ax] + d[ax] / 2; else b.e[ax] = b.s[ax] + d[ax] / 2;
+    if (side) { part -= pivot; n_parts -= pivot; } else n_parts = pivot;
+  }
+  return b;
+}
+
+struct HostItem { uint32_t src_cell, dst_cell, flags; };
+
+} // namespace
+
+struct xnb_ctx
+{
+  int device = 0;
+  std::string err;
+  // ---- Domain / decomposition
+  double dmin[3] = {0, 0, 0}, dmax[3] = {0, 0, 0}, cs = 0;
+  int64_t ddims[3] = {0, 0, 0};
+  int periodic[3] = {1, 1, 1};
+  bool have_domain = false, have_block = false, have_dist = false, grid_ready = false;
+  int rank = 0, nranks = 1;
+  std::vector<Block> blocks;
+  double rcut_max = 0, rcut_inc = 0, nbh_dist = 0, max_displ = 0, ghost_dist = 0;
+  double sub_grid_density = 6.5;
+  GridP g{};
+  // ---- particles (double buffered SoA)
+  DBuf<double> f64[2][9];
+  DBuf<unsigned long long> idb[2];
+  DBuf<uint8_t> typeb[2];
+  int cur = 0;
+  int64_t n_inner = 0, n_total = 0;
+  DBuf<uint32_t> atom_cell[2]; int cur_ac = 0;
+  DBuf<uint32_t> key, rnk, perm, perm2, leave_list;
+  DBuf<uint32_t> cell_start, cell_count;
+  DBuf<uint32_t> backup;
+  DBuf<double> mass; int n_types = 0;
+  // ---- AMR
+  DBuf<uint8_t> side_lut;
+  DBuf<uint32_t> sg_size; DBuf<unsigned long long> sub_grid_start; DBuf<uint32_t> sub_grid_cells;
+  int64_t n_sub_grid_cells = 0; uint32_t max_side = 1;
+  // ---- ghosts
+  std::vector<int> send_first, recv_first;            // per partner rank [nranks+1] ranges into the item arrays
+  int n_send_items = 0, n_recv_items = 0;
+  DBuf<uint32_t> it_src_cell, it_flags, it_partner, it_count, it_offset;
+  DBuf<double> it_outer;
+  DBuf<uint32_t> rc_dst_cell, rc_count, rc_offset;
+  DBuf<uint32_t> send_src; DBuf<uint16_t> send_flags;
+  DBuf<double> stage; DBuf<uint8_t> stage_type;
+  std::vector<uint32_t> h_send_base, h_recv_base;      // per partner particle offsets [nranks+1]
+  int64_t n_send = 0, n_ghost = 0;
+  // ---- neighbours
+  DBuf<uint32_t> nb_len, nb_cnt, nb_off, stream_size, stream_size_padded, cell_stream_bytes;
+  DBuf<unsigned long long> stream_off;
+  DBuf<uint16_t> pool; DBuf<uint16_t*> cell_stream;
+  int64_t pool_used = 0; uint32_t max_neighbors = 0; bool have_nbh = false;
+  // ---- misc device scalars
+  DBuf<unsigned long long> scan_tmp64; DBuf<uint32_t> scan_tmp32;
+  DBuf<unsigned long long> d_scalars64;   // [0] displacement counter, [1] scan total
+  DBuf<uint32_t> d_scalars32;             // [0] error word, [1] leave_count, [2] max_side, [3] max_nbh, [4] scan total, [8..8+64) migrate counts
+  DBuf<double> ev_partials;
+  DBuf<int> d_blocks;
+  DBuf<uint32_t> mig_rank, mig_pos, mig_base;
+  void* h_pinned = nullptr;               // 4 KB pinned scratch for small read-backs
+  // ---- NCCL
+  ncclComm_t comm = nullptr; bool own_comm = false;
+  // ---- counters
+  int64_t launches = 0, rebuilds = 0;
+  bool timing = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double force_ms = 0, nbh_ms = 0; int64_t force_launches = 0, nbh_launches = 0;
+
+  int fail(int code, const std::string& m) { err = m; return code; }
+  ParticlesP P(int which)
+  {
+    ParticlesP p;
+    p.rx = f64[which][0].p; p.ry = f64[which][1].p; p.rz = f64[which][2].p;
+    p.vx = f64[which][3].p; p.vy = f64[which][4].p; p.vz = f64[which][5].p;
+    p.fx = f64[which][6].p; p.fy = f64[which][7].p; p.fz = f64[which][8].p;
+    p.id = idb[which].p; p.type = typeb[which].p;
+    return p;
+  }
+};
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return c->fail(XNB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+#define NK(call) do { ncclResult_t r__ = (call); if (r__ != 0) return c->fail(XNB_ERR_NCCL, std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error")); } while (0)
+#define LAUNCH(kernel, grid, block, stream, ...) do { kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); c->launches++; CK(cudaGetLastError()); } while (0)
+static inline unsigned nblk(int64_t n, int b) { return (unsigned)std::max<int64_t>((n + b - 1) / b, 1); }
+
+namespace {
+
+// exclusive scan of n elements; `total` (device pointer, may be null) receives the grand total
+template <class TIn, class T>
+int scan_exclusive(xnb_ctx* c, const TIn* in, T* out, size_t n, T* d_total, DBuf<T>& tmp, cudaStream_t st)
+{
+  const size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  CK(tmp.ensure(std::max<size_t>(tiles, 1)));
+  if (n == 0) { if (d_total) CK(cudaMemsetAsync(d_total, 0, sizeof(T), st)); return 0; }
+  LAUNCH((k_scan_tiles<TIn, T>), (unsigned)tiles, SCAN_BLOCK, st, in, out, tmp.p, n);
+  LAUNCH((k_scan_sums<T>), 1, SCAN_BLOCK, st, tmp.p, tiles, d_total);
+  LAUNCH((k_scan_add<T>), (unsigned)tiles, SCAN_BLOCK, st, out, tmp.p, n);
+  return 0;
+}
+
+int ensure_particle_capacity(xnb_ctx* c, size_t n, size_t keep)
+{
+  for (int w = 0; w < 2; w++)
+  {
+    const size_t k = (w == c->cur) ? keep : 0;
+    for (int f = 0; f < 9; f++) CK(c->f64[w][f].ensure(n, k, 1.1));
+    CK(c->idb[w].ensure(n, k, 1.1));
+    CK(c->typeb[w].ensure(n, k, 1.1));
+    CK(c->atom_cell[w].ensure(n, (w == c->cur_ac) ? keep : 0, 1.1));
+  }
+  return 0;
+}
+
+// enumerate the ghost send items of rank `from` towards rank `to`, in the reference's order
+// (update_ghosts_comm_scheme.cpp:168-196 shift loops k,j,i ; :429-443 cell loop k,j,i and ghost-shell membership)
+void enumerate_sends(const xnb_ctx* c, int from, int to, int gl, std::vector<HostItem>& out)
+{
+  const Block& bf = c->blocks[(size_t)from];
+  const Block& bt = c->blocks[(size_t)to];
+  int64_t gs[3], ge[3], tdims[3], fdims[3], foff[3];
+  for (int d = 0; d < 3; d++) { gs[d] = bt.s[d] - gl; ge[d] = bt.e[d] + gl; tdims[d] = ge[d] - gs[d]; fdims[d] = bf.e[d] - bf.s[d] + 2 * gl; foff[d] = bf.s[d] - gl; }
+  const int lo[3] = {c->periodic[0] ? -1 : 0, c->periodic[1] ? -1 : 0, c->periodic[2] ? -1 : 0};
+  const int hi[3] = {c->periodic[0] ? 1 : 0, c->periodic[1] ? 1 : 0, c->periodic[2] ? 1 : 0};
+  for (int sk = lo[2]; sk <= hi[2]; sk++) for (int sj = lo[1]; sj <= hi[1]; sj++) for (int si = lo[0]; si <= hi[0]; si++)
+  {
+    if (si == 0 && sj == 0 && sk == 0 && from == to) continue;
+    const int sh[3] = {si, sj, sk};
+    uint32_t flags = 0;
+    if (si == -1) flags |= GB_SHIFT_X; if (si == 1) flags |= GB_SHIFT_X | GB_SIDE_X;
+    if (sj == -1) flags |= GB_SHIFT_Y; if (sj == 1) flags |= GB_SHIFT_Y | GB_SIDE_Y;
+    if (sk == -1) flags |= GB_SHIFT_Z; if (sk == 1) flags |= GB_SHIFT_Z | GB_SIDE_Z;
+    int64_t a[3], b[3];
+    bool empty = false;
+    for (int d = 0; d < 3; d++)
+    {
+      const int64_t s = (int64_t)sh[d] * c->ddims[d];
+      a[d] = std::max(bf.s[d], gs[d] - s); b[d] = std::min(bf.e[d], ge[d] - s);
+      if (a[d] >= b[d]) empty = true;
+    }
+    if (empty) continue;
+    for (int64_t k = a[2]; k < b[2]; k++) for (int64_t j = a[1]; j < b[1]; j++) for (int64_t i = a[0]; i < b[0]; i++)
+    {
+      const int64_t dl[3] = {i, j, k};
+      int64_t t[3];
+      bool inside_inner = true;
+      for (int d = 0; d < 3; d++) { t[d] = dl[d] + (int64_t)sh[d] * c->ddims[d]; if (t[d] < bt.s[d] || t[d] >= bt.e[d]) inside_inner = false; }
+      if (inside_inner) continue;   // can only happen for degenerate tiny domains
+      HostItem it;
+      it.src_cell = (uint32_t)(((k - foff[2]) * fdims[1] + (j - foff[1])) * fdims[0] + (i - foff[0]));
+      it.dst_cell = (uint32_t)(((t[2] - gs[2]) * tdims[1] + (t[1] - gs[1])) * tdims[0] + (t[0] - gs[0]));
+      it.flags = flags;
+      out.push_back(it);
+    }
+  }
+}
+
+// builds GridP, the AMR side table and the static ghost item lists once domain, block and distances are known
+int ensure_grid(xnb_ctx* c)
+{
+  if (c->grid_ready) return 0;
+  if (!c->have_domain) return c->fail(XNB_ERR_INVALID, "xnb_set_domain has not been called");
+  if (!c->have_dist) return c->fail(XNB_ERR_INVALID, "xnb_set_nbh_dist has not been called");
+  if (!c->have_block)
+  {
+    c->rank = 0; c->nranks = 1; c->blocks.assign(1, Block{{0, 0, 0}, {c->ddims[0], c->ddims[1], c->ddims[2]}}); c->have_block = true;
+  }
+  GridP& g = c->g;
+  const int gl = (int)std::ceil(c->ghost_dist / c->cs);          // grid.h:110
+  const int gap = (int)std::ceil(c->nbh_dist / c->cs);           // amr_grid_algorithm.h:451
+  if (gap > 15) return c->fail(XNB_ERR_CAPACITY, "neighbour cell offset beyond +-15 cells (chunk_neighbors.h:140-142)");
+  const Block& b = c->blocks[(size_t)c->rank];
+  int64_t ncell = 1;
+  for (int d = 0; d < 3; d++)
+  {
+    g.org[d] = c->dmin[d]; g.dmin[d] = c->dmin[d]; g.dmax[d] = c->dmax[d];
+    g.dims[d] = (int)(b.e[d] - b.s[d] + 2 * gl); g.off[d] = (int)(b.s[d] - gl);
+    g.ddims[d] = (int)c->ddims[d]; g.bstart[d] = (int)b.s[d]; g.bend[d] = (int)b.e[d]; g.periodic[d] = c->periodic[d];
+    ncell *= g.dims[d];
+    if (c->periodic[d] && c->ddims[d] < 2 * gl) return c->fail(XNB_ERR_INVALID, "periodic domain thinner than two ghost layers is not supported");
+  }
+  if (ncell > 0x7fffffff) return c->fail(XNB_ERR_CAPACITY, "too many cells");
+  g.cs = c->cs; g.gl = gl; g.n_cells = (int)ncell;
+  CK(c->cell_start.ensure((size_t)ncell)); CK(c->cell_count.ensure((size_t)ncell));
+  CK(c->d_scalars64.ensure(8)); CK(c->d_scalars32.ensure(128));
+  CK(cudaMemset(c->d_scalars64.p, 0, 8 * 8)); CK(cudaMemset(c->d_scalars32.p, 0, 128 * 4));
+  CK(cudaMemset(c->cell_count.p, 0, (size_t)ncell * 4)); CK(cudaMemset(c->cell_start.p, 0, (size_t)ncell * 4));
+  if (!c->h_pinned) CK(cudaMallocHost(&c->h_pinned, 4096));
+  // sub_grid_size(n, density) table (amr_grid_algorithm.h:66-78), computed on the host with std::cbrt like the reference
+  {
+    std::vector<uint8_t> lut(65536);
+    for (size_t n = 0; n < 65536; n++)
+    {
+      size_t side = 0;
+      if (n > 0) { const double s = std::cbrt((double)n / c->sub_grid_density); side = (s < 2.0) ? 1 : std::min((size_t)std::floor(s), (size_t)16); }
+      lut[n] = (uint8_t)side;
+    }
+    CK(c->side_lut.ensure(65536));
+    CK(cudaMemcpy(c->side_lut.p, lut.data(), 65536, cudaMemcpyHostToDevice));
+  }
+  // decomposition table for migration
+  {
+    std::vector<int> hb((size_t)c->nranks * 6);
+    for (int r = 0; r < c->nranks; r++) for (int d = 0; d < 3; d++) { hb[(size_t)r * 6 + d] = (int)c->blocks[(size_t)r].s[d]; hb[(size_t)r * 6 + 3 + d] = (int)c->blocks[(size_t)r].e[d]; }
+    CK(c->d_blocks.ensure(hb.size()));
+    CK(cudaMemcpy(c->d_blocks.p, hb.data(), hb.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  // static ghost items
+  {
+    std::vector<uint32_t> s_src, s_flags, s_partner, r_dst;
+    std::vector<double> outer((size_t)c->nranks * 6);
+    c->send_first.assign((size_t)c->nranks + 1, 0); c->recv_first.assign((size_t)c->nranks + 1, 0);
+    for (int p = 0; p < c->nranks; p++)
+    {
+      const Block& bp = c->blocks[(size_t)p];
+      for (int d = 0; d < 3; d++)
+      {
+        // block_to_bounds then enlarge by Grid::max_neighbor_distance (update_ghosts_comm_scheme.cpp:405-406)
+        outer[(size_t)p * 6 + d] = (c->dmin[d] + (double)bp.s[d] * c->cs) - c->ghost_dist;
+        outer[(size_t)p * 6 + 3 + d] = (c->dmin[d] + (double)bp.e[d] * c->cs) + c->ghost_dist;
+      }
+      std::vector<HostItem> snd, rcv;
+      enumerate_sends(c, c->rank, p, gl, snd);
+      enumerate_sends(c, p, c->rank, gl, rcv);
+      c->send_first[(size_t)p] = (int)s_src.size(); c->recv_first[(size_t)p] = (int)r_dst.size();
+      for (const HostItem& it : snd) { s_src.push_back(it.src_cell); s_flags.push_back(it.flags); s_partner.push_back((uint32_t)p); }
+      for (const HostItem& it : rcv) r_dst.push_back(it.dst_cell);
+    }
+    c->send_first[(size_t)c->nranks] = (int)s_src.size(); c->recv_first[(size_t)c->nranks] = (int)r_dst.size();
+    c->n_send_items = (int)s_src.size(); c->n_recv_items = (int)r_dst.size();
+    const size_t ns = std::max<size_t>(s_src.size(), 1), nr = std::max<size_t>(r_dst.size(), 1);
+    CK(c->it_src_cell.ensure(ns)); CK(c->it_flags.ensure(ns)); CK(c->it_partner.ensure(ns)); CK(c->it_count.ensure(ns + 1)); CK(c->it_offset.ensure(ns + 1));
+    CK(c->rc_dst_cell.ensure(nr)); CK(c->rc_count.ensure(nr + 1)); CK(c->rc_offset.ensure(nr + 1));
+    CK(c->it_outer.ensure(outer.size()));
+    if (!s_src.empty())
+    {
+      CK(cudaMemcpy(c->it_src_cell.p, s_src.data(), s_src.size() * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(c->it_flags.p, s_flags.data(), s_flags.size() * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(c->it_partner.p, s_partner.data(), s_partner.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (!r_dst.empty()) CK(cudaMemcpy(c->rc_dst_cell.p, r_dst.data(), r_dst.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->it_outer.p, outer.data(), outer.size() * 8, cudaMemcpyHostToDevice));
+    c->h_send_base.assign((size_t)c->nranks + 1, 0); c->h_recv_base.assign((size_t)c->nranks + 1, 0);
+  }
+  c->grid_ready = true;
+  return 0;
+}
+
+int check_device_errors(xnb_ctx* c, cudaStream_t st)
+{
+  uint32_t* h = (uint32_t*)c->h_pinned;
+  CK(cudaMemcpyAsync(h, c->d_scalars32.p, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint32_t e = h[0];
+  if (!e) return 0;
+  CK(cudaMemsetAsync(c->d_scalars32.p, 0, 4, st));
+  if (e & DERR_LOST_PARTICLE) return c->fail(XNB_ERR_LOST_PARTICLE, "a particle left a non periodic domain (reference: stays in otb_particles)");
+  if (e & DERR_CELL_OVERFLOW) return c->fail(XNB_ERR_CAPACITY, "more than 65535 particles in a cell (u16 stream index, chunk_neighbors_execute.h:229)");
+  if (e & DERR_GROUP_OVERFLOW) return c->fail(XNB_ERR_CAPACITY, "u16 counter overflow in a neighbour stream (chunk_neighbors_execute.h:362,369)");
+  if (e & DERR_SORT_CAPACITY) return c->fail(XNB_ERR_CAPACITY, "more than 2048 particles in a cell: in-cell sort capacity exceeded");
+  if (e & DERR_ID_RANGE) return c->fail(XNB_ERR_CAPACITY, "particle id >= 2^52");
+  return c->fail(XNB_ERR_INVALID, "device error word " + std::to_string(e));
+}
+
+// small synchronous read-back through the pinned scratch page
+template <class T>
+int read_back(xnb_ctx* c, const T* d, size_t n, T* out, cudaStream_t st)
+{
+  CK(cudaMemcpyAsync(c->h_pinned, d, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(out, c->h_pinned, n * sizeof(T));
+  return 0;
+}
+
+int require_binned(xnb_ctx* c)
+{
+  int rc = ensure_grid(c);
+  if (rc) return rc;
+  return 0;
+}
+
+} // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+const char* xnb_version(void) { return "exanbody_b200 hot path 0.1 (sm_100a)"; }
+
+const char* xnb_last_error(const xnb_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int xnb_create(xnb_ctx** out, int device)
+{
+  if (!out) return XNB_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) { g_create_error = "no CUDA device: the exaNBody B200 hot path has no CPU fallback"; return XNB_ERR_NO_DEVICE; }
+  if (device < 0 || device >= ndev) { g_create_error = "invalid CUDA device index"; return XNB_ERR_INVALID; }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return XNB_ERR_CUDA; }
+  xnb_ctx* c = new xnb_ctx();
+  c->device = device;
+  double one = 1.0;
+  if (c->mass.ensure(256) != cudaSuccess) { g_create_error = "cudaMalloc failed"; delete c; return XNB_ERR_CUDA; }
+  std::vector<double> m(256, one);
+  cudaMemcpy(c->mass.p, m.data(), 256 * 8, cudaMemcpyHostToDevice);
+  c->n_types = 256;
+  *out = c;
+  return XNB_OK;
+}
+
+void xnb_destroy(xnb_ctx* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->comm && c->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  delete c;
+}
+
+int xnb_set_domain(xnb_ctx* c, const double bmin[3], const double bmax[3], double cell_size, const int64_t grid_dims[3], const int32_t periodic[3])
+{
+  if (!c) return XNB_ERR_INVALID;
+  if (!(cell_size > 0)) return c->fail(XNB_ERR_INVALID, "cell_size must be > 0");
+  for (int d = 0; d < 3; d++)
+  {
+    c->dmin[d] = bmin[d]; c->dmax[d] = bmax[d]; c->ddims[d] = grid_dims[d]; c->periodic[d] = periodic[d] ? 1 : 0;
+    if (grid_dims[d] <= 0) return c->fail(XNB_ERR_INVALID, "grid_dims must be > 0");
+    // check_domain (src/core/lib/domain.cpp:82-84): bounds must match grid_dims*cell_size
+    if (std::fabs(1.0 - ((double)grid_dims[d] * cell_size) / (bmax[d] - bmin[d])) > 1e-12) return c->fail(XNB_ERR_INVALID, "domain bounds do not match grid_dims*cell_size");
+  }
+  c->cs = cell_size; c->have_domain = true; c->grid_ready = false;
+  return XNB_OK;
+}
+
+int xnb_init_rcb_grid(xnb_ctx* c, int rank, int nranks)
+{
+  if (!c) return XNB_ERR_INVALID;
+  if (!c->have_domain) return c->fail(XNB_ERR_INVALID, "xnb_set_domain first");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return c->fail(XNB_ERR_INVALID, "bad rank/nranks");
+  c->rank = rank; c->nranks = nranks;
+  c->blocks.resize((size_t)nranks);
+  const Block whole{{0, 0, 0}, {c->ddims[0], c->ddims[1], c->ddims[2]}};
+  for (int r = 0; r < nranks; r++) c->blocks[(size_t)r] = simple_block_rcb(whole, (size_t)nranks, (size_t)r);
+  c->have_block = true; c->grid_ready = false;
+  return XNB_OK;
+}
+
+int xnb_set_nbh_dist(xnb_ctx* c, double rcut_max, double rcut_inc)
+{
+  if (!c) return XNB_ERR_INVALID;
+  c->rcut_max = rcut_max; c->rcut_inc = rcut_inc;
+  c->nbh_dist = rcut_max + rcut_inc;          // nbh_dist.cpp:47
+  c->max_displ = rcut_inc / 2.0;              // :48
+  c->ghost_dist = rcut_max + rcut_inc;        // :60-62 with ghost_dist_max = rcut_max, no bonds
+  c->have_dist = true; c->grid_ready = false;
+  return XNB_OK;
+}
+
+int xnb_set_type_mass(xnb_ctx* c, const double* m, int n)
+{
+  if (!c || !m || n < 1 || n > 256) return XNB_ERR_INVALID;
+  CK(cudaMemcpy(c->mass.p, m, (size_t)n * 8, cudaMemcpyHostToDevice));
+  c->n_types = n;
+  return XNB_OK;
+}
+
+int xnb_set_sub_grid_density(xnb_ctx* c, double d) { if (!c || !(d > 0)) return XNB_ERR_INVALID; c->sub_grid_density = d; c->grid_ready = false; return XNB_OK; }
+
+int xnb_set_nccl_comm(xnb_ctx* c, void* comm)
+{
+  if (!c) return XNB_ERR_INVALID;
+  if (comm && !nccl_load()) return c->fail(XNB_ERR_NCCL, "NCCL library not found");
+  c->comm = comm; c->own_comm = false;
+  return XNB_OK;
+}
+
+int xnb_nccl_unique_id(uint8_t id[128])
+{
+  if (!nccl_load()) return XNB_ERR_NCCL;
+  return g_nccl.GetUniqueId(id) == 0 ? XNB_OK : XNB_ERR_NCCL;
+}
+
+int xnb_nccl_init_rank(xnb_ctx* c, const uint8_t id[128], int rank, int nranks)
+{
+  if (!c) return XNB_ERR_INVALID;
+  if (!nccl_load()) return c->fail(XNB_ERR_NCCL, "NCCL library not found");
+  CK(cudaSetDevice(c->device));
+  Id128 u; memcpy(u.b, id, 128);
+  NK(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
+  c->own_comm = true;
+  return XNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int xnb_set_particles(xnb_ctx* c, int64_t n, const double* rx, const double* ry, const double* rz,
+                      const double* vx, const double* vy, const double* vz, const uint64_t* id, const uint8_t* type)
+{
+  if (!c || n < 0 || (n > 0 && (!rx || !ry || !rz))) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_grid(c); if (rc) return rc;
+  const Block& b = c->blocks[(size_t)c->rank];
+  // keep the particles whose (periodically wrapped) cell lies in my block, as each rank's `lattice` does
+  std::vector<int64_t> keep; keep.reserve((size_t)n);
+  for (int64_t i = 0; i < n; i++)
+  {
+    const double r[3] = {rx[i], ry[i], rz[i]};
+    bool mine = true;
+    for (int d = 0; d < 3 && mine; d++)
+    {
+      int64_t loc = (int64_t)std::floor((r[d] - c->dmin[d]) / c->cs);
+      if (c->periodic[d]) loc = ((loc % c->ddims[d]) + c->ddims[d]) % c->ddims[d];
+      if (loc < b.s[d] || loc >= b.e[d]) mine = false;
+    }
+    if (mine || c->nranks == 1) keep.push_back(i);
+  }
+  const size_t m = keep.size();
+  rc = ensure_particle_capacity(c, std::max<size_t>((size_t)((double)m * 1.6), 1024), 0); if (rc) return rc;
+  std::vector<double> tmp(m);
+  const double* src[9] = {rx, ry, rz, vx, vy, vz, nullptr, nullptr, nullptr};
+  for (int f = 0; f < 9; f++)
+  {
+    for (size_t k = 0; k < m; k++) tmp[k] = src[f] ? src[f][keep[k]] : 0.0;
+    if (m) CK(cudaMemcpy(c->f64[c->cur][f].p, tmp.data(), m * 8, cudaMemcpyHostToDevice));
+  }
+  std::vector<unsigned long long> ids(m); std::vector<uint8_t> ty(m);
+  for (size_t k = 0; k < m; k++) { ids[k] = id ? id[keep[k]] : (unsigned long long)keep[k]; ty[k] = type ? type[keep[k]] : 0; }
+  if (m) { CK(cudaMemcpy(c->idb[c->cur].p, ids.data(), m * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(c->typeb[c->cur].p, ty.data(), m, cudaMemcpyHostToDevice)); }
+  c->n_inner = (int64_t)m; c->n_total = (int64_t)m; c->have_nbh = false; c->n_ghost = 0;
+  return XNB_OK;
+}
+
+int64_t xnb_num_inner(const xnb_ctx* c) { return c ? c->n_inner : 0; }
+int64_t xnb_num_total(const xnb_ctx* c) { return c ? c->n_total : 0; }
+
+int xnb_get_particles(xnb_ctx* c, int64_t first, int64_t n, double* rx, double* ry, double* rz, double* vx, double* vy, double* vz,
+                      double* fx, double* fy, double* fz, uint64_t* id, uint8_t* type, uint32_t* cell)
+{
+  if (!c || first < 0 || n < 0 || first + n > c->n_total) return c ? c->fail(XNB_ERR_INVALID, "range out of bounds") : XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  double* dst[9] = {rx, ry, rz, vx, vy, vz, fx, fy, fz};
+  for (int f = 0; f < 9; f++) if (dst[f] && n) CK(cudaMemcpy(dst[f], c->f64[c->cur][f].p + first, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  if (id && n) CK(cudaMemcpy(id, c->idb[c->cur].p + first, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  if (type && n) CK(cudaMemcpy(type, c->typeb[c->cur].p + first, (size_t)n, cudaMemcpyDeviceToHost));
+  if (cell && n) CK(cudaMemcpy(cell, c->atom_cell[c->cur_ac].p + first, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return XNB_OK;
+}
+
+int xnb_upload_rv(xnb_ctx* c, const double* rx, const double* ry, const double* rz, const double* vx, const double* vy, const double* vz, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const double* src[6] = {rx, ry, rz, vx, vy, vz};
+  for (int f = 0; f < 6; f++) if (src[f] && c->n_inner) CK(cudaMemcpyAsync(c->f64[c->cur][f].p, src[f], (size_t)c->n_inner * 8, cudaMemcpyHostToDevice, st));
+  return XNB_OK;
+}
+
+int xnb_download_rvf(xnb_ctx* c, double* rx, double* ry, double* rz, double* vx, double* vy, double* vz, double* fx, double* fy, double* fz, uint64_t* id, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* dst[9] = {rx, ry, rz, vx, vy, vz, fx, fy, fz};
+  for (int f = 0; f < 9; f++) if (dst[f] && c->n_inner) CK(cudaMemcpyAsync(dst[f], c->f64[c->cur][f].p, (size_t)c->n_inner * 8, cudaMemcpyDeviceToHost, st));
+  if (id && c->n_inner) CK(cudaMemcpyAsync(id, c->idb[c->cur].p, (size_t)c->n_inner * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return XNB_OK;
+}
+
+int xnb_get_grid_info(const xnb_ctx* cc, xnb_grid_info* out)
+{
+  xnb_ctx* c = const_cast<xnb_ctx*>(cc);
+  if (!c || !out) return XNB_ERR_INVALID;
+  int rc = ensure_grid(c); if (rc) return rc;
+  for (int d = 0; d < 3; d++) { out->dims[d] = c->g.dims[d]; out->offset[d] = c->g.off[d]; out->block_start[d] = c->g.bstart[d]; out->block_end[d] = c->g.bend[d]; }
+  out->ghost_layers = c->g.gl; out->n_cells = c->g.n_cells;
+  return XNB_OK;
+}
+
+int xnb_get_cells(xnb_ctx* c, uint32_t* cell_start, uint32_t* cell_count)
+{
+  if (!c) return XNB_ERR_INVALID;
+  int rc = ensure_grid(c); if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  if (cell_start) CK(cudaMemcpy(cell_start, c->cell_start.p, (size_t)c->g.n_cells * 4, cudaMemcpyDeviceToHost));
+  if (cell_count) CK(cudaMemcpy(cell_count, c->cell_count.p, (size_t)c->g.n_cells * 4, cudaMemcpyDeviceToHost));
+  return XNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// move_particles (+ migrate for nranks > 1)
+// ---------------------------------------------------------------------------------------------------------------------
+int xnb_move_particles(xnb_ctx* c, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_grid(c); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridP& g = c->g;
+  int64_t n = c->n_inner;
+  uint32_t* s32 = c->d_scalars32.p;
+  CK(c->key.ensure((size_t)n + 16, 0, 1.2)); CK(c->rnk.ensure((size_t)n + 16, 0, 1.2)); CK(c->leave_list.ensure((size_t)n + 16, 0, 1.2));
+  CK(cudaMemsetAsync(c->cell_count.p, 0, (size_t)g.n_cells * 4, st));
+  CK(cudaMemsetAsync(s32 + 1, 0, 4, st));
+  ParticlesP A = c->P(c->cur);
+  if (n) LAUNCH(k_bin_locate, nblk(n, 256), 256, st, g, (int)n, A.rx, A.ry, A.rz, c->key.p, c->rnk.p, c->cell_count.p, c->leave_list.p, s32 + 1, s32);
+  int64_t n_src = n;        // entries of the source arrays (stayers + holes + arrivals)
+  int64_t n_leave = 0, n_arrive = 0;
+  if (c->nranks > 1)
+  {
+    if (!c->comm) return c->fail(XNB_ERR_NCCL, "nranks > 1 needs an NCCL communicator (xnb_nccl_init_rank)");
+    uint32_t hl = 0;
+    rc = read_back(c, s32 + 1, 1, &hl, st); if (rc) return rc;
+    n_leave = hl;
+    // destination ranks and per-destination counts
+    uint32_t* d_cnt = s32 + 8;
+    CK(cudaMemsetAsync(d_cnt, 0, 64 * 4, st));
+    CK(c->mig_rank.ensure((size_t)n_leave + 16)); CK(c->mig_pos.ensure((size_t)n_leave + 16)); CK(c->mig_base.ensure(64));
+    if (c->nranks > 64) return c->fail(XNB_ERR_INVALID, "more than 64 ranks not supported");
+    if (n_leave) LAUNCH(k_migrate_dest, nblk(n_leave, 128), 128, st, g, (int)n_leave, c->leave_list.p, A.rx, A.ry, A.rz, c->d_blocks.p, c->nranks,
+                        c->mig_rank.p, c->mig_pos.p, d_cnt, s32);
+    // all ranks learn the full count matrix
+    DBuf<uint32_t>& mat = c->scan_tmp32;
+    CK(mat.ensure((size_t)c->nranks * 64 + 64));
+    NK(g_nccl.AllGather(d_cnt, mat.p, 64, nccl_uint32, c->comm, st));
+    std::vector<uint32_t> hmat((size_t)c->nranks * 64);
+    CK(cudaMemcpyAsync(hmat.data(), mat.p, hmat.size() * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<uint32_t> sbase((size_t)c->nranks + 1, 0), rbase((size_t)c->nranks + 1, 0);
+    for (int p = 0; p < c->nranks; p++) { sbase[(size_t)p + 1] = sbase[(size_t)p] + hmat[(size_t)c->rank * 64 + p]; rbase[(size_t)p + 1] = rbase[(size_t)p] + hmat[(size_t)p * 64 + c->rank]; }
+    n_arrive = rbase[(size_t)c->nranks];
+    if ((int64_t)sbase[(size_t)c->nranks] != n_leave) return c->fail(XNB_ERR_LOST_PARTICLE, "migration: particles without owner");
+    CK(cudaMemcpyAsync(c->mig_base.p, sbase.data(), (size_t)c->nranks * 4, cudaMemcpyHostToDevice, st));
+    CK(c->stage.ensure((size_t)n_leave * 10 + 16, 0, 1.5)); CK(c->stage_type.ensure((size_t)n_leave + 16, 0, 1.5));
+    if (n_leave) LAUNCH(k_migrate_pack, nblk(n_leave, 128), 128, st, (int)n_leave, c->leave_list.p, c->mig_rank.p, c->mig_pos.p, c->mig_base.p, A, c->stage.p, c->stage_type.p);
+    rc = ensure_particle_capacity(c, (size_t)(n + n_arrive), (size_t)n); if (rc) return rc;
+    A = c->P(c->cur);
+    CK(c->key.ensure((size_t)(n + n_arrive) + 16, (size_t)n, 1.2)); CK(c->rnk.ensure((size_t)(n + n_arrive) + 16, (size_t)n, 1.2));
+    NK(g_nccl.GroupStart());
+    for (int p = 0; p < c->nranks; p++)
+    {
+      const size_t ns = sbase[(size_t)p + 1] - sbase[(size_t)p], nr = rbase[(size_t)p + 1] - rbase[(size_t)p];
+      if (p == c->rank) continue;
+      if (ns)
+      {
+        for (int f = 0; f < 9; f++) NK(g_nccl.Send(c->stage.p + (size_t)f * n_leave + sbase[(size_t)p], ns, nccl_float64, p, c->comm, st));
+        NK(g_nccl.Send(c->stage.p + (size_t)9 * n_leave + sbase[(size_t)p], ns, nccl_uint64, p, c->comm, st));
+        NK(g_nccl.Send(c->stage_type.p + sbase[(size_t)p], ns, nccl_uint8, p, c->comm, st));
+      }
+      if (nr)
+      {
+        for (int f = 0; f < 9; f++) NK(g_nccl.Recv(c->f64[c->cur][f].p + n + rbase[(size_t)p], nr, nccl_float64, p, c->comm, st));
+        NK(g_nccl.Recv(c->idb[c->cur].p + n + rbase[(size_t)p], nr, nccl_uint64, p, c->comm, st));
+        NK(g_nccl.Recv(c->typeb[c->cur].p + n + rbase[(size_t)p], nr, nccl_uint8, p, c->comm, st));
+      }
+    }
+    NK(g_nccl.GroupEnd());
+    // locate the arrivals (they are inside my block by construction)
+    if (n_arrive) LAUNCH(k_bin_locate, nblk(n_arrive, 256), 256, st, g, (int)n_arrive, A.rx + n, A.ry + n, A.rz + n, c->key.p + n, c->rnk.p + n, c->cell_count.p,
+                         (uint32_t*)nullptr, s32 + 1, s32);
+    n_src = n + n_arrive;
+  }
+  const int64_t n_new = n - n_leave + n_arrive;
+  CK(c->perm.ensure((size_t)n_src + 16, 0, 1.2)); CK(c->perm2.ensure((size_t)n_src + 16, 0, 1.2));
+  rc = scan_exclusive<uint32_t, uint32_t>(c, c->cell_count.p, c->cell_start.p, (size_t)g.n_cells, (uint32_t*)nullptr, c->scan_tmp32, st); if (rc) return rc;
+  if (n_src) LAUNCH(k_bin_scatter, nblk(n_src, 256), 256, st, (int)n_src, c->key.p, c->rnk.p, c->cell_start.p, c->perm.p);
+  LAUNCH((k_cell_sort<false>), (unsigned)g.n_cells, CELLSORT_THREADS, st, g, c->cell_start.p, c->cell_count.p, c->perm.p, c->perm2.p,
+         A.rx, A.ry, A.rz, A.id, c->side_lut.p, (const unsigned long long*)nullptr, (uint32_t*)nullptr, s32);
+  rc = ensure_particle_capacity(c, (size_t)std::max<int64_t>(n_new, 1), (size_t)n_src); if (rc) return rc;
+  A = c->P(c->cur);
+  ParticlesP B = c->P(1 - c->cur);
+  if (n_new) LAUNCH(k_gather, nblk(n_new, 256), 256, st, (int)n_new, c->perm2.p, A, B, c->key.p, c->atom_cell[1 - c->cur_ac].p);
+  c->cur = 1 - c->cur; c->cur_ac = 1 - c->cur_ac;
+  c->n_inner = n_new; c->n_total = n_new; c->n_ghost = 0; c->have_nbh = false;
+  LAUNCH(k_ghost_cells_clear, nblk(g.n_cells, 256), 256, st, g, (uint32_t)n_new, c->cell_start.p, c->cell_count.p);
+  return check_device_errors(c, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int xnb_rebuild_amr(xnb_ctx* c, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_grid(c); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridP& g = c->g;
+  uint32_t* s32 = c->d_scalars32.p;
+  CK(c->sg_size.ensure((size_t)g.n_cells + 1)); CK(c->sub_grid_start.ensure((size_t)g.n_cells + 1));
+  CK(cudaMemsetAsync(c->sg_size.p + g.n_cells, 0, 4, st));
+  CK(cudaMemsetAsync(s32 + 2, 0, 4, st));
+  LAUNCH(k_amr_sizes, nblk(g.n_cells, 256), 256, st, g, c->cell_count.p, c->side_lut.p, c->sg_size.p, s32 + 2);
+  rc = scan_exclusive<uint32_t, unsigned long long>(c, c->sg_size.p, c->sub_grid_start.p, (size_t)g.n_cells + 1, c->d_scalars64.p + 1, c->scan_tmp64, st); if (rc) return rc;
+  uint32_t ms = 0; unsigned long long tot = 0;
+  rc = read_back(c, s32 + 2, 1, &ms, st); if (rc) return rc;
+  rc = read_back(c, c->d_scalars64.p + 1, 1, &tot, st); if (rc) return rc;
+  c->max_side = std::max(ms, 1u); c->n_sub_grid_cells = (int64_t)tot;
+  if (ms <= 1) return XNB_OK;          // every cell has a 1x1x1 sub grid: nothing to reorder (C2/C3)
+  const int64_t n = c->n_inner;
+  CK(c->sub_grid_cells.ensure((size_t)tot + 16));
+  CK(c->perm.ensure((size_t)n + 16)); CK(c->perm2.ensure((size_t)n + 16));
+  ParticlesP A = c->P(c->cur), B = c->P(1 - c->cur);
+  LAUNCH(k_iota, nblk(n, 256), 256, st, (int)n, c->perm.p);
+  LAUNCH((k_cell_sort<true>), (unsigned)g.n_cells, CELLSORT_THREADS, st, g, c->cell_start.p, c->cell_count.p, c->perm.p, c->perm2.p,
+         A.rx, A.ry, A.rz, A.id, c->side_lut.p, c->sub_grid_start.p, c->sub_grid_cells.p, s32);
+  LAUNCH(k_gather, nblk(n, 256), 256, st, (int)n, c->perm2.p, A, B, c->atom_cell[c->cur_ac].p, c->atom_cell[1 - c->cur_ac].p);
+  c->cur = 1 - c->cur; c->cur_ac = 1 - c->cur_ac;
+  return XNB_OK;
+}
+
+int xnb_backup_r(xnb_ctx* c, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  int rc = ensure_grid(c); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(c->backup.ensure((size_t)c->n_inner * 3 + 16, 0, 1.2));
+  ParticlesP A = c->P(c->cur);
+  if (c->n_inner) LAUNCH(k_backup_r, nblk(c->n_inner, 256), 256, st, c->g, (int)c->n_inner, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->backup.p);
+  return XNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ghosts
+// ---------------------------------------------------------------------------------------------------------------------
+int xnb_ghost_comm_scheme(xnb_ctx* c, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_grid(c); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridP& g = c->g;
+  ParticlesP A = c->P(c->cur);
+  GhostItemsP it{c->it_src_cell.p, c->it_flags.p, c->it_partner.p, c->it_outer.p, c->n_send_items};
+  const int ns = c->n_send_items, nr = c->n_recv_items;
+  // the previous ghosts are discarded (migrate_cell_particles leaves ghost cells empty)
+  LAUNCH(k_ghost_cells_clear, nblk(g.n_cells, 256), 256, st, g, (uint32_t)c->n_inner, c->cell_start.p, c->cell_count.p);
+  c->n_total = c->n_inner; c->n_ghost = 0; c->n_send = 0;
+  if (ns) LAUNCH(k_ghost_count, nblk((int64_t)ns * 32, 128), 128, st, g, it, c->cell_start.p, c->cell_count.p, A.rx, A.ry, A.rz, c->it_count.p);
+  CK(cudaMemsetAsync(c->it_count.p + ns, 0, 4, st));
+  rc = scan_exclusive<uint32_t, uint32_t>(c, c->it_count.p, c->it_offset.p, (size_t)ns + 1, (uint32_t*)nullptr, c->scan_tmp32, st); if (rc) return rc;
+  // exchange per-item counts with the partners (update_ghosts_comm_scheme.cpp:257-303)
+  if (c->nranks > 1)
+  {
+    if (!c->comm) return c->fail(XNB_ERR_NCCL, "nranks > 1 needs an NCCL communicator");
+    NK(g_nccl.GroupStart());
+    for (int p = 0; p < c->nranks; p++)
+    {
+      if (p == c->rank) continue;
+      const int s0 = c->send_first[(size_t)p], s1 = c->send_first[(size_t)p + 1], r0 = c->recv_first[(size_t)p], r1 = c->recv_first[(size_t)p + 1];
+      if (s1 > s0) NK(g_nccl.Send(c->it_count.p + s0, (size_t)(s1 - s0), nccl_uint32, p, c->comm, st));
+      if (r1 > r0) NK(g_nccl.Recv(c->rc_count.p + r0, (size_t)(r1 - r0), nccl_uint32, p, c->comm, st));
+    }
+    NK(g_nccl.GroupEnd());
+  }
+  {
+    const int s0 = c->send_first[(size_t)c->rank], s1 = c->send_first[(size_t)c->rank + 1], r0 = c->recv_first[(size_t)c->rank];
+    if (s1 > s0) CK(cudaMemcpyAsync(c->rc_count.p + r0, c->it_count.p + s0, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  CK(cudaMemsetAsync(c->rc_count.p + nr, 0, 4, st));
+  rc = scan_exclusive<uint32_t, uint32_t>(c, c->rc_count.p, c->rc_offset.p, (size_t)nr + 1, (uint32_t*)nullptr, c->scan_tmp32, st); if (rc) return rc;
+  // per partner particle bases (host needs them for the NCCL calls and the totals for allocation)
+  std::vector<uint32_t> hso((size_t)ns + 1), hro((size_t)nr + 1);
+  CK(cudaMemcpyAsync(hso.data(), c->it_offset.p, ((size_t)ns + 1) * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hro.data(), c->rc_offset.p, ((size_t)nr + 1) * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int p = 0; p <= c->nranks; p++) { c->h_send_base[(size_t)p] = hso[(size_t)c->send_first[(size_t)p]]; c->h_recv_base[(size_t)p] = hro[(size_t)c->recv_first[(size_t)p]]; }
+  c->n_send = hso[(size_t)ns]; c->n_ghost = hro[(size_t)nr];
+  CK(c->send_src.ensure((size_t)c->n_send + 16, 0, 1.2)); CK(c->send_flags.ensure((size_t)c->n_send + 16, 0, 1.2));
+  if (ns) LAUNCH(k_ghost_fill, nblk((int64_t)ns * 32, 128), 128, st, g, it, c->cell_start.p, c->cell_count.p, A.rx, A.ry, A.rz, c->it_offset.p, c->send_src.p, c->send_flags.p);
+  rc = ensure_particle_capacity(c, (size_t)(c->n_inner + c->n_ghost), (size_t)c->n_inner); if (rc) return rc;
+  if (nr) LAUNCH(k_ghost_cells, nblk((int64_t)nr * 32, 128), 128, st, nr, c->rc_dst_cell.p, c->rc_count.p, c->rc_offset.p, (uint32_t)c->n_inner,
+                 c->cell_start.p, c->cell_count.p, c->atom_cell[c->cur_ac].p);
+  c->n_total = c->n_inner + c->n_ghost;
+  c->have_nbh = false;
+  return XNB_OK;
+}
+
+} // extern "C"
+static int ghost_update(xnb_ctx* c, bool all, cudaStream_t st)
+{
+  const GridP& g = c->g;
+  if (c->n_send == 0 && c->n_ghost == 0) return XNB_OK;
+  ParticlesP A = c->P(c->cur);
+  const int self_first = (int)c->h_send_base[(size_t)c->rank], self_end = (int)c->h_send_base[(size_t)c->rank + 1];
+  const uint32_t self_dst = (uint32_t)(c->n_inner + c->h_recv_base[(size_t)c->rank]);
+  const size_t ns = (size_t)c->n_send;
+  if (c->nranks > 1) { CK(c->stage.ensure(ns * (all ? 10 : 3) + 16, 0, 1.2)); if (all) CK(c->stage_type.ensure(ns + 16, 0, 1.2)); }
+  if (ns)
+  {
+    if (all) LAUNCH((k_ghost_pack<true>), nblk((int64_t)ns, 256), 256, st, g, (int)ns, c->send_src.p, c->send_flags.p, A, self_first, self_end, self_dst, c->stage.p, c->stage_type.p);
+    else     LAUNCH((k_ghost_pack<false>), nblk((int64_t)ns, 256), 256, st, g, (int)ns, c->send_src.p, c->send_flags.p, A, self_first, self_end, self_dst, c->stage.p, c->stage_type.p);
+  }
+  if (c->nranks > 1)
+  {
+    const int nf = all ? 9 : 3;
+    NK(g_nccl.GroupStart());
+    for (int p = 0; p < c->nranks; p++)
+    {
+      if (p == c->rank) continue;
+      const size_t s0 = c->h_send_base[(size_t)p], sn = c->h_send_base[(size_t)p + 1] - s0;
+      const size_t r0 = c->h_recv_base[(size_t)p], rn = c->h_recv_base[(size_t)p + 1] - r0;
+      if (sn)
+      {
+        for (int f = 0; f < nf; f++) NK(g_nccl.Send(c->stage.p + (size_t)f * ns + s0, sn, nccl_float64, p, c->comm, st));
+        if (all) { NK(g_nccl.Send(c->stage.p + (size_t)9 * ns + s0, sn, nccl_uint64, p, c->comm, st)); NK(g_nccl.Send(c->stage_type.p + s0, sn, nccl_uint8, p, c->comm, st)); }
+      }
+      if (rn)
+      {
+        const size_t d0 = (size_t)c->n_inner + r0;
+        for (int f = 0; f < nf; f++) NK(g_nccl.Recv(c->f64[c->cur][f].p + d0, rn, nccl_float64, p, c->comm, st));
+        if (all) { NK(g_nccl.Recv(c->idb[c->cur].p + d0, rn, nccl_uint64, p, c->comm, st)); NK(g_nccl.Recv(c->typeb[c->cur].p + d0, rn, nccl_uint8, p, c->comm, st)); }
+      }
+    }
+    NK(g_nccl.GroupEnd());
+  }
+  return XNB_OK;
+}
+
+extern "C" {
+int xnb_ghost_update_all(xnb_ctx* c, void* stream) { if (!c) return XNB_ERR_INVALID; CK(cudaSetDevice(c->device)); return ghost_update(c, true, (cudaStream_t)stream); }
+int xnb_ghost_update_r(xnb_ctx* c, void* stream) { if (!c) return XNB_ERR_INVALID; CK(cudaSetDevice(c->device)); return ghost_update(c, false, (cudaStream_t)stream); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// chunk_neighbors
+// ---------------------------------------------------------------------------------------------------------------------
+int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_grid(c); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridP& g = c->g;
+  const int64_t n = c->n_total;
+  const int gap = (int)std::ceil(c->nbh_dist / c->cs);
+  const double md2 = c->nbh_dist * c->nbh_dist;
+  uint32_t* s32 = c->d_scalars32.p;
+  CK(c->nb_len.ensure((size_t)n + 16, 0, 1.1)); CK(c->nb_cnt.ensure((size_t)n + 16, 0, 1.1)); CK(c->nb_off.ensure((size_t)n + 16, 0, 1.1));
+  CK(c->stream_size.ensure((size_t)g.n_cells + 1)); CK(c->stream_size_padded.ensure((size_t)g.n_cells + 1)); CK(c->stream_off.ensure((size_t)g.n_cells + 1));
+  CK(c->cell_stream.ensure((size_t)g.n_cells)); CK(c->cell_stream_bytes.ensure((size_t)g.n_cells));
+  ParticlesP A = c->P(c->cur);
+  if (c->timing) CK(cudaEventRecord(c->ev0, st));
+  NbhOut out{c->nb_len.p, c->nb_cnt.p, c->nb_off.p, c->cell_stream.p};
+  if (n) LAUNCH((k_nbh_build<false>), nblk(n, 128), 128, st, g, (int)n, gap, md2, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
+  CK(cudaMemsetAsync(s32 + 3, 0, 4, st));
+  LAUNCH(k_nbh_cell_sizes, nblk((int64_t)g.n_cells * 32, 128), 128, st, g.n_cells, c->cell_start.p, c->cell_count.p, c->nb_len.p, c->nb_cnt.p, c->nb_off.p,
+         c->stream_size.p, c->stream_size_padded.p, s32 + 3, s32);
+  rc = scan_exclusive<uint32_t, unsigned long long>(c, c->stream_size_padded.p, c->stream_off.p, (size_t)g.n_cells, c->d_scalars64.p + 1, c->scan_tmp64, st); if (rc) return rc;
+  unsigned long long tot = 0; uint32_t mx = 0;
+  rc = read_back(c, c->d_scalars64.p + 1, 1, &tot, st); if (rc) return rc;
+  rc = read_back(c, s32 + 3, 1, &mx, st); if (rc) return rc;
+  c->pool_used = (int64_t)tot; c->max_neighbors = mx;
+  // realloc_stream_pool (chunk_neighbors.h:70-96): grow with the reference's 5% head-room (update-particles.msp:20)
+  CK(c->pool.ensure((size_t)tot + 64, 0, 1.05));
+  LAUNCH(k_nbh_pointers, nblk(g.n_cells, 256), 256, st, g.n_cells, c->pool.p, c->stream_off.p, c->stream_size.p, c->cell_stream.p, c->cell_stream_bytes.p);
+  if (n) LAUNCH((k_nbh_build<true>), nblk(n, 128), 128, st, g, (int)n, gap, md2, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
+  if (c->timing)
+  {
+    CK(cudaEventRecord(c->ev1, st)); CK(cudaEventSynchronize(c->ev1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->nbh_ms += ms; c->nbh_launches++;
+  }
+  c->have_nbh = true;
+  return check_device_errors(c, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// force / integrate
+// ---------------------------------------------------------------------------------------------------------------------
+int xnb_zero_particle_force(xnb_ctx* c, int ghost, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  ParticlesP A = c->P(c->cur);
+  const int64_t n = ghost ? c->n_total : c->n_inner;
+  if (n) LAUNCH(k_zero_force, nblk(n, 256), 256, st, (int)n, A.fx, A.fy, A.fz);
+  return XNB_OK;
+}
+
+} // extern "C"
+static LJP make_lj(double eps, double sig, double rcut) { LJP p; p.eps24 = 24.0 * eps; p.sig2 = sig * sig; p.rcut2 = rcut * rcut; p.eps4 = 4.0 * eps; return p; }
+
+template <int MODE, bool EV>
+static int launch_force(xnb_ctx* c, int64_t first, int64_t n, int64_t n_zero_end, const LJP& lj, double dth, double* evp, cudaStream_t st)
+{
+  ParticlesP A = c->P(c->cur);
+  const int64_t span = std::max(n, n_zero_end - first);
+  if (span <= 0) return XNB_OK;
+  if (c->timing) CK(cudaEventRecord(c->ev0, st));
+  LAUNCH((k_lj_force<MODE, EV>), nblk(span, 128), 128, st, c->g, (int)first, (int)n, (int)n_zero_end, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, A.fx, A.fy, A.fz,
+         A.type, c->mass.p, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p, evp);
+  if (c->timing)
+  {
+    CK(cudaEventRecord(c->ev1, st)); CK(cudaEventSynchronize(c->ev1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->force_ms += ms; c->force_launches++;
+  }
+  return XNB_OK;
+}
+
+extern "C" {
+int xnb_lennard_jones_force(xnb_ctx* c, double eps, double sig, double rcut, int ghost, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "lennard_jones_force: no neighbour list (run xnb_chunk_neighbors)");
+  c->rcut_max = std::max(c->rcut_max, rcut);    // lennard_jones.cu:193
+  const int64_t n = ghost ? c->n_total : c->n_inner;
+  return launch_force<0, false>(c, 0, n, 0, make_lj(eps, sig, rcut), 0.0, nullptr, (cudaStream_t)stream);
+}
+
+int xnb_divide_force_by_mass(xnb_ctx* c, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  ParticlesP A = c->P(c->cur);
+  if (c->n_inner) LAUNCH(k_divide_force_by_mass, nblk(c->n_inner, 256), 256, st, (int)c->n_inner, A.fx, A.fy, A.fz, A.type, c->mass.p);
+  return XNB_OK;
+}
+
+int xnb_push_f_v_r(xnb_ctx* c, double dt, double dt_scale, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  ParticlesP A = c->P(c->cur);
+  const double delta_t = dt * dt_scale, delta_t2 = delta_t * delta_t * 0.5;     // push_vec3_2nd_order.h:87-88
+  if (c->n_inner) LAUNCH(k_push_f_v_r, nblk(c->n_inner, 256), 256, st, (int)c->n_inner, delta_t, delta_t2, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, A.fx, A.fy, A.fz);
+  return XNB_OK;
+}
+
+int xnb_push_f_v(xnb_ctx* c, double dt, double dt_scale, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  ParticlesP A = c->P(c->cur);
+  if (c->n_inner) LAUNCH(k_push_f_v, nblk(c->n_inner, 256), 256, st, (int)c->n_inner, dt * dt_scale, A.vx, A.vy, A.vz, A.fx, A.fy, A.fz);
+  return XNB_OK;
+}
+
+int xnb_read_displ_over(xnb_ctx* c, uint64_t* count_out, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  // MPI_Allreduce(SUM, 1 x u64) of particle_displ_over.cu:174
+  if (c->nranks > 1) { if (!c->comm) return c->fail(XNB_ERR_NCCL, "no communicator"); NK(g_nccl.AllReduce(c->d_scalars64.p, c->d_scalars64.p, 1, nccl_uint64, nccl_sum, c->comm, st)); }
+  unsigned long long v = 0;
+  int rc = read_back(c, c->d_scalars64.p, 1, &v, st); if (rc) return rc;
+  if (count_out) *count_out = v;
+  return XNB_OK;
+}
+
+int xnb_particle_displ_over(xnb_ctx* c, uint64_t* count_out, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  ParticlesP A = c->P(c->cur);
+  CK(cudaMemsetAsync(c->d_scalars64.p, 0, 8, st));
+  if (c->n_inner) LAUNCH(k_displ_over, nblk(c->n_inner, 256), 256, st, c->g, (int)c->n_inner, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->backup.p,
+                         c->max_displ * c->max_displ, c->d_scalars64.p);
+  return xnb_read_displ_over(c, count_out, stream);
+}
+
+int xnb_verlet_first_half(xnb_ctx* c, double dt, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  ParticlesP A = c->P(c->cur);
+  CK(cudaMemsetAsync(c->d_scalars64.p, 0, 8, st));
+  if (c->n_inner) LAUNCH(k_verlet_first_half, nblk(c->n_inner, 256), 256, st, c->g, (int)c->n_inner, dt, dt * dt * 0.5, dt * 0.5, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
+                         A.fx, A.fy, A.fz, c->atom_cell[c->cur_ac].p, c->backup.p, c->max_displ * c->max_displ, c->d_scalars64.p);
+  return XNB_OK;
+}
+
+int xnb_force_and_second_half(xnb_ctx* c, double eps, double sig, double rcut, double dth, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "no neighbour list (run xnb_chunk_neighbors)");
+  return launch_force<1, false>(c, 0, c->n_inner, c->n_total, make_lj(eps, sig, rcut), dth, nullptr, (cudaStream_t)stream);
+}
+
+} // extern "C"
+static int update_particles_full(xnb_ctx* c, void* stream)
+{
+  int rc;
+  if ((rc = xnb_rebuild_amr(c, stream))) return rc;
+  if ((rc = xnb_backup_r(c, stream))) return rc;
+  if ((rc = xnb_ghost_comm_scheme(c, stream))) return rc;
+  if ((rc = xnb_ghost_update_all(c, stream))) return rc;
+  if ((rc = xnb_chunk_neighbors(c, stream))) return rc;
+  c->rebuilds++;
+  return XNB_OK;
+}
+
+extern "C" {
+int xnb_first_iteration(xnb_ctx* c, double eps, double sig, double rcut, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  int rc;
+  if ((rc = xnb_move_particles(c, stream))) return rc;
+  if ((rc = update_particles_full(c, stream))) return rc;
+  return xnb_force_and_second_half(c, eps, sig, rcut, 0.0, stream);
+}
+
+int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, double rcut, void* stream, int* rebuilds_out)
+{
+  if (!c) return XNB_ERR_INVALID;
+  int rebuilds = 0, rc;
+  for (int it = 0; it < nsteps; it++)
+  {
+    if ((rc = xnb_verlet_first_half(c, dt, stream))) return rc;
+    uint64_t over = 0;
+    if ((rc = xnb_read_displ_over(c, &over, stream))) return rc;
+    if (over > 0)
+    {
+      if ((rc = xnb_move_particles(c, stream))) return rc;
+      if ((rc = update_particles_full(c, stream))) return rc;
+      rebuilds++;
+    }
+    else if ((rc = xnb_ghost_update_r(c, stream))) return rc;
+    if ((rc = xnb_force_and_second_half(c, eps, sig, rcut, dt * 0.5, stream))) return rc;
+  }
+  if (rebuilds_out) *rebuilds_out = rebuilds;
+  return XNB_OK;
+}
+
+int xnb_energy_virial(xnb_ctx* c, double eps, double sig, double rcut, double* epot, double virial[6], double* ekin, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "no neighbour list");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = c->n_inner;
+  const unsigned nb = nblk(n, 128), nb2 = nblk(n, 256);
+  CK(c->ev_partials.ensure((size_t)nb * 7 + nb2 + 16));
+  // MODE 0 accumulates into f: run it on a scratch copy of f so the state is untouched
+  DBuf<double> scratch; CK(scratch.ensure((size_t)n * 3 + 16));
+  ParticlesP A = c->P(c->cur);
+  double* keep[3] = {A.fx, A.fy, A.fz};
+  // temporarily point the force arrays at the scratch
+  double* sfx = scratch.p, *sfy = scratch.p + n, *sfz = scratch.p + 2 * n;
+  CK(cudaMemsetAsync(scratch.p, 0, (size_t)n * 3 * 8, st));
+  if (n)
+  {
+    k_lj_force<0, true><<<nb, 128, 0, st>>>(c->g, 0, (int)n, 0, make_lj(eps, sig, rcut), 0.0, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, sfx, sfy, sfz,
+                                            A.type, c->mass.p, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p, c->ev_partials.p);
+    c->launches++; CK(cudaGetLastError());
+    LAUNCH(k_ekin, nb2, 256, st, (int)n, A.vx, A.vy, A.vz, A.type, c->mass.p, c->ev_partials.p + (size_t)nb * 7);
+  }
+  (void)keep;
+  std::vector<double> h((size_t)nb * 7 + nb2, 0.0);
+  CK(cudaMemcpyAsync(h.data(), c->ev_partials.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  auto ksum = [&](size_t first, size_t count, size_t stride) { double s = 0., cc = 0.; for (size_t q = 0; q < count; q++) { const double x = h[first + q * stride]; const double t = s + x; cc += (std::fabs(s) >= std::fabs(x)) ? (s - t) + x : (x - t) + s; s = t; } return s + cc; };
+  if (n == 0) { if (epot) *epot = 0; if (virial) for (int q = 0; q < 6; q++) virial[q] = 0; if (ekin) *ekin = 0; return XNB_OK; }
+  if (epot) *epot = ksum(0, nb, 7);
+  if (virial) for (int q = 0; q < 6; q++) virial[q] = ksum((size_t)q + 1, nb, 7);
+  if (ekin) *ekin = ksum((size_t)nb * 7, nb2, 1);
+  return XNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// views / downloads
+// ---------------------------------------------------------------------------------------------------------------------
+int xnb_view_chunk_neighbors(xnb_ctx* c, const uint16_t* const** d_cell_stream, const uint32_t** d_bytes, uint32_t* max_neighbors)
+{
+  if (!c || !c->have_nbh) return XNB_ERR_INVALID;
+  if (d_cell_stream) *d_cell_stream = (const uint16_t* const*)c->cell_stream.p;
+  if (d_bytes) *d_bytes = c->cell_stream_bytes.p;
+  if (max_neighbors) *max_neighbors = c->max_neighbors;
+  return XNB_OK;
+}
+
+int64_t xnb_stream_pool_u16(const xnb_ctx* c) { return c ? c->pool_used : 0; }
+
+int xnb_get_streams(xnb_ctx* c, uint32_t* size_u16, uint16_t* data)
+{
+  if (!c || !c->have_nbh) return XNB_ERR_INVALID;
+  CK(cudaDeviceSynchronize());
+  const size_t nc = (size_t)c->g.n_cells;
+  std::vector<uint32_t> sz(nc); std::vector<unsigned long long> off(nc);
+  CK(cudaMemcpy(sz.data(), c->stream_size.p, nc * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(off.data(), c->stream_off.p, nc * 8, cudaMemcpyDeviceToHost));
+  if (size_u16) memcpy(size_u16, sz.data(), nc * 4);
+  if (data)
+  {
+    std::vector<uint16_t> pool((size_t)c->pool_used);
+    if (c->pool_used) CK(cudaMemcpy(pool.data(), c->pool.p, (size_t)c->pool_used * 2, cudaMemcpyDeviceToHost));
+    size_t o = 0;
+    for (size_t q = 0; q < nc; q++) { if (sz[q]) memcpy(data + o, pool.data() + off[q], (size_t)sz[q] * 2); o += sz[q]; }
+  }
+  return XNB_OK;
+}
+
+int64_t xnb_get_amr(xnb_ctx* c, int64_t* sgs, uint32_t* sgc)
+{
+  if (!c) return -1;
+  cudaDeviceSynchronize();
+  const size_t nc = (size_t)c->g.n_cells;
+  if (sgs)
+  {
+    std::vector<unsigned long long> h(nc + 1);
+    if (cudaMemcpy(h.data(), c->sub_grid_start.p, (nc + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (size_t q = 0; q <= nc; q++) sgs[q] = (int64_t)h[q];
+  }
+  if (sgc && c->n_sub_grid_cells && c->max_side > 1)
+    if (cudaMemcpy(sgc, c->sub_grid_cells.p, (size_t)c->n_sub_grid_cells * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return c->n_sub_grid_cells;
+}
+
+int xnb_get_backup(xnb_ctx* c, uint32_t* out)
+{
+  if (!c || !out) return XNB_ERR_INVALID;
+  CK(cudaDeviceSynchronize());
+  if (c->n_inner) CK(cudaMemcpy(out, c->backup.p, (size_t)c->n_inner * 12, cudaMemcpyDeviceToHost));
+  return XNB_OK;
+}
+
+int64_t xnb_rebuild_count(const xnb_ctx* c) { return c ? c->rebuilds : 0; }
+int64_t xnb_kernel_launches(const xnb_ctx* c) { return c ? c->launches : 0; }
+
+int xnb_timing_enable(xnb_ctx* c, int on)
+{
+  if (!c) return XNB_ERR_INVALID;
+  if (on && !c->ev0) { CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1)); }
+  c->timing = on != 0;
+  return XNB_OK;
+}
+
+int xnb_timing_read(xnb_ctx* c, double* fms, int64_t* fl, double* nms, int64_t* nl, int reset)
+{
+  if (!c) return XNB_ERR_INVALID;
+  if (fms) *fms = c->force_ms; if (fl) *fl = c->force_launches; if (nms) *nms = c->nbh_ms; if (nl) *nl = c->nbh_launches;
+  if (reset) { c->force_ms = c->nbh_ms = 0; c->force_launches = c->nbh_launches = 0; }
+  return XNB_OK;
+}
+
+int xnb_measure_dfma_peak(int device, double* tflops)
+{
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return XNB_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return XNB_ERR_CUDA;
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device);
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double* out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * 8) != cudaSuccess) return XNB_ERR_CUDA;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++)
+  {
+    cudaEventRecord(e0);
+    k_dfma_probe<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+    if (rep > 0 && ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  if (tflops) *tflops = best;
+  return cudaGetLastError() == cudaSuccess ? XNB_OK : XNB_ERR_CUDA;
+}
+
+} // extern "C"

@@ -1,0 +1,852 @@
+// xnb_kernels.cuh -- hand-written sm_100a kernels of the exaNBody LJ hot path.
+//
+//   K1  binning          : k_bin_locate -> scan -> k_bin_scatter -> k_cell_sort -> k_gather      (move_particles)
+//   K1c in-cell sub-grid : k_amr_sizes -> scan -> k_cell_sort<AMR> -> k_gather                    (rebuild_amr)
+//   K1e backup           : k_backup_r                                                             (backup_r)
+//   K6/7 ghosts          : k_ghost_count -> scan -> k_ghost_fill -> k_ghost_cells, k_ghost_pack   (ghost_comm_scheme, ghost_update_*)
+//   K2  neighbour build  : k_nbh_build<COUNT> -> k_nbh_cell_sizes -> scan -> k_nbh_build<FILL>    (chunk_neighbors)
+//   K3  pair sweep       : k_lj_force<...>                                                         (lennard_jones_force [+ fused epilogue])
+//   K4/5 integrate       : k_verlet_first_half, k_push_f_v_r, k_push_f_v, k_displ_over, ...
+//
+// Data layout (HBM): flat SoA over particles; inner particles [0,n_inner) sorted by local cell index, ghost particles
+// [n_inner,n_total) grouped by ghost cell; cell_start[c]/cell_count[c] give each cell's slice (the per-cell SoA view
+// of the reference's CellParticles).  Neighbour streams live in one u16 pool, one 16-byte aligned slice per cell in
+// the exact GridChunkNeighbors format.
+#pragma once
+#include "xnb_common.cuh"
+
+namespace xnb {
+
+// ------------------------------------------------------------------------------------------------------------------
+// exclusive scan (three-kernel, any length)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+template <class T>
+XNB_DEVINL T block_exclusive_scan(T v, T* total, T* smem /* 32 entries */)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  T x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { T y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) smem[warp] = x;
+  __syncthreads();
+  if (warp == 0)
+  {
+    T w = (lane < nwarp) ? smem[lane] : T(0);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { T y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+    smem[lane] = w;   // inclusive over warps
+  }
+  __syncthreads();
+  const T warp_off = (warp > 0) ? smem[warp - 1] : T(0);
+  *total = smem[nwarp - 1];
+  __syncthreads();
+  return warp_off + x - v;
+}
+
+template <class TIn, class T>
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_tiles(const TIn* __restrict__ in, T* __restrict__ out, T* __restrict__ tile_sums, size_t n)
+{
+  __shared__ T sm[32];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  T v[SCAN_ITEMS]; T s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? (T)in[base + k] : T(0); s += v[k]; }
+  T total;
+  T off = block_exclusive_scan<T>(s, &total, sm);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = off; off += v[k]; }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+template <class T>
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_sums(T* __restrict__ tile_sums, size_t n_tiles, T* __restrict__ grand_total)
+{
+  __shared__ T sm[32];
+  T carry = 0;
+  for (size_t base = 0; base < n_tiles; base += SCAN_TILE)
+  {
+    const size_t b = base + (size_t)threadIdx.x * SCAN_ITEMS;
+    T v[SCAN_ITEMS]; T s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (b + k < n_tiles) ? tile_sums[b + k] : T(0); s += v[k]; }
+    T total;
+    T off = carry + block_exclusive_scan<T>(s, &total, sm);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (b + k < n_tiles) tile_sums[b + k] = off; off += v[k]; }
+    carry += total;
+  }
+  if (threadIdx.x == 0 && grand_total) *grand_total = carry;
+}
+
+template <class T>
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(T* __restrict__ out, const T* __restrict__ tile_sums, size_t n)
+{
+  const T add = tile_sums[blockIdx.x];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) out[base + k] += add;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K1 binning.  reference: move_particles_across_cells.h:104-156 (wrap + locate, domain.h:160-191)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t KEY_LEAVING = 0xFFFFFFFFu;
+
+// periodic wrap of one coordinate and domain cell location, bit-identical to the oracle's domain_periodic_location
+XNB_DEVINL int locate_axis(double& r, double dmin, double cs, int ddim, int periodic)
+{
+  const double rel = __dadd_rn(r, -dmin);
+  long long loc = (long long)floor(__ddiv_rn(rel, cs));
+  if ((loc < 0 || loc >= ddim) && periodic)
+  {
+    const long long o = loc;
+    loc = ((loc % ddim) + ddim) % ddim;
+    r = __dadd_rn(r, __dmul_rn((double)(loc - o), cs));
+  }
+  return (int)max(min(loc, (long long)INT32_MAX), (long long)INT32_MIN);
+}
+
+// one thread per inner particle: wrap position in place, compute destination local cell, count per cell.
+// rank[i] = arrival order inside the destination cell (arbitrary; fixed afterwards by k_cell_sort).
+// Particles whose destination is outside this rank's inner block get KEY_LEAVING and are appended to leave_list.
+__global__ void k_bin_locate(GridP g, int n, double* __restrict__ rx, double* __restrict__ ry, double* __restrict__ rz,
+                             uint32_t* __restrict__ key, uint32_t* __restrict__ rank, uint32_t* __restrict__ cell_count,
+                             uint32_t* __restrict__ leave_list, uint32_t* __restrict__ leave_count, uint32_t* __restrict__ err)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = rx[i], y = ry[i], z = rz[i];
+  const int li = locate_axis(x, g.dmin[0], g.cs, g.ddims[0], g.periodic[0]);
+  const int lj = locate_axis(y, g.dmin[1], g.cs, g.ddims[1], g.periodic[1]);
+  const int lk = locate_axis(z, g.dmin[2], g.cs, g.ddims[2], g.periodic[2]);
+  rx[i] = x; ry[i] = y; rz[i] = z;
+  if (li < 0 || li >= g.ddims[0] || lj < 0 || lj >= g.ddims[1] || lk < 0 || lk >= g.ddims[2])
+  {
+    atomicOr(err, DERR_LOST_PARTICLE);   // left a non periodic domain: reference drops it into otb_particles for good
+    key[i] = KEY_LEAVING; rank[i] = 0;
+    return;
+  }
+  if (li < g.bstart[0] || li >= g.bend[0] || lj < g.bstart[1] || lj >= g.bend[1] || lk < g.bstart[2] || lk >= g.bend[2])
+  {
+    // otb_particles (move_particles_across_cells.h:124-138): handed to migrate (multi-GPU)
+    key[i] = KEY_LEAVING;
+    rank[i] = atomicAdd(leave_count, 1u);
+    if (leave_list) leave_list[rank[i]] = (uint32_t)i;
+    return;
+  }
+  const int c = ijk_to_index(g.dims, li - g.off[0], lj - g.off[1], lk - g.off[2]);
+  key[i] = (uint32_t)c;
+  rank[i] = atomicAdd(&cell_count[c], 1u);
+}
+
+// cell_start for INNER cells from the exclusive scan of counts over all local cells (ghost cells hold 0 here)
+__global__ void k_bin_scatter(int n, const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank,
+                              const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ perm)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = key[i];
+  if (c == KEY_LEAVING) return;
+  perm[cell_start[c] + rank[i]] = (uint32_t)i;
+}
+
+XNB_DEVINL void cell_origin(const GridP& g, uint32_t c, double& ox, double& oy, double& oz)
+{
+  const int ci = c % g.dims[0], cj = (c / g.dims[0]) % g.dims[1], ck = c / (g.dims[0] * g.dims[1]);
+  ox = __dadd_rn(g.org[0], __dmul_rn((double)(g.off[0] + ci), g.cs));
+  oy = __dadd_rn(g.org[1], __dmul_rn((double)(g.off[1] + cj), g.cs));
+  oz = __dadd_rn(g.org[2], __dmul_rn((double)(g.off[2] + ck), g.cs));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// in-cell ordering.  One block per cell.  perm[cell_start[c] .. +n) holds source indices; they are re-ordered by
+//   AMR=false : particle id  (the reference's in-cell order after move_particles depends on OpenMP scheduling, i.e. is
+//               unspecified; ordering by id makes ours deterministic AND independent of the domain decomposition)
+//   AMR=true  : (sub-cell index, particle id): the sub-cell grouping of project_particles_in_sub_grids
+//               (amr_grid_algorithm.h:188-299); sub_grid_cells[] gets the cumulative end offsets (:283-292)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int CELLSORT_MAX = 2048;   // particles per cell the in-cell sort handles (reference hard limit: 65535)
+constexpr int CELLSORT_THREADS = 128;
+
+template <bool AMR>
+__global__ void __launch_bounds__(CELLSORT_THREADS)
+k_cell_sort(GridP g, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+            const uint32_t* __restrict__ perm_in, uint32_t* __restrict__ perm_out,
+            const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+            const unsigned long long* __restrict__ id,
+            const uint8_t* __restrict__ side_lut, const unsigned long long* __restrict__ sub_grid_start,
+            uint32_t* __restrict__ sub_grid_cells, uint32_t* __restrict__ err)
+{
+  __shared__ unsigned long long keys[CELLSORT_MAX];
+  __shared__ uint32_t srcs[CELLSORT_MAX];
+  __shared__ uint32_t hist[AMR ? 4096 : 1];
+  const int c = blockIdx.x;
+  const int n = (int)cell_count[c];
+  if (n == 0) return;
+  if (n > CELLSORT_MAX) { if (threadIdx.x == 0) atomicOr(err, DERR_SORT_CAPACITY); return; }
+  const uint32_t s0 = cell_start[c];
+  int side = 1;
+  if (AMR)
+  {
+    side = side_lut[min(n, 65535)];
+    if (side < 1) side = 1;
+  }
+  const int nsub = side * side * side;
+  if (AMR) { for (int q = threadIdx.x; q < nsub; q += blockDim.x) hist[q] = 0; __syncthreads(); }
+  // cell low corner: origin + (offset+loc)*cell_size   (grid.h:113-116, oracle Grid::cell_position)
+  double lx, ly, lz;
+  cell_origin(g, (uint32_t)c, lx, ly, lz);
+  for (int t = threadIdx.x; t < n; t += blockDim.x)
+  {
+    const uint32_t src = perm_in[s0 + t];
+    unsigned long long sub = 0;
+    if (AMR && side > 1)
+    {
+      // particle_pcoord (grid.h:184-190) then trunc(p*side) clamped (amr_grid_algorithm.h:188-205)
+      const double px = __ddiv_rn(__dadd_rn(rx[src], -lx), g.cs), py = __ddiv_rn(__dadd_rn(ry[src], -ly), g.cs), pz = __ddiv_rn(__dadd_rn(rz[src], -lz), g.cs);
+      long long si = (long long)__dmul_rn(px, (double)side), sj = (long long)__dmul_rn(py, (double)side), sk = (long long)__dmul_rn(pz, (double)side);
+      si = max(0ll, min(si, (long long)side - 1)); sj = max(0ll, min(sj, (long long)side - 1)); sk = max(0ll, min(sk, (long long)side - 1));
+      sub = (unsigned long long)((sk * side + sj) * side + si);
+      atomicAdd(&hist[(int)sub], 1u);
+    }
+    const unsigned long long pid = id[src];
+    if (pid >> 52) atomicOr(err, DERR_ID_RANGE);
+    keys[t] = (sub << 52) | (pid & ((1ull << 52) - 1ull));
+    srcs[t] = src;
+  }
+  __syncthreads();
+  // rank sort (n is small: 32..256 in the benchmark configs); ids are unique so ranks are a permutation
+  for (int t = threadIdx.x; t < n; t += blockDim.x)
+  {
+    const unsigned long long my = keys[t];
+    int r = 0;
+    for (int u = 0; u < n; u++) r += (keys[u] < my) ? 1 : 0;
+    perm_out[s0 + r] = srcs[t];
+  }
+  if (AMR && side > 1)
+  {
+    // cumulative END offsets of sub-cells 0..nsub-2
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      const unsigned long long sg0 = sub_grid_start[c];
+      uint32_t acc = 0;
+      for (int q = 0; q < nsub - 1; q++) { acc += hist[q]; sub_grid_cells[sg0 + q] = acc; }
+    }
+  }
+}
+
+// number of sub_grid_cells entries per cell: max(side^3-1,0), inner cells only (ghost cells are empty when rebuild_amr
+// runs in the reference: update-particles.msp:48-52), reference amr_grid_algorithm.h:400-417
+__global__ void k_amr_sizes(GridP g, const uint32_t* __restrict__ cell_count, const uint8_t* __restrict__ side_lut,
+                            uint32_t* __restrict__ sg_size, uint32_t* __restrict__ max_side)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.n_cells) return;
+  const int ci = c % g.dims[0], cj = (c / g.dims[0]) % g.dims[1], ck = c / (g.dims[0] * g.dims[1]);
+  const bool inner = ci >= g.gl && ci < g.dims[0] - g.gl && cj >= g.gl && cj < g.dims[1] - g.gl && ck >= g.gl && ck < g.dims[2] - g.gl;
+  int side = 0;
+  if (inner) side = side_lut[min(cell_count[c], 65535u)];
+  sg_size[c] = (side > 1) ? (uint32_t)(side * side * side - 1) : 0u;
+  if (side > 1) atomicMax(max_side, (uint32_t)side);
+}
+
+// gather all particle fields through a permutation (dest j takes source perm[j]); also writes atom_cell
+__global__ void k_gather(int n, const uint32_t* __restrict__ perm, ParticlesP src, ParticlesP dst,
+                         const uint32_t* __restrict__ key_src, uint32_t* __restrict__ atom_cell)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t s = perm[j];
+  dst.rx[j] = src.rx[s]; dst.ry[j] = src.ry[s]; dst.rz[j] = src.rz[s];
+  dst.vx[j] = src.vx[s]; dst.vy[j] = src.vy[s]; dst.vz[j] = src.vz[s];
+  dst.fx[j] = src.fx[s]; dst.fy[j] = src.fy[s]; dst.fz[j] = src.fz[s];
+  dst.id[j] = src.id[s]; dst.type[j] = src.type[s];
+  atom_cell[j] = key_src[s];
+}
+
+// identity permutation restricted to cell slices (used by rebuild_amr, where particles are already cell sorted)
+__global__ void k_iota(int n, uint32_t* __restrict__ p) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = (uint32_t)i; }
+
+__global__ void k_fill_u32(size_t n, uint32_t* __restrict__ p, uint32_t v) { const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// backup_r.  reference: io/backup_r.cpp:56-78, core/backup_r.h:36-51
+// ------------------------------------------------------------------------------------------------------------------
+XNB_DEVINL uint32_t encode_double_u32(double x, double o, double r)
+{
+  const double xo = __dadd_rn(x, -o);
+  long long q = (long long)__ddiv_rn(__dmul_rn(xo, 4294967296.0), r);
+  q = max(0ll, min(q, 4294967295ll));
+  const uint32_t a = (uint32_t)q, b = a - 1u, c = a + 1u;
+  const double ea = fabs(__dadd_rn(restore_u32_double(a, o, r), -x));
+  const double eb = fabs(__dadd_rn(restore_u32_double(b, o, r), -x));
+  const double ec = fabs(__dadd_rn(restore_u32_double(c, o, r), -x));
+  if (eb < ea) return b;
+  if (ec < ea) return c;
+  return a;
+}
+
+__global__ void k_backup_r(GridP g, int n_inner, const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                           const uint32_t* __restrict__ atom_cell, uint32_t* __restrict__ backup)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inner) return;
+  double ox, oy, oz;
+  cell_origin(g, atom_cell[i], ox, oy, oz);
+  backup[3 * (size_t)i + 0] = encode_double_u32(rx[i], ox, g.cs);
+  backup[3 * (size_t)i + 1] = encode_double_u32(ry[i], oy, g.cs);
+  backup[3 * (size_t)i + 2] = encode_double_u32(rz[i], oz, g.cs);
+}
+
+// displacement test of one particle (particle_displ_over.cu:47-65): |r - restore(backup)|^2 >= threshold^2
+XNB_DEVINL bool displ_over_test(const GridP& g, uint32_t cell, const uint32_t* __restrict__ rb, double x, double y, double z, double thr2)
+{
+  double ox, oy, oz;
+  cell_origin(g, cell, ox, oy, oz);
+  const double dx = __dadd_rn(x, -restore_u32_double(rb[0], ox, g.cs));
+  const double dy = __dadd_rn(y, -restore_u32_double(rb[1], oy, g.cs));
+  const double dz = __dadd_rn(z, -restore_u32_double(rb[2], oz, g.cs));
+  return norm2_exact(dx, dy, dz) >= thr2;
+}
+
+XNB_DEVINL void block_count_add(bool flag, unsigned long long* counter)
+{
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(counter, (unsigned long long)__popc(m));
+}
+
+__global__ void k_displ_over(GridP g, int n_inner, const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                             const uint32_t* __restrict__ atom_cell, const uint32_t* __restrict__ backup, double thr2,
+                             unsigned long long* __restrict__ counter)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool over = false;
+  if (i < n_inner) over = displ_over_test(g, atom_cell[i], backup + 3 * (size_t)i, rx[i], ry[i], rz[i], thr2);
+  block_count_add(over, counter);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// integrators.  reference: push_vec3_2nd_order.h:29-39, push_vec3_1st_order.h:29-38 (identity xform).
+// Arithmetic is written with explicit round-to-nearest ops in the reference's order so that it is bit-identical to
+// the oracle (which is compiled with -ffp-contract=off).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_push_f_v_r(int n, double dt, double dt2, double* __restrict__ rx, double* __restrict__ ry, double* __restrict__ rz,
+                             const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
+                             const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rx[i] = __dadd_rn(rx[i], __dadd_rn(__dmul_rn(vx[i], dt), __dmul_rn(fx[i], dt2)));
+  ry[i] = __dadd_rn(ry[i], __dadd_rn(__dmul_rn(vy[i], dt), __dmul_rn(fy[i], dt2)));
+  rz[i] = __dadd_rn(rz[i], __dadd_rn(__dmul_rn(vz[i], dt), __dmul_rn(fz[i], dt2)));
+}
+
+__global__ void k_push_f_v(int n, double dt, double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
+                           const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  vx[i] = __dadd_rn(vx[i], __dmul_rn(fx[i], dt));
+  vy[i] = __dadd_rn(vy[i], __dmul_rn(fy[i], dt));
+  vz[i] = __dadd_rn(vz[i], __dmul_rn(fz[i], dt));
+}
+
+// K4: verlet_first_half (push_f_v_r{1.0} + push_f_v{0.5}) fused with the particle_displ_over reduction.
+__global__ void k_verlet_first_half(GridP g, int n, double dt, double dt2, double dth,
+                                    double* __restrict__ rx, double* __restrict__ ry, double* __restrict__ rz,
+                                    double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
+                                    const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
+                                    const uint32_t* __restrict__ atom_cell, const uint32_t* __restrict__ backup, double thr2,
+                                    unsigned long long* __restrict__ counter)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool over = false;
+  if (i < n)
+  {
+    const double ax = fx[i], ay = fy[i], az = fz[i];
+    const double ux = vx[i], uy = vy[i], uz = vz[i];
+    const double x = __dadd_rn(rx[i], __dadd_rn(__dmul_rn(ux, dt), __dmul_rn(ax, dt2)));
+    const double y = __dadd_rn(ry[i], __dadd_rn(__dmul_rn(uy, dt), __dmul_rn(ay, dt2)));
+    const double z = __dadd_rn(rz[i], __dadd_rn(__dmul_rn(uz, dt), __dmul_rn(az, dt2)));
+    rx[i] = x; ry[i] = y; rz[i] = z;
+    vx[i] = __dadd_rn(ux, __dmul_rn(ax, dth));
+    vy[i] = __dadd_rn(uy, __dmul_rn(ay, dth));
+    vz[i] = __dadd_rn(uz, __dmul_rn(az, dth));
+    over = displ_over_test(g, atom_cell[i], backup + 3 * (size_t)i, x, y, z, thr2);
+  }
+  block_count_add(over, counter);
+}
+
+__global__ void k_zero_force(int n, double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { fx[i] = 0.; fy[i] = 0.; fz[i] = 0.; }
+}
+
+// divide_force_by_type_scalar: mass (vec3_typescalar_op.cu:118-122, math_functors.h:136-141): a true division per component
+__global__ void k_divide_force_by_mass(int n, double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+                                       const uint8_t* __restrict__ type, const double* __restrict__ mass)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double m = mass[type[i]];
+  fx[i] = __ddiv_rn(fx[i], m); fy[i] = __ddiv_rn(fy[i], m); fz[i] = __ddiv_rn(fz[i], m);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// ghosts.  reference: update_ghosts_comm_scheme.cpp:403-481 (particle selection), update_ghost_functors.h:172-254 (pack)
+// A "send item" = (my inner cell, partner, partner ghost cell, boundary flags); the item list is static for a static
+// decomposition and is built on the host (xnb_ctx.cu); per rebuild the device selects particles.
+// ------------------------------------------------------------------------------------------------------------------
+struct GhostItemsP
+{
+  const uint32_t* src_cell;   // my cell
+  const uint32_t* flags;      // GhostBoundaryModifier flags
+  const uint32_t* partner;    // partner slot -> outer bounds
+  const double* outer;        // [n_partner_slots][6] partner inner bounds enlarged by ghost_dist (lo xyz, hi xyz)
+  int n_items;
+};
+
+XNB_DEVINL bool ghost_selected(const GridP& g, const double* __restrict__ ob, uint32_t fl, double x, double y, double z)
+{
+  const double gx = coord_shift(x, g.dmin[0], g.dmax[0], fl >> 0);
+  const double gy = coord_shift(y, g.dmin[1], g.dmax[1], fl >> 3);
+  const double gz = coord_shift(z, g.dmin[2], g.dmax[2], fl >> 6);
+  return gx >= ob[0] && gx <= ob[3] && gy >= ob[1] && gy <= ob[4] && gz >= ob[2] && gz <= ob[5];
+}
+
+// one warp per item: count selected particles
+__global__ void k_ghost_count(GridP g, GhostItemsP it, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+                              const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                              uint32_t* __restrict__ item_count)
+{
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= it.n_items) return;
+  const uint32_t c = it.src_cell[w], fl = it.flags[w];
+  const double* ob = it.outer + 6 * it.partner[w];
+  const uint32_t s0 = cell_start[c], n = cell_count[c];
+  uint32_t cnt = 0;
+  for (uint32_t p = lane; p < ((n + 31u) & ~31u); p += 32)
+  {
+    const bool sel = (p < n) && ghost_selected(g, ob, fl, rx[s0 + p], ry[s0 + p], rz[s0 + p]);
+    cnt += __popc(__ballot_sync(0xffffffffu, sel));
+  }
+  if (lane == 0) item_count[w] = cnt;
+}
+
+// one warp per item: write the selected particle indices (in-cell order preserved, update_ghosts_comm_scheme.cpp:462-470)
+__global__ void k_ghost_fill(GridP g, GhostItemsP it, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+                             const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                             const uint32_t* __restrict__ item_offset, uint32_t* __restrict__ send_src, uint16_t* __restrict__ send_flags)
+{
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= it.n_items) return;
+  const uint32_t c = it.src_cell[w], fl = it.flags[w];
+  const double* ob = it.outer + 6 * it.partner[w];
+  const uint32_t s0 = cell_start[c], n = cell_count[c];
+  uint32_t base = item_offset[w];
+  for (uint32_t p = lane; p < ((n + 31u) & ~31u); p += 32)
+  {
+    const bool sel = (p < n) && ghost_selected(g, ob, fl, rx[s0 + p], ry[s0 + p], rz[s0 + p]);
+    const unsigned m = __ballot_sync(0xffffffffu, sel);
+    if (sel) { const uint32_t k = base + __popc(m & ((1u << lane) - 1u)); send_src[k] = s0 + p; send_flags[k] = (uint16_t)fl; }
+    base += __popc(m);
+  }
+}
+
+// receive side: one warp per received item. Sets the ghost cell slice and the cell id of its particles.
+__global__ void k_ghost_cells(int n_items, const uint32_t* __restrict__ dst_cell, const uint32_t* __restrict__ recv_count,
+                              const uint32_t* __restrict__ recv_offset, uint32_t n_inner,
+                              uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ atom_cell)
+{
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_items) return;
+  const uint32_t c = dst_cell[w], n = recv_count[w], s0 = n_inner + recv_offset[w];
+  if (lane == 0 && n > 0) { cell_start[c] = s0; cell_count[c] = n; }
+  for (uint32_t p = lane; p < n; p += 32) atom_cell[s0 + p] = c;
+}
+
+// reset ghost cells to empty (migrate_cell_particles leaves them empty: mpi/migrate_cell_particles.cpp:101-110)
+__global__ void k_ghost_cells_clear(GridP g, uint32_t n_inner, uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_count)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.n_cells) return;
+  const int ci = c % g.dims[0], cj = (c / g.dims[0]) % g.dims[1], ck = c / (g.dims[0] * g.dims[1]);
+  const bool inner = ci >= g.gl && ci < g.dims[0] - g.gl && cj >= g.gl && cj < g.dims[1] - g.gl && ck >= g.gl && ck < g.dims[2] - g.gl;
+  if (!inner) { cell_start[c] = n_inner; cell_count[c] = 0; }
+}
+
+// pack: ghost g takes particle send_src[g] with the periodic shift applied (update_ghost_functors.h:41-67,172-217).
+// Sends to myself (periodic images, grid_update_ghosts.h:176-187) go straight into the ghost slots [self_dst ...);
+// the others go to the plane-major staging buffer handed to ncclSend.
+template <bool ALL_FIELDS>
+__global__ void k_ghost_pack(GridP g, int n_send, const uint32_t* __restrict__ send_src, const uint16_t* __restrict__ send_flags,
+                             ParticlesP p, int self_first, int self_end, uint32_t self_dst,
+                             double* __restrict__ stage /* planes of n_send doubles: x y z [vx vy vz fx fy fz id] */, uint8_t* __restrict__ stage_type)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_send) return;
+  const uint32_t s = send_src[q], fl = send_flags[q];
+  const double x = coord_shift(p.rx[s], g.dmin[0], g.dmax[0], fl >> 0);
+  const double y = coord_shift(p.ry[s], g.dmin[1], g.dmax[1], fl >> 3);
+  const double z = coord_shift(p.rz[s], g.dmin[2], g.dmax[2], fl >> 6);
+  if (q >= self_first && q < self_end)
+  {
+    const uint32_t d = self_dst + (uint32_t)(q - self_first);
+    p.rx[d] = x; p.ry[d] = y; p.rz[d] = z;
+    if (ALL_FIELDS)
+    {
+      p.vx[d] = p.vx[s]; p.vy[d] = p.vy[s]; p.vz[d] = p.vz[s];
+      p.fx[d] = p.fx[s]; p.fy[d] = p.fy[s]; p.fz[d] = p.fz[s];
+      p.id[d] = p.id[s]; p.type[d] = p.type[s];
+    }
+  }
+  else
+  {
+    const size_t n = (size_t)n_send;
+    stage[q] = x; stage[n + q] = y; stage[2 * n + q] = z;
+    if (ALL_FIELDS)
+    {
+      stage[3 * n + q] = p.vx[s]; stage[4 * n + q] = p.vy[s]; stage[5 * n + q] = p.vz[s];
+      stage[6 * n + q] = p.fx[s]; stage[7 * n + q] = p.fy[s]; stage[8 * n + q] = p.fz[s];
+      reinterpret_cast<unsigned long long*>(stage)[9 * n + q] = p.id[s];
+      stage_type[q] = p.type[s];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2 chunk neighbour build.  reference: chunk_neighbors_execute.h:110-411.
+// One thread per particle (ALL cells, ghost cells included, :110).  Neighbour cells are visited in ascending (k,j,i)
+// = ascending encoded cell id, particles in ascending p_b, so each particle's list comes out already sorted and unique:
+// the reference's per-particle std::sort + dedup (:308-324) is a no-op for this traversal.  The sub-cell pair cache of
+// the reference (amr_grid_pairs) only prunes candidates; the distance filter below decides membership.
+//   COUNT pass: nb_len[i] = 1 + 2*G + N (u16 words of the particle's list), nb_cnt[i] = N
+//   FILL  pass: writes the list and the particle's u32 offset-table entry
+// ------------------------------------------------------------------------------------------------------------------
+struct NbhOut
+{
+  uint32_t* nb_len;                    // per particle list length (u16 words)
+  uint32_t* nb_cnt;                    // per particle neighbour count
+  const uint32_t* nb_off;              // per particle offset of its list inside the cell's list area (u16 words)
+  uint16_t* const* cell_stream;        // per cell stream base pointer (device)
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_nbh_build(GridP g, int n_total, int gap, double max_dist2,
+            const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+            const uint32_t* __restrict__ atom_cell, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+            NbhOut out, uint32_t* __restrict__ err)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  const uint32_t ca = atom_cell[i];
+  const int ai = ca % g.dims[0], aj = (ca / g.dims[0]) % g.dims[1], ak = ca / (g.dims[0] * g.dims[1]);
+  const double xa = rx[i], ya = ry[i], za = rz[i];
+  uint16_t* w = nullptr;
+  if (FILL)
+  {
+    const uint32_t na = cell_count[ca], pa = (uint32_t)i - cell_start[ca];
+    uint16_t* base = out.cell_stream[ca];
+    const uint32_t off = out.nb_off[i];
+    // offset table entry: u16 index of the list relative to the first list, + number of tables (1)  (:279-283)
+    reinterpret_cast<uint32_t*>(base)[pa] = off + 1u;
+    if (pa == na - 1u) reinterpret_cast<uint32_t*>(base)[na] = off + out.nb_len[i] + 1u;   // closing entry (:390-398)
+    w = base + 2u * (na + 1u) + off;
+  }
+  uint32_t groups = 0, total = 0;
+  uint16_t* wg = w;            // position of the group counter
+  if (FILL) w++;
+  const int k0 = max(ak - gap, 0), k1 = min(ak + gap, g.dims[2] - 1);
+  const int j0 = max(aj - gap, 0), j1 = min(aj + gap, g.dims[1] - 1);
+  const int i0 = max(ai - gap, 0), i1 = min(ai + gap, g.dims[0] - 1);
+  for (int bk = k0; bk <= k1; bk++)
+    for (int bj = j0; bj <= j1; bj++)
+      for (int bi = i0; bi <= i1; bi++)
+      {
+        const int cb = ijk_to_index(g.dims, bi, bj, bk);
+        const uint32_t nb = cell_count[cb];
+        if (nb == 0) continue;
+        const uint32_t sb = cell_start[cb];
+        uint32_t cnt = 0;
+        uint16_t* wc = w;      // group header position (enc, n)
+        for (uint32_t pb = 0; pb < nb; pb++)
+        {
+          const uint32_t j = sb + pb;
+          // :225-227  dr = r_a - r_b ; d2 = |dr|^2 ; keep if not self, d2 > 0, d2 <= max_dist^2
+          const double d2 = norm2_exact(__dadd_rn(xa, -rx[j]), __dadd_rn(ya, -ry[j]), __dadd_rn(za, -rz[j]));
+          if (j != (uint32_t)i && d2 > 0.0 && d2 <= max_dist2)
+          {
+            if (FILL) wc[2 + cnt] = (uint16_t)pb;
+            cnt++;
+          }
+        }
+        if (cnt > 0)
+        {
+          if (FILL)
+          {
+            // encode_cell_index (chunk_neighbors.h:137-150)
+            wc[0] = (uint16_t)(((((bk - ak) + 16) << 5) + ((bj - aj) + 16)) << 5) + (uint16_t)((bi - ai) + 16);
+            wc[1] = (uint16_t)cnt;
+            w = wc + 2 + cnt;
+          }
+          if (cnt >= 65535u) atomicOr(err, DERR_GROUP_OVERFLOW);
+          groups++; total += cnt;
+        }
+      }
+  if (FILL) *wg = (uint16_t)groups;
+  else
+  {
+    if (groups >= 65535u) atomicOr(err, DERR_GROUP_OVERFLOW);
+    out.nb_len[i] = 1u + 2u * groups + total;
+    out.nb_cnt[i] = total;
+  }
+}
+
+// one warp per cell: in-cell exclusive offsets of the particle lists, the cell's stream size (u16 words, unpadded and
+// padded to 16 bytes) and the running maximum neighbour count (m_max_neighbors, chunk_neighbors_execute.h:403-406)
+__global__ void k_nbh_cell_sizes(int n_cells, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+                                 const uint32_t* __restrict__ nb_len, const uint32_t* __restrict__ nb_cnt, uint32_t* __restrict__ nb_off,
+                                 uint32_t* __restrict__ stream_size, uint32_t* __restrict__ stream_size_padded, uint32_t* __restrict__ max_nbh,
+                                 uint32_t* __restrict__ err)
+{
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= n_cells) return;
+  const uint32_t n = cell_count[c], s0 = cell_start[c];
+  if (n == 0) { if (lane == 0) { stream_size[c] = 0; stream_size_padded[c] = 0; } return; }
+  if (n > 65535u && lane == 0) atomicOr(err, DERR_CELL_OVERFLOW);
+  uint32_t run = 0, mx = 0;
+  for (uint32_t p0 = 0; p0 < n; p0 += 32)
+  {
+    const uint32_t p = p0 + lane;
+    const uint32_t v = (p < n) ? nb_len[s0 + p] : 0u;
+    if (p < n) mx = max(mx, nb_cnt[s0 + p]);
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (p < n) nb_off[s0 + p] = run + x - v;
+    run += __shfl_sync(0xffffffffu, x, 31);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0)
+  {
+    const uint32_t sz = 2u * (n + 1u) + run;
+    stream_size[c] = sz;
+    stream_size_padded[c] = (sz + 7u) & ~7u;
+    atomicMax(max_nbh, mx);
+  }
+}
+
+// per cell: stream pointer (nullptr for empty cells, chunk_neighbors_host_write_accessor.h:47-52) and size in BYTES
+__global__ void k_nbh_pointers(int n_cells, uint16_t* __restrict__ pool, const unsigned long long* __restrict__ stream_off,
+                               const uint32_t* __restrict__ stream_size, uint16_t** __restrict__ cell_stream, uint32_t* __restrict__ cell_stream_bytes)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  const uint32_t sz = stream_size[c];
+  cell_stream[c] = sz ? pool + stream_off[c] : nullptr;
+  cell_stream_bytes[c] = sz * 2u;
+  if (sz)
+  {
+    // zero the alignment padding so the pool content is deterministic
+    const uint32_t pad = ((sz + 7u) & ~7u) - sz;
+    for (uint32_t q = 0; q < pad; q++) pool[stream_off[c] + sz + q] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3 pair sweep with the Lennard-Jones functor.
+// reference: compute_cell_particle_pairs_impl_default.h:87-239 (stream decoding, d2 re-test against rcut^2),
+//            lennard_jones.cu:46-56,106-124 (functor).
+// One thread per particle of the swept range; the thread walks the particle's u16 list through the cell's u32 offset
+// table.  dr = r_b - r_a (:183); accept iff d2 > 0 && d2 <= rcut2 (:186) with d2 evaluated exactly like the oracle.
+// The functor is restated with one reciprocal instead of sqrt + two divisions:
+//   de/r = -24 eps (2 s12 - s6) / d2 ,  s6 = (sigma^2/d2)^3     (identical to lennard_jones.cu:46-56 up to rounding)
+// MODE 0: f += sum            (op lennard_jones_force, accumulating like the reference functor)
+// MODE 1: f  = sum / m[type]; v += f*dth   (zero_particle_force + lennard_jones_force + divide_force_by_type_scalar
+//                                           + verlet_second_half fused; dth = 0 leaves v untouched bit-for-bit)
+// EV: additionally accumulate per-block partial sums of energy and virial (oracle-defined observables)
+// ------------------------------------------------------------------------------------------------------------------
+struct LJP { double eps24; double sig2; double rcut2; double eps4; };
+
+template <int MODE, bool EV>
+__global__ void __launch_bounds__(128)
+k_lj_force(GridP g, int first, int n, int n_zero_end, LJP lj, double dth,
+           const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+           double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
+           double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+           const uint8_t* __restrict__ type, const double* __restrict__ mass,
+           const uint32_t* __restrict__ atom_cell, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+           const uint16_t* const* __restrict__ cell_stream, double* __restrict__ ev_partials /* [gridDim.x][7] */)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = first + t;
+  double ax = 0., ay = 0., az = 0.;
+  double e = 0., wxx = 0., wyy = 0., wzz = 0., wxy = 0., wxz = 0., wyz = 0.;
+  if (t < n)
+  {
+    const uint32_t ca = atom_cell[i];
+    const uint32_t na = cell_count[ca], pa = (uint32_t)i - cell_start[ca];
+    const uint16_t* base = cell_stream[ca];
+    const uint32_t off = reinterpret_cast<const uint32_t*>(base)[pa];
+    const uint16_t* s = base + 2u * (na + 1u) + (off - 1u);
+    const double xa = rx[i], ya = ry[i], za = rz[i];
+    const int di = g.dims[0], dj = g.dims[1];
+    int groups = *s++;
+    for (; groups > 0; --groups)
+    {
+      const uint32_t enc = *s++;
+      int cnt = *s++;
+      const int ri = (int)(enc & 31u) - 16, rj = (int)((enc >> 5) & 31u) - 16, rk = (int)((enc >> 10) & 31u) - 16;
+      const uint32_t sb = cell_start[(int)ca + (rk * dj + rj) * di + ri];
+      for (; cnt > 0; --cnt)
+      {
+        const uint32_t j = sb + *s++;
+        const double dx = __dadd_rn(rx[j], -xa), dy = __dadd_rn(ry[j], -ya), dz = __dadd_rn(rz[j], -za);
+        const double d2 = norm2_exact(dx, dy, dz);
+        if (d2 > 0.0 && d2 <= lj.rcut2)
+        {
+          const double inv = 1.0 / d2;
+          const double s2 = lj.sig2 * inv;
+          const double s6 = s2 * s2 * s2;
+          const double de = -lj.eps24 * (2.0 * s6 * s6 - s6) * inv;
+          ax += de * dx; ay += de * dy; az += de * dz;
+          if (EV)
+          {
+            e += 0.5 * lj.eps4 * (s6 * s6 - s6);
+            const double px = de * dx, py = de * dy, pz = de * dz;
+            wxx -= 0.5 * dx * px; wyy -= 0.5 * dy * py; wzz -= 0.5 * dz * pz;
+            wxy -= 0.5 * dx * py; wxz -= 0.5 * dx * pz; wyz -= 0.5 * dy * pz;
+          }
+        }
+      }
+    }
+    if (MODE == 0)
+    {
+      fx[i] += ax; fy[i] += ay; fz[i] += az;
+    }
+    else
+    {
+      const double m = mass[type[i]];
+      ax = __ddiv_rn(ax, m); ay = __ddiv_rn(ay, m); az = __ddiv_rn(az, m);
+      fx[i] = ax; fy[i] = ay; fz[i] = az;
+      if (dth != 0.0)
+      {
+        vx[i] = __dadd_rn(vx[i], __dmul_rn(ax, dth));
+        vy[i] = __dadd_rn(vy[i], __dmul_rn(ay, dth));
+        vz[i] = __dadd_rn(vz[i], __dmul_rn(az, dth));
+      }
+    }
+  }
+  else if (MODE == 1 && i < n_zero_end)
+  {
+    fx[i] = 0.; fy[i] = 0.; fz[i] = 0.;   // zero_particle_force{ghost:true}: ghost particles keep f = 0
+  }
+  if (EV)
+  {
+    __shared__ double red[7][4];
+    double vals[7] = {e, wxx, wyy, wzz, wxy, wxz, wyz};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 7; q++)
+    {
+      double v = vals[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[q][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7)
+    {
+      double v = 0.;
+      for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++) v += red[threadIdx.x][wq];
+      ev_partials[(size_t)blockIdx.x * 7 + threadIdx.x] = v;
+    }
+  }
+}
+
+// kinetic energy partial sums: sum 1/2 m v^2 per block
+__global__ void __launch_bounds__(256)
+k_ekin(int n, const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
+       const uint8_t* __restrict__ type, const double* __restrict__ mass, double* __restrict__ partials)
+{
+  __shared__ double red[8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.;
+  if (i < n) v = 0.5 * mass[type[i]] * (vx[i] * vx[i] + vy[i] * vy[i] + vz[i] * vz[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0.; for (int w = 0; w < 8; w++) s += red[w]; partials[blockIdx.x] = s; }
+}
+
+// FP64 FMA peak probe: 8 independent dependent-chains per thread
+__global__ void __launch_bounds__(256) k_dfma_probe(double* out, int iters, double a, double b)
+{
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int k = 0; k < iters; k++)
+  {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+} // namespace xnb
+
+// ------------------------------------------------------------------------------------------------------------------
+// migrate_cell_particles (multi-GPU hand-off of particles that left this rank's block).
+// reference: otb_particles of move_particles_across_cells.h:124-138 consumed by mpi/migrate_cell_particles.cpp:101-143.
+// ------------------------------------------------------------------------------------------------------------------
+namespace xnb {
+
+__global__ void k_migrate_dest(GridP g, int n_leave, const uint32_t* __restrict__ leave_list,
+                               const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                               const int* __restrict__ blocks /* nranks x 6 : start ijk, end ijk */, int nranks,
+                               uint32_t* __restrict__ dest_rank, uint32_t* __restrict__ dest_pos, uint32_t* __restrict__ dest_count,
+                               uint32_t* __restrict__ err)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_leave) return;
+  const uint32_t i = leave_list[q];
+  const int li = (int)floor(__ddiv_rn(__dadd_rn(rx[i], -g.dmin[0]), g.cs));
+  const int lj = (int)floor(__ddiv_rn(__dadd_rn(ry[i], -g.dmin[1]), g.cs));
+  const int lk = (int)floor(__ddiv_rn(__dadd_rn(rz[i], -g.dmin[2]), g.cs));
+  int owner = -1;
+  for (int r = 0; r < nranks; r++)
+  {
+    const int* b = blocks + 6 * r;
+    if (li >= b[0] && li < b[3] && lj >= b[1] && lj < b[4] && lk >= b[2] && lk < b[5]) { owner = r; break; }
+  }
+  if (owner < 0) { atomicOr(err, DERR_LOST_PARTICLE); dest_rank[q] = 0xFFFFFFFFu; dest_pos[q] = 0; return; }
+  dest_rank[q] = (uint32_t)owner;
+  dest_pos[q] = atomicAdd(&dest_count[owner], 1u);
+}
+
+// stage = 10 planes of n_leave 8-byte words (rx ry rz vx vy vz fx fy fz id) + one byte plane (type); slot = base[rank]+pos
+__global__ void k_migrate_pack(int n_leave, const uint32_t* __restrict__ leave_list, const uint32_t* __restrict__ dest_rank,
+                               const uint32_t* __restrict__ dest_pos, const uint32_t* __restrict__ dest_base, ParticlesP p,
+                               double* __restrict__ stage, uint8_t* __restrict__ stage_type)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_leave) return;
+  const uint32_t r = dest_rank[q];
+  if (r == 0xFFFFFFFFu) return;
+  const uint32_t i = leave_list[q];
+  const size_t n = (size_t)n_leave, k = (size_t)dest_base[r] + dest_pos[q];
+  stage[k] = p.rx[i]; stage[n + k] = p.ry[i]; stage[2 * n + k] = p.rz[i];
+  stage[3 * n + k] = p.vx[i]; stage[4 * n + k] = p.vy[i]; stage[5 * n + k] = p.vz[i];
+  stage[6 * n + k] = p.fx[i]; stage[7 * n + k] = p.fy[i]; stage[8 * n + k] = p.fz[i];
+  reinterpret_cast<unsigned long long*>(stage)[9 * n + k] = p.id[i];
+  stage_type[k] = p.type[i];
+}
+
+} // namespace xnb

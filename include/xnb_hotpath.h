@@ -1,0 +1,184 @@
+/*
+ * xnb_hotpath.h -- C-ABI of the B200-native exaNBody hot path (libxnb_hotpath.so).
+ *
+ * One xnb_ctx = one sub-domain on one GPU (the reference's "one MPI rank": a Grid + Domain + GridChunkNeighbors +
+ * AmrGrid + PositionBackupData + GhostCommunicationScheme living in operator slots).  The ctx owns every device
+ * buffer; callers borrow views.  All compute entry points enqueue hand-written sm_100a kernels on the caller's
+ * cudaStream_t (passed as void*, NULL = default stream) and do not synchronise unless stated.  There is NO CPU
+ * fallback: every entry point returns XNB_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Return value: 0 = ok, otherwise an XNB_ERR_* code; xnb_last_error() gives the message
+ * (the reference aborts through fatal_error(); the C++ shim in exanbody_b200/host maps non-zero to the same abort).
+ *
+ * Each entry point cites the reference operator / function it replaces (paths relative to the reference tree).
+ */
+#ifndef XNB_HOTPATH_H
+#define XNB_HOTPATH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XNB_OK 0
+#define XNB_ERR_NO_DEVICE 1
+#define XNB_ERR_INVALID 2
+#define XNB_ERR_CUDA 3
+#define XNB_ERR_CAPACITY 4     /* u16 stream limits: > 65535 atoms in a cell, neighbour cell offset beyond +-15 */
+#define XNB_ERR_LOST_PARTICLE 5 /* particle left a non-periodic domain (reference: otb_particles never re-homed) */
+#define XNB_ERR_NCCL 6
+
+typedef struct xnb_ctx xnb_ctx;
+
+/* ---- life cycle -------------------------------------------------------------------------------------------- */
+int  xnb_create(xnb_ctx** out, int cuda_device);        /* replaces onika init_cuda + slot construction          */
+void xnb_destroy(xnb_ctx* ctx);
+const char* xnb_last_error(const xnb_ctx* ctx);         /* ctx may be NULL: last error of a failed xnb_create     */
+const char* xnb_version(void);
+
+/* ---- configuration ----------------------------------------------------------------------------------------- */
+/* op `domain` : src/core/include/exanb/core/domain.h:36-129 (bounds, cell_size, grid_dims, periodic; identity xform) */
+int xnb_set_domain(xnb_ctx*, const double bounds_min[3], const double bounds_max[3], double cell_size,
+                   const int64_t grid_dims[3], const int32_t periodic[3]);
+/* op `init_rcb_grid` : src/grid_cell_particles/init_rcb_grid.cpp:37-84 + src/core/lib/simple_block_rcb.cpp:27-59.
+   Chooses this rank's block of domain cells by recursive bisection; nranks == 1 => whole domain.                */
+int xnb_init_rcb_grid(xnb_ctx*, int rank, int nranks);
+/* op `nbh_dist` : src/particle_neighbors/nbh_dist.cpp:47-71.  nbh_dist = rcut_max + rcut_inc, max_displ = rcut_inc/2,
+   ghost_dist = rcut_max + rcut_inc (identity xform).                                                            */
+int xnb_set_nbh_dist(xnb_ctx*, double rcut_max, double rcut_inc);
+/* per-type scalar `mass` used by divide_force_by_type_scalar: src/compute/vec3_typescalar_op.cu:71-122          */
+int xnb_set_type_mass(xnb_ctx*, const double* mass_per_type, int n_types);
+/* rebuild_amr sub_grid_density (data/config/update-particles.msp:9), default 6.5                                */
+int xnb_set_sub_grid_density(xnb_ctx*, double density);
+/* attach an NCCL communicator (ncclComm_t) for the multi-GPU halo; NULL = single GPU                            */
+int xnb_set_nccl_comm(xnb_ctx*, void* nccl_comm);
+/* ncclGetUniqueId / ncclCommInitRank through the NCCL already loaded in the process (128-byte id)               */
+int xnb_nccl_unique_id(uint8_t id_out[128]);
+int xnb_nccl_init_rank(xnb_ctx*, const uint8_t id[128], int rank, int nranks);
+
+/* ---- particles in / out (HOST pointers; id/type may be NULL) ----------------------------------------------- */
+/* replaces filling Grid cells (src/core/include/exanb/core/grid.h:57-688).  Particles may be in any order and
+   anywhere in the domain: only those located in this rank's block are kept (as `lattice` does,
+   generate_particle_lattice.h:289-321).  Synchronous.                                                           */
+int xnb_set_particles(xnb_ctx*, int64_t n, const double* rx, const double* ry, const double* rz,
+                      const double* vx, const double* vy, const double* vz, const uint64_t* id, const uint8_t* type);
+int64_t xnb_num_inner(const xnb_ctx*);     /* particles of inner cells                                           */
+int64_t xnb_num_total(const xnb_ctx*);     /* inner + ghost                                                      */
+/* flat copy-out in device order [0,n_inner) inner particles sorted by cell, [n_inner,n_total) ghosts. Synchronous */
+int xnb_get_particles(xnb_ctx*, int64_t first, int64_t n, double* rx, double* ry, double* rz,
+                      double* vx, double* vy, double* vz, double* fx, double* fy, double* fz,
+                      uint64_t* id, uint8_t* type, uint32_t* cell);
+/* end-to-end helper: async H2D of r,v for the inner particles in current device order (pinned host memory)      */
+int xnb_upload_rv(xnb_ctx*, const double* rx, const double* ry, const double* rz,
+                  const double* vx, const double* vy, const double* vz, void* stream);
+int xnb_download_rvf(xnb_ctx*, double* rx, double* ry, double* rz, double* vx, double* vy, double* vz,
+                     double* fx, double* fy, double* fz, uint64_t* id, void* stream);
+
+/* ---- grid description ------------------------------------------------------------------------------------- */
+typedef struct xnb_grid_info
+{
+  int64_t dims[3];        /* local grid incl. ghost layers (Grid::dimension)      */
+  int64_t offset[3];      /* Grid::offset : location of local cell (0,0,0) in the domain grid */
+  int64_t ghost_layers;   /* Grid::ghost_layers, grid.h:110                        */
+  int64_t n_cells;
+  int64_t block_start[3]; /* inner block in domain cells                           */
+  int64_t block_end[3];
+} xnb_grid_info;
+int xnb_get_grid_info(const xnb_ctx*, xnb_grid_info* out);
+/* per-cell particle count and start index into the flat arrays (the per-cell SoA views of CellParticles)        */
+int xnb_get_cells(xnb_ctx*, uint32_t* cell_start /* n_cells */, uint32_t* cell_count /* n_cells */);
+
+/* ---- operators of the hot path (asynchronous on `stream`) --------------------------------------------------- */
+/* op `move_particles` : src/grid_cell_particles/include/exanb/grid_cell_particles/move_particles_across_cells.h:78-235
+   periodic wrap + cell location + re-binning of all inner particles (K1).  Multi-GPU: also performs the
+   `migrate_cell_particles` hand-off of particles that left the block (src/mpi/migrate_cell_particles.cpp:101-143). */
+int xnb_move_particles(xnb_ctx*, void* stream);
+/* op `rebuild_amr` : src/amr/rebuild_amr.cpp:35-62, amr_grid_algorithm.h:66-78,112-434 (in-cell sub-grid sort + tables) */
+int xnb_rebuild_amr(xnb_ctx*, void* stream);
+/* op `backup_r` : src/io/backup_r.cpp:36-78, src/core/include/exanb/core/backup_r.h:31-51                       */
+int xnb_backup_r(xnb_ctx*, void* stream);
+/* op `ghost_comm_scheme` : src/mpi/update_ghosts_comm_scheme.cpp:84-489 (who sends which particles of which cell) */
+int xnb_ghost_comm_scheme(xnb_ctx*, void* stream);
+/* ops `ghost_update_all` / `ghost_update_r` : src/mpi/update_ghosts.cu:45-64, include/exanb/mpi/grid_update_ghosts.h:63-202 */
+int xnb_ghost_update_all(xnb_ctx*, void* stream);
+int xnb_ghost_update_r(xnb_ctx*, void* stream);
+/* ops `amr_grid_pairs` + `chunk_neighbors` : src/particle_neighbors/chunk_neighbors.cpp:48-74,
+   include/exanb/particle_neighbors/chunk_neighbors_execute.h:40-423 (K2).  Config = build_particle_offset, chunk 1. */
+int xnb_chunk_neighbors(xnb_ctx*, void* stream);
+/* op `zero_particle_force` : src/compute/zero_particle_force.cu:15-53                                           */
+int xnb_zero_particle_force(xnb_ctx*, int ghost, void* stream);
+/* op `lennard_jones_force` : contribs/md/lennard_jones/lennard_jones.cu:171-215 through
+   compute_cell_particle_pairs (src/compute/include/exanb/compute/compute_cell_particle_pairs.h:122-189).
+   ACCUMULATES into fx,fy,fz like the reference (call xnb_zero_particle_force first).                            */
+int xnb_lennard_jones_force(xnb_ctx*, double epsilon, double sigma, double rcut, int ghost, void* stream);
+/* op `divide_force_by_type_scalar: mass` : src/compute/vec3_typescalar_op.cu:118-122                            */
+int xnb_divide_force_by_mass(xnb_ctx*, void* stream);
+/* ops `push_f_v_r` / `push_f_v` : src/defbox/include/exanb/defbox/push_vec3_2nd_order.h:29-118, push_vec3_1st_order.h:29-107 */
+int xnb_push_f_v_r(xnb_ctx*, double dt, double dt_scale, void* stream);
+int xnb_push_f_v(xnb_ctx*, double dt, double dt_scale, void* stream);
+/* op `particle_displ_over` : src/mpi/particle_displ_over.cu:39-178.  Synchronises; *count_out = global count
+   (all ranks) of particles displaced >= max_displ since backup_r.                                               */
+int xnb_particle_displ_over(xnb_ctx*, uint64_t* count_out, void* stream);
+
+/* ---- fused forms (same results, fewer HBM passes) ---------------------------------------------------------- */
+/* verlet_first_half + trigger_move_particles (numerical-scheme.msp:13-15, update-particles.msp:1-6) in one kernel (K4);
+   the displacement count stays on the device until xnb_read_displ_over().                                       */
+int xnb_verlet_first_half(xnb_ctx*, double dt, void* stream);
+int xnb_read_displ_over(xnb_ctx*, uint64_t* count_out, void* stream);
+/* compute_all_forces_energy of the LJ deck (input_lj_Ni.msp:88-92) + verlet_second_half in one kernel (K3):
+   f = LJ(r) (written, not accumulated), a = f/m[type], v += a*dt/2.  dt_half_kick = 0 skips the kick.           */
+int xnb_force_and_second_half(xnb_ctx*, double epsilon, double sigma, double rcut, double dt_half_kick, void* stream);
+/* whole `numerical_scheme` loop (numerical-scheme.msp:21-25 + check_and_update_particles): nsteps iterations.
+   Synchronises once per step to read the rebuild trigger (the reference does an MPI_Allreduce there).           */
+int xnb_run_steps(xnb_ctx*, int nsteps, double dt, double epsilon, double sigma, double rcut, void* stream, int* rebuilds_out);
+/* init_particles + first force (update-particles.msp:55-60, compute-loop.msp:1-7)                               */
+int xnb_first_iteration(xnb_ctx*, double epsilon, double sigma, double rcut, void* stream);
+
+/* ---- oracle-defined observables (unpinned by the reference) ---------------------------------- */
+/* E = 1/2 sum_ij e_ij (un-shifted lj_compute_energy, lennard_jones.cu:46-56), W = -1/2 sum dr (x) f, inner atoms;
+   ekin = sum 1/2 m v^2.  Synchronous, local to this rank.                                                       */
+int xnb_energy_virial(xnb_ctx*, double epsilon, double sigma, double rcut, double* epot, double virial[6], double* ekin, void* stream);
+
+/* ---- views / downloads of derived data -------------------------------------------------------------------- */
+/* GridChunkNeighbors (src/particle_neighbors/include/exanb/particle_neighbors/chunk_neighbors.h:40-120):
+   device array of per-cell stream pointers (= GridChunkNeighborsData) and per-cell sizes in BYTES.              */
+int xnb_view_chunk_neighbors(xnb_ctx*, const uint16_t* const** d_cell_stream, const uint32_t** d_cell_stream_size,
+                             uint32_t* max_neighbors);
+int64_t xnb_stream_pool_u16(const xnb_ctx*);    /* total u16 words in use (incl. 16-byte alignment padding)      */
+/* host copy: per-cell size in u16 (without padding) and the streams concatenated in cell order. Synchronous.    */
+int xnb_get_streams(xnb_ctx*, uint32_t* size_u16 /* n_cells */, uint16_t* data /* sum(size) or NULL */);
+/* AmrGrid tables (src/amr/include/exanb/amr/amr_grid.h:31-61) */
+int64_t xnb_get_amr(xnb_ctx*, int64_t* sub_grid_start /* n_cells+1 or NULL */, uint32_t* sub_grid_cells /* or NULL */);
+/* PositionBackupData: 3 x u32 per inner particle in flat order */
+int xnb_get_backup(xnb_ctx*, uint32_t* out /* 3*n_inner */);
+/* counters */
+int64_t xnb_rebuild_count(const xnb_ctx*);
+int64_t xnb_kernel_launches(const xnb_ctx*);    /* number of kernels this ctx has launched so far                */
+/* device time of the force kernel launches since the last reset (CUDA events on the launching stream)           */
+int xnb_timing_enable(xnb_ctx*, int on);
+int xnb_timing_read(xnb_ctx*, double* force_ms, int64_t* force_launches, double* nbh_ms, int64_t* nbh_launches, int reset);
+
+/* ---- host-side input operators of the LJ decks (not on the timed path) ------------------------------------ */
+/* ops `lattice` (structure FCC) + `gaussian_noise_r` with deterministic_noise:
+   src/grid_cell_particles/include/exanb/grid_cell_particles/generate_particle_lattice.h:247-388,
+   src/compute/include/exanb/compute/gaussian_noise.h:61-80,150-161.  vel_sigma / spheres are the synthetic-config
+   extensions of SURVEY.md 8d.  Returns the particle count (negative = capacity too small), domain-cell order, ids from 1. */
+typedef struct xnb_lattice_cfg
+{
+  double bounds_min[3], bounds_max[3], cell_size;
+  int64_t grid_dims[3];
+  double lattice_a, noise_sigma, vel_sigma;
+  int32_t n_spheres; double sphere_rmin, sphere_rmax, drift_speed;
+} xnb_lattice_cfg;
+int64_t xnb_host_lattice_fcc(const xnb_lattice_cfg* cfg, int64_t capacity, double* rx, double* ry, double* rz,
+                             double* vx, double* vy, double* vz, uint64_t* id, uint8_t* type);
+
+/* stand-alone FP64 FMA peak probe (DFMA/s) used for the FP64 roofline denominator                               */
+int xnb_measure_dfma_peak(int cuda_device, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

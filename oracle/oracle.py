@@ -43,7 +43,7 @@ def lib():
         L.xo_create.restype = P; L.xo_create.argtypes = [C.POINTER(XoConfig)]
         L.xo_destroy.argtypes = [P]
         L.xo_last_error.restype = C.c_char_p
-        for f in ("xo_init", "xo_move_particles", "xo_update_particles_full", "xo_ghost_update_r", "xo_build_neighbors",
+        for f in ("xo_init", "xo_generate", "xo_first_iteration", "xo_move_particles", "xo_update_particles_full", "xo_ghost_update_r", "xo_build_neighbors",
                   "xo_compute_force", "xo_push_f_v_r", "xo_check_streams"):
             getattr(L, f).argtypes = [P]; getattr(L, f).restype = C.c_int
         L.xo_run.argtypes = [P, C.c_int]; L.xo_run.restype = C.c_int
@@ -102,6 +102,8 @@ class Oracle:
             raise RuntimeError("oracle: " + self.L.xo_last_error().decode())
 
     def init(self): self._chk(self.L.xo_init(self.h))
+    def generate(self): self._chk(self.L.xo_generate(self.h))
+    def first_iteration(self): self._chk(self.L.xo_first_iteration(self.h))
 
     def run(self, n):
         r = self.L.xo_run(self.h, n)

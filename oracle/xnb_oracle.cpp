@@ -910,15 +910,27 @@ xo_sim* xo_create(const xo_config* cfg)
 }
 void xo_destroy(xo_sim* s) { delete s; }
 
-int xo_init(xo_sim* s)
+/* input_data of the deck: lattice + gaussian_noise_r (+ synthetic velocities) */
+int xo_generate(xo_sim* s)
 {
   lattice_fcc(*s);
   if (s->cfg.noise_sigma > 0.) gaussian_noise(*s, s->cfg.noise_sigma, false, 0);
   if (s->cfg.vel_sigma > 0.) { gaussian_noise(*s, s->cfg.vel_sigma, true, 1); zero_momentum(*s); }
-  /* init_particles (update-particles.msp:55-60) then first force (compute-loop.msp:1-7) */
+  return 0;
+}
+
+/* init_particles (update-particles.msp:55-60) then first force (compute-loop.msp:1-7) */
+int xo_first_iteration(xo_sim* s)
+{
   if (move_particles(*s)) return 1;
   if (update_particles_full(*s)) return 1;
   return compute_force(*s, nullptr, nullptr);
+}
+
+int xo_init(xo_sim* s)
+{
+  if (xo_generate(s)) return 1;
+  return xo_first_iteration(s);
 }
 
 int xo_run(xo_sim* s, int nsteps)

@@ -57,7 +57,9 @@ void    xo_destroy(xo_sim*);
 const char* xo_last_error(void);
 
 /* input_data + init_particles + first force (main-config.msp:33-49, compute-loop.msp:1-7) */
-int xo_init(xo_sim*);
+int xo_init(xo_sim*);              /* = xo_generate + xo_first_iteration */
+int xo_generate(xo_sim*);          /* lattice + gaussian_noise_r (+ synthetic velocities); grid without ghost layers */
+int xo_first_iteration(xo_sim*);   /* move_particles + parallel_update_particles + first force */
 /* n iterations of numerical_scheme (numerical-scheme.msp:21-25); returns #rebuilds done */
 int xo_run(xo_sim*, int nsteps);
 

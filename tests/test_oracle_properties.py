@@ -1,0 +1,71 @@
+"""Oracle self-checks on CPU: restated reference invariants (verify_chunk_neighbors.cpp:89-130,
+chunk_neighbors_stream_check.h:52-99, debug_total_force.cpp:51-93) and physics properties, on every test configuration."""
+import numpy as np
+import pytest
+
+from conftest import ni_deck_kwargs, lj_reduced_kwargs
+from oracle import oracle as O
+
+CASES = {
+    "ni2": ni_deck_kwargs(cells=2),
+    "lj2k": lj_reduced_kwargs(ncell_units=8, cell_units=2),
+    "lj_gap2": lj_reduced_kwargs(ncell_units=6, cell_units=1),
+    "lj_voids": lj_reduced_kwargs(ncell_units=12, cell_units=2, n_spheres=5, sphere_rmin=2.5, sphere_rmax=5.0, drift_speed=1.0),
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_streams_and_pairs(case):
+    o = O.Oracle(O.make_config(**CASES[case]))
+    o.init()
+    rc, msg = o.check_streams()
+    assert rc == 0, msg
+    pairs = o.pairs()
+    # the full (non symmetric) list is symmetric as a set: (a,b) listed <=> (b,a) listed
+    fwd = set(map(tuple, pairs.tolist())); assert len(fwd) == len(pairs)
+    assert all((b, a) in fwd for a, b in fwd)
+    # brute force reference on ids: minimum-image distance <= rc + skin (no particle sits within 1 ulp of the radius here)
+    p = o.particles(); m = o.inner_mask()
+    kw = CASES[case]
+    L = np.array(kw["bounds_max"]); r = np.stack([p["rx"][m], p["ry"][m], p["rz"][m]], 1); ids = p["id"][m]
+    if len(ids) <= 3000:
+        d = r[:, None, :] - r[None, :, :]; d -= L * np.round(d / L)
+        d2 = (d ** 2).sum(-1)
+        nd = kw["rcut"] + kw["rcut_inc"]
+        ia, ib = np.nonzero((d2 <= nd * nd) & (d2 > 0))
+        brute = set(zip(ids[ia].tolist(), ids[ib].tolist()))
+        assert brute == fwd
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_total_force_and_energy_conservation(case):
+    kw = CASES[case]
+    o = O.Oracle(O.make_config(**kw))
+    o.init()
+    p = o.particles(); m = o.inner_mask()
+    f = np.stack([p["fx"][m], p["fy"][m], p["fz"][m]], 1)
+    assert np.abs(f.sum(0)).max() <= 1e-11 * max(np.abs(f).sum(), 1.0)
+    e0, w0, k0 = o.energy_virial()
+    o.run(40)
+    e1, w1, k1 = o.energy_virial()
+    # velocity-Verlet: total energy drifts only through the unshifted cut-off and dt^2 errors
+    assert abs((e1 + k1) - (e0 + k0)) <= 2e-3 * max(abs(e0), abs(k0), 1.0)
+    p = o.particles(); m = o.inner_mask()
+    mom = np.stack([p["vx"][m], p["vy"][m], p["vz"][m]], 1).sum(0)
+    assert np.abs(mom).max() <= 1e-9 * max(1.0, np.abs(p["vx"][m]).sum())
+
+
+def test_backup_codec_roundtrip():
+    """encode_double_u32 / restore_u32_double (core/backup_r.h:31-51): |restore(encode(x)) - x| <= cell/2^33"""
+    kw = CASES["lj2k"]
+    o = O.Oracle(O.make_config(**kw)); o.init()
+    gi = o.grid_info(); d = gi["dims"]; gl = gi["ghost_layers"]; cs = kw["cell_size"]
+    p = o.particles(); m = o.inner_mask(); cnt = o.cell_counts()
+    cell = np.repeat(np.arange(len(cnt)), cnt)[m]
+    ci = cell % d[0]; cj = (cell // d[0]) % d[1]; ck = cell // (d[0] * d[1])
+    b = o.backup().reshape(-1, 3)
+    for ax, (c, name) in enumerate(((ci, "rx"), (cj, "ry"), (ck, "rz"))):
+        org = (gi["offset"][ax] + c) * cs
+        back = org + b[:, ax].astype(np.float64) * cs / 2.0 ** 32
+        assert np.abs(back - p[name][m]).max() <= cs / 2.0 ** 33 * 1.0001
+    assert o.displ_over() == 0
