@@ -69,8 +69,8 @@ def vec(p, names):
 
 def decode_pairs(counts, ids, sizes, data, dims, inner_cells):
     """pure-python decoder of GridChunkNeighbors streams (cell-ordered) into a sorted (id_a,id_b) array; small cases only"""
-    cstart = np.concatenate([[0], np.cumsum(counts)])
-    sstart = np.concatenate([[0], np.cumsum(sizes)])
+    cstart = np.concatenate([[0], np.cumsum(np.asarray(counts, np.int64))])
+    sstart = np.concatenate([[0], np.cumsum(np.asarray(sizes, np.int64))])
     out = []
     di, dj = int(dims[0]), int(dims[1])
     for ca in inner_cells:
