@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- atom-timesteps/s of the LJ hot path (binning + chunk neighbour build + ghost update + force + integrate).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload auto|C1|C2|C3|C4|C5]
+
+One "step" = one MD time step (numerical_scheme of data/config/numerical-scheme.msp:21-25) of the named workload, neighbour
+rebuilds included whenever the displacement trigger fires.  N=1 runs C2 (2 048 000 atoms); N>1 runs C3 (4 000 000 atoms per
+GPU, spatial decomposition, NCCL halo) under torchrun.  Prints ONE JSON line (rank 0).
+
+  value     device-resident rate: atoms(all ranks) * K / max-over-ranks CUDA-event time of the K steps
+  e2e       the same steps driven through the C-ABI with HOST buffers: every step uploads r,v from pinned host memory,
+            runs the step and downloads r,v,f (+ids) -- copies inside the timed region
+  roofline  the dominant kernel (pair sweep k_lj_force): algorithmic bytes per launch / its mean CUDA-event duration
+  cpu_baseline  the CPU oracle (oracle/, the OpenMP restatement of the reference) on a bounded sample of the same workload
+
+--impl reference times the reference's CPU implementation of the path.  The reference itself cannot be built here (it needs
+onika, yaml-cpp and MPI, none of which is in the image: DESIGN.md), so that arm is the oracle port with every host thread.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+A_FCC = (4.0 / 0.8442) ** (1.0 / 3.0)      # rho* = 0.8442
+
+
+def workload(name, nranks=1):
+    """SURVEY.md 8(d) restated as concrete inputs (reduced LJ units except C1)."""
+    def lj(units, cell_units=2, rcut=2.5, skin=0.3, noise=0.02, vel_sigma=1.2, **kw):
+        units = tuple(units) if isinstance(units, (tuple, list)) else (units,) * 3
+        d = dict(bounds_max=tuple(A_FCC * u for u in units), cell_size=A_FCC * cell_units, grid_dims=tuple(u // cell_units for u in units),
+                 lattice_a=A_FCC, epsilon=1.0, sigma=1.0, rcut=rcut, rcut_inc=skin, dt=0.005, mass=1.0, noise_sigma=noise,
+                 vel_sigma=vel_sigma, max_neighbors=1024)
+        d.update(kw)
+        return d
+    if name == "C1":
+        ev = 1.6021892e-19 / (1.66053904e-27 * 1e-20 / 1e-24)
+        return dict(bounds_max=(139.2,) * 3, cell_size=13.92, grid_dims=(10,) * 3, lattice_a=3.48, epsilon=0.3729 * ev, sigma=2.2808,
+                    rcut=2.5 * 2.2808, rcut_inc=2.0, dt=2e-3, mass=58.693, noise_sigma=0.05, vel_sigma=0.0, max_neighbors=1024), \
+            "C1: Ni LJ FCC 40^3 unit cells (256000 atoms), rc=2.5 sigma, skin 2.0 A"
+    if name == "C2":
+        return lj(80), "C2: LJ FCC 80^3 unit cells = 2048000 atoms fp64, rc=2.5, skin=0.3, dt=0.005, T*=1.44 (binning + chunk neighbour build + force + integrate)"
+    if name == "C3":
+        mult = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[nranks]
+        return lj(tuple(100 * m for m in mult)), "C3: LJ FCC weak scaling, 100^3 unit cells = 4000000 atoms per GPU, rc=2.5, skin=0.3, RCB blocks %dx%dx%d, NCCL halo" % mult
+    if name == "C4":
+        return lj(48, cell_units=4, rcut=5.0, noise=0.1), "C4: dense LJ rc=5 sigma, 48^3 unit cells = 442368 atoms, cell = 4a"
+    if name == "C5":
+        return lj(80, n_spheres=64, sphere_rmin=6.0, sphere_rmax=14.0, drift_speed=2.0), "C5: clusters + voids in an 80^3 unit cell box"
+    raise SystemExit("unknown workload " + name)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def make_oracle_config(kw):
+    from oracle import oracle as O
+    return O.make_config(**kw)
+
+
+def run_cpu_oracle(kw, nsteps, budget_s):
+    """the CPU oracle on the same workload: init untimed, then up to nsteps steps (stops early when budget_s is spent)."""
+    from oracle import oracle as O
+    o = O.Oracle(make_oracle_config(kw))
+    o.generate(); o.first_iteration()
+    n = o.n_inner()
+    done, rebuilds, t0 = 0, 0, time.perf_counter()
+    chunk = 1
+    while done < nsteps:
+        k = min(chunk, nsteps - done)
+        rebuilds += o.run(k); done += k
+        el = time.perf_counter() - t0
+        if el > budget_s:
+            break
+    el = time.perf_counter() - t0
+    o.close()
+    return dict(atoms=n, steps=done, seconds=el, rebuilds=rebuilds, rate=n * done / el, threads=O.num_threads())
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    name = args.workload if args.workload != "auto" else ("C2" if args.gpus == 1 else "C3")
+    kw, desc = workload(name, args.gpus)
+    # warmup steps are part of the bounded budget; the oracle is deterministic so they only warm caches
+    budget = float(os.environ.get("XNB_REF_BUDGET_S", "150"))
+    r = run_cpu_oracle(kw, args.steps, budget)
+    line = {
+        "impl": "reference", "metric": "atom-timesteps/s (LJ neighbor+force+ghost)", "value": r["rate"], "unit": "atom-timesteps/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": 0, "ms_per_step": 1e3 * r["seconds"] / max(r["steps"], 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "atoms": r["atoms"], "rebuilds": r["rebuilds"], "l2": "inputs larger than L2"},
+        "cpu_baseline": {"value": r["rate"], "unit": "atom-timesteps/s", "cores": r["threads"], "kind": "port",
+                         "sample": "CPU oracle (OpenMP restatement of the reference; the reference needs onika/yaml-cpp/MPI and cannot be built), "
+                                   "%d steps of the full workload after untimed init, %d rebuilds" % (r["steps"], r["rebuilds"])},
+        "e2e": {"value": r["rate"], "unit": "atom-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def b200_arm(args):
+    import torch
+    from exanbody_b200 import capi
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    name = args.workload if args.workload != "auto" else ("C2" if world == 1 else "C3")
+    kw, desc = workload(name, world)
+    eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
+
+    ctx = capi.Context(local)
+    ctx.set_domain((0., 0., 0.), kw["bounds_max"], kw["cell_size"], kw["grid_dims"], (1, 1, 1))
+    ctx.init_rcb_grid(rank, world)
+    ctx.set_nbh_dist(rc, kw["rcut_inc"])
+    ctx.set_type_mass([kw["mass"]])
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.from_numpy(ctx.nccl_unique_id().copy())
+        uid = uid.cuda(); dist.broadcast(uid, 0); ctx.nccl_init_rank(uid.cpu().numpy(), rank, world)
+    gi = ctx.grid_info()
+    inp = capi.lattice_fcc(kw["bounds_max"], kw["cell_size"], kw["grid_dims"], kw["lattice_a"], noise_sigma=kw["noise_sigma"], vel_sigma=kw["vel_sigma"],
+                           n_spheres=kw.get("n_spheres", 0), sphere_rmin=kw.get("sphere_rmin", 0.), sphere_rmax=kw.get("sphere_rmax", 0.),
+                           drift_speed=kw.get("drift_speed", 0.))      # whole domain; xnb_set_particles keeps this rank's block
+    ctx.set_particles(inp["rx"], inp["ry"], inp["rz"], inp["vx"], inp["vy"], inp["vz"], inp["id"], inp["type"])
+    del inp
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ctx.first_iteration(eps, sig, rc, sh)
+    n_atoms_local = ctx.n_inner
+    n_atoms = int(round(sum_over_ranks(float(n_atoms_local))))
+
+    # ---- device-resident rate ---------------------------------------------------------------------------------------
+    ctx.run_steps(args.warmup, dt, eps, sig, rc, sh)
+    ctx.timing_enable(True); ctx.timing_read(reset=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    l0 = ctx.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    rebuilds = ctx.run_steps(args.steps, dt, eps, sig, rc, sh)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.kernel_launches() - l0
+    tim = ctx.timing_read(reset=True)
+    ctx.timing_enable(False)
+    n_atoms_after = int(round(sum_over_ranks(float(ctx.n_inner))))
+    assert n_atoms_after == n_atoms, "atoms lost: %d -> %d" % (n_atoms, n_atoms_after)
+    value = n_atoms * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (pair sweep) -----------------------------------------------------------------
+    sz = ctx.stream_sizes()
+    d, gl = gi["dims"], gi["ghost_layers"]
+    k, j, i = np.meshgrid(np.arange(d[2]), np.arange(d[1]), np.arange(d[0]), indexing="ij")
+    inner = ((i >= gl) & (i < d[0] - gl) & (j >= gl) & (j < d[1] - gl) & (k >= gl) & (k < d[2] - gl)).ravel()
+    S = 2.0 * float(sz[inner].sum()) / max(n_atoms_local, 1)          # stream bytes per inner atom (reference u16 format)
+    force_bytes = 97.0 + S                                            # R r 24 + R stream S + W f 24 + R v 24 + R type 1 + W v 24
+    step_bytes = 253.0 + S                                            # minimal fused traffic of a steady step
+    peak, peak_src = measured_peaks()
+    fk_ms = tim["force"]["ms"] / max(tim["force"]["n"], 1)
+    achieved = force_bytes * n_atoms_local / (fk_ms * 1e-3) / 1e9 if fk_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_lj_force (pair sweep + fused second half kick)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic("k_lj_force"), "peak_source": peak_src,
+                "algorithmic_bytes_per_atom": force_bytes, "stream_bytes_per_atom": S, "kernel_ms": fk_ms,
+                "whole_step": {"algorithmic_bytes_per_atom": step_bytes, "achieved": step_bytes * value / world / 1e9, "frac": step_bytes * value / world / 1e9 / peak}}
+    breakdown = {k2: (v["ms"] / args.steps) for k2, v in tim.items()}
+
+    # ---- end to end through the C-ABI with host buffers -----------------------------------------------------------------
+    n = ctx.n_inner
+    hb = {k2: torch.empty(n, dtype=torch.float64).pin_memory() for k2 in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz")}
+    hid = torch.empty(n, dtype=torch.int64).pin_memory()
+    ptr = {k2: v.data_ptr() for k2, v in hb.items()}
+    ctx.download_rvf(ptr["rx"], ptr["ry"], ptr["rz"], ptr["vx"], ptr["vy"], ptr["vz"], ptr["fx"], ptr["fy"], ptr["fz"], hid.data_ptr(), sh)
+
+    def e2e_step():
+        ctx.upload_rv(ptr["rx"], ptr["ry"], ptr["rz"], ptr["vx"], ptr["vy"], ptr["vz"], sh)
+        ctx.run_steps(1, dt, eps, sig, rc, sh)
+        assert ctx.n_inner == n or world > 1
+        ctx.download_rvf(ptr["rx"], ptr["ry"], ptr["rz"], ptr["vx"], ptr["vy"], ptr["vz"], ptr["fx"], ptr["fy"], ptr["fz"], hid.data_ptr(), sh)
+
+    e2e = None
+    if world == 1:       # with several ranks atoms migrate between ranks, so host buffers change size: e2e is defined at N=1
+        e2e_steps = max(3, min(args.steps, 20))
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+        ems = e0.elapsed_time(e1)
+        e2e = {"value": n_atoms * e2e_steps / (ems * 1e-3), "unit": "atom-timesteps/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 80 * n,
+               "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
+               "what": "per step: xnb_upload_rv (r,v from pinned host) + xnb_run_steps(1) + xnb_download_rvf (r,v,f,id to pinned host)"}
+
+    # ---- CPU baseline (bounded sample, rank 0, N=1 only) ----------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_cpu_oracle(kw, 20, float(os.environ.get("XNB_CPU_BUDGET_S", "25")))
+        cpu = {"value": r["rate"], "unit": "atom-timesteps/s", "cores": r["threads"], "kind": "port",
+               "sample": "CPU oracle (OpenMP port of the reference path), same %d-atom input, %d steps (%d rebuilds) after untimed init" % (r["atoms"], r["steps"], r["rebuilds"])}
+
+    if rank == 0:
+        try:
+            dfma = capi.measure_dfma_peak(local)
+        except Exception:
+            dfma = None
+        line = {
+            "metric": "atom-timesteps/s (LJ neighbor+force+ghost)", "value": value, "unit": "atom-timesteps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "atoms": n_atoms, "rebuilds": rebuilds, "l2": "inputs larger than L2 (state + neighbour streams >> 126 MB), no flush",
+                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "breakdown_ms_per_step": breakdown, "fp64_dfma_peak_tflops": dfma,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+    return b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

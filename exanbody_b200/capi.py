@@ -79,7 +79,7 @@ def load():
         "xnb_view_chunk_neighbors": (I, [P, P, P, P]), "xnb_stream_pool_u16": (I64, [P]), "xnb_get_streams": (I, [P, P, P]),
         "xnb_get_amr": (I64, [P, P, P]), "xnb_get_backup": (I, [P, P]), "xnb_rebuild_count": (I64, [P]), "xnb_kernel_launches": (I64, [P]),
         "xnb_host_lattice_fcc": (I64, [C.POINTER(XnbLatticeCfg), I64] + [P] * 8),
-        "xnb_timing_enable": (I, [P, I]), "xnb_timing_read": (I, [P, P, P, P, P, I]), "xnb_measure_dfma_peak": (I, [I, P]),
+        "xnb_timing_enable": (I, [P, I]), "xnb_timing_read": (I, [P, P, P, I]), "xnb_measure_dfma_peak": (I, [I, P]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -245,6 +245,12 @@ class Context:
         self._ck(self.L.xnb_get_streams(self.h, _p(sz), _p(data)))
         return sz, data
 
+    def stream_sizes(self):
+        """per-cell stream size in u16 words (GridChunkNeighbors::m_cell_stream_size / 2)"""
+        sz = np.zeros(self.grid_info()["n_cells"], np.uint32)
+        self._ck(self.L.xnb_get_streams(self.h, _p(sz), None))
+        return sz
+
     def view_chunk_neighbors(self):
         ps = C.c_void_p(); pb = C.c_void_p(); mx = C.c_uint32()
         self._ck(self.L.xnb_view_chunk_neighbors(self.h, C.addressof(ps), C.addressof(pb), C.addressof(mx)))
@@ -270,10 +276,13 @@ class Context:
     def kernel_launches(self): return self.L.xnb_kernel_launches(self.h)
     def timing_enable(self, on=True): self._ck(self.L.xnb_timing_enable(self.h, int(on)))
 
+    TIMING_SCOPES = ("force", "nbh", "first_half", "bin", "ghost_scheme", "ghost_update")
+
     def timing_read(self, reset=True):
-        f = C.c_double(); fl = C.c_int64(); n = C.c_double(); nl = C.c_int64()
-        self._ck(self.L.xnb_timing_read(self.h, C.addressof(f), C.addressof(fl), C.addressof(n), C.addressof(nl), int(reset)))
-        return dict(force_ms=f.value, force_launches=fl.value, nbh_ms=n.value, nbh_launches=nl.value)
+        """device ms and scope count per kernel group (XNB_T_* of the header) since the last reset"""
+        ms = np.zeros(len(self.TIMING_SCOPES)); n = np.zeros(len(self.TIMING_SCOPES), np.int64)
+        self._ck(self.L.xnb_timing_read(self.h, _p(ms), _p(n), int(reset)))
+        return {k: dict(ms=float(ms[i]), n=int(n[i])) for i, k in enumerate(self.TIMING_SCOPES)}
 
 
 def measure_dfma_peak(device=0):

@@ -146,7 +146,7 @@ struct xnb_ctx
   DBuf<uint32_t> nb_len, nb_cnt, nb_off, stream_size, stream_size_padded, cell_stream_bytes;
   DBuf<unsigned long long> stream_off;
   DBuf<uint16_t> pool; DBuf<uint16_t*> cell_stream;
-  int64_t pool_used = 0; uint32_t max_neighbors = 0; bool have_nbh = false;
+  int64_t pool_used = 0; uint32_t max_neighbors = 0, max_cell_count = 0, max_stream = 0; double avg_stream = 0; bool have_nbh = false;
   // ---- misc device scalars
   DBuf<unsigned long long> scan_tmp64; DBuf<uint32_t> scan_tmp32;
   DBuf<unsigned long long> d_scalars64;   // [0] displacement counter, [1] scan total
@@ -159,8 +159,11 @@ struct xnb_ctx
   ncclComm_t comm = nullptr; bool own_comm = false;
   // ---- counters
   int64_t launches = 0, rebuilds = 0;
-  bool timing = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double force_ms = 0, nbh_ms = 0; int64_t force_launches = 0, nbh_launches = 0;
+  // device-side timing without synchronisation: per category a pool of event pairs recorded on the launching stream and
+  // summed at xnb_timing_read (categories XNB_T_* of the header)
+  bool timing = false;
+  struct TPool { std::vector<cudaEvent_t> ev; size_t used = 0; double ms = 0; int64_t n = 0; int64_t dropped = 0; };
+  TPool tpool[XNB_T_COUNT];
 
   int fail(int code, const std::string& m) { err = m; return code; }
   ParticlesP P(int which)
@@ -176,8 +179,46 @@ struct xnb_ctx
 
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return c->fail(XNB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
 #define NK(call) do { ncclResult_t r__ = (call); if (r__ != 0) return c->fail(XNB_ERR_NCCL, std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error")); } while (0)
+// timing scope helpers: record an event pair around a group of launches (no host synchronisation)
+static int t_begin(xnb_ctx* c, int cat, cudaStream_t st);
+static int t_end(xnb_ctx* c, int cat, cudaStream_t st);
 #define LAUNCH(kernel, grid, block, stream, ...) do { kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); c->launches++; CK(cudaGetLastError()); } while (0)
 static inline unsigned nblk(int64_t n, int b) { return (unsigned)std::max<int64_t>((n + b - 1) / b, 1); }
+
+static const size_t T_POOL_MAX = 8192;   // event pairs per category between two xnb_timing_read calls
+static int t_begin(xnb_ctx* c, int cat, cudaStream_t st)
+{
+  if (!c->timing) return 0;
+  xnb_ctx::TPool& t = c->tpool[cat];
+  if (t.used >= T_POOL_MAX) { t.dropped++; return 0; }
+  if (t.ev.size() < 2 * (t.used + 1)) { cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); t.ev.push_back(a); t.ev.push_back(b); }
+  CK(cudaEventRecord(t.ev[2 * t.used], st));
+  return 0;
+}
+static int t_end(xnb_ctx* c, int cat, cudaStream_t st)
+{
+  if (!c->timing) return 0;
+  xnb_ctx::TPool& t = c->tpool[cat];
+  if (t.used >= T_POOL_MAX || t.ev.size() < 2 * (t.used + 1)) return 0;
+  CK(cudaEventRecord(t.ev[2 * t.used + 1], st));
+  t.used++;
+  return 0;
+}
+static int t_collect(xnb_ctx* c)
+{
+  for (int cat = 0; cat < XNB_T_COUNT; cat++)
+  {
+    xnb_ctx::TPool& t = c->tpool[cat];
+    for (size_t q = 0; q < t.used; q++)
+    {
+      CK(cudaEventSynchronize(t.ev[2 * q + 1]));
+      float ms = 0; CK(cudaEventElapsedTime(&ms, t.ev[2 * q], t.ev[2 * q + 1]));
+      t.ms += ms; t.n++;
+    }
+    t.used = 0;
+  }
+  return 0;
+}
 
 namespace {
 
@@ -409,8 +450,7 @@ void xnb_destroy(xnb_ctx* c)
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  if (c->ev0) cudaEventDestroy(c->ev0);
-  if (c->ev1) cudaEventDestroy(c->ev1);
+  for (int cat = 0; cat < XNB_T_COUNT; cat++) for (cudaEvent_t e : c->tpool[cat].ev) cudaEventDestroy(e);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->comm && c->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   delete c;
@@ -835,26 +875,26 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
   CK(c->stream_size.ensure((size_t)g.n_cells + 1)); CK(c->stream_size_padded.ensure((size_t)g.n_cells + 1)); CK(c->stream_off.ensure((size_t)g.n_cells + 1));
   CK(c->cell_stream.ensure((size_t)g.n_cells)); CK(c->cell_stream_bytes.ensure((size_t)g.n_cells));
   ParticlesP A = c->P(c->cur);
-  if (c->timing) CK(cudaEventRecord(c->ev0, st));
+  if ((rc = t_begin(c, XNB_T_NBH, st))) return rc;
   NbhOut out{c->nb_len.p, c->nb_cnt.p, c->nb_off.p, c->cell_stream.p};
   if (n) LAUNCH((k_nbh_build<false>), nblk(n, 128), 128, st, g, (int)n, gap, md2, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
-  CK(cudaMemsetAsync(s32 + 3, 0, 4, st));
-  LAUNCH(k_nbh_cell_sizes, nblk((int64_t)g.n_cells * 32, 128), 128, st, g.n_cells, c->cell_start.p, c->cell_count.p, c->nb_len.p, c->nb_cnt.p, c->nb_off.p,
-         c->stream_size.p, c->stream_size_padded.p, s32 + 3, s32);
+  CK(cudaMemsetAsync(s32 + 3, 0, 16, st)); CK(cudaMemsetAsync(c->d_scalars64.p + 2, 0, 8, st));
+  LAUNCH(k_nbh_cell_sizes, nblk((int64_t)g.n_cells * 32, 128), 128, st, g, g.n_cells, c->cell_start.p, c->cell_count.p, c->nb_len.p, c->nb_cnt.p, c->nb_off.p,
+         c->stream_size.p, c->stream_size_padded.p, s32 + 3, s32 + 5, s32 + 6, c->d_scalars64.p + 2, s32);
   rc = scan_exclusive<uint32_t, unsigned long long>(c, c->stream_size_padded.p, c->stream_off.p, (size_t)g.n_cells, c->d_scalars64.p + 1, c->scan_tmp64, st); if (rc) return rc;
-  unsigned long long tot = 0; uint32_t mx = 0;
-  rc = read_back(c, c->d_scalars64.p + 1, 1, &tot, st); if (rc) return rc;
-  rc = read_back(c, s32 + 3, 1, &mx, st); if (rc) return rc;
-  c->pool_used = (int64_t)tot; c->max_neighbors = mx;
+  unsigned long long tot = 0, tot2[2] = {0, 0}; uint32_t mx = 0;
+  rc = read_back(c, c->d_scalars64.p + 1, 2, tot2, st); if (rc) return rc;
+  tot = tot2[0];
+  uint32_t sc[4] = {0, 0, 0, 0};
+  rc = read_back(c, s32 + 3, 4, sc, st); if (rc) return rc;
+  mx = sc[0];
+  c->pool_used = (int64_t)tot; c->max_neighbors = mx; c->max_cell_count = sc[2]; c->max_stream = sc[3];
+  c->avg_stream = c->n_inner ? (double)tot2[1] / (double)c->n_inner : 0.0;      // padded u16 words per inner particle
   // realloc_stream_pool (chunk_neighbors.h:70-96): grow with the reference's 5% head-room (update-particles.msp:20)
   CK(c->pool.ensure((size_t)tot + 64, 0, 1.05));
   LAUNCH(k_nbh_pointers, nblk(g.n_cells, 256), 256, st, g.n_cells, c->pool.p, c->stream_off.p, c->stream_size.p, c->cell_stream.p, c->cell_stream_bytes.p);
   if (n) LAUNCH((k_nbh_build<true>), nblk(n, 128), 128, st, g, (int)n, gap, md2, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
-  if (c->timing)
-  {
-    CK(cudaEventRecord(c->ev1, st)); CK(cudaEventSynchronize(c->ev1));
-    float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->nbh_ms += ms; c->nbh_launches++;
-  }
+  if ((rc = t_end(c, XNB_T_NBH, st))) return rc;
   c->have_nbh = true;
   return check_device_errors(c, st);
 }
@@ -873,23 +913,95 @@ int xnb_zero_particle_force(xnb_ctx* c, int ghost, void* stream)
 }
 
 } // extern "C"
-static LJP make_lj(double eps, double sig, double rcut) { LJP p; p.eps24 = 24.0 * eps; p.sig2 = sig * sig; p.rcut2 = rcut * rcut; p.eps4 = 4.0 * eps; return p; }
+static LJP make_lj(double eps, double sig, double rcut) { LJP p; p.eps24 = 24.0 * eps; p.sig2 = sig * sig; p.rcut2 = rcut * rcut; p.eps4 = 4.0 * eps; p.neg_eps48 = -48.0 * eps; return p; }
+
+// tile shape of the pair sweep: ti x tj cells per block, thread count and staging capacities from the cell occupancy
+struct TileCfg { TileP tp; int threads; size_t smem; unsigned blocks; };
+static int env_int(const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; }
+static TileCfg make_tiles(const xnb_ctx* c, bool ghost)
+{
+  const GridP& g = c->g;
+  TileCfg t{};
+  TileP& tp = t.tp;
+  tp.gap = (int)std::ceil(c->nbh_dist / c->cs);
+  for (int d = 0; d < 3; d++) { tp.lo[d] = ghost ? 0 : g.gl; tp.hi[d] = ghost ? g.dims[d] : g.dims[d] - g.gl; }
+  const int ni = tp.hi[0] - tp.lo[0], nj = tp.hi[1] - tp.lo[1], nk = tp.hi[2] - tp.lo[2];
+  const int64_t ncell_in = (int64_t)(g.dims[0] - 2 * g.gl) * (g.dims[1] - 2 * g.gl) * (g.dims[2] - 2 * g.gl);
+  const double avg = std::max(ncell_in > 0 ? (double)c->n_inner / (double)ncell_in : 1.0, 1.0);
+  const double mx = (double)std::max<uint32_t>(c->max_cell_count, 1);
+  const double wpp = std::max(c->avg_stream, 8.0);                  // stream words per particle
+  // candidate tile shapes: pick the one with the best (resident warps per SM) subject to the shared memory budget,
+  // preferring fewer staged bytes per particle
+  const size_t SM_BYTES = 224 * 1024;
+  double best_score = -1; int bi = 1, bj = 1, bthreads = 64; size_t bsmem = 0; int bcap = 0, bcaps = 0;
+  const int eti = env_int("XNB_TILE_I"), etj = env_int("XNB_TILE_J");
+  for (int ti = 1; ti <= std::min(8, ni); ti++) for (int tj = 1; tj <= std::min(4, nj); tj++)
+  {
+    if (eti > 0 && ti != std::min(eti, ni)) continue;
+    if (etj > 0 && tj != std::min(etj, nj)) continue;
+    const int tc = ti * tj;
+    const double tile_avg = avg * tc;
+    const double tile_max = std::min(mx * tc, tile_avg * 1.10 + 10.0);
+    int threads = 32 * (int)std::ceil(tile_max / 32.0);
+    if (threads > 640) continue;
+    threads = std::max(threads, 64);
+    const int hx = ti + 2 * tp.gap, hy = tj + 2 * tp.gap, hz = 2 * tp.gap + 1;
+    const int nh = hx * hy * hz;
+    const size_t head = (((size_t)(nh + 1 + 4 * tc + 2) * 4 + 15) & ~(size_t)15);
+    const size_t cap = (size_t)std::min(mx * nh, avg * nh * 1.2 + 128.0);
+    size_t cap_s = (size_t)std::min((double)c->max_stream * tc, wpp * tile_avg * 1.15 + 512.0);
+    cap_s = (cap_s + 7) & ~(size_t)7;
+    const size_t smem = head + cap_s * 2 + cap * 24;
+    if (smem + 1024 > SM_BYTES) continue;
+    const int by_smem = (int)(SM_BYTES / (smem + 1024));
+    const int by_regs = 65536 / (threads * 96);
+    const int by_warps = 64 / (threads / 32);
+    const int resident = std::min(std::min(by_smem, by_regs), std::min(by_warps, 32));
+    if (resident < 1) continue;
+    const double warps = resident * (threads / 32) * (tile_avg / threads);      // useful resident warps
+    const double staged_per_particle = (double)smem / tile_avg;
+    const double score = warps - 1e-3 * staged_per_particle;
+    if (score > best_score) { best_score = score; bi = ti; bj = tj; bthreads = threads; bsmem = smem; bcap = (int)cap; bcaps = (int)cap_s; }
+  }
+  if (best_score < 0)
+  {
+    // nothing fits (fat cells): 1x1 tiles without staging, the kernel takes its global-memory path
+    bi = bj = 1; bthreads = 32 * (int)std::min(16.0, std::max(2.0, std::ceil(avg / 32.0))); bcap = 0; bcaps = 8;
+    const int nh = (1 + 2 * tp.gap) * (1 + 2 * tp.gap) * (1 + 2 * tp.gap);
+    bsmem = (((size_t)(nh + 1 + 4 + 2) * 4 + 15) & ~(size_t)15) + 16;
+  }
+  if (env_int("XNB_FORCE_THREADS") > 0) bthreads = env_int("XNB_FORCE_THREADS");
+  tp.ti = bi; tp.tj = bj;
+  tp.tiles_i = (ni + bi - 1) / bi; tp.tiles_j = (nj + bj - 1) / bj;
+  tp.hx = bi + 2 * tp.gap; tp.hy = bj + 2 * tp.gap; tp.hz = 2 * tp.gap + 1;
+  tp.cap = bcap; tp.cap_s = bcaps;
+  t.threads = bthreads; t.smem = bsmem;
+  t.blocks = (unsigned)((int64_t)tp.tiles_i * tp.tiles_j * nk);
+  if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] force tiles %dx%d threads %d smem %zu cap %d cap_s %d blocks %u (avg %.1f max %.0f wpp %.1f)\n", bi, bj, bthreads, bsmem, bcap, bcaps, t.blocks, avg, mx, wpp);
+  return t;
+}
 
 template <int MODE, bool EV>
-static int launch_force(xnb_ctx* c, int64_t first, int64_t n, int64_t n_zero_end, const LJP& lj, double dth, double* evp, cudaStream_t st)
+static int launch_force(xnb_ctx* c, bool ghost, const LJP& lj, double dth, double* fxo, double* fyo, double* fzo, double** evp_out, unsigned* nblocks_out, cudaStream_t st)
 {
   ParticlesP A = c->P(c->cur);
-  const int64_t span = std::max(n, n_zero_end - first);
-  if (span <= 0) return XNB_OK;
-  if (c->timing) CK(cudaEventRecord(c->ev0, st));
-  LAUNCH((k_lj_force<MODE, EV>), nblk(span, 128), 128, st, c->g, (int)first, (int)n, (int)n_zero_end, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, A.fx, A.fy, A.fz,
-         A.type, c->mass.p, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p, evp);
-  if (c->timing)
+  const TileCfg t = make_tiles(c, ghost);
+  if (t.blocks == 0) return XNB_OK;
+  if (EV) { CK(c->ev_partials.ensure((size_t)t.blocks * 7 + 16)); if (evp_out) *evp_out = c->ev_partials.p; if (nblocks_out) *nblocks_out = t.blocks; }
+  static bool attr_done[2][2] = {{false, false}, {false, false}};
+  if (!attr_done[MODE][EV ? 1 : 0])
   {
-    CK(cudaEventRecord(c->ev1, st)); CK(cudaEventSynchronize(c->ev1));
-    float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->force_ms += ms; c->force_launches++;
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_lj_force_tiled<MODE, EV>));
+    CK(cudaFuncSetAttribute(k_lj_force_tiled<MODE, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
+    attr_done[MODE][EV ? 1 : 0] = true;
   }
-  return XNB_OK;
+  int rc;
+  if ((rc = t_begin(c, XNB_T_FORCE, st))) return rc;
+  k_lj_force_tiled<MODE, EV><<<t.blocks, t.threads, t.smem, st>>>(c->g, t.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
+      fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p,
+      c->stream_size.p, EV ? c->ev_partials.p : nullptr);
+  c->launches++; CK(cudaGetLastError());
+  return t_end(c, XNB_T_FORCE, st);
 }
 
 extern "C" {
@@ -898,8 +1010,7 @@ int xnb_lennard_jones_force(xnb_ctx* c, double eps, double sig, double rcut, int
   if (!c) return XNB_ERR_INVALID;
   if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "lennard_jones_force: no neighbour list (run xnb_chunk_neighbors)");
   c->rcut_max = std::max(c->rcut_max, rcut);    // lennard_jones.cu:193
-  const int64_t n = ghost ? c->n_total : c->n_inner;
-  return launch_force<0, false>(c, 0, n, 0, make_lj(eps, sig, rcut), 0.0, nullptr, (cudaStream_t)stream);
+  return launch_force<0, false>(c, ghost != 0, make_lj(eps, sig, rcut), 0.0, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int xnb_divide_force_by_mass(xnb_ctx* c, void* stream)
@@ -958,27 +1069,36 @@ int xnb_verlet_first_half(xnb_ctx* c, double dt, void* stream)
   if (!c) return XNB_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   ParticlesP A = c->P(c->cur);
+  int rc;
+  if ((rc = t_begin(c, XNB_T_FIRST_HALF, st))) return rc;
   CK(cudaMemsetAsync(c->d_scalars64.p, 0, 8, st));
   if (c->n_inner) LAUNCH(k_verlet_first_half, nblk(c->n_inner, 256), 256, st, c->g, (int)c->n_inner, dt, dt * dt * 0.5, dt * 0.5, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
                          A.fx, A.fy, A.fz, c->atom_cell[c->cur_ac].p, c->backup.p, c->max_displ * c->max_displ, c->d_scalars64.p);
-  return XNB_OK;
+  return t_end(c, XNB_T_FIRST_HALF, st);
 }
 
 int xnb_force_and_second_half(xnb_ctx* c, double eps, double sig, double rcut, double dth, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
   if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "no neighbour list (run xnb_chunk_neighbors)");
-  return launch_force<1, false>(c, 0, c->n_inner, c->n_total, make_lj(eps, sig, rcut), dth, nullptr, (cudaStream_t)stream);
+  return launch_force<1, false>(c, false, make_lj(eps, sig, rcut), dth, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 } // extern "C"
-static int update_particles_full(xnb_ctx* c, void* stream)
+// move_particles + parallel_update_particles (update-particles.msp:47-68)
+static int move_and_update_full(xnb_ctx* c, void* stream)
 {
   int rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = t_begin(c, XNB_T_BIN, st))) return rc;
+  if ((rc = xnb_move_particles(c, stream))) return rc;
   if ((rc = xnb_rebuild_amr(c, stream))) return rc;
   if ((rc = xnb_backup_r(c, stream))) return rc;
+  if ((rc = t_end(c, XNB_T_BIN, st))) return rc;
+  if ((rc = t_begin(c, XNB_T_GHOST_SCHEME, st))) return rc;
   if ((rc = xnb_ghost_comm_scheme(c, stream))) return rc;
   if ((rc = xnb_ghost_update_all(c, stream))) return rc;
+  if ((rc = t_end(c, XNB_T_GHOST_SCHEME, st))) return rc;
   if ((rc = xnb_chunk_neighbors(c, stream))) return rc;
   c->rebuilds++;
   return XNB_OK;
@@ -989,8 +1109,7 @@ int xnb_first_iteration(xnb_ctx* c, double eps, double sig, double rcut, void* s
 {
   if (!c) return XNB_ERR_INVALID;
   int rc;
-  if ((rc = xnb_move_particles(c, stream))) return rc;
-  if ((rc = update_particles_full(c, stream))) return rc;
+  if ((rc = move_and_update_full(c, stream))) return rc;
   return xnb_force_and_second_half(c, eps, sig, rcut, 0.0, stream);
 }
 
@@ -1005,11 +1124,15 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
     if ((rc = xnb_read_displ_over(c, &over, stream))) return rc;
     if (over > 0)
     {
-      if ((rc = xnb_move_particles(c, stream))) return rc;
-      if ((rc = update_particles_full(c, stream))) return rc;
+      if ((rc = move_and_update_full(c, stream))) return rc;
       rebuilds++;
     }
-    else if ((rc = xnb_ghost_update_r(c, stream))) return rc;
+    else
+    {
+      if ((rc = t_begin(c, XNB_T_GHOST_UPDATE, (cudaStream_t)stream))) return rc;
+      if ((rc = xnb_ghost_update_r(c, stream))) return rc;
+      if ((rc = t_end(c, XNB_T_GHOST_UPDATE, (cudaStream_t)stream))) return rc;
+    }
     if ((rc = xnb_force_and_second_half(c, eps, sig, rcut, dt * 0.5, stream))) return rc;
   }
   if (rebuilds_out) *rebuilds_out = rebuilds;
@@ -1022,28 +1145,24 @@ int xnb_energy_virial(xnb_ctx* c, double eps, double sig, double rcut, double* e
   if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "no neighbour list");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = c->n_inner;
-  const unsigned nb = nblk(n, 128), nb2 = nblk(n, 256);
-  CK(c->ev_partials.ensure((size_t)nb * 7 + nb2 + 16));
-  // MODE 0 accumulates into f: run it on a scratch copy of f so the state is untouched
-  DBuf<double> scratch; CK(scratch.ensure((size_t)n * 3 + 16));
+  const unsigned nb2 = nblk(n, 256);
+  unsigned nb = 0; double* evp = nullptr;
+  // MODE 0 accumulates into f: run it on a zeroed scratch copy of f so the state is untouched
+  DBuf<double> scratch; CK(scratch.ensure((size_t)c->n_total * 3 + 16));
+  DBuf<double> ekp; CK(ekp.ensure((size_t)nb2 + 16));
   ParticlesP A = c->P(c->cur);
-  double* keep[3] = {A.fx, A.fy, A.fz};
-  // temporarily point the force arrays at the scratch
-  double* sfx = scratch.p, *sfy = scratch.p + n, *sfz = scratch.p + 2 * n;
-  CK(cudaMemsetAsync(scratch.p, 0, (size_t)n * 3 * 8, st));
+  CK(cudaMemsetAsync(scratch.p, 0, (size_t)c->n_total * 3 * 8, st));
   if (n)
   {
-    k_lj_force<0, true><<<nb, 128, 0, st>>>(c->g, 0, (int)n, 0, make_lj(eps, sig, rcut), 0.0, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, sfx, sfy, sfz,
-                                            A.type, c->mass.p, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p, c->ev_partials.p);
-    c->launches++; CK(cudaGetLastError());
-    LAUNCH(k_ekin, nb2, 256, st, (int)n, A.vx, A.vy, A.vz, A.type, c->mass.p, c->ev_partials.p + (size_t)nb * 7);
+    int rc = launch_force<0, true>(c, false, make_lj(eps, sig, rcut), 0.0, scratch.p, scratch.p + c->n_total, scratch.p + 2 * c->n_total, &evp, &nb, st); if (rc) return rc;
+    LAUNCH(k_ekin, nb2, 256, st, (int)n, A.vx, A.vy, A.vz, A.type, c->mass.p, ekp.p);
   }
-  (void)keep;
+  if (n == 0) { if (epot) *epot = 0; if (virial) for (int q = 0; q < 6; q++) virial[q] = 0; if (ekin) *ekin = 0; return XNB_OK; }
   std::vector<double> h((size_t)nb * 7 + nb2, 0.0);
-  CK(cudaMemcpyAsync(h.data(), c->ev_partials.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h.data(), evp, (size_t)nb * 7 * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h.data() + (size_t)nb * 7, ekp.p, (size_t)nb2 * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   auto ksum = [&](size_t first, size_t count, size_t stride) { double s = 0., cc = 0.; for (size_t q = 0; q < count; q++) { const double x = h[first + q * stride]; const double t = s + x; cc += (std::fabs(s) >= std::fabs(x)) ? (s - t) + x : (x - t) + s; s = t; } return s + cc; };
-  if (n == 0) { if (epot) *epot = 0; if (virial) for (int q = 0; q < 6; q++) virial[q] = 0; if (ekin) *ekin = 0; return XNB_OK; }
   if (epot) *epot = ksum(0, nb, 7);
   if (virial) for (int q = 0; q < 6; q++) virial[q] = ksum((size_t)q + 1, nb, 7);
   if (ekin) *ekin = ksum((size_t)nb * 7, nb2, 1);
@@ -1113,16 +1232,20 @@ int64_t xnb_kernel_launches(const xnb_ctx* c) { return c ? c->launches : 0; }
 int xnb_timing_enable(xnb_ctx* c, int on)
 {
   if (!c) return XNB_ERR_INVALID;
-  if (on && !c->ev0) { CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1)); }
   c->timing = on != 0;
   return XNB_OK;
 }
 
-int xnb_timing_read(xnb_ctx* c, double* fms, int64_t* fl, double* nms, int64_t* nl, int reset)
+int xnb_timing_read(xnb_ctx* c, double ms[XNB_T_COUNT], int64_t scopes[XNB_T_COUNT], int reset)
 {
   if (!c) return XNB_ERR_INVALID;
-  if (fms) *fms = c->force_ms; if (fl) *fl = c->force_launches; if (nms) *nms = c->nbh_ms; if (nl) *nl = c->nbh_launches;
-  if (reset) { c->force_ms = c->nbh_ms = 0; c->force_launches = c->nbh_launches = 0; }
+  int rc = t_collect(c); if (rc) return rc;
+  for (int cat = 0; cat < XNB_T_COUNT; cat++)
+  {
+    if (ms) ms[cat] = c->tpool[cat].ms;
+    if (scopes) scopes[cat] = c->tpool[cat].n;
+    if (reset) { c->tpool[cat].ms = 0; c->tpool[cat].n = 0; c->tpool[cat].dropped = 0; }
+  }
   return XNB_OK;
 }
 

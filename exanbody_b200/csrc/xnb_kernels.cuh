@@ -611,9 +611,10 @@ k_nbh_build(GridP g, int n_total, int gap, double max_dist2,
 
 // one warp per cell: in-cell exclusive offsets of the particle lists, the cell's stream size (u16 words, unpadded and
 // padded to 16 bytes) and the running maximum neighbour count (m_max_neighbors, chunk_neighbors_execute.h:403-406)
-__global__ void k_nbh_cell_sizes(int n_cells, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+__global__ void k_nbh_cell_sizes(GridP g, int n_cells, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
                                  const uint32_t* __restrict__ nb_len, const uint32_t* __restrict__ nb_cnt, uint32_t* __restrict__ nb_off,
                                  uint32_t* __restrict__ stream_size, uint32_t* __restrict__ stream_size_padded, uint32_t* __restrict__ max_nbh,
+                                 uint32_t* __restrict__ max_cell_count, uint32_t* __restrict__ max_stream, unsigned long long* __restrict__ inner_words,
                                  uint32_t* __restrict__ err)
 {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -641,6 +642,11 @@ __global__ void k_nbh_cell_sizes(int n_cells, const uint32_t* __restrict__ cell_
     stream_size[c] = sz;
     stream_size_padded[c] = (sz + 7u) & ~7u;
     atomicMax(max_nbh, mx);
+    atomicMax(max_cell_count, n);
+    atomicMax(max_stream, (sz + 7u) & ~7u);
+    const int ci = c % g.dims[0], cj = (c / g.dims[0]) % g.dims[1], ck = c / (g.dims[0] * g.dims[1]);
+    const bool inner = ci >= g.gl && ci < g.dims[0] - g.gl && cj >= g.gl && cj < g.dims[1] - g.gl && ck >= g.gl && ck < g.dims[2] - g.gl;
+    if (inner) atomicAdd(inner_words, (unsigned long long)((sz + 7u) & ~7u));
   }
 }
 
@@ -674,7 +680,7 @@ __global__ void k_nbh_pointers(int n_cells, uint16_t* __restrict__ pool, const u
 //                                           + verlet_second_half fused; dth = 0 leaves v untouched bit-for-bit)
 // EV: additionally accumulate per-block partial sums of energy and virial (oracle-defined observables)
 // ------------------------------------------------------------------------------------------------------------------
-struct LJP { double eps24; double sig2; double rcut2; double eps4; };
+struct LJP { double eps24; double sig2; double rcut2; double eps4; double neg_eps48; };
 
 template <int MODE, bool EV>
 __global__ void __launch_bounds__(128)
@@ -753,6 +759,364 @@ k_lj_force(GridP g, int first, int n, int n_zero_end, LJP lj, double dth,
   {
     __shared__ double red[7][4];
     double vals[7] = {e, wxx, wyy, wzz, wxy, wxz, wyz};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 7; q++)
+    {
+      double v = vals[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[q][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7)
+    {
+      double v = 0.;
+      for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++) v += red[threadIdx.x][wq];
+      ev_partials[(size_t)blockIdx.x * 7 + threadIdx.x] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3 tiled pair sweep (the hot-path kernel).  Same contract as k_lj_force above, which stays as the small reference
+// form (used for tiles that do not fit shared memory and by the fused-vs-unfused cross-check).
+//
+// One block = one TILE of ti x tj cells (same k).  The block stages into shared memory
+//   (a) the prefix table hstart[] of the tile's halo box ((ti+2gap) x (tj+2gap) x (2gap+1) cells, clamped to the grid),
+//   (b) the positions of every particle of the halo box as three fp64 arrays (coalesced SoA loads: each neighbour cell
+//       is fetched once per tile instead of once per particle),
+//   (c) the u16 neighbour streams of the tile's cells, verbatim (each cell stream is one contiguous 16-byte aligned
+//       block of the GridChunkNeighbors pool).
+// Then one thread per particle walks its list out of shared memory with a FLAT loop over pair words; the group header
+// (cell code, count) is consumed by a short predicated block when the running position reaches the end of the
+// current group, so the 32 lanes of a warp advance through their own lists in lock step without diverging on the
+// nested structure of the reference format, and no lane ever issues a scattered global load.
+// ------------------------------------------------------------------------------------------------------------------
+struct TileP
+{
+  int ti, tj;        // cells per tile along i and j
+  int gap;           // neighbour cell layers = ceil(nbh_dist / cell_size)
+  int lo[3], hi[3];  // swept cell range [lo,hi) per axis (inner cells, or all cells when ghost=true)
+  int tiles_i, tiles_j;
+  int cap;           // staging capacity in particles
+  int cap_s;         // staging capacity in u16 stream words (multiple of 8)
+  int hx, hy, hz;    // nominal halo box dims
+};
+
+// d2 in (0, rcut2]  <=>  bits(d2) - 1 < bits(rcut2) as unsigned integers (d2 >= +0, never NaN for finite positions):
+// keeps the two comparisons off the FP64 pipe
+XNB_DEVINL bool in_cut(double d2, unsigned long long rcut2_bits)
+{
+  return (unsigned long long)(__double_as_longlong(d2) - 1ll) < rcut2_bits;
+}
+
+// 1/x for normal x > 0: hardware seed (MUFU.RCP64H) + Newton steps; two steps give relative error < 2^-50
+XNB_DEVINL double fast_rcp(double x)
+{
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+// asynchronous global -> shared copies (LDGSTS): issued back to back, completed by cp_async_wait_all()
+XNB_DEVINL void cp_async8(void* smem_dst, const void* gsrc)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+XNB_DEVINL void cp_async16(void* smem_dst, const void* gsrc)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+XNB_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct LJAcc { double ax, ay, az, e, wxx, wyy, wzz, wxy, wxz, wyz; };
+
+// the Lennard-Jones functor, buffer-less call form (lennard_jones.cu:106-124) restated with one reciprocal:
+//   de/r = -24 eps (2 s12 - s6) / d2 = (24 eps - 48 eps s6) * (s6 / d2),  s6 = (sigma^2/d2)^3
+template <bool EV>
+XNB_DEVINL void lj_pair(const LJP& lj, double dx, double dy, double dz, double d2, LJAcc& a)
+{
+  const double inv = fast_rcp(d2);
+  const double s2 = lj.sig2 * inv;
+  const double s6 = s2 * s2 * s2;
+  const double de = fma(lj.neg_eps48, s6, lj.eps24) * (s6 * inv);
+  a.ax = fma(de, dx, a.ax); a.ay = fma(de, dy, a.ay); a.az = fma(de, dz, a.az);
+  if (EV)
+  {
+    a.e += 0.5 * lj.eps4 * (s6 * s6 - s6);
+    const double px = de * dx, py = de * dy, pz = de * dz;
+    a.wxx -= 0.5 * dx * px; a.wyy -= 0.5 * dy * py; a.wzz -= 0.5 * dz * pz;
+    a.wxy -= 0.5 * dx * py; a.wxz -= 0.5 * dx * pz; a.wyz -= 0.5 * dy * pz;
+  }
+}
+
+// U pairs at once, branch free, so that the U reciprocal / power chains are independent and overlap in the FP64 pipe
+template <bool EV, int U>
+XNB_DEVINL void lj_pairs(const LJP& lj, const double (&dx)[U], const double (&dy)[U], const double (&dz)[U], const double (&d2)[U], const bool (&ok)[U], LJAcc& a)
+{
+  double inv[U], s6[U], de[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) inv[u] = fast_rcp(d2[u]);
+#pragma unroll
+  for (int u = 0; u < U; u++) { const double s2 = lj.sig2 * inv[u]; s6[u] = s2 * s2 * s2; }
+#pragma unroll
+  for (int u = 0; u < U; u++) { de[u] = fma(lj.neg_eps48, s6[u], lj.eps24) * (s6[u] * inv[u]); if (!ok[u]) de[u] = 0.0; }
+#pragma unroll
+  for (int u = 0; u < U; u++) { a.ax = fma(de[u], dx[u], a.ax); a.ay = fma(de[u], dy[u], a.ay); a.az = fma(de[u], dz[u], a.az); }
+  if (EV)
+  {
+#pragma unroll
+    for (int u = 0; u < U; u++)
+    {
+      if (ok[u]) a.e += 0.5 * lj.eps4 * (s6[u] * s6[u] - s6[u]);
+      const double px = de[u] * dx[u], py = de[u] * dy[u], pz = de[u] * dz[u];
+      a.wxx -= 0.5 * dx[u] * px; a.wyy -= 0.5 * dy[u] * py; a.wzz -= 0.5 * dz[u] * pz;
+      a.wxy -= 0.5 * dx[u] * py; a.wxz -= 0.5 * dx[u] * pz; a.wyz -= 0.5 * dy[u] * pz;
+    }
+  }
+}
+
+template <int MODE, bool EV>
+__global__ void __launch_bounds__(640)
+k_lj_force_tiled(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth,
+                 const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                 double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
+                 double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+                 const uint8_t* __restrict__ type, const double* __restrict__ mass,
+                 const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+                 const uint16_t* const* __restrict__ cell_stream, const uint32_t* __restrict__ stream_size,
+                 double* __restrict__ ev_partials /* [gridDim.x][7] */)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nh_max = tp.hx * tp.hy * tp.hz;
+  const int tc_max = tp.ti * tp.tj;
+  uint32_t* hstart = reinterpret_cast<uint32_t*>(smem_raw);                       // [nh_max + 1] particle prefix of the halo cells
+  uint32_t* tstart = hstart + nh_max + 1;                                           // [tc_max + 1] particle prefix of the tile cells
+  uint32_t* tfirst = tstart + tc_max + 1;                                           // [tc_max] flat index of each tile cell's first particle
+  uint32_t* sstart = tfirst + tc_max;                                               // [tc_max + 1] stream word offset of each staged tile cell in S
+  uint32_t* swords = sstart + tc_max + 1;                                           // [tc_max] padded stream size of each tile cell (u16 words)
+  const size_t head = (((size_t)(nh_max + 1 + 4 * tc_max + 2) * 4 + 15) & ~(size_t)15);
+  uint16_t* S = reinterpret_cast<uint16_t*>(smem_raw + head);
+  double* sx = reinterpret_cast<double*>(smem_raw + head + (size_t)tp.cap_s * 2);
+  double* sy = sx + tp.cap;
+  double* sz = sy + tp.cap;
+  __shared__ uint32_t s_scan[32];
+  __shared__ int s_staged, s_q1, s_fit;
+
+  // ---- tile geometry
+  const int nj_t = tp.tiles_j;
+  int b = blockIdx.x;
+  const int t_i = b % tp.tiles_i; b /= tp.tiles_i;
+  const int t_j = b % nj_t; const int ck = tp.lo[2] + b / nj_t;
+  const int ci0 = tp.lo[0] + t_i * tp.ti, cj0 = tp.lo[1] + t_j * tp.tj;
+  const int tci = min(tp.ti, tp.hi[0] - ci0), tcj = min(tp.tj, tp.hi[1] - cj0);
+  const int tcells = tci * tcj;
+  // halo box clamped to the local grid
+  const int bx0 = max(ci0 - tp.gap, 0), bx1 = min(ci0 + tci - 1 + tp.gap, g.dims[0] - 1);
+  const int by0 = max(cj0 - tp.gap, 0), by1 = min(cj0 + tcj - 1 + tp.gap, g.dims[1] - 1);
+  const int bz0 = max(ck - tp.gap, 0), bz1 = min(ck + tp.gap, g.dims[2] - 1);
+  const int HX = bx1 - bx0 + 1, HY = by1 - by0 + 1, HZ = bz1 - bz0 + 1;
+  const int NH = HX * HY * HZ;
+
+  // ---- prefix table of the halo cells (block scan)
+  {
+    uint32_t carry = 0;
+    for (int base = 0; base < NH; base += blockDim.x)
+    {
+      const int h = base + threadIdx.x;
+      uint32_t cnt = 0;
+      if (h < NH)
+      {
+        const int hxq = h % HX, hyq = (h / HX) % HY, hzq = h / (HX * HY);
+        cnt = cell_count[ijk_to_index(g.dims, bx0 + hxq, by0 + hyq, bz0 + hzq)];
+      }
+      uint32_t total;
+      const uint32_t off = block_exclusive_scan<uint32_t>(cnt, &total, s_scan);
+      if (h < NH) hstart[h] = carry + off;
+      carry += total;
+    }
+    if (threadIdx.x == 0) { hstart[NH] = carry; s_staged = (carry <= (uint32_t)tp.cap) ? 1 : 0; }
+    // tile cells: one lane per cell, warp scan of the counts (a tile has at most 32 cells)
+    if (threadIdx.x < 32)
+    {
+      const int q = threadIdx.x;
+      uint32_t cnt = 0;
+      if (q < tcells)
+      {
+        const int c = ijk_to_index(g.dims, ci0 + q % tci, cj0 + q / tci, ck);
+        cnt = cell_count[c]; tfirst[q] = cell_start[c]; swords[q] = (stream_size[c] + 7u) & ~7u;
+      }
+      uint32_t x = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (q >= o) x += y; }
+      if (q < tcells) tstart[q] = x - cnt;
+      if (q == tcells - 1) tstart[tcells] = x;
+    }
+  }
+  __syncthreads();
+  const bool pos_staged = s_staged != 0;
+  const int n_tile = (int)tstart[tcells];
+
+  if (pos_staged && n_tile > 0)
+  {
+    // ---- (b) halo positions: one warp per halo cell, lanes over its particles (coalesced reads)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int h = warp; h < NH; h += nwarp)
+    {
+      const uint32_t d0 = hstart[h], cnt = hstart[h + 1] - d0;
+      if (cnt == 0) continue;
+      const int hxq = h % HX, hyq = (h / HX) % HY, hzq = h / (HX * HY);
+      const uint32_t s0 = cell_start[ijk_to_index(g.dims, bx0 + hxq, by0 + hyq, bz0 + hzq)];
+      for (uint32_t p = lane; p < cnt; p += 32) { cp_async8(sx + d0 + p, rx + s0 + p); cp_async8(sy + d0 + p, ry + s0 + p); cp_async8(sz + d0 + p, rz + s0 + p); }
+    }
+  }
+
+  LJAcc acc;
+  acc.e = acc.wxx = acc.wyy = acc.wzz = acc.wxy = acc.wxz = acc.wyz = 0.;
+  const unsigned long long rc2b = (unsigned long long)__double_as_longlong(lj.rcut2);
+  const int HXY = HX * HY;
+
+  // ---- (c) streams, staged in batches of whole cells that fit the stream buffer (normally the whole tile at once)
+  for (int q0 = 0; q0 < tcells && n_tile > 0;)
+  {
+    if (threadIdx.x == 0)
+    {
+      uint32_t sacc = 0; int q1 = q0;
+      while (q1 < tcells) { const uint32_t w = swords[q1]; if (q1 > q0 && sacc + w > (uint32_t)tp.cap_s) break; sstart[q1] = sacc; sacc += w; q1++; }
+      sstart[q1] = sacc; s_q1 = q1; s_fit = (sacc <= (uint32_t)tp.cap_s) ? 1 : 0;
+    }
+    __syncthreads();
+    const int q1 = s_q1;
+    const bool staged = pos_staged && s_fit != 0;
+    if (staged)
+    {
+      for (int q = q0; q < q1; q++)
+      {
+        const int c = ijk_to_index(g.dims, ci0 + q % tci, cj0 + q / tci, ck);
+        const uint4* src = reinterpret_cast<const uint4*>(cell_stream[c]);
+        uint4* dst = reinterpret_cast<uint4*>(S + sstart[q]);
+        const int nv = (int)(swords[q] >> 3);
+        for (int v = threadIdx.x; v < nv; v += blockDim.x) cp_async16(dst + v, src + v);
+      }
+    }
+    cp_async_wait_all();      // streams of this batch and (first batch) the halo positions
+    __syncthreads();
+  for (int t = (int)tstart[q0] + (int)threadIdx.x; t < (int)tstart[q1]; t += blockDim.x)
+  {
+    int q = q0;
+    while (q + 1 < q1 && (uint32_t)t >= tstart[q + 1]) q++;
+    const uint32_t pa = (uint32_t)t - tstart[q];
+    const uint32_t i = tfirst[q] + pa;
+    const uint32_t na = tstart[q + 1] - tstart[q];
+    const int cia = ci0 + q % tci, cja = cj0 + q / tci;
+    const int ca = ijk_to_index(g.dims, cia, cja, ck);
+    const double xa = rx[i], ya = ry[i], za = rz[i];
+    // epilogue operands fetched now so that their latency hides behind the pair loop
+    double m = 1.0, ux = 0., uy = 0., uz = 0.;
+    if (MODE == 1) { m = mass[type[i]]; if (dth != 0.0) { ux = vx[i]; uy = vy[i]; uz = vz[i]; } }
+    acc.ax = acc.ay = acc.az = 0.;
+    if (staged)
+    {
+      const uint16_t* cs = S + sstart[q];
+      const uint32_t off0 = reinterpret_cast<const uint32_t*>(cs)[pa], off1 = reinterpret_cast<const uint32_t*>(cs)[pa + 1];
+      const uint16_t* lists = cs + 2u * (na + 1u);
+      const uint16_t* p = lists + off0;          // = list start + 1: skips the group counter (off is biased by +1 table)
+      const uint16_t* const end = lists + (off1 - 1u);
+      const uint16_t* gend = p;
+      // halo index of cell (cia + ri, cja + rj, ck + rk) = hb2 + (enc >> 10) * HXY + ((enc >> 5) & 31) * HX + (enc & 31)
+      const int hb2 = ((ck - bz0) * HY + (cja - by0)) * HX + (cia - bx0) - 16 * (HXY + HX + 1);
+      uint32_t sb = 0;
+      // next pair of this particle as a shared-memory particle index; the group header (cell code, count) is consumed
+      // when the running position reaches the end of the current group
+      auto fetch = [&]() -> uint32_t
+      {
+        if (p == gend)
+        {
+          const uint32_t enc = p[0], n = p[1];
+          sb = hstart[hb2 + (int)(enc >> 10) * HXY + (int)((enc >> 5) & 31u) * HX + (int)(enc & 31u)];
+          p += 2; gend = p + n;
+        }
+        return sb + *p++;
+      };
+      // UNROLL independent pairs per trip: their FP64 dependency chains overlap (the loop is latency bound otherwise)
+      constexpr int UNROLL = 4;
+      while (p < end)
+      {
+        uint32_t j[UNROLL]; bool live[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) { live[u] = p < end; j[u] = live[u] ? fetch() : 0u; }
+        double dx[UNROLL], dy[UNROLL], dz[UNROLL], d2[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+        {
+          dx[u] = __dadd_rn(sx[j[u]], -xa); dy[u] = __dadd_rn(sy[j[u]], -ya); dz[u] = __dadd_rn(sz[j[u]], -za);
+          d2[u] = norm2_exact(dx[u], dy[u], dz[u]);
+        }
+        // branch free: out-of-range / padding pairs are evaluated at d2 = 1 and contribute a zero coefficient
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) { live[u] = live[u] && in_cut(d2[u], rc2b); if (!live[u]) d2[u] = 1.0; }
+        lj_pairs<EV, UNROLL>(lj, dx, dy, dz, d2, live, acc);
+      }
+    }
+    else
+    {
+      // tile too large for the staging buffers: walk the stream in global memory (nested form of impl_default.h:143-179)
+      const uint16_t* base = cell_stream[ca];
+      const uint32_t off = reinterpret_cast<const uint32_t*>(base)[pa];
+      const uint16_t* s = base + 2u * (na + 1u) + (off - 1u);
+      int groups = *s++;
+      for (; groups > 0; --groups)
+      {
+        const uint32_t enc = *s++;
+        int cnt = *s++;
+        const int ri = (int)(enc & 31u) - 16, rj = (int)((enc >> 5) & 31u) - 16, rk = (int)((enc >> 10) & 31u) - 16;
+        const uint32_t sbg = cell_start[ca + (rk * g.dims[1] + rj) * g.dims[0] + ri];
+        for (; cnt > 0; --cnt)
+        {
+          const uint32_t j = sbg + *s++;
+          const double dx = __dadd_rn(rx[j], -xa), dy = __dadd_rn(ry[j], -ya), dz = __dadd_rn(rz[j], -za);
+          const double d2 = norm2_exact(dx, dy, dz);
+          if (in_cut(d2, rc2b)) lj_pair<EV>(lj, dx, dy, dz, d2, acc);
+        }
+      }
+    }
+    double ax = acc.ax, ay = acc.ay, az = acc.az;
+    if (MODE == 0)
+    {
+      fx[i] += ax; fy[i] += ay; fz[i] += az;
+    }
+    else
+    {
+      ax = __ddiv_rn(ax, m); ay = __ddiv_rn(ay, m); az = __ddiv_rn(az, m);
+      fx[i] = ax; fy[i] = ay; fz[i] = az;
+      if (dth != 0.0)
+      {
+        vx[i] = __dadd_rn(ux, __dmul_rn(ax, dth));
+        vy[i] = __dadd_rn(uy, __dmul_rn(ay, dth));
+        vz[i] = __dadd_rn(uz, __dmul_rn(az, dth));
+      }
+    }
+  }
+    __syncthreads();      // the stream buffer is reused by the next batch
+    q0 = q1;
+  }
+  if (MODE == 1)
+  {
+    // zero_particle_force{ghost:true}: ghost particles keep f = 0 (each block clears its slice of the ghost range)
+    const int ng = n_total - n_inner;
+    const int per = (ng + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int g0 = n_inner + (int)blockIdx.x * per, g1 = min(g0 + per, n_total);
+    for (int i = g0 + (int)threadIdx.x; i < g1; i += blockDim.x) { fx[i] = 0.; fy[i] = 0.; fz[i] = 0.; }
+  }
+  if (EV)
+  {
+    __shared__ double red[7][20];
+    double vals[7] = {acc.e, acc.wxx, acc.wyy, acc.wzz, acc.wxy, acc.wxz, acc.wyz};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int q = 0; q < 7; q++)

@@ -156,9 +156,17 @@ int xnb_get_backup(xnb_ctx*, uint32_t* out /* 3*n_inner */);
 /* counters */
 int64_t xnb_rebuild_count(const xnb_ctx*);
 int64_t xnb_kernel_launches(const xnb_ctx*);    /* number of kernels this ctx has launched so far                */
-/* device time of the force kernel launches since the last reset (CUDA events on the launching stream)           */
+/* device time per kernel group since the last reset: CUDA event pairs recorded on the launching stream around each
+   group, never synchronising inside the timed region; xnb_timing_read waits for the recorded events and sums them. */
+#define XNB_T_FORCE 0        /* pair sweep (K3)                                  */
+#define XNB_T_NBH 1          /* chunk_neighbors (K2)                             */
+#define XNB_T_FIRST_HALF 2   /* verlet_first_half + displacement test (K4)       */
+#define XNB_T_BIN 3          /* move_particles + rebuild_amr + backup_r (K1)     */
+#define XNB_T_GHOST_SCHEME 4 /* ghost_comm_scheme + ghost_update_all             */
+#define XNB_T_GHOST_UPDATE 5 /* ghost_update_r (K6/K7 + NCCL)                    */
+#define XNB_T_COUNT 6
 int xnb_timing_enable(xnb_ctx*, int on);
-int xnb_timing_read(xnb_ctx*, double* force_ms, int64_t* force_launches, double* nbh_ms, int64_t* nbh_launches, int reset);
+int xnb_timing_read(xnb_ctx*, double ms[XNB_T_COUNT], int64_t scopes[XNB_T_COUNT], int reset);
 
 /* ---- host-side input operators of the LJ decks (not on the timed path) ------------------------------------ */
 /* ops `lattice` (structure FCC) + `gaussian_noise_r` with deterministic_noise:
