@@ -292,7 +292,7 @@ def b200_arm(args):
         ctx.download_rvf(ptr["rx"], ptr["ry"], ptr["rz"], ptr["vx"], ptr["vy"], ptr["vz"], ptr["fx"], ptr["fy"], ptr["fz"], hid.data_ptr(), sh)
 
     e2e = None
-    if world == 1:       # with several ranks atoms migrate between ranks, so host buffers change size: e2e is defined at N=1
+    if world == 1 and not args.no_e2e:       # with several ranks atoms migrate between ranks, so host buffers change size: e2e is defined at N=1
         e2e_steps = max(3, min(args.steps, 20))
         for _ in range(3):
             e2e_step()
@@ -343,6 +343,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
