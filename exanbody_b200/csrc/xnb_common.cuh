@@ -48,7 +48,8 @@ enum : uint32_t
   DERR_GROUP_OVERFLOW = 1u << 2,  // u16 counter overflow in a stream
   DERR_FAR_MIGRATION = 1u << 3,   // particle jumped to a rank that is not a ghost partner
   DERR_SORT_CAPACITY = 1u << 4,   // cell too large for the in-cell sort
-  DERR_ID_RANGE = 1u << 5         // particle id >= 2^52
+  DERR_ID_RANGE = 1u << 5,        // particle id >= 2^52
+  DERR_TILE_CAPACITY = 1u << 6    // a tile did not fit its shared-memory staging capacity (host falls back to the untiled kernels)
 };
 
 #define XNB_DEVINL __device__ __forceinline__

@@ -60,6 +60,8 @@ bool nccl_load()
 }
 
 std::string g_create_error;
+bool env_flag(const char* name) { const char* v = getenv(name); return v && *v && *v != '0'; }
+int env_int(const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; }
 
 template <class T>
 struct DBuf
@@ -146,6 +148,7 @@ struct xnb_ctx
   DBuf<uint32_t> nb_len, nb_cnt, nb_off, stream_size, stream_size_padded, cell_stream_bytes;
   DBuf<unsigned long long> stream_off;
   DBuf<uint16_t> pool; DBuf<uint16_t*> cell_stream;
+  int nbh_cap_l = 0; uint32_t nbh_slot_words = 0; bool nbh_full_cap = false;   // capacities of the tiled build (grow on demand)
   int64_t pool_used = 0; uint32_t max_neighbors = 0, max_cell_count = 0, max_stream = 0; double avg_stream = 0; bool have_nbh = false;
   // ---- misc device scalars
   DBuf<unsigned long long> scan_tmp64; DBuf<uint32_t> scan_tmp32;
@@ -395,6 +398,7 @@ int check_device_errors(xnb_ctx* c, cudaStream_t st)
   if (e & DERR_GROUP_OVERFLOW) return c->fail(XNB_ERR_CAPACITY, "u16 counter overflow in a neighbour stream (chunk_neighbors_execute.h:362,369)");
   if (e & DERR_SORT_CAPACITY) return c->fail(XNB_ERR_CAPACITY, "more than 2048 particles in a cell: in-cell sort capacity exceeded");
   if (e & DERR_ID_RANGE) return c->fail(XNB_ERR_CAPACITY, "particle id >= 2^52");
+  if (e & DERR_TILE_CAPACITY) return c->fail(XNB_ERR_CAPACITY, "a tile exceeded its shared-memory staging capacity");
   return c->fail(XNB_ERR_INVALID, "device error word " + std::to_string(e));
 }
 
@@ -877,16 +881,98 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
   ParticlesP A = c->P(c->cur);
   if ((rc = t_begin(c, XNB_T_NBH, st))) return rc;
   NbhOut out{c->nb_len.p, c->nb_cnt.p, c->nb_off.p, c->cell_stream.p};
+
+  // ---- tiled single-kernel form (k_nbh_fused) when a tile fits shared memory, else the per-particle two-pass kernels
+  bool tiled = n > 0 && !env_flag("XNB_NBH_UNTILED");
+  if (tiled)
+  {
+    CK(cudaMemsetAsync(s32 + 5, 0, 4, st));
+    LAUNCH(k_max_u32, nblk(g.n_cells, 256), 256, st, g.n_cells, c->cell_count.p, s32 + 5);
+    uint32_t mcc = 0;
+    rc = read_back(c, s32 + 5, 1, &mcc, st); if (rc) return rc;
+    mcc = std::max<uint32_t>(mcc, 1);
+    const int nslot = (2 * gap + 1) * (2 * gap + 1) * (2 * gap + 1);
+    const bool u8 = mcc <= 127 && nslot <= 128 && !env_flag("XNB_NBH_U16");     // byte list areas (k_nbh_fused<true>)
+    const size_t SMEM_MAX = 200 * 1024;
+    if (mcc > 32u * NBH_MAX_CHUNKS) tiled = false;
+    if (c->nbh_cap_l == 0) c->nbh_cap_l = 160;
+    static const int shapes[][2] = {{4, 2}, {2, 2}, {2, 1}, {1, 1}};
+    int first_shape = env_int("XNB_NBH_TILE");      // tuning knobs: index into shapes[], warps per block
+    int nwarp = env_int("XNB_NBH_WARPS") > 0 ? std::min(env_int("XNB_NBH_WARPS"), 8) : 8;
+    for (int attempt = 0; attempt < 6 && tiled; attempt++)
+    {
+      NbhTileP tp{};
+      tp.gap = gap; tp.max_dist2 = md2; tp.cap_l = (c->nbh_cap_l + 15) & ~15;
+      tp.tail = (1 + nslot * (2 + (int)mcc) + 15) & ~15;
+      if (c->nbh_slot_words == 0) c->nbh_slot_words = (uint32_t)((2 * (mcc + 1) + (size_t)mcc * tp.cap_l * 3 / 4 + 7) & ~(size_t)7);
+      tp.slot_words = (int)c->nbh_slot_words;
+      const size_t lists = (size_t)nwarp * (size_t)(31 * tp.cap_l + tp.tail) * (u8 ? 1 : 2);
+      int pick = -1; size_t smem = 0;
+      for (int q = std::max(first_shape, 0); q < 4; q++)
+      {
+        const int ti = std::min(shapes[q][0], g.dims[0]), tj = std::min(shapes[q][1], g.dims[1]);
+        const size_t nh = (size_t)std::min(ti + 2 * gap, g.dims[0]) * std::min(tj + 2 * gap, g.dims[1]) * std::min(2 * gap + 1, g.dims[2]);
+        if (nh > (size_t)NBH_MAX_HALO) continue;
+        // staging capacity: every halo cell at 85% of the fullest cell (a fuller tile makes the kernel report
+        // DERR_TILE_CAPACITY and the build is re-run with the exact bound, then with the next smaller tile shape)
+        const size_t cap = (size_t)std::ceil((double)nh * (double)mcc * (c->nbh_full_cap ? 1.0 : 0.85)) + 32;
+        smem = ((cap * 16 + 15) & ~(size_t)15) + lists;
+        if (smem <= SMEM_MAX) { pick = q; tp.ti = ti; tp.tj = tj; tp.cap = (int)cap; break; }
+      }
+      if (pick < 0 || (size_t)g.n_cells * c->nbh_slot_words > ((size_t)24 << 30)) { tiled = false; break; }
+      tp.tiles_i = (g.dims[0] + tp.ti - 1) / tp.ti; tp.tiles_j = (g.dims[1] + tp.tj - 1) / tp.tj;
+      CK(c->pool.ensure((size_t)g.n_cells * c->nbh_slot_words + 64));
+      uint32_t* stats = s32 + 96;
+      CK(cudaMemsetAsync(stats, 0, 6 * 4, st)); CK(cudaMemsetAsync(c->d_scalars64.p + 1, 0, 16, st));
+      NbhCellOut o{c->pool.p, c->cell_stream.p, c->stream_size.p, c->cell_stream_bytes.p, c->stream_off.p, stats, c->d_scalars64.p + 1};
+      static bool attr_done = false;
+      if (!attr_done)
+      {
+        CK(cudaFuncSetAttribute(k_nbh_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        CK(cudaFuncSetAttribute(k_nbh_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        attr_done = true;
+      }
+      const unsigned blocks = (unsigned)((int64_t)tp.tiles_i * tp.tiles_j * g.dims[2]);
+      if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh tiles %dx%d warps %d u8 %d cap %d cap_l %d slot %d smem %zu blocks %u (max cell %u)\n", tp.ti, tp.tj, nwarp, (int)u8, tp.cap, tp.cap_l, tp.slot_words, smem, blocks, mcc);
+      if (u8) k_nbh_fused<true><<<blocks, nwarp * 32, smem, st>>>(g, tp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, s32);
+      else    k_nbh_fused<false><<<blocks, nwarp * 32, smem, st>>>(g, tp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, s32);
+      c->launches++; CK(cudaGetLastError());
+      uint32_t hs[6]; unsigned long long tot2[2]; uint32_t e = 0;
+      rc = read_back(c, stats, 6, hs, st); if (rc) return rc;
+      rc = read_back(c, c->d_scalars64.p + 1, 2, tot2, st); if (rc) return rc;
+      rc = read_back(c, s32, 1, &e, st); if (rc) return rc;
+      bool again = false;
+      if (e & DERR_TILE_CAPACITY)
+      {
+        // this tile shape was too optimistic: clear the bit and retry with exact-capacity staging / a smaller tile
+        LAUNCH(k_clear_bits_u32, 1, 1, st, s32, (uint32_t)DERR_TILE_CAPACITY);
+        if (!c->nbh_full_cap) c->nbh_full_cap = true; else first_shape = pick + 1;
+        if (first_shape >= 4) { tiled = false; break; }
+        again = true;
+      }
+      if (hs[4] > (uint32_t)tp.cap_l) { c->nbh_cap_l = (int)(hs[4] * 1.15) + 8; again = true; }
+      if (hs[5] > c->nbh_slot_words) { c->nbh_slot_words = (uint32_t)(((size_t)(hs[5] * 1.12) + 64 + 7) & ~(size_t)7); again = true; }
+      else if (hs[4] > (uint32_t)tp.cap_l) { c->nbh_slot_words = (uint32_t)(((size_t)(c->nbh_slot_words * 1.25) + 7) & ~(size_t)7); }
+      if (again) continue;
+      c->pool_used = (int64_t)tot2[0]; c->max_neighbors = hs[0]; c->max_cell_count = hs[2]; c->max_stream = hs[3];
+      c->avg_stream = c->n_inner ? (double)tot2[1] / (double)c->n_inner : 0.0;
+      if ((rc = t_end(c, XNB_T_NBH, st))) return rc;
+      c->have_nbh = true;
+      return check_device_errors(c, st);
+    }
+    if (tiled) return c->fail(XNB_ERR_CAPACITY, "chunk_neighbors: tiled build did not converge");
+  }
+  // ---- per-particle two-pass form (count -> sizes -> scan -> fill)
   if (n) LAUNCH((k_nbh_build<false>), nblk(n, 128), 128, st, g, (int)n, gap, md2, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
-  CK(cudaMemsetAsync(s32 + 3, 0, 16, st)); CK(cudaMemsetAsync(c->d_scalars64.p + 2, 0, 8, st));
+  CK(cudaMemsetAsync(s32 + 3, 0, 20, st)); CK(cudaMemsetAsync(c->d_scalars64.p + 2, 0, 8, st));
   LAUNCH(k_nbh_cell_sizes, nblk((int64_t)g.n_cells * 32, 128), 128, st, g, g.n_cells, c->cell_start.p, c->cell_count.p, c->nb_len.p, c->nb_cnt.p, c->nb_off.p,
-         c->stream_size.p, c->stream_size_padded.p, s32 + 3, s32 + 5, s32 + 6, c->d_scalars64.p + 2, s32);
+         c->stream_size.p, c->stream_size_padded.p, s32 + 3, s32 + 5, s32 + 6, s32 + 7, c->d_scalars64.p + 2, s32);
   rc = scan_exclusive<uint32_t, unsigned long long>(c, c->stream_size_padded.p, c->stream_off.p, (size_t)g.n_cells, c->d_scalars64.p + 1, c->scan_tmp64, st); if (rc) return rc;
   unsigned long long tot = 0, tot2[2] = {0, 0}; uint32_t mx = 0;
   rc = read_back(c, c->d_scalars64.p + 1, 2, tot2, st); if (rc) return rc;
   tot = tot2[0];
-  uint32_t sc[4] = {0, 0, 0, 0};
-  rc = read_back(c, s32 + 3, 4, sc, st); if (rc) return rc;
+  uint32_t sc[5] = {0, 0, 0, 0, 0};
+  rc = read_back(c, s32 + 3, 5, sc, st); if (rc) return rc;
   mx = sc[0];
   c->pool_used = (int64_t)tot; c->max_neighbors = mx; c->max_cell_count = sc[2]; c->max_stream = sc[3];
   c->avg_stream = c->n_inner ? (double)tot2[1] / (double)c->n_inner : 0.0;      // padded u16 words per inner particle
@@ -917,7 +1003,6 @@ static LJP make_lj(double eps, double sig, double rcut) { LJP p; p.eps24 = 24.0 
 
 // tile shape of the pair sweep: ti x tj cells per block, thread count and staging capacities from the cell occupancy
 struct TileCfg { TileP tp; int threads; size_t smem; unsigned blocks; };
-static int env_int(const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; }
 static TileCfg make_tiles(const xnb_ctx* c, bool ghost)
 {
   const GridP& g = c->g;
@@ -1194,8 +1279,11 @@ int xnb_get_streams(xnb_ctx* c, uint32_t* size_u16, uint16_t* data)
   if (size_u16) memcpy(size_u16, sz.data(), nc * 4);
   if (data)
   {
-    std::vector<uint16_t> pool((size_t)c->pool_used);
-    if (c->pool_used) CK(cudaMemcpy(pool.data(), c->pool.p, (size_t)c->pool_used * 2, cudaMemcpyDeviceToHost));
+    // the streams sit at stream_off[] in the pool (compact after the two-pass build, fixed slots after the tiled one)
+    size_t extent = 0;
+    for (size_t q = 0; q < nc; q++) if (sz[q]) extent = std::max(extent, (size_t)off[q] + sz[q]);
+    std::vector<uint16_t> pool(extent);
+    if (extent) CK(cudaMemcpy(pool.data(), c->pool.p, extent * 2, cudaMemcpyDeviceToHost));
     size_t o = 0;
     for (size_t q = 0; q < nc; q++) { if (sz[q]) memcpy(data + o, pool.data() + off[q], (size_t)sz[q] * 2); o += sz[q]; }
   }

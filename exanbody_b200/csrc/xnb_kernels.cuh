@@ -14,6 +14,7 @@
 // the exact GridChunkNeighbors format.
 #pragma once
 #include "xnb_common.cuh"
+#include <type_traits>
 
 namespace xnb {
 
@@ -614,15 +615,15 @@ k_nbh_build(GridP g, int n_total, int gap, double max_dist2,
 __global__ void k_nbh_cell_sizes(GridP g, int n_cells, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
                                  const uint32_t* __restrict__ nb_len, const uint32_t* __restrict__ nb_cnt, uint32_t* __restrict__ nb_off,
                                  uint32_t* __restrict__ stream_size, uint32_t* __restrict__ stream_size_padded, uint32_t* __restrict__ max_nbh,
-                                 uint32_t* __restrict__ max_cell_count, uint32_t* __restrict__ max_stream, unsigned long long* __restrict__ inner_words,
-                                 uint32_t* __restrict__ err)
+                                 uint32_t* __restrict__ max_cell_count, uint32_t* __restrict__ max_stream, uint32_t* __restrict__ max_chunk_words,
+                                 unsigned long long* __restrict__ inner_words, uint32_t* __restrict__ err)
 {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= n_cells) return;
   const uint32_t n = cell_count[c], s0 = cell_start[c];
   if (n == 0) { if (lane == 0) { stream_size[c] = 0; stream_size_padded[c] = 0; } return; }
   if (n > 65535u && lane == 0) atomicOr(err, DERR_CELL_OVERFLOW);
-  uint32_t run = 0, mx = 0;
+  uint32_t run = 0, mx = 0, mxc = 0;
   for (uint32_t p0 = 0; p0 < n; p0 += 32)
   {
     const uint32_t p = p0 + lane;
@@ -632,7 +633,9 @@ __global__ void k_nbh_cell_sizes(GridP g, int n_cells, const uint32_t* __restric
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
     if (p < n) nb_off[s0 + p] = run + x - v;
-    run += __shfl_sync(0xffffffffu, x, 31);
+    const uint32_t chunk = __shfl_sync(0xffffffffu, x, 31);
+    mxc = max(mxc, chunk);      // list words of one 32-particle chunk (k_nbh_emit image size)
+    run += chunk;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -644,6 +647,7 @@ __global__ void k_nbh_cell_sizes(GridP g, int n_cells, const uint32_t* __restric
     atomicMax(max_nbh, mx);
     atomicMax(max_cell_count, n);
     atomicMax(max_stream, (sz + 7u) & ~7u);
+    atomicMax(max_chunk_words, mxc);
     const int ci = c % g.dims[0], cj = (c / g.dims[0]) % g.dims[1], ck = c / (g.dims[0] * g.dims[1]);
     const bool inner = ci >= g.gl && ci < g.dims[0] - g.gl && cj >= g.gl && cj < g.dims[1] - g.gl && ck >= g.gl && ck < g.dims[2] - g.gl;
     if (inner) atomicAdd(inner_words, (unsigned long long)((sz + 7u) & ~7u));
@@ -665,6 +669,376 @@ __global__ void k_nbh_pointers(int n_cells, uint16_t* __restrict__ pool, const u
     const uint32_t pad = ((sz + 7u) & ~7u) - sz;
     for (uint32_t q = 0; q < pad; q++) pool[stream_off[c] + sz + q] = 0;
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K2 (tiled form): the whole chunk neighbour build in ONE kernel, k_nbh_fused.
+//
+// One block = one tile of ti x tj cells (same k) of the whole local grid (ghost cells included,
+// chunk_neighbors_execute.h:110).  The block stages the tile's halo box into shared memory as one float4 per particle,
+// q = (-2x', -2y', -2z', |x'|^2) with x' = x - O relative to the centre O of the box.  One warp owns one cell A
+// (lane = particle p_a, 32 at a time); every neighbour cell B is swept with ALL lanes reading the same q_j (one
+// broadcast LDS.128), so   d2 - |x_a'|^2 = q.w + x_a' q.x + y_a' q.y + z_a' q.z   costs three FFMA per candidate.
+// The fp32 value only CLASSIFIES: "surely in" (<= max_dist^2 - band), "surely out" (> max_dist^2 + band); the few
+// candidates inside the band (and, in the own cell, closer than the band to zero) are decided by the exact fp64 test of
+// the reference (dr = r_a - r_b, d2 = norm2(dr), d2 > 0 && d2 <= max_dist^2, :225-227) on the original coordinates, so
+// the lists are bit-identical to the all-fp64 form.  band is derived from the largest |x'| actually staged.
+// Accepted p_b are appended to the lane's list in shared memory in the reference's stream order (ascending cell code,
+// ascending p_b => already sorted and unique, :308-324); when the 32 lists of a chunk are complete the warp writes the
+// u32 offset-table entries and copies the lists, coalesced, into the cell's stream.
+// Streams live in fixed slots of the pool: cell c owns pool[c*slot_words, (c+1)*slot_words) (deterministic placement,
+// no allocator and no second pass; the reference uses a bump allocator, chunk_neighbors.h:70-96).  If a list or a cell
+// outgrows its capacity the kernel keeps counting, reports the size it needs, and the host re-runs it with more room.
+// ------------------------------------------------------------------------------------------------------------------
+struct NbhTileP
+{
+  int ti, tj;            // cells per tile along i, j
+  int tiles_i, tiles_j;  // tiles per k-plane (covering the whole local grid)
+  int gap;               // neighbour cell layers
+  int cap;               // staging capacity in particles
+  int cap_l;             // list capacity per particle (u16 words)
+  int tail;              // extra words behind the last lane's list area (overflow stays inside the block's memory)
+  int slot_words;        // stream capacity per cell (u16 words, multiple of 8)
+  double max_dist2;
+};
+
+struct NbhCellOut
+{
+  uint16_t* pool;
+  uint16_t** cell_stream;            // per cell stream pointer (nullptr for empty cells, host_write_accessor.h:47-52)
+  uint32_t* stream_size;             // u16 words
+  uint32_t* cell_stream_bytes;       // bytes (GridChunkNeighbors::m_cell_stream_size)
+  unsigned long long* stream_off;    // u16 offset of the stream in the pool
+  uint32_t* stats;                   // [0] max neighbours [2] max cell count [3] max padded stream [4] needed cap_l [5] needed slot_words
+  unsigned long long* totals;        // [0] padded words of all cells [1] padded words of inner cells
+};
+
+XNB_DEVINL unsigned float_flip(float f) { return __float_as_uint(f); }   // for non-negative floats the bit pattern is monotone
+
+// exact decision for one ambiguous candidate (rare): the reference's test on the original fp64 coordinates
+__device__ __noinline__ bool nbh_exact_one(uint32_t self, uint32_t j, double max_dist2,
+                                           const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz)
+{
+  const double d2 = norm2_exact(__dadd_rn(rx[self], -rx[j]), __dadd_rn(ry[self], -ry[j]), __dadd_rn(rz[self], -rz[j]));
+  return j != self && d2 > 0.0 && d2 <= max_dist2;
+}
+
+constexpr int NBH_MAX_HALO = 1024;   // halo cells per tile the kernel supports ((ti+2gap)(tj+2gap)(2gap+1))
+constexpr int NBH_MAX_TCELLS = 8;    // cells per tile
+constexpr int NBH_MAX_CHUNKS = 32;   // 32-particle chunks per cell (cells of up to 1024 particles)
+
+// U8 = true: list areas hold bytes (p_b, counts < 128; group header = 0x80|slot, n), expanded to the u16 stream words
+// when the lists are copied out -- half the shared memory per warp, twice the resident warps.  Requires max cell count
+// <= 127 and (2gap+1)^3 <= 128.  U8 = false: list areas hold the final u16 words.
+template <bool U8>
+__global__ void __launch_bounds__(256)
+k_nbh_fused(GridP g, NbhTileP tp,
+            const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+            const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+            NbhCellOut out, uint32_t* __restrict__ err)
+{
+  typedef typename std::conditional<U8, uint8_t, uint16_t>::type LT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t hstart[NBH_MAX_HALO + 1];
+  __shared__ uint32_t hfirst[NBH_MAX_HALO];
+  __shared__ uint32_t s_scan[32];
+  __shared__ unsigned s_rmax;
+  __shared__ uint32_t s_stats[6];
+  __shared__ unsigned long long s_tot[2];
+  __shared__ uint32_t ustart[NBH_MAX_TCELLS + 1];
+  __shared__ uint32_t s_cum[NBH_MAX_TCELLS][NBH_MAX_CHUNKS + 1];   // list words of the cell before chunk ic (0xFFFFFFFF = not yet known)
+  __shared__ uint32_t s_next, s_done;
+  __shared__ uint16_t s_enc[128];
+  float4* S4 = reinterpret_cast<float4*>(smem_raw);
+  LT* LB = reinterpret_cast<LT*>(smem_raw + (size_t)tp.cap * 16);
+
+  int b = blockIdx.x;
+  const int t_i = b % tp.tiles_i; b /= tp.tiles_i;
+  const int t_j = b % tp.tiles_j; const int ck = b / tp.tiles_j;
+  const int ci0 = t_i * tp.ti, cj0 = t_j * tp.tj;
+  const int tci = min(tp.ti, g.dims[0] - ci0), tcj = min(tp.tj, g.dims[1] - cj0);
+  const int tcells = tci * tcj;
+  const int gap = tp.gap;
+  const int nslot1 = 2 * gap + 1;
+  const int bx0 = max(ci0 - gap, 0), bx1 = min(ci0 + tci - 1 + gap, g.dims[0] - 1);
+  const int by0 = max(cj0 - gap, 0), by1 = min(cj0 + tcj - 1 + gap, g.dims[1] - 1);
+  const int bz0 = max(ck - gap, 0), bz1 = min(ck + gap, g.dims[2] - 1);
+  const int HX = bx1 - bx0 + 1, HY = by1 - by0 + 1, HZ = bz1 - bz0 + 1;
+  const int NH = HX * HY * HZ;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+
+  // ---- prefix table of the halo cells
+  {
+    uint32_t carry = 0;
+    for (int base = 0; base < NH; base += blockDim.x)
+    {
+      const int h = base + threadIdx.x;
+      uint32_t cnt = 0;
+      if (h < NH)
+      {
+        const int hxq = h % HX, hyq = (h / HX) % HY, hzq = h / (HX * HY);
+        const int c = ijk_to_index(g.dims, bx0 + hxq, by0 + hyq, bz0 + hzq);
+        cnt = cell_count[c]; hfirst[h] = cell_start[c];
+      }
+      uint32_t total;
+      const uint32_t off = block_exclusive_scan<uint32_t>(cnt, &total, s_scan);
+      if (h < NH) hstart[h] = carry + off;
+      carry += total;
+    }
+    if (threadIdx.x == 0) { hstart[NH] = carry; s_rmax = 0u; s_tot[0] = 0ull; s_tot[1] = 0ull; s_next = 0u; s_done = 0u; }
+    if (threadIdx.x < 6) s_stats[threadIdx.x] = 0u;
+    if (U8)
+      for (int sl = threadIdx.x; sl < nslot1 * nslot1 * nslot1; sl += blockDim.x)
+      {
+        // encode_cell_index (chunk_neighbors.h:137-150) of neighbour slot sl = ((rk+gap)*n + (rj+gap))*n + (ri+gap)
+        const int ri = sl % nslot1 - gap, rj = (sl / nslot1) % nslot1 - gap, rk = sl / (nslot1 * nslot1) - gap;
+        s_enc[sl] = (uint16_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint16_t)(ri + 16);
+      }
+  }
+  __syncthreads();
+  const uint32_t n_halo = hstart[NH];
+  if (n_halo > (uint32_t)tp.cap) { if (threadIdx.x == 0) atomicOr(err, DERR_TILE_CAPACITY); return; }
+
+  // ---- work units = (tile cell, 32-particle chunk), handed out in order through s_next; empty cells are closed here
+  if (threadIdx.x == 0)
+  {
+    uint32_t acc = 0;
+    for (int q = 0; q < tcells; q++)
+    {
+      const int hq = ((ck - bz0) * HY + (cj0 + q / tci - by0)) * HX + (ci0 + q % tci - bx0);
+      const uint32_t nq = hstart[hq + 1] - hstart[hq];
+      ustart[q] = acc; acc += (nq + 31u) >> 5;
+      s_cum[q][0] = 0u;
+      for (uint32_t ic = 1; ic <= ((nq + 31u) >> 5) && ic <= (uint32_t)NBH_MAX_CHUNKS; ic++) s_cum[q][ic] = 0xFFFFFFFFu;
+      if (nq == 0)
+      {
+        const int cq = ijk_to_index(g.dims, ci0 + q % tci, cj0 + q / tci, ck);
+        out.cell_stream[cq] = nullptr; out.stream_size[cq] = 0u; out.cell_stream_bytes[cq] = 0u;
+        out.stream_off[cq] = (unsigned long long)cq * (unsigned long long)tp.slot_words;
+      }
+    }
+    ustart[tcells] = acc;
+  }
+
+  // ---- stage q = (-2x', -2y', -2z', |x'|^2), one warp per halo cell;  O = centre of the tile (fp64)
+  const double ox = __dadd_rn(g.org[0], __dmul_rn((double)(g.off[0] + ci0) + 0.5 * (double)tci, g.cs));
+  const double oy = __dadd_rn(g.org[1], __dmul_rn((double)(g.off[1] + cj0) + 0.5 * (double)tcj, g.cs));
+  const double oz = __dadd_rn(g.org[2], __dmul_rn((double)(g.off[2] + ck) + 0.5, g.cs));
+  {
+    float rmax = 0.f;
+    for (int h = warp; h < NH; h += nwarp)
+    {
+      const uint32_t d0 = hstart[h], cnt = hstart[h + 1] - d0, s0 = hfirst[h];
+      for (uint32_t p = lane; p < cnt; p += 32)
+      {
+        const float x = (float)(rx[s0 + p] - ox), y = (float)(ry[s0 + p] - oy), z = (float)(rz[s0 + p] - oz);
+        rmax = fmaxf(rmax, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
+        S4[d0 + p] = make_float4(-2.f * x, -2.f * y, -2.f * z, (float)((double)x * x + (double)y * y + (double)z * z));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    if (lane == 0) atomicMax(&s_rmax, float_flip(rmax));
+  }
+  __syncthreads();
+  // classification band: |fp32 value - exact d2| <= 2^-24 (60 R^2 + 1.01 max_dist2), R = max |coordinate|;
+  // the band used is 2^-24 * 128 * (3 R^2 + max_dist2)
+  const double R = (double)__uint_as_float(s_rmax);
+  const double band = 128.0 * 5.9604644775390625e-08 * (3.0 * R * R + tp.max_dist2);
+  const int cap_l = tp.cap_l;
+  LT* const Lw = LB + (size_t)warp * (size_t)(31 * cap_l + tp.tail);   // this warp's 32 list areas
+  LT* const L = Lw + (size_t)lane * cap_l;
+  const uint32_t n_units = ustart[tcells];
+
+  for (;;)
+  {
+    uint32_t u = 0;
+    if (lane == 0) u = atomicAdd(&s_next, 1u);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= n_units) break;
+    int q = 0;
+    while (q + 1 < tcells && u >= ustart[q + 1]) q++;
+    const uint32_t ic = u - ustart[q];
+    const int cia = ci0 + q % tci, cja = cj0 + q / tci;
+    const int ca = ijk_to_index(g.dims, cia, cja, ck);
+    const int hA = ((ck - bz0) * HY + (cja - by0)) * HX + (cia - bx0);
+    const uint32_t sA = hstart[hA], nA = hstart[hA + 1] - sA, gA = hfirst[hA];
+    const unsigned long long slot_off = (unsigned long long)ca * (unsigned long long)tp.slot_words;
+    uint16_t* const base = out.pool + slot_off;
+    uint16_t* const lists = base + 2u * (nA + 1u);
+    {
+      const uint32_t ia = ic * 32u + lane;
+      const bool active = ia < nA;
+      const float4 qa = S4[sA + (active ? ia : 0u)];
+      const float xi = -0.5f * qa.x, yi = -0.5f * qa.y, zi = -0.5f * qa.z;
+      const float lo = (float)(tp.max_dist2 - band - (double)qa.w);
+      const float hi = active ? (float)(tp.max_dist2 + band - (double)qa.w) : -INFINITY;   // idle lanes accept nothing
+      const float zlo = (float)(band - (double)qa.w);            // own cell only: d2 <= band is "ambiguous" (d2 > 0 test)
+      const uint32_t atom = gA + ia;
+      uint32_t cw = 1, groups = 0;                               // L[0] = group counter
+      for (int rk = -gap; rk <= gap; rk++)
+      {
+        const int bk = ck + rk;
+        if (bk < 0 || bk >= g.dims[2]) continue;
+        for (int rj = -gap; rj <= gap; rj++)
+        {
+          const int bj = cja + rj;
+          if (bj < 0 || bj >= g.dims[1]) continue;
+          for (int ri = -gap; ri <= gap; ri++)
+          {
+            const int bi = cia + ri;
+            if (bi < 0 || bi >= g.dims[0]) continue;
+            const int hB = ((bk - bz0) * HY + (bj - by0)) * HX + (bi - bx0);
+            const uint32_t sB = hstart[hB], nB = hstart[hB + 1] - sB;
+            if (nB == 0) continue;
+            const uint32_t gB = hfirst[hB];
+            const float4* __restrict__ Q = S4 + sB;
+            const uint32_t hdr = cw;
+            cw += 2;
+            uint32_t wi = cw;
+            if (!(rk == 0 && rj == 0 && ri == 0))
+            {
+              // blocks of 8 candidates; the last block may read up to 7 staged entries past the cell (the staging
+              // buffer is padded) and masks them out
+              for (uint32_t j = 0; j < nB; j += 8)
+              {
+                float t[8];
+#pragma unroll
+                for (int v = 0; v < 8; v++)
+                {
+                  const float4 qj = Q[j + v];
+                  t[v] = fmaf(zi, qj.z, fmaf(yi, qj.y, fmaf(xi, qj.x, qj.w)));
+                }
+                if (j + 8 > nB)
+                {
+#pragma unroll
+                  for (int v = 1; v < 8; v++) if (j + v >= nB) t[v] = INFINITY;
+                }
+                int amb = 0;
+#pragma unroll
+                for (int v = 0; v < 8; v++) amb |= (int)(t[v] <= hi) & (int)(t[v] > lo);
+                if (!amb)
+                {
+#pragma unroll
+                  for (int v = 0; v < 8; v++) if (t[v] <= hi) { L[wi] = (LT)(j + v); wi++; }
+                }
+                else
+                {
+                  // some candidate of this block sits inside the band: decide those with the exact fp64 test
+                  for (int v = 0; v < 8; v++)
+                    if (t[v] <= hi && (t[v] <= lo || nbh_exact_one(atom, gB + j + v, tp.max_dist2, rx, ry, rz))) { L[wi] = (LT)(j + v); wi++; }
+                }
+              }
+            }
+            else
+            {
+              for (uint32_t j = 0; j < nB; j++)
+              {
+                const float4 qj = Q[j];
+                const float t = fmaf(zi, qj.z, fmaf(yi, qj.y, fmaf(xi, qj.x, qj.w)));
+                // (cell_a,p_a) != (cell_b,p_b); d2 > 0 is decided exactly when the fp32 value is within the band of zero
+                if (t <= hi && j != ia && ((t <= lo && t > zlo) || nbh_exact_one(atom, gB + j, tp.max_dist2, rx, ry, rz))) { L[wi] = (LT)j; wi++; }
+              }
+            }
+            const uint32_t n = wi - cw;
+            if (n)
+            {
+              const int slot = ((rk + gap) * nslot1 + (rj + gap)) * nslot1 + (ri + gap);
+              // encode_cell_index (chunk_neighbors.h:137-150); in byte mode the code is looked up at copy-out
+              L[hdr] = U8 ? (LT)(0x80 | slot) : (LT)((uint16_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint16_t)(ri + 16));
+              L[hdr + 1] = (LT)n;
+              cw += n; groups++;
+            }
+            else cw = hdr;
+          }
+        }
+      }
+      L[0] = (LT)groups;
+      const uint32_t len = active ? cw : 0u;
+      const uint32_t ncand = active ? cw - 1u - 2u * groups : 0u;
+      if (active && (groups >= 65535u || ncand >= 65535u)) atomicOr(err, DERR_GROUP_OVERFLOW);
+      // warp statistics + exclusive scan of the list lengths
+      uint32_t x = len, mxl = len, mxc = ncand;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { mxl = max(mxl, __shfl_xor_sync(0xffffffffu, mxl, o)); mxc = max(mxc, __shfl_xor_sync(0xffffffffu, mxc, o)); }
+      const uint32_t chunk_total = __shfl_sync(0xffffffffu, x, 31);
+      // list words of this cell before this chunk: published by the warp that owns the previous chunk
+      uint32_t run = 0;
+      if (lane == 0)
+      {
+        volatile uint32_t* cum = &s_cum[q][0];
+        if (ic < (uint32_t)NBH_MAX_CHUNKS) { while ((run = cum[ic]) == 0xFFFFFFFFu) { } cum[ic + 1] = run + chunk_total; }
+        atomicMax(&s_stats[0], mxc);
+        if (mxl > (uint32_t)cap_l) atomicMax(&s_stats[4], mxl);
+      }
+      run = __shfl_sync(0xffffffffu, run, 0);
+      const uint32_t off = run + x - len;
+      const bool ovf = mxl > (uint32_t)cap_l || 2u * (nA + 1u) + run + chunk_total > (uint32_t)tp.slot_words;
+      __syncwarp();
+      if (!ovf)
+      {
+        if (active)
+        {
+          // offset table entry (chunk_neighbors_execute.h:279-283) and closing entry (:390-398)
+          reinterpret_cast<uint32_t*>(base)[ia] = off + 1u;
+          if (ia == nA - 1u) reinterpret_cast<uint32_t*>(base)[nA] = off + len + 1u;
+        }
+        const int nact = (int)min(32u, nA - ic * 32u);
+        for (int l = 0; l < nact; l++)
+        {
+          const uint32_t len_l = __shfl_sync(0xffffffffu, len, l), off_l = __shfl_sync(0xffffffffu, off, l);
+          const LT* src = Lw + (size_t)l * cap_l;
+          uint16_t* dst = lists + off_l;
+          for (uint32_t v = lane; v < len_l; v += 32)
+          {
+            const uint32_t wv = src[v];
+            dst[v] = (U8 && (wv & 0x80u)) ? s_enc[wv & 0x7fu] : (uint16_t)wv;
+          }
+        }
+      }
+      __syncwarp();
+      // ---- the warp that closes the cell's last chunk does the per cell bookkeeping
+      if (lane == 0 && (ic + 1u) * 32u >= nA)
+      {
+        const uint32_t sz = 2u * (nA + 1u) + run + chunk_total;
+        const uint32_t szp = (sz + 7u) & ~7u;
+        const bool fits = szp <= (uint32_t)tp.slot_words;
+        out.cell_stream[ca] = fits ? base : nullptr;
+        out.stream_size[ca] = sz;
+        out.cell_stream_bytes[ca] = sz * 2u;
+        out.stream_off[ca] = slot_off;
+        if (fits) for (uint32_t p = sz; p < szp; p++) base[p] = 0;   // deterministic padding
+        atomicMax(&s_stats[2], nA); atomicMax(&s_stats[3], szp); atomicMax(&s_stats[5], szp);
+        atomicAdd(&s_tot[0], (unsigned long long)szp);
+        const bool inner = cia >= g.gl && cia < g.dims[0] - g.gl && cja >= g.gl && cja < g.dims[1] - g.gl && ck >= g.gl && ck < g.dims[2] - g.gl;
+        if (inner) atomicAdd(&s_tot[1], (unsigned long long)szp);
+      }
+    }
+  }
+  // ---- the last warp to run out of work flushes the block statistics (no block-wide barrier: warps retire independently)
+  uint32_t done = 0;
+  if (lane == 0) { __threadfence_block(); done = atomicAdd(&s_done, 1u); }
+  done = __shfl_sync(0xffffffffu, done, 0);
+  if (done == (uint32_t)nwarp - 1u)
+  {
+    __threadfence_block();
+    if (lane < 6 && s_stats[lane]) atomicMax(&out.stats[lane], s_stats[lane]);
+    if (lane < 2 && s_tot[lane]) atomicAdd(&out.totals[lane], s_tot[lane]);
+  }
+}
+
+__global__ void k_clear_bits_u32(uint32_t* p, uint32_t bits) { *p &= ~bits; }
+
+// maximum of a u32 array (cell counts) -> *out (atomicMax)
+__global__ void k_max_u32(int n, const uint32_t* __restrict__ a, uint32_t* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t v = (i < n) ? a[i] : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

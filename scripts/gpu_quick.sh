@@ -1,0 +1,15 @@
+#!/bin/bash
+# quick GPU iteration: parity tests + a short bench (no CPU baseline / e2e); extra args go to bench.py
+set -u
+mkdir -p gpurun_out
+TAG=${1:-q}; shift || true
+( time timeout 1200 python -m pytest tests -m gpu -x -q ) > gpurun_out/${TAG}_pytest.log 2>&1
+tail -4 gpurun_out/${TAG}_pytest.log
+( timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e "$@" ) > gpurun_out/${TAG}_bench.log 2>&1
+tail -1 gpurun_out/${TAG}_bench.log | python -c "
+import sys,json
+l=sys.stdin.read().strip()
+try:
+    d=json.loads(l); print('value %.4g  ms/step %.4f  rebuilds %s' % (d['value'], d['ms_per_step'], d['config']['rebuilds'])); print({k:round(v,4) for k,v in d['breakdown_ms_per_step'].items()}); print('force kernel ms', round(d['roofline']['kernel_ms'],4), 'frac', round(d['roofline']['frac'],4))
+except Exception as e: print('bench failed:', l[-2000:])
+"

@@ -40,8 +40,15 @@ def setup_pair(kw):
     return o, ctx
 
 
+@pytest.mark.parametrize("nbh_kernels", ["tiled", "untiled"])
 @pytest.mark.parametrize("case", list(CASES))
-def test_rebuild_pipeline_bit_exact(case):
+def test_rebuild_pipeline_bit_exact(case, nbh_kernels, monkeypatch):
+    # "tiled": k_nbh_masks (fp32 classification + exact fp64 decision inside the band) + k_nbh_emit;
+    # "untiled": the per-particle all-fp64 kernels kept as the fallback for tiles that do not fit shared memory
+    if nbh_kernels == "untiled":
+        monkeypatch.setenv("XNB_NBH_UNTILED", "1")
+    else:
+        monkeypatch.delenv("XNB_NBH_UNTILED", raising=False)
     kw = CASES[case]
     o, ctx = setup_pair(kw)
     o.move_particles(); o.update_particles_full()
@@ -77,6 +84,59 @@ def test_rebuild_pipeline_bit_exact(case):
     assert ctx.view_chunk_neighbors()[2] == o.max_neighbors()
     # ---- and the pair set (by id) equals the one of the oracle's own, independently ordered run
     assert np.array_equal(o.pairs(), pairs_ref)
+
+
+def boundary_case():
+    """hand-made input that sits ON the decision boundaries: an exact FCC lattice with a = 1 (coordinates are multiples of
+    0.5, so every d2 is exact) and nbh_dist = 1.0, i.e. the whole second shell has d2 == max_dist^2 exactly (kept: <=);
+    some atoms nudged by +-1e-13 / +-3e-8 (just inside / outside), and a few coincident duplicates (d2 == 0: never
+    neighbours, chunk_neighbors_execute.h:225-227)."""
+    n = 8
+    kw = dict(bounds_max=(8.0,) * 3, cell_size=2.0, grid_dims=(4,) * 3, lattice_a=1.0, epsilon=1.0, sigma=0.5, rcut=0.75, rcut_inc=0.25,
+              dt=1e-4, mass=1.0, noise_sigma=0.0, vel_sigma=0.0, max_neighbors=1024)
+    basis = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0]])
+    ijk = np.stack(np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij"), -1).reshape(-1, 1, 3)
+    r = (ijk + basis[None]).reshape(-1, 3).astype(np.float64) + 0.25          # +0.25 keeps atoms off the cell faces
+    rng = np.random.default_rng(7)
+    k = rng.choice(len(r), 400, replace=False)
+    r[k[:100], 0] += 1e-13; r[k[100:200], 1] -= 1e-13; r[k[200:300], 2] += 3e-8; r[k[300:400], 0] -= 3e-8
+    dup = r[rng.choice(len(r), 12, replace=False)].copy()                        # coincident distinct particles
+    r = np.concatenate([r, dup])
+    m = len(r)
+    p = dict(rx=r[:, 0].copy(), ry=r[:, 1].copy(), rz=r[:, 2].copy(), vx=np.zeros(m), vy=np.zeros(m), vz=np.zeros(m),
+             id=np.arange(1, m + 1, dtype=np.uint64), type=np.zeros(m, np.uint8))
+    return kw, p
+
+
+@pytest.mark.parametrize("nbh_kernels", ["tiled", "untiled"])
+def test_neighbour_decisions_on_the_boundary(nbh_kernels, monkeypatch):
+    if nbh_kernels == "untiled":
+        monkeypatch.setenv("XNB_NBH_UNTILED", "1")
+    else:
+        monkeypatch.delenv("XNB_NBH_UNTILED", raising=False)
+    kw, p = boundary_case()
+    o = U.make_oracle(kw); o.generate()
+    counts = np.zeros(o.grid_info()["n_cells"], np.int32); counts[0] = len(p["id"])
+    o.set_particles(counts, p)
+    ctx = U.make_ctx(kw, particles=p)
+    o.move_particles(); o.update_particles_full()
+    ctx.move_particles(); ctx.update_particles_full()
+    pairs_ref = o.pairs()
+    # second shell (6 pairs at d2 == max_dist^2) must be present for unperturbed atoms: 12 + 6 neighbours
+    assert len(pairs_ref) > 17 * 2000
+    pg, cnt_g = U.gpu_particles_cell_order(ctx)
+    assert np.array_equal(cnt_g, o.cell_counts())
+    o.set_particles(cnt_g, pg)
+    o.build_neighbors()
+    sz_o, data_o = o.streams(); sz_g, data_g = ctx.streams()
+    assert np.array_equal(sz_o, sz_g) and np.array_equal(data_o, data_g)
+    assert np.array_equal(o.pairs(), pairs_ref)
+    # coincident particles are not neighbours of each other
+    ids = pairs_ref.astype(np.int64)
+    pos = {int(i): (x, y, z) for i, x, y, z in zip(p["id"], p["rx"], p["ry"], p["rz"])}
+    n_dup = len(p["id"]) - 12
+    for a, b in ids[ids[:, 0] > n_dup]:
+        assert pos[int(a)] != pos[int(b)]
 
 
 @pytest.mark.parametrize("case", ["ni16k", "lj2k", "lj_gap2", "lj_voids"])
