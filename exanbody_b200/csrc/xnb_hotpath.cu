@@ -149,6 +149,7 @@ struct xnb_ctx
   DBuf<unsigned long long> stream_off;
   DBuf<uint16_t> pool; DBuf<uint16_t*> cell_stream;
   int nbh_cap_l = 0; uint32_t nbh_slot_words = 0; bool nbh_full_cap = false;   // capacities of the tiled build (grow on demand)
+  int64_t n_nonempty_inner = 0;
   int64_t pool_used = 0; uint32_t max_neighbors = 0, max_cell_count = 0, max_stream = 0; double avg_stream = 0; bool have_nbh = false;
   // ---- misc device scalars
   DBuf<unsigned long long> scan_tmp64; DBuf<uint32_t> scan_tmp32;
@@ -954,7 +955,7 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
       if (hs[5] > c->nbh_slot_words) { c->nbh_slot_words = (uint32_t)(((size_t)(hs[5] * 1.12) + 64 + 7) & ~(size_t)7); again = true; }
       else if (hs[4] > (uint32_t)tp.cap_l) { c->nbh_slot_words = (uint32_t)(((size_t)(c->nbh_slot_words * 1.25) + 7) & ~(size_t)7); }
       if (again) continue;
-      c->pool_used = (int64_t)tot2[0]; c->max_neighbors = hs[0]; c->max_cell_count = hs[2]; c->max_stream = hs[3];
+      c->pool_used = (int64_t)tot2[0]; c->max_neighbors = hs[0]; c->n_nonempty_inner = hs[1]; c->max_cell_count = hs[2]; c->max_stream = hs[3];
       c->avg_stream = c->n_inner ? (double)tot2[1] / (double)c->n_inner : 0.0;
       if ((rc = t_end(c, XNB_T_NBH, st))) return rc;
       c->have_nbh = true;
@@ -964,17 +965,18 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
   }
   // ---- per-particle two-pass form (count -> sizes -> scan -> fill)
   if (n) LAUNCH((k_nbh_build<false>), nblk(n, 128), 128, st, g, (int)n, gap, md2, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
-  CK(cudaMemsetAsync(s32 + 3, 0, 20, st)); CK(cudaMemsetAsync(c->d_scalars64.p + 2, 0, 8, st));
+  CK(cudaMemsetAsync(s32 + 3, 0, 16, st)); CK(cudaMemsetAsync(s32 + 109, 0, 8, st)); CK(cudaMemsetAsync(c->d_scalars64.p + 2, 0, 8, st));
   LAUNCH(k_nbh_cell_sizes, nblk((int64_t)g.n_cells * 32, 128), 128, st, g, g.n_cells, c->cell_start.p, c->cell_count.p, c->nb_len.p, c->nb_cnt.p, c->nb_off.p,
-         c->stream_size.p, c->stream_size_padded.p, s32 + 3, s32 + 5, s32 + 6, s32 + 7, c->d_scalars64.p + 2, s32);
+         c->stream_size.p, c->stream_size_padded.p, s32 + 3, s32 + 5, s32 + 6, s32 + 109, c->d_scalars64.p + 2, s32);
   rc = scan_exclusive<uint32_t, unsigned long long>(c, c->stream_size_padded.p, c->stream_off.p, (size_t)g.n_cells, c->d_scalars64.p + 1, c->scan_tmp64, st); if (rc) return rc;
   unsigned long long tot = 0, tot2[2] = {0, 0}; uint32_t mx = 0;
   rc = read_back(c, c->d_scalars64.p + 1, 2, tot2, st); if (rc) return rc;
   tot = tot2[0];
-  uint32_t sc[5] = {0, 0, 0, 0, 0};
-  rc = read_back(c, s32 + 3, 5, sc, st); if (rc) return rc;
+  uint32_t sc[4] = {0, 0, 0, 0}, sc2[2] = {0, 0};
+  rc = read_back(c, s32 + 3, 4, sc, st); if (rc) return rc;
+  rc = read_back(c, s32 + 109, 2, sc2, st); if (rc) return rc;
   mx = sc[0];
-  c->pool_used = (int64_t)tot; c->max_neighbors = mx; c->max_cell_count = sc[2]; c->max_stream = sc[3];
+  c->pool_used = (int64_t)tot; c->max_neighbors = mx; c->max_cell_count = sc[2]; c->max_stream = sc[3]; c->n_nonempty_inner = sc2[1];
   c->avg_stream = c->n_inner ? (double)tot2[1] / (double)c->n_inner : 0.0;      // padded u16 words per inner particle
   // realloc_stream_pool (chunk_neighbors.h:70-96): grow with the reference's 5% head-room (update-particles.msp:20)
   CK(c->pool.ensure((size_t)tot + 64, 0, 1.05));
@@ -1011,51 +1013,54 @@ static TileCfg make_tiles(const xnb_ctx* c, bool ghost)
   tp.gap = (int)std::ceil(c->nbh_dist / c->cs);
   for (int d = 0; d < 3; d++) { tp.lo[d] = ghost ? 0 : g.gl; tp.hi[d] = ghost ? g.dims[d] : g.dims[d] - g.gl; }
   const int ni = tp.hi[0] - tp.lo[0], nj = tp.hi[1] - tp.lo[1], nk = tp.hi[2] - tp.lo[2];
-  const int64_t ncell_in = (int64_t)(g.dims[0] - 2 * g.gl) * (g.dims[1] - 2 * g.gl) * (g.dims[2] - 2 * g.gl);
-  const double avg = std::max(ncell_in > 0 ? (double)c->n_inner / (double)ncell_in : 1.0, 1.0);
+  // occupancy of the non-empty inner cells (clusters + voids: the dense tiles set the capacities)
+  const double ne = (double)std::max<int64_t>(c->n_nonempty_inner, 1);
+  const double avg = std::max((double)c->n_inner / ne, 1.0);
   const double mx = (double)std::max<uint32_t>(c->max_cell_count, 1);
-  const double wpp = std::max(c->avg_stream, 8.0);                  // stream words per particle
-  // candidate tile shapes: pick the one with the best (resident warps per SM) subject to the shared memory budget,
-  // preferring fewer staged bytes per particle
-  const size_t SM_BYTES = 224 * 1024;
+  const double wpp = std::max(c->avg_stream, 8.0);                  // padded stream words per inner particle
+  const size_t SM_BYTES = 227 * 1024;
+  static const int shapes[][2] = {{4, 2}, {4, 1}, {2, 2}, {2, 1}, {1, 1}, {8, 2}, {4, 4}, {4, 3}, {8, 1}};
   double best_score = -1; int bi = 1, bj = 1, bthreads = 64; size_t bsmem = 0; int bcap = 0, bcaps = 0;
   const int eti = env_int("XNB_TILE_I"), etj = env_int("XNB_TILE_J");
-  for (int ti = 1; ti <= std::min(8, ni); ti++) for (int tj = 1; tj <= std::min(4, nj); tj++)
+  const double slack = 1.10;
+  for (const auto& sh : shapes)
   {
+    const int ti = std::min(sh[0], ni), tj = std::min(sh[1], nj);
     if (eti > 0 && ti != std::min(eti, ni)) continue;
     if (etj > 0 && tj != std::min(etj, nj)) continue;
     const int tc = ti * tj;
+    if (tc > 32) continue;
     const double tile_avg = avg * tc;
-    const double tile_max = std::min(mx * tc, tile_avg * 1.10 + 10.0);
-    int threads = 32 * (int)std::ceil(tile_max / 32.0);
-    if (threads > 640) continue;
+    int threads = 32 * (int)std::ceil(std::min(mx * tc, tile_avg * 1.08 + 8.0) / 32.0);
+    if (threads > SWEEP_MAX_THREADS) continue;
     threads = std::max(threads, 64);
     const int hx = ti + 2 * tp.gap, hy = tj + 2 * tp.gap, hz = 2 * tp.gap + 1;
     const int nh = hx * hy * hz;
-    const size_t head = (((size_t)(nh + 1 + 4 * tc + 2) * 4 + 15) & ~(size_t)15);
-    const size_t cap = (size_t)std::min(mx * nh, avg * nh * 1.2 + 128.0);
-    size_t cap_s = (size_t)std::min((double)c->max_stream * tc, wpp * tile_avg * 1.15 + 512.0);
+    const size_t head = (((size_t)(2 * nh + 1 + 4 * tc + 2) * 4 + 15) & ~(size_t)15);
+    const size_t cap = (size_t)std::min(mx * nh, avg * nh * slack + 64.0);
+    if (cap > 32767) continue;
+    size_t cap_s = (size_t)std::min((double)c->max_stream * tc, wpp * tile_avg * slack + 256.0);
     cap_s = (cap_s + 7) & ~(size_t)7;
-    const size_t smem = head + cap_s * 2 + cap * 24;
+    const size_t smem = head + (cap_s + 16) * 2 + cap * 24;
     if (smem + 1024 > SM_BYTES) continue;
     const int by_smem = (int)(SM_BYTES / (smem + 1024));
-    const int by_regs = 65536 / (threads * 96);
+    const int by_regs = 65536 / (threads * 104);
     const int by_warps = 64 / (threads / 32);
     const int resident = std::min(std::min(by_smem, by_regs), std::min(by_warps, 32));
     if (resident < 1) continue;
-    const double warps = resident * (threads / 32) * (tile_avg / threads);      // useful resident warps
-    const double staged_per_particle = (double)smem / tile_avg;
-    const double score = warps - 1e-3 * staged_per_particle;
+    const double warps = resident * (tile_avg / 32.0);                // useful resident warps per SM
+    const double staged_per_particle = (double)smem / tile_avg;       // tie-break: less staging per particle
+    const double score = warps + (resident >= 2 ? 4.0 : 0.0) - 1e-3 * staged_per_particle;
     if (score > best_score) { best_score = score; bi = ti; bj = tj; bthreads = threads; bsmem = smem; bcap = (int)cap; bcaps = (int)cap_s; }
   }
   if (best_score < 0)
   {
     // nothing fits (fat cells): 1x1 tiles without staging, the kernel takes its global-memory path
-    bi = bj = 1; bthreads = 32 * (int)std::min(16.0, std::max(2.0, std::ceil(avg / 32.0))); bcap = 0; bcaps = 8;
+    bi = bj = 1; bthreads = 32 * (int)std::min((double)(SWEEP_MAX_THREADS / 32), std::max(2.0, std::ceil(avg / 32.0))); bcap = 0; bcaps = 0;
     const int nh = (1 + 2 * tp.gap) * (1 + 2 * tp.gap) * (1 + 2 * tp.gap);
-    bsmem = (((size_t)(nh + 1 + 4 + 2) * 4 + 15) & ~(size_t)15) + 16;
+    bsmem = (((size_t)(2 * nh + 1 + 4 + 2) * 4 + 15) & ~(size_t)15) + 16;
   }
-  if (env_int("XNB_FORCE_THREADS") > 0) bthreads = env_int("XNB_FORCE_THREADS");
+  if (env_int("XNB_FORCE_THREADS") > 0) bthreads = std::min(env_int("XNB_FORCE_THREADS"), SWEEP_MAX_THREADS);
   tp.ti = bi; tp.tj = bj;
   tp.tiles_i = (ni + bi - 1) / bi; tp.tiles_j = (nj + bj - 1) / bj;
   tp.hx = bi + 2 * tp.gap; tp.hy = bj + 2 * tp.gap; tp.hz = 2 * tp.gap + 1;
@@ -1076,13 +1081,13 @@ static int launch_force(xnb_ctx* c, bool ghost, const LJP& lj, double dth, doubl
   static bool attr_done[2][2] = {{false, false}, {false, false}};
   if (!attr_done[MODE][EV ? 1 : 0])
   {
-    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_lj_force_tiled<MODE, EV>));
-    CK(cudaFuncSetAttribute(k_lj_force_tiled<MODE, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_lj_sweep<MODE, EV>));
+    CK(cudaFuncSetAttribute(k_lj_sweep<MODE, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
     attr_done[MODE][EV ? 1 : 0] = true;
   }
   int rc;
   if ((rc = t_begin(c, XNB_T_FORCE, st))) return rc;
-  k_lj_force_tiled<MODE, EV><<<t.blocks, t.threads, t.smem, st>>>(c->g, t.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
+  k_lj_sweep<MODE, EV><<<t.blocks, t.threads, t.smem, st>>>(c->g, t.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
       fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p,
       c->stream_size.p, EV ? c->ev_partials.p : nullptr);
   c->launches++; CK(cudaGetLastError());

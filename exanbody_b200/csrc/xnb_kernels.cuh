@@ -650,7 +650,7 @@ __global__ void k_nbh_cell_sizes(GridP g, int n_cells, const uint32_t* __restric
     atomicMax(max_chunk_words, mxc);
     const int ci = c % g.dims[0], cj = (c / g.dims[0]) % g.dims[1], ck = c / (g.dims[0] * g.dims[1]);
     const bool inner = ci >= g.gl && ci < g.dims[0] - g.gl && cj >= g.gl && cj < g.dims[1] - g.gl && ck >= g.gl && ck < g.dims[2] - g.gl;
-    if (inner) atomicAdd(inner_words, (unsigned long long)((sz + 7u) & ~7u));
+    if (inner) { atomicAdd(inner_words, (unsigned long long)((sz + 7u) & ~7u)); atomicAdd(max_chunk_words + 1, 1u); }   // [+1]: non-empty inner cells
   }
 }
 
@@ -709,7 +709,7 @@ struct NbhCellOut
   uint32_t* stream_size;             // u16 words
   uint32_t* cell_stream_bytes;       // bytes (GridChunkNeighbors::m_cell_stream_size)
   unsigned long long* stream_off;    // u16 offset of the stream in the pool
-  uint32_t* stats;                   // [0] max neighbours [2] max cell count [3] max padded stream [4] needed cap_l [5] needed slot_words
+  uint32_t* stats;                   // [0] max neighbours [1] non-empty inner cells [2] max cell count [3] max padded stream [4] needed cap_l [5] needed slot_words
   unsigned long long* totals;        // [0] padded words of all cells [1] padded words of inner cells
 };
 
@@ -1013,7 +1013,7 @@ k_nbh_fused(GridP g, NbhTileP tp,
         atomicMax(&s_stats[2], nA); atomicMax(&s_stats[3], szp); atomicMax(&s_stats[5], szp);
         atomicAdd(&s_tot[0], (unsigned long long)szp);
         const bool inner = cia >= g.gl && cia < g.dims[0] - g.gl && cja >= g.gl && cja < g.dims[1] - g.gl && ck >= g.gl && ck < g.dims[2] - g.gl;
-        if (inner) atomicAdd(&s_tot[1], (unsigned long long)szp);
+        if (inner) { atomicAdd(&s_tot[1], (unsigned long long)szp); atomicAdd(&s_stats[1], 1u); }
       }
     }
   }
@@ -1024,7 +1024,7 @@ k_nbh_fused(GridP g, NbhTileP tp,
   if (done == (uint32_t)nwarp - 1u)
   {
     __threadfence_block();
-    if (lane < 6 && s_stats[lane]) atomicMax(&out.stats[lane], s_stats[lane]);
+    if (lane < 6 && s_stats[lane]) { if (lane == 1) atomicAdd(&out.stats[1], s_stats[1]); else atomicMax(&out.stats[lane], s_stats[lane]); }
     if (lane < 2 && s_tot[lane]) atomicAdd(&out.totals[lane], s_tot[lane]);
   }
 }
@@ -1042,159 +1042,51 @@ __global__ void k_max_u32(int n, const uint32_t* __restrict__ a, uint32_t* __res
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K3 pair sweep with the Lennard-Jones functor.
+// K3 pair sweep with the Lennard-Jones functor (the hot-path kernel).
 // reference: compute_cell_particle_pairs_impl_default.h:87-239 (stream decoding, d2 re-test against rcut^2),
-//            lennard_jones.cu:46-56,106-124 (functor).
-// One thread per particle of the swept range; the thread walks the particle's u16 list through the cell's u32 offset
-// table.  dr = r_b - r_a (:183); accept iff d2 > 0 && d2 <= rcut2 (:186) with d2 evaluated exactly like the oracle.
-// The functor is restated with one reciprocal instead of sqrt + two divisions:
-//   de/r = -24 eps (2 s12 - s6) / d2 ,  s6 = (sigma^2/d2)^3     (identical to lennard_jones.cu:46-56 up to rounding)
+//            lennard_jones.cu:46-56,106-124 (functor, buffer-less call form).
+// dr = r_b - r_a (:183); accept iff d2 > 0 && d2 <= rcut2 (:186) with d2 evaluated exactly like the oracle
+// (((x*x)+(y*y))+(z*z), every operation rounded).  The functor is restated with one reciprocal instead of sqrt + two
+// divisions:  de/r = -24 eps (2 s12 - s6) / d2 = (24 eps - 48 eps s6) (s6 / d2),  s6 = (sigma^2/d2)^3.
 // MODE 0: f += sum            (op lennard_jones_force, accumulating like the reference functor)
 // MODE 1: f  = sum / m[type]; v += f*dth   (zero_particle_force + lennard_jones_force + divide_force_by_type_scalar
 //                                           + verlet_second_half fused; dth = 0 leaves v untouched bit-for-bit)
 // EV: additionally accumulate per-block partial sums of energy and virial (oracle-defined observables)
+//
+// One block = one TILE of ti x tj cells (same k), one thread per particle of the tile.  The block stages into shared
+// memory (cp.async)
+//   (a) the positions of every particle of the tile's halo box ((ti+2gap) x (tj+2gap) x (2gap+1) cells, clamped to the
+//       grid) as {x,y} pairs + z: each neighbour cell is fetched from HBM/L2 once per tile with coalesced reads, and a
+//       candidate costs one LDS.128 + one LDS.64;
+//   (b) the u16 neighbour streams of the tile's cells, verbatim (each cell stream is one 16-byte aligned block).
+// A short pre-pass (one thread per particle, hopping over its own group headers) rewrites every non-candidate word of
+// the staged copy -- group counter, (cell code, count) headers, alignment padding -- as 0x8000 | base, base = index of
+// the neighbour cell's first particle in the staged halo.  After that a list is a flat sequence in which a word >= 0x8000
+// sets the current base and anything else is a candidate p_b, so the main loop has no nested structure and no
+// divergent branch: every trip reads four words with one aligned LDS.64 and evaluates up to four candidates with
+// independent FP64 dependency chains.
 // ------------------------------------------------------------------------------------------------------------------
 struct LJP { double eps24; double sig2; double rcut2; double eps4; double neg_eps48; };
 
-template <int MODE, bool EV>
-__global__ void __launch_bounds__(128)
-k_lj_force(GridP g, int first, int n, int n_zero_end, LJP lj, double dth,
-           const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
-           double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
-           double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
-           const uint8_t* __restrict__ type, const double* __restrict__ mass,
-           const uint32_t* __restrict__ atom_cell, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
-           const uint16_t* const* __restrict__ cell_stream, double* __restrict__ ev_partials /* [gridDim.x][7] */)
-{
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = first + t;
-  double ax = 0., ay = 0., az = 0.;
-  double e = 0., wxx = 0., wyy = 0., wzz = 0., wxy = 0., wxz = 0., wyz = 0.;
-  if (t < n)
-  {
-    const uint32_t ca = atom_cell[i];
-    const uint32_t na = cell_count[ca], pa = (uint32_t)i - cell_start[ca];
-    const uint16_t* base = cell_stream[ca];
-    const uint32_t off = reinterpret_cast<const uint32_t*>(base)[pa];
-    const uint16_t* s = base + 2u * (na + 1u) + (off - 1u);
-    const double xa = rx[i], ya = ry[i], za = rz[i];
-    const int di = g.dims[0], dj = g.dims[1];
-    int groups = *s++;
-    for (; groups > 0; --groups)
-    {
-      const uint32_t enc = *s++;
-      int cnt = *s++;
-      const int ri = (int)(enc & 31u) - 16, rj = (int)((enc >> 5) & 31u) - 16, rk = (int)((enc >> 10) & 31u) - 16;
-      const uint32_t sb = cell_start[(int)ca + (rk * dj + rj) * di + ri];
-      for (; cnt > 0; --cnt)
-      {
-        const uint32_t j = sb + *s++;
-        const double dx = __dadd_rn(rx[j], -xa), dy = __dadd_rn(ry[j], -ya), dz = __dadd_rn(rz[j], -za);
-        const double d2 = norm2_exact(dx, dy, dz);
-        if (d2 > 0.0 && d2 <= lj.rcut2)
-        {
-          const double inv = 1.0 / d2;
-          const double s2 = lj.sig2 * inv;
-          const double s6 = s2 * s2 * s2;
-          const double de = -lj.eps24 * (2.0 * s6 * s6 - s6) * inv;
-          ax += de * dx; ay += de * dy; az += de * dz;
-          if (EV)
-          {
-            e += 0.5 * lj.eps4 * (s6 * s6 - s6);
-            const double px = de * dx, py = de * dy, pz = de * dz;
-            wxx -= 0.5 * dx * px; wyy -= 0.5 * dy * py; wzz -= 0.5 * dz * pz;
-            wxy -= 0.5 * dx * py; wxz -= 0.5 * dx * pz; wyz -= 0.5 * dy * pz;
-          }
-        }
-      }
-    }
-    if (MODE == 0)
-    {
-      fx[i] += ax; fy[i] += ay; fz[i] += az;
-    }
-    else
-    {
-      const double m = mass[type[i]];
-      ax = __ddiv_rn(ax, m); ay = __ddiv_rn(ay, m); az = __ddiv_rn(az, m);
-      fx[i] = ax; fy[i] = ay; fz[i] = az;
-      if (dth != 0.0)
-      {
-        vx[i] = __dadd_rn(vx[i], __dmul_rn(ax, dth));
-        vy[i] = __dadd_rn(vy[i], __dmul_rn(ay, dth));
-        vz[i] = __dadd_rn(vz[i], __dmul_rn(az, dth));
-      }
-    }
-  }
-  else if (MODE == 1 && i < n_zero_end)
-  {
-    fx[i] = 0.; fy[i] = 0.; fz[i] = 0.;   // zero_particle_force{ghost:true}: ghost particles keep f = 0
-  }
-  if (EV)
-  {
-    __shared__ double red[7][4];
-    double vals[7] = {e, wxx, wyy, wzz, wxy, wxz, wyz};
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int q = 0; q < 7; q++)
-    {
-      double v = vals[q];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) red[q][warp] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 7)
-    {
-      double v = 0.;
-      for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++) v += red[threadIdx.x][wq];
-      ev_partials[(size_t)blockIdx.x * 7 + threadIdx.x] = v;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// K3 tiled pair sweep (the hot-path kernel).  Same contract as k_lj_force above, which stays as the small reference
-// form (used for tiles that do not fit shared memory and by the fused-vs-unfused cross-check).
-//
-// One block = one TILE of ti x tj cells (same k).  The block stages into shared memory
-//   (a) the prefix table hstart[] of the tile's halo box ((ti+2gap) x (tj+2gap) x (2gap+1) cells, clamped to the grid),
-//   (b) the positions of every particle of the halo box as three fp64 arrays (coalesced SoA loads: each neighbour cell
-//       is fetched once per tile instead of once per particle),
-//   (c) the u16 neighbour streams of the tile's cells, verbatim (each cell stream is one contiguous 16-byte aligned
-//       block of the GridChunkNeighbors pool).
-// Then one thread per particle walks its list out of shared memory with a FLAT loop over pair words; the group header
-// (cell code, count) is consumed by a short predicated block when the running position reaches the end of the
-// current group, so the 32 lanes of a warp advance through their own lists in lock step without diverging on the
-// nested structure of the reference format, and no lane ever issues a scattered global load.
-// ------------------------------------------------------------------------------------------------------------------
 struct TileP
 {
   int ti, tj;        // cells per tile along i and j
   int gap;           // neighbour cell layers = ceil(nbh_dist / cell_size)
   int lo[3], hi[3];  // swept cell range [lo,hi) per axis (inner cells, or all cells when ghost=true)
   int tiles_i, tiles_j;
-  int cap;           // staging capacity in particles
+  int cap;           // staging capacity in particles (< 32768)
   int cap_s;         // staging capacity in u16 stream words (multiple of 8)
   int hx, hy, hz;    // nominal halo box dims
 };
 
-// d2 in (0, rcut2]  <=>  bits(d2) - 1 < bits(rcut2) as unsigned integers (d2 >= +0, never NaN for finite positions):
-// keeps the two comparisons off the FP64 pipe
-XNB_DEVINL bool in_cut(double d2, unsigned long long rcut2_bits)
-{
-  return (unsigned long long)(__double_as_longlong(d2) - 1ll) < rcut2_bits;
-}
-
-// 1/x for normal x > 0: hardware seed (MUFU.RCP64H) + Newton steps; two steps give relative error < 2^-50
+// 1/x for normal x > 0: hardware seed (MUFU.RCP64H, ~2^-20) + one cubically convergent step: y (1 + e + e^2), e = 1 - x y
 XNB_DEVINL double fast_rcp(double x)
 {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  return y;
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);                      // relative error e^3 ~ 2^-60, + rounding
 }
 
 // asynchronous global -> shared copies (LDGSTS): issued back to back, completed by cp_async_wait_all()
@@ -1210,8 +1102,7 @@ XNB_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "mem
 
 struct LJAcc { double ax, ay, az, e, wxx, wyy, wzz, wxy, wxz, wyz; };
 
-// the Lennard-Jones functor, buffer-less call form (lennard_jones.cu:106-124) restated with one reciprocal:
-//   de/r = -24 eps (2 s12 - s6) / d2 = (24 eps - 48 eps s6) * (s6 / d2),  s6 = (sigma^2/d2)^3
+// the Lennard-Jones functor on one pair (global-memory fallback path)
 template <bool EV>
 XNB_DEVINL void lj_pair(const LJP& lj, double dx, double dy, double dz, double d2, LJAcc& a)
 {
@@ -1229,23 +1120,35 @@ XNB_DEVINL void lj_pair(const LJP& lj, double dx, double dy, double dz, double d
   }
 }
 
-// U pairs at once, branch free, so that the U reciprocal / power chains are independent and overlap in the FP64 pipe
-template <bool EV, int U>
-XNB_DEVINL void lj_pairs(const LJP& lj, const double (&dx)[U], const double (&dy)[U], const double (&dz)[U], const double (&d2)[U], const bool (&ok)[U], LJAcc& a)
+constexpr uint32_t SW_MARK = 0x8000u;      // staged stream word >= SW_MARK: "set base", not a candidate
+constexpr int SWEEP_MAX_THREADS = 384;
+
+// scheduling fence: everything that produces v0..v3 is placed before this point and everything that consumes them after
+// it, so the four candidates advance phase by phase (independent FP64 chains in flight) instead of one after the other
+XNB_DEVINL void fence4(double& v0, double& v1, double& v2, double& v3) { asm volatile("" : "+d"(v0), "+d"(v1), "+d"(v2), "+d"(v3)); }
+
+// four candidates at once.  ok[u] = false (not a candidate, or outside the cut) contributes exactly zero; its d2 may be
+// anything (the coefficient is replaced, not multiplied).
+template <bool EV>
+XNB_DEVINL void lj_pairs4(const LJP& lj, const double (&dx)[4], const double (&dy)[4], const double (&dz)[4], double (&d2)[4], const bool (&ok)[4], LJAcc& a)
 {
-  double inv[U], s6[U], de[U];
+  double inv[4], s6[4], de[4];
+  fence4(d2[0], d2[1], d2[2], d2[3]);
 #pragma unroll
-  for (int u = 0; u < U; u++) inv[u] = fast_rcp(d2[u]);
+  for (int u = 0; u < 4; u++) inv[u] = fast_rcp(d2[u]);
+  fence4(inv[0], inv[1], inv[2], inv[3]);
 #pragma unroll
-  for (int u = 0; u < U; u++) { const double s2 = lj.sig2 * inv[u]; s6[u] = s2 * s2 * s2; }
+  for (int u = 0; u < 4; u++) { const double s2 = lj.sig2 * inv[u]; s6[u] = s2 * s2 * s2; }
+  fence4(s6[0], s6[1], s6[2], s6[3]);
 #pragma unroll
-  for (int u = 0; u < U; u++) { de[u] = fma(lj.neg_eps48, s6[u], lj.eps24) * (s6[u] * inv[u]); if (!ok[u]) de[u] = 0.0; }
+  for (int u = 0; u < 4; u++) { de[u] = fma(lj.neg_eps48, s6[u], lj.eps24) * (s6[u] * inv[u]); if (!ok[u]) de[u] = 0.0; }
+  fence4(de[0], de[1], de[2], de[3]);
 #pragma unroll
-  for (int u = 0; u < U; u++) { a.ax = fma(de[u], dx[u], a.ax); a.ay = fma(de[u], dy[u], a.ay); a.az = fma(de[u], dz[u], a.az); }
+  for (int u = 0; u < 4; u++) { a.ax = fma(de[u], dx[u], a.ax); a.ay = fma(de[u], dy[u], a.ay); a.az = fma(de[u], dz[u], a.az); }
   if (EV)
   {
 #pragma unroll
-    for (int u = 0; u < U; u++)
+    for (int u = 0; u < 4; u++)
     {
       if (ok[u]) a.e += 0.5 * lj.eps4 * (s6[u] * s6[u] - s6[u]);
       const double px = de[u] * dx[u], py = de[u] * dy[u], pz = de[u] * dz[u];
@@ -1255,49 +1158,97 @@ XNB_DEVINL void lj_pairs(const LJP& lj, const double (&dx)[U], const double (&dy
   }
 }
 
+// decode one aligned chunk of four staged stream words: a word >= SW_MARK sets the base, anything else is a candidate
+// (if `live`); FIRST: the chunk's first `skip` words belong to the previous list
+template <bool FIRST>
+XNB_DEVINL void sweep_decode(const uint2 c, uint32_t skip, bool live, uint32_t& sb, uint32_t (&j)[4], bool (&ok)[4])
+{
+  const uint32_t w[4] = {c.x & 0xffffu, c.x >> 16, c.y & 0xffffu, c.y >> 16};
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+  {
+    const bool mark = w[u] >= SW_MARK;
+    if (mark) sb = w[u] & 0x7fffu;
+    ok[u] = !mark && live && (!FIRST || (uint32_t)u >= skip);
+    j[u] = sb + w[u];
+  }
+}
+
+XNB_DEVINL void sweep_load(const double2* __restrict__ XY, const double* __restrict__ Z, const uint32_t (&j)[4], const bool (&ok)[4],
+                           double2 (&pxy)[4], double (&pz)[4])
+{
+  // branch free: a slot that is not a candidate reads particle 0 (all such lanes hit the same address: a broadcast)
+#pragma unroll
+  for (int u = 0; u < 4; u++) { const uint32_t jj = ok[u] ? j[u] : 0u; pxy[u] = XY[jj]; pz[u] = Z[jj]; }
+}
+
+// one trip of the sweep: evaluate the four candidates whose positions were loaded last trip (pxy, pz, okc) while the
+// positions of the next trip (decoded from chunk cn) are fetched into (nxy, nz, okn)
+template <bool EV>
+XNB_DEVINL void sweep_trip(const LJP& lj, unsigned long long rc2b, const double2* __restrict__ XY, const double* __restrict__ Z, double xa, double ya, double za,
+                           const uint2 cn, bool live_next, uint32_t& sb,
+                           const double2 (&pxy)[4], const double (&pz)[4], const bool (&okc)[4],
+                           double2 (&nxy)[4], double (&nz)[4], bool (&okn)[4], LJAcc& acc)
+{
+  uint32_t jn[4];
+  sweep_decode<false>(cn, 0u, live_next, sb, jn, okn);
+  sweep_load(XY, Z, jn, okn, nxy, nz);
+  double dx[4], dy[4], dz[4], d2[4]; bool ok[4];
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+  {
+    dx[u] = __dadd_rn(pxy[u].x, -xa); dy[u] = __dadd_rn(pxy[u].y, -ya); dz[u] = __dadd_rn(pz[u], -za);
+    d2[u] = norm2_exact(dx[u], dy[u], dz[u]);
+  }
+  // accept iff d2 > 0 && d2 <= rcut2 (impl_default.h:186):  bits(d2) - 1 < bits(rcut2) as unsigned integers
+  // (d2 >= +0, never NaN for finite positions) -- one predicate, off the FP64 pipe
+#pragma unroll
+  for (int u = 0; u < 4; u++) ok[u] = okc[u] && (unsigned long long)(__double_as_longlong(d2[u]) - 1ll) < rc2b;
+  lj_pairs4<EV>(lj, dx, dy, dz, d2, ok, acc);
+}
+
 template <int MODE, bool EV>
-__global__ void __launch_bounds__(640)
-k_lj_force_tiled(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth,
-                 const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
-                 double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
-                 double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
-                 const uint8_t* __restrict__ type, const double* __restrict__ mass,
-                 const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
-                 const uint16_t* const* __restrict__ cell_stream, const uint32_t* __restrict__ stream_size,
-                 double* __restrict__ ev_partials /* [gridDim.x][7] */)
+__global__ void __launch_bounds__(SWEEP_MAX_THREADS)
+k_lj_sweep(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth,
+           const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+           double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
+           double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+           const uint8_t* __restrict__ type, const double* __restrict__ mass,
+           const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+           const uint16_t* const* __restrict__ cell_stream, const uint32_t* __restrict__ stream_size,
+           double* __restrict__ ev_partials /* [gridDim.x][7] */)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nh_max = tp.hx * tp.hy * tp.hz;
   const int tc_max = tp.ti * tp.tj;
   uint32_t* hstart = reinterpret_cast<uint32_t*>(smem_raw);                       // [nh_max + 1] particle prefix of the halo cells
-  uint32_t* tstart = hstart + nh_max + 1;                                           // [tc_max + 1] particle prefix of the tile cells
+  uint32_t* hfirst = hstart + nh_max + 1;                                           // [nh_max] flat index of each halo cell's first particle
+  uint32_t* tstart = hfirst + nh_max;                                               // [tc_max + 1] particle prefix of the tile cells
   uint32_t* tfirst = tstart + tc_max + 1;                                           // [tc_max] flat index of each tile cell's first particle
-  uint32_t* sstart = tfirst + tc_max;                                               // [tc_max + 1] stream word offset of each staged tile cell in S
-  uint32_t* swords = sstart + tc_max + 1;                                           // [tc_max] padded stream size of each tile cell (u16 words)
-  const size_t head = (((size_t)(nh_max + 1 + 4 * tc_max + 2) * 4 + 15) & ~(size_t)15);
-  uint16_t* S = reinterpret_cast<uint16_t*>(smem_raw + head);
-  double* sx = reinterpret_cast<double*>(smem_raw + head + (size_t)tp.cap_s * 2);
-  double* sy = sx + tp.cap;
-  double* sz = sy + tp.cap;
+  uint32_t* sstart = tfirst + tc_max;                                               // [tc_max + 1] u16 offset of each staged tile cell stream in S
+  uint32_t* ssize = sstart + tc_max + 1;                                            // [tc_max] stream size of each tile cell (u16 words, unpadded)
+  const size_t head = (((size_t)(2 * nh_max + 1 + 4 * tc_max + 2) * 4 + 15) & ~(size_t)15);
+  uint16_t* S = reinterpret_cast<uint16_t*>(smem_raw + head);                       // [cap_s + 16] (the loop reads up to 4 chunks ahead)
+  double2* XY = reinterpret_cast<double2*>(smem_raw + head + (size_t)(tp.cap_s + 16) * 2);  // [cap]
+  double* Z = reinterpret_cast<double*>(XY + tp.cap);                               // [cap]
   __shared__ uint32_t s_scan[32];
-  __shared__ int s_staged, s_q1, s_fit;
+  __shared__ int s_fit;
 
   // ---- tile geometry
-  const int nj_t = tp.tiles_j;
   int b = blockIdx.x;
   const int t_i = b % tp.tiles_i; b /= tp.tiles_i;
-  const int t_j = b % nj_t; const int ck = tp.lo[2] + b / nj_t;
+  const int t_j = b % tp.tiles_j; const int ck = tp.lo[2] + b / tp.tiles_j;
   const int ci0 = tp.lo[0] + t_i * tp.ti, cj0 = tp.lo[1] + t_j * tp.tj;
   const int tci = min(tp.ti, tp.hi[0] - ci0), tcj = min(tp.tj, tp.hi[1] - cj0);
   const int tcells = tci * tcj;
-  // halo box clamped to the local grid
   const int bx0 = max(ci0 - tp.gap, 0), bx1 = min(ci0 + tci - 1 + tp.gap, g.dims[0] - 1);
   const int by0 = max(cj0 - tp.gap, 0), by1 = min(cj0 + tcj - 1 + tp.gap, g.dims[1] - 1);
   const int bz0 = max(ck - tp.gap, 0), bz1 = min(ck + tp.gap, g.dims[2] - 1);
   const int HX = bx1 - bx0 + 1, HY = by1 - by0 + 1, HZ = bz1 - bz0 + 1;
-  const int NH = HX * HY * HZ;
+  const int NH = HX * HY * HZ, HXY = HX * HY;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
 
-  // ---- prefix table of the halo cells (block scan)
+  // ---- prefix tables: halo cells (block scan) and tile cells (one warp)
   {
     uint32_t carry = 0;
     for (int base = 0; base < NH; base += blockDim.x)
@@ -1306,89 +1257,107 @@ k_lj_force_tiled(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth
       uint32_t cnt = 0;
       if (h < NH)
       {
-        const int hxq = h % HX, hyq = (h / HX) % HY, hzq = h / (HX * HY);
-        cnt = cell_count[ijk_to_index(g.dims, bx0 + hxq, by0 + hyq, bz0 + hzq)];
+        const int hxq = h % HX, hyq = (h / HX) % HY, hzq = h / HXY;
+        const int c = ijk_to_index(g.dims, bx0 + hxq, by0 + hyq, bz0 + hzq);
+        cnt = cell_count[c]; hfirst[h] = cell_start[c];
       }
       uint32_t total;
       const uint32_t off = block_exclusive_scan<uint32_t>(cnt, &total, s_scan);
       if (h < NH) hstart[h] = carry + off;
       carry += total;
     }
-    if (threadIdx.x == 0) { hstart[NH] = carry; s_staged = (carry <= (uint32_t)tp.cap) ? 1 : 0; }
-    // tile cells: one lane per cell, warp scan of the counts (a tile has at most 32 cells)
-    if (threadIdx.x < 32)
+    if (threadIdx.x == 0) hstart[NH] = carry;
+    if (warp == nwarp - 1)
     {
-      const int q = threadIdx.x;
-      uint32_t cnt = 0;
+      const int q = lane;
+      uint32_t cnt = 0, sw = 0;
       if (q < tcells)
       {
         const int c = ijk_to_index(g.dims, ci0 + q % tci, cj0 + q / tci, ck);
-        cnt = cell_count[c]; tfirst[q] = cell_start[c]; swords[q] = (stream_size[c] + 7u) & ~7u;
+        cnt = cell_count[c]; tfirst[q] = cell_start[c]; ssize[q] = stream_size[c]; sw = (stream_size[c] + 7u) & ~7u;
       }
-      uint32_t x = cnt;
+      uint32_t x = cnt, y = sw;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (q >= o) x += y; }
-      if (q < tcells) tstart[q] = x - cnt;
-      if (q == tcells - 1) tstart[tcells] = x;
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const uint32_t x2 = __shfl_up_sync(0xffffffffu, x, o), y2 = __shfl_up_sync(0xffffffffu, y, o);
+        if (q >= o) { x += x2; y += y2; }
+      }
+      if (q < tcells) { tstart[q] = x - cnt; sstart[q] = y - sw; }
+      if (q == tcells - 1) { tstart[tcells] = x; sstart[tcells] = y; }
     }
   }
   __syncthreads();
-  const bool pos_staged = s_staged != 0;
   const int n_tile = (int)tstart[tcells];
+  if (threadIdx.x == 0) s_fit = (hstart[NH] <= (uint32_t)tp.cap && sstart[tcells] <= (uint32_t)tp.cap_s) ? 1 : 0;
+  __syncthreads();
+  const bool staged = s_fit != 0;
 
-  if (pos_staged && n_tile > 0)
+  if (staged && n_tile > 0)
   {
-    // ---- (b) halo positions: one warp per halo cell, lanes over its particles (coalesced reads)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    // ---- (a) halo positions: one warp per halo cell, lanes over its particles (coalesced reads)
     for (int h = warp; h < NH; h += nwarp)
     {
-      const uint32_t d0 = hstart[h], cnt = hstart[h + 1] - d0;
-      if (cnt == 0) continue;
-      const int hxq = h % HX, hyq = (h / HX) % HY, hzq = h / (HX * HY);
-      const uint32_t s0 = cell_start[ijk_to_index(g.dims, bx0 + hxq, by0 + hyq, bz0 + hzq)];
-      for (uint32_t p = lane; p < cnt; p += 32) { cp_async8(sx + d0 + p, rx + s0 + p); cp_async8(sy + d0 + p, ry + s0 + p); cp_async8(sz + d0 + p, rz + s0 + p); }
+      const uint32_t d0 = hstart[h], cnt = hstart[h + 1] - d0, s0 = hfirst[h];
+      for (uint32_t p = lane; p < cnt; p += 32)
+      {
+        cp_async8(&XY[d0 + p].x, rx + s0 + p); cp_async8(&XY[d0 + p].y, ry + s0 + p); cp_async8(Z + d0 + p, rz + s0 + p);
+      }
     }
+    // ---- (b) streams of the tile cells, 16 bytes per copy
+    for (int q = 0; q < tcells; q++)
+    {
+      const int c = ijk_to_index(g.dims, ci0 + q % tci, cj0 + q / tci, ck);
+      const uint4* src = reinterpret_cast<const uint4*>(cell_stream[c]);
+      uint4* dst = reinterpret_cast<uint4*>(S + sstart[q]);
+      const int nv = (int)((sstart[q + 1] - sstart[q]) >> 3);
+      for (int v = threadIdx.x; v < nv; v += blockDim.x) cp_async16(dst + v, src + v);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- (c) pre-pass: every thread rewrites the non-candidate words of its own list
+    for (int t = (int)threadIdx.x; t < n_tile; t += blockDim.x)
+    {
+      int q = 0;
+      while (q + 1 < tcells && (uint32_t)t >= tstart[q + 1]) q++;
+      const uint32_t pa = (uint32_t)t - tstart[q], na = tstart[q + 1] - tstart[q];
+      uint16_t* cs = S + sstart[q];
+      const uint32_t off0 = reinterpret_cast<const uint32_t*>(cs)[pa], off1 = reinterpret_cast<const uint32_t*>(cs)[pa + 1];
+      uint16_t* lists = cs + 2u * (na + 1u);
+      uint16_t* p = lists + (off0 - 1u);              // group counter (offsets are biased by the number of tables = 1)
+      uint16_t* const end = lists + (off1 - 1u);
+      const int cia = ci0 + q % tci, cja = cj0 + q / tci;
+      const int hb2 = ((ck - bz0) * HY + (cja - by0)) * HX + (cia - bx0) - 16 * (HXY + HX + 1);
+      *p++ = (uint16_t)SW_MARK;
+      while (p < end)
+      {
+        const uint32_t enc = p[0], n = p[1];
+        // halo index of cell (cia + ri, cja + rj, ck + rk), (ri,rj,rk) = 5-bit fields of enc minus 16 (chunk_neighbors.h:137-162)
+        const uint32_t sb = hstart[hb2 + (int)(enc >> 10) * HXY + (int)((enc >> 5) & 31u) * HX + (int)(enc & 31u)];
+        p[0] = (uint16_t)(SW_MARK | sb); p[1] = (uint16_t)(SW_MARK | sb);
+        p += 2u + n;
+      }
+      if (pa == na - 1u)
+      {
+        // alignment padding behind the last list of the cell
+        uint16_t* const pend = cs + (sstart[q + 1] - sstart[q]);
+        for (uint16_t* z = cs + ssize[q]; z < pend; z++) *z = (uint16_t)SW_MARK;
+      }
+    }
+    __syncthreads();
   }
 
   LJAcc acc;
   acc.e = acc.wxx = acc.wyy = acc.wzz = acc.wxy = acc.wxz = acc.wyz = 0.;
-  const unsigned long long rc2b = (unsigned long long)__double_as_longlong(lj.rcut2);
-  const int HXY = HX * HY;
+  const unsigned long long rc2b = (unsigned long long)__double_as_longlong(lj.rcut2);   // bits(d2) - 1 < bits(rcut2) <=> d2 in (0, rcut2]
 
-  // ---- (c) streams, staged in batches of whole cells that fit the stream buffer (normally the whole tile at once)
-  for (int q0 = 0; q0 < tcells && n_tile > 0;)
+  for (int t = (int)threadIdx.x; t < n_tile; t += blockDim.x)
   {
-    if (threadIdx.x == 0)
-    {
-      uint32_t sacc = 0; int q1 = q0;
-      while (q1 < tcells) { const uint32_t w = swords[q1]; if (q1 > q0 && sacc + w > (uint32_t)tp.cap_s) break; sstart[q1] = sacc; sacc += w; q1++; }
-      sstart[q1] = sacc; s_q1 = q1; s_fit = (sacc <= (uint32_t)tp.cap_s) ? 1 : 0;
-    }
-    __syncthreads();
-    const int q1 = s_q1;
-    const bool staged = pos_staged && s_fit != 0;
-    if (staged)
-    {
-      for (int q = q0; q < q1; q++)
-      {
-        const int c = ijk_to_index(g.dims, ci0 + q % tci, cj0 + q / tci, ck);
-        const uint4* src = reinterpret_cast<const uint4*>(cell_stream[c]);
-        uint4* dst = reinterpret_cast<uint4*>(S + sstart[q]);
-        const int nv = (int)(swords[q] >> 3);
-        for (int v = threadIdx.x; v < nv; v += blockDim.x) cp_async16(dst + v, src + v);
-      }
-    }
-    cp_async_wait_all();      // streams of this batch and (first batch) the halo positions
-    __syncthreads();
-  for (int t = (int)tstart[q0] + (int)threadIdx.x; t < (int)tstart[q1]; t += blockDim.x)
-  {
-    int q = q0;
-    while (q + 1 < q1 && (uint32_t)t >= tstart[q + 1]) q++;
+    int q = 0;
+    while (q + 1 < tcells && (uint32_t)t >= tstart[q + 1]) q++;
     const uint32_t pa = (uint32_t)t - tstart[q];
     const uint32_t i = tfirst[q] + pa;
     const uint32_t na = tstart[q + 1] - tstart[q];
-    const int cia = ci0 + q % tci, cja = cj0 + q / tci;
-    const int ca = ijk_to_index(g.dims, cia, cja, ck);
     const double xa = rx[i], ya = ry[i], za = rz[i];
     // epilogue operands fetched now so that their latency hides behind the pair loop
     double m = 1.0, ux = 0., uy = 0., uz = 0.;
@@ -1396,50 +1365,31 @@ k_lj_force_tiled(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth
     acc.ax = acc.ay = acc.az = 0.;
     if (staged)
     {
-      const uint16_t* cs = S + sstart[q];
-      const uint32_t off0 = reinterpret_cast<const uint32_t*>(cs)[pa], off1 = reinterpret_cast<const uint32_t*>(cs)[pa + 1];
-      const uint16_t* lists = cs + 2u * (na + 1u);
-      const uint16_t* p = lists + off0;          // = list start + 1: skips the group counter (off is biased by +1 table)
-      const uint16_t* const end = lists + (off1 - 1u);
-      const uint16_t* gend = p;
-      // halo index of cell (cia + ri, cja + rj, ck + rk) = hb2 + (enc >> 10) * HXY + ((enc >> 5) & 31) * HX + (enc & 31)
-      const int hb2 = ((ck - bz0) * HY + (cja - by0)) * HX + (cia - bx0) - 16 * (HXY + HX + 1);
+      const uint32_t cbase = sstart[q];
+      const uint32_t off0 = reinterpret_cast<const uint32_t*>(S + cbase)[pa], off1 = reinterpret_cast<const uint32_t*>(S + cbase)[pa + 1];
+      const uint32_t kb = cbase + 2u * (na + 1u) + off0;            // first word after the group counter
+      const uint32_t ke = cbase + 2u * (na + 1u) + (off1 - 1u);     // end of the list
+      const uint2* S64 = reinterpret_cast<const uint2*>(S);
+      uint32_t k = kb & ~3u;
       uint32_t sb = 0;
-      // next pair of this particle as a shared-memory particle index; the group header (cell code, count) is consumed
-      // when the running position reaches the end of the current group
-      auto fetch = [&]() -> uint32_t
+      // software pipeline: chunk t+2 is being read and the positions of trip t+1 are in flight while trip t is evaluated;
+      // two trips per iteration so that the two register sets (A, B) swap roles without copies
+      uint32_t jA[4]; bool okA[4], okB[4]; double2 xyA[4], xyB[4]; double zA[4], zB[4];
+      sweep_decode<true>(S64[k >> 2], kb & 3u, k < ke, sb, jA, okA);
+      sweep_load(XY, Z, jA, okA, xyA, zA);
+      uint2 c1 = S64[(k >> 2) + 1];
+      for (; k < ke; k += 8u)
       {
-        if (p == gend)
-        {
-          const uint32_t enc = p[0], n = p[1];
-          sb = hstart[hb2 + (int)(enc >> 10) * HXY + (int)((enc >> 5) & 31u) * HX + (int)(enc & 31u)];
-          p += 2; gend = p + n;
-        }
-        return sb + *p++;
-      };
-      // UNROLL independent pairs per trip: their FP64 dependency chains overlap (the loop is latency bound otherwise)
-      constexpr int UNROLL = 4;
-      while (p < end)
-      {
-        uint32_t j[UNROLL]; bool live[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) { live[u] = p < end; j[u] = live[u] ? fetch() : 0u; }
-        double dx[UNROLL], dy[UNROLL], dz[UNROLL], d2[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++)
-        {
-          dx[u] = __dadd_rn(sx[j[u]], -xa); dy[u] = __dadd_rn(sy[j[u]], -ya); dz[u] = __dadd_rn(sz[j[u]], -za);
-          d2[u] = norm2_exact(dx[u], dy[u], dz[u]);
-        }
-        // branch free: out-of-range / padding pairs are evaluated at d2 = 1 and contribute a zero coefficient
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) { live[u] = live[u] && in_cut(d2[u], rc2b); if (!live[u]) d2[u] = 1.0; }
-        lj_pairs<EV, UNROLL>(lj, dx, dy, dz, d2, live, acc);
+        const uint2 c2 = S64[(k >> 2) + 2], c3 = S64[(k >> 2) + 3];
+        sweep_trip<EV>(lj, rc2b, XY, Z, xa, ya, za, c1, k + 4u < ke, sb, xyA, zA, okA, xyB, zB, okB, acc);
+        sweep_trip<EV>(lj, rc2b, XY, Z, xa, ya, za, c2, k + 8u < ke, sb, xyB, zB, okB, xyA, zA, okA, acc);
+        c1 = c3;
       }
     }
     else
     {
       // tile too large for the staging buffers: walk the stream in global memory (nested form of impl_default.h:143-179)
+      const int ca = ijk_to_index(g.dims, ci0 + q % tci, cj0 + q / tci, ck);
       const uint16_t* base = cell_stream[ca];
       const uint32_t off = reinterpret_cast<const uint32_t*>(base)[pa];
       const uint16_t* s = base + 2u * (na + 1u) + (off - 1u);
@@ -1455,7 +1405,7 @@ k_lj_force_tiled(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth
           const uint32_t j = sbg + *s++;
           const double dx = __dadd_rn(rx[j], -xa), dy = __dadd_rn(ry[j], -ya), dz = __dadd_rn(rz[j], -za);
           const double d2 = norm2_exact(dx, dy, dz);
-          if (in_cut(d2, rc2b)) lj_pair<EV>(lj, dx, dy, dz, d2, acc);
+          if ((unsigned long long)(__double_as_longlong(d2) - 1ll) < rc2b) lj_pair<EV>(lj, dx, dy, dz, d2, acc);
         }
       }
     }
@@ -1476,9 +1426,6 @@ k_lj_force_tiled(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth
       }
     }
   }
-    __syncthreads();      // the stream buffer is reused by the next batch
-    q0 = q1;
-  }
   if (MODE == 1)
   {
     // zero_particle_force{ghost:true}: ghost particles keep f = 0 (each block clears its slice of the ghost range)
@@ -1489,9 +1436,8 @@ k_lj_force_tiled(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth
   }
   if (EV)
   {
-    __shared__ double red[7][20];
+    __shared__ double red[7][SWEEP_MAX_THREADS / 32];
     double vals[7] = {acc.e, acc.wxx, acc.wyy, acc.wzz, acc.wxy, acc.wxz, acc.wyz};
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int q = 0; q < 7; q++)
     {
@@ -1504,7 +1450,7 @@ k_lj_force_tiled(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth
     if (threadIdx.x < 7)
     {
       double v = 0.;
-      for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++) v += red[threadIdx.x][wq];
+      for (int wq = 0; wq < nwarp; wq++) v += red[threadIdx.x][wq];
       ev_partials[(size_t)blockIdx.x * 7 + threadIdx.x] = v;
     }
   }
