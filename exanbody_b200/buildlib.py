@@ -29,7 +29,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [NVCC] + FLAGS + ["-o", LIB, os.path.join(SRC, "xnb_hotpath.cu"), os.path.join(SRC, "xnb_host_inputs.cpp")]
+    cmd = [NVCC] + FLAGS + ["-o", LIB, os.path.join(SRC, "xnb_hotpath.cu"), os.path.join(SRC, "xnb_host_inputs.cpp"),
+                                           os.path.join(SRC, "xnb_host_decomp.cpp")]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

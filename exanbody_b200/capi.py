@@ -23,7 +23,7 @@ SYMBOLS = [
     "xnb_read_displ_over", "xnb_force_and_second_half", "xnb_run_steps", "xnb_first_iteration", "xnb_energy_virial",
     "xnb_view_chunk_neighbors", "xnb_stream_pool_u16", "xnb_get_streams", "xnb_get_amr", "xnb_get_backup",
     "xnb_rebuild_count", "xnb_kernel_launches", "xnb_timing_enable", "xnb_timing_read", "xnb_measure_dfma_peak",
-    "xnb_host_lattice_fcc",
+    "xnb_host_lattice_fcc", "xnb_host_rcb_block", "xnb_host_ghost_items",
 ]
 
 
@@ -79,6 +79,7 @@ def load():
         "xnb_view_chunk_neighbors": (I, [P, P, P, P]), "xnb_stream_pool_u16": (I64, [P]), "xnb_get_streams": (I, [P, P, P]),
         "xnb_get_amr": (I64, [P, P, P]), "xnb_get_backup": (I, [P, P]), "xnb_rebuild_count": (I64, [P]), "xnb_kernel_launches": (I64, [P]),
         "xnb_host_lattice_fcc": (I64, [C.POINTER(XnbLatticeCfg), I64] + [P] * 8),
+        "xnb_host_rcb_block": (I, [P, I, I, P, P]), "xnb_host_ghost_items": (I64, [P, P, I, I, I, I, I64, P, P, P]),
         "xnb_timing_enable": (I, [P, I]), "xnb_timing_read": (I, [P, P, P, I]), "xnb_measure_dfma_peak": (I, [I, P]),
     }
     for name, (res, args) in sig.items():
@@ -311,3 +312,25 @@ def lattice_fcc(bounds_max, cell_size, grid_dims, lattice_a, noise_sigma=0.0, ve
     if n < 0:
         raise XnbError(4, "lattice capacity")
     return {k: v[:n].copy() for k, v in out.items()}
+
+
+def rcb_block(grid_dims, nranks, rank):
+    """op init_rcb_grid (host only): this rank's block [start, end) of the domain cell grid"""
+    L = load()
+    gd = np.ascontiguousarray(grid_dims, np.int64); s = np.zeros(3, np.int64); e = np.zeros(3, np.int64)
+    rc = L.xnb_host_rcb_block(_p(gd), nranks, rank, _p(s), _p(e))
+    if rc:
+        raise XnbError(rc, "xnb_host_rcb_block")
+    return s, e
+
+
+def ghost_items(grid_dims, periodic, ghost_layers, nranks, src_rank, dst_rank):
+    """op ghost_comm_scheme, static part (host only): (sender cell, receiver ghost cell, flags) of every cell src_rank sends to dst_rank"""
+    L = load()
+    gd = np.ascontiguousarray(grid_dims, np.int64); per = np.ascontiguousarray(periodic, np.int32)
+    n = L.xnb_host_ghost_items(_p(gd), _p(per), ghost_layers, nranks, src_rank, dst_rank, 0, None, None, None)
+    if n < 0:
+        raise XnbError(2, "xnb_host_ghost_items")
+    a = np.zeros(n, np.uint32); b = np.zeros(n, np.uint32); f = np.zeros(n, np.uint32)
+    L.xnb_host_ghost_items(_p(gd), _p(per), ghost_layers, nranks, src_rank, dst_rank, n, _p(a), _p(b), _p(f))
+    return a, b, f

@@ -1,0 +1,99 @@
+// xnb_host_decomp.cpp -- static spatial decomposition and ghost item lists (host only, no CUDA).
+//   reference: src/core/lib/simple_block_rcb.cpp:27-59, src/grid_cell_particles/init_rcb_grid.cpp:65-77,
+//              src/mpi/update_ghosts_comm_scheme.cpp:130-196,429-443, src/mpi/include/exanb/mpi/ghosts_comm_scheme.h:46-81
+#include "../../include/xnb_hotpath.h"
+#include "xnb_host_decomp.hpp"
+#include <algorithm>
+
+namespace xnb {
+
+// GhostBoundaryModifier flags, same bit layout as the reference (ghosts_comm_scheme.h:46-81); mirrored in xnb_common.cuh
+enum : uint32_t { H_SHIFT_X = 1u << 0, H_SIDE_X = 1u << 2, H_SHIFT_Y = 1u << 3, H_SIDE_Y = 1u << 5, H_SHIFT_Z = 1u << 6, H_SIDE_Z = 1u << 8 };
+
+Block simple_block_rcb(Block b, size_t n_parts, size_t part)
+{
+  while (n_parts > 1)
+  {
+    const size_t pivot = n_parts / 2;
+    const bool side = part >= pivot;
+    const int64_t d[3] = {b.e[0] - b.s[0], b.e[1] - b.s[1], b.e[2] - b.s[2]};
+    int ax = 2;
+    if (d[0] >= d[1] && d[0] >= d[2]) ax = 0; else if (d[1] >= d[0] && d[1] >= d[2]) ax = 1;
+    if (side) b.s[ax] = b.s[ax] + d[ax] / 2; else b.e[ax] = b.s[ax] + d[ax] / 2;
+    if (side) { part -= pivot; n_parts -= pivot; } else n_parts = pivot;
+  }
+  return b;
+}
+
+void enumerate_sends(const std::vector<Block>& blocks, const int64_t ddims[3], const int periodic[3], int from, int to, int gl,
+                     std::vector<HostItem>& out)
+{
+  const Block& bf = blocks[(size_t)from];
+  const Block& bt = blocks[(size_t)to];
+  int64_t gs[3], ge[3], tdims[3], fdims[3], foff[3];
+  for (int d = 0; d < 3; d++) { gs[d] = bt.s[d] - gl; ge[d] = bt.e[d] + gl; tdims[d] = ge[d] - gs[d]; fdims[d] = bf.e[d] - bf.s[d] + 2 * gl; foff[d] = bf.s[d] - gl; }
+  const int lo[3] = {periodic[0] ? -1 : 0, periodic[1] ? -1 : 0, periodic[2] ? -1 : 0};
+  const int hi[3] = {periodic[0] ? 1 : 0, periodic[1] ? 1 : 0, periodic[2] ? 1 : 0};
+  for (int sk = lo[2]; sk <= hi[2]; sk++) for (int sj = lo[1]; sj <= hi[1]; sj++) for (int si = lo[0]; si <= hi[0]; si++)
+  {
+    if (si == 0 && sj == 0 && sk == 0 && from == to) continue;
+    const int sh[3] = {si, sj, sk};
+    uint32_t flags = 0;
+    if (si == -1) flags |= H_SHIFT_X; if (si == 1) flags |= H_SHIFT_X | H_SIDE_X;
+    if (sj == -1) flags |= H_SHIFT_Y; if (sj == 1) flags |= H_SHIFT_Y | H_SIDE_Y;
+    if (sk == -1) flags |= H_SHIFT_Z; if (sk == 1) flags |= H_SHIFT_Z | H_SIDE_Z;
+    int64_t a[3], b[3];
+    bool empty = false;
+    for (int d = 0; d < 3; d++)
+    {
+      const int64_t s = (int64_t)sh[d] * ddims[d];
+      a[d] = std::max(bf.s[d], gs[d] - s); b[d] = std::min(bf.e[d], ge[d] - s);
+      if (a[d] >= b[d]) empty = true;
+    }
+    if (empty) continue;
+    for (int64_t k = a[2]; k < b[2]; k++) for (int64_t j = a[1]; j < b[1]; j++) for (int64_t i = a[0]; i < b[0]; i++)
+    {
+      const int64_t dl[3] = {i, j, k};
+      int64_t t[3];
+      bool inside_inner = true;
+      for (int d = 0; d < 3; d++) { t[d] = dl[d] + (int64_t)sh[d] * ddims[d]; if (t[d] < bt.s[d] || t[d] >= bt.e[d]) inside_inner = false; }
+      if (inside_inner) continue;   // can only happen for degenerate tiny domains
+      HostItem it;
+      it.src_cell = (uint32_t)(((k - foff[2]) * fdims[1] + (j - foff[1])) * fdims[0] + (i - foff[0]));
+      it.dst_cell = (uint32_t)(((t[2] - gs[2]) * tdims[1] + (t[1] - gs[1])) * tdims[0] + (t[0] - gs[0]));
+      it.flags = flags;
+      out.push_back(it);
+    }
+  }
+}
+
+} // namespace xnb
+
+extern "C" int xnb_host_rcb_block(const int64_t grid_dims[3], int nranks, int rank, int64_t start[3], int64_t end[3])
+{
+  if (!grid_dims || !start || !end || nranks < 1 || rank < 0 || rank >= nranks) return XNB_ERR_INVALID;
+  const xnb::Block whole{{0, 0, 0}, {grid_dims[0], grid_dims[1], grid_dims[2]}};
+  const xnb::Block b = xnb::simple_block_rcb(whole, (size_t)nranks, (size_t)rank);
+  for (int d = 0; d < 3; d++) { start[d] = b.s[d]; end[d] = b.e[d]; }
+  return XNB_OK;
+}
+
+extern "C" int64_t xnb_host_ghost_items(const int64_t grid_dims[3], const int32_t periodic[3], int ghost_layers, int nranks, int from, int to,
+                                        int64_t capacity, uint32_t* src_cell, uint32_t* dst_cell, uint32_t* flags)
+{
+  if (!grid_dims || !periodic || nranks < 1 || from < 0 || from >= nranks || to < 0 || to >= nranks || ghost_layers < 0) return -1;
+  std::vector<xnb::Block> blocks((size_t)nranks);
+  const xnb::Block whole{{0, 0, 0}, {grid_dims[0], grid_dims[1], grid_dims[2]}};
+  for (int r = 0; r < nranks; r++) blocks[(size_t)r] = xnb::simple_block_rcb(whole, (size_t)nranks, (size_t)r);
+  const int per[3] = {periodic[0] ? 1 : 0, periodic[1] ? 1 : 0, periodic[2] ? 1 : 0};
+  std::vector<xnb::HostItem> items;
+  xnb::enumerate_sends(blocks, grid_dims, per, from, to, ghost_layers, items);
+  if ((int64_t)items.size() <= capacity)
+    for (size_t q = 0; q < items.size(); q++)
+    {
+      if (src_cell) src_cell[q] = items[q].src_cell;
+      if (dst_cell) dst_cell[q] = items[q].dst_cell;
+      if (flags) flags[q] = items[q].flags;
+    }
+  return (int64_t)items.size();
+}

@@ -2,6 +2,7 @@
 // One xnb_ctx = one sub-domain on one GPU.  No CPU compute path exists here: without a CUDA device every entry fails.
 #include "../../include/xnb_hotpath.h"
 #include "xnb_kernels.cuh"
+#include "xnb_host_decomp.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -82,26 +83,6 @@ struct DBuf
     return cudaSuccess;
   }
 };
-
-struct Block { int64_t s[3], e[3]; };
-
-// reference src/core/lib/simple_block_rcb.cpp:27-59 : recursive bisection, longest axis first (ties: i, then j)
-Block simple_block_rcb(Block b, size_t n_parts, size_t part)
-{
-  while (n_parts > 1)
-  {
-    const size_t pivot = n_parts / 2;
-    const bool side = part >= pivot;
-    const int64_t d[3] = {b.e[0] - b.s[0], b.e[1] - b.s[1], b.e[2] - b.s[2]};
-    int ax = 2;
-    if (d[0] >= d[1] && d[0] >= d[2]) ax = 0; else if (d[1] >= d[0] && d[1] >= d[2]) ax = 1;
-    if (side) b.s[ax] = b.s[ax] + d[ax] / 2; else b.e[ax] = b.s[ax] + d[ax] / 2;
-    if (side) { part -= pivot; n_parts -= pivot; } else n_parts = pivot;
-  }
-  return b;
-}
-
-struct HostItem { uint32_t src_cell, dst_cell, flags; };
 
 } // namespace
 
@@ -252,49 +233,6 @@ int ensure_particle_capacity(xnb_ctx* c, size_t n, size_t keep)
   return 0;
 }
 
-// enumerate the ghost send items of rank `from` towards rank `to`, in the reference's order
-// (update_ghosts_comm_scheme.cpp:168-196 shift loops k,j,i ; :429-443 cell loop k,j,i and ghost-shell membership)
-void enumerate_sends(const xnb_ctx* c, int from, int to, int gl, std::vector<HostItem>& out)
-{
-  const Block& bf = c->blocks[(size_t)from];
-  const Block& bt = c->blocks[(size_t)to];
-  int64_t gs[3], ge[3], tdims[3], fdims[3], foff[3];
-  for (int d = 0; d < 3; d++) { gs[d] = bt.s[d] - gl; ge[d] = bt.e[d] + gl; tdims[d] = ge[d] - gs[d]; fdims[d] = bf.e[d] - bf.s[d] + 2 * gl; foff[d] = bf.s[d] - gl; }
-  const int lo[3] = {c->periodic[0] ? -1 : 0, c->periodic[1] ? -1 : 0, c->periodic[2] ? -1 : 0};
-  const int hi[3] = {c->periodic[0] ? 1 : 0, c->periodic[1] ? 1 : 0, c->periodic[2] ? 1 : 0};
-  for (int sk = lo[2]; sk <= hi[2]; sk++) for (int sj = lo[1]; sj <= hi[1]; sj++) for (int si = lo[0]; si <= hi[0]; si++)
-  {
-    if (si == 0 && sj == 0 && sk == 0 && from == to) continue;
-    const int sh[3] = {si, sj, sk};
-    uint32_t flags = 0;
-    if (si == -1) flags |= GB_SHIFT_X; if (si == 1) flags |= GB_SHIFT_X | GB_SIDE_X;
-    if (sj == -1) flags |= GB_SHIFT_Y; if (sj == 1) flags |= GB_SHIFT_Y | GB_SIDE_Y;
-    if (sk == -1) flags |= GB_SHIFT_Z; if (sk == 1) flags |= GB_SHIFT_Z | GB_SIDE_Z;
-    int64_t a[3], b[3];
-    bool empty = false;
-    for (int d = 0; d < 3; d++)
-    {
-      const int64_t s = (int64_t)sh[d] * c->ddims[d];
-      a[d] = std::max(bf.s[d], gs[d] - s); b[d] = std::min(bf.e[d], ge[d] - s);
-      if (a[d] >= b[d]) empty = true;
-    }
-    if (empty) continue;
-    for (int64_t k = a[2]; k < b[2]; k++) for (int64_t j = a[1]; j < b[1]; j++) for (int64_t i = a[0]; i < b[0]; i++)
-    {
-      const int64_t dl[3] = {i, j, k};
-      int64_t t[3];
-      bool inside_inner = true;
-      for (int d = 0; d < 3; d++) { t[d] = dl[d] + (int64_t)sh[d] * c->ddims[d]; if (t[d] < bt.s[d] || t[d] >= bt.e[d]) inside_inner = false; }
-      if (inside_inner) continue;   // can only happen for degenerate tiny domains
-      HostItem it;
-      it.src_cell = (uint32_t)(((k - foff[2]) * fdims[1] + (j - foff[1])) * fdims[0] + (i - foff[0]));
-      it.dst_cell = (uint32_t)(((t[2] - gs[2]) * tdims[1] + (t[1] - gs[1])) * tdims[0] + (t[0] - gs[0]));
-      it.flags = flags;
-      out.push_back(it);
-    }
-  }
-}
-
 // builds GridP, the AMR side table and the static ghost item lists once domain, block and distances are known
 int ensure_grid(xnb_ctx* c)
 {
@@ -360,8 +298,8 @@ int ensure_grid(xnb_ctx* c)
         outer[(size_t)p * 6 + 3 + d] = (c->dmin[d] + (double)bp.e[d] * c->cs) + c->ghost_dist;
       }
       std::vector<HostItem> snd, rcv;
-      enumerate_sends(c, c->rank, p, gl, snd);
-      enumerate_sends(c, p, c->rank, gl, rcv);
+      enumerate_sends(c->blocks, c->ddims, c->periodic, c->rank, p, gl, snd);
+      enumerate_sends(c->blocks, c->ddims, c->periodic, p, c->rank, gl, rcv);
       c->send_first[(size_t)p] = (int)s_src.size(); c->recv_first[(size_t)p] = (int)r_dst.size();
       for (const HostItem& it : snd) { s_src.push_back(it.src_cell); s_flags.push_back(it.flags); s_partner.push_back((uint32_t)p); }
       for (const HostItem& it : rcv) r_dst.push_back(it.dst_cell);

@@ -183,6 +183,15 @@ typedef struct xnb_lattice_cfg
 int64_t xnb_host_lattice_fcc(const xnb_lattice_cfg* cfg, int64_t capacity, double* rx, double* ry, double* rz,
                              double* vx, double* vy, double* vz, uint64_t* id, uint8_t* type);
 
+/* ---- static decomposition, host only (no CUDA): what every rank derives for itself and its partners -------------- */
+/* src/core/lib/simple_block_rcb.cpp:27-59 (via init_rcb_grid.cpp:65-77): block [start,end) of `rank` among `nranks` */
+int xnb_host_rcb_block(const int64_t grid_dims[3], int nranks, int rank, int64_t start[3], int64_t end[3]);
+/* src/mpi/update_ghosts_comm_scheme.cpp:168-196,429-443: the cells rank `from` sends to rank `to` (sender local cell,
+   receiver local ghost cell, GhostBoundaryModifier flags, ghosts_comm_scheme.h:46-81), in the reference's order.
+   Returns the item count (arrays are filled when capacity suffices); -1 on invalid arguments.                     */
+int64_t xnb_host_ghost_items(const int64_t grid_dims[3], const int32_t periodic[3], int ghost_layers, int nranks, int from, int to,
+                             int64_t capacity, uint32_t* src_cell, uint32_t* dst_cell, uint32_t* flags);
+
 /* stand-alone FP64 FMA peak probe (DFMA/s) used for the FP64 roofline denominator                               */
 int xnb_measure_dfma_peak(int cuda_device, double* tflops_out);
 
