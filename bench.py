@@ -138,10 +138,10 @@ def make_oracle_config(kw):
 
 def run_cpu_oracle(kw, nsteps, budget_s):
     """the CPU oracle on the same workload: init untimed, then up to nsteps steps (stops early when budget_s is spent)."""
-    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses every host core the container exposes
-    if os.environ.get("OMP_NUM_THREADS", "") in ("", "1") and "XNB_KEEP_OMP" not in os.environ:
-        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     from oracle import oracle as O
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses every host core the container exposes
+    if "XNB_KEEP_OMP" not in os.environ:
+        O.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     o = O.Oracle(make_oracle_config(kw))
     o.generate(); o.first_iteration()
     n = o.n_inner()

@@ -37,5 +37,22 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+DECK = os.path.join(OUT_DIR, "lj_deck")
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def build_host(force=False):
+    """C++17 operator mirror (exanbody_b200/host) + the LJ deck program, linked against libxnb_hotpath.so"""
+    lib = build()
+    src = [os.path.join(HOST, f) for f in ("xnb_operators.cpp", "lj_deck.cpp")]
+    dep = src + [os.path.join(HOST, "xnb_operators.hpp"), lib]
+    if not force and os.path.exists(DECK) and all(os.path.getmtime(f) <= os.path.getmtime(DECK) for f in dep):
+        return DECK
+    cmd = [CXX, "-std=c++17", "-O2", "-Wall", "-o", DECK] + src + ["-L" + OUT_DIR, "-lxnb_hotpath", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return DECK
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

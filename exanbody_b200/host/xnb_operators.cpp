@@ -1,0 +1,501 @@
+// xnb_operators.cpp -- the operators of the LJ hot path behind the reference's operator interface (see xnb_operators.hpp).
+// Each operator cites the reference operator whose name, slots and YAML keys it mirrors; execute() forwards to the C-ABI.
+#include "xnb_operators.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace xnb { namespace host {
+
+void fatal_error(const std::string& msg) { std::fprintf(stderr, "*** fatal error: %s\n", msg.c_str()); std::fflush(stderr); std::abort(); }
+
+static void ck(xnb_ctx* c, int rc, const char* what) { if (rc != XNB_OK) fatal_error(std::string(what) + ": " + xnb_last_error(c)); }
+
+Grid::~Grid() { if (ctx) xnb_destroy(ctx); }
+int64_t Grid::number_of_particles() const { return ctx ? xnb_num_total(ctx) : 0; }
+int64_t Grid::number_of_cells() const { if (!ctx) return 0; xnb_grid_info gi; return xnb_get_grid_info(ctx, &gi) == XNB_OK ? gi.n_cells : 0; }
+size_t GridChunkNeighbors::number_of_cells() const { if (!ctx) return 0; xnb_grid_info gi; return xnb_get_grid_info(ctx, &gi) == XNB_OK ? (size_t)gi.n_cells : 0; }
+
+// ---- parameters -----------------------------------------------------------------------------------------------------
+static std::string trim(const std::string& s) { size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n"); return a == std::string::npos ? "" : s.substr(a, b - a + 1); }
+
+// internal units of the LJ decks (input_lj_Ni.msp:15-24): angstrom, picosecond, Dalton.  Constants as recovered from the
+// reference's golden file (tests/golden/README.md): e = 1.6021892e-19 C, u = 1.66053904e-27 kg.
+double convert_quantity(const std::string& text)
+{
+  std::istringstream is(text);
+  double v = 0; std::string unit;
+  if (!(is >> v)) fatal_error("not a quantity: '" + text + "'");
+  is >> unit;
+  static const double J_INTERNAL = 1.0 / (1.66053904e-27 * 1e-20 / 1e-24);
+  if (unit.empty()) return v;
+  if (unit == "ang" || unit == "angstrom") return v;
+  if (unit == "nm") return v * 10.0;
+  if (unit == "um") return v * 1e4;
+  if (unit == "m") return v * 1e10;
+  if (unit == "ps") return v;
+  if (unit == "fs") return v * 1e-3;
+  if (unit == "ns") return v * 1e3;
+  if (unit == "s") return v * 1e12;
+  if (unit == "Da" || unit == "Dalton") return v;
+  if (unit == "eV") return v * 1.6021892e-19 * J_INTERNAL;
+  if (unit == "J") return v * J_INTERNAL;
+  fatal_error("unknown unit '" + unit + "' in '" + text + "'");
+}
+
+Params Params::parse(const std::string& text)
+{
+  Params p;
+  std::string s = trim(text);
+  if (s.empty()) return p;
+  if (s.front() == '{' && s.back() == '}') s = s.substr(1, s.size() - 2);
+  // split on top level commas (brackets and braces nest)
+  std::vector<std::string> items; int depth = 0; std::string cur;
+  for (char ch : s)
+  {
+    if (ch == '[' || ch == '{') depth++;
+    if (ch == ']' || ch == '}') depth--;
+    if (ch == ',' && depth == 0) { items.push_back(cur); cur.clear(); } else cur += ch;
+  }
+  if (!trim(cur).empty()) items.push_back(cur);
+  for (const std::string& it : items)
+  {
+    const size_t c = it.find(':');
+    if (c == std::string::npos) fatal_error("expected 'key: value' in '" + it + "'");
+    const std::string k = trim(it.substr(0, c)), v = trim(it.substr(c + 1));
+    if (!v.empty() && v.front() == '{') { Params sub = parse(v); for (auto& kv : sub.kv) p.kv[k + "." + kv.first] = kv.second; }
+    else p.kv[k] = v;
+  }
+  return p;
+}
+double Params::quantity(const std::string& k) const { auto it = kv.find(k); if (it == kv.end()) fatal_error("missing parameter '" + k + "'"); return convert_quantity(it->second); }
+bool Params::boolean(const std::string& k) const { const std::string v = kv.at(k); return v == "true" || v == "True" || v == "yes" || v == "1"; }
+std::vector<double> Params::quantities(const std::string& k) const
+{
+  std::string v = kv.at(k); std::vector<double> out; std::string cur;
+  for (char ch : v) { if (ch == '[' || ch == ']') continue; if (ch == ',') { if (!trim(cur).empty()) out.push_back(convert_quantity(trim(cur))); cur.clear(); } else cur += ch; }
+  if (!trim(cur).empty()) out.push_back(convert_quantity(trim(cur)));
+  return out;
+}
+
+// ---- slots / factory / batch ---------------------------------------------------------------------------------------
+SlotBase::SlotBase(OperatorNode* op, const char* n, SlotDirection d, bool req, const char* doc_, std::type_index t)
+  : name(n), dir(d), required(req), doc(doc_), type(t) { op->slots.push_back(this); }
+
+OperatorNodeFactory* OperatorNodeFactory::instance() { static OperatorNodeFactory f; return &f; }
+std::unique_ptr<OperatorNode> OperatorNodeFactory::make_operator(const std::string& name) const
+{
+  auto it = makers_.find(name);
+  if (it == makers_.end()) fatal_error("no operator factory registered for '" + name + "'");
+  auto op = it->second(); op->name = name; return op;
+}
+std::vector<std::string> OperatorNodeFactory::available_operators() const { std::vector<std::string> v; for (auto& kv : makers_) v.push_back(kv.first); return v; }
+
+OperatorNode* Batch::add(const std::string& op_name, const std::string& params, const std::map<std::string, std::string>& rebind)
+{
+  register_hot_path_operators();
+  std::unique_ptr<OperatorNode> op = OperatorNodeFactory::instance()->make_operator(op_name);
+  op->stream = stream_;
+  const Params p = Params::parse(params);
+  for (SlotBase* s : op->slots)
+  {
+    if (s->dir == PRIVATE) { s->bind(s->make_default()); continue; }
+    auto rb = rebind.find(s->name);
+    const std::string gname = rb == rebind.end() ? s->name : rb->second;
+    Entry& e = table()[gname];
+    if (!e.p)
+    {
+      // nobody produced it yet: outputs and defaulted inputs create the graph value, a REQUIRED input without producer
+      // is resolved at execute() time (a later yaml_initialize may still provide it)
+      std::shared_ptr<void> d = s->make_default();
+      if (d) { e.p = d; e.t = s->type; }
+    }
+    if (e.p)
+    {
+      if (e.t != s->type) fatal_error("slot '" + s->name + "' of operator '" + op_name + "' is connected to '" + gname + "' of another type");
+      s->bind(e.p);
+    }
+  }
+  op->yaml_initialize(p);
+  ops_.push_back(std::move(op));
+  return ops_.back().get();
+}
+
+void Batch::execute()
+{
+  for (auto& op : ops_)
+  {
+    for (SlotBase* s : op->slots)
+      if (s->required && !s->has_value() && s->dir != OUTPUT) fatal_error("operator '" + op->name + "': required slot '" + s->name + "' is not connected");
+    op->execute();
+  }
+}
+
+// =====================================================================================================================
+// operators
+// =====================================================================================================================
+namespace {
+
+struct MpiRank { int rank = 0, nranks = 1; };
+
+// scalar parameter of an operator: YAML value if given, else the connected slot
+#define XNB_PARAM_QUANTITY(p, slotname) do { if (p.has(#slotname)) { if (!slotname.value) slotname.value = std::make_shared<double>(); *slotname.value = p.quantity(#slotname); } } while (0)
+#define XNB_PARAM_BOOL(p, slotname) do { if (p.has(#slotname)) { slotname.value = std::make_shared<bool>(p.boolean(#slotname)); } } while (0)
+
+// op `domain` (core/lib/domain.cpp:359-..., YAML keys of input_lj_Ni.msp:63-69)
+struct DomainOp : OperatorNode
+{
+  ADD_SLOT(Domain, domain, INPUT_OUTPUT);
+  void yaml_initialize(const Params& p) override
+  {
+    Domain& d = *domain;
+    if (p.has("cell_size")) d.cell_size = p.quantity("cell_size");
+    if (p.has("grid_dims")) { auto v = p.quantities("grid_dims"); d.grid_dims = IJK{(int64_t)v.at(0), (int64_t)v.at(1), (int64_t)v.at(2)}; }
+    if (p.has("bounds"))
+    {
+      auto v = p.quantities("bounds");           // [ [ xmin, ymin, zmin ] , [ xmax, ymax, zmax ] ]
+      d.bounds.bmin = Vec3d{v.at(0), v.at(1), v.at(2)}; d.bounds.bmax = Vec3d{v.at(3), v.at(4), v.at(5)};
+    }
+    if (p.has("periodic"))
+    {
+      std::string s = p.str("periodic"); int q = 0; std::string cur;
+      for (char ch : s + ",") { if (ch == '[' || ch == ']' || ch == ' ') continue; if (ch == ',') { if (!cur.empty() && q < 3) d.periodic[q++] = (cur == "true"); cur.clear(); } else cur += ch; }
+    }
+    if (p.has("expandable")) d.expandable = p.boolean("expandable");
+  }
+  void execute() override {}
+};
+
+// op `init_rcb_grid` (grid_cell_particles/init_rcb_grid.cpp:37-84): creates the local grid = this rank's RCB block
+struct InitRcbGrid : OperatorNode
+{
+  ADD_SLOT(MpiRank, mpi, INPUT, MpiRank{});
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT);
+  void execute() override
+  {
+    Grid& g = *grid;
+    if (!g.ctx) { int rc = xnb_create(&g.ctx, g.device); if (rc != XNB_OK) fatal_error(std::string("init_rcb_grid: ") + xnb_last_error(nullptr)); }
+    const Domain& d = *domain;
+    const double bmin[3] = {d.bounds.bmin.x, d.bounds.bmin.y, d.bounds.bmin.z}, bmax[3] = {d.bounds.bmax.x, d.bounds.bmax.y, d.bounds.bmax.z};
+    const int64_t gd[3] = {d.grid_dims.i, d.grid_dims.j, d.grid_dims.k};
+    const int32_t per[3] = {d.periodic[0], d.periodic[1], d.periodic[2]};
+    ck(g.ctx, xnb_set_domain(g.ctx, bmin, bmax, d.cell_size, gd, per), "domain");
+    ck(g.ctx, xnb_init_rcb_grid(g.ctx, mpi->rank, mpi->nranks), "init_rcb_grid");
+  }
+};
+
+// ops `particle_types` / `particle_type_add_properties` reduced to what the path reads: the per-type mass
+struct ParticleTypeAddProperties : OperatorNode
+{
+  ADD_SLOT(ParticleTypeProperties, particle_type_properties, INPUT_OUTPUT);
+  void yaml_initialize(const Params& p) override
+  {
+    for (auto& kv : p.kv) { const size_t dot = kv.first.find(".mass"); if (dot != std::string::npos) particle_type_properties->mass.push_back(convert_quantity(kv.second)); }
+  }
+  void execute() override {}
+};
+
+// ops `lattice` (structure FCC) and `gaussian_noise_r` with deterministic_noise
+// (generate_particle_lattice.h:247-388, gaussian_noise.h:61-80,150-161).  The particles stay on the host until
+// move_particles bins them (the reference fills cells directly).
+struct LatticeRecipe { bool have = false; double a = 0, noise_sigma = 0, vel_sigma = 0; };
+static void generate_particles(const Domain& d, const LatticeRecipe& r, ParticleSet& ps)
+{
+  xnb_lattice_cfg cfg{};
+  cfg.bounds_min[0] = d.bounds.bmin.x; cfg.bounds_min[1] = d.bounds.bmin.y; cfg.bounds_min[2] = d.bounds.bmin.z;
+  cfg.bounds_max[0] = d.bounds.bmax.x; cfg.bounds_max[1] = d.bounds.bmax.y; cfg.bounds_max[2] = d.bounds.bmax.z;
+  cfg.cell_size = d.cell_size; cfg.grid_dims[0] = d.grid_dims.i; cfg.grid_dims[1] = d.grid_dims.j; cfg.grid_dims[2] = d.grid_dims.k;
+  cfg.lattice_a = r.a; cfg.noise_sigma = r.noise_sigma; cfg.vel_sigma = r.vel_sigma;
+  const double vol = (cfg.bounds_max[0] - cfg.bounds_min[0]) * (cfg.bounds_max[1] - cfg.bounds_min[1]) * (cfg.bounds_max[2] - cfg.bounds_min[2]);
+  const int64_t cap = (int64_t)(4.0 * vol / (r.a * r.a * r.a) * 1.1) + 1024;
+  for (auto* v : {&ps.rx, &ps.ry, &ps.rz, &ps.vx, &ps.vy, &ps.vz}) v->assign((size_t)cap, 0.0);
+  ps.id.assign((size_t)cap, 0); ps.type.assign((size_t)cap, 0);
+  const int64_t n = xnb_host_lattice_fcc(&cfg, cap, ps.rx.data(), ps.ry.data(), ps.rz.data(), ps.vx.data(), ps.vy.data(), ps.vz.data(), ps.id.data(), ps.type.data());
+  if (n < 0) fatal_error("lattice: capacity");
+  for (auto* v : {&ps.rx, &ps.ry, &ps.rz, &ps.vx, &ps.vy, &ps.vz}) v->resize((size_t)n);
+  ps.id.resize((size_t)n); ps.type.resize((size_t)n);
+}
+struct Lattice : OperatorNode
+{
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  ADD_SLOT(LatticeRecipe, lattice_recipe, INPUT_OUTPUT);
+  ADD_SLOT(ParticleSet, pending_particles, INPUT_OUTPUT);
+  void yaml_initialize(const Params& p) override
+  {
+    if (p.has("structure") && p.str("structure") != "FCC") fatal_error("lattice: only structure FCC is on the LJ hot path");
+    if (p.has("size")) lattice_recipe->a = p.quantities("size").at(0);
+  }
+  void execute() override { lattice_recipe->have = true; generate_particles(*domain, *lattice_recipe, *pending_particles); }
+};
+struct GaussianNoiseR : OperatorNode
+{
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  ADD_SLOT(double, sigma, INPUT, 1.0);
+  ADD_SLOT(bool, deterministic_noise, INPUT, false);
+  ADD_SLOT(LatticeRecipe, lattice_recipe, INPUT_OUTPUT);
+  ADD_SLOT(ParticleSet, pending_particles, INPUT_OUTPUT);
+  void yaml_initialize(const Params& p) override { XNB_PARAM_QUANTITY(p, sigma); }
+  void execute() override
+  {
+    if (!lattice_recipe->have) fatal_error("gaussian_noise_r: no lattice to perturb");
+    if (!*deterministic_noise) fatal_error("gaussian_noise_r: only deterministic_noise: true is reproducible (gaussian_noise.h:150-161)");
+    lattice_recipe->noise_sigma = *sigma; generate_particles(*domain, *lattice_recipe, *pending_particles);
+  }
+};
+
+// op `nbh_dist` (particle_neighbors/nbh_dist.cpp:30-88), identity xform: grid space == lab space
+struct NeighborDistance : OperatorNode
+{
+  ADD_SLOT(double, rcut_max, INPUT, 0.0, DocString{"maximum search distance for the neighborhood, in physical space"});
+  ADD_SLOT(double, rcut_inc, INPUT, 0.0, DocString{"value added to the search distance to update neighbor list less frequently"});
+  ADD_SLOT(double, ghost_dist_max, INPUT_OUTPUT, 0.0, DocString{"maximum distance needed for ghost particles out of sub domain"});
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  ADD_SLOT(double, nbh_dist_lab, INPUT_OUTPUT, DocString{"neighborhood distance, in lab space"});
+  ADD_SLOT(double, nbh_dist, INPUT_OUTPUT, DocString{"neighborhood distance, in grid space"});
+  ADD_SLOT(double, ghost_dist, INPUT_OUTPUT, DocString{"thickness of ghost particle layer, in grid space"});
+  ADD_SLOT(double, max_displ, INPUT_OUTPUT, DocString{"move threshold, in grid space, that must trigger a neighbor list update"});
+  ADD_SLOT(double, max_displ_lab, INPUT_OUTPUT, DocString{"move threshold, in lab space"});
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT, DocString{"(mirror only) the ctx that receives the distances"});
+  void execute() override
+  {
+    *nbh_dist_lab = *rcut_max + *rcut_inc; *nbh_dist = *nbh_dist_lab;                      // :47
+    *max_displ_lab = *rcut_inc / 2.0; *max_displ = *max_displ_lab;                        // :48
+    *ghost_dist_max = std::max(*ghost_dist_max, *rcut_max); *ghost_dist = *ghost_dist_max + *rcut_inc;   // :60-62
+    ck(grid->ctx, xnb_set_nbh_dist(grid->ctx, *rcut_max, *rcut_inc), "nbh_dist");
+  }
+};
+
+// op `move_particles` (grid_cell_particles/move_particles.cpp:42-48 -> move_particles_across_cells.h:78-235);
+// with several ranks it also performs the migrate_cell_particles hand-off
+struct MoveParticles : OperatorNode
+{
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT);
+  ADD_SLOT(ParticleSet, pending_particles, INPUT_OUTPUT);
+  ADD_SLOT(ParticleTypeProperties, particle_type_properties, INPUT, ParticleTypeProperties{});
+  void execute() override
+  {
+    ParticleSet& ps = *pending_particles;
+    if (!ps.rx.empty())
+    {
+      if (!particle_type_properties->mass.empty()) ck(grid->ctx, xnb_set_type_mass(grid->ctx, particle_type_properties->mass.data(), (int)particle_type_properties->mass.size()), "particle masses");
+      ck(grid->ctx, xnb_set_particles(grid->ctx, (int64_t)ps.rx.size(), ps.rx.data(), ps.ry.data(), ps.rz.data(), ps.vx.data(), ps.vy.data(), ps.vz.data(), ps.id.data(), ps.type.data()), "lattice upload");
+      ps = ParticleSet{};
+    }
+    ck(grid->ctx, xnb_move_particles(grid->ctx, stream), "move_particles");
+  }
+};
+struct Nop : OperatorNode { void execute() override {} };     // operators whose work is folded into a neighbour (see registration)
+
+struct RebuildAmr : OperatorNode        // amr/rebuild_amr.cpp:35-68 (slot default 5.0; the default decks set 6.5, update-particles.msp:9)
+{
+  ADD_SLOT(double, sub_grid_density, INPUT, 5.0);
+  ADD_SLOT(long, enforced_ordering, INPUT, 1L);
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT);
+  ADD_SLOT(AmrGrid, amr, INPUT_OUTPUT);
+  void yaml_initialize(const Params& p) override { XNB_PARAM_QUANTITY(p, sub_grid_density); }
+  void execute() override { ck(grid->ctx, xnb_set_sub_grid_density(grid->ctx, *sub_grid_density), "rebuild_amr"); ck(grid->ctx, xnb_rebuild_amr(grid->ctx, stream), "rebuild_amr"); amr->ctx = grid->ctx; }
+};
+struct BackupR : OperatorNode           // io/backup_r.cpp:36-78
+{
+  ADD_SLOT(Grid, grid, INPUT);
+  ADD_SLOT(Domain, domain, INPUT);
+  ADD_SLOT(PositionBackupData, backup_r, INPUT_OUTPUT);
+  void execute() override { ck(grid->ctx, xnb_backup_r(grid->ctx, stream), "backup_r"); backup_r->ctx = grid->ctx; }
+};
+struct GhostCommSchemeOp : OperatorNode // mpi/update_ghosts_comm_scheme.cpp:58-492
+{
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT);
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  ADD_SLOT(GhostCommunicationScheme, ghost_comm_scheme, INPUT_OUTPUT);
+  void execute() override { ck(grid->ctx, xnb_ghost_comm_scheme(grid->ctx, stream), "ghost_comm_scheme"); ghost_comm_scheme->ctx = grid->ctx; }
+};
+template <bool ALL>
+struct GhostUpdate : OperatorNode       // mpi/update_ghosts.cu:45-64, update_ghosts.h:53-190
+{
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT);
+  ADD_SLOT(GhostCommunicationScheme, ghost_comm_scheme, INPUT_OUTPUT);
+  ADD_SLOT(UpdateGhostConfig, update_ghost_config, INPUT, UpdateGhostConfig{});
+  void execute() override { ck(grid->ctx, ALL ? xnb_ghost_update_all(grid->ctx, stream) : xnb_ghost_update_r(grid->ctx, stream), ALL ? "ghost_update_all" : "ghost_update_r"); }
+};
+struct BuildChunkNeighbors : OperatorNode   // particle_neighbors/chunk_neighbors.cpp:48-74
+{
+  ADD_SLOT(Grid, grid, INPUT);
+  ADD_SLOT(AmrGrid, amr, INPUT, AmrGrid{});
+  ADD_SLOT(AmrSubCellPairCache, amr_grid_pairs, INPUT, AmrSubCellPairCache{});
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  ADD_SLOT(double, nbh_dist_lab, INPUT, REQUIRED);
+  ADD_SLOT(GridChunkNeighbors, chunk_neighbors, INPUT_OUTPUT);
+  ADD_SLOT(ChunkNeighborsConfig, config, INPUT_OUTPUT, ChunkNeighborsConfig{});
+  void yaml_initialize(const Params& p) override
+  {
+    if (p.has("config.chunk_size") && (unsigned)p.quantity("config.chunk_size") != 1u) fatal_error("chunk_neighbors: chunk_size is frozen at 1 (chunk_neighbors_config.h:49,74)");
+    if (p.has("config.half_symmetric") && p.boolean("config.half_symmetric")) fatal_error("chunk_neighbors: half_symmetric lists are not on the LJ hot path (SURVEY 8f)");
+    if (p.has("config.build_particle_offset") && !p.boolean("config.build_particle_offset")) fatal_error("chunk_neighbors: build_particle_offset: false is not supported");
+  }
+  void execute() override
+  {
+    config->chunk_size = 1;
+    ck(grid->ctx, xnb_chunk_neighbors(grid->ctx, stream), "chunk_neighbors");
+    GridChunkNeighbors& n = *chunk_neighbors; n.ctx = grid->ctx;
+    ck(grid->ctx, xnb_view_chunk_neighbors(grid->ctx, &n.cell_stream, &n.cell_stream_size, &n.max_neighbors), "chunk_neighbors view");
+  }
+};
+struct ZeroParticleForce : OperatorNode     // compute/zero_particle_force.cu:32-53
+{
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT);
+  ADD_SLOT(bool, ghost, INPUT, false);
+  void yaml_initialize(const Params& p) override { XNB_PARAM_BOOL(p, ghost); }
+  void execute() override { ck(grid->ctx, xnb_zero_particle_force(grid->ctx, *ghost ? 1 : 0, stream), "zero_particle_force"); }
+};
+struct LennardJonesForce : OperatorNode     // contribs/md/lennard_jones/lennard_jones.cu:171-215
+{
+  ADD_SLOT(LennardJonesParms, config, INPUT, REQUIRED, DocString{"Lennard-Jones potential parameters"});
+  ADD_SLOT(double, rcut, INPUT, 0.0, DocString{"Cutoff distance"});
+  ADD_SLOT(GridChunkNeighbors, chunk_neighbors, INPUT, GridChunkNeighbors{}, DocString{"neighbor list"});
+  ADD_SLOT(bool, ghost, INPUT, false, DocString{"Enables computation in ghost cells"});
+  ADD_SLOT(bool, experimental_ccb, INPUT, false, DocString{"accepted and ignored: the sweep kernel is always block cooperative"});
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED, DocString{"Simulation domain"});
+  ADD_SLOT(double, rcut_max, INPUT_OUTPUT, 0.0, DocString{"Updated max rcut"});
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT, DocString{"Local sub-domain particles grid"});
+  void yaml_initialize(const Params& p) override
+  {
+    if (p.has("config.epsilon")) { if (!config.value) config.value = std::make_shared<LennardJonesParms>(); config->epsilon = p.quantity("config.epsilon"); config->sigma = p.quantity("config.sigma"); }
+    if (p.has("rcut")) { rcut.value = std::make_shared<double>(p.quantity("rcut")); }
+    XNB_PARAM_BOOL(p, ghost);
+    *rcut_max = std::max(*rcut, *rcut_max);        // the reference raises rcut_max when the graph is initialised so that nbh_dist sees it (:193)
+  }
+  void execute() override
+  {
+    *rcut_max = std::max(*rcut, *rcut_max);
+    if (grid->number_of_cells() == 0) return;
+    ck(grid->ctx, xnb_lennard_jones_force(grid->ctx, config->epsilon, config->sigma, *rcut, *ghost ? 1 : 0, stream), "lennard_jones_force");
+  }
+};
+struct DivideForceByTypeScalar : OperatorNode   // compute/vec3_typescalar_op.cu:71-122 (`divide_force_by_type_scalar: mass`)
+{
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT);
+  void execute() override { ck(grid->ctx, xnb_divide_force_by_mass(grid->ctx, stream), "divide_force_by_type_scalar"); }
+};
+struct PushFVR : OperatorNode                   // defbox/push_vec3_2nd_order.h:77-117
+{
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT);
+  ADD_SLOT(double, dt, INPUT);
+  ADD_SLOT(double, dt_scale, INPUT, 1.0);
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  void yaml_initialize(const Params& p) override { XNB_PARAM_QUANTITY(p, dt_scale); }
+  void execute() override { ck(grid->ctx, xnb_push_f_v_r(grid->ctx, *dt, *dt_scale, stream), "push_f_v_r"); }
+};
+struct PushFV : OperatorNode                    // defbox/push_vec3_1st_order.h:71-106
+{
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT);
+  ADD_SLOT(double, dt, INPUT);
+  ADD_SLOT(double, dt_scale, INPUT, 1.0);
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  void yaml_initialize(const Params& p) override { XNB_PARAM_QUANTITY(p, dt_scale); }
+  void execute() override { ck(grid->ctx, xnb_push_f_v(grid->ctx, *dt, *dt_scale, stream), "push_f_v"); }
+};
+struct ParticleDisplOver : OperatorNode         // mpi/particle_displ_over.cu:98-178
+{
+  ADD_SLOT(Grid, grid, INPUT);
+  ADD_SLOT(Domain, domain, INPUT);
+  ADD_SLOT(PositionBackupData, backup_r, INPUT);
+  ADD_SLOT(double, threshold, INPUT, 0.0);
+  ADD_SLOT(double, threshold_lab, INPUT, 0.0);
+  ADD_SLOT(bool, async, INPUT, false);
+  ADD_SLOT(bool, result, OUTPUT);
+  void execute() override { uint64_t n = 0; ck(grid->ctx, xnb_particle_displ_over(grid->ctx, &n, stream), "particle_displ_over"); *result = n > 0; }
+};
+
+// op `check_values` (debug/check_values.cpp:52-405), reader side: [id, r(3), a(3), v(3)] hex-float rows
+struct CheckValues : OperatorNode
+{
+  ADD_SLOT(Grid, grid, INPUT);
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  ADD_SLOT(std::string, file, INPUT, std::string("check_values.dat"));
+  ADD_SLOT(double, pos_threshold, INPUT, 1e-5);
+  ADD_SLOT(double, acc_threshold, INPUT, 1e-5);
+  ADD_SLOT(double, vel_threshold, INPUT, 1e-5);
+  ADD_SLOT(double, max_error, OUTPUT);
+  void yaml_initialize(const Params& p) override
+  {
+    if (p.has("file")) { file.value = std::make_shared<std::string>(p.str("file")); }
+    XNB_PARAM_QUANTITY(p, pos_threshold); XNB_PARAM_QUANTITY(p, acc_threshold); XNB_PARAM_QUANTITY(p, vel_threshold);
+  }
+  void execute() override
+  {
+    std::ifstream in(*file);
+    if (!in) fatal_error("check_values: cannot read '" + *file + "'");
+    const int64_t n = xnb_num_inner(grid->ctx);
+    std::vector<double> f[9]; for (auto& v : f) v.resize((size_t)n);
+    std::vector<uint64_t> ids((size_t)n);
+    ck(grid->ctx, xnb_get_particles(grid->ctx, 0, n, f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data(), f[6].data(), f[7].data(), f[8].data(), ids.data(), nullptr, nullptr), "check_values");
+    std::map<uint64_t, size_t> where; for (size_t q = 0; q < (size_t)n; q++) where[ids[q]] = q;
+    const Domain& d = *domain;
+    const double L[3] = {d.bounds.bmax.x - d.bounds.bmin.x, d.bounds.bmax.y - d.bounds.bmin.y, d.bounds.bmax.z - d.bounds.bmin.z};
+    // the file is a YAML list of rows "[ id , x , y , z , ax , ay , az , vx , vy , vz ]" of hex floats: take every number
+    std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    std::vector<std::string> rows; { std::string cur; int depth = 0; for (char ch : text) { if (ch == '[') { depth++; if (depth == 1) cur.clear(); else cur += ' '; } else if (ch == ']') { depth--; if (depth == 0) rows.push_back(cur); } else if (depth >= 1) cur += (ch == ',' ? ' ' : ch); } }
+    double worst = 0; size_t checked = 0;
+    for (const std::string& row : rows)
+    {
+      std::istringstream is(row); std::vector<double> v; std::string tok;
+      while (is >> tok) { char* end = nullptr; const double x = std::strtod(tok.c_str(), &end); if (end != tok.c_str()) v.push_back(x); }
+      if (v.size() != 10) continue;
+      auto it = where.find((uint64_t)v[0]);
+      if (it == where.end()) fatal_error("check_values: particle id missing");
+      const size_t q = it->second;
+      for (int c = 0; c < 3; c++)
+      {
+        double dr = f[c][q] - v[1 + c]; dr -= L[c] * std::round(dr / L[c]);          // periodic un-wrap (check_values.cpp:244,255-257)
+        const double da = f[6 + c][q] - v[4 + c], dv = f[3 + c][q] - v[7 + c];
+        if (std::fabs(dr) > *pos_threshold || std::fabs(da) > *acc_threshold || std::fabs(dv) > *vel_threshold) fatal_error("check_values: particle differs from the reference values beyond the thresholds");
+        worst = std::max(worst, std::max(std::fabs(dr), std::max(std::fabs(da), std::fabs(dv))));
+      }
+      checked++;
+    }
+    if (checked == 0) fatal_error("check_values: no sample rows in '" + *file + "'");
+    *max_error = worst;
+    std::printf("check_values: %zu particles within thresholds, max abs error %.3e\n", checked, worst);
+  }
+};
+
+} // namespace
+
+void register_hot_path_operators()
+{
+  static bool done = false;
+  if (done) return;
+  done = true;
+  OperatorNodeFactory* f = OperatorNodeFactory::instance();
+  f->register_factory("domain", make_simple_operator<DomainOp>());
+  f->register_factory("init_rcb_grid", make_simple_operator<InitRcbGrid>());
+  f->register_factory("particle_type_add_properties", make_simple_operator<ParticleTypeAddProperties>());
+  f->register_factory("lattice", make_simple_operator<Lattice>());
+  f->register_factory("gaussian_noise_r", make_simple_operator<GaussianNoiseR>());
+  f->register_factory("nbh_dist", make_simple_operator<NeighborDistance>());
+  f->register_factory("move_particles", make_simple_operator<MoveParticles>());
+  f->register_factory("migrate_cell_particles", make_simple_operator<Nop>());    // hand-off happens inside move_particles (static blocks)
+  f->register_factory("rebuild_amr", make_simple_operator<RebuildAmr>());
+  f->register_factory("backup_r", make_simple_operator<BackupR>());
+  f->register_factory("ghost_comm_scheme", make_simple_operator<GhostCommSchemeOp>());
+  f->register_factory("ghost_update_all", make_simple_operator<GhostUpdate<true>>());
+  f->register_factory("ghost_update_r", make_simple_operator<GhostUpdate<false>>());
+  f->register_factory("amr_grid_pairs", make_simple_operator<Nop>());            // the sub-cell pair cache only prunes candidates; the tiled build does not need it
+  f->register_factory("chunk_neighbors", make_simple_operator<BuildChunkNeighbors>());
+  f->register_factory("resize_particle_locks", make_simple_operator<Nop>());     // ComputePairOptionalLocks<false>: LJ takes no locks
+  f->register_factory("zero_particle_force", make_simple_operator<ZeroParticleForce>());
+  f->register_factory("lennard_jones_force", make_simple_operator<LennardJonesForce>());
+  f->register_factory("update_force_from_ghost", make_simple_operator<Nop>());   // value-wise a no-op for the full (non symmetric) list
+  f->register_factory("divide_force_by_type_scalar", make_simple_operator<DivideForceByTypeScalar>());
+  f->register_factory("push_f_v_r", make_simple_operator<PushFVR>());
+  f->register_factory("push_f_v", make_simple_operator<PushFV>());
+  f->register_factory("particle_displ_over", make_simple_operator<ParticleDisplOver>());
+  f->register_factory("check_values", make_simple_operator<CheckValues>());
+}
+
+}} // namespace xnb::host

@@ -61,6 +61,7 @@ def lib():
         L.xo_pairs.argtypes = [P, P]; L.xo_pairs.restype = C.c_int64
         L.xo_energy_virial.argtypes = [P, P, P, P]
         L.xo_num_threads.restype = C.c_int
+        L.xo_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -188,3 +189,7 @@ class Oracle:
 
 def num_threads():
     return lib().xo_num_threads()
+
+
+def set_num_threads(n):
+    lib().xo_set_num_threads(int(n))

@@ -888,6 +888,7 @@ extern "C" {
 
 const char* xo_last_error(void) { return g_err.c_str(); }
 int xo_num_threads(void) { return omp_get_max_threads(); }
+void xo_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 xo_sim* xo_create(const xo_config* cfg)
 {

@@ -106,6 +106,7 @@ void    xo_energy_virial(const xo_sim*, double* epot, double virial[6] /* xx yy 
 
 int64_t xo_rebuild_count(const xo_sim*);
 int     xo_num_threads(void);
+void    xo_set_num_threads(int n);   /* omp_set_num_threads (torchrun exports OMP_NUM_THREADS=1 to its workers) */
 
 #ifdef __cplusplus
 }
