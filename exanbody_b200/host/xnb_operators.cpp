@@ -142,7 +142,9 @@ namespace {
 struct MpiRank { int rank = 0, nranks = 1; };
 
 // scalar parameter of an operator: YAML value if given, else the connected slot
-#define XNB_PARAM_QUANTITY(p, slotname) do { if (p.has(#slotname)) { if (!slotname.value) slotname.value = std::make_shared<double>(); *slotname.value = p.quantity(#slotname); } } while (0)
+// (a YAML value is private to the operator: it must not write through to the graph value other operators are bound to,
+// e.g. push_f_v_r{dt_scale: 1.0} followed by push_f_v{dt_scale: 0.5})
+#define XNB_PARAM_QUANTITY(p, slotname) do { if (p.has(#slotname)) { slotname.value = std::make_shared<double>(p.quantity(#slotname)); } } while (0)
 #define XNB_PARAM_BOOL(p, slotname) do { if (p.has(#slotname)) { slotname.value = std::make_shared<bool>(p.boolean(#slotname)); } } while (0)
 
 // op `domain` (core/lib/domain.cpp:359-..., YAML keys of input_lj_Ni.msp:63-69)
@@ -453,7 +455,13 @@ struct CheckValues : OperatorNode
       {
         double dr = f[c][q] - v[1 + c]; dr -= L[c] * std::round(dr / L[c]);          // periodic un-wrap (check_values.cpp:244,255-257)
         const double da = f[6 + c][q] - v[4 + c], dv = f[3 + c][q] - v[7 + c];
-        if (std::fabs(dr) > *pos_threshold || std::fabs(da) > *acc_threshold || std::fabs(dv) > *vel_threshold) fatal_error("check_values: particle differs from the reference values beyond the thresholds");
+        if (std::fabs(dr) > *pos_threshold || std::fabs(da) > *acc_threshold || std::fabs(dv) > *vel_threshold)
+        {
+          char msg[256];
+          std::snprintf(msg, sizeof msg, "check_values: particle %llu differs from the reference values beyond the thresholds (axis %d: dr %.3e da %.3e dv %.3e)",
+                        (unsigned long long)v[0], c, dr, da, dv);
+          fatal_error(msg);
+        }
         worst = std::max(worst, std::max(std::fabs(dr), std::max(std::fabs(da), std::fabs(dv))));
       }
       checked++;

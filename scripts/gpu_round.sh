@@ -10,6 +10,6 @@ tail -3 gpurun_out/${TAG}_pytest.log
 tail -2 gpurun_out/${TAG}_bench.log | cut -c1-1800
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
    python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lj_force_tiled -s 4 -c 2 -f -o gpurun_out/${TAG}_force \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lj_sweep -s 4 -c 2 -f -o gpurun_out/${TAG}_force \
    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_force.log 2>&1
 ls -la gpurun_out | tail -20
