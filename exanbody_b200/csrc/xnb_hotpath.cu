@@ -2,6 +2,7 @@
 // One xnb_ctx = one sub-domain on one GPU.  No CPU compute path exists here: without a CUDA device every entry fails.
 #include "../../include/xnb_hotpath.h"
 #include "xnb_kernels.cuh"
+#include "xnb_sweep_cl.cuh"
 #include "xnb_host_decomp.hpp"
 
 #include <algorithm>
@@ -112,7 +113,7 @@ struct xnb_ctx
   DBuf<uint32_t> backup;
   DBuf<double> mass; int n_types = 0;
   // ---- AMR
-  DBuf<uint8_t> side_lut;
+  DBuf<uint8_t> side_lut; double side_lut_density = 0;
   DBuf<uint32_t> sg_size; DBuf<unsigned long long> sub_grid_start; DBuf<uint32_t> sub_grid_cells;
   int64_t n_sub_grid_cells = 0; uint32_t max_side = 1;
   // ---- ghosts
@@ -130,6 +131,10 @@ struct xnb_ctx
   DBuf<unsigned long long> stream_off;
   DBuf<uint16_t> pool; DBuf<uint16_t*> cell_stream;
   int nbh_cap_l = 0; uint32_t nbh_slot_words = 0; bool nbh_full_cap = false;   // capacities of the tiled build (grow on demand)
+  // ---- compiled lists of the pair sweep (xnb_sweep_cl.cuh): derived from the streams after every rebuild
+  struct ClCfg { bool valid = false, ghost = false; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; };
+  ClCfg cl;
+  DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0;
   int64_t n_nonempty_inner = 0;
   int64_t pool_used = 0; uint32_t max_neighbors = 0, max_cell_count = 0, max_stream = 0; double avg_stream = 0; bool have_nbh = false;
   // ---- misc device scalars
@@ -234,9 +239,27 @@ int ensure_particle_capacity(xnb_ctx* c, size_t n, size_t keep)
 }
 
 // builds GridP, the AMR side table and the static ghost item lists once domain, block and distances are known
+// sub_grid_size(n, density) table (amr_grid_algorithm.h:66-78), computed on the host with std::cbrt like the reference;
+// re-uploaded when rebuild_amr's sub_grid_density changes (it must not invalidate the binned grid)
+int ensure_side_lut(xnb_ctx* c)
+{
+  if (c->side_lut.p && c->side_lut_density == c->sub_grid_density) return 0;
+  std::vector<uint8_t> lut(65536);
+  for (size_t n = 0; n < 65536; n++)
+  {
+    size_t side = 0;
+    if (n > 0) { const double s = std::cbrt((double)n / c->sub_grid_density); side = (s < 2.0) ? 1 : std::min((size_t)std::floor(s), (size_t)16); }
+    lut[n] = (uint8_t)side;
+  }
+  CK(c->side_lut.ensure(65536));
+  CK(cudaMemcpy(c->side_lut.p, lut.data(), 65536, cudaMemcpyHostToDevice));
+  c->side_lut_density = c->sub_grid_density;
+  return 0;
+}
+
 int ensure_grid(xnb_ctx* c)
 {
-  if (c->grid_ready) return 0;
+  if (c->grid_ready) return ensure_side_lut(c);
   if (!c->have_domain) return c->fail(XNB_ERR_INVALID, "xnb_set_domain has not been called");
   if (!c->have_dist) return c->fail(XNB_ERR_INVALID, "xnb_set_nbh_dist has not been called");
   if (!c->have_block)
@@ -264,18 +287,7 @@ int ensure_grid(xnb_ctx* c)
   CK(cudaMemset(c->d_scalars64.p, 0, 8 * 8)); CK(cudaMemset(c->d_scalars32.p, 0, 128 * 4));
   CK(cudaMemset(c->cell_count.p, 0, (size_t)ncell * 4)); CK(cudaMemset(c->cell_start.p, 0, (size_t)ncell * 4));
   if (!c->h_pinned) CK(cudaMallocHost(&c->h_pinned, 4096));
-  // sub_grid_size(n, density) table (amr_grid_algorithm.h:66-78), computed on the host with std::cbrt like the reference
-  {
-    std::vector<uint8_t> lut(65536);
-    for (size_t n = 0; n < 65536; n++)
-    {
-      size_t side = 0;
-      if (n > 0) { const double s = std::cbrt((double)n / c->sub_grid_density); side = (s < 2.0) ? 1 : std::min((size_t)std::floor(s), (size_t)16); }
-      lut[n] = (uint8_t)side;
-    }
-    CK(c->side_lut.ensure(65536));
-    CK(cudaMemcpy(c->side_lut.p, lut.data(), 65536, cudaMemcpyHostToDevice));
-  }
+  { int rc = ensure_side_lut(c); if (rc) return rc; }
   // decomposition table for migration
   {
     std::vector<int> hb((size_t)c->nranks * 6);
@@ -446,7 +458,7 @@ int xnb_set_type_mass(xnb_ctx* c, const double* m, int n)
   return XNB_OK;
 }
 
-int xnb_set_sub_grid_density(xnb_ctx* c, double d) { if (!c || !(d > 0)) return XNB_ERR_INVALID; c->sub_grid_density = d; c->grid_ready = false; return XNB_OK; }
+int xnb_set_sub_grid_density(xnb_ctx* c, double d) { if (!c || !(d > 0)) return XNB_ERR_INVALID; c->sub_grid_density = d; return XNB_OK; }
 
 int xnb_set_nccl_comm(xnb_ctx* c, void* comm)
 {
@@ -800,6 +812,119 @@ extern "C" {
 int xnb_ghost_update_all(xnb_ctx* c, void* stream) { if (!c) return XNB_ERR_INVALID; CK(cudaSetDevice(c->device)); return ghost_update(c, true, (cudaStream_t)stream); }
 int xnb_ghost_update_r(xnb_ctx* c, void* stream) { if (!c) return XNB_ERR_INVALID; CK(cudaSetDevice(c->device)); return ghost_update(c, false, (cudaStream_t)stream); }
 
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// compiled lists of the pair sweep: tile shape from the cell occupancy, then k_cl_compile (re-run with more room if a
+// capacity was too small).  Not finding a shape that fits is not an error: the sweep then reads the streams directly
+// (k_lj_sweep).
+// ---------------------------------------------------------------------------------------------------------------------
+static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
+{
+  c->cl.valid = false;
+  if (env_flag("XNB_SWEEP_STREAMS") || c->n_total == 0 || !c->have_nbh) return XNB_OK;
+  const GridP& g = c->g;
+  ClTileP tp{};
+  tp.gap = (int)std::ceil(c->nbh_dist / c->cs);
+  for (int d = 0; d < 3; d++) { tp.lo[d] = ghost ? 0 : g.gl; tp.hi[d] = ghost ? g.dims[d] : g.dims[d] - g.gl; }
+  const int nc[3] = {tp.hi[0] - tp.lo[0], tp.hi[1] - tp.lo[1], tp.hi[2] - tp.lo[2]};
+  if (nc[0] <= 0 || nc[1] <= 0 || nc[2] <= 0) return XNB_OK;
+  const double ne = (double)std::max<int64_t>(c->n_nonempty_inner, 1);
+  const double avg = std::max((double)c->n_inner / ne, 1.0);
+  const double mx = (double)std::max<uint32_t>(c->max_cell_count, 1);
+  const size_t SM_BYTES = 227 * 1024;
+  static const int shapes[][3] = {{4, 2, 2}, {4, 4, 1}, {2, 2, 2}, {4, 2, 1}, {3, 3, 2}, {4, 3, 1}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}, {4, 4, 2}, {3, 2, 2}, {8, 2, 1}, {8, 2, 2}};
+  int et[3] = {0, 0, 0};
+  if (const char* e = getenv("XNB_CL_TILE")) sscanf(e, "%d,%d,%d", &et[0], &et[1], &et[2]);
+  struct Cand { int t[3]; int threads, var; size_t smem; int cap, nh, tc; double score; };
+  std::vector<Cand> cands;
+  for (const auto& sh : shapes)
+  {
+    Cand k{};
+    for (int d = 0; d < 3; d++) k.t[d] = std::min(sh[d], nc[d]);
+    if (et[0] > 0 && (k.t[0] != std::min(et[0], nc[0]) || k.t[1] != std::min(et[1], nc[1]) || k.t[2] != std::min(et[2], nc[2]))) continue;
+    k.tc = k.t[0] * k.t[1] * k.t[2];
+    if (k.tc > 32) continue;
+    bool dup = false; for (const Cand& o : cands) dup |= (o.t[0] == k.t[0] && o.t[1] == k.t[1] && o.t[2] == k.t[2]);
+    if (dup) continue;
+    k.nh = std::min(k.t[0] + 2 * tp.gap, g.dims[0]) * std::min(k.t[1] + 2 * tp.gap, g.dims[1]) * std::min(k.t[2] + 2 * tp.gap, g.dims[2]);
+    const double tile_avg = avg * k.tc;
+    k.threads = 32 * (int)std::ceil(std::min(mx * k.tc, tile_avg * 1.04 + 8.0) / 32.0);
+    if (k.threads > 1024) continue;
+    k.threads = std::max(k.threads, 64);
+    k.var = k.threads <= 576 ? 0 : 1;
+    const double capd = std::min(mx * k.nh, avg * k.nh * 1.08 + 64.0);
+    if (capd > 65535.0) continue;
+    k.cap = ((int)capd + 1) & ~1;
+    k.smem = (((size_t)(2 * k.nh + 2 * k.tc + 2) * 4 + 15) & ~(size_t)15) + (size_t)k.cap * 24;
+    if (k.smem + 1024 + 2048 > SM_BYTES) continue;
+    const int by_smem = (int)(SM_BYTES / (k.smem + 1024 + 256));
+    const int by_regs = 65536 / (k.threads * (k.var == 0 ? 56 : 64));
+    const int by_warps = 64 / (k.threads / 32);
+    const int resident = std::min(std::min(by_smem, by_regs), std::min(by_warps, 32));
+    if (resident < 1) continue;
+    const double useful = resident * (tile_avg / 32.0);               // useful resident warps per SM
+    k.score = std::min(useful, 36.0) - 0.25 * (double)k.nh / (double)k.tc;
+    cands.push_back(k);
+  }
+  std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.score > b.score; });
+  uint32_t* counters = c->d_scalars32.p + 112;
+  for (const Cand& k : cands)
+  {
+    tp.ti = k.t[0]; tp.tj = k.t[1]; tp.tk = k.t[2];
+    tp.tiles_i = (nc[0] + tp.ti - 1) / tp.ti; tp.tiles_j = (nc[1] + tp.tj - 1) / tp.tj; tp.tiles_k = (nc[2] + tp.tk - 1) / tp.tk;
+    tp.nh_max = (tp.ti + 2 * tp.gap) * (tp.tj + 2 * tp.gap) * (tp.tk + 2 * tp.gap); tp.tc_max = k.tc;
+    tp.cap = k.cap; tp.gmax = k.threads / 32;
+    if (c->cl.tp.ti == tp.ti && c->cl.tp.tj == tp.tj && c->cl.tp.tk == tp.tk && c->cl.ghost == ghost)
+    {
+      // same shape as last time: start from the capacities that worked (no second compile pass per rebuild)
+      tp.gmax = std::max(tp.gmax, c->cl.tp.gmax);
+      if (c->cl.tp.cap > tp.cap && (((size_t)(2 * tp.nh_max + 2 * tp.tc_max + 2) * 4 + 15) & ~(size_t)15) + (size_t)c->cl.tp.cap * 24 + 1024 + 2048 <= SM_BYTES) tp.cap = c->cl.tp.cap;
+    }
+    const unsigned blocks = (unsigned)((int64_t)tp.tiles_i * tp.tiles_j * tp.tiles_k);
+    size_t smem = (((size_t)(2 * tp.nh_max + 2 * tp.tc_max + 2) * 4 + 15) & ~(size_t)15) + (size_t)tp.cap * 24;
+    bool ok = false;
+    for (int attempt = 0; attempt < 5; attempt++)
+    {
+      if (c->cl_cap_rows == 0) c->cl_cap_rows = (uint32_t)std::min<double>(4.0e9, (double)c->pool_used / 128.0 * 1.10 + 4096.0);
+      CK(c->cl_rows.ensure((size_t)c->cl_cap_rows * 128 + 64));
+      CK(c->cl_groups.ensure((size_t)blocks * tp.gmax + 16));
+      CK(cudaMemsetAsync(counters, 0, 3 * 4, st));
+      const size_t tbytes = (((size_t)(2 * tp.nh_max + 2 * tp.tc_max + 2) * 4 + 15) & ~(size_t)15);
+      k_cl_compile<<<blocks, 32 * std::min(tp.gmax, 32), tbytes, st>>>(g, tp, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p, c->cl_groups.p,
+                                                                     reinterpret_cast<uint2*>(c->cl_rows.p), c->cl_cap_rows, counters);
+      c->launches++; CK(cudaGetLastError());
+      uint32_t h[3]; int rc = read_back(c, counters, 3, h, st); if (rc) return rc;
+      bool again = false;
+      if ((int)h[1] > tp.gmax) { if (h[1] * 32u > 1024u) break; tp.gmax = (int)h[1]; again = true; }
+      if ((int)h[2] > tp.cap)
+      {
+        tp.cap = ((int)h[2] + 1) & ~1; smem = tbytes + (size_t)tp.cap * 24;
+        if (tp.cap > 65535 || smem + 1024 + 2048 > SM_BYTES) break;
+        again = true;
+      }
+      if (!again && h[0] > c->cl_cap_rows) { c->cl_cap_rows = (uint32_t)((double)h[0] * 1.05) + 1024u; again = true; }
+      if (again) continue;
+      // every tile is swept in one pass: one warp per group of the fullest tile
+      c->cl.tp = tp; c->cl.ghost = ghost; c->cl.blocks = blocks; c->cl.smem = smem; c->cl.rows = h[0];
+      c->cl.threads = std::max(32 * (int)std::max<uint32_t>(h[1], 1u), 64);
+      if (env_int("XNB_CL_THREADS") > 0) c->cl.threads = std::min(env_int("XNB_CL_THREADS") & ~31, 1024);
+      c->cl.var = c->cl.threads <= 576 ? 0 : 1;
+      ok = true;
+      break;
+    }
+    if (ok) { c->cl.valid = true; break; }
+  }
+  if (getenv("XNB_TILE_DEBUG"))
+  {
+    if (c->cl.valid) fprintf(stderr, "[xnb] compiled lists: tiles %dx%dx%d threads %d var %d smem %zu cap %d gmax %d blocks %u rows %u (avg %.1f max %.0f)\n", c->cl.tp.ti, c->cl.tp.tj, c->cl.tp.tk,
+                             c->cl.threads, c->cl.var, c->cl.smem, c->cl.tp.cap, c->cl.tp.gmax, c->cl.blocks, c->cl.rows, avg, mx);
+    else fprintf(stderr, "[xnb] compiled lists: no tile shape fits, sweeping the streams\n");
+  }
+  return XNB_OK;
+}
+
+extern "C" {
 // ---------------------------------------------------------------------------------------------------------------------
 // chunk_neighbors
 // ---------------------------------------------------------------------------------------------------------------------
@@ -895,8 +1020,9 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
       if (again) continue;
       c->pool_used = (int64_t)tot2[0]; c->max_neighbors = hs[0]; c->n_nonempty_inner = hs[1]; c->max_cell_count = hs[2]; c->max_stream = hs[3];
       c->avg_stream = c->n_inner ? (double)tot2[1] / (double)c->n_inner : 0.0;
-      if ((rc = t_end(c, XNB_T_NBH, st))) return rc;
       c->have_nbh = true;
+      if ((rc = cl_prepare(c, false, st))) return rc;
+      if ((rc = t_end(c, XNB_T_NBH, st))) return rc;
       return check_device_errors(c, st);
     }
     if (tiled) return c->fail(XNB_ERR_CAPACITY, "chunk_neighbors: tiled build did not converge");
@@ -920,8 +1046,9 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
   CK(c->pool.ensure((size_t)tot + 64, 0, 1.05));
   LAUNCH(k_nbh_pointers, nblk(g.n_cells, 256), 256, st, g.n_cells, c->pool.p, c->stream_off.p, c->stream_size.p, c->cell_stream.p, c->cell_stream_bytes.p);
   if (n) LAUNCH((k_nbh_build<true>), nblk(n, 128), 128, st, g, (int)n, gap, md2, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
-  if ((rc = t_end(c, XNB_T_NBH, st))) return rc;
   c->have_nbh = true;
+  if ((rc = cl_prepare(c, false, st))) return rc;
+  if ((rc = t_end(c, XNB_T_NBH, st))) return rc;
   return check_device_errors(c, st);
 }
 
@@ -1013,6 +1140,27 @@ template <int MODE, bool EV>
 static int launch_force(xnb_ctx* c, bool ghost, const LJP& lj, double dth, double* fxo, double* fyo, double* fzo, double** evp_out, unsigned* nblocks_out, cudaStream_t st)
 {
   ParticlesP A = c->P(c->cur);
+  int rc;
+  if (c->cl.ghost != ghost) { if ((rc = cl_prepare(c, ghost, st))) return rc; c->cl.ghost = ghost; }
+  if (c->cl.valid)
+  {
+    const xnb_ctx::ClCfg& k = c->cl;
+    if (EV) { CK(c->ev_partials.ensure((size_t)k.blocks * 7 + 16)); if (evp_out) *evp_out = c->ev_partials.p; if (nblocks_out) *nblocks_out = k.blocks; }
+    static bool cl_attr_done[2][2][2] = {{{false, false}, {false, false}}, {{false, false}, {false, false}}};
+#define XNB_CL_LAUNCH(VAR) do { \
+      if (!cl_attr_done[MODE][EV ? 1 : 0][VAR]) { \
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (k_lj_sweep_cl<MODE, EV, VAR>))); \
+        CK(cudaFuncSetAttribute((k_lj_sweep_cl<MODE, EV, VAR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes)); \
+        cl_attr_done[MODE][EV ? 1 : 0][VAR] = true; } \
+      if ((rc = t_begin(c, XNB_T_FORCE, st))) return rc; \
+      k_lj_sweep_cl<MODE, EV, VAR><<<k.blocks, k.threads, k.smem, st>>>(c->g, k.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, \
+          fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, c->cl_groups.p, \
+          reinterpret_cast<const uint2*>(c->cl_rows.p), EV ? c->ev_partials.p : nullptr, c->d_scalars32.p); } while (0)
+    if (k.var == 0) XNB_CL_LAUNCH(0); else XNB_CL_LAUNCH(1);
+#undef XNB_CL_LAUNCH
+    c->launches++; CK(cudaGetLastError());
+    return t_end(c, XNB_T_FORCE, st);
+  }
   const TileCfg t = make_tiles(c, ghost);
   if (t.blocks == 0) return XNB_OK;
   if (EV) { CK(c->ev_partials.ensure((size_t)t.blocks * 7 + 16)); if (evp_out) *evp_out = c->ev_partials.p; if (nblocks_out) *nblocks_out = t.blocks; }
@@ -1023,7 +1171,6 @@ static int launch_force(xnb_ctx* c, bool ghost, const LJP& lj, double dth, doubl
     CK(cudaFuncSetAttribute(k_lj_sweep<MODE, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
     attr_done[MODE][EV ? 1 : 0] = true;
   }
-  int rc;
   if ((rc = t_begin(c, XNB_T_FORCE, st))) return rc;
   k_lj_sweep<MODE, EV><<<t.blocks, t.threads, t.smem, st>>>(c->g, t.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
       fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p,

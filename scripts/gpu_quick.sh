@@ -3,9 +3,10 @@
 set -u
 mkdir -p gpurun_out
 TAG=${1:-q}; shift || true
-( time timeout 1200 python -m pytest tests -m gpu -x -q ) > gpurun_out/${TAG}_pytest.log 2>&1
-tail -4 gpurun_out/${TAG}_pytest.log
-( timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e "$@" ) > gpurun_out/${TAG}_bench.log 2>&1
+( time timeout 1500 python -m pytest tests -m gpu -q ) > gpurun_out/${TAG}_pytest.log 2>&1
+grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/${TAG}_pytest.log | tail -12
+( XNB_TILE_DEBUG=1 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-e2e "$@" ) > gpurun_out/${TAG}_bench.log 2>&1
+grep "^\[xnb\]" gpurun_out/${TAG}_bench.log | sort | uniq -c | head
 tail -1 gpurun_out/${TAG}_bench.log | python -c "
 import sys,json
 l=sys.stdin.read().strip()

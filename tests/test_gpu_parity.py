@@ -156,8 +156,13 @@ def test_stream_decoding_independent_of_oracle(case):
     assert np.array_equal(pairs, o.pairs())
 
 
+@pytest.mark.parametrize("sweep", ["compiled", "streams"])
 @pytest.mark.parametrize("case", list(CASES))
-def test_force_parity(case):
+def test_force_parity(case, sweep, monkeypatch):
+    """sweep = compiled: k_lj_sweep_cl over the compiled lists (the default); streams: k_lj_sweep reading the
+    GridChunkNeighbors streams directly (the fallback when no tile shape fits)"""
+    if sweep == "streams":
+        monkeypatch.setenv("XNB_SWEEP_STREAMS", "1")
     kw = CASES[case]
     o, ctx = setup_pair(kw)
     o.first_iteration()
@@ -177,6 +182,36 @@ def test_force_parity(case):
     assert abs(e_g - e_o) <= TOL * abs(e_o)
     assert np.abs(w_g - w_o).max() <= TOL * np.abs(w_o).max()
     assert abs(k_g - k_o) <= TOL * max(abs(k_o), 1e-300)
+
+
+@pytest.mark.parametrize("tile", ["", "1,1,1", "2,2,2", "4,4,1", "3,3,2", "8,2,2"])
+@pytest.mark.parametrize("case", ["ni16k", "lj2k", "lj_gap2", "lj_voids", "lj_dense"])
+def test_compiled_lists_sweep_equals_stream_sweep(case, tile, monkeypatch):
+    """the compiled lists hold the same candidates in the same order as the streams: forces, energy and virial of the two
+    sweeps are bit-identical per atom, whatever the tile shape (also with ghost cells swept)"""
+    kw = CASES[case]
+    eps, sig, rc = kw["epsilon"], kw["sigma"], kw["rcut"]
+    res = []
+    for streams in (True, False):
+        if streams:
+            monkeypatch.setenv("XNB_SWEEP_STREAMS", "1")
+        else:
+            monkeypatch.delenv("XNB_SWEEP_STREAMS")
+            if tile:
+                monkeypatch.setenv("XNB_CL_TILE", tile)
+        _, ctx = setup_pair(kw)
+        ctx.first_iteration(eps, sig, rc)
+        p = ctx.get_particles()
+        ev = ctx.energy_virial(eps, sig, rc)
+        ctx.zero_particle_force(True); ctx.lennard_jones_force(eps, sig, rc, ghost=True)
+        pg = ctx.get_particles()
+        res.append((p, ev, pg))
+    (pa, eva, pga), (pb, evb, pgb) = res
+    for k in ("fx", "fy", "fz"):
+        assert np.array_equal(pa[k], pb[k]), k
+        assert np.array_equal(pga[k], pgb[k]), k
+    # energy / virial: per-tile partial sums, so only the summation order differs
+    assert abs(eva[0] - evb[0]) <= 1e-12 * abs(eva[0]) and np.abs(eva[1] - evb[1]).max() <= 1e-12 * np.abs(eva[1]).max()
 
 
 @pytest.mark.parametrize("case", ["ni16k", "lj2k", "lj_gap2", "lj_voids"])
