@@ -966,7 +966,7 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
     for (int attempt = 0; attempt < 6 && tiled; attempt++)
     {
       NbhTileP tp{};
-      tp.gap = gap; tp.max_dist2 = md2; tp.cap_l = (c->nbh_cap_l + 15) & ~15;
+      tp.gap = gap; tp.max_dist2 = md2; tp.cap_l = ((c->nbh_cap_l + 7) & ~7) + 4;      // cap_l / 4 odd: the 32 list areas of a warp start in 32 different banks
       tp.tail = (1 + nslot * (2 + (int)mcc) + 15) & ~15;
       if (c->nbh_slot_words == 0) c->nbh_slot_words = (uint32_t)((2 * (mcc + 1) + (size_t)mcc * tp.cap_l * 3 / 4 + 7) & ~(size_t)7);
       tp.slot_words = (int)c->nbh_slot_words;
@@ -979,7 +979,8 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
         if (nh > (size_t)NBH_MAX_HALO) continue;
         // staging capacity: every halo cell at 85% of the fullest cell (a fuller tile makes the kernel report
         // DERR_TILE_CAPACITY and the build is re-run with the exact bound, then with the next smaller tile shape)
-        const size_t cap = (size_t)std::ceil((double)nh * (double)mcc * (c->nbh_full_cap ? 1.0 : 0.85)) + 32;
+        // (cells are staged padded to multiples of 4)
+        const size_t cap = (size_t)std::ceil((double)nh * (double)((mcc + 3) & ~3u) * (c->nbh_full_cap ? 1.0 : 0.85)) + 3 * nh + 32;
         smem = ((cap * 16 + 15) & ~(size_t)15) + lists;
         if (smem <= SMEM_MAX) { pick = q; tp.ti = ti; tp.tj = tj; tp.cap = (int)cap; break; }
       }

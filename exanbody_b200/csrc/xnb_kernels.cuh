@@ -723,7 +723,36 @@ __device__ __noinline__ bool nbh_exact_one(uint32_t self, uint32_t j, double max
   return j != self && d2 > 0.0 && d2 <= max_dist2;
 }
 
+// hot-loop step of the tiled build: if (t <= hi) { append v to the lane's list; mx = max(mx, t) } as four predicated
+// instructions on a shared-state-space address (no generic-address arithmetic in the loop)
+template <class LT>
+XNB_DEVINL void nbh_append(uint32_t& wa, float& mx, float t, float hi, uint32_t v)
+{
+  if (sizeof(LT) == 1)
+    asm volatile("{ .reg .pred p; setp.le.f32 p, %2, %3; @p st.shared.u8 [%0], %4; @p add.u32 %0, %0, 1; @p max.f32 %1, %1, %2; }"
+                 : "+r"(wa), "+f"(mx) : "f"(t), "f"(hi), "r"(v) : "memory");
+  else
+    asm volatile("{ .reg .pred p; setp.le.f32 p, %2, %3; @p st.shared.u16 [%0], %4; @p add.u32 %0, %0, 2; @p max.f32 %1, %1, %2; }"
+                 : "+r"(wa), "+f"(mx) : "f"(t), "f"(hi), "r"(v) : "memory");
+}
+template <class LT> XNB_DEVINL uint32_t nbh_lds(uint32_t a)
+{
+  uint32_t v;
+  if (sizeof(LT) == 1) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+template <class LT> XNB_DEVINL void nbh_sts(uint32_t a, uint32_t v)
+{
+  if (sizeof(LT) == 1) asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+  else asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+
 constexpr int NBH_MAX_HALO = 1024;   // halo cells per tile the kernel supports ((ti+2gap)(tj+2gap)(2gap+1))
+constexpr uint32_t NBH_TRANSPOSE_MAX = 8;   // a trailing chunk of at most this many particles is built candidate-per-lane
+// lane-per-particle chunks of a cell of n particles: chunks of 32 until at most NBH_TRANSPOSE_MAX particles remain; those are
+// built candidate-per-lane by the warp that owns the last chunk
+XNB_DEVINL uint32_t nbh_full_chunks(uint32_t n) { return n == 0u ? 0u : (max(n, NBH_TRANSPOSE_MAX + 1u) - NBH_TRANSPOSE_MAX + 31u) >> 5; }
 constexpr int NBH_MAX_TCELLS = 8;    // cells per tile
 constexpr int NBH_MAX_CHUNKS = 32;   // 32-particle chunks per cell (cells of up to 1024 particles)
 
@@ -739,8 +768,9 @@ k_nbh_fused(GridP g, NbhTileP tp,
 {
   typedef typename std::conditional<U8, uint8_t, uint16_t>::type LT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t hstart[NBH_MAX_HALO + 1];
-  __shared__ uint32_t hfirst[NBH_MAX_HALO];
+  __shared__ uint32_t hstart[NBH_MAX_HALO + 1];   // staged index of each halo cell's first particle (cells padded to multiples of 4)
+  __shared__ uint32_t hfirst[NBH_MAX_HALO];       // global index of each halo cell's first particle
+  __shared__ uint16_t hcount[NBH_MAX_HALO];       // particles of each halo cell
   __shared__ uint32_t s_scan[32];
   __shared__ unsigned s_rmax;
   __shared__ uint32_t s_stats[6];
@@ -778,7 +808,8 @@ k_nbh_fused(GridP g, NbhTileP tp,
       {
         const int hxq = h % HX, hyq = (h / HX) % HY, hzq = h / (HX * HY);
         const int c = ijk_to_index(g.dims, bx0 + hxq, by0 + hyq, bz0 + hzq);
-        cnt = cell_count[c]; hfirst[h] = cell_start[c];
+        cnt = cell_count[c]; hfirst[h] = cell_start[c]; hcount[h] = (uint16_t)cnt;
+        cnt = (cnt + 3u) & ~3u;
       }
       uint32_t total;
       const uint32_t off = block_exclusive_scan<uint32_t>(cnt, &total, s_scan);
@@ -806,8 +837,9 @@ k_nbh_fused(GridP g, NbhTileP tp,
     for (int q = 0; q < tcells; q++)
     {
       const int hq = ((ck - bz0) * HY + (cj0 + q / tci - by0)) * HX + (ci0 + q % tci - bx0);
-      const uint32_t nq = hstart[hq + 1] - hstart[hq];
-      ustart[q] = acc; acc += (nq + 31u) >> 5;
+      const uint32_t nq = hcount[hq];
+      // work units: chunks of 32 particles; a trailing chunk of <= NBH_TRANSPOSE_MAX particles is its own (cheap) unit
+      ustart[q] = acc; acc += nbh_full_chunks(nq);
       s_cum[q][0] = 0u;
       for (uint32_t ic = 1; ic <= ((nq + 31u) >> 5) && ic <= (uint32_t)NBH_MAX_CHUNKS; ic++) s_cum[q][ic] = 0xFFFFFFFFu;
       if (nq == 0)
@@ -826,14 +858,35 @@ k_nbh_fused(GridP g, NbhTileP tp,
   const double oz = __dadd_rn(g.org[2], __dmul_rn((double)(g.off[2] + ck) + 0.5, g.cs));
   {
     float rmax = 0.f;
-    for (int h = warp; h < NH; h += nwarp)
+    // three halo cells per warp and trip, all loads issued before the first use (the loop is latency bound otherwise)
+    for (int h0 = warp; h0 < NH; h0 += 3 * nwarp)
     {
-      const uint32_t d0 = hstart[h], cnt = hstart[h + 1] - d0, s0 = hfirst[h];
-      for (uint32_t p = lane; p < cnt; p += 32)
+      double px[3], py[3], pz[3]; uint32_t d0[3], cnt[3], cnt4[3], s0[3];
+#pragma unroll
+      for (int u = 0; u < 3; u++)
       {
-        const float x = (float)(rx[s0 + p] - ox), y = (float)(ry[s0 + p] - oy), z = (float)(rz[s0 + p] - oz);
-        rmax = fmaxf(rmax, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
-        S4[d0 + p] = make_float4(-2.f * x, -2.f * y, -2.f * z, (float)((double)x * x + (double)y * y + (double)z * z));
+        const int h = h0 + u * nwarp;
+        d0[u] = cnt[u] = cnt4[u] = s0[u] = 0u; px[u] = py[u] = pz[u] = 0.;
+        if (h < NH)
+        {
+          d0[u] = hstart[h]; cnt[u] = hcount[h]; cnt4[u] = hstart[h + 1] - d0[u]; s0[u] = hfirst[h];
+          if ((uint32_t)lane < cnt[u]) { px[u] = rx[s0[u] + lane]; py[u] = ry[s0[u] + lane]; pz[u] = rz[s0[u] + lane]; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 3; u++)
+      {
+        for (uint32_t p = lane; p < cnt4[u]; p += 32)
+        {
+          if (p < cnt[u])
+          {
+            const double xd = p < 32u ? px[u] : rx[s0[u] + p], yd = p < 32u ? py[u] : ry[s0[u] + p], zd = p < 32u ? pz[u] : rz[s0[u] + p];
+            const float x = (float)(xd - ox), y = (float)(yd - oy), z = (float)(zd - oz);
+            rmax = fmaxf(rmax, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
+            S4[d0[u] + p] = make_float4(-2.f * x, -2.f * y, -2.f * z, (float)((double)x * x + (double)y * y + (double)z * z));
+          }
+          else S4[d0[u] + p] = make_float4(0.f, 0.f, 0.f, INFINITY);     // pad: never within any distance
+        }
       }
     }
 #pragma unroll
@@ -842,9 +895,9 @@ k_nbh_fused(GridP g, NbhTileP tp,
   }
   __syncthreads();
   // classification band: |fp32 value - exact d2| <= 2^-24 (60 R^2 + 1.01 max_dist2), R = max |coordinate|;
-  // the band used is 2^-24 * 128 * (3 R^2 + max_dist2)
+  // the band used is 2^-24 (128 R^2 + 4 max_dist2), more than twice that
   const double R = (double)__uint_as_float(s_rmax);
-  const double band = 128.0 * 5.9604644775390625e-08 * (3.0 * R * R + tp.max_dist2);
+  const double band = 5.9604644775390625e-08 * (128.0 * R * R + 4.0 * tp.max_dist2);
   const int cap_l = tp.cap_l;
   LT* const Lw = LB + (size_t)warp * (size_t)(31 * cap_l + tp.tail);   // this warp's 32 list areas
   LT* const L = Lw + (size_t)lane * cap_l;
@@ -858,100 +911,172 @@ k_nbh_fused(GridP g, NbhTileP tp,
     if (u >= n_units) break;
     int q = 0;
     while (q + 1 < tcells && u >= ustart[q + 1]) q++;
-    const uint32_t ic = u - ustart[q];
+    const uint32_t ic0 = u - ustart[q];
     const int cia = ci0 + q % tci, cja = cj0 + q / tci;
     const int ca = ijk_to_index(g.dims, cia, cja, ck);
     const int hA = ((ck - bz0) * HY + (cja - by0)) * HX + (cia - bx0);
-    const uint32_t sA = hstart[hA], nA = hstart[hA + 1] - sA, gA = hfirst[hA];
+    const uint32_t sA = hstart[hA], nA = hcount[hA], gA = hfirst[hA];
     const unsigned long long slot_off = (unsigned long long)ca * (unsigned long long)tp.slot_words;
     uint16_t* const base = out.pool + slot_off;
     uint16_t* const lists = base + 2u * (nA + 1u);
+    const uint32_t nfull = nbh_full_chunks(nA);
+    // pass 0: this unit's lane-per-particle chunk; pass 1 (owner of the last chunk only): the trailing few particles
+    for (uint32_t pass = 0; pass < 2u; pass++)
     {
+      const uint32_t ic = ic0 + pass;
+      const bool transposed = pass == 1u;
+      if (transposed && !(ic == nfull && nA > 32u * nfull)) break;
       const uint32_t ia = ic * 32u + lane;
       const bool active = ia < nA;
-      const float4 qa = S4[sA + (active ? ia : 0u)];
-      const float xi = -0.5f * qa.x, yi = -0.5f * qa.y, zi = -0.5f * qa.z;
-      const float lo = (float)(tp.max_dist2 - band - (double)qa.w);
-      const float hi = active ? (float)(tp.max_dist2 + band - (double)qa.w) : -INFINITY;   // idle lanes accept nothing
-      const float zlo = (float)(band - (double)qa.w);            // own cell only: d2 <= band is "ambiguous" (d2 > 0 test)
-      const uint32_t atom = gA + ia;
       uint32_t cw = 1, groups = 0;                               // L[0] = group counter
-      for (int rk = -gap; rk <= gap; rk++)
+      if (!transposed)
       {
-        const int bk = ck + rk;
-        if (bk < 0 || bk >= g.dims[2]) continue;
-        for (int rj = -gap; rj <= gap; rj++)
+        // ---- lane = particle p_a; all lanes sweep neighbour cell B reading the same q_j (broadcast)
+        const float4 qa = S4[sA + (active ? ia : 0u)];
+        const float xi = -0.5f * qa.x, yi = -0.5f * qa.y, zi = -0.5f * qa.z;
+        const float lo = (float)(tp.max_dist2 - band - (double)qa.w);
+        const float hi = active ? (float)(tp.max_dist2 + band - (double)qa.w) : -INFINITY;   // idle lanes accept nothing
+        const float zlo = (float)(band - (double)qa.w);            // own cell only: d2 <= band is "ambiguous" (d2 > 0 test)
+        const uint32_t atom = gA + ia;
+        const uint32_t Lsh = (uint32_t)__cvta_generic_to_shared(L);
+        for (int rk = -gap; rk <= gap; rk++)
         {
-          const int bj = cja + rj;
-          if (bj < 0 || bj >= g.dims[1]) continue;
-          for (int ri = -gap; ri <= gap; ri++)
+          const int bk = ck + rk;
+          if (bk < 0 || bk >= g.dims[2]) continue;
+          for (int rj = -gap; rj <= gap; rj++)
           {
-            const int bi = cia + ri;
-            if (bi < 0 || bi >= g.dims[0]) continue;
-            const int hB = ((bk - bz0) * HY + (bj - by0)) * HX + (bi - bx0);
-            const uint32_t sB = hstart[hB], nB = hstart[hB + 1] - sB;
-            if (nB == 0) continue;
-            const uint32_t gB = hfirst[hB];
-            const float4* __restrict__ Q = S4 + sB;
-            const uint32_t hdr = cw;
-            cw += 2;
-            uint32_t wi = cw;
-            if (!(rk == 0 && rj == 0 && ri == 0))
+            const int bj = cja + rj;
+            if (bj < 0 || bj >= g.dims[1]) continue;
+            for (int ri = -gap; ri <= gap; ri++)
             {
-              // blocks of 8 candidates; the last block may read up to 7 staged entries past the cell (the staging
-              // buffer is padded) and masks them out
-              for (uint32_t j = 0; j < nB; j += 8)
+              const int bi = cia + ri;
+              if (bi < 0 || bi >= g.dims[0]) continue;
+              const int hB = ((bk - bz0) * HY + (bj - by0)) * HX + (bi - bx0);
+              const uint32_t nB = hcount[hB];
+              if (nB == 0) continue;
+              const uint32_t gB = hfirst[hB];
+              const float4* __restrict__ Q = S4 + hstart[hB];
+              const uint32_t hdr = cw;
+              const uint32_t wa0 = Lsh + (cw + 2u) * (uint32_t)sizeof(LT);
+              uint32_t wa = wa0;
+              float mx = -INFINITY;                                // largest accepted fp32 value of this segment
+              // four candidates per trip (cells are staged padded to multiples of 4 with never-accepted entries):
+              // 4 x (LDS.128 broadcast, 3 FFMA, compare, predicated append)
+              for (uint32_t j = 0; j < nB; j += 4)
               {
-                float t[8];
+                float t[4];
 #pragma unroll
-                for (int v = 0; v < 8; v++)
+                for (int v = 0; v < 4; v++)
                 {
                   const float4 qj = Q[j + v];
                   t[v] = fmaf(zi, qj.z, fmaf(yi, qj.y, fmaf(xi, qj.x, qj.w)));
                 }
-                if (j + 8 > nB)
-                {
 #pragma unroll
-                  for (int v = 1; v < 8; v++) if (j + v >= nB) t[v] = INFINITY;
-                }
-                int amb = 0;
-#pragma unroll
-                for (int v = 0; v < 8; v++) amb |= (int)(t[v] <= hi) & (int)(t[v] > lo);
-                if (!amb)
-                {
-#pragma unroll
-                  for (int v = 0; v < 8; v++) if (t[v] <= hi) { L[wi] = (LT)(j + v); wi++; }
-                }
-                else
-                {
-                  // some candidate of this block sits inside the band: decide those with the exact fp64 test
-                  for (int v = 0; v < 8; v++)
-                    if (t[v] <= hi && (t[v] <= lo || nbh_exact_one(atom, gB + j + v, tp.max_dist2, rx, ry, rz))) { L[wi] = (LT)(j + v); wi++; }
-                }
+                for (int v = 0; v < 4; v++) nbh_append<LT>(wa, mx, t[v], hi, j + v);
               }
-            }
-            else
-            {
-              for (uint32_t j = 0; j < nB; j++)
+              const bool own = rk == 0 && rj == 0 && ri == 0;
+              if (own || mx > lo)
               {
-                const float4 qj = Q[j];
-                const float t = fmaf(zi, qj.z, fmaf(yi, qj.y, fmaf(xi, qj.x, qj.w)));
-                // (cell_a,p_a) != (cell_b,p_b); d2 > 0 is decided exactly when the fp32 value is within the band of zero
-                if (t <= hi && j != ia && ((t <= lo && t > zlo) || nbh_exact_one(atom, gB + j, tp.max_dist2, rx, ry, rz))) { L[wi] = (LT)j; wi++; }
+                // some accepted candidate of this segment sits inside the band (or this is the own cell): re-walk the
+                // few accepted entries and decide the ambiguous ones with the exact fp64 test of the reference
+                uint32_t wr = wa0;
+                for (uint32_t rd = wa0; rd < wa; rd += (uint32_t)sizeof(LT))
+                {
+                  const uint32_t jj = nbh_lds<LT>(rd);
+                  const float4 qj = Q[jj];
+                  const float t = fmaf(zi, qj.z, fmaf(yi, qj.y, fmaf(xi, qj.x, qj.w)));
+                  bool keep = jj < nB && !(own && jj == ia);      // (jj >= nB: only in an overflowed list area; the build is re-run)
+                  // (cell_a,p_a) != (cell_b,p_b); d2 > 0 is decided exactly when the fp32 value is within the band of zero
+                  if (keep && (t > lo || (own && t <= zlo))) keep = nbh_exact_one(atom, gB + jj, tp.max_dist2, rx, ry, rz);
+                  if (keep) { nbh_sts<LT>(wr, jj); wr += (uint32_t)sizeof(LT); }
+                }
+                wa = wr;
+              }
+              const uint32_t n = (wa - wa0) / (uint32_t)sizeof(LT);
+              if (n)
+              {
+                const int slot = ((rk + gap) * nslot1 + (rj + gap)) * nslot1 + (ri + gap);
+                // encode_cell_index (chunk_neighbors.h:137-150); in byte mode the code is looked up at copy-out
+                L[hdr] = U8 ? (LT)(0x80 | slot) : (LT)((uint16_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint16_t)(ri + 16));
+                L[hdr + 1] = (LT)n;
+                cw = hdr + 2u + n; groups++;
               }
             }
-            const uint32_t n = wi - cw;
-            if (n)
-            {
-              const int slot = ((rk + gap) * nslot1 + (rj + gap)) * nslot1 + (ri + gap);
-              // encode_cell_index (chunk_neighbors.h:137-150); in byte mode the code is looked up at copy-out
-              L[hdr] = U8 ? (LT)(0x80 | slot) : (LT)((uint16_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint16_t)(ri + 16));
-              L[hdr + 1] = (LT)n;
-              cw += n; groups++;
-            }
-            else cw = hdr;
           }
         }
+      }
+      else
+      {
+        // ---- trailing chunk of a few particles: one particle at a time, lane = candidate, accepted candidates appended
+        // in order with ballot + popc (a full lane-per-particle pass would cost as much as a 32-particle chunk)
+        const uint32_t nrem = nA - ic * 32u;
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        for (uint32_t a = 0; a < nrem; a++)
+        {
+          const uint32_t iaa = ic * 32u + a;
+          const float4 qa = S4[sA + iaa];
+          const float xi = -0.5f * qa.x, yi = -0.5f * qa.y, zi = -0.5f * qa.z;
+          const float lo = (float)(tp.max_dist2 - band - (double)qa.w);
+          const float hi = (float)(tp.max_dist2 + band - (double)qa.w);
+          const float zlo = (float)(band - (double)qa.w);
+          const uint32_t atom = gA + iaa;
+          LT* const La = Lw + (size_t)a * cap_l;
+          uint32_t cwa = 1, ga = 0;
+          for (int rk = -gap; rk <= gap; rk++)
+          {
+            const int bk = ck + rk;
+            if (bk < 0 || bk >= g.dims[2]) continue;
+            for (int rj = -gap; rj <= gap; rj++)
+            {
+              const int bj = cja + rj;
+              if (bj < 0 || bj >= g.dims[1]) continue;
+              for (int ri = -gap; ri <= gap; ri++)
+              {
+                const int bi = cia + ri;
+                if (bi < 0 || bi >= g.dims[0]) continue;
+                const int hB = ((bk - bz0) * HY + (bj - by0)) * HX + (bi - bx0);
+                const uint32_t nB = hcount[hB];
+                if (nB == 0) continue;
+                const uint32_t gB = hfirst[hB];
+                const float4* __restrict__ Q = S4 + hstart[hB];
+                const bool own = rk == 0 && rj == 0 && ri == 0;
+                const uint32_t hdr = cwa;
+                uint32_t wi = cwa + 2u;
+                for (uint32_t j0 = 0; j0 < nB; j0 += 64u)
+                {
+                  // two candidates per lane (j, j + 32): most cells take a single trip
+                  const uint32_t j = j0 + lane, j2 = j + 32u;
+                  const bool valid = j < nB, valid2 = j2 < nB;
+                  const float4 qj = Q[valid ? j : 0u], qk = Q[valid2 ? j2 : 0u];
+                  const float t = fmaf(zi, qj.z, fmaf(yi, qj.y, fmaf(xi, qj.x, qj.w)));
+                  const float t2 = fmaf(zi, qk.z, fmaf(yi, qk.y, fmaf(xi, qk.x, qk.w)));
+                  bool acc = valid && t <= hi && !(own && j == iaa);
+                  bool acc2 = valid2 && t2 <= hi && !(own && j2 == iaa);
+                  if (acc && (t > lo || (own && t <= zlo))) acc = nbh_exact_one(atom, gB + j, tp.max_dist2, rx, ry, rz);
+                  if (acc2 && (t2 > lo || (own && t2 <= zlo))) acc2 = nbh_exact_one(atom, gB + j2, tp.max_dist2, rx, ry, rz);
+                  const uint32_t m = __ballot_sync(0xffffffffu, acc), m2 = __ballot_sync(0xffffffffu, acc2);
+                  if (acc) La[wi + (uint32_t)__popc(m & lt_mask)] = (LT)j;
+                  wi += (uint32_t)__popc(m);
+                  if (acc2) La[wi + (uint32_t)__popc(m2 & lt_mask)] = (LT)j2;
+                  wi += (uint32_t)__popc(m2);
+                }
+                const uint32_t n = wi - (hdr + 2u);
+                if (n)
+                {
+                  const int slot = ((rk + gap) * nslot1 + (rj + gap)) * nslot1 + (ri + gap);
+                  if (lane == 0)
+                  {
+                    La[hdr] = U8 ? (LT)(0x80 | slot) : (LT)((uint16_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint16_t)(ri + 16));
+                    La[hdr + 1] = (LT)n;
+                  }
+                  cwa = wi; ga++;
+                }
+              }
+            }
+          }
+          if (lane == a) { cw = cwa; groups = ga; }
+        }
+        __syncwarp();
       }
       L[0] = (LT)groups;
       const uint32_t len = active ? cw : 0u;
@@ -969,7 +1094,7 @@ k_nbh_fused(GridP g, NbhTileP tp,
       if (lane == 0)
       {
         volatile uint32_t* cum = &s_cum[q][0];
-        if (ic < (uint32_t)NBH_MAX_CHUNKS) { while ((run = cum[ic]) == 0xFFFFFFFFu) { } cum[ic + 1] = run + chunk_total; }
+        if (ic < (uint32_t)NBH_MAX_CHUNKS) { while ((run = cum[ic]) == 0xFFFFFFFFu) { __nanosleep(64); } cum[ic + 1] = run + chunk_total; }
         atomicMax(&s_stats[0], mxc);
         if (mxl > (uint32_t)cap_l) atomicMax(&s_stats[4], mxl);
       }
@@ -985,16 +1110,25 @@ k_nbh_fused(GridP g, NbhTileP tp,
           reinterpret_cast<uint32_t*>(base)[ia] = off + 1u;
           if (ia == nA - 1u) reinterpret_cast<uint32_t*>(base)[nA] = off + len + 1u;
         }
-        const int nact = (int)min(32u, nA - ic * 32u);
-        for (int l = 0; l < nact; l++)
+        if (len)
         {
-          const uint32_t len_l = __shfl_sync(0xffffffffu, len, l), off_l = __shfl_sync(0xffffffffu, off, l);
-          const LT* src = Lw + (size_t)l * cap_l;
-          uint16_t* dst = lists + off_l;
-          for (uint32_t v = lane; v < len_l; v += 32)
+          // every lane copies its own list: 8-byte stores once the destination is 8-byte aligned (the 32 lists of a chunk are
+          // adjacent in the stream, so the partial sectors of neighbouring lanes merge in L2)
+          uint16_t* const dst = lists + off;
+          const uint32_t head = min(len, (uint32_t)(((8u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 7u)) & 7u) >> 1));
+          uint32_t v = 0;
+          for (; v < head; v++) dst[v] = (uint16_t)L[v];
+          for (; v + 4u <= len; v += 4u)
           {
-            const uint32_t wv = src[v];
-            dst[v] = (U8 && (wv & 0x80u)) ? s_enc[wv & 0x7fu] : (uint16_t)wv;
+            const uint32_t w0 = L[v], w1 = L[v + 1], w2 = L[v + 2], w3 = L[v + 3];
+            *reinterpret_cast<uint2*>(dst + v) = make_uint2(w0 | (w1 << 16), w2 | (w3 << 16));
+          }
+          for (; v < len; v++) dst[v] = (uint16_t)L[v];
+          if (U8)
+          {
+            // byte mode: the group headers hold 0x80|slot; hop over them and write the cell codes
+            uint32_t pos = 1;
+            for (uint32_t gq = 0; gq < groups; gq++) { const uint32_t code = L[pos], n = L[pos + 1]; dst[pos] = s_enc[code & 0x7fu]; pos += 2u + n; }
           }
         }
       }

@@ -231,6 +231,8 @@ k_cl_compile(GridP g, ClTileP tp, const uint32_t* __restrict__ cell_start, const
 // independent FP64 chains.  Arithmetic identical to k_lj_sweep.
 // VAR 0: <= 576 threads, two blocks per SM (<= 56 registers); VAR 1: <= 1024 threads.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t CL_PREFETCH_ROWS = 8;
+
 XNB_DEVINL uint2 ld_stream8(const uint2* p)
 {
   uint2 v;
@@ -262,6 +264,14 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, LJP lj, double dth,
   const bool bad = ngroups > (uint32_t)tp.gmax || n_halo > (uint32_t)tp.cap;   // cannot happen after a successful compile
   if (bad && threadIdx.x == 0) atomicOr(err, DERR_TILE_CAPACITY);
 
+  const uint2* const gt = groups + (size_t)blockIdx.x * (size_t)tp.gmax;
+  if (!bad && threadIdx.x < ngroups * 32u)
+  {
+    // start pulling this warp's first list rows towards L2 while the positions are staged
+    const uint2 ge = gt[threadIdx.x >> 5];
+    const uint2* R = rows + ((size_t)ge.x * 32u + (uint32_t)lane);
+    for (uint32_t k = 0; k < min(ge.y, CL_PREFETCH_ROWS); k++) asm volatile("prefetch.global.L2 [%0];" :: "l"(R + (size_t)k * 32u));
+  }
   if (!bad && n_tile > 0)
   {
     // halo positions: one warp per halo cell, lanes over its particles (coalesced reads)
@@ -280,7 +290,6 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, LJP lj, double dth,
   LJAcc acc;
   acc.e = acc.wxx = acc.wyy = acc.wzz = acc.wxy = acc.wxz = acc.wyz = 0.;
   const unsigned long long rc2b = (unsigned long long)__double_as_longlong(lj.rcut2);   // bits(d2) - 1 < bits(rcut2) <=> d2 in (0, rcut2]
-  const uint2* const gt = groups + (size_t)blockIdx.x * (size_t)tp.gmax;
 
   if (!bad)
   for (uint32_t t = threadIdx.x; t < ngroups * 32u; t += blockDim.x)
@@ -307,6 +316,8 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, LJP lj, double dth,
     {
       uint2 w2 = w0;
       if (k + 2u < trips) w2 = ld_stream8(R + (size_t)(k + 2u) * 32u);
+      // the rows are streamed from HBM exactly once: pull them into L2 well ahead of the register prefetch
+      if (k + CL_PREFETCH_ROWS < trips) asm volatile("prefetch.global.L2 [%0];" :: "l"(R + (size_t)(k + CL_PREFETCH_ROWS) * 32u));
       const uint32_t j[4] = {w0.x & 0xffffu, w0.x >> 16, w0.y & 0xffffu, w0.y >> 16};
       double dx[4], dy[4], dz[4], d2[4]; bool ok[4];
 #pragma unroll
