@@ -10,7 +10,7 @@ GPU, spatial decomposition, NCCL halo) under torchrun.  Prints ONE JSON line (ra
   value     device-resident rate: atoms(all ranks) * K / max-over-ranks CUDA-event time of the K steps
   e2e       the same steps driven through the C-ABI with HOST buffers: every step uploads r,v from pinned host memory,
             runs the step and downloads r,v,f (+ids) -- copies inside the timed region
-  roofline  the dominant kernel (pair sweep k_lj_force): algorithmic bytes per launch / its mean CUDA-event duration
+  roofline  the dominant kernel (pair sweep k_lj_sweep_cl): algorithmic bytes per launch / its mean CUDA-event duration
   cpu_baseline  the CPU oracle (oracle/, the OpenMP restatement of the reference) on a bounded sample of the same workload
 
 --impl reference times the reference's CPU implementation of the path.  The reference itself cannot be built here (it needs
@@ -62,16 +62,48 @@ def workload(name, nranks=1):
 
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML polled every 5 ms from a
+    thread (the timed C call releases the GIL); nvidia-smi -lms as the fallback when NVML cannot be loaded."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _poll(self, nv, h):
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
@@ -82,6 +114,12 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.sm:
+                out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=float(max(self.mx)), reasons=sorted(self.reasons), samples=len(self.sm), source="nvml")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -106,7 +144,7 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
         return out
 
 
@@ -275,10 +313,15 @@ def b200_arm(args):
     peak, peak_src = measured_peaks()
     fk_ms = tim["force"]["ms"] / max(tim["force"]["n"], 1)
     achieved = force_bytes * n_atoms_local / (fk_ms * 1e-3) / 1e9 if fk_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_lj_force (pair sweep + fused second half kick)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic("k_lj_force"), "peak_source": peak_src,
+    si = ctx.sweep_info()
+    kname = "k_lj_sweep_cl" if si["compiled"] else "k_lj_sweep"
+    n_list = si["candidates"] / max(n_atoms_local, 1) if si["compiled"] else None        # list entries per atom (78 on the perfect lattice)
+    roofline = {"bound": "hbm", "kernel": kname + " (pair sweep + fused second half kick)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(kname), "peak_source": peak_src,
                 "algorithmic_bytes_per_atom": force_bytes, "stream_bytes_per_atom": S, "kernel_ms": fk_ms,
-                "whole_step": {"algorithmic_bytes_per_atom": step_bytes, "achieved": step_bytes * value / world / 1e9, "frac": step_bytes * value / world / 1e9 / peak}}
+                "whole_step": {"algorithmic_bytes_per_atom": step_bytes, "achieved": step_bytes * value / world / 1e9, "frac": step_bytes * value / world / 1e9 / peak},
+                "sweep": {"compiled_lists": si["compiled"], "tile_cells": si["tile"], "threads": si["threads"], "blocks": si["blocks"], "smem_bytes": si["smem_bytes"],
+                          "list_entries_per_atom": n_list, "compiled_list_bytes_per_atom": (si["rows"] * 256.0 / max(n_atoms_local, 1)) if si["compiled"] else None}}
     breakdown = {k2: (v["ms"] / args.steps) for k2, v in tim.items()}
 
     # ---- end to end through the C-ABI with host buffers -----------------------------------------------------------------
@@ -322,6 +365,15 @@ def b200_arm(args):
             dfma = capi.measure_dfma_peak(local)
         except Exception:
             dfma = None
+        if dfma and n_list:
+            # F_alg = 8 N_list + 19 N_cut + 30 flop per atom-step; N_cut estimated from N_list by the volume ratio
+            # (rc / (rc + skin))^3 (54 of 78 on the perfect lattice).  The slower of the two ceilings bounds the path.
+            n_cut = n_list * (rc / (rc + kw["rcut_inc"])) ** 3
+            f_sweep = 8.0 * n_list + 19.0 * n_cut
+            roofline["fp64"] = {"peak_tflops": dfma, "peak_source": "k_dfma_probe measured in this run", "flop_per_atom_sweep": f_sweep,
+                                "achieved_tflops": f_sweep * n_atoms_local / (fk_ms * 1e-3) / 1e12 if fk_ms > 0 else 0.0,
+                                "frac": (f_sweep * n_atoms_local / (fk_ms * 1e-3) / 1e12 / dfma) if fk_ms > 0 else 0.0,
+                                "whole_step_ceiling_atom_steps_per_s": {"hbm": peak * 1e9 / step_bytes, "fp64": dfma * 1e12 / (f_sweep + 30.0)}}
         line = {
             "metric": "atom-timesteps/s (LJ neighbor+force+ghost)", "value": value, "unit": "atom-timesteps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -17,7 +17,7 @@ SYMBOLS = [
     "xnb_create", "xnb_destroy", "xnb_last_error", "xnb_version", "xnb_set_domain", "xnb_init_rcb_grid", "xnb_set_nbh_dist",
     "xnb_set_type_mass", "xnb_set_sub_grid_density", "xnb_set_nccl_comm", "xnb_nccl_unique_id", "xnb_nccl_init_rank",
     "xnb_set_particles", "xnb_num_inner", "xnb_num_total", "xnb_get_particles", "xnb_upload_rv", "xnb_download_rvf",
-    "xnb_get_grid_info", "xnb_get_cells", "xnb_move_particles", "xnb_rebuild_amr", "xnb_backup_r", "xnb_ghost_comm_scheme",
+    "xnb_get_grid_info", "xnb_get_sweep_info", "xnb_get_cells", "xnb_move_particles", "xnb_rebuild_amr", "xnb_backup_r", "xnb_ghost_comm_scheme",
     "xnb_ghost_update_all", "xnb_ghost_update_r", "xnb_chunk_neighbors", "xnb_zero_particle_force", "xnb_lennard_jones_force",
     "xnb_divide_force_by_mass", "xnb_push_f_v_r", "xnb_push_f_v", "xnb_particle_displ_over", "xnb_verlet_first_half",
     "xnb_read_displ_over", "xnb_force_and_second_half", "xnb_run_steps", "xnb_first_iteration", "xnb_energy_virial",
@@ -30,6 +30,11 @@ SYMBOLS = [
 class XnbGridInfo(C.Structure):
     _fields_ = [("dims", C.c_int64 * 3), ("offset", C.c_int64 * 3), ("ghost_layers", C.c_int64), ("n_cells", C.c_int64),
                 ("block_start", C.c_int64 * 3), ("block_end", C.c_int64 * 3)]
+
+
+class XnbSweepInfo(C.Structure):
+    _fields_ = [("compiled", C.c_int32), ("ghost", C.c_int32), ("tile", C.c_int64 * 3), ("threads", C.c_int64), ("blocks", C.c_int64),
+                ("smem_bytes", C.c_int64), ("rows", C.c_int64), ("candidates", C.c_int64)]
 
 
 class XnbLatticeCfg(C.Structure):
@@ -68,7 +73,7 @@ def load():
         "xnb_nccl_unique_id": (I, [P]), "xnb_nccl_init_rank": (I, [P, P, I, I]),
         "xnb_set_particles": (I, [P, I64] + [P] * 8), "xnb_num_inner": (I64, [P]), "xnb_num_total": (I64, [P]),
         "xnb_get_particles": (I, [P, I64, I64] + [P] * 12), "xnb_upload_rv": (I, [P] * 8), "xnb_download_rvf": (I, [P] * 12),
-        "xnb_get_grid_info": (I, [P, C.POINTER(XnbGridInfo)]), "xnb_get_cells": (I, [P, P, P]),
+        "xnb_get_grid_info": (I, [P, C.POINTER(XnbGridInfo)]), "xnb_get_sweep_info": (I, [P, C.POINTER(XnbSweepInfo)]), "xnb_get_cells": (I, [P, P, P]),
         "xnb_move_particles": (I, [P, P]), "xnb_rebuild_amr": (I, [P, P]), "xnb_backup_r": (I, [P, P]), "xnb_ghost_comm_scheme": (I, [P, P]),
         "xnb_ghost_update_all": (I, [P, P]), "xnb_ghost_update_r": (I, [P, P]), "xnb_chunk_neighbors": (I, [P, P]),
         "xnb_zero_particle_force": (I, [P, I, P]), "xnb_lennard_jones_force": (I, [P, D, D, D, I, P]), "xnb_divide_force_by_mass": (I, [P, P]),
@@ -184,6 +189,12 @@ class Context:
         self._ck(self.L.xnb_get_grid_info(self.h, C.byref(gi)))
         return dict(dims=np.array(gi.dims[:]), offset=np.array(gi.offset[:]), ghost_layers=gi.ghost_layers, n_cells=gi.n_cells,
                     block_start=np.array(gi.block_start[:]), block_end=np.array(gi.block_end[:]))
+
+    def sweep_info(self):
+        si = XnbSweepInfo()
+        self._ck(self.L.xnb_get_sweep_info(self.h, C.byref(si)))
+        return dict(compiled=bool(si.compiled), ghost=bool(si.ghost), tile=tuple(si.tile[:]), threads=si.threads, blocks=si.blocks,
+                    smem_bytes=si.smem_bytes, rows=si.rows, candidates=si.candidates)
 
     def cells(self):
         nc = self.grid_info()["n_cells"]

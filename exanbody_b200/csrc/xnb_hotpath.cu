@@ -132,7 +132,7 @@ struct xnb_ctx
   DBuf<uint16_t> pool; DBuf<uint16_t*> cell_stream;
   int nbh_cap_l = 0; uint32_t nbh_slot_words = 0; bool nbh_full_cap = false;   // capacities of the tiled build (grow on demand)
   // ---- compiled lists of the pair sweep (xnb_sweep_cl.cuh): derived from the streams after every rebuild
-  struct ClCfg { bool valid = false, ghost = false; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; };
+  struct ClCfg { bool valid = false, ghost = false; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; int64_t candidates = 0; };
   ClCfg cl;
   DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0;
   int64_t n_nonempty_inner = 0;
@@ -570,6 +570,20 @@ int xnb_get_grid_info(const xnb_ctx* cc, xnb_grid_info* out)
   return XNB_OK;
 }
 
+int xnb_get_sweep_info(const xnb_ctx* c, xnb_sweep_info* out)
+{
+  if (!c || !out) return XNB_ERR_INVALID;
+  memset(out, 0, sizeof *out);
+  out->compiled = c->cl.valid ? 1 : 0;
+  if (c->cl.valid)
+  {
+    out->tile[0] = c->cl.tp.ti; out->tile[1] = c->cl.tp.tj; out->tile[2] = c->cl.tp.tk;
+    out->threads = c->cl.threads; out->blocks = c->cl.blocks; out->smem_bytes = (int64_t)c->cl.smem;
+    out->rows = c->cl.rows; out->candidates = c->cl.candidates; out->ghost = c->cl.ghost ? 1 : 0;
+  }
+  return XNB_OK;
+}
+
 int xnb_get_cells(xnb_ctx* c, uint32_t* cell_start, uint32_t* cell_count)
 {
   if (!c) return XNB_ERR_INVALID;
@@ -889,12 +903,12 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
       if (c->cl_cap_rows == 0) c->cl_cap_rows = (uint32_t)std::min<double>(4.0e9, (double)c->pool_used / 128.0 * 1.10 + 4096.0);
       CK(c->cl_rows.ensure((size_t)c->cl_cap_rows * 128 + 64));
       CK(c->cl_groups.ensure((size_t)blocks * tp.gmax + 16));
-      CK(cudaMemsetAsync(counters, 0, 3 * 4, st));
+      CK(cudaMemsetAsync(counters, 0, 6 * 4, st));      // [0..2] u32 counters, [4..5] one u64 (8-byte aligned): list entries
       const size_t tbytes = (((size_t)(2 * tp.nh_max + 2 * tp.tc_max + 2) * 4 + 15) & ~(size_t)15);
       k_cl_compile<<<blocks, 32 * std::min(tp.gmax, 32), tbytes, st>>>(g, tp, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p, c->cl_groups.p,
-                                                                     reinterpret_cast<uint2*>(c->cl_rows.p), c->cl_cap_rows, counters);
+                                                                     reinterpret_cast<uint2*>(c->cl_rows.p), c->cl_cap_rows, counters, reinterpret_cast<unsigned long long*>(counters + 4));
       c->launches++; CK(cudaGetLastError());
-      uint32_t h[3]; int rc = read_back(c, counters, 3, h, st); if (rc) return rc;
+      uint32_t h[6]; int rc = read_back(c, counters, 6, h, st); if (rc) return rc;
       bool again = false;
       if ((int)h[1] > tp.gmax) { if (h[1] * 32u > 1024u) break; tp.gmax = (int)h[1]; again = true; }
       if ((int)h[2] > tp.cap)
@@ -907,6 +921,7 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
       if (again) continue;
       // every tile is swept in one pass: one warp per group of the fullest tile
       c->cl.tp = tp; c->cl.ghost = ghost; c->cl.blocks = blocks; c->cl.smem = smem; c->cl.rows = h[0];
+      c->cl.candidates = (int64_t)(((unsigned long long)h[5] << 32) | h[4]);
       c->cl.threads = std::max(32 * (int)std::max<uint32_t>(h[1], 1u), 64);
       if (env_int("XNB_CL_THREADS") > 0) c->cl.threads = std::min(env_int("XNB_CL_THREADS") & ~31, 1024);
       c->cl.var = c->cl.threads <= 576 ? 0 : 1;

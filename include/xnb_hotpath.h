@@ -87,6 +87,22 @@ typedef struct xnb_grid_info
   int64_t block_end[3];
 } xnb_grid_info;
 int xnb_get_grid_info(const xnb_ctx*, xnb_grid_info* out);
+/* layout of the pair sweep's own copy of the neighbour lists ("compiled lists", derived from the GridChunkNeighbors
+   streams after every xnb_chunk_neighbors; no reference counterpart: the reference sweeps the streams directly,
+   src/compute/include/exanb/compute/compute_cell_particle_pairs_impl_default.h:143-179).  compiled = 0: no tile shape
+   fits shared memory and the sweep reads the streams.                                                             */
+typedef struct xnb_sweep_info
+{
+  int32_t compiled;       /* 1 if the sweep runs over compiled lists                                   */
+  int32_t ghost;          /* lists compiled for ghost cells too (lennard_jones_force ghost=true)       */
+  int64_t tile[3];        /* cells per tile (= per thread block)                                       */
+  int64_t threads;        /* threads per block                                                         */
+  int64_t blocks;
+  int64_t smem_bytes;     /* staged positions of a tile's halo box                                     */
+  int64_t rows;           /* 256-byte rows of the compiled lists (32 lanes x 4 candidates)             */
+  int64_t candidates;     /* list entries of all swept particles (sum of neighbour counts)             */
+} xnb_sweep_info;
+int xnb_get_sweep_info(const xnb_ctx*, xnb_sweep_info* out);
 /* per-cell particle count and start index into the flat arrays (the per-cell SoA views of CellParticles)        */
 int xnb_get_cells(xnb_ctx*, uint32_t* cell_start /* n_cells */, uint32_t* cell_count /* n_cells */);
 
