@@ -48,7 +48,8 @@ def main():
             allp = U.by_id({k: np.concatenate([e[k] for e in everyone]) for k in everyone[0]})
             assert np.array_equal(allp["id"], pr["id"]), "%s: atoms lost or duplicated across ranks" % name
             assert rb == rb_ref and rb > 0, (name, rb, rb_ref)
-            assert min(len(e["id"]) for e in everyone) > 0
+            if name != "lj_voids":                 # clusters and voids: a rank may legitimately own no atom at all (covered on purpose)
+                assert min(len(e["id"]) for e in everyone) > 0
             for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
                 assert np.array_equal(allp[k], pr[k]), "%s: %s differs between %d ranks and 1 rank (max %g)" % (name, k, world, np.abs(allp[k] - pr[k]).max())
             print("mgpu parity ok: %s, %d ranks, %d atoms, %d steps, %d rebuilds, atoms per rank %s" % (name, world, len(pr["id"]), nsteps, rb, [len(e["id"]) for e in everyone]), flush=True)
