@@ -34,7 +34,7 @@ class XnbGridInfo(C.Structure):
 
 class XnbSweepInfo(C.Structure):
     _fields_ = [("compiled", C.c_int32), ("ghost", C.c_int32), ("tile", C.c_int64 * 3), ("threads", C.c_int64), ("blocks", C.c_int64),
-                ("smem_bytes", C.c_int64), ("rows", C.c_int64), ("candidates", C.c_int64)]
+                ("smem_bytes", C.c_int64), ("rows", C.c_int64), ("candidates", C.c_int64), ("interior_tiles", C.c_int64), ("boundary_tiles", C.c_int64)]
 
 
 class XnbLatticeCfg(C.Structure):
@@ -194,7 +194,7 @@ class Context:
         si = XnbSweepInfo()
         self._ck(self.L.xnb_get_sweep_info(self.h, C.byref(si)))
         return dict(compiled=bool(si.compiled), ghost=bool(si.ghost), tile=tuple(si.tile[:]), threads=si.threads, blocks=si.blocks,
-                    smem_bytes=si.smem_bytes, rows=si.rows, candidates=si.candidates)
+                    smem_bytes=si.smem_bytes, rows=si.rows, candidates=si.candidates, interior_tiles=si.interior_tiles, boundary_tiles=si.boundary_tiles)
 
     def cells(self):
         nc = self.grid_info()["n_cells"]

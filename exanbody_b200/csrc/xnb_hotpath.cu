@@ -132,9 +132,11 @@ struct xnb_ctx
   DBuf<uint16_t> pool; DBuf<uint16_t*> cell_stream;
   int nbh_cap_l = 0; uint32_t nbh_slot_words = 0; bool nbh_full_cap = false;   // capacities of the tiled build (grow on demand)
   // ---- compiled lists of the pair sweep (xnb_sweep_cl.cuh): derived from the streams after every rebuild
-  struct ClCfg { bool valid = false, ghost = false; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; int64_t candidates = 0; };
+  struct ClCfg { bool valid = false, ghost = false; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; int64_t candidates = 0;
+                 unsigned n_interior = 0, n_boundary = 0; };    // tiles whose halo box holds no ghost cell / the others (cl_tile_list: interior first)
   ClCfg cl;
-  DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0;
+  DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0; DBuf<uint32_t> cl_tile_list;
+  cudaStream_t st_comm = nullptr; cudaEvent_t ev_pos = nullptr, ev_ghost = nullptr;      // halo exchange overlapped with the interior tiles
   int64_t n_nonempty_inner = 0;
   int64_t pool_used = 0; uint32_t max_neighbors = 0, max_cell_count = 0, max_stream = 0; double avg_stream = 0; bool have_nbh = false;
   // ---- misc device scalars
@@ -144,7 +146,8 @@ struct xnb_ctx
   DBuf<double> ev_partials;
   DBuf<int> d_blocks;
   DBuf<uint32_t> mig_rank, mig_pos, mig_base;
-  void* h_pinned = nullptr;               // 4 KB pinned scratch for small read-backs
+  void* h_pinned = nullptr;               // 4 KB pinned scratch for small read-backs ([1024..1032): displacement count of xnb_run_steps)
+  cudaEvent_t ev_flag = nullptr;
   // ---- NCCL
   ncclComm_t comm = nullptr; bool own_comm = false;
   // ---- counters
@@ -407,6 +410,10 @@ void xnb_destroy(xnb_ctx* c)
   cudaDeviceSynchronize();
   for (int cat = 0; cat < XNB_T_COUNT; cat++) for (cudaEvent_t e : c->tpool[cat].ev) cudaEventDestroy(e);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->ev_flag) cudaEventDestroy(c->ev_flag);
+  if (c->ev_pos) cudaEventDestroy(c->ev_pos);
+  if (c->ev_ghost) cudaEventDestroy(c->ev_ghost);
+  if (c->st_comm) cudaStreamDestroy(c->st_comm);
   if (c->comm && c->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   delete c;
 }
@@ -580,6 +587,7 @@ int xnb_get_sweep_info(const xnb_ctx* c, xnb_sweep_info* out)
     out->tile[0] = c->cl.tp.ti; out->tile[1] = c->cl.tp.tj; out->tile[2] = c->cl.tp.tk;
     out->threads = c->cl.threads; out->blocks = c->cl.blocks; out->smem_bytes = (int64_t)c->cl.smem;
     out->rows = c->cl.rows; out->candidates = c->cl.candidates; out->ghost = c->cl.ghost ? 1 : 0;
+    out->interior_tiles = c->cl.n_interior; out->boundary_tiles = c->cl.n_boundary;
   }
   return XNB_OK;
 }
@@ -925,6 +933,24 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
       c->cl.threads = std::max(32 * (int)std::max<uint32_t>(h[1], 1u), 64);
       if (env_int("XNB_CL_THREADS") > 0) c->cl.threads = std::min(env_int("XNB_CL_THREADS") & ~31, 1024);
       c->cl.var = c->cl.threads <= 576 ? 0 : 1;
+      {
+        // interior tiles: the halo box touches no ghost cell, so they can be swept while the halo exchange is in flight
+        std::vector<uint32_t> inner, outer;
+        for (unsigned b = 0; b < blocks; b++)
+        {
+          const int t_i = (int)(b % tp.tiles_i), t_j = (int)((b / tp.tiles_i) % tp.tiles_j), t_k = (int)(b / ((unsigned)tp.tiles_i * tp.tiles_j));
+          const int c0[3] = {tp.lo[0] + t_i * tp.ti, tp.lo[1] + t_j * tp.tj, tp.lo[2] + t_k * tp.tk};
+          const int tc[3] = {std::min(tp.ti, tp.hi[0] - c0[0]), std::min(tp.tj, tp.hi[1] - c0[1]), std::min(tp.tk, tp.hi[2] - c0[2])};
+          bool in = !ghost;
+          for (int d = 0; d < 3; d++) in = in && c0[d] - tp.gap >= g.gl && c0[d] + tc[d] - 1 + tp.gap < g.dims[d] - g.gl;
+          (in ? inner : outer).push_back(b);
+        }
+        c->cl.n_interior = (unsigned)inner.size(); c->cl.n_boundary = (unsigned)outer.size();
+        inner.insert(inner.end(), outer.begin(), outer.end());
+        CK(c->cl_tile_list.ensure(inner.size() + 16));
+        CK(cudaMemcpyAsync(c->cl_tile_list.p, inner.data(), inner.size() * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));      // `inner` is pageable host memory that goes out of scope
+      }
       ok = true;
       break;
     }
@@ -1153,7 +1179,9 @@ static TileCfg make_tiles(const xnb_ctx* c, bool ghost)
 }
 
 template <int MODE, bool EV>
-static int launch_force(xnb_ctx* c, bool ghost, const LJP& lj, double dth, double* fxo, double* fyo, double* fzo, double** evp_out, unsigned* nblocks_out, cudaStream_t st)
+// part: 0 = every tile, 1 = interior tiles only, 2 = boundary tiles only (compiled lists; 1 and 2 are timed by the caller)
+static int launch_force(xnb_ctx* c, bool ghost, const LJP& lj, double dth, double* fxo, double* fyo, double* fzo, double** evp_out, unsigned* nblocks_out, cudaStream_t st,
+                        const unsigned long long* skip_if_nonzero = nullptr, int part = 0)
 {
   ParticlesP A = c->P(c->cur);
   int rc;
@@ -1168,14 +1196,17 @@ static int launch_force(xnb_ctx* c, bool ghost, const LJP& lj, double dth, doubl
         cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (k_lj_sweep_cl<MODE, EV, VAR>))); \
         CK(cudaFuncSetAttribute((k_lj_sweep_cl<MODE, EV, VAR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes)); \
         cl_attr_done[MODE][EV ? 1 : 0][VAR] = true; } \
-      if ((rc = t_begin(c, XNB_T_FORCE, st))) return rc; \
-      k_lj_sweep_cl<MODE, EV, VAR><<<k.blocks, k.threads, k.smem, st>>>(c->g, k.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, \
+      if (part == 0 && (rc = t_begin(c, XNB_T_FORCE, st))) return rc; \
+      k_lj_sweep_cl<MODE, EV, VAR><<<nb, k.threads, k.smem, st>>>(c->g, k.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, \
           fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, c->cl_groups.p, \
-          reinterpret_cast<const uint2*>(c->cl_rows.p), EV ? c->ev_partials.p : nullptr, c->d_scalars32.p); } while (0)
+          reinterpret_cast<const uint2*>(c->cl_rows.p), EV ? c->ev_partials.p : nullptr, c->d_scalars32.p, skip_if_nonzero, tl); } while (0)
+    const unsigned nb = part == 0 ? k.blocks : part == 1 ? k.n_interior : k.n_boundary;
+    const uint32_t* tl = part == 0 ? nullptr : part == 1 ? c->cl_tile_list.p : c->cl_tile_list.p + k.n_interior;
+    if (nb == 0) return XNB_OK;
     if (k.var == 0) XNB_CL_LAUNCH(0); else XNB_CL_LAUNCH(1);
 #undef XNB_CL_LAUNCH
     c->launches++; CK(cudaGetLastError());
-    return t_end(c, XNB_T_FORCE, st);
+    return part == 0 ? t_end(c, XNB_T_FORCE, st) : XNB_OK;
   }
   const TileCfg t = make_tiles(c, ghost);
   if (t.blocks == 0) return XNB_OK;
@@ -1190,7 +1221,7 @@ static int launch_force(xnb_ctx* c, bool ghost, const LJP& lj, double dth, doubl
   if ((rc = t_begin(c, XNB_T_FORCE, st))) return rc;
   k_lj_sweep<MODE, EV><<<t.blocks, t.threads, t.smem, st>>>(c->g, t.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
       fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p,
-      c->stream_size.p, EV ? c->ev_partials.p : nullptr);
+      c->stream_size.p, EV ? c->ev_partials.p : nullptr, skip_if_nonzero);
   c->launches++; CK(cudaGetLastError());
   return t_end(c, XNB_T_FORCE, st);
 }
@@ -1307,24 +1338,72 @@ int xnb_first_iteration(xnb_ctx* c, double eps, double sig, double rcut, void* s
 int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, double rcut, void* stream, int* rebuilds_out)
 {
   if (!c) return XNB_ERR_INVALID;
+  if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "no neighbour list (run xnb_first_iteration)");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
   int rebuilds = 0, rc;
+  if (!c->ev_flag) CK(cudaEventCreateWithFlags(&c->ev_flag, cudaEventDisableTiming));
+  volatile unsigned long long* h_flag = reinterpret_cast<volatile unsigned long long*>(static_cast<char*>(c->h_pinned) + 1024);
+  const bool speculate = !env_flag("XNB_NO_SPECULATION");
   for (int it = 0; it < nsteps; it++)
   {
     if ((rc = xnb_verlet_first_half(c, dt, stream))) return rc;
-    uint64_t over = 0;
-    if ((rc = xnb_read_displ_over(c, &over, stream))) return rc;
+    // trigger_move_particles (update-particles.msp:1-6): MPI_Allreduce(SUM, 1 x u64) of particle_displ_over.cu:174, then the
+    // host reads the count.  The fast path (ghost_update_r + sweep) is enqueued BEFORE the host waits for that count, so the GPU
+    // never idles on the host round trip; the sweep reads the same counter on the device and returns at once if a rebuild is due
+    // (ghost_update_r before a rebuild is harmless: the rebuild recreates every ghost).
+    if (c->nranks > 1) { if (!c->comm) return c->fail(XNB_ERR_NCCL, "no communicator"); NK(g_nccl.AllReduce(c->d_scalars64.p, c->d_scalars64.p, 1, nccl_uint64, nccl_sum, c->comm, st)); }
+    CK(cudaMemcpyAsync(const_cast<unsigned long long*>(h_flag), c->d_scalars64.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c->ev_flag, st));
+    size_t force_scopes = c->tpool[XNB_T_FORCE].used;
+    const bool overlap = speculate && c->nranks > 1 && c->cl.valid && !c->cl.ghost && c->cl.n_interior > 0 && c->cl.n_boundary > 0 && !env_flag("XNB_NO_OVERLAP");
+    if (overlap)
+    {
+      // halo exchange (pack kernel + NCCL send/recv) on its own stream while the interior tiles are swept; the boundary tiles
+      // wait for it.  One timing scope spans both sweep launches.
+      if (!c->st_comm)
+      {
+        // highest priority: the pack kernel and the NCCL kernels must get SMs while the interior sweep fills the GPU
+        int prio_lo = 0, prio_hi = 0; CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&c->st_comm, cudaStreamNonBlocking, prio_hi));
+        CK(cudaEventCreateWithFlags(&c->ev_pos, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_ghost, cudaEventDisableTiming));
+      }
+      const LJP lj = make_lj(eps, sig, rcut);
+      CK(cudaEventRecord(c->ev_pos, st));
+      CK(cudaStreamWaitEvent(c->st_comm, c->ev_pos, 0));
+      if ((rc = t_begin(c, XNB_T_GHOST_UPDATE, c->st_comm))) return rc;
+      if ((rc = xnb_ghost_update_r(c, c->st_comm))) return rc;
+      if ((rc = t_end(c, XNB_T_GHOST_UPDATE, c->st_comm))) return rc;
+      CK(cudaEventRecord(c->ev_ghost, c->st_comm));
+      if ((rc = t_begin(c, XNB_T_FORCE, st))) return rc;
+      if ((rc = launch_force<1, false>(c, false, lj, dt * 0.5, nullptr, nullptr, nullptr, nullptr, nullptr, st, c->d_scalars64.p, 1))) return rc;
+      CK(cudaStreamWaitEvent(st, c->ev_ghost, 0));
+      if ((rc = launch_force<1, false>(c, false, lj, dt * 0.5, nullptr, nullptr, nullptr, nullptr, nullptr, st, c->d_scalars64.p, 2))) return rc;
+      if ((rc = t_end(c, XNB_T_FORCE, st))) return rc;
+    }
+    else if (speculate)
+    {
+      if ((rc = t_begin(c, XNB_T_GHOST_UPDATE, st))) return rc;
+      if ((rc = xnb_ghost_update_r(c, stream))) return rc;
+      if ((rc = t_end(c, XNB_T_GHOST_UPDATE, st))) return rc;
+      if ((rc = launch_force<1, false>(c, false, make_lj(eps, sig, rcut), dt * 0.5, nullptr, nullptr, nullptr, nullptr, nullptr, st, c->d_scalars64.p))) return rc;
+    }
+    CK(cudaEventSynchronize(c->ev_flag));
+    const unsigned long long over = *h_flag;
     if (over > 0)
     {
+      if (speculate && c->timing && c->tpool[XNB_T_FORCE].used == force_scopes + 1) c->tpool[XNB_T_FORCE].used = force_scopes;   // the void launch is not a sweep
       if ((rc = move_and_update_full(c, stream))) return rc;
       rebuilds++;
+      if ((rc = xnb_force_and_second_half(c, eps, sig, rcut, dt * 0.5, stream))) return rc;
     }
-    else
+    else if (!speculate)
     {
-      if ((rc = t_begin(c, XNB_T_GHOST_UPDATE, (cudaStream_t)stream))) return rc;
+      if ((rc = t_begin(c, XNB_T_GHOST_UPDATE, st))) return rc;
       if ((rc = xnb_ghost_update_r(c, stream))) return rc;
-      if ((rc = t_end(c, XNB_T_GHOST_UPDATE, (cudaStream_t)stream))) return rc;
+      if ((rc = t_end(c, XNB_T_GHOST_UPDATE, st))) return rc;
+      if ((rc = xnb_force_and_second_half(c, eps, sig, rcut, dt * 0.5, stream))) return rc;
     }
-    if ((rc = xnb_force_and_second_half(c, eps, sig, rcut, dt * 0.5, stream))) return rc;
   }
   if (rebuilds_out) *rebuilds_out = rebuilds;
   return XNB_OK;

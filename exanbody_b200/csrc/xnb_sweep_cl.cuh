@@ -250,11 +250,16 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, LJP lj, double dth,
               const uint8_t* __restrict__ type, const double* __restrict__ mass,
               const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
               const uint2* __restrict__ groups, const uint2* __restrict__ rows,
-              double* __restrict__ ev_partials /* [gridDim.x][7] */, uint32_t* __restrict__ err)
+              double* __restrict__ ev_partials /* [gridDim.x][7] */, uint32_t* __restrict__ err,
+              const unsigned long long* __restrict__ skip_if_nonzero, const uint32_t* __restrict__ tile_list)
 {
+  // speculative launch (xnb_run_steps): the displacement counter says a rebuild is due -> this launch is void
+  if (skip_if_nonzero && *skip_if_nonzero) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_scan[32];
-  const ClTile T = cl_tile(g, tp, (int)blockIdx.x);
+  // tile_list: this launch sweeps a subset of the tiles (interior tiles while the halo is in flight, boundary tiles after)
+  const uint32_t tile = tile_list ? tile_list[blockIdx.x] : blockIdx.x;
+  const ClTile T = cl_tile(g, tp, (int)tile);
   const ClTables tb = cl_tables(smem_raw, tp);
   double2* XY = reinterpret_cast<double2*>(smem_raw + cl_tables_bytes(tp.nh_max, tp.tc_max));   // [cap]
   double* Z = reinterpret_cast<double*>(XY + tp.cap);                                             // [cap]
@@ -265,7 +270,7 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, LJP lj, double dth,
   const bool bad = ngroups > (uint32_t)tp.gmax || n_halo > (uint32_t)tp.cap;   // cannot happen after a successful compile
   if (bad && threadIdx.x == 0) atomicOr(err, DERR_TILE_CAPACITY);
 
-  const uint2* const gt = groups + (size_t)blockIdx.x * (size_t)tp.gmax;
+  const uint2* const gt = groups + (size_t)tile * (size_t)tp.gmax;
   if (!bad && threadIdx.x < ngroups * 32u)
   {
     // start pulling this warp's first list rows towards L2 while the positions are staged

@@ -101,6 +101,8 @@ typedef struct xnb_sweep_info
   int64_t smem_bytes;     /* staged positions of a tile's halo box                                     */
   int64_t rows;           /* 256-byte rows of the compiled lists (32 lanes x 4 candidates)             */
   int64_t candidates;     /* list entries of all swept particles (sum of neighbour counts)             */
+  int64_t interior_tiles; /* tiles whose halo box holds no ghost cell: swept while the halo exchange   */
+  int64_t boundary_tiles; /*   of xnb_run_steps is in flight (several ranks); the others wait for it   */
 } xnb_sweep_info;
 int xnb_get_sweep_info(const xnb_ctx*, xnb_sweep_info* out);
 /* per-cell particle count and start index into the flat arrays (the per-cell SoA views of CellParticles)        */

@@ -28,7 +28,14 @@ def main():
         "lj_12x8x8": dict(lj_reduced_kwargs(ncell_units=8, cell_units=2), bounds_max=tuple(((4.0 / 0.8442) ** (1 / 3.)) * n for n in (24, 16, 16)), grid_dims=(12, 8, 8)),
         "lj_voids": lj_reduced_kwargs(ncell_units=16, cell_units=2, n_spheres=6, sphere_rmin=3.0, sphere_rmax=6.0, drift_speed=1.5),
     }
+    # same lattice case again with small sweep tiles: every rank then has interior tiles, i.e. the halo exchange of
+    # xnb_run_steps runs on its own stream while they are swept (asserted below through xnb_get_sweep_info)
+    cases["lj_12x8x8_overlap"] = cases["lj_12x8x8"]
     for name, kw in cases.items():
+        if name.endswith("_overlap"):
+            os.environ["XNB_CL_TILE"] = "2,1,1"
+        else:
+            os.environ.pop("XNB_CL_TILE", None)
         inp = U.generate_input(kw)
         ctx = U.make_ctx(kw, rank=rank, nranks=world, device=local, particles=inp)
         uid = [ctx.nccl_unique_id().copy() if rank == 0 else None]
@@ -37,6 +44,9 @@ def main():
         eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
         ctx.first_iteration(eps, sig, rc)
         rb = ctx.run_steps(nsteps, dt, eps, sig, rc)
+        if name.endswith("_overlap"):
+            si = ctx.sweep_info()
+            assert si["compiled"] and si["interior_tiles"] > 0 and si["boundary_tiles"] > 0, si
         mine = ctx.get_particles(0, ctx.n_inner)
         everyone = [None] * world
         dist.all_gather_object(everyone, {k: mine[k] for k in ("id", "rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz")})
