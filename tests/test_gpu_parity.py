@@ -265,6 +265,63 @@ def test_trajectory_parity(case, nsteps):
     assert err < 1e-7, err                    # chaotic amplification of 1e-16 rounding over the run; single-step bar is 1e-10 above
 
 
+def test_speculative_fast_path_changes_nothing(monkeypatch):
+    """xnb_run_steps enqueues ghost_update_r + the sweep before the host has read the displacement count (the launches are void
+    when a rebuild is due): same rebuild steps and bit-identical state as the strictly sequential loop"""
+    kw = CASES["lj2k"]
+    eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
+    out = []
+    for seq in (False, True):
+        if seq:
+            monkeypatch.setenv("XNB_NO_SPECULATION", "1")
+        _, ctx = setup_pair(kw)
+        ctx.first_iteration(eps, sig, rc)
+        rb = [ctx.run_steps(1, dt, eps, sig, rc) for _ in range(30)]
+        out.append((rb, ctx.get_particles(0, ctx.n_inner)))
+    (rb_a, pa), (rb_b, pb) = out
+    assert rb_a == rb_b and sum(rb_a) > 0
+    for k in ("id", "rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
+        assert np.array_equal(pa[k], pb[k]), k
+
+
+def test_sweep_info():
+    kw = CASES["lj2k"]
+    _, ctx = setup_pair(kw)
+    assert not ctx.sweep_info()["compiled"]                 # no lists yet
+    ctx.first_iteration(kw["epsilon"], kw["sigma"], kw["rcut"])
+    si = ctx.sweep_info()
+    assert si["compiled"] and not si["ghost"]
+    assert si["blocks"] == si["interior_tiles"] + si["boundary_tiles"] and si["threads"] % 32 == 0
+    # list entries of the inner particles = stream words minus group counters, (code, count) headers and the offset tables
+    pairs = sum(len(v) for v in ctx_pairs(ctx))
+    assert si["candidates"] == pairs
+    assert si["rows"] * 128 >= si["candidates"]
+
+
+def ctx_pairs(ctx):
+    """per inner particle neighbour lists decoded from the GridChunkNeighbors streams (pure python reader)"""
+    gi = ctx.grid_info(); d, gl = gi["dims"], gi["ghost_layers"]
+    start, cnt = ctx.cells()
+    sz, data = ctx.streams()
+    off = np.concatenate([[0], np.cumsum(np.asarray(sz, np.int64))])
+    lists = []
+    for c in range(gi["n_cells"]):
+        i, j, k = c % d[0], (c // d[0]) % d[1], c // (d[0] * d[1])
+        if not (gl <= i < d[0] - gl and gl <= j < d[1] - gl and gl <= k < d[2] - gl) or cnt[c] == 0:
+            continue
+        s = data[off[c]:off[c] + sz[c]]
+        n = int(cnt[c])
+        table = s[:2 * (n + 1)].view(np.uint32)
+        body = s[2 * (n + 1):]
+        for p in range(n):
+            w = body[table[p] - 1:table[p + 1] - 1]
+            g, q, cand = int(w[0]), 1, []
+            for _ in range(g):
+                m = int(w[q + 1]); cand.extend(w[q + 2:q + 2 + m].tolist()); q += 2 + m
+            lists.append(cand)
+    return lists
+
+
 def test_reference_golden_file_through_the_cuda_path():
     """the reference's own regression deck, run end to end on the GPU: check_values_lj_Ni.dat within the deck's 1e-5"""
     from test_oracle_kat import compare_with_golden
