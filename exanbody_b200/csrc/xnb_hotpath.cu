@@ -948,8 +948,8 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
         c->cl.n_interior = (unsigned)inner.size(); c->cl.n_boundary = (unsigned)outer.size();
         inner.insert(inner.end(), outer.begin(), outer.end());
         CK(c->cl_tile_list.ensure(inner.size() + 16));
+        // (pageable source: the call returns once the data sits in the driver's staging buffer, `inner` may go out of scope)
         CK(cudaMemcpyAsync(c->cl_tile_list.p, inner.data(), inner.size() * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));      // `inner` is pageable host memory that goes out of scope
       }
       ok = true;
       break;
@@ -1044,9 +1044,15 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
       else    k_nbh_fused<false><<<blocks, nwarp * 32, smem, st>>>(g, tp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, s32);
       c->launches++; CK(cudaGetLastError());
       uint32_t hs[6]; unsigned long long tot2[2]; uint32_t e = 0;
-      rc = read_back(c, stats, 6, hs, st); if (rc) return rc;
-      rc = read_back(c, c->d_scalars64.p + 1, 2, tot2, st); if (rc) return rc;
-      rc = read_back(c, s32, 1, &e, st); if (rc) return rc;
+      {
+        // one host synchronisation for the three small results (statistics, totals, error word)
+        char* hp = static_cast<char*>(c->h_pinned);
+        CK(cudaMemcpyAsync(hp, stats, 6 * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hp + 32, c->d_scalars64.p + 1, 2 * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hp + 64, s32, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(hs, hp, 24); memcpy(tot2, hp + 32, 16); memcpy(&e, hp + 64, 4);
+      }
       bool again = false;
       if (e & DERR_TILE_CAPACITY)
       {
