@@ -29,6 +29,22 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert sorted(capi.SYMBOLS) == declared          # the ctypes binding covers the whole header
 
 
+def test_header_is_plain_c_and_structs_match_the_ctypes_mirror(tmp_path):
+    """include/xnb_hotpath.h compiles as C99 (no C++ or torch types in the boundary) and the structs of the ctypes binding have
+    the sizes and field offsets the C compiler gives them"""
+    import subprocess
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "xnb_hotpath.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(xnb_grid_info), sizeof(xnb_sweep_info), sizeof(xnb_lattice_cfg),'
+                   ' offsetof(xnb_sweep_info, tile), offsetof(xnb_sweep_info, candidates), offsetof(xnb_grid_info, block_end)); return 0; }\n')
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    want = [ctypes.sizeof(capi.XnbGridInfo), ctypes.sizeof(capi.XnbSweepInfo), ctypes.sizeof(capi.XnbLatticeCfg),
+            capi.XnbSweepInfo.tile.offset, capi.XnbSweepInfo.candidates.offset, capi.XnbGridInfo.block_end.offset]
+    assert got == want, (got, want)
+
+
 def test_every_entry_point_cites_the_reference():
     txt = open(os.path.join(ROOT, "include", "xnb_hotpath.h")).read()
     for op in ("move_particles_across_cells.h", "chunk_neighbors_execute.h", "lennard_jones.cu", "compute_cell_particle_pairs.h",
