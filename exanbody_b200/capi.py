@@ -18,7 +18,7 @@ SYMBOLS = [
     "xnb_set_type_mass", "xnb_set_sub_grid_density", "xnb_set_nccl_comm", "xnb_nccl_unique_id", "xnb_nccl_init_rank",
     "xnb_set_particles", "xnb_num_inner", "xnb_num_total", "xnb_get_particles", "xnb_upload_rv", "xnb_download_rvf",
     "xnb_get_grid_info", "xnb_get_sweep_info", "xnb_get_cells", "xnb_move_particles", "xnb_rebuild_amr", "xnb_backup_r", "xnb_ghost_comm_scheme",
-    "xnb_ghost_update_all", "xnb_ghost_update_r", "xnb_chunk_neighbors", "xnb_zero_particle_force", "xnb_lennard_jones_force",
+    "xnb_ghost_update_all", "xnb_ghost_update_r", "xnb_chunk_neighbors", "xnb_zero_particle_force", "xnb_set_pair_functor", "xnb_lennard_jones_force",
     "xnb_divide_force_by_mass", "xnb_push_f_v_r", "xnb_push_f_v", "xnb_particle_displ_over", "xnb_verlet_first_half",
     "xnb_read_displ_over", "xnb_force_and_second_half", "xnb_run_steps", "xnb_first_iteration", "xnb_energy_virial",
     "xnb_view_chunk_neighbors", "xnb_stream_pool_u16", "xnb_get_streams", "xnb_get_amr", "xnb_get_backup",
@@ -53,7 +53,8 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB
+    # XNB_HOTPATH_LIB: development knob (kernel experiments built beside the product library); default = the in-tree build
+    return os.environ.get("XNB_HOTPATH_LIB") or _build.LIB
 
 
 def load():
@@ -76,7 +77,7 @@ def load():
         "xnb_get_grid_info": (I, [P, C.POINTER(XnbGridInfo)]), "xnb_get_sweep_info": (I, [P, C.POINTER(XnbSweepInfo)]), "xnb_get_cells": (I, [P, P, P]),
         "xnb_move_particles": (I, [P, P]), "xnb_rebuild_amr": (I, [P, P]), "xnb_backup_r": (I, [P, P]), "xnb_ghost_comm_scheme": (I, [P, P]),
         "xnb_ghost_update_all": (I, [P, P]), "xnb_ghost_update_r": (I, [P, P]), "xnb_chunk_neighbors": (I, [P, P]),
-        "xnb_zero_particle_force": (I, [P, I, P]), "xnb_lennard_jones_force": (I, [P, D, D, D, I, P]), "xnb_divide_force_by_mass": (I, [P, P]),
+        "xnb_zero_particle_force": (I, [P, I, P]), "xnb_set_pair_functor": (I, [P, I]), "xnb_lennard_jones_force": (I, [P, D, D, D, I, P]), "xnb_divide_force_by_mass": (I, [P, P]),
         "xnb_push_f_v_r": (I, [P, D, D, P]), "xnb_push_f_v": (I, [P, D, D, P]), "xnb_particle_displ_over": (I, [P, P, P]),
         "xnb_verlet_first_half": (I, [P, D, P]), "xnb_read_displ_over": (I, [P, P, P]), "xnb_force_and_second_half": (I, [P, D, D, D, D, P]),
         "xnb_run_steps": (I, [P, I, D, D, D, D, P, P]), "xnb_first_iteration": (I, [P, D, D, D, P]),
@@ -211,6 +212,9 @@ class Context:
     def ghost_update_r(self, stream=None): self._ck(self.L.xnb_ghost_update_r(self.h, _p(stream)))
     def chunk_neighbors(self, stream=None): self._ck(self.L.xnb_chunk_neighbors(self.h, _p(stream)))
     def zero_particle_force(self, ghost=True, stream=None): self._ck(self.L.xnb_zero_particle_force(self.h, int(ghost), _p(stream)))
+    def set_pair_functor(self, functor):
+        """0 = restated LJ functor (default), 1 = the reference's literal LJ form through the generic buffer-less call"""
+        self._ck(self.L.xnb_set_pair_functor(self.h, int(functor)))
     def lennard_jones_force(self, epsilon, sigma, rcut, ghost=False, stream=None):
         self._ck(self.L.xnb_lennard_jones_force(self.h, epsilon, sigma, rcut, int(ghost), _p(stream)))
     def divide_force_by_mass(self, stream=None): self._ck(self.L.xnb_divide_force_by_mass(self.h, _p(stream)))

@@ -152,6 +152,7 @@ struct xnb_ctx
   ncclComm_t comm = nullptr; bool own_comm = false;
   // ---- counters
   int64_t launches = 0, rebuilds = 0;
+  int pair_functor = XNB_FUNCTOR_LJ;   // xnb_set_pair_functor
   // device-side timing without synchronisation: per category a pool of event pairs recorded on the launching stream and
   // summed at xnb_timing_read (categories XNB_T_* of the header)
   bool timing = false;
@@ -876,9 +877,9 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
     k.threads = std::max(k.threads, 64);
     k.var = k.threads <= 576 ? 0 : 1;
     const double capd = std::min(mx * k.nh, avg * k.nh * 1.08 + 64.0);
-    if (capd > 65535.0) continue;
+    if (capd > 8191.0) continue;
     k.cap = ((int)capd + 1) & ~1;
-    k.smem = (((size_t)(2 * k.nh + 2 * k.tc + 2) * 4 + 15) & ~(size_t)15) + (size_t)k.cap * 24;
+    k.smem = cl_sweep_smem_bytes(k.nh, k.tc, k.cap, k.threads / 32);
     if (k.smem + 1024 + 2048 > SM_BYTES) continue;
     const int by_smem = (int)(SM_BYTES / (k.smem + 1024 + 256));
     const int by_regs = 65536 / (k.threads * (k.var == 0 ? 56 : 64));
@@ -901,10 +902,10 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
     {
       // same shape as last time: start from the capacities that worked (no second compile pass per rebuild)
       tp.gmax = std::max(tp.gmax, c->cl.tp.gmax);
-      if (c->cl.tp.cap > tp.cap && (((size_t)(2 * tp.nh_max + 2 * tp.tc_max + 2) * 4 + 15) & ~(size_t)15) + (size_t)c->cl.tp.cap * 24 + 1024 + 2048 <= SM_BYTES) tp.cap = c->cl.tp.cap;
+      if (c->cl.tp.cap > tp.cap && cl_sweep_smem_bytes(tp.nh_max, tp.tc_max, c->cl.tp.cap, tp.gmax) + 1024 + 2048 <= SM_BYTES) tp.cap = c->cl.tp.cap;
     }
     const unsigned blocks = (unsigned)((int64_t)tp.tiles_i * tp.tiles_j * tp.tiles_k);
-    size_t smem = (((size_t)(2 * tp.nh_max + 2 * tp.tc_max + 2) * 4 + 15) & ~(size_t)15) + (size_t)tp.cap * 24;
+    size_t smem = cl_sweep_smem_bytes(tp.nh_max, tp.tc_max, tp.cap, tp.gmax);
     bool ok = false;
     for (int attempt = 0; attempt < 5; attempt++)
     {
@@ -919,12 +920,9 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
       uint32_t h[6]; int rc = read_back(c, counters, 6, h, st); if (rc) return rc;
       bool again = false;
       if ((int)h[1] > tp.gmax) { if (h[1] * 32u > 1024u) break; tp.gmax = (int)h[1]; again = true; }
-      if ((int)h[2] > tp.cap)
-      {
-        tp.cap = ((int)h[2] + 1) & ~1; smem = tbytes + (size_t)tp.cap * 24;
-        if (tp.cap > 65535 || smem + 1024 + 2048 > SM_BYTES) break;
-        again = true;
-      }
+      if ((int)h[2] > tp.cap) { tp.cap = ((int)h[2] + 1) & ~1; again = true; }
+      smem = cl_sweep_smem_bytes(tp.nh_max, tp.tc_max, tp.cap, tp.gmax);
+      if (tp.cap > 8191 || smem + 1024 + 2048 > SM_BYTES) break;
       if (!again && h[0] > c->cl_cap_rows) { c->cl_cap_rows = (uint32_t)((double)h[0] * 1.05) + 1024u; again = true; }
       if (again) continue;
       // every tile is swept in one pass: one warp per group of the fullest tile
@@ -933,6 +931,8 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
       c->cl.threads = std::max(32 * (int)std::max<uint32_t>(h[1], 1u), 64);
       if (env_int("XNB_CL_THREADS") > 0) c->cl.threads = std::min(env_int("XNB_CL_THREADS") & ~31, 1024);
       c->cl.var = c->cl.threads <= 576 ? 0 : 1;
+      if (getenv("XNB_CL_VAR")) { const int v = env_int("XNB_CL_VAR"); if ((v == 2 && c->cl.threads <= 288) || (v == 3 && c->cl.threads <= 576)) c->cl.var = v; }   // experiments: 2 = three blocks per SM (<= 72 registers), 3 = one block per SM
+      c->cl.smem = cl_sweep_smem_bytes(tp.nh_max, tp.tc_max, tp.cap, std::max(tp.gmax, c->cl.threads / 32));   // one ring of list rows per warp
       {
         // interior tiles: the halo box touches no ghost cell, so they can be swept while the halo exchange is in flight
         std::vector<uint32_t> inner, outer;
@@ -1114,7 +1114,7 @@ int xnb_zero_particle_force(xnb_ctx* c, int ghost, void* stream)
 }
 
 } // extern "C"
-static LJP make_lj(double eps, double sig, double rcut) { LJP p; p.eps24 = 24.0 * eps; p.sig2 = sig * sig; p.rcut2 = rcut * rcut; p.eps4 = 4.0 * eps; p.neg_eps48 = -48.0 * eps; return p; }
+static LJP make_lj(double eps, double sig, double rcut) { LJP p; p.eps24 = 24.0 * eps; p.sig2 = sig * sig; p.rcut2 = rcut * rcut; p.eps4 = 4.0 * eps; p.neg_eps48 = -48.0 * eps; p.eps = eps; p.sig = sig; return p; }
 
 // tile shape of the pair sweep: ti x tj cells per block, thread count and staging capacities from the cell occupancy
 struct TileCfg { TileP tp; int threads; size_t smem; unsigned blocks; };
@@ -1184,10 +1184,10 @@ static TileCfg make_tiles(const xnb_ctx* c, bool ghost)
   return t;
 }
 
-template <int MODE, bool EV>
 // part: 0 = every tile, 1 = interior tiles only, 2 = boundary tiles only (compiled lists; 1 and 2 are timed by the caller)
-static int launch_force(xnb_ctx* c, bool ghost, const LJP& lj, double dth, double* fxo, double* fyo, double* fzo, double** evp_out, unsigned* nblocks_out, cudaStream_t st,
-                        const unsigned long long* skip_if_nonzero = nullptr, int part = 0)
+template <class F, int MODE, bool EV>
+static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, double* fxo, double* fyo, double* fzo, double** evp_out, unsigned* nblocks_out, cudaStream_t st,
+                        const unsigned long long* skip_if_nonzero, int part)
 {
   ParticlesP A = c->P(c->cur);
   int rc;
@@ -1196,20 +1196,20 @@ static int launch_force(xnb_ctx* c, bool ghost, const LJP& lj, double dth, doubl
   {
     const xnb_ctx::ClCfg& k = c->cl;
     if (EV) { CK(c->ev_partials.ensure((size_t)k.blocks * 7 + 16)); if (evp_out) *evp_out = c->ev_partials.p; if (nblocks_out) *nblocks_out = k.blocks; }
-    static bool cl_attr_done[2][2][2] = {{{false, false}, {false, false}}, {{false, false}, {false, false}}};
+    static bool cl_attr_done[2][2][4] = {};
 #define XNB_CL_LAUNCH(VAR) do { \
       if (!cl_attr_done[MODE][EV ? 1 : 0][VAR]) { \
-        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (k_lj_sweep_cl<MODE, EV, VAR>))); \
-        CK(cudaFuncSetAttribute((k_lj_sweep_cl<MODE, EV, VAR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes)); \
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (k_lj_sweep_cl<F, MODE, EV, VAR>))); \
+        CK(cudaFuncSetAttribute((k_lj_sweep_cl<F, MODE, EV, VAR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes)); \
         cl_attr_done[MODE][EV ? 1 : 0][VAR] = true; } \
       if (part == 0 && (rc = t_begin(c, XNB_T_FORCE, st))) return rc; \
-      k_lj_sweep_cl<MODE, EV, VAR><<<nb, k.threads, k.smem, st>>>(c->g, k.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, \
+      k_lj_sweep_cl<F, MODE, EV, VAR><<<nb, k.threads, k.smem, st>>>(c->g, k.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, \
           fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, c->cl_groups.p, \
           reinterpret_cast<const uint2*>(c->cl_rows.p), EV ? c->ev_partials.p : nullptr, c->d_scalars32.p, skip_if_nonzero, tl); } while (0)
     const unsigned nb = part == 0 ? k.blocks : part == 1 ? k.n_interior : k.n_boundary;
     const uint32_t* tl = part == 0 ? nullptr : part == 1 ? c->cl_tile_list.p : c->cl_tile_list.p + k.n_interior;
     if (nb == 0) return XNB_OK;
-    if (k.var == 0) XNB_CL_LAUNCH(0); else XNB_CL_LAUNCH(1);
+    if (k.var == 0) XNB_CL_LAUNCH(0); else if (k.var == 1) XNB_CL_LAUNCH(1); else if (k.var == 2) XNB_CL_LAUNCH(2); else XNB_CL_LAUNCH(3);
 #undef XNB_CL_LAUNCH
     c->launches++; CK(cudaGetLastError());
     return part == 0 ? t_end(c, XNB_T_FORCE, st) : XNB_OK;
@@ -1220,19 +1220,38 @@ static int launch_force(xnb_ctx* c, bool ghost, const LJP& lj, double dth, doubl
   static bool attr_done[2][2] = {{false, false}, {false, false}};
   if (!attr_done[MODE][EV ? 1 : 0])
   {
-    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_lj_sweep<MODE, EV>));
-    CK(cudaFuncSetAttribute(k_lj_sweep<MODE, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_lj_sweep<F, MODE, EV>));
+    CK(cudaFuncSetAttribute(k_lj_sweep<F, MODE, EV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
     attr_done[MODE][EV ? 1 : 0] = true;
   }
   if ((rc = t_begin(c, XNB_T_FORCE, st))) return rc;
-  k_lj_sweep<MODE, EV><<<t.blocks, t.threads, t.smem, st>>>(c->g, t.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
+  k_lj_sweep<F, MODE, EV><<<t.blocks, t.threads, t.smem, st>>>(c->g, t.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
       fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p,
       c->stream_size.p, EV ? c->ev_partials.p : nullptr, skip_if_nonzero);
   c->launches++; CK(cudaGetLastError());
   return t_end(c, XNB_T_FORCE, st);
 }
 
+// the functor the sweeps are instantiated with: the restated LJ functor (four-candidate hook) or the literal reference form
+// through the generic buffer-less call (xnb_set_pair_functor)
+template <int MODE, bool EV>
+static int launch_force(xnb_ctx* c, bool ghost, const LJP& lj, double dth, double* fxo, double* fyo, double* fzo, double** evp_out, unsigned* nblocks_out, cudaStream_t st,
+                        const unsigned long long* skip_if_nonzero = nullptr, int part = 0)
+{
+  if (c->pair_functor == XNB_FUNCTOR_LJ_REFERENCE_FORM)
+    return launch_force_f<LennardJonesForceFunctorRef, MODE, EV>(c, ghost, LennardJonesForceFunctorRef{lj}, dth, fxo, fyo, fzo, evp_out, nblocks_out, st, skip_if_nonzero, part);
+  return launch_force_f<LennardJonesForceFunctor, MODE, EV>(c, ghost, LennardJonesForceFunctor{lj}, dth, fxo, fyo, fzo, evp_out, nblocks_out, st, skip_if_nonzero, part);
+}
+
 extern "C" {
+int xnb_set_pair_functor(xnb_ctx* c, int form)
+{
+  if (!c) return XNB_ERR_INVALID;
+  if (form != XNB_FUNCTOR_LJ && form != XNB_FUNCTOR_LJ_REFERENCE_FORM) return c->fail(XNB_ERR_INVALID, "set_pair_functor: unknown functor");
+  c->pair_functor = form;
+  return XNB_OK;
+}
+
 int xnb_lennard_jones_force(xnb_ctx* c, double eps, double sig, double rcut, int ghost, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;

@@ -14,6 +14,7 @@
 // the exact GridChunkNeighbors format.
 #pragma once
 #include "xnb_common.cuh"
+#include "xnb_pair_functor.cuh"
 #include <type_traits>
 
 namespace xnb {
@@ -760,7 +761,7 @@ constexpr int NBH_MAX_CHUNKS = 32;   // 32-particle chunks per cell (cells of up
 // when the lists are copied out -- half the shared memory per warp, twice the resident warps.  Requires max cell count
 // <= 127 and (2gap+1)^3 <= 128.  U8 = false: list areas hold the final u16 words.
 template <bool U8>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)   // two blocks per SM (shared memory allows no more): <= 128 registers, no spills in either form
 k_nbh_fused(GridP g, NbhTileP tp,
             const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
             const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
@@ -1200,7 +1201,7 @@ __global__ void k_max_u32(int n, const uint32_t* __restrict__ a, uint32_t* __res
 // divergent branch: every trip reads four words with one aligned LDS.64 and evaluates up to four candidates with
 // independent FP64 dependency chains.
 // ------------------------------------------------------------------------------------------------------------------
-struct LJP { double eps24; double sig2; double rcut2; double eps4; double neg_eps48; };
+// (LJP, the Lennard-Jones functors and the functor concept: xnb_pair_functor.cuh)
 
 struct TileP
 {
@@ -1213,20 +1214,14 @@ struct TileP
   int hx, hy, hz;    // nominal halo box dims
 };
 
-// 1/x for normal x > 0: hardware seed (MUFU.RCP64H, ~2^-20) + one cubically convergent step: y (1 + e + e^2), e = 1 - x y
-XNB_DEVINL double fast_rcp(double x)
-{
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double e = fma(-x, y, 1.0);
-  const double t = fma(e, e, e);
-  return fma(y, t, y);                      // relative error e^3 ~ 2^-60, + rounding
-}
-
 // asynchronous global -> shared copies (LDGSTS): issued back to back, completed by cp_async_wait_all()
 XNB_DEVINL void cp_async8(void* smem_dst, const void* gsrc)
 {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+XNB_DEVINL void cp_async8_sh(uint32_t smem_addr, const void* gsrc)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gsrc) : "memory");
 }
 XNB_DEVINL void cp_async16(void* smem_dst, const void* gsrc)
 {
@@ -1234,63 +1229,8 @@ XNB_DEVINL void cp_async16(void* smem_dst, const void* gsrc)
 }
 XNB_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-struct LJAcc { double ax, ay, az, e, wxx, wyy, wzz, wxy, wxz, wyz; };
-
-// the Lennard-Jones functor on one pair (global-memory fallback path)
-template <bool EV>
-XNB_DEVINL void lj_pair(const LJP& lj, double dx, double dy, double dz, double d2, LJAcc& a)
-{
-  const double inv = fast_rcp(d2);
-  const double s2 = lj.sig2 * inv;
-  const double s6 = s2 * s2 * s2;
-  const double de = fma(lj.neg_eps48, s6, lj.eps24) * (s6 * inv);
-  a.ax = fma(de, dx, a.ax); a.ay = fma(de, dy, a.ay); a.az = fma(de, dz, a.az);
-  if (EV)
-  {
-    a.e += 0.5 * lj.eps4 * (s6 * s6 - s6);
-    const double px = de * dx, py = de * dy, pz = de * dz;
-    a.wxx -= 0.5 * dx * px; a.wyy -= 0.5 * dy * py; a.wzz -= 0.5 * dz * pz;
-    a.wxy -= 0.5 * dx * py; a.wxz -= 0.5 * dx * pz; a.wyz -= 0.5 * dy * pz;
-  }
-}
-
 constexpr uint32_t SW_MARK = 0x8000u;      // staged stream word >= SW_MARK: "set base", not a candidate
 constexpr int SWEEP_MAX_THREADS = 384;
-
-// scheduling fence: everything that produces v0..v3 is placed before this point and everything that consumes them after
-// it, so the four candidates advance phase by phase (independent FP64 chains in flight) instead of one after the other
-XNB_DEVINL void fence4(double& v0, double& v1, double& v2, double& v3) { asm volatile("" : "+d"(v0), "+d"(v1), "+d"(v2), "+d"(v3)); }
-
-// four candidates at once.  ok[u] = false (not a candidate, or outside the cut) contributes exactly zero; its d2 may be
-// anything (the coefficient is replaced, not multiplied).
-template <bool EV>
-XNB_DEVINL void lj_pairs4(const LJP& lj, const double (&dx)[4], const double (&dy)[4], const double (&dz)[4], double (&d2)[4], const bool (&ok)[4], LJAcc& a)
-{
-  double inv[4], s6[4], de[4];
-  fence4(d2[0], d2[1], d2[2], d2[3]);
-#pragma unroll
-  for (int u = 0; u < 4; u++) inv[u] = fast_rcp(d2[u]);
-  fence4(inv[0], inv[1], inv[2], inv[3]);
-#pragma unroll
-  for (int u = 0; u < 4; u++) { const double s2 = lj.sig2 * inv[u]; s6[u] = s2 * s2 * s2; }
-  fence4(s6[0], s6[1], s6[2], s6[3]);
-#pragma unroll
-  for (int u = 0; u < 4; u++) { de[u] = fma(lj.neg_eps48, s6[u], lj.eps24) * (s6[u] * inv[u]); if (!ok[u]) de[u] = 0.0; }
-  fence4(de[0], de[1], de[2], de[3]);
-#pragma unroll
-  for (int u = 0; u < 4; u++) { a.ax = fma(de[u], dx[u], a.ax); a.ay = fma(de[u], dy[u], a.ay); a.az = fma(de[u], dz[u], a.az); }
-  if (EV)
-  {
-#pragma unroll
-    for (int u = 0; u < 4; u++)
-    {
-      if (ok[u]) a.e += 0.5 * lj.eps4 * (s6[u] * s6[u] - s6[u]);
-      const double px = de[u] * dx[u], py = de[u] * dy[u], pz = de[u] * dz[u];
-      a.wxx -= 0.5 * dx[u] * px; a.wyy -= 0.5 * dy[u] * py; a.wzz -= 0.5 * dz[u] * pz;
-      a.wxy -= 0.5 * dx[u] * py; a.wxz -= 0.5 * dx[u] * pz; a.wyz -= 0.5 * dy[u] * pz;
-    }
-  }
-}
 
 // decode one aligned chunk of four staged stream words: a word >= SW_MARK sets the base, anything else is a candidate
 // (if `live`); FIRST: the chunk's first `skip` words belong to the previous list
@@ -1318,13 +1258,12 @@ XNB_DEVINL void sweep_load(const double2* __restrict__ XY, const double* __restr
 
 // one trip of the sweep: evaluate the four candidates whose positions were loaded last trip (pxy, pz, okc) while the
 // positions of the next trip (decoded from chunk cn) are fetched into (nxy, nz, okn)
-template <bool EV>
-XNB_DEVINL void sweep_trip(const LJP& lj, unsigned long long rc2b, const double2* __restrict__ XY, const double* __restrict__ Z, double xa, double ya, double za,
+template <bool EV, class F>
+XNB_DEVINL void sweep_trip(const F& lj, unsigned long long rc2b, const double2* __restrict__ XY, const double* __restrict__ Z, double xa, double ya, double za,
                            const uint2 cn, bool live_next, uint32_t& sb,
-                           const double2 (&pxy)[4], const double (&pz)[4], const bool (&okc)[4],
-                           double2 (&nxy)[4], double (&nz)[4], bool (&okn)[4], LJAcc& acc)
+                           const double2 (&pxy)[4], const double (&pz)[4], const bool (&okc)[4], const uint32_t (&jc)[4],
+                           double2 (&nxy)[4], double (&nz)[4], bool (&okn)[4], uint32_t (&jn)[4], PairAcc& acc)
 {
-  uint32_t jn[4];
   sweep_decode<false>(cn, 0u, live_next, sb, jn, okn);
   sweep_load(XY, Z, jn, okn, nxy, nz);
   double dx[4], dy[4], dz[4], d2[4]; bool ok[4];
@@ -1338,12 +1277,12 @@ XNB_DEVINL void sweep_trip(const LJP& lj, unsigned long long rc2b, const double2
   // (d2 >= +0, never NaN for finite positions) -- one predicate, off the FP64 pipe
 #pragma unroll
   for (int u = 0; u < 4; u++) ok[u] = okc[u] && (unsigned long long)(__double_as_longlong(d2[u]) - 1ll) < rc2b;
-  lj_pairs4<EV>(lj, dx, dy, dz, d2, ok, acc);
+  pair_apply4<EV>(lj, dx, dy, dz, d2, ok, jc, acc);
 }
 
-template <int MODE, bool EV>
+template <class F, int MODE, bool EV>
 __global__ void __launch_bounds__(SWEEP_MAX_THREADS)
-k_lj_sweep(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth,
+k_lj_sweep(GridP g, TileP tp, int n_inner, int n_total, F lj, double dth,
            const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
            double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
            double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
@@ -1483,9 +1422,9 @@ k_lj_sweep(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth,
     __syncthreads();
   }
 
-  LJAcc acc;
+  PairAcc acc;
   acc.e = acc.wxx = acc.wyy = acc.wzz = acc.wxy = acc.wxz = acc.wyz = 0.;
-  const unsigned long long rc2b = (unsigned long long)__double_as_longlong(lj.rcut2);   // bits(d2) - 1 < bits(rcut2) <=> d2 in (0, rcut2]
+  const unsigned long long rc2b = (unsigned long long)__double_as_longlong(lj.rcut2());   // bits(d2) - 1 < bits(rcut2) <=> d2 in (0, rcut2]
 
   for (int t = (int)threadIdx.x; t < n_tile; t += blockDim.x)
   {
@@ -1510,15 +1449,15 @@ k_lj_sweep(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth,
       uint32_t sb = 0;
       // software pipeline: chunk t+2 is being read and the positions of trip t+1 are in flight while trip t is evaluated;
       // two trips per iteration so that the two register sets (A, B) swap roles without copies
-      uint32_t jA[4]; bool okA[4], okB[4]; double2 xyA[4], xyB[4]; double zA[4], zB[4];
+      uint32_t jA[4], jB[4]; bool okA[4], okB[4]; double2 xyA[4], xyB[4]; double zA[4], zB[4];
       sweep_decode<true>(S64[k >> 2], kb & 3u, k < ke, sb, jA, okA);
       sweep_load(XY, Z, jA, okA, xyA, zA);
       uint2 c1 = S64[(k >> 2) + 1];
       for (; k < ke; k += 8u)
       {
         const uint2 c2 = S64[(k >> 2) + 2], c3 = S64[(k >> 2) + 3];
-        sweep_trip<EV>(lj, rc2b, XY, Z, xa, ya, za, c1, k + 4u < ke, sb, xyA, zA, okA, xyB, zB, okB, acc);
-        sweep_trip<EV>(lj, rc2b, XY, Z, xa, ya, za, c2, k + 8u < ke, sb, xyB, zB, okB, xyA, zA, okA, acc);
+        sweep_trip<EV>(lj, rc2b, XY, Z, xa, ya, za, c1, k + 4u < ke, sb, xyA, zA, okA, jA, xyB, zB, okB, jB, acc);
+        sweep_trip<EV>(lj, rc2b, XY, Z, xa, ya, za, c2, k + 8u < ke, sb, xyB, zB, okB, jB, xyA, zA, okA, jA, acc);
         c1 = c3;
       }
     }
@@ -1541,7 +1480,7 @@ k_lj_sweep(GridP g, TileP tp, int n_inner, int n_total, LJP lj, double dth,
           const uint32_t j = sbg + *s++;
           const double dx = __dadd_rn(rx[j], -xa), dy = __dadd_rn(ry[j], -ya), dz = __dadd_rn(rz[j], -za);
           const double d2 = norm2_exact(dx, dy, dz);
-          if ((unsigned long long)(__double_as_longlong(d2) - 1ll) < rc2b) lj_pair<EV>(lj, dx, dy, dz, d2, acc);
+          if ((unsigned long long)(__double_as_longlong(d2) - 1ll) < rc2b) pair_apply1<EV>(lj, dx, dy, dz, d2, j, acc);
         }
       }
     }

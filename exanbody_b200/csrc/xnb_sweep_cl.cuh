@@ -6,7 +6,8 @@
 //
 //   * the swept cells are cut into tiles of ti x tj x tk cells; one block sweeps one tile and stages the positions of
 //     the tile's halo box in shared memory.  A candidate is stored as the u16 index of the neighbour in that staged
-//     array, so the sweep needs no (cell code, count) headers and no cell-base lookups at all;
+//     array (times 8: the byte offset of its z, half the byte offset of its {x,y} pair), so the sweep needs no (cell
+//     code, count) headers, no cell-base lookups and one shift-add per address;
 //   * the particles of a tile are numbered 0..n_tile-1 (tile cell after tile cell); 32 consecutive particles form a
 //     GROUP = one warp of the sweep.  The lists of a group are stored row by row, row k holding words 4k..4k+3 of all 32
 //     lists (8 bytes per lane, 256 bytes per row): every warp load is one fully coalesced 256-byte line, streamed once;
@@ -26,7 +27,7 @@ struct ClTileP
   int gap;                              // neighbour cell layers
   int lo[3], hi[3];                     // swept cell range [lo,hi)
   int tiles_i, tiles_j, tiles_k;
-  int cap;                              // staging capacity in particles (<= 65535: u16 staged indices)
+  int cap;                              // staging capacity in particles (<= 8191: a u16 list word is 8 x the staged index)
   int nh_max, tc_max;                   // nominal halo cells / tile cells: sizes of the shared-memory tables
   int gmax;                             // group-table entries per tile
 };
@@ -54,6 +55,11 @@ XNB_DEVINL ClTile cl_tile(const GridP& g, const ClTileP& tp, int b)
 struct ClTables { uint32_t *hstart, *hfirst, *tstart, *thalo; };
 
 XNB_DEVINL size_t cl_tables_bytes(int nh_max, int tc_max) { return (((size_t)(2 * nh_max + 2 * tc_max + 2) * 4 + 15) & ~(size_t)15); }
+// dynamic shared memory of the sweep: tables | {x,y}[cap] | z[cap]
+__host__ __device__ inline size_t cl_sweep_smem_bytes(int nh_max, int tc_max, int cap, int /*warps*/)
+{
+  return (((size_t)(2 * nh_max + 2 * tc_max + 2) * 4 + 15) & ~(size_t)15) + (size_t)cap * 24;
+}
 
 XNB_DEVINL ClTables cl_tables(unsigned char* smem, const ClTileP& tp)
 {
@@ -198,7 +204,7 @@ k_cl_compile(GridP g, ClTileP tp, const uint32_t* __restrict__ cell_start, const
           left--;
           if (cnt)
           {
-            buf = (buf >> 16) | ((unsigned long long)(base + w) << 48);
+            buf = (buf >> 16) | ((unsigned long long)((base + w) << 3) << 48);     // a list word = 8 x staged index (<= 65528)
             cnt--; r++;
             if ((r & 3u) == 0u) col[(size_t)((r >> 2) - 1u) * 32u] = make_uint2((uint32_t)buf, (uint32_t)(buf >> 32));
           }
@@ -216,7 +222,7 @@ k_cl_compile(GridP g, ClTileP tp, const uint32_t* __restrict__ cell_start, const
     // pads: the particle's own staged index, up to the group's trip count
     while (r < 4u * trips)
     {
-      buf = (buf >> 16) | ((unsigned long long)self << 48);
+      buf = (buf >> 16) | ((unsigned long long)(self << 3) << 48);
       r++;
       if ((r & 3u) == 0u) col[(size_t)((r >> 2) - 1u) * 32u] = make_uint2((uint32_t)buf, (uint32_t)(buf >> 32));
     }
@@ -240,10 +246,20 @@ XNB_DEVINL uint2 ld_stream8(const uint2* p)
   asm volatile("ld.global.cs.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
 }
-
-template <int MODE, bool EV, int VAR>
-__global__ void __launch_bounds__(VAR == 0 ? 576 : 1024, VAR == 0 ? 2 : 1)
-k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, LJP lj, double dth,
+XNB_DEVINL void lds_f64x2(uint32_t a, double& x, double& y) { asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a)); }
+XNB_DEVINL void lds_f64(uint32_t a, double& x) { asm("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a)); }
+// 0 < d2 <= rc2 as ONE predicate: d2 != 0 read off the high word feeds the FP64 compare (DSETP.LE.AND); written in C the two
+// tests become two predicates and twice the selects
+XNB_DEVINL bool in_cut(double d2, double rc2)
+{
+  uint32_t r;
+  asm("{ .reg .pred p, q; .reg .b32 l, h; mov.b64 {l, h}, %1; setp.ne.s32 q, h, 0; setp.le.and.f64 p, %1, %2, q; selp.u32 %0, 1, 0, p; }"
+      : "=r"(r) : "d"(d2), "d"(rc2));
+  return r != 0u;
+}
+template <class F, int MODE, bool EV, int VAR>
+__global__ void __launch_bounds__(VAR == 0 ? 576 : VAR == 1 ? 1024 : VAR == 2 ? 288 : 576, VAR == 0 ? 2 : VAR == 1 ? 1 : VAR == 2 ? 3 : 1)
+k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
               const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
               double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
               double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
@@ -293,9 +309,10 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, LJP lj, double dth,
   }
   __syncthreads();
 
-  LJAcc acc;
+  PairAcc acc;
   acc.e = acc.wxx = acc.wyy = acc.wzz = acc.wxy = acc.wxz = acc.wyz = 0.;
-  const unsigned long long rc2b = (unsigned long long)__double_as_longlong(lj.rcut2);   // bits(d2) - 1 < bits(rcut2) <=> d2 in (0, rcut2]
+  const double rc2 = lj.rcut2();
+  const uint32_t xyb = (uint32_t)__cvta_generic_to_shared(XY), zb = (uint32_t)__cvta_generic_to_shared(Z);
 
   if (!bad)
   for (uint32_t t = threadIdx.x; t < ngroups * 32u; t += blockDim.x)
@@ -312,9 +329,14 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, LJP lj, double dth,
     if (MODE == 1 && active) { m = mass[type[i]]; if (dth != 0.0) { ux = vx[i]; uy = vy[i]; uz = vz[i]; } }
     acc.ax = acc.ay = acc.az = 0.;
     const uint2 ge = gt[t >> 5];
+#if XNB_CL_ABL == 14      // EXPERIMENT (wrong forces): no pair loop at all -- prologue and epilogue only
+    const uint32_t trips = ge.y >> 10;
+#else
     const uint32_t trips = ge.y;
+#endif
     const uint2* R = rows + ((size_t)ge.x * 32u + (uint32_t)lane);
-    const uint32_t selfw = self | (self << 16);
+    // register prefetch two rows ahead; the rows are streamed from HBM exactly once, so they are pulled into L2 well ahead of that
+    const uint32_t selfw = (self << 3) | (self << 19);
     uint2 w0 = make_uint2(selfw, selfw), w1 = w0;
     if (trips > 0u) w0 = ld_stream8(R);
     if (trips > 1u) w1 = ld_stream8(R + 32);
@@ -322,25 +344,46 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, LJP lj, double dth,
     {
       uint2 w2 = w0;
       if (k + 2u < trips) w2 = ld_stream8(R + (size_t)(k + 2u) * 32u);
-      // the rows are streamed from HBM exactly once: pull them into L2 well ahead of the register prefetch
       if (k + CL_PREFETCH_ROWS < trips) asm volatile("prefetch.global.L2 [%0];" :: "l"(R + (size_t)(k + CL_PREFETCH_ROWS) * 32u));
-      const uint32_t j[4] = {w0.x & 0xffffu, w0.x >> 16, w0.y & 0xffffu, w0.y >> 16};
+      // a list word is 8 x the staged index of the candidate: byte offset of its z, half the byte offset of its {x,y}
+#if XNB_CL_ABL == 11 || XNB_CL_ABL == 15      // EXPERIMENT (wrong forces): conflict-free gather addresses that do not depend on the list words
+      const uint32_t kk = 4u * k;
+      const uint32_t j[4] = {8u * (lane + 32u * (kk & 63u)), 8u * (lane + 32u * ((kk + 1u) & 63u)), 8u * (lane + 32u * ((kk + 2u) & 63u)), 8u * (lane + 32u * ((kk + 3u) & 63u))};
+#elif XNB_CL_ABL == 12    // EXPERIMENT (wrong forces): conflict-free gather addresses that depend on the list words
+      const uint32_t kk = 4u * k;
+      const uint32_t j[4] = {8u * (((w0.x >> 15) & 1u) + lane + 32u * (kk & 63u)), 8u * ((w0.x >> 31) + lane + 32u * ((kk + 1u) & 63u)),
+                             8u * (((w0.y >> 15) & 1u) + lane + 32u * ((kk + 2u) & 63u)), 8u * ((w0.y >> 31) + lane + 32u * ((kk + 3u) & 63u))};
+#else
+      // (PRMT for the low halves: written as `& 0xffff` the compiler folds the mask into the scaled address and needs two more instructions)
+      const uint32_t j[4] = {__byte_perm(w0.x, 0u, 0x4410), w0.x >> 16, __byte_perm(w0.y, 0u, 0x4410), w0.y >> 16};
+#endif
       double dx[4], dy[4], dz[4], d2[4]; bool ok[4];
 #pragma unroll
       for (int u = 0; u < 4; u++)
       {
-        const double2 p = XY[j[u]]; const double pz = Z[j[u]];
-        dx[u] = __dadd_rn(p.x, -xa); dy[u] = __dadd_rn(p.y, -ya); dz[u] = __dadd_rn(pz, -za);
+        double px, py, pz;
+        lds_f64x2(xyb + j[u] + j[u], px, py); lds_f64(zb + j[u], pz);
+        dx[u] = __dadd_rn(px, -xa); dy[u] = __dadd_rn(py, -ya); dz[u] = __dadd_rn(pz, -za);
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) d2[u] = norm2_exact(dx[u], dy[u], dz[u]);
-      // accept iff d2 > 0 && d2 <= rcut2 (impl_default.h:186): one unsigned compare, off the FP64 pipe
+      // accept iff d2 > 0 && d2 <= rcut2 (impl_default.h:186).  d2 > 0 is read off the high word (a sum of squares is never
+      // -0; below 2^-1022 it counts as zero: DESIGN.md 4), so the test costs one integer and one FP64 compare
 #pragma unroll
-      for (int u = 0; u < 4; u++) ok[u] = (unsigned long long)(__double_as_longlong(d2[u]) - 1ll) < rc2b;
-      lj_pairs4<EV>(lj, dx, dy, dz, d2, ok, acc);
+      for (int u = 0; u < 4; u++) ok[u] = in_cut(d2[u], rc2);
+#if XNB_CL_ABL == 13 || XNB_CL_ABL == 15      // EXPERIMENT (wrong forces): real gathers, functor skipped
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (ok[u]) { acc.ax += d2[u]; acc.ay += dx[u]; acc.az += dz[u] + dy[u]; }
+#else
+      pair_apply4<EV>(lj, dx, dy, dz, d2, ok, j, acc);
+#endif
       w0 = w1; w1 = w2;
     }
+#if XNB_CL_ABL >= 10     // EXPERIMENTS: results are never stored (all variants then see the same -- force-free -- dynamics)
+    if (active && acc.ax == 1234.56789)
+#else
     if (active)
+#endif
     {
       double ax = acc.ax, ay = acc.ay, az = acc.az;
       if (MODE == 0)

@@ -127,6 +127,15 @@ int xnb_ghost_update_r(xnb_ctx*, void* stream);
 int xnb_chunk_neighbors(xnb_ctx*, void* stream);
 /* op `zero_particle_force` : src/compute/zero_particle_force.cu:15-53                                           */
 int xnb_zero_particle_force(xnb_ctx*, int ghost, void* stream);
+/* The functor the pair sweeps are instantiated with (the functor concept: compute_pair_traits.h:24-74, restated in
+   exanbody_b200/csrc/xnb_pair_functor.cuh).  XNB_FUNCTOR_LJ (default): LennardJonesForceFunctor restated with one
+   reciprocal and a four-candidate hook.  XNB_FUNCTOR_LJ_REFERENCE_FORM: lj_compute_energy + the buffer-less operator()
+   exactly as written in lennard_jones.cu:46-56,106-124 (sqrt, two divisions), driven through the generic buffer-less
+   call, one candidate at a time -- the route any further functor of the concept takes.  Same pair sets; forces agree
+   to rounding (<= 3e-13 relative).                                                                                */
+#define XNB_FUNCTOR_LJ 0
+#define XNB_FUNCTOR_LJ_REFERENCE_FORM 1
+int xnb_set_pair_functor(xnb_ctx*, int functor);
 /* op `lennard_jones_force` : contribs/md/lennard_jones/lennard_jones.cu:171-215 through
    compute_cell_particle_pairs (src/compute/include/exanb/compute/compute_cell_particle_pairs.h:122-189).
    ACCUMULATES into fx,fy,fz like the reference (call xnb_zero_particle_force first).                            */

@@ -156,15 +156,20 @@ def test_stream_decoding_independent_of_oracle(case):
     assert np.array_equal(pairs, o.pairs())
 
 
+@pytest.mark.parametrize("functor", ["lj", "lj_reference_form"])
 @pytest.mark.parametrize("sweep", ["compiled", "streams"])
 @pytest.mark.parametrize("case", list(CASES))
-def test_force_parity(case, sweep, monkeypatch):
+def test_force_parity(case, sweep, functor, monkeypatch):
     """sweep = compiled: k_lj_sweep_cl over the compiled lists (the default); streams: k_lj_sweep reading the
-    GridChunkNeighbors streams directly (the fallback when no tile shape fits)"""
+    GridChunkNeighbors streams directly (the fallback when no tile shape fits).
+    functor = lj: the restated Lennard-Jones functor (four-candidate hook); lj_reference_form: lj_compute_energy + the
+    buffer-less operator() as written in lennard_jones.cu:46-56,106-124, driven through the generic buffer-less call of
+    the functor concept (xnb_pair_functor.cuh) -- the route any other functor would take"""
     if sweep == "streams":
         monkeypatch.setenv("XNB_SWEEP_STREAMS", "1")
     kw = CASES[case]
     o, ctx = setup_pair(kw)
+    ctx.set_pair_functor(1 if functor == "lj_reference_form" else 0)
     o.first_iteration()
     ctx.first_iteration(kw["epsilon"], kw["sigma"], kw["rcut"])
     po = U.by_id(o.particles(), o.inner_mask())
