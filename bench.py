@@ -162,7 +162,8 @@ def ncu_traffic(kernel):
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel)
+            e = json.load(open(p)).get(kernel)
+            return float(e["dram_bytes_per_launch"]) if e else None      # bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)
         except Exception:
             return None
     return None
@@ -317,7 +318,8 @@ def b200_arm(args):
     kname = "k_lj_sweep_cl" if si["compiled"] else "k_lj_sweep"
     n_list = si["candidates"] / max(n_atoms_local, 1) if si["compiled"] else None        # list entries per atom (78 on the perfect lattice)
     roofline = {"bound": "hbm", "kernel": kname + " (pair sweep + fused second half kick)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(kname), "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(kname), "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/ncu_traffic.json)",
+                "algorithmic_bytes_per_launch": force_bytes * n_atoms_local, "peak_source": peak_src,
                 "algorithmic_bytes_per_atom": force_bytes, "stream_bytes_per_atom": S, "kernel_ms": fk_ms,
                 "whole_step": {"algorithmic_bytes_per_atom": step_bytes, "achieved": step_bytes * value / world / 1e9, "frac": step_bytes * value / world / 1e9 / peak},
                 "sweep": {"compiled_lists": si["compiled"], "tile_cells": si["tile"], "threads": si["threads"], "blocks": si["blocks"], "smem_bytes": si["smem_bytes"],
@@ -331,11 +333,15 @@ def b200_arm(args):
     ptr = {k2: v.data_ptr() for k2, v in hb.items()}
     ctx.download_rvf(ptr["rx"], ptr["ry"], ptr["rz"], ptr["vx"], ptr["vy"], ptr["vz"], ptr["fx"], ptr["fy"], ptr["fz"], hid.data_ptr(), sh)
 
+    e2e_rebuilds = [0]
+
     def e2e_step():
-        ctx.upload_rv(ptr["rx"], ptr["ry"], ptr["rz"], ptr["vx"], ptr["vy"], ptr["vz"], sh)
-        ctx.run_steps(1, dt, eps, sig, rc, sh)
-        assert ctx.n_inner == n or world > 1
-        ctx.download_rvf(ptr["rx"], ptr["ry"], ptr["rz"], ptr["vx"], ptr["vy"], ptr["vz"], ptr["fx"], ptr["fy"], ptr["fz"], hid.data_ptr(), sh)
+        # particles live in host memory (as the reference's Grid does): one C-ABI call uploads r,v, runs the step and returns r,v,f
+        # (positions travel back while the sweep runs; ids only when the step rebuilt, i.e. when the particle order changed)
+        e2e_rebuilds[0] += ctx.step_host(dt, eps, sig, rc, in_r=(ptr["rx"], ptr["ry"], ptr["rz"]), in_v=(ptr["vx"], ptr["vy"], ptr["vz"]),
+                                         out_r=(ptr["rx"], ptr["ry"], ptr["rz"]), out_v=(ptr["vx"], ptr["vy"], ptr["vz"]),
+                                         out_f=(ptr["fx"], ptr["fy"], ptr["fz"]), out_id=hid.data_ptr(), stream=sh)
+        assert ctx.n_inner == n
 
     e2e = None
     if world == 1 and not args.no_e2e:       # with several ranks atoms migrate between ranks, so host buffers change size: e2e is defined at N=1
@@ -343,15 +349,17 @@ def b200_arm(args):
         for _ in range(3):
             e2e_step()
         barrier()
+        e2e_rebuilds[0] = 0
         e0.record(stream)
         for _ in range(e2e_steps):
             e2e_step()
         e1.record(stream)
         barrier()
         ems = e0.elapsed_time(e1)
-        e2e = {"value": n_atoms * e2e_steps / (ems * 1e-3), "unit": "atom-timesteps/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 80 * n,
-               "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
-               "what": "per step: xnb_upload_rv (r,v from pinned host) + xnb_run_steps(1) + xnb_download_rvf (r,v,f,id to pinned host)"}
+        e2e = {"value": n_atoms * e2e_steps / (ems * 1e-3), "unit": "atom-timesteps/s", "h2d_bytes_per_step": 48 * n,
+               "d2h_bytes_per_step": 72 * n + 8 * n * e2e_rebuilds[0] / e2e_steps, "steps": e2e_steps, "rebuilds": e2e_rebuilds[0], "ms_per_step": ems / e2e_steps,
+               "what": "per step one xnb_step_host call: r,v from pinned host memory -> one step -> r,v,f back (ids too on the steps that rebuild: "
+                       "the particle order changes only there); d2h_bytes_per_step is the mean over the timed steps"}
 
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ----------------------------------------------------------------
     cpu = None

@@ -146,6 +146,9 @@ struct xnb_ctx
   DBuf<double> ev_partials;
   DBuf<int> d_blocks;
   DBuf<uint32_t> mig_rank, mig_pos, mig_base;
+  // ---- xnb_step_host: positions (and ids) go back to the host on their own stream as soon as they are final
+  struct HostOut { bool active = false, issued = false, id_always = false, id_copied = false; double* r[3] = {nullptr, nullptr, nullptr}; uint64_t* id = nullptr; };
+  HostOut hout; cudaStream_t st_d2h = nullptr; cudaEvent_t ev_d2h_go = nullptr, ev_d2h_done = nullptr;
   void* h_pinned = nullptr;               // 4 KB pinned scratch for small read-backs ([1024..1032): displacement count of xnb_run_steps)
   cudaEvent_t ev_flag = nullptr;
   // ---- NCCL
@@ -415,6 +418,9 @@ void xnb_destroy(xnb_ctx* c)
   if (c->ev_pos) cudaEventDestroy(c->ev_pos);
   if (c->ev_ghost) cudaEventDestroy(c->ev_ghost);
   if (c->st_comm) cudaStreamDestroy(c->st_comm);
+  if (c->ev_d2h_go) cudaEventDestroy(c->ev_d2h_go);
+  if (c->ev_d2h_done) cudaEventDestroy(c->ev_d2h_done);
+  if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
   if (c->comm && c->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   delete c;
 }
@@ -1332,6 +1338,21 @@ int xnb_force_and_second_half(xnb_ctx* c, double eps, double sig, double rcut, d
 }
 
 } // extern "C"
+// xnb_step_host: the inner positions (and the particle order) of this step are final once `after` has happened on its stream;
+// their device-to-host copies start then, on a second stream, and overlap whatever the step still has to compute
+static int host_out_positions(xnb_ctx* c, cudaEvent_t after, bool rebuilt)
+{
+  xnb_ctx::HostOut& h = c->hout;
+  if (!h.active || h.issued) return XNB_OK;
+  h.issued = true;
+  CK(cudaStreamWaitEvent(c->st_d2h, after, 0));
+  const size_t n = (size_t)c->n_inner;
+  for (int f = 0; f < 3; f++) if (h.r[f] && n) CK(cudaMemcpyAsync(h.r[f], c->f64[c->cur][f].p, n * 8, cudaMemcpyDeviceToHost, c->st_d2h));
+  h.id_copied = h.id && (rebuilt || h.id_always);
+  if (h.id_copied && n) CK(cudaMemcpyAsync(h.id, c->idb[c->cur].p, n * 8, cudaMemcpyDeviceToHost, c->st_d2h));
+  return XNB_OK;
+}
+
 // move_particles + parallel_update_particles (update-particles.msp:47-68)
 static int move_and_update_full(xnb_ctx* c, void* stream)
 {
@@ -1342,6 +1363,7 @@ static int move_and_update_full(xnb_ctx* c, void* stream)
   if ((rc = xnb_rebuild_amr(c, stream))) return rc;
   if ((rc = xnb_backup_r(c, stream))) return rc;
   if ((rc = t_end(c, XNB_T_BIN, st))) return rc;
+  if (c->hout.active && !c->hout.issued) { CK(cudaEventRecord(c->ev_d2h_go, st)); if ((rc = host_out_positions(c, c->ev_d2h_go, true))) return rc; }
   if ((rc = t_begin(c, XNB_T_GHOST_SCHEME, st))) return rc;
   if ((rc = xnb_ghost_comm_scheme(c, stream))) return rc;
   if ((rc = xnb_ghost_update_all(c, stream))) return rc;
@@ -1422,7 +1444,8 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
       rebuilds++;
       if ((rc = xnb_force_and_second_half(c, eps, sig, rcut, dt * 0.5, stream))) return rc;
     }
-    else if (!speculate)
+    else if ((rc = host_out_positions(c, c->ev_flag, false))) return rc;     // no rebuild: positions are final since the first half
+    if (over == 0 && !speculate)
     {
       if ((rc = t_begin(c, XNB_T_GHOST_UPDATE, st))) return rc;
       if ((rc = xnb_ghost_update_r(c, stream))) return rc;
@@ -1431,6 +1454,51 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
     }
   }
   if (rebuilds_out) *rebuilds_out = rebuilds;
+  return XNB_OK;
+}
+
+int xnb_step_host(xnb_ctx* c, double dt, double eps, double sig, double rcut,
+                  const double* const in_r[3], const double* const in_v[3],
+                  double* const out_r[3], double* const out_v[3], double* const out_f[3], uint64_t* out_id, int id_always,
+                  void* stream, int* rebuilt_out)
+{
+  if (!c) return XNB_ERR_INVALID;
+  if (c->nranks != 1) return c->fail(XNB_ERR_INVALID, "xnb_step_host: host-resident stepping is defined for a single sub-domain (particles migrate between ranks otherwise)");
+  if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "no neighbour list (run xnb_first_iteration)");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!c->st_d2h)
+  {
+    CK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_d2h_go, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_d2h_done, cudaEventDisableTiming));
+  }
+  const size_t n = (size_t)c->n_inner;
+  for (int f = 0; f < 3; f++)
+  {
+    if (in_r && in_r[f] && n) CK(cudaMemcpyAsync(c->f64[c->cur][f].p, in_r[f], n * 8, cudaMemcpyHostToDevice, st));
+    if (in_v && in_v[f] && n) CK(cudaMemcpyAsync(c->f64[c->cur][3 + f].p, in_v[f], n * 8, cudaMemcpyHostToDevice, st));
+  }
+  xnb_ctx::HostOut& h = c->hout;
+  h = xnb_ctx::HostOut();
+  h.active = true; h.id_always = id_always != 0; h.id = out_id;
+  for (int f = 0; f < 3; f++) h.r[f] = out_r ? out_r[f] : nullptr;
+  int rebuilds = 0;
+  int rc = xnb_run_steps(c, 1, dt, eps, sig, rcut, stream, &rebuilds);
+  const bool issued = h.issued;
+  h.active = false;
+  if (rc) { cudaStreamSynchronize(c->st_d2h); return rc; }
+  if (!issued) return c->fail(XNB_ERR_INVALID, "xnb_step_host: internal error (positions never became final)");
+  if ((size_t)c->n_inner != n) { cudaStreamSynchronize(c->st_d2h); return c->fail(XNB_ERR_INVALID, "xnb_step_host: the number of particles changed (a particle left a non-periodic domain)"); }
+  // v and f are final after the sweep's epilogue
+  for (int f = 0; f < 3; f++)
+  {
+    if (out_v && out_v[f] && n) CK(cudaMemcpyAsync(out_v[f], c->f64[c->cur][3 + f].p, n * 8, cudaMemcpyDeviceToHost, st));
+    if (out_f && out_f[f] && n) CK(cudaMemcpyAsync(out_f[f], c->f64[c->cur][6 + f].p, n * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaEventRecord(c->ev_d2h_done, c->st_d2h));
+  CK(cudaStreamWaitEvent(st, c->ev_d2h_done, 0));
+  CK(cudaStreamSynchronize(st));
+  if (rebuilt_out) *rebuilt_out = rebuilds;
   return XNB_OK;
 }
 

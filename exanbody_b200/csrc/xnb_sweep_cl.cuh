@@ -335,16 +335,18 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
     const uint32_t trips = ge.y;
 #endif
     const uint2* R = rows + ((size_t)ge.x * 32u + (uint32_t)lane);
-    // register prefetch two rows ahead; the rows are streamed from HBM exactly once, so they are pulled into L2 well ahead of that
+    // register prefetch ONE row ahead, issued at the very top of a trip and pinned there by a warp barrier.  (Written as a
+    // two-rows-ahead rotation, ptxas sank the load to the bottom of the loop body; the six scoreboards of a warp are all needed by
+    // the eight position gathers of the body, so the loop head then waited for that load every trip: 15 % of all stall samples,
+    // profiles/r1m_sweep_cl.md.)  The rows are streamed from HBM exactly once, so they are pulled into L2 well ahead of that.
     const uint32_t selfw = (self << 3) | (self << 19);
     uint2 w0 = make_uint2(selfw, selfw), w1 = w0;
     if (trips > 0u) w0 = ld_stream8(R);
-    if (trips > 1u) w1 = ld_stream8(R + 32);
     for (uint32_t k = 0; k < trips; k++)
     {
-      uint2 w2 = w0;
-      if (k + 2u < trips) w2 = ld_stream8(R + (size_t)(k + 2u) * 32u);
+      if (k + 1u < trips) w1 = ld_stream8(R + (size_t)(k + 1u) * 32u);
       if (k + CL_PREFETCH_ROWS < trips) asm volatile("prefetch.global.L2 [%0];" :: "l"(R + (size_t)(k + CL_PREFETCH_ROWS) * 32u));
+      __syncwarp();
       // a list word is 8 x the staged index of the candidate: byte offset of its z, half the byte offset of its {x,y}
 #if XNB_CL_ABL == 11 || XNB_CL_ABL == 15      // EXPERIMENT (wrong forces): conflict-free gather addresses that do not depend on the list words
       const uint32_t kk = 4u * k;
@@ -377,7 +379,7 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
 #else
       pair_apply4<EV>(lj, dx, dy, dz, d2, ok, j, acc);
 #endif
-      w0 = w1; w1 = w2;
+      w0 = w1;
     }
 #if XNB_CL_ABL >= 10     // EXPERIMENTS: results are never stored (all variants then see the same -- force-free -- dynamics)
     if (active && acc.ax == 1234.56789)

@@ -160,6 +160,17 @@ int xnb_force_and_second_half(xnb_ctx*, double epsilon, double sigma, double rcu
 /* whole `numerical_scheme` loop (numerical-scheme.msp:21-25 + check_and_update_particles): nsteps iterations.
    Synchronises once per step to read the rebuild trigger (the reference does an MPI_Allreduce there).           */
 int xnb_run_steps(xnb_ctx*, int nsteps, double dt, double epsilon, double sigma, double rcut, void* stream, int* rebuilds_out);
+/* one iteration of the same loop for a caller whose particles live in HOST memory, as the reference's Grid does
+   (core/grid.h:57-688, host / managed allocations): uploads r,v of the inner particles (current device order; NULL
+   = keep the device copy), runs one step exactly as xnb_run_steps(1) does, and returns r,v,f (NULL = not wanted).
+   Positions go back on a second stream as soon as they are final (after the first half, or after binning when
+   the step rebuilds), overlapping the pair sweep; v and f follow the sweep.  out_id is written when the step
+   rebuilt (the particle order changed: *rebuilt_out = 1) or when id_always != 0.  Pinned host buffers make the
+   copies asynchronous.  Synchronises `stream` before returning.  Single sub-domain only (nranks == 1).          */
+int xnb_step_host(xnb_ctx*, double dt, double epsilon, double sigma, double rcut,
+                  const double* const in_r[3], const double* const in_v[3],
+                  double* const out_r[3], double* const out_v[3], double* const out_f[3], uint64_t* out_id, int id_always,
+                  void* stream, int* rebuilt_out);
 /* init_particles + first force (update-particles.msp:55-60, compute-loop.msp:1-7)                               */
 int xnb_first_iteration(xnb_ctx*, double epsilon, double sigma, double rcut, void* stream);
 

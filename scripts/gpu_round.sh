@@ -13,3 +13,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lj_sweep -s 4 -c 2 -f -o gpurun_out/${TAG}_force \
    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_force.log 2>&1
 ls -la gpurun_out | tail -20
+( time timeout 600 python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/${TAG}_bench_ref.log 2>&1
+tail -1 gpurun_out/${TAG}_bench_ref.log | cut -c1-600

@@ -289,6 +289,51 @@ def test_speculative_fast_path_changes_nothing(monkeypatch):
         assert np.array_equal(pa[k], pb[k]), k
 
 
+@pytest.mark.parametrize("sequential", [False, True])
+def test_step_host_equals_run_steps(sequential, monkeypatch):
+    """xnb_step_host (particles resident in host memory, positions copied back while the sweep runs) = upload + xnb_run_steps(1)
+    + download, bit for bit, on steps with and without a rebuild; ids are rewritten exactly when the step rebuilt"""
+    import torch
+    if sequential:
+        monkeypatch.setenv("XNB_NO_SPECULATION", "1")
+    kw = CASES["lj2k"]
+    eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
+    _, ca = setup_pair(kw)
+    _, cb = setup_pair(kw)
+    ca.first_iteration(eps, sig, rc); cb.first_iteration(eps, sig, rc)
+    n = ca.n_inner
+    names = ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz")
+    hb = {k: torch.zeros(n, dtype=torch.float64).pin_memory() for k in names}
+    hid = torch.zeros(n, dtype=torch.int64).pin_memory()
+    p0 = cb.get_particles(0, n)
+    for k in names:
+        hb[k].numpy()[:] = p0[k]
+    hid.numpy()[:] = p0["id"].astype(np.int64)
+    P = {k: v.data_ptr() for k, v in hb.items()}
+    total = 0
+    for it in range(30):
+        rb_a = ca.run_steps(1, dt, eps, sig, rc)
+        id_before = hid.numpy().copy()
+        rb_b = cb.step_host(dt, eps, sig, rc, in_r=(P["rx"], P["ry"], P["rz"]), in_v=(P["vx"], P["vy"], P["vz"]),
+                            out_r=(P["rx"], P["ry"], P["rz"]), out_v=(P["vx"], P["vy"], P["vz"]), out_f=(P["fx"], P["fy"], P["fz"]),
+                            out_id=hid.data_ptr())
+        assert rb_a == rb_b, it
+        total += rb_b
+        pa = ca.get_particles(0, n)
+        for k in names:
+            assert np.array_equal(pa[k], hb[k].numpy()), (it, k)
+        assert np.array_equal(pa["id"].astype(np.int64), hid.numpy()), it
+        if not rb_b:
+            assert np.array_equal(id_before, hid.numpy())
+    assert total > 0
+    # only part of the outputs wanted, inputs kept on the device
+    rb_a = ca.run_steps(1, dt, eps, sig, rc)
+    hb["fx"].zero_(); hid.zero_()
+    rb_b = cb.step_host(dt, eps, sig, rc, out_f=(P["fx"], None, None), out_id=hid.data_ptr(), id_always=True)
+    pa = ca.get_particles(0, n)
+    assert rb_a == rb_b and np.array_equal(pa["fx"], hb["fx"].numpy()) and np.array_equal(pa["id"].astype(np.int64), hid.numpy())
+
+
 def test_sweep_info():
     kw = CASES["lj2k"]
     _, ctx = setup_pair(kw)
