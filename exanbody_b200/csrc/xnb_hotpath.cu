@@ -130,6 +130,7 @@ struct xnb_ctx
   DBuf<uint32_t> nb_len, nb_cnt, nb_off, stream_size, stream_size_padded, cell_stream_bytes;
   DBuf<unsigned long long> stream_off;
   DBuf<uint16_t> pool; DBuf<uint16_t*> cell_stream;
+  bool nbh_half_symmetric = false, nbh_skip_ghosts = false;       // ChunkNeighborsConfig (xnb_set_chunk_neighbors_config)
   int nbh_cap_l = 0; uint32_t nbh_slot_words = 0; bool nbh_full_cap = false;   // capacities of the tiled build (grow on demand)
   // ---- compiled lists of the pair sweep (xnb_sweep_cl.cuh): derived from the streams after every rebuild
   struct ClCfg { bool valid = false, ghost = false; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; int64_t candidates = 0;
@@ -994,7 +995,8 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
   NbhOut out{c->nb_len.p, c->nb_cnt.p, c->nb_off.p, c->cell_stream.p};
 
   // ---- tiled single-kernel form (k_nbh_fused) when a tile fits shared memory, else the per-particle two-pass kernels
-  bool tiled = n > 0 && !env_flag("XNB_NBH_UNTILED");
+  // (lists filtered by ChunkNeighborsConfig::half_symmetric / skip_ghosts are built by the two-pass kernels)
+  bool tiled = n > 0 && !env_flag("XNB_NBH_UNTILED") && !c->nbh_half_symmetric && !c->nbh_skip_ghosts;
   if (tiled)
   {
     CK(cudaMemsetAsync(s32 + 5, 0, 4, st));
@@ -1082,7 +1084,7 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
     if (tiled) return c->fail(XNB_ERR_CAPACITY, "chunk_neighbors: tiled build did not converge");
   }
   // ---- per-particle two-pass form (count -> sizes -> scan -> fill)
-  if (n) LAUNCH((k_nbh_build<false>), nblk(n, 128), 128, st, g, (int)n, gap, md2, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
+  if (n) LAUNCH((k_nbh_build<false>), nblk(n, 128), 128, st, g, (int)n, gap, md2, (int)c->nbh_half_symmetric, (int)c->nbh_skip_ghosts, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
   CK(cudaMemsetAsync(s32 + 3, 0, 16, st)); CK(cudaMemsetAsync(s32 + 109, 0, 8, st)); CK(cudaMemsetAsync(c->d_scalars64.p + 2, 0, 8, st));
   LAUNCH(k_nbh_cell_sizes, nblk((int64_t)g.n_cells * 32, 128), 128, st, g, g.n_cells, c->cell_start.p, c->cell_count.p, c->nb_len.p, c->nb_cnt.p, c->nb_off.p,
          c->stream_size.p, c->stream_size_padded.p, s32 + 3, s32 + 5, s32 + 6, s32 + 109, c->d_scalars64.p + 2, s32);
@@ -1099,7 +1101,7 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
   // realloc_stream_pool (chunk_neighbors.h:70-96): grow with the reference's 5% head-room (update-particles.msp:20)
   CK(c->pool.ensure((size_t)tot + 64, 0, 1.05));
   LAUNCH(k_nbh_pointers, nblk(g.n_cells, 256), 256, st, g.n_cells, c->pool.p, c->stream_off.p, c->stream_size.p, c->cell_stream.p, c->cell_stream_bytes.p);
-  if (n) LAUNCH((k_nbh_build<true>), nblk(n, 128), 128, st, g, (int)n, gap, md2, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
+  if (n) LAUNCH((k_nbh_build<true>), nblk(n, 128), 128, st, g, (int)n, gap, md2, (int)c->nbh_half_symmetric, (int)c->nbh_skip_ghosts, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
   c->have_nbh = true;
   if ((rc = cl_prepare(c, false, st))) return rc;
   if ((rc = t_end(c, XNB_T_NBH, st))) return rc;
@@ -1264,6 +1266,70 @@ int xnb_lennard_jones_force(xnb_ctx* c, double eps, double sig, double rcut, int
   if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "lennard_jones_force: no neighbour list (run xnb_chunk_neighbors)");
   c->rcut_max = std::max(c->rcut_max, rcut);    // lennard_jones.cu:193
   return launch_force<0, false>(c, ghost != 0, make_lj(eps, sig, rcut), 0.0, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int xnb_set_chunk_neighbors_config(xnb_ctx* c, int half_symmetric, int skip_ghosts)
+{
+  if (!c) return XNB_ERR_INVALID;
+  const bool h = half_symmetric != 0, s = skip_ghosts != 0;
+  if (h != c->nbh_half_symmetric || s != c->nbh_skip_ghosts) { c->have_nbh = false; c->cl.valid = false; }    // lists of the other kind are void
+  c->nbh_half_symmetric = h; c->nbh_skip_ghosts = s;
+  return XNB_OK;
+}
+
+int xnb_lennard_jones_force_symmetric(xnb_ctx* c, double eps, double sig, double rcut, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "no neighbour list (run xnb_chunk_neighbors)");
+  if (!c->nbh_half_symmetric) return c->fail(XNB_ERR_INVALID, "the symmetric sweep needs half_symmetric lists (xnb_set_chunk_neighbors_config)");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  ParticlesP A = c->P(c->cur);
+  int rc;
+  if ((rc = t_begin(c, XNB_T_FORCE, st))) return rc;
+  const LJP lj = make_lj(eps, sig, rcut);
+  if (c->n_inner)
+  {
+    if (c->pair_functor == XNB_FUNCTOR_LJ_REFERENCE_FORM)
+      LAUNCH((k_pair_sweep_sym<LennardJonesForceFunctorRef>), nblk(c->n_inner, 128), 128, st, c->g, (int)c->n_inner, LennardJonesForceFunctorRef{lj}, A.rx, A.ry, A.rz, A.fx, A.fy, A.fz,
+             c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p);
+    else
+      LAUNCH((k_pair_sweep_sym<LennardJonesForceFunctor>), nblk(c->n_inner, 128), 128, st, c->g, (int)c->n_inner, LennardJonesForceFunctor{lj}, A.rx, A.ry, A.rz, A.fx, A.fy, A.fz,
+             c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p);
+  }
+  return t_end(c, XNB_T_FORCE, st);
+}
+
+int xnb_update_force_from_ghost(xnb_ctx* c, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->n_send == 0 && c->n_ghost == 0) return XNB_OK;
+  const size_t ns = (size_t)c->n_send;
+  const int self_first = (int)c->h_send_base[(size_t)c->rank], self_end = (int)c->h_send_base[(size_t)c->rank + 1];
+  const uint32_t self_dst = (uint32_t)(c->n_inner + c->h_recv_base[(size_t)c->rank]);
+  int rc;
+  if ((rc = t_begin(c, XNB_T_GHOST_UPDATE, st))) return rc;
+  if (c->nranks > 1)
+  {
+    // the forward exchange run backwards: every rank returns the forces of the ghosts it holds to the rank that sent them
+    if (!c->comm) return c->fail(XNB_ERR_NCCL, "nranks > 1 needs an NCCL communicator");
+    CK(c->stage.ensure(ns * 3 + 16, 0, 1.2));
+    NK(g_nccl.GroupStart());
+    for (int p = 0; p < c->nranks; p++)
+    {
+      if (p == c->rank) continue;
+      const size_t s0 = c->h_send_base[(size_t)p], sn = c->h_send_base[(size_t)p + 1] - s0;
+      const size_t r0 = c->h_recv_base[(size_t)p], rn = c->h_recv_base[(size_t)p + 1] - r0;
+      if (rn) for (int f = 0; f < 3; f++) NK(g_nccl.Send(c->f64[c->cur][6 + f].p + (size_t)c->n_inner + r0, rn, nccl_float64, p, c->comm, st));
+      if (sn) for (int f = 0; f < 3; f++) NK(g_nccl.Recv(c->stage.p + (size_t)f * ns + s0, sn, nccl_float64, p, c->comm, st));
+    }
+    NK(g_nccl.GroupEnd());
+  }
+  ParticlesP A = c->P(c->cur);
+  if (ns) LAUNCH(k_ghost_unpack_add, nblk((int64_t)ns, 256), 256, st, (int)ns, c->send_src.p, self_first, self_end, self_dst, c->stage.p, A.fx, A.fy, A.fz);
+  return t_end(c, XNB_T_GHOST_UPDATE, st);
 }
 
 int xnb_divide_force_by_mass(xnb_ctx* c, void* stream)

@@ -541,7 +541,7 @@ struct NbhOut
 
 template <bool FILL>
 __global__ void __launch_bounds__(128)
-k_nbh_build(GridP g, int n_total, int gap, double max_dist2,
+k_nbh_build(GridP g, int n_total, int gap, double max_dist2, int half_symmetric, int skip_ghosts,
             const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
             const uint32_t* __restrict__ atom_cell, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
             NbhOut out, uint32_t* __restrict__ err)
@@ -573,7 +573,11 @@ k_nbh_build(GridP g, int n_total, int gap, double max_dist2,
       for (int bi = i0; bi <= i1; bi++)
       {
         const int cb = ijk_to_index(g.dims, bi, bj, bk);
-        const uint32_t nb = cell_count[cb];
+        uint32_t nb = cell_count[cb];
+        // NeighborFilterHalfSymGhost (neighbor_filter_func.h:36-52): half_symmetric keeps b "before" a (cell_b < cell_a, or the
+        // same cell and p_b < p_a); skip_ghosts drops every b of a ghost cell
+        if (half_symmetric) { if ((uint32_t)cb > ca) continue; if ((uint32_t)cb == ca) nb = (uint32_t)i - cell_start[ca]; }
+        if (skip_ghosts && (bi < g.gl || bi >= g.dims[0] - g.gl || bj < g.gl || bj >= g.dims[1] - g.gl || bk < g.gl || bk >= g.dims[2] - g.gl)) continue;
         if (nb == 0) continue;
         const uint32_t sb = cell_start[cb];
         uint32_t cnt = 0;

@@ -435,4 +435,74 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// k_pair_sweep_sym: Newton-3 pair sweep over half_symmetric GridChunkNeighbors lists --
+// compute_cell_particle_pairs<Symmetric = true> (impl_default.h:143-239) with ComputePairOptionalLocks<true>
+// (compute_pair_optional_args.h:152-161): each listed pair is evaluated once, f_a += de*dr and f_b -= de*dr, b may be a
+// ghost (update_force_from_ghost returns that part to its owner).  Where the reference serialises the concurrent updates
+// of a cell's particles with per-cell spin locks, this kernel uses FP64 atomic adds (RED.ADD.F64): the sums are the same
+// up to the order of the additions.  One thread per inner particle, reading the reference-format stream directly.
+// Forces must have been zeroed (zero_particle_force{ghost: true}).
+// ------------------------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128)
+k_pair_sweep_sym(GridP g, int n_inner, F func, const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                 double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+                 const uint32_t* __restrict__ atom_cell, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+                 const uint16_t* const* __restrict__ cell_stream)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inner) return;
+  const uint32_t ca = atom_cell[i];
+  const uint32_t na = cell_count[ca], pa = (uint32_t)i - cell_start[ca];
+  const uint16_t* cs = cell_stream[ca];
+  const uint32_t off0 = reinterpret_cast<const uint32_t*>(cs)[pa];
+  const uint16_t* lst = cs + 2u * (na + 1u) + off0;          // first word behind the group counter (offsets are biased by the number of tables = 1)
+  uint32_t ngrp = (uint32_t)lst[-1];
+  const double xa = rx[i], ya = ry[i], za = rz[i];
+  const double rc2 = func.rcut2();
+  double ax = 0., ay = 0., az = 0.;
+  const int dxy = g.dims[0] * g.dims[1];
+  bool stop = false;
+  for (; ngrp > 0u && !stop; ngrp--)
+  {
+    const uint32_t code = *lst++; uint32_t n = *lst++;
+    // chunk_neighbors.h:137-162: 5-bit fields of the code minus 16 = cell of b relative to the cell of a
+    const int cb = (int)ca + ((int)(code >> 10) - 16) * dxy + ((int)((code >> 5) & 31u) - 16) * g.dims[0] + ((int)(code & 31u) - 16);
+    const uint32_t sb = cell_start[cb];
+    for (; n > 0u; n--)
+    {
+      const uint32_t pb = *lst++;
+      if ((uint32_t)cb > ca || ((uint32_t)cb == ca && pb > pa)) { stop = true; break; }        // impl_default.h:181
+      const uint32_t j = sb + pb;
+      const double dx = __dadd_rn(rx[j], -xa), dy = __dadd_rn(ry[j], -ya), dz = __dadd_rn(rz[j], -za);
+      const double d2 = norm2_exact(dx, dy, dz);
+      if (d2 > 0.0 && d2 <= rc2)
+      {
+        double px = 0., py = 0., pz = 0.;
+        func(make_double3(dx, dy, dz), d2, px, py, pz, PairNbh{j}, 1.0);
+        ax += px; ay += py; az += pz;
+        atomicAdd(fx + j, -px); atomicAdd(fy + j, -py); atomicAdd(fz + j, -pz);
+      }
+    }
+  }
+  atomicAdd(fx + i, ax); atomicAdd(fy + i, ay); atomicAdd(fz + i, az);
+}
+
+// update_force_from_ghost (UpdateFromGhosts<fx,fy,fz,UpdateValueAdd>, mpi/update_force_from_ghost.cu:44): unpack side.  Send-list
+// entry q created one ghost of particle send_src[q]; that ghost's force (received in `stage`, or read in place for the periodic
+// self images) is added to the particle.  A particle can have several images, hence the atomic adds.
+__global__ void k_ghost_unpack_add(int n_send, const uint32_t* __restrict__ send_src, int self_first, int self_end, uint32_t self_dst,
+                                   const double* __restrict__ stage /* planes of n_send doubles: fx fy fz */,
+                                   double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_send) return;
+  const uint32_t s = send_src[q];
+  double x, y, z;
+  if (q >= self_first && q < self_end) { const uint32_t d = self_dst + (uint32_t)(q - self_first); x = fx[d]; y = fy[d]; z = fz[d]; }
+  else { const size_t n = (size_t)n_send; x = stage[q]; y = stage[n + q]; z = stage[2 * n + q]; }
+  atomicAdd(fx + s, x); atomicAdd(fy + s, y); atomicAdd(fz + s, z);
+}
+
 } // namespace xnb

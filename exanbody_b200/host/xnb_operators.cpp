@@ -336,12 +336,14 @@ struct BuildChunkNeighbors : OperatorNode   // particle_neighbors/chunk_neighbor
   void yaml_initialize(const Params& p) override
   {
     if (p.has("config.chunk_size") && (unsigned)p.quantity("config.chunk_size") != 1u) fatal_error("chunk_neighbors: chunk_size is frozen at 1 (chunk_neighbors_config.h:49,74)");
-    if (p.has("config.half_symmetric") && p.boolean("config.half_symmetric")) fatal_error("chunk_neighbors: half_symmetric lists are not on the LJ hot path (SURVEY 8f)");
+    if (p.has("config.half_symmetric")) config->half_symmetric = p.boolean("config.half_symmetric");      // chunk_neighbors_config.h:72
+    if (p.has("config.skip_ghosts")) config->skip_ghosts = p.boolean("config.skip_ghosts");
     if (p.has("config.build_particle_offset") && !p.boolean("config.build_particle_offset")) fatal_error("chunk_neighbors: build_particle_offset: false is not supported");
   }
   void execute() override
   {
     config->chunk_size = 1;
+    ck(grid->ctx, xnb_set_chunk_neighbors_config(grid->ctx, config->half_symmetric ? 1 : 0, config->skip_ghosts ? 1 : 0), "chunk_neighbors config");
     ck(grid->ctx, xnb_chunk_neighbors(grid->ctx, stream), "chunk_neighbors");
     GridChunkNeighbors& n = *chunk_neighbors; n.ctx = grid->ctx;
     ck(grid->ctx, xnb_view_chunk_neighbors(grid->ctx, &n.cell_stream, &n.cell_stream_size, &n.max_neighbors), "chunk_neighbors view");
@@ -354,6 +356,9 @@ struct ZeroParticleForce : OperatorNode     // compute/zero_particle_force.cu:32
   void yaml_initialize(const Params& p) override { XNB_PARAM_BOOL(p, ghost); }
   void execute() override { ck(grid->ctx, xnb_zero_particle_force(grid->ctx, *ghost ? 1 : 0, stream), "zero_particle_force"); }
 };
+// SYMMETRIC = true is an extension registered as `lennard_jones_force_symmetric` (same slots): the Newton-3 sweep over
+// half_symmetric lists, to be followed by update_force_from_ghost
+template <bool SYMMETRIC>
 struct LennardJonesForce : OperatorNode     // contribs/md/lennard_jones/lennard_jones.cu:171-215
 {
   ADD_SLOT(LennardJonesParms, config, INPUT, REQUIRED, DocString{"Lennard-Jones potential parameters"});
@@ -375,8 +380,14 @@ struct LennardJonesForce : OperatorNode     // contribs/md/lennard_jones/lennard
   {
     *rcut_max = std::max(*rcut, *rcut_max);
     if (grid->number_of_cells() == 0) return;
-    ck(grid->ctx, xnb_lennard_jones_force(grid->ctx, config->epsilon, config->sigma, *rcut, *ghost ? 1 : 0, stream), "lennard_jones_force");
+    if (SYMMETRIC) ck(grid->ctx, xnb_lennard_jones_force_symmetric(grid->ctx, config->epsilon, config->sigma, *rcut, stream), "lennard_jones_force (symmetric)");
+    else ck(grid->ctx, xnb_lennard_jones_force(grid->ctx, config->epsilon, config->sigma, *rcut, *ghost ? 1 : 0, stream), "lennard_jones_force");
   }
+};
+struct UpdateForceFromGhost : OperatorNode  // mpi/update_force_from_ghost.cu:44 (UpdateFromGhosts<fx,fy,fz, UpdateValueAdd>)
+{
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT);
+  void execute() override { ck(grid->ctx, xnb_update_force_from_ghost(grid->ctx, stream), "update_force_from_ghost"); }
 };
 struct DivideForceByTypeScalar : OperatorNode   // compute/vec3_typescalar_op.cu:71-122 (`divide_force_by_type_scalar: mass`)
 {
@@ -497,8 +508,9 @@ void register_hot_path_operators()
   f->register_factory("chunk_neighbors", make_simple_operator<BuildChunkNeighbors>());
   f->register_factory("resize_particle_locks", make_simple_operator<Nop>());     // ComputePairOptionalLocks<false>: LJ takes no locks
   f->register_factory("zero_particle_force", make_simple_operator<ZeroParticleForce>());
-  f->register_factory("lennard_jones_force", make_simple_operator<LennardJonesForce>());
-  f->register_factory("update_force_from_ghost", make_simple_operator<Nop>());   // value-wise a no-op for the full (non symmetric) list
+  f->register_factory("lennard_jones_force", make_simple_operator<LennardJonesForce<false>>());
+  f->register_factory("lennard_jones_force_symmetric", make_simple_operator<LennardJonesForce<true>>());
+  f->register_factory("update_force_from_ghost", make_simple_operator<UpdateForceFromGhost>());   // adds zeros after a full-list sweep (ghost forces are 0 then)
   f->register_factory("divide_force_by_type_scalar", make_simple_operator<DivideForceByTypeScalar>());
   f->register_factory("push_f_v_r", make_simple_operator<PushFVR>());
   f->register_factory("push_f_v", make_simple_operator<PushFV>());

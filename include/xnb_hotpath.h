@@ -140,6 +140,21 @@ int xnb_set_pair_functor(xnb_ctx*, int functor);
    compute_cell_particle_pairs (src/compute/include/exanb/compute/compute_cell_particle_pairs.h:122-189).
    ACCUMULATES into fx,fy,fz like the reference (call xnb_zero_particle_force first).                            */
 int xnb_lennard_jones_force(xnb_ctx*, double epsilon, double sigma, double rcut, int ghost, void* stream);
+/* ---- Newton-3 path ---------------------------------------------------------------------- */
+/* ChunkNeighborsConfig::half_symmetric / skip_ghosts of the chunk_neighbors operator (chunk_neighbors_config.h:35-36),
+   i.e. NeighborFilterHalfSymGhost (neighbor_filter_func.h:36-52): half_symmetric keeps b only if cell_b < cell_a or
+   (same cell and p_b < p_a); skip_ghosts drops neighbours that live in ghost cells.  Takes effect at the next
+   xnb_chunk_neighbors; the lists stay in the GridChunkNeighbors format (bit-identical to the reference's filter).  */
+int xnb_set_chunk_neighbors_config(xnb_ctx*, int half_symmetric, int skip_ghosts);
+/* compute_cell_particle_pairs<Symmetric> with ComputePairOptionalLocks<true> (impl_default.h:143-239,
+   compute_pair_optional_args.h:152-161) and the LJ functor applied once per pair: f_a += de*dr, f_b -= de*dr
+   (accumulates: zero the forces, ghosts included, first).  Needs half_symmetric lists.                            */
+int xnb_lennard_jones_force_symmetric(xnb_ctx*, double epsilon, double sigma, double rcut, void* stream);
+/* replaces op `update_force_from_ghost` (mpi/update_force_from_ghost.cu:44, update_from_ghosts.h:152-,
+   update_from_ghost_functors.h:36-120, UpdateValueAdd): the force of every ghost is added to the particle it is an
+   image of; between ranks the ghost exchange runs backwards (NCCL send/recv of fx,fy,fz).                         */
+int xnb_update_force_from_ghost(xnb_ctx*, void* stream);
+
 /* op `divide_force_by_type_scalar: mass` : src/compute/vec3_typescalar_op.cu:118-122                            */
 int xnb_divide_force_by_mass(xnb_ctx*, void* stream);
 /* ops `push_f_v_r` / `push_f_v` : src/defbox/include/exanb/defbox/push_vec3_2nd_order.h:29-118, push_vec3_1st_order.h:29-107 */

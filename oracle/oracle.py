@@ -44,13 +44,14 @@ def lib():
         L.xo_destroy.argtypes = [P]
         L.xo_last_error.restype = C.c_char_p
         for f in ("xo_init", "xo_generate", "xo_first_iteration", "xo_move_particles", "xo_update_particles_full", "xo_ghost_update_r", "xo_build_neighbors",
-                  "xo_compute_force", "xo_push_f_v_r", "xo_check_streams"):
+                  "xo_compute_force", "xo_compute_force_symmetric", "xo_push_f_v_r", "xo_check_streams"):
             getattr(L, f).argtypes = [P]; getattr(L, f).restype = C.c_int
         L.xo_run.argtypes = [P, C.c_int]; L.xo_run.restype = C.c_int
         L.xo_push_f_v.argtypes = [P, C.c_double]; L.xo_push_f_v.restype = C.c_int
         for f in ("xo_displ_over", "xo_total_particles", "xo_inner_particles", "xo_stream_total_u16", "xo_max_neighbors",
                   "xo_rebuild_count"):
             getattr(L, f).argtypes = [P]; getattr(L, f).restype = C.c_int64
+        L.xo_set_nbh_config.argtypes = [P, C.c_int, C.c_int]; L.xo_set_nbh_config.restype = None
         L.xo_grid_info.argtypes = [P, P, P, P, P]
         L.xo_cell_counts.argtypes = [P, P]
         L.xo_get_particles.argtypes = [P] * 12
@@ -117,6 +118,10 @@ class Oracle:
     def ghost_update_r(self): self._chk(self.L.xo_ghost_update_r(self.h))
     def build_neighbors(self): self._chk(self.L.xo_build_neighbors(self.h))
     def compute_force(self): self._chk(self.L.xo_compute_force(self.h))
+    def compute_force_symmetric(self): self._chk(self.L.xo_compute_force_symmetric(self.h))
+
+    def set_nbh_config(self, half_symmetric=False, skip_ghosts=False):
+        self.L.xo_set_nbh_config(self.h, int(bool(half_symmetric)), int(bool(skip_ghosts)))
     def push_f_v_r(self): self._chk(self.L.xo_push_f_v_r(self.h))
     def push_f_v(self, s): self._chk(self.L.xo_push_f_v(self.h, s))
     def displ_over(self): return self.L.xo_displ_over(self.h)
@@ -125,6 +130,7 @@ class Oracle:
         return rc, self.L.xo_last_error().decode() if rc else ""
     def rebuild_count(self): return self.L.xo_rebuild_count(self.h)
     def max_neighbors(self): return self.L.xo_max_neighbors(self.h)
+    def stream_total_u16(self): return self.L.xo_stream_total_u16(self.h)
 
     def grid_info(self):
         d = np.zeros(3, np.int64); o = np.zeros(3, np.int64); gl = C.c_int64(); nc = C.c_int64()

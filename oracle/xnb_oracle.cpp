@@ -146,6 +146,8 @@ struct xo_sim
   std::vector<std::vector<uint16_t>> streams;
   unsigned max_neighbors = 0;
   i64 rebuilds = 0;
+  /* ChunkNeighborsConfig::half_symmetric / skip_ghosts (chunk_neighbors_config.h:35-36) */
+  bool nbh_half_symmetric = false, nbh_skip_ghosts = false;
 };
 
 namespace {
@@ -649,6 +651,7 @@ static void chunk_neighbors(xo_sim& s)
       {
         const IJK lb{bi, bj, bk};
         const i64 cell_b = ijk_to_index(dims, lb);
+        const bool ghost_b = g.is_ghost_cell(lb);
         const Cell& B = g.cells[(size_t)cell_b];
         const size_t nb = B.size();
         const i64 sgstart_b = (i64)s.sub_grid_start[(size_t)cell_b];
@@ -689,7 +692,13 @@ static void chunk_neighbors(xo_sim& s)
               /* :225-227 : dr = r_a - r_b ; identity LinearXForm is exact ; d2 = x*x + y*y + z*z ; filter d2 > 0 && d2 <= max_dist2 */
               const double dx = A.rx[pa] - B.rx[pb], dy = A.ry[pa] - B.ry[pb], dz = A.rz[pa] - B.rz[pb];
               const double d2 = dx * dx + dy * dy + dz * dz;
-              if ((cell_a != cell_b || pa != pb) && d2 > 0.0 && d2 <= max_dist2) pn[pa].push_back({enc, (uint16_t)pb});
+              if ((cell_a != cell_b || pa != pb) && d2 > 0.0 && d2 <= max_dist2)
+              {
+                /* NeighborFilterHalfSymGhost (neighbor_filter_func.h:36-52) */
+                if (s.nbh_half_symmetric && (cell_a < cell_b || (cell_a == cell_b && pa < pb))) continue;
+                if (s.nbh_skip_ghosts && ghost_b) continue;
+                pn[pa].push_back({enc, (uint16_t)pb});
+              }
             }
         }
       }
@@ -838,6 +847,86 @@ static int compute_force(xo_sim& s, double* epot_out, double* vir_out)
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Symmetric (Newton-3) pair sweep over half_symmetric lists -- SURVEY 8(f) rank 2.  The reference has no symmetric LJ
+ * operator; this restates what its machinery does for a symmetric pair functor:
+ *   zero_particle_force{ghost:true}
+ *   compute_cell_particle_pairs<Symmetric=true> over the inner cells (impl_default.h:143-239; :181 stops a particle's walk
+ *     at the first entry that lies "after" it -- with half_symmetric lists there is none), functor of lennard_jones.cu:46-56
+ *     applied once per pair: f_a += de*dr, f_b -= de*dr (b may be a ghost; ComputePairOptionalLocks<true> serialises the
+ *     concurrent updates of a cell, compute_pair_optional_args.h:152-161 -- here the sweep is sequential instead)
+ *   update_force_from_ghost (UpdateFromGhosts<fx,fy,fz, UpdateValueAdd>, mpi/update_force_from_ghost.cu:44,
+ *     update_from_ghost_functors.h:36-120): every ghost's force is ADDED to the particle it is an image of
+ *   divide_force_by_type_scalar: mass
+ * Parity unpinned by the reference's tests (like energy / virial); pinned here by: forces equal those of the full-list
+ * sweep to rounding (tests/test_oracle_properties.py).
+ * ---------------------------------------------------------------------------------------------- */
+static void update_force_from_ghost(xo_sim& s)
+{
+  Grid& g = s.grid;
+  for (size_t q = 0; q < s.sends.size(); q++)
+  {
+    const GhostSend& snd = s.sends[q];
+    Cell& src = g.cells[(size_t)snd.cell_i];
+    const Cell& gh = g.cells[(size_t)snd.partner_cell_i];
+    for (size_t t = 0; t < snd.particle_i.size(); t++)
+    {
+      const size_t p = snd.particle_i[t];
+      src.fx[p] += gh.fx[t]; src.fy[p] += gh.fy[t]; src.fz[p] += gh.fz[t];
+    }
+  }
+}
+
+static int compute_force_symmetric(xo_sim& s)
+{
+  Grid& g = s.grid;
+  const i64 gl = g.ghost_layers();
+  const double rcut2 = s.cfg.rcut * s.cfg.rcut;
+  const double eps = s.cfg.epsilon, sig = s.cfg.sigma, mass = s.cfg.mass;
+  if (!s.nbh_half_symmetric) { g_err = "compute_force_symmetric needs half_symmetric lists"; return 1; }
+  for (Cell& c : g.cells) { std::fill(c.fx.begin(), c.fx.end(), 0.); std::fill(c.fy.begin(), c.fy.end(), 0.); std::fill(c.fz.begin(), c.fz.end(), 0.); }
+  for (i64 k = gl; k < g.dims.k - gl; k++) for (i64 j = gl; j < g.dims.j - gl; j++) for (i64 i = gl; i < g.dims.i - gl; i++)
+  {
+    const i64 cell_a = ijk_to_index(g.dims, IJK{i, j, k});
+    Cell& A = g.cells[(size_t)cell_a];
+    const size_t na = A.size();
+    const StreamInfo si = stream_info(s.streams[(size_t)cell_a], na);
+    for (size_t pa = 0; pa < na; pa++)
+    {
+      const double xa = A.rx[pa], ya = A.ry[pa], za = A.rz[pa];
+      bool stop = false;
+      for_each_listed(s, cell_a, pa, si, [&](i64 cell_b, size_t pb) {
+        if (stop) return;
+        if (cell_b > cell_a || (cell_b == cell_a && pb > pa)) { stop = true; return; }      /* impl_default.h:181 */
+        Cell& B = g.cells[(size_t)cell_b];
+        const double dx = B.rx[pb] - xa, dy = B.ry[pb] - ya, dz = B.rz[pb] - za;
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 > 0.0 && d2 <= rcut2)
+        {
+          const double r = std::sqrt(d2);
+          const double inv_r = 1.0 / r;
+          const double ratio = sig * inv_r;
+          const double ratio2 = ratio * ratio;
+          const double ratio6 = ratio2 * ratio2 * ratio2;
+          const double ratio12 = ratio6 * ratio6;
+          double de = (-24. * eps * (2. * ratio12 - ratio6)) * inv_r;
+          de *= 1.0 / r;
+          const double fx = de * dx, fy = de * dy, fz = de * dz;
+          A.fx[pa] += fx; A.fy[pa] += fy; A.fz[pa] += fz;
+          B.fx[pb] -= fx; B.fy[pb] -= fy; B.fz[pb] -= fz;
+        }
+      });
+    }
+  }
+  update_force_from_ghost(s);
+  for (i64 k = gl; k < g.dims.k - gl; k++) for (i64 j = gl; j < g.dims.j - gl; j++) for (i64 i = gl; i < g.dims.i - gl; i++)
+  {
+    Cell& A = g.cells[(size_t)ijk_to_index(g.dims, IJK{i, j, k})];
+    for (size_t pa = 0; pa < A.size(); pa++) { A.fx[pa] /= mass; A.fy[pa] /= mass; A.fz[pa] /= mass; }
+  }
+  return 0;
+}
+
 /* defbox/push_vec3_2nd_order.h:29-39,85-88 via compute_cell_particles (inner cells) */
 static void push_f_v_r(xo_sim& s)
 {
@@ -956,6 +1045,8 @@ int xo_update_particles_full(xo_sim* s) { return update_particles_full(*s); }
 int xo_ghost_update_r(xo_sim* s) { ghost_update(*s, false); return 0; }
 int xo_build_neighbors(xo_sim* s) { amr_grid_pairs(*s); chunk_neighbors(*s); return 0; }
 int xo_compute_force(xo_sim* s) { return compute_force(*s, nullptr, nullptr); }
+int xo_compute_force_symmetric(xo_sim* s) { return compute_force_symmetric(*s); }
+void xo_set_nbh_config(xo_sim* s, int half_symmetric, int skip_ghosts) { s->nbh_half_symmetric = half_symmetric != 0; s->nbh_skip_ghosts = skip_ghosts != 0; }
 int xo_push_f_v_r(xo_sim* s) { push_f_v_r(*s); return 0; }
 int xo_push_f_v(xo_sim* s, double sc) { push_f_v(*s, sc); return 0; }
 int64_t xo_displ_over(xo_sim* s) { return displ_over(*s); }

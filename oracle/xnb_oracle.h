@@ -69,6 +69,10 @@ int xo_update_particles_full(xo_sim*);    /* update-particles.msp:62-68 (without
 int xo_ghost_update_r(xo_sim*);           /* update_ghosts.cu:46 */
 int xo_build_neighbors(xo_sim*);          /* amr_grid_pairs + chunk_neighbors */
 int xo_compute_force(xo_sim*);            /* zero_particle_force{ghost} + lennard_jones_force + divide by mass */
+/* ChunkNeighborsConfig::half_symmetric / skip_ghosts (chunk_neighbors_config.h:35-36, neighbor_filter_func.h:36-52); takes effect at the next build */
+void xo_set_nbh_config(xo_sim*, int half_symmetric, int skip_ghosts);
+/* Newton-3 sweep over half_symmetric lists + update_force_from_ghost + divide by mass */
+int xo_compute_force_symmetric(xo_sim*);
 int xo_push_f_v_r(xo_sim*);               /* push_vec3_2nd_order.h */
 int xo_push_f_v(xo_sim*, double dt_scale);/* push_vec3_1st_order.h */
 int64_t xo_displ_over(xo_sim*);           /* particle_displ_over.cu: count of atoms over threshold */

@@ -50,6 +50,15 @@ def main():
         mine = ctx.get_particles(0, ctx.n_inner)
         everyone = [None] * world
         dist.all_gather_object(everyone, {k: mine[k] for k in ("id", "rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz")})
+        # Newton-3 path on the final configuration: half_symmetric lists, symmetric sweep, and the ghost
+        # exchange run backwards (update_force_from_ghost over NCCL) must reproduce the full-list forces (= a, mass 1 here)
+        ctx.set_chunk_neighbors_config(half_symmetric=True); ctx.chunk_neighbors()
+        ctx.zero_particle_force(ghost=True); ctx.lennard_jones_force_symmetric(eps, sig, rc); ctx.update_force_from_ghost(); ctx.divide_force_by_mass()
+        sym = ctx.get_particles(0, ctx.n_inner)
+        assert np.array_equal(sym["id"], mine["id"])
+        if len(sym["id"]):
+            err = U.force_error(U.vec(sym, ("fx", "fy", "fz")), U.vec(mine, ("fx", "fy", "fz")))
+            assert err < 1e-10, "%s rank %d: Newton-3 forces differ from the full-list forces (%g)" % (name, rank, err)
         if rank == 0:
             ref = U.make_ctx(kw, device=local, particles=inp)
             ref.first_iteration(eps, sig, rc)

@@ -289,6 +289,55 @@ def test_speculative_fast_path_changes_nothing(monkeypatch):
         assert np.array_equal(pa[k], pb[k]), k
 
 
+@pytest.mark.parametrize("case", ["ni16k", "lj2k", "lj_gap2", "lj_voids"])
+def test_newton3_path(case):
+    """SURVEY 8f rank 2: chunk_neighbors with ChunkNeighborsConfig::half_symmetric / skip_ghosts (neighbor_filter_func.h:36-52)
+    builds byte-identical GridChunkNeighbors streams; zero_particle_force{ghost} + the symmetric LJ sweep (each pair once, f_b -=
+    via FP64 atomics where the reference takes per-cell locks) + update_force_from_ghost + divide by mass gives the oracle's
+    Newton-3 forces, which are the full-list forces"""
+    kw = CASES[case]
+    eps, sig, rc = kw["epsilon"], kw["sigma"], kw["rcut"]
+    o, ctx = setup_pair(kw)
+    o.move_particles(); o.update_particles_full()
+    ctx.move_particles(); ctx.update_particles_full()
+    # full-list forces of the standard path
+    ctx.zero_particle_force(ghost=True); ctx.lennard_jones_force(eps, sig, rc); ctx.divide_force_by_mass()
+    f_full = U.vec(U.by_id(ctx.get_particles(0, ctx.n_inner)), ("fx", "fy", "fz"))
+    n_full = int(ctx.streams()[0].sum())
+    # ---- Newton-3 forces
+    o.set_nbh_config(half_symmetric=True); o.build_neighbors(); o.compute_force_symmetric()
+    po = U.by_id(o.particles(), o.inner_mask())
+    ctx.set_chunk_neighbors_config(half_symmetric=True)
+    with pytest.raises(Exception):
+        ctx.lennard_jones_force_symmetric(eps, sig, rc)            # the full lists are void now
+    ctx.chunk_neighbors()
+    assert int(ctx.streams()[0].sum()) < n_full
+    for functor in (0, 1):
+        ctx.set_pair_functor(functor)
+        ctx.zero_particle_force(ghost=True); ctx.lennard_jones_force_symmetric(eps, sig, rc); ctx.update_force_from_ghost(); ctx.divide_force_by_mass()
+        pg = U.by_id(ctx.get_particles(0, ctx.n_inner))
+        assert np.array_equal(po["id"], pg["id"])
+        f_sym = U.vec(pg, ("fx", "fy", "fz"))
+        assert U.force_error(f_sym, U.vec(po, ("fx", "fy", "fz"))) < TOL
+        assert U.force_error(f_sym, f_full) < TOL
+    ctx.set_pair_functor(0)
+    # ---- streams of the three filtered configurations, byte for byte, with the oracle in the GPU's in-cell order
+    pg_all, cnt_g = U.gpu_particles_cell_order(ctx)
+    o.set_particles(cnt_g, pg_all)
+    for half, skip in ((True, False), (False, True), (True, True), (False, False)):
+        o.set_nbh_config(half_symmetric=half, skip_ghosts=skip); o.build_neighbors()
+        rc_, msg = o.check_streams(); assert rc_ == 0, msg
+        ctx.set_chunk_neighbors_config(half_symmetric=half, skip_ghosts=skip); ctx.chunk_neighbors()
+        sz_o, data_o = o.streams(); sz_g, data_g = ctx.streams()
+        assert np.array_equal(sz_o, sz_g), (half, skip)
+        assert np.array_equal(data_o, data_g), (half, skip)
+        assert ctx.view_chunk_neighbors()[2] == o.max_neighbors()
+    assert int(ctx.streams()[0].sum()) == n_full
+    # the symmetric sweep refuses full lists
+    with pytest.raises(Exception):
+        ctx.lennard_jones_force_symmetric(eps, sig, rc)
+
+
 @pytest.mark.parametrize("sequential", [False, True])
 def test_step_host_equals_run_steps(sequential, monkeypatch):
     """xnb_step_host (particles resident in host memory, positions copied back while the sweep runs) = upload + xnb_run_steps(1)

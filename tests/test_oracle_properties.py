@@ -69,3 +69,34 @@ def test_backup_codec_roundtrip():
         back = org + b[:, ax].astype(np.float64) * cs / 2.0 ** 32
         assert np.abs(back - p[name][m]).max() <= cs / 2.0 ** 33 * 1.0001
     assert o.displ_over() == 0
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_half_symmetric_lists_and_newton3_sweep(case):
+    """ChunkNeighborsConfig::half_symmetric / skip_ghosts (chunk_neighbors_config.h:35-36, neighbor_filter_func.h:36-52) and the
+    symmetric sweep + update_force_from_ghost: the half list holds each unordered pair once, and the Newton-3 forces equal the
+    full-list forces to rounding"""
+    kw = CASES[case]
+    o = O.Oracle(O.make_config(**kw)); o.init()
+    p = o.particles(); m = o.inner_mask()
+    f_full = np.stack([p["fx"][m], p["fy"][m], p["fz"][m]], 1)
+    n_full = o.stream_total_u16()
+    full = o.pairs()
+    o.set_nbh_config(half_symmetric=True); o.build_neighbors()
+    rc, msg = o.check_streams(); assert rc == 0, msg
+    half = o.pairs()
+    assert o.stream_total_u16() < n_full
+    # pairs() lists (id_a, id_b) for inner a: an inner-inner pair appears once, an inner-ghost pair once on at most one side
+    hs = set(map(tuple, half.tolist())); fs = set(map(tuple, full.tolist()))
+    assert hs <= fs and all(((a, b) in hs) or ((b, a) in hs) for a, b in fs)
+    o.compute_force_symmetric()
+    p = o.particles()
+    f_sym = np.stack([p["fx"][m], p["fy"][m], p["fz"][m]], 1)
+    scale = max(np.sqrt((f_full ** 2).sum(1).mean()), 1e-300)
+    assert np.abs(f_sym - f_full).max() <= 1e-12 * max(scale, np.abs(f_full).max())
+    # skip_ghosts: no listed neighbour lives in a ghost cell -> fewer entries than the full list whenever there are ghosts
+    o.set_nbh_config(skip_ghosts=True); o.build_neighbors()
+    rc, msg = o.check_streams(); assert rc == 0, msg
+    assert o.stream_total_u16() < n_full
+    o.set_nbh_config(); o.build_neighbors()
+    assert o.stream_total_u16() == n_full
