@@ -195,7 +195,7 @@ class Context:
     def sweep_info(self):
         si = XnbSweepInfo()
         self._ck(self.L.xnb_get_sweep_info(self.h, C.byref(si)))
-        return dict(compiled=bool(si.compiled), ghost=bool(si.ghost), tile=tuple(si.tile[:]), threads=si.threads, blocks=si.blocks,
+        return dict(compiled=bool(si.compiled), paired=(si.compiled == 2), ghost=bool(si.ghost), tile=tuple(si.tile[:]), threads=si.threads, blocks=si.blocks,
                     smem_bytes=si.smem_bytes, rows=si.rows, candidates=si.candidates, interior_tiles=si.interior_tiles, boundary_tiles=si.boundary_tiles)
 
     def cells(self):

@@ -133,10 +133,10 @@ struct xnb_ctx
   bool nbh_half_symmetric = false, nbh_skip_ghosts = false;       // ChunkNeighborsConfig (xnb_set_chunk_neighbors_config)
   int nbh_cap_l = 0; uint32_t nbh_slot_words = 0; bool nbh_full_cap = false;   // capacities of the tiled build (grow on demand)
   // ---- compiled lists of the pair sweep (xnb_sweep_cl.cuh): derived from the streams after every rebuild
-  struct ClCfg { bool valid = false, ghost = false; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; int64_t candidates = 0;
+  struct ClCfg { bool valid = false, ghost = false, paired = false; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; int64_t candidates = 0;
                  unsigned n_interior = 0, n_boundary = 0; };    // tiles whose halo box holds no ghost cell / the others (cl_tile_list: interior first)
   ClCfg cl;
-  DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0; DBuf<uint32_t> cl_tile_list;
+  DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0; DBuf<uint32_t> cl_tile_list; DBuf<uint16_t> cl_perm; double cl_union_per_pair = 0;
   cudaStream_t st_comm = nullptr; cudaEvent_t ev_pos = nullptr, ev_ghost = nullptr;      // halo exchange overlapped with the interior tiles
   int64_t n_nonempty_inner = 0;
   int64_t pool_used = 0; uint32_t max_neighbors = 0, max_cell_count = 0, max_stream = 0; double avg_stream = 0; bool have_nbh = false;
@@ -589,7 +589,7 @@ int xnb_get_sweep_info(const xnb_ctx* c, xnb_sweep_info* out)
 {
   if (!c || !out) return XNB_ERR_INVALID;
   memset(out, 0, sizeof *out);
-  out->compiled = c->cl.valid ? 1 : 0;
+  out->compiled = c->cl.valid ? (c->cl.paired ? 2 : 1) : 0;   // 2: pair-merged lists (two particles per sweep thread)
   if (c->cl.valid)
   {
     out->tile[0] = c->cl.tp.ti; out->tile[1] = c->cl.tp.tj; out->tile[2] = c->cl.tp.tk;
@@ -863,6 +863,9 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
   const double avg = std::max((double)c->n_inner / ne, 1.0);
   const double mx = (double)std::max<uint32_t>(c->max_cell_count, 1);
   const size_t SM_BYTES = 227 * 1024;
+  // pair-merged lists (xnb_sweep_cl.cuh): two tile particles per sweep thread, a group = 64 slots
+  const bool paired = env_flag("XNB_CL_PAIRED");
+  const int gsz = paired ? 64 : 32;
   static const int shapes[][3] = {{4, 2, 2}, {4, 4, 1}, {2, 2, 2}, {4, 2, 1}, {3, 3, 2}, {4, 3, 1}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}, {4, 4, 2}, {3, 2, 2}, {8, 2, 1}, {8, 2, 2}};
   int et[3] = {0, 0, 0};
   if (const char* e = getenv("XNB_CL_TILE")) sscanf(e, "%d,%d,%d", &et[0], &et[1], &et[2]);
@@ -879,21 +882,21 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
     if (dup) continue;
     k.nh = std::min(k.t[0] + 2 * tp.gap, g.dims[0]) * std::min(k.t[1] + 2 * tp.gap, g.dims[1]) * std::min(k.t[2] + 2 * tp.gap, g.dims[2]);
     const double tile_avg = avg * k.tc;
-    k.threads = 32 * (int)std::ceil(std::min(mx * k.tc, tile_avg * 1.04 + 8.0) / 32.0);
-    if (k.threads > 1024) continue;
+    k.threads = 32 * (int)std::ceil(std::min(mx * k.tc, tile_avg * 1.04 + 8.0) / (double)gsz);
+    if (k.threads > (paired ? 576 : 1024)) continue;
     k.threads = std::max(k.threads, 64);
-    k.var = k.threads <= 576 ? 0 : 1;
+    k.var = paired ? (k.threads <= 288 ? 0 : 1) : (k.threads <= 576 ? 0 : 1);
     const double capd = std::min(mx * k.nh, avg * k.nh * 1.08 + 64.0);
     if (capd > 8191.0) continue;
     k.cap = ((int)capd + 1) & ~1;
     k.smem = cl_sweep_smem_bytes(k.nh, k.tc, k.cap, k.threads / 32);
     if (k.smem + 1024 + 2048 > SM_BYTES) continue;
     const int by_smem = (int)(SM_BYTES / (k.smem + 1024 + 256));
-    const int by_regs = 65536 / (k.threads * (k.var == 0 ? 56 : 64));
+    const int by_regs = 65536 / (k.threads * (paired ? 112 : k.var == 0 ? 56 : 64));
     const int by_warps = 64 / (k.threads / 32);
     const int resident = std::min(std::min(by_smem, by_regs), std::min(by_warps, 32));
     if (resident < 1) continue;
-    const double useful = resident * (tile_avg / 32.0);               // useful resident warps per SM
+    const double useful = resident * (tile_avg / 32.0);               // useful resident warps per SM (paired: two particles per lane)
     k.score = std::min(useful, 36.0) - 0.25 * (double)k.nh / (double)k.tc;
     cands.push_back(k);
   }
@@ -905,7 +908,7 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
     tp.tiles_i = (nc[0] + tp.ti - 1) / tp.ti; tp.tiles_j = (nc[1] + tp.tj - 1) / tp.tj; tp.tiles_k = (nc[2] + tp.tk - 1) / tp.tk;
     tp.nh_max = (tp.ti + 2 * tp.gap) * (tp.tj + 2 * tp.gap) * (tp.tk + 2 * tp.gap); tp.tc_max = k.tc;
     tp.cap = k.cap; tp.gmax = k.threads / 32;
-    if (c->cl.tp.ti == tp.ti && c->cl.tp.tj == tp.tj && c->cl.tp.tk == tp.tk && c->cl.ghost == ghost)
+    if (c->cl.tp.ti == tp.ti && c->cl.tp.tj == tp.tj && c->cl.tp.tk == tp.tk && c->cl.ghost == ghost && c->cl.paired == paired)
     {
       // same shape as last time: start from the capacities that worked (no second compile pass per rebuild)
       tp.gmax = std::max(tp.gmax, c->cl.tp.gmax);
@@ -919,26 +922,36 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
       if (c->cl_cap_rows == 0) c->cl_cap_rows = (uint32_t)std::min<double>(4.0e9, (double)c->pool_used / 128.0 * 1.10 + 4096.0);
       CK(c->cl_rows.ensure((size_t)c->cl_cap_rows * 128 + 64));
       CK(c->cl_groups.ensure((size_t)blocks * tp.gmax + 16));
-      CK(cudaMemsetAsync(counters, 0, 6 * 4, st));      // [0..2] u32 counters, [4..5] one u64 (8-byte aligned): list entries
+      CK(cudaMemsetAsync(counters, 0, 8 * 4, st));      // [0..2] u32 counters, [4..5] one u64 (8-byte aligned): list entries, [6..7] one u64: union entries (paired)
       const size_t tbytes = (((size_t)(2 * tp.nh_max + 2 * tp.tc_max + 2) * 4 + 15) & ~(size_t)15);
+      if (paired)
+      {
+        ParticlesP A = c->P(c->cur);
+        CK(c->cl_perm.ensure((size_t)blocks * tp.gmax * 64 + 64));
+        k_cl_compile_paired<<<blocks, 32 * std::min(2 * tp.gmax, 32), tbytes + (size_t)tp.gmax * 64 * 3, st>>>(g, tp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p,
+            (const uint16_t* const*)c->cell_stream.p, c->cl_groups.p, reinterpret_cast<uint2*>(c->cl_rows.p), c->cl_perm.p, c->cl_cap_rows, counters,
+            reinterpret_cast<unsigned long long*>(counters + 4));
+      }
+      else
       k_cl_compile<<<blocks, 32 * std::min(tp.gmax, 32), tbytes, st>>>(g, tp, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p, c->cl_groups.p,
                                                                      reinterpret_cast<uint2*>(c->cl_rows.p), c->cl_cap_rows, counters, reinterpret_cast<unsigned long long*>(counters + 4));
       c->launches++; CK(cudaGetLastError());
-      uint32_t h[6]; int rc = read_back(c, counters, 6, h, st); if (rc) return rc;
+      uint32_t h[8]; int rc = read_back(c, counters, 8, h, st); if (rc) return rc;
       bool again = false;
-      if ((int)h[1] > tp.gmax) { if (h[1] * 32u > 1024u) break; tp.gmax = (int)h[1]; again = true; }
+      if ((int)h[1] > tp.gmax) { if (h[1] * 32u > (paired ? 576u : 1024u)) break; tp.gmax = (int)h[1]; again = true; }
       if ((int)h[2] > tp.cap) { tp.cap = ((int)h[2] + 1) & ~1; again = true; }
       smem = cl_sweep_smem_bytes(tp.nh_max, tp.tc_max, tp.cap, tp.gmax);
       if (tp.cap > 8191 || smem + 1024 + 2048 > SM_BYTES) break;
       if (!again && h[0] > c->cl_cap_rows) { c->cl_cap_rows = (uint32_t)((double)h[0] * 1.05) + 1024u; again = true; }
       if (again) continue;
       // every tile is swept in one pass: one warp per group of the fullest tile
-      c->cl.tp = tp; c->cl.ghost = ghost; c->cl.blocks = blocks; c->cl.smem = smem; c->cl.rows = h[0];
+      c->cl.tp = tp; c->cl.ghost = ghost; c->cl.paired = paired; c->cl.blocks = blocks; c->cl.smem = smem; c->cl.rows = h[0];
       c->cl.candidates = (int64_t)(((unsigned long long)h[5] << 32) | h[4]);
+      c->cl_union_per_pair = (double)(((unsigned long long)h[7] << 32) | h[6]) / std::max(0.5 * (double)(ghost ? c->n_total : c->n_inner), 1.0);
       c->cl.threads = std::max(32 * (int)std::max<uint32_t>(h[1], 1u), 64);
       if (env_int("XNB_CL_THREADS") > 0) c->cl.threads = std::min(env_int("XNB_CL_THREADS") & ~31, 1024);
-      c->cl.var = c->cl.threads <= 576 ? 0 : 1;
-      if (getenv("XNB_CL_VAR")) { const int v = env_int("XNB_CL_VAR"); if ((v == 2 && c->cl.threads <= 288) || (v == 3 && c->cl.threads <= 576)) c->cl.var = v; }   // experiments: 2 = three blocks per SM (<= 72 registers), 3 = one block per SM
+      c->cl.var = paired ? (c->cl.threads <= 288 ? 0 : 1) : (c->cl.threads <= 576 ? 0 : 1);
+      if (!paired && getenv("XNB_CL_VAR")) { const int v = env_int("XNB_CL_VAR"); if ((v == 2 && c->cl.threads <= 288) || (v == 3 && c->cl.threads <= 576)) c->cl.var = v; }   // experiments: 2 = three blocks per SM (<= 72 registers), 3 = one block per SM
       c->cl.smem = cl_sweep_smem_bytes(tp.nh_max, tp.tc_max, tp.cap, std::max(tp.gmax, c->cl.threads / 32));   // one ring of list rows per warp
       {
         // interior tiles: the halo box touches no ghost cell, so they can be swept while the halo exchange is in flight
@@ -965,6 +978,7 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
   }
   if (getenv("XNB_TILE_DEBUG"))
   {
+    if (c->cl.valid && c->cl.paired) fprintf(stderr, "[xnb] pair-merged lists: %.2f union entries per particle pair, %.2f list entries per particle\n", c->cl_union_per_pair, (double)c->cl.candidates / std::max<double>((double)c->n_inner, 1.0));
     if (c->cl.valid) fprintf(stderr, "[xnb] compiled lists: tiles %dx%dx%d threads %d var %d smem %zu cap %d gmax %d blocks %u rows %u (avg %.1f max %.0f)\n", c->cl.tp.ti, c->cl.tp.tj, c->cl.tp.tk,
                              c->cl.threads, c->cl.var, c->cl.smem, c->cl.tp.cap, c->cl.tp.gmax, c->cl.blocks, c->cl.rows, avg, mx);
     else fprintf(stderr, "[xnb] compiled lists: no tile shape fits, sweeping the streams\n");
@@ -1217,8 +1231,21 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
     const unsigned nb = part == 0 ? k.blocks : part == 1 ? k.n_interior : k.n_boundary;
     const uint32_t* tl = part == 0 ? nullptr : part == 1 ? c->cl_tile_list.p : c->cl_tile_list.p + k.n_interior;
     if (nb == 0) return XNB_OK;
+    static bool cl2_attr_done[2][2][2] = {};
+#define XNB_CL2_LAUNCH(VAR) do { \
+      if (!cl2_attr_done[MODE][EV ? 1 : 0][VAR]) { \
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (k_lj_sweep_cl2<F, MODE, EV, VAR>))); \
+        CK(cudaFuncSetAttribute((k_lj_sweep_cl2<F, MODE, EV, VAR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes)); \
+        cl2_attr_done[MODE][EV ? 1 : 0][VAR] = true; } \
+      if (part == 0 && (rc = t_begin(c, XNB_T_FORCE, st))) return rc; \
+      k_lj_sweep_cl2<F, MODE, EV, VAR><<<nb, k.threads, k.smem, st>>>(c->g, k.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, \
+          fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, c->cl_groups.p, \
+          reinterpret_cast<const uint2*>(c->cl_rows.p), c->cl_perm.p, EV ? c->ev_partials.p : nullptr, c->d_scalars32.p, skip_if_nonzero, tl); } while (0)
+    if (k.paired) { if (k.var == 0) XNB_CL2_LAUNCH(0); else XNB_CL2_LAUNCH(1); }
+    else
     if (k.var == 0) XNB_CL_LAUNCH(0); else if (k.var == 1) XNB_CL_LAUNCH(1); else if (k.var == 2) XNB_CL_LAUNCH(2); else XNB_CL_LAUNCH(3);
 #undef XNB_CL_LAUNCH
+#undef XNB_CL2_LAUNCH
     c->launches++; CK(cudaGetLastError());
     return part == 0 ? t_end(c, XNB_T_FORCE, st) : XNB_OK;
   }
