@@ -65,6 +65,8 @@ std::string g_create_error;
 bool env_flag(const char* name) { const char* v = getenv(name); return v && *v && *v != '0'; }
 int env_int(const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; }
 
+constexpr int XNB_MAX_DEVICES = 64;
+
 template <class T>
 struct DBuf
 {
@@ -468,6 +470,7 @@ int xnb_set_nbh_dist(xnb_ctx* c, double rcut_max, double rcut_inc)
 int xnb_set_type_mass(xnb_ctx* c, const double* m, int n)
 {
   if (!c || !m || n < 1 || n > 256) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   CK(cudaMemcpy(c->mass.p, m, (size_t)n * 8, cudaMemcpyHostToDevice));
   c->n_types = n;
   return XNB_OK;
@@ -558,6 +561,7 @@ int xnb_get_particles(xnb_ctx* c, int64_t first, int64_t n, double* rx, double* 
 int xnb_upload_rv(xnb_ctx* c, const double* rx, const double* ry, const double* rz, const double* vx, const double* vy, const double* vz, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   const double* src[6] = {rx, ry, rz, vx, vy, vz};
   for (int f = 0; f < 6; f++) if (src[f] && c->n_inner) CK(cudaMemcpyAsync(c->f64[c->cur][f].p, src[f], (size_t)c->n_inner * 8, cudaMemcpyHostToDevice, st));
@@ -567,6 +571,7 @@ int xnb_upload_rv(xnb_ctx* c, const double* rx, const double* ry, const double* 
 int xnb_download_rvf(xnb_ctx* c, double* rx, double* ry, double* rz, double* vx, double* vy, double* vz, double* fx, double* fy, double* fz, uint64_t* id, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   double* dst[9] = {rx, ry, rz, vx, vy, vz, fx, fy, fz};
   for (int f = 0; f < 9; f++) if (dst[f] && c->n_inner) CK(cudaMemcpyAsync(dst[f], c->f64[c->cur][f].p, (size_t)c->n_inner * 8, cudaMemcpyDeviceToHost, st));
@@ -603,6 +608,7 @@ int xnb_get_sweep_info(const xnb_ctx* c, xnb_sweep_info* out)
 int xnb_get_cells(xnb_ctx* c, uint32_t* cell_start, uint32_t* cell_count)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   int rc = ensure_grid(c); if (rc) return rc;
   CK(cudaDeviceSynchronize());
   if (cell_start) CK(cudaMemcpy(cell_start, c->cell_start.p, (size_t)c->g.n_cells * 4, cudaMemcpyDeviceToHost));
@@ -733,6 +739,7 @@ int xnb_rebuild_amr(xnb_ctx* c, void* stream)
 int xnb_backup_r(xnb_ctx* c, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   int rc = ensure_grid(c); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   CK(c->backup.ensure((size_t)c->n_inner * 3 + 16, 0, 1.2));
@@ -1053,7 +1060,8 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
       uint32_t* stats = s32 + 96;
       CK(cudaMemsetAsync(stats, 0, 6 * 4, st)); CK(cudaMemsetAsync(c->d_scalars64.p + 1, 0, 16, st));
       NbhCellOut o{c->pool.p, c->cell_stream.p, c->stream_size.p, c->cell_stream_bytes.p, c->stream_off.p, stats, c->d_scalars64.p + 1};
-      static bool attr_done = false;
+      static bool attr_done_dev[XNB_MAX_DEVICES] = {};      // function attributes are per device
+      bool& attr_done = attr_done_dev[c->device % XNB_MAX_DEVICES];
       if (!attr_done)
       {
         CK(cudaFuncSetAttribute(k_nbh_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
@@ -1128,6 +1136,7 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
 int xnb_zero_particle_force(xnb_ctx* c, int ghost, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   ParticlesP A = c->P(c->cur);
   const int64_t n = ghost ? c->n_total : c->n_inner;
@@ -1218,7 +1227,8 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
   {
     const xnb_ctx::ClCfg& k = c->cl;
     if (EV) { CK(c->ev_partials.ensure((size_t)k.blocks * 7 + 16)); if (evp_out) *evp_out = c->ev_partials.p; if (nblocks_out) *nblocks_out = k.blocks; }
-    static bool cl_attr_done[2][2][4] = {};
+    static bool cl_attr_done_dev[XNB_MAX_DEVICES][2][2][4] = {};
+    auto& cl_attr_done = cl_attr_done_dev[c->device % XNB_MAX_DEVICES];
 #define XNB_CL_LAUNCH(VAR) do { \
       if (!cl_attr_done[MODE][EV ? 1 : 0][VAR]) { \
         cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (k_lj_sweep_cl<F, MODE, EV, VAR>))); \
@@ -1231,7 +1241,8 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
     const unsigned nb = part == 0 ? k.blocks : part == 1 ? k.n_interior : k.n_boundary;
     const uint32_t* tl = part == 0 ? nullptr : part == 1 ? c->cl_tile_list.p : c->cl_tile_list.p + k.n_interior;
     if (nb == 0) return XNB_OK;
-    static bool cl2_attr_done[2][2][2] = {};
+    static bool cl2_attr_done_dev[XNB_MAX_DEVICES][2][2][2] = {};
+    auto& cl2_attr_done = cl2_attr_done_dev[c->device % XNB_MAX_DEVICES];
 #define XNB_CL2_LAUNCH(VAR) do { \
       if (!cl2_attr_done[MODE][EV ? 1 : 0][VAR]) { \
         cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (k_lj_sweep_cl2<F, MODE, EV, VAR>))); \
@@ -1252,7 +1263,8 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
   const TileCfg t = make_tiles(c, ghost);
   if (t.blocks == 0) return XNB_OK;
   if (EV) { CK(c->ev_partials.ensure((size_t)t.blocks * 7 + 16)); if (evp_out) *evp_out = c->ev_partials.p; if (nblocks_out) *nblocks_out = t.blocks; }
-  static bool attr_done[2][2] = {{false, false}, {false, false}};
+  static bool attr_done_dev[XNB_MAX_DEVICES][2][2] = {};
+  auto& attr_done = attr_done_dev[c->device % XNB_MAX_DEVICES];
   if (!attr_done[MODE][EV ? 1 : 0])
   {
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_lj_sweep<F, MODE, EV>));
@@ -1290,6 +1302,7 @@ int xnb_set_pair_functor(xnb_ctx* c, int form)
 int xnb_lennard_jones_force(xnb_ctx* c, double eps, double sig, double rcut, int ghost, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "lennard_jones_force: no neighbour list (run xnb_chunk_neighbors)");
   c->rcut_max = std::max(c->rcut_max, rcut);    // lennard_jones.cu:193
   return launch_force<0, false>(c, ghost != 0, make_lj(eps, sig, rcut), 0.0, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
@@ -1362,6 +1375,7 @@ int xnb_update_force_from_ghost(xnb_ctx* c, void* stream)
 int xnb_divide_force_by_mass(xnb_ctx* c, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   ParticlesP A = c->P(c->cur);
   if (c->n_inner) LAUNCH(k_divide_force_by_mass, nblk(c->n_inner, 256), 256, st, (int)c->n_inner, A.fx, A.fy, A.fz, A.type, c->mass.p);
@@ -1371,6 +1385,7 @@ int xnb_divide_force_by_mass(xnb_ctx* c, void* stream)
 int xnb_push_f_v_r(xnb_ctx* c, double dt, double dt_scale, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   ParticlesP A = c->P(c->cur);
   const double delta_t = dt * dt_scale, delta_t2 = delta_t * delta_t * 0.5;     // push_vec3_2nd_order.h:87-88
@@ -1381,6 +1396,7 @@ int xnb_push_f_v_r(xnb_ctx* c, double dt, double dt_scale, void* stream)
 int xnb_push_f_v(xnb_ctx* c, double dt, double dt_scale, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   ParticlesP A = c->P(c->cur);
   if (c->n_inner) LAUNCH(k_push_f_v, nblk(c->n_inner, 256), 256, st, (int)c->n_inner, dt * dt_scale, A.vx, A.vy, A.vz, A.fx, A.fy, A.fz);
@@ -1390,6 +1406,7 @@ int xnb_push_f_v(xnb_ctx* c, double dt, double dt_scale, void* stream)
 int xnb_read_displ_over(xnb_ctx* c, uint64_t* count_out, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   // MPI_Allreduce(SUM, 1 x u64) of particle_displ_over.cu:174
   if (c->nranks > 1) { if (!c->comm) return c->fail(XNB_ERR_NCCL, "no communicator"); NK(g_nccl.AllReduce(c->d_scalars64.p, c->d_scalars64.p, 1, nccl_uint64, nccl_sum, c->comm, st)); }
@@ -1402,6 +1419,7 @@ int xnb_read_displ_over(xnb_ctx* c, uint64_t* count_out, void* stream)
 int xnb_particle_displ_over(xnb_ctx* c, uint64_t* count_out, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   ParticlesP A = c->P(c->cur);
   CK(cudaMemsetAsync(c->d_scalars64.p, 0, 8, st));
@@ -1413,6 +1431,7 @@ int xnb_particle_displ_over(xnb_ctx* c, uint64_t* count_out, void* stream)
 int xnb_verlet_first_half(xnb_ctx* c, double dt, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   ParticlesP A = c->P(c->cur);
   int rc;
@@ -1426,6 +1445,7 @@ int xnb_verlet_first_half(xnb_ctx* c, double dt, void* stream)
 int xnb_force_and_second_half(xnb_ctx* c, double eps, double sig, double rcut, double dth, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "no neighbour list (run xnb_chunk_neighbors)");
   return launch_force<1, false>(c, false, make_lj(eps, sig, rcut), dth, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -1470,6 +1490,7 @@ extern "C" {
 int xnb_first_iteration(xnb_ctx* c, double eps, double sig, double rcut, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   int rc;
   if ((rc = move_and_update_full(c, stream))) return rc;
   return xnb_force_and_second_half(c, eps, sig, rcut, 0.0, stream);
@@ -1598,6 +1619,7 @@ int xnb_step_host(xnb_ctx* c, double dt, double eps, double sig, double rcut,
 int xnb_energy_virial(xnb_ctx* c, double eps, double sig, double rcut, double* epot, double virial[6], double* ekin, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "no neighbour list");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = c->n_inner;
@@ -1631,6 +1653,7 @@ int xnb_energy_virial(xnb_ctx* c, double eps, double sig, double rcut, double* e
 int xnb_view_chunk_neighbors(xnb_ctx* c, const uint16_t* const** d_cell_stream, const uint32_t** d_bytes, uint32_t* max_neighbors)
 {
   if (!c || !c->have_nbh) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   if (d_cell_stream) *d_cell_stream = (const uint16_t* const*)c->cell_stream.p;
   if (d_bytes) *d_bytes = c->cell_stream_bytes.p;
   if (max_neighbors) *max_neighbors = c->max_neighbors;
@@ -1642,6 +1665,7 @@ int64_t xnb_stream_pool_u16(const xnb_ctx* c) { return c ? c->pool_used : 0; }
 int xnb_get_streams(xnb_ctx* c, uint32_t* size_u16, uint16_t* data)
 {
   if (!c || !c->have_nbh) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   CK(cudaDeviceSynchronize());
   const size_t nc = (size_t)c->g.n_cells;
   std::vector<uint32_t> sz(nc); std::vector<unsigned long long> off(nc);
@@ -1680,6 +1704,7 @@ int64_t xnb_get_amr(xnb_ctx* c, int64_t* sgs, uint32_t* sgc)
 int xnb_get_backup(xnb_ctx* c, uint32_t* out)
 {
   if (!c || !out) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   CK(cudaDeviceSynchronize());
   if (c->n_inner) CK(cudaMemcpy(out, c->backup.p, (size_t)c->n_inner * 12, cudaMemcpyDeviceToHost));
   return XNB_OK;
@@ -1698,6 +1723,7 @@ int xnb_timing_enable(xnb_ctx* c, int on)
 int xnb_timing_read(xnb_ctx* c, double ms[XNB_T_COUNT], int64_t scopes[XNB_T_COUNT], int reset)
 {
   if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
   int rc = t_collect(c); if (rc) return rc;
   for (int cat = 0; cat < XNB_T_COUNT; cat++)
   {

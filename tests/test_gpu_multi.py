@@ -19,3 +19,31 @@ def test_decomposed_run_is_bit_identical_to_single_gpu(world):
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("mgpu parity ok") == 3, r.stdout[-2000:]
+
+
+def test_two_contexts_on_two_devices_in_one_process():
+    """one process may hold sub-domains on several GPUs (kernel attributes and the current device are handled per context):
+    the same input stepped alternately on cuda:0 and cuda:1 gives bit-identical results"""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import lj_reduced_kwargs
+    import parity_util as U
+    kw = lj_reduced_kwargs(ncell_units=8, cell_units=2)
+    eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
+    inp = U.generate_input(kw)
+    ctxs = [U.make_ctx(kw, device=d, particles=inp) for d in (0, 1)]
+    for c in ctxs:
+        c.first_iteration(eps, sig, rc)
+    rb = [0, 0]
+    for _ in range(15):
+        for q, c in enumerate(ctxs):
+            rb[q] += c.run_steps(2, dt, eps, sig, rc)
+    assert rb[0] == rb[1] and rb[0] > 0
+    pa, pb = (c.get_particles(0, c.n_inner) for c in ctxs)
+    for k in ("id", "rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
+        assert np.array_equal(pa[k], pb[k]), k
+    ea, eb = (c.energy_virial(eps, sig, rc) for c in ctxs)
+    assert ea[0] == eb[0]
