@@ -7,6 +7,10 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <set>
+#include <random>
+#include <ctime>
+#include <cstdio>
 
 namespace xnb { namespace host {
 
@@ -430,6 +434,7 @@ struct CheckValues : OperatorNode
   ADD_SLOT(Grid, grid, INPUT);
   ADD_SLOT(Domain, domain, INPUT, REQUIRED);
   ADD_SLOT(std::string, file, INPUT, std::string("check_values.dat"));
+  ADD_SLOT(long, samples, INPUT, 128L);
   ADD_SLOT(double, pos_threshold, INPUT, 1e-5);
   ADD_SLOT(double, acc_threshold, INPUT, 1e-5);
   ADD_SLOT(double, vel_threshold, INPUT, 1e-5);
@@ -437,16 +442,42 @@ struct CheckValues : OperatorNode
   void yaml_initialize(const Params& p) override
   {
     if (p.has("file")) { file.value = std::make_shared<std::string>(p.str("file")); }
+    if (p.has("samples")) { samples.value = std::make_shared<long>((long)p.quantity("samples")); }
     XNB_PARAM_QUANTITY(p, pos_threshold); XNB_PARAM_QUANTITY(p, acc_threshold); XNB_PARAM_QUANTITY(p, vel_threshold);
   }
   void execute() override
   {
     std::ifstream in(*file);
-    if (!in) fatal_error("check_values: cannot read '" + *file + "'");
     const int64_t n = xnb_num_inner(grid->ctx);
     std::vector<double> f[9]; for (auto& v : f) v.resize((size_t)n);
     std::vector<uint64_t> ids((size_t)n);
     ck(grid->ctx, xnb_get_particles(grid->ctx, 0, n, f[0].data(), f[1].data(), f[2].data(), f[3].data(), f[4].data(), f[5].data(), f[6].data(), f[7].data(), f[8].data(), ids.data(), nullptr, nullptr), "check_values");
+    if (!in)
+    {
+      // no reference file yet: sample `samples` distinct inner particles and write "[id, r, a, v]" rows of hex floats sorted by
+      // id (check_values.cpp:146-212,296-303,363-386; row format core/yaml_check_particles.h:68-87).  The reference draws the
+      // samples from its run-time random engine; a fixed seed makes the file reproducible here.
+      const size_t want = (size_t)std::min<int64_t>(std::max<long>(*samples, 1L), n);
+      std::mt19937_64 re(20240613u);
+      std::set<uint64_t> chosen;
+      std::vector<size_t> rows_q;
+      while (rows_q.size() < want) { const size_t q = (size_t)(re() % (uint64_t)n); if (chosen.insert(ids[q]).second) rows_q.push_back(q); }
+      std::sort(rows_q.begin(), rows_q.end(), [&](size_t a, size_t b) { return ids[a] < ids[b]; });
+      std::ofstream fout(*file);
+      if (!fout) fatal_error("check_values: cannot write '" + *file + "'");
+      char date[64]; { time_t now; time(&now); strftime(date, sizeof date, "%d-%m-%Y %H:%M:%S", localtime(&now)); }
+      fout << "date: '" << date << "'\nlength_unit: 1.0 ang\nvalues:\n";
+      for (size_t q : rows_q)
+      {
+        fout << "- [" << ids[q];
+        const int order[9] = {0, 1, 2, 6, 7, 8, 3, 4, 5};      // r, a, v
+        for (int c : order) { char buf[64]; std::snprintf(buf, sizeof buf, ", %a", f[c][q]); fout << buf; }
+        fout << "]\n";
+      }
+      *max_error = 0.0;
+      std::printf("check_values: wrote %zu reference particles to %s\n", rows_q.size(), file->c_str());
+      return;
+    }
     std::map<uint64_t, size_t> where; for (size_t q = 0; q < (size_t)n; q++) where[ids[q]] = q;
     const Domain& d = *domain;
     const double L[3] = {d.bounds.bmax.x - d.bounds.bmin.x, d.bounds.bmax.y - d.bounds.bmin.y, d.bounds.bmax.z - d.bounds.bmin.z};

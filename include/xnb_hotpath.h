@@ -93,7 +93,7 @@ int xnb_get_grid_info(const xnb_ctx*, xnb_grid_info* out);
    fits shared memory and the sweep reads the streams.                                                             */
 typedef struct xnb_sweep_info
 {
-  int32_t compiled;       /* 1 if the sweep runs over compiled lists                                   */
+  int32_t compiled;       /* 1 if the sweep runs over compiled lists, 2: pair-merged lists (XNB_CL_PAIRED) */
   int32_t ghost;          /* lists compiled for ghost cells too (lennard_jones_force ghost=true)       */
   int64_t tile[3];        /* cells per tile (= per thread block)                                       */
   int64_t threads;        /* threads per block                                                         */
