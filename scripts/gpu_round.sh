@@ -15,3 +15,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lj
 ls -la gpurun_out | tail -20
 ( time timeout 600 python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/${TAG}_bench_ref.log 2>&1
 tail -1 gpurun_out/${TAG}_bench_ref.log | cut -c1-600
+( time timeout 600 python __graft_entry__.py smoke ) > gpurun_out/${TAG}_smoke.log 2>&1
+tail -2 gpurun_out/${TAG}_smoke.log

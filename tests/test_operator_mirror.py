@@ -92,7 +92,7 @@ def test_check_values_writes_then_reads_its_own_file(tmp_path):
     import yaml
     deck = buildlib.build_host()
     f = str(tmp_path / "cv_own.dat")
-    r = subprocess.run([deck, f, "2", "10"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([deck, f, "2", "10", "check"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "check_values: wrote 128 reference particles" in r.stdout
     doc = yaml.safe_load(open(f))                   # the reader tests/test_oracle_kat.py uses for the reference's golden file
@@ -101,7 +101,7 @@ def test_check_values_writes_then_reads_its_own_file(tmp_path):
     ids = [int(x[0]) for x in rows]
     assert len(rows) == 128 and ids == sorted(ids) and len(set(ids)) == 128 and all(len(x) == 10 for x in rows)
     assert all(abs(float.fromhex(v)) < 1e6 for x in rows for v in x[1:])
-    r = subprocess.run([deck, f, "2", "10"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([deck, f, "2", "10", "check"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "check_values: 128 particles within thresholds" in r.stdout
     assert float(r.stdout.split("max abs error")[1].split()[0]) == 0.0
