@@ -117,7 +117,7 @@ struct xnb_ctx
   // ---- AMR
   DBuf<uint8_t> side_lut; double side_lut_density = 0;
   DBuf<uint32_t> sg_size; DBuf<unsigned long long> sub_grid_start; DBuf<uint32_t> sub_grid_cells;
-  int64_t n_sub_grid_cells = 0; uint32_t max_side = 1;
+  int64_t n_sub_grid_cells = 0; uint32_t max_side = 1; bool amr_current = false;   // amr_current: the tables describe the present in-cell order
   // ---- ghosts
   std::vector<int> send_first, recv_first;            // per partner rank [nranks+1] ranges into the item arrays
   int n_send_items = 0, n_recv_items = 0;
@@ -537,7 +537,7 @@ int xnb_set_particles(xnb_ctx* c, int64_t n, const double* rx, const double* ry,
   std::vector<unsigned long long> ids(m); std::vector<uint8_t> ty(m);
   for (size_t k = 0; k < m; k++) { ids[k] = id ? id[keep[k]] : (unsigned long long)keep[k]; ty[k] = type ? type[keep[k]] : 0; }
   if (m) { CK(cudaMemcpy(c->idb[c->cur].p, ids.data(), m * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(c->typeb[c->cur].p, ty.data(), m, cudaMemcpyHostToDevice)); }
-  c->n_inner = (int64_t)m; c->n_total = (int64_t)m; c->have_nbh = false; c->n_ghost = 0;
+  c->n_inner = (int64_t)m; c->n_total = (int64_t)m; c->have_nbh = false; c->n_ghost = 0; c->amr_current = false;
   return XNB_OK;
 }
 
@@ -562,6 +562,7 @@ int xnb_upload_rv(xnb_ctx* c, const double* rx, const double* ry, const double* 
 {
   if (!c) return XNB_ERR_INVALID;
   CK(cudaSetDevice(c->device));
+  c->amr_current = false;      // positions change: the sub-cell tables no longer bound them
   cudaStream_t st = (cudaStream_t)stream;
   const double* src[6] = {rx, ry, rz, vx, vy, vz};
   for (int f = 0; f < 6; f++) if (src[f] && c->n_inner) CK(cudaMemcpyAsync(c->f64[c->cur][f].p, src[f], (size_t)c->n_inner * 8, cudaMemcpyHostToDevice, st));
@@ -700,7 +701,7 @@ int xnb_move_particles(xnb_ctx* c, void* stream)
   ParticlesP B = c->P(1 - c->cur);
   if (n_new) LAUNCH(k_gather, nblk(n_new, 256), 256, st, (int)n_new, c->perm2.p, A, B, c->key.p, c->atom_cell[1 - c->cur_ac].p);
   c->cur = 1 - c->cur; c->cur_ac = 1 - c->cur_ac;
-  c->n_inner = n_new; c->n_total = n_new; c->n_ghost = 0; c->have_nbh = false;
+  c->n_inner = n_new; c->n_total = n_new; c->n_ghost = 0; c->have_nbh = false; c->amr_current = false;
   LAUNCH(k_ghost_cells_clear, nblk(g.n_cells, 256), 256, st, g, (uint32_t)n_new, c->cell_start.p, c->cell_count.p);
   return check_device_errors(c, st);
 }
@@ -722,7 +723,7 @@ int xnb_rebuild_amr(xnb_ctx* c, void* stream)
   uint32_t ms = 0; unsigned long long tot = 0;
   rc = read_back(c, s32 + 2, 1, &ms, st); if (rc) return rc;
   rc = read_back(c, c->d_scalars64.p + 1, 1, &tot, st); if (rc) return rc;
-  c->max_side = std::max(ms, 1u); c->n_sub_grid_cells = (int64_t)tot;
+  c->max_side = std::max(ms, 1u); c->n_sub_grid_cells = (int64_t)tot; c->amr_current = true;
   if (ms <= 1) return XNB_OK;          // every cell has a 1x1x1 sub grid: nothing to reorder (C2/C3)
   const int64_t n = c->n_inner;
   CK(c->sub_grid_cells.ensure((size_t)tot + 16));
@@ -1106,7 +1107,12 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
     if (tiled) return c->fail(XNB_ERR_CAPACITY, "chunk_neighbors: tiled build did not converge");
   }
   // ---- per-particle two-pass form (count -> sizes -> scan -> fill)
-  if (n) LAUNCH((k_nbh_build<false>), nblk(n, 128), 128, st, g, (int)n, gap, md2, (int)c->nbh_half_symmetric, (int)c->nbh_skip_ghosts, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
+  // the AMR tables prune whole sub-cells when they describe the current in-cell order (rebuild_amr ran after the last binning)
+  const bool prune = c->amr_current && c->max_side > 1 && c->sub_grid_cells.p && !env_flag("XNB_NBH_NO_SUBCELLS");
+  const unsigned long long* sgs_prune = prune ? c->sub_grid_start.p : nullptr;
+  const uint32_t* sgc_prune = prune ? c->sub_grid_cells.p : nullptr;
+  if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] two-pass neighbour build: %lld particles, sub-cell pruning %s (max side %u, tables current %d)\n", (long long)n, prune ? "on" : "off", c->max_side, (int)c->amr_current);
+  if (n) LAUNCH((k_nbh_build<false>), nblk(n, 128), 128, st, g, (int)n, gap, md2, (int)c->nbh_half_symmetric, (int)c->nbh_skip_ghosts, sgs_prune, sgc_prune, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
   CK(cudaMemsetAsync(s32 + 3, 0, 16, st)); CK(cudaMemsetAsync(s32 + 109, 0, 8, st)); CK(cudaMemsetAsync(c->d_scalars64.p + 2, 0, 8, st));
   LAUNCH(k_nbh_cell_sizes, nblk((int64_t)g.n_cells * 32, 128), 128, st, g, g.n_cells, c->cell_start.p, c->cell_count.p, c->nb_len.p, c->nb_cnt.p, c->nb_off.p,
          c->stream_size.p, c->stream_size_padded.p, s32 + 3, s32 + 5, s32 + 6, s32 + 109, c->d_scalars64.p + 2, s32);
@@ -1123,7 +1129,7 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
   // realloc_stream_pool (chunk_neighbors.h:70-96): grow with the reference's 5% head-room (update-particles.msp:20)
   CK(c->pool.ensure((size_t)tot + 64, 0, 1.05));
   LAUNCH(k_nbh_pointers, nblk(g.n_cells, 256), 256, st, g.n_cells, c->pool.p, c->stream_off.p, c->stream_size.p, c->cell_stream.p, c->cell_stream_bytes.p);
-  if (n) LAUNCH((k_nbh_build<true>), nblk(n, 128), 128, st, g, (int)n, gap, md2, (int)c->nbh_half_symmetric, (int)c->nbh_skip_ghosts, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
+  if (n) LAUNCH((k_nbh_build<true>), nblk(n, 128), 128, st, g, (int)n, gap, md2, (int)c->nbh_half_symmetric, (int)c->nbh_skip_ghosts, sgs_prune, sgc_prune, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
   c->have_nbh = true;
   if ((rc = cl_prepare(c, false, st))) return rc;
   if ((rc = t_end(c, XNB_T_NBH, st))) return rc;
@@ -1386,6 +1392,7 @@ int xnb_push_f_v_r(xnb_ctx* c, double dt, double dt_scale, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
   CK(cudaSetDevice(c->device));
+  c->amr_current = false;      // positions change: the sub-cell tables no longer bound them
   cudaStream_t st = (cudaStream_t)stream;
   ParticlesP A = c->P(c->cur);
   const double delta_t = dt * dt_scale, delta_t2 = delta_t * delta_t * 0.5;     // push_vec3_2nd_order.h:87-88
@@ -1432,6 +1439,7 @@ int xnb_verlet_first_half(xnb_ctx* c, double dt, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
   CK(cudaSetDevice(c->device));
+  c->amr_current = false;      // positions change: the sub-cell tables no longer bound them
   cudaStream_t st = (cudaStream_t)stream;
   ParticlesP A = c->P(c->cur);
   int rc;
@@ -1586,6 +1594,7 @@ int xnb_step_host(xnb_ctx* c, double dt, double eps, double sig, double rcut,
     CK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_d2h_go, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_d2h_done, cudaEventDisableTiming));
   }
+  c->amr_current = false;
   const size_t n = (size_t)c->n_inner;
   for (int f = 0; f < 3; f++)
   {

@@ -542,6 +542,7 @@ struct NbhOut
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_nbh_build(GridP g, int n_total, int gap, double max_dist2, int half_symmetric, int skip_ghosts,
+            const unsigned long long* __restrict__ sub_grid_start, const uint32_t* __restrict__ sub_grid_cells,
             const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
             const uint32_t* __restrict__ atom_cell, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
             NbhOut out, uint32_t* __restrict__ err)
@@ -551,6 +552,7 @@ k_nbh_build(GridP g, int n_total, int gap, double max_dist2, int half_symmetric,
   const uint32_t ca = atom_cell[i];
   const int ai = ca % g.dims[0], aj = (ca / g.dims[0]) % g.dims[1], ak = ca / (g.dims[0] * g.dims[1]);
   const double xa = rx[i], ya = ry[i], za = rz[i];
+  const double nbh_reach = sub_grid_start ? sqrt(max_dist2) : 0.0;
   uint16_t* w = nullptr;
   if (FILL)
   {
@@ -582,15 +584,49 @@ k_nbh_build(GridP g, int n_total, int gap, double max_dist2, int half_symmetric,
         const uint32_t sb = cell_start[cb];
         uint32_t cnt = 0;
         uint16_t* wc = w;      // group header position (enc, n)
-        for (uint32_t pb = 0; pb < nb; pb++)
+        // sub-cells of cell b (AmrGrid, amr_grid.h:31-61): the particles of a cell are stored sub-cell after sub-cell, so a
+        // sub-cell whose box lies farther than the list radius from r_a is skipped as a whole.  This only prunes (the role of the
+        // reference's AmrSubCellPairCache, amr_grid_algorithm.cpp:102-218): membership is still decided by the exact test below,
+        // and sub-cells are visited in ascending order, i.e. ascending p_b.
+        uint32_t nsub = 1u, side = 1u; unsigned long long sg0 = 0ull;
+        if (sub_grid_start) { sg0 = sub_grid_start[cb]; nsub = (uint32_t)(sub_grid_start[cb + 1] - sg0) + 1u; while (side * side * side < nsub) side++; }
+        // per axis, the sub-cell indices of cell b whose slab lies within the list radius of r_a (a box around the sphere; integer
+        // tests per sub-cell, the sub-cells stay in lockstep across the warp so that the candidate loads remain broadcasts)
+        int slo[3] = {0, 0, 0}, shi[3] = {0, 0, 0};
+        if (nsub > 1u)
         {
-          const uint32_t j = sb + pb;
-          // :225-227  dr = r_a - r_b ; d2 = |dr|^2 ; keep if not self, d2 > 0, d2 <= max_dist^2
-          const double d2 = norm2_exact(__dadd_rn(xa, -rx[j]), __dadd_rn(ya, -ry[j]), __dadd_rn(za, -rz[j]));
-          if (j != (uint32_t)i && d2 > 0.0 && d2 <= max_dist2)
+          double box[3]; cell_origin(g, (uint32_t)cb, box[0], box[1], box[2]);
+          const double inv_h = (double)side / g.cs, reach = nbh_reach + 1e-9 * g.cs;
+          const double ra[3] = {xa, ya, za};
+#pragma unroll
+          for (int d = 0; d < 3; d++)
           {
-            if (FILL) wc[2 + cnt] = (uint16_t)pb;
-            cnt++;
+            const double rel = ra[d] - box[d];
+            slo[d] = max((int)floor((rel - reach) * inv_h), 0); shi[d] = min((int)floor((rel + reach) * inv_h), (int)side - 1);
+          }
+        }
+        uint32_t si = 0u, sj = 0u, sk = 0u;
+        for (uint32_t sc = 0; sc < nsub; sc++)
+        {
+          uint32_t p0 = 0u, p1 = nb;
+          if (nsub > 1u)
+          {
+            const bool in_box = (int)si >= slo[0] && (int)si <= shi[0] && (int)sj >= slo[1] && (int)sj <= shi[1] && (int)sk >= slo[2] && (int)sk <= shi[2];
+            if (++si == side) { si = 0u; if (++sj == side) { sj = 0u; ++sk; } }
+            if (!in_box) continue;
+            p0 = sc > 0u ? sub_grid_cells[sg0 + sc - 1u] : 0u;
+            p1 = min(sc + 1u < nsub ? sub_grid_cells[sg0 + sc] : nb, nb);
+          }
+          for (uint32_t pb = p0; pb < p1; pb++)
+          {
+            const uint32_t j = sb + pb;
+            // :225-227  dr = r_a - r_b ; d2 = |dr|^2 ; keep if not self, d2 > 0, d2 <= max_dist^2
+            const double d2 = norm2_exact(__dadd_rn(xa, -rx[j]), __dadd_rn(ya, -ry[j]), __dadd_rn(za, -rz[j]));
+            if (j != (uint32_t)i && d2 > 0.0 && d2 <= max_dist2)
+            {
+              if (FILL) wc[2 + cnt] = (uint16_t)pb;
+              cnt++;
+            }
           }
         }
         if (cnt > 0)
