@@ -1228,6 +1228,9 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
 {
   ParticlesP A = c->P(c->cur);
   int rc;
+  // a full-list sweep over half_symmetric lists would apply every pair to one of its two particles only (the reference's operator
+  // does exactly that, silently); here it is an error: use xnb_lennard_jones_force_symmetric + xnb_update_force_from_ghost
+  if (c->nbh_half_symmetric) return c->fail(XNB_ERR_INVALID, "the full-list pair sweep needs full lists: chunk_neighbors was configured half_symmetric");
   if (c->cl.ghost != ghost) { if ((rc = cl_prepare(c, ghost, st))) return rc; c->cl.ghost = ghost; }
   if (c->cl.valid)
   {

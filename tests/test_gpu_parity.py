@@ -335,6 +335,8 @@ def test_newton3_path(case):
         ctx.lennard_jones_force_symmetric(eps, sig, rc)            # the full lists are void now
     ctx.chunk_neighbors()
     assert int(ctx.streams()[0].sum()) < n_full
+    with pytest.raises(Exception):
+        ctx.lennard_jones_force(eps, sig, rc)                      # ... and the full-list sweep refuses half lists
     for functor in (0, 1):
         ctx.set_pair_functor(functor)
         ctx.zero_particle_force(ghost=True); ctx.lennard_jones_force_symmetric(eps, sig, rc); ctx.update_force_from_ghost(); ctx.divide_force_by_mass()
