@@ -119,3 +119,19 @@ study("Morton-consecutive, groups as stored", pairs_morton, False)
 study("Morton-consecutive, length-balanced", pairs_morton, True)
 study("closest-first matching, as stored", pairs_greedy, False)
 study("closest-first matching, balanced", pairs_greedy, True)
+
+
+def rows_unpaired_sorted():
+    """the unpaired layout with a tile's particles ordered by list length before groups of 32 are formed"""
+    tot = 0
+    for cells in tiles.values():
+        parts = np.concatenate([order[start[c]:start[c + 1]] for c in cells])
+        l = np.sort(ln[parts])[::-1]
+        for g in range(0, len(l), 32):
+            tot += -(-l[g:g + 32].max() // 4)
+    return tot
+
+
+sr = rows_unpaired_sorted()
+ideal = sum(-(-int(ln[np.concatenate([order[start[c]:start[c + 1]] for c in cells])].sum()) // 128) for cells in tiles.values())
+print("unpaired, groups formed by list length: padded entries per particle %.1f (as stored %.1f, no padding at all %.1f)" % (sr * 128 / n, base_rows * 128 / n, ideal * 128 / n))
