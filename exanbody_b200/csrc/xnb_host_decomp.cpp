@@ -4,6 +4,7 @@
 #include "../../include/xnb_hotpath.h"
 #include "xnb_host_decomp.hpp"
 #include <algorithm>
+#include <vector>
 
 namespace xnb {
 
@@ -21,6 +22,83 @@ Block simple_block_rcb(Block b, size_t n_parts, size_t part)
     if (d[0] >= d[1] && d[0] >= d[2]) ax = 0; else if (d[1] >= d[0] && d[1] >= d[2]) ax = 1;
     if (side) b.s[ax] = b.s[ax] + d[ax] / 2; else b.e[ax] = b.s[ax] + d[ax] / 2;
     if (side) { part -= pivot; n_parts -= pivot; } else n_parts = pivot;
+  }
+  return b;
+}
+
+// ---- cost-weighted recursive bisection (load_balance_rcb.cpp, non-Zoltan path) ---------------------------------------------
+namespace {
+struct Split1D { size_t position = 0; double worst_balance = 0.0; long surf = 0; int axis = 0; bool valid = false; };
+
+// :510-545  best cut of a 1-D cost profile between `left` and `right` ranks: minimise max(cost_left/left, cost_right/right)
+Split1D best_split(const std::vector<double>& v, size_t left, size_t right)
+{
+  Split1D r;
+  const size_t n = v.size();
+  double sum_right = 0., sum_left = 0.;
+  for (double x : v) sum_right += x;
+  if (n == 0) { r.position = 0; r.worst_balance = sum_right; return r; }
+  if (right == 0) { r.position = n - 1; r.worst_balance = sum_right / (double)n; return r; }
+  if (left == 0) { r.position = 0; r.worst_balance = sum_right / (double)n; return r; }
+  double best = sum_right / (double)right; size_t best_p = 0;
+  for (size_t p = 1; p < n; p++)
+  {
+    sum_left += v[p - 1]; sum_right -= v[p - 1];
+    const double wb = std::max(sum_left / (double)left, sum_right / (double)right);
+    if (wb < best) { best = wb; best_p = p; }
+  }
+  r.position = best_p; r.worst_balance = best; r.surf = -1; r.axis = -1;
+  return r;
+}
+} // namespace
+
+Block load_balance_rcb(const int64_t ddims[3], const double* costs, size_t n_parts, size_t part)
+{
+  Block b{{0, 0, 0}, {ddims[0], ddims[1], ddims[2]}};
+  size_t group = n_parts, rank_in_group = part;
+  auto empty = [](const Block& q) { return q.e[0] <= q.s[0] || q.e[1] <= q.s[1] || q.e[2] <= q.s[2]; };
+  while (group > 1 && !empty(b))                                       // :285
+  {
+    const int64_t d[3] = {b.e[0] - b.s[0], b.e[1] - b.s[1], b.e[2] - b.s[2]};
+    std::vector<double> prof[3] = {std::vector<double>((size_t)d[0], 0.), std::vector<double>((size_t)d[1], 0.), std::vector<double>((size_t)d[2], 0.)};
+    for (int64_t k = 0; k < d[2]; k++) for (int64_t j = 0; j < d[1]; j++) for (int64_t i = 0; i < d[0]; i++)      // :293-306 cost profiles of the block
+    {
+      const double c = costs[((b.s[2] + k) * ddims[1] + (b.s[1] + j)) * ddims[0] + (b.s[0] + i)];
+      prof[0][(size_t)i] += c; prof[1][(size_t)j] += c; prof[2][(size_t)k] += c;
+    }
+    const size_t left = group / 2, right = group - left;               // :313-326
+    const bool side = rank_in_group >= left;
+    Split1D sp[3];
+    for (int a = 0; a < 3; a++)                                          // :332-349
+    {
+      sp[a] = best_split(prof[a], left, right);
+      sp[a].surf = (long)(d[(a + 1) % 3] * d[(a + 2) % 3]);
+      sp[a].valid = d[a] >= 2 && sp[a].position > 0 && (int64_t)sp[a].position < d[a];
+      sp[a].axis = a;
+    }
+    // :351-362  the better balanced cut wins; within 5 % of each other the smaller cut surface wins (same comparator, same std::sort)
+    auto better = [](const Split1D& x, const Split1D& y) -> bool
+    {
+      if (!x.valid) return false;
+      if (!y.valid) return true;
+      const double mx = std::max(x.worst_balance, y.worst_balance);
+      if (mx == 0.0) return true;
+      const double mn = std::min(x.worst_balance, y.worst_balance);
+      if (mn / mx > 0.95) return x.surf < y.surf;
+      return x.worst_balance < y.worst_balance;
+    };
+    std::sort(sp, sp + 3, better);
+    Block lb = b, rb = b;
+    if (sp[0].valid) { lb.e[sp[0].axis] = b.s[sp[0].axis] + (int64_t)sp[0].position; rb.s[sp[0].axis] = lb.e[sp[0].axis]; }      // :368-388
+    else
+    {
+      // :389-412  no cut balances anything (e.g. zero costs): halve the longest axis (ties: i, then j)
+      int a = 2;
+      if (d[0] >= d[1] && d[0] >= d[2]) a = 0; else if (d[1] >= d[0] && d[1] >= d[2]) a = 1;
+      lb.e[a] = b.s[a] + d[a] / 2; rb.s[a] = lb.e[a];
+    }
+    b = side ? rb : lb;                                                  // :428-440
+    if (side) { rank_in_group -= left; group = right; } else group = left;
   }
   return b;
 }
@@ -68,6 +146,18 @@ void enumerate_sends(const std::vector<Block>& blocks, const int64_t ddims[3], c
 }
 
 } // namespace xnb
+
+extern "C" int xnb_host_load_balance_rcb(const int64_t grid_dims[3], const double* cell_costs, int nranks, int rank, int64_t start[3], int64_t end[3],
+                                         double* block_cost)
+{
+  if (!grid_dims || !cell_costs || !start || !end || nranks < 1 || rank < 0 || rank >= nranks || grid_dims[0] < 1 || grid_dims[1] < 1 || grid_dims[2] < 1) return XNB_ERR_INVALID;
+  const xnb::Block b = xnb::load_balance_rcb(grid_dims, cell_costs, (size_t)nranks, (size_t)rank);
+  double cost = 0.0;
+  for (int64_t k = b.s[2]; k < b.e[2]; k++) for (int64_t j = b.s[1]; j < b.e[1]; j++) for (int64_t i = b.s[0]; i < b.e[0]; i++) cost += cell_costs[(k * grid_dims[1] + j) * grid_dims[0] + i];
+  for (int d = 0; d < 3; d++) { start[d] = b.s[d]; end[d] = b.e[d]; }
+  if (block_cost) *block_cost = cost;        // :443-452 feeds lb_inbalance = (max - avg) / avg over the ranks
+  return XNB_OK;
+}
 
 extern "C" int xnb_host_rcb_block(const int64_t grid_dims[3], int nranks, int rank, int64_t start[3], int64_t end[3])
 {

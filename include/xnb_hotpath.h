@@ -239,6 +239,13 @@ int64_t xnb_host_lattice_fcc(const xnb_lattice_cfg* cfg, int64_t capacity, doubl
 /* ---- static decomposition, host only (no CUDA): what every rank derives for itself and its partners -------------- */
 /* src/core/lib/simple_block_rcb.cpp:27-59 (via init_rcb_grid.cpp:65-77): block [start,end) of `rank` among `nranks` */
 int xnb_host_rcb_block(const int64_t grid_dims[3], int nranks, int rank, int64_t start[3], int64_t end[3]);
+/* host half of op `load_balance_rcb` (src/mpi/load_balance_rcb.cpp:228-452,510-545, the path without Zoltan; SURVEY.md 8f
+   rank 1): cost-weighted recursive bisection of the domain cell grid.  cell_costs = the all-reduced cost of every domain
+   cell, index (k*dj + j)*di + i (CellCosts, e.g. simple_cost_model).  Every rank calls it with the same costs and obtains
+   its own block; *block_cost (may be NULL) = the cost inside it, from which lb_inbalance = (max - avg)/avg follows.
+   Applying a new block to a live xnb_ctx (re-partition + migration) is not implemented yet.                          */
+int xnb_host_load_balance_rcb(const int64_t grid_dims[3], const double* cell_costs, int nranks, int rank,
+                              int64_t start[3], int64_t end[3], double* block_cost);
 /* src/mpi/update_ghosts_comm_scheme.cpp:168-196,429-443: the cells rank `from` sends to rank `to` (sender local cell,
    receiver local ghost cell, GhostBoundaryModifier flags, ghosts_comm_scheme.h:46-81), in the reference's order.
    Returns the item count (arrays are filled when capacity suffices); -1 on invalid arguments.                     */
