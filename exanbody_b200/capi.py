@@ -23,7 +23,7 @@ SYMBOLS = [
     "xnb_read_displ_over", "xnb_force_and_second_half", "xnb_run_steps", "xnb_step_host", "xnb_first_iteration", "xnb_energy_virial",
     "xnb_view_chunk_neighbors", "xnb_stream_pool_u16", "xnb_get_streams", "xnb_get_amr", "xnb_get_backup",
     "xnb_rebuild_count", "xnb_kernel_launches", "xnb_timing_enable", "xnb_timing_read", "xnb_measure_dfma_peak",
-    "xnb_host_lattice_fcc", "xnb_host_rcb_block", "xnb_host_load_balance_rcb", "xnb_host_ghost_items",
+    "xnb_host_lattice_fcc", "xnb_host_rcb_block", "xnb_host_load_balance_rcb", "xnb_host_simple_cost_model", "xnb_host_ghost_items",
 ]
 
 
@@ -86,7 +86,8 @@ def load():
         "xnb_view_chunk_neighbors": (I, [P, P, P, P]), "xnb_stream_pool_u16": (I64, [P]), "xnb_get_streams": (I, [P, P, P]),
         "xnb_get_amr": (I64, [P, P, P]), "xnb_get_backup": (I, [P, P]), "xnb_rebuild_count": (I64, [P]), "xnb_kernel_launches": (I64, [P]),
         "xnb_host_lattice_fcc": (I64, [C.POINTER(XnbLatticeCfg), I64] + [P] * 8),
-        "xnb_host_rcb_block": (I, [P, I, I, P, P]), "xnb_host_load_balance_rcb": (I, [P, P, I, I, P, P, P]), "xnb_host_ghost_items": (I64, [P, P, I, I, I, I, I64, P, P, P]),
+        "xnb_host_rcb_block": (I, [P, I, I, P, P]), "xnb_host_load_balance_rcb": (I, [P, P, I, I, P, P, P]),
+        "xnb_host_simple_cost_model": (I, [I64, P, D, P, P]), "xnb_host_ghost_items": (I64, [P, P, I, I, I, I, I64, P, P, P]),
         "xnb_timing_enable": (I, [P, I]), "xnb_timing_read": (I, [P, P, P, I]), "xnb_measure_dfma_peak": (I, [I, P]),
     }
     for name, (res, args) in sig.items():
@@ -359,6 +360,16 @@ def rcb_block(grid_dims, nranks, rank):
     if rc:
         raise XnbError(rc, "xnb_host_rcb_block")
     return s, e
+
+
+def simple_cost_model(cell_count, cell_size, coefs=(0.0, 0.0, 1.0, 0.0)):
+    """op simple_cost_model, arithmetic only: per-cell cost from the particle counts"""
+    L = load()
+    cnt = np.ascontiguousarray(cell_count, np.uint32); co = np.ascontiguousarray(coefs, np.float64); out = np.zeros(cnt.size, np.float64)
+    rc = L.xnb_host_simple_cost_model(cnt.size, _p(cnt), float(cell_size), _p(co), _p(out))
+    if rc:
+        raise XnbError(rc, "xnb_host_simple_cost_model")
+    return out
 
 
 def load_balance_rcb(grid_dims, cell_costs, nranks, rank):

@@ -147,6 +147,20 @@ void enumerate_sends(const std::vector<Block>& blocks, const int64_t ddims[3], c
 
 } // namespace xnb
 
+extern "C" int xnb_host_simple_cost_model(int64_t n_cells, const uint32_t* cell_count, double cell_size, const double coefs[4], double* cell_costs)
+{
+  // simple_cost_model.h:67-146: p = N / cell volume ; cost = coefs[0] p^3 + coefs[1] p^2 + coefs[2] p + coefs[3]   (defaults {0, 0, 1, 0})
+  if (n_cells < 0 || (n_cells > 0 && (!cell_count || !cell_costs)) || !coefs || !(cell_size > 0.0)) return XNB_ERR_INVALID;
+  const double d3 = coefs[0], d2 = coefs[1], d1 = coefs[2], cc = coefs[3];
+  const double cell_volume = cell_size * cell_size * cell_size;
+  for (int64_t c = 0; c < n_cells; c++)
+  {
+    const double pvol = (double)cell_count[c] / cell_volume;
+    cell_costs[c] = pvol * d1 + pvol * pvol * d2 + pvol * pvol * pvol * d3 + cc;
+  }
+  return XNB_OK;
+}
+
 extern "C" int xnb_host_load_balance_rcb(const int64_t grid_dims[3], const double* cell_costs, int nranks, int rank, int64_t start[3], int64_t end[3],
                                          double* block_cost)
 {

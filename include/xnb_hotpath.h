@@ -239,6 +239,11 @@ int64_t xnb_host_lattice_fcc(const xnb_lattice_cfg* cfg, int64_t capacity, doubl
 /* ---- static decomposition, host only (no CUDA): what every rank derives for itself and its partners -------------- */
 /* src/core/lib/simple_block_rcb.cpp:27-59 (via init_rcb_grid.cpp:65-77): block [start,end) of `rank` among `nranks` */
 int xnb_host_rcb_block(const int64_t grid_dims[3], int nranks, int rank, int64_t start[3], int64_t end[3]);
+/* op `simple_cost_model` (src/mpi/include/exanb/mpi/simple_cost_model.h:67-146), arithmetic only: cost of a cell from its
+   particle count, p = N / cell_size^3, cost = coefs[0] p^3 + coefs[1] p^2 + coefs[2] p + coefs[3] (the reference's default
+   coefficients are {0, 0, 1, 0}).  Feed it the inner-cell counts of xnb_get_cells; ghost cells carry no cost (:103).  */
+int xnb_host_simple_cost_model(int64_t n_cells, const uint32_t* cell_count, double cell_size, const double coefs[4],
+                               double* cell_costs);
 /* host half of op `load_balance_rcb` (src/mpi/load_balance_rcb.cpp:228-452,510-545, the path without Zoltan; SURVEY.md 8f
    rank 1): cost-weighted recursive bisection of the domain cell grid.  cell_costs = the all-reduced cost of every domain
    cell, index (k*dj + j)*di + i (CellCosts, e.g. simple_cost_model).  Every rank calls it with the same costs and obtains

@@ -163,3 +163,28 @@ def test_ranks_derive_a_consistent_partition(world):
     for p in procs:
         p.join(60)
     assert all(r[1] == "ok" for r in res), res
+
+
+def test_simple_cost_model_and_the_chain_to_blocks():
+    """simple_cost_model.h:143-145: cost = d1 p + d2 p^2 + d3 p^3 + cc with p = N / cell volume; chained into the bisection, a dense
+    slab is shared evenly where the static, cost-blind blocks leave one rank with most of it"""
+    cnt = np.array([0, 1, 32, 256], np.uint32)
+    cs = 2.0
+    p = cnt / cs ** 3
+    assert np.array_equal(capi.simple_cost_model(cnt, cs), p)                                   # default coefficients {0, 0, 1, 0}
+    co = (0.5, 0.25, 2.0, 3.0)
+    assert np.allclose(capi.simple_cost_model(cnt, cs, co), p * 2.0 + p * p * 0.25 + p ** 3 * 0.5 + 3.0, rtol=1e-15, atol=0)
+    with pytest.raises(capi.XnbError):
+        capi.simple_cost_model(cnt, 0.0)
+    dims = (16, 4, 4)
+    counts = np.full(dims[::-1], 2, np.uint32); counts[:, :, :4] = 60                             # a dense slab at low i
+    costs = capi.simple_cost_model(counts.ravel(), cs)
+    blocks = [capi.load_balance_rcb(dims, costs, 4, r) for r in range(4)]
+    bc = np.array([c for _, _, c in blocks])
+    assert (bc.max() - bc.mean()) / bc.mean() < 0.05                                            # cuts across the slab balance it exactly
+    c3 = costs.reshape(dims[::-1]); static = []
+    for r in range(4):
+        s, e = capi.rcb_block(dims, 4, r)
+        static.append(c3[s[2]:e[2], s[1]:e[1], s[0]:e[0]].sum())
+    static = np.array(static)
+    assert (static.max() - static.mean()) / static.mean() > 0.5                                 # the cost-blind blocks do not
