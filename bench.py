@@ -8,8 +8,8 @@ rebuilds included whenever the displacement trigger fires.  N=1 runs C2 (2 048 0
 GPU, spatial decomposition, NCCL halo) under torchrun.  Prints ONE JSON line (rank 0).
 
   value     device-resident rate: atoms(all ranks) * K / max-over-ranks CUDA-event time of the K steps
-  e2e       the same steps driven through the C-ABI with HOST buffers: every step uploads r,v from pinned host memory,
-            runs the step and downloads r,v,f (+ids) -- copies inside the timed region
+  e2e       the same steps driven through the C-ABI with HOST buffers (one xnb_step_host call per step): r,v go up from pinned
+            host memory, the step runs, r,v,f come back (ids too on the steps that rebuild) -- copies inside the timed region
   roofline  the dominant kernel (pair sweep k_lj_sweep_cl): algorithmic bytes per launch / its mean CUDA-event duration
   cpu_baseline  the CPU oracle (oracle/, the OpenMP restatement of the reference) on a bounded sample of the same workload
 
