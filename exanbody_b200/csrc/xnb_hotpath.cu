@@ -693,13 +693,14 @@ int xnb_move_particles(xnb_ctx* c, void* stream)
   const int64_t n_new = n - n_leave + n_arrive;
   CK(c->perm.ensure((size_t)n_src + 16, 0, 1.2)); CK(c->perm2.ensure((size_t)n_src + 16, 0, 1.2));
   rc = scan_exclusive<uint32_t, uint32_t>(c, c->cell_count.p, c->cell_start.p, (size_t)g.n_cells, (uint32_t*)nullptr, c->scan_tmp32, st); if (rc) return rc;
+  CK(cudaMemsetAsync(c->perm2.p, 0xFF, ((size_t)n_src + 16) * 4, st));      // sentinel: slots no kernel fills (error paths) are skipped by k_gather
   if (n_src) LAUNCH(k_bin_scatter, nblk(n_src, 256), 256, st, (int)n_src, c->key.p, c->rnk.p, c->cell_start.p, c->perm.p);
   LAUNCH((k_cell_sort<false>), (unsigned)g.n_cells, CELLSORT_THREADS, st, g, c->cell_start.p, c->cell_count.p, c->perm.p, c->perm2.p,
          A.rx, A.ry, A.rz, A.id, c->side_lut.p, (const unsigned long long*)nullptr, (uint32_t*)nullptr, s32);
   rc = ensure_particle_capacity(c, (size_t)std::max<int64_t>(n_new, 1), (size_t)n_src); if (rc) return rc;
   A = c->P(c->cur);
   ParticlesP B = c->P(1 - c->cur);
-  if (n_new) LAUNCH(k_gather, nblk(n_new, 256), 256, st, (int)n_new, c->perm2.p, A, B, c->key.p, c->atom_cell[1 - c->cur_ac].p);
+  if (n_new) LAUNCH(k_gather, nblk(n_new, 256), 256, st, (int)n_new, (uint32_t)n_src, c->perm2.p, A, B, c->key.p, c->atom_cell[1 - c->cur_ac].p);
   c->cur = 1 - c->cur; c->cur_ac = 1 - c->cur_ac;
   c->n_inner = n_new; c->n_total = n_new; c->n_ghost = 0; c->have_nbh = false; c->amr_current = false;
   LAUNCH(k_ghost_cells_clear, nblk(g.n_cells, 256), 256, st, g, (uint32_t)n_new, c->cell_start.p, c->cell_count.p);
@@ -732,7 +733,7 @@ int xnb_rebuild_amr(xnb_ctx* c, void* stream)
   LAUNCH(k_iota, nblk(n, 256), 256, st, (int)n, c->perm.p);
   LAUNCH((k_cell_sort<true>), (unsigned)g.n_cells, CELLSORT_THREADS, st, g, c->cell_start.p, c->cell_count.p, c->perm.p, c->perm2.p,
          A.rx, A.ry, A.rz, A.id, c->side_lut.p, c->sub_grid_start.p, c->sub_grid_cells.p, s32);
-  LAUNCH(k_gather, nblk(n, 256), 256, st, (int)n, c->perm2.p, A, B, c->atom_cell[c->cur_ac].p, c->atom_cell[1 - c->cur_ac].p);
+  LAUNCH(k_gather, nblk(n, 256), 256, st, (int)n, (uint32_t)n, c->perm2.p, A, B, c->atom_cell[c->cur_ac].p, c->atom_cell[1 - c->cur_ac].p);
   c->cur = 1 - c->cur; c->cur_ac = 1 - c->cur_ac;
   return XNB_OK;
 }

@@ -258,12 +258,15 @@ __global__ void k_amr_sizes(GridP g, const uint32_t* __restrict__ cell_count, co
 }
 
 // gather all particle fields through a permutation (dest j takes source perm[j]); also writes atom_cell
-__global__ void k_gather(int n, const uint32_t* __restrict__ perm, ParticlesP src, ParticlesP dst,
+// (n_src: entries of the source arrays; a slot whose perm entry was never written -- error paths: lost particles,
+// in-cell sort capacity -- holds the 0xFFFFFFFF sentinel and is skipped, the error word tells the host)
+__global__ void k_gather(int n, uint32_t n_src, const uint32_t* __restrict__ perm, ParticlesP src, ParticlesP dst,
                          const uint32_t* __restrict__ key_src, uint32_t* __restrict__ atom_cell)
 {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const uint32_t s = perm[j];
+  if (s >= n_src) return;
   dst.rx[j] = src.rx[s]; dst.ry[j] = src.ry[s]; dst.rz[j] = src.rz[s];
   dst.vx[j] = src.vx[s]; dst.vy[j] = src.vy[s]; dst.vz[j] = src.vz[s];
   dst.fx[j] = src.fx[s]; dst.fy[j] = src.fy[s]; dst.fz[j] = src.fz[s];

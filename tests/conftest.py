@@ -11,6 +11,30 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
 
 
+_HAVE_GPU = None
+
+
+def have_gpu():
+    """one probe per session through the C-ABI itself: xnb_create answers XNB_ERR_NO_DEVICE on a box without a GPU"""
+    global _HAVE_GPU
+    if _HAVE_GPU is None:
+        try:
+            from exanbody_b200 import capi
+            capi.Context(0).close()
+            _HAVE_GPU = True
+        except Exception:
+            _HAVE_GPU = False
+    return _HAVE_GPU
+
+
+def pytest_collection_modifyitems(config, items):
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if gpu_items and not have_gpu():
+        skip = pytest.mark.skip(reason="no CUDA device (the hot path has no CPU fallback)")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 # Unit constants recovered from the reference's golden file (tests/golden/README.md): with these the oracle reproduces
 # check_values_lj_Ni.dat to 1e-10; onika (not in the reference tree) holds the originals.
 ELEMENTARY_CHARGE = 1.6021892e-19   # C
