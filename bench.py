@@ -175,8 +175,9 @@ def make_oracle_config(kw):
     return O.make_config(**kw)
 
 
-def run_cpu_oracle(kw, nsteps, budget_s):
-    """the CPU oracle on the same workload: init untimed, then up to nsteps steps (stops early when budget_s is spent)."""
+def run_cpu_oracle(kw, nsteps, budget_s, keep=False):
+    """the CPU oracle on the same workload: init untimed, then up to nsteps steps (stops early when budget_s is spent).
+    keep: return the oracle (state after the steps) for the parity check instead of closing it."""
     from oracle import oracle as O
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses every host core the container exposes
     if "XNB_KEEP_OMP" not in os.environ:
@@ -193,8 +194,85 @@ def run_cpu_oracle(kw, nsteps, budget_s):
         if el > budget_s:
             break
     el = time.perf_counter() - t0
-    o.close()
-    return dict(atoms=n, steps=done, seconds=el, rebuilds=rebuilds, rate=n * done / el, threads=O.num_threads())
+    res = dict(atoms=n, steps=done, seconds=el, rebuilds=rebuilds, rate=n * done / el, threads=O.num_threads())
+    if keep:
+        res["oracle"] = o
+    else:
+        o.close()
+    return res
+
+
+def parity_against_oracle(o, steps, rebuilds_oracle, kw, device):
+    """untimed tail: the SAME input stepped the same number of steps by the CUDA path (fresh context) and by the CPU oracle `o`
+    (already stepped): atoms, rebuild count, positions, forces (|df| <= 1e-10 max(|f|, f_rms) is the single-step bar; after
+    `steps` chaotic steps the bound reported is what it is), and the neighbour streams of the final configuration byte for byte
+    (the oracle rebuilds its lists on the GPU's in-cell order first, as tests/test_gpu_parity.py does)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity_util as U
+    eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
+    ctx = U.make_ctx(kw, device=device)
+    ctx.first_iteration(eps, sig, rc)
+    rb = ctx.run_steps(steps, dt, eps, sig, rc)
+    po = U.by_id(o.particles(), o.inner_mask()); pg = U.by_id(ctx.get_particles(0, ctx.n_inner))
+    out = {"steps": steps, "atoms_equal": bool(np.array_equal(po["id"], pg["id"])), "rebuilds": [int(rb), int(rebuilds_oracle)],
+           "rebuilds_equal": int(rb) == int(rebuilds_oracle)}
+    if out["atoms_equal"]:
+        L = np.array(kw["bounds_max"])
+        dr = U.vec(pg, ("rx", "ry", "rz")) - U.vec(po, ("rx", "ry", "rz")); dr -= L * np.round(dr / L)
+        out["max_position_error_over_cell"] = float(np.abs(dr).max() / kw["cell_size"])
+        out["max_force_error"] = float(U.force_error(U.vec(pg, ("fx", "fy", "fz")), U.vec(po, ("fx", "fy", "fz"))))
+        # single-step force parity on IDENTICAL positions: hand the GPU's state to the oracle and let it recompute lists and forces
+        pcell, cnt = U.gpu_particles_cell_order(ctx)
+        o.set_particles(cnt, pcell); o.build_neighbors(); o.compute_force()
+        sz_o, data_o = o.streams(); sz_g, data_g = ctx.streams()
+        out["streams_equal"] = bool(np.array_equal(sz_o, sz_g) and np.array_equal(data_o, data_g))
+        out["stream_words"] = int(np.asarray(sz_g, np.int64).sum())
+        ctx.zero_particle_force(True); ctx.lennard_jones_force(eps, sig, rc); ctx.divide_force_by_mass()
+        po2 = U.by_id(o.particles(), o.inner_mask()); pg2 = U.by_id(ctx.get_particles(0, ctx.n_inner))
+        out["max_force_error_same_positions"] = float(U.force_error(U.vec(pg2, ("fx", "fy", "fz")), U.vec(po2, ("fx", "fy", "fz"))))
+        out["ok"] = bool(out["rebuilds_equal"] and out["streams_equal"] and out["max_force_error_same_positions"] < 1e-10)
+    else:
+        out["ok"] = False
+    ctx.close()
+    return out
+
+
+def short_run(name, device, steps=12, warmup=3):
+    """a short single-GPU run of another BASELINE workload (C1, C4, C5) after the timed region: value, rebuilds, kernel breakdown"""
+    import torch
+    from exanbody_b200 import capi
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity_util as U
+    kw, desc = workload(name)
+    eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
+    ctx = U.make_ctx(kw, device=device)
+    sh = torch.cuda.current_stream().cuda_stream
+    ctx.first_iteration(eps, sig, rc, sh)
+    ctx.run_steps(warmup, dt, eps, sig, rc, sh)
+    ctx.timing_enable(True); ctx.timing_read(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(); rb = ctx.run_steps(steps, dt, eps, sig, rc, sh); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    tim = ctx.timing_read(reset=True); ctx.timing_enable(False)
+    n = ctx.n_inner
+    si = ctx.sweep_info()
+    sz = ctx.stream_sizes()
+    gi = ctx.grid_info(); d, gl = gi["dims"], gi["ghost_layers"]
+    k, j, i = np.meshgrid(np.arange(d[2]), np.arange(d[1]), np.arange(d[0]), indexing="ij")
+    inner = ((i >= gl) & (i < d[0] - gl) & (j >= gl) & (j < d[1] - gl) & (k >= gl) & (k < d[2] - gl)).ravel()
+    S = 2.0 * float(sz[inner].sum()) / max(n, 1)
+    peak, _ = measured_peaks()
+    value = n * steps / (ms * 1e-3)
+    fk = tim["force"]["ms"] / max(tim["force"]["n"], 1)
+    nb = tim["nbh"]["ms"] / max(tim["nbh"]["n"], 1)
+    out = {"workload": desc, "atoms": int(n), "steps": steps, "rebuilds": int(rb), "value": value, "ms_per_step": ms / steps,
+           "sweep_kernel_ms": fk, "nbh_build_ms": nb, "compiled_lists": bool(si["compiled"]), "tile_cells": list(si["tile"]),
+           "list_entries_per_atom": si["candidates"] / max(n, 1) if si["compiled"] else None,
+           "whole_step_hbm_frac": (253.0 + S) * value / 1e9 / peak}
+    ctx.close()
+    return out
+
 
 
 def reference_arm(args):
@@ -325,6 +403,10 @@ def b200_arm(args):
                 "sweep": {"compiled_lists": si["compiled"], "tile_cells": si["tile"], "threads": si["threads"], "blocks": si["blocks"], "smem_bytes": si["smem_bytes"],
                           "list_entries_per_atom": n_list, "compiled_list_bytes_per_atom": (si["rows"] * 256.0 / max(n_atoms_local, 1)) if si["compiled"] else None}}
     breakdown = {k2: (v["ms"] / args.steps) for k2, v in tim.items()}
+    dom = max(breakdown, key=lambda k2: breakdown[k2]) if breakdown else None
+    roofline["dominant_by_time"] = {"group": dom, "ms_per_step": breakdown.get(dom), "share_of_step": (breakdown.get(dom, 0.0) / (ms / args.steps)) if ms > 0 else None,
+                                    "groups": "force = pair sweep, nbh = chunk_neighbors (k_nbh_bits), first_half = verlet_first_half + displacement test, "
+                                              "bin = move_particles + rebuild_amr + backup_r, ghost_scheme / ghost_update = halo"}
 
     # ---- end to end through the C-ABI with host buffers -----------------------------------------------------------------
     n = ctx.n_inner
@@ -363,10 +445,28 @@ def b200_arm(args):
 
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ----------------------------------------------------------------
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = run_cpu_oracle(kw, 20, float(os.environ.get("XNB_CPU_BUDGET_S", "25")))
+        r = run_cpu_oracle(kw, 20, float(os.environ.get("XNB_CPU_BUDGET_S", "25")), keep=not args.no_parity)
         cpu = {"value": r["rate"], "unit": "atom-timesteps/s", "cores": r["threads"], "kind": "port",
                "sample": "CPU oracle (OpenMP port of the reference path), same %d-atom input, %d steps (%d rebuilds) after untimed init" % (r["atoms"], r["steps"], r["rebuilds"])}
+        if "oracle" in r:
+            # parity where the number is quoted: same input, same number of steps, CUDA path against the oracle (untimed)
+            try:
+                parity = parity_against_oracle(r["oracle"], r["steps"], r["rebuilds"], kw, local)
+            except Exception as ex:                                        # never lose the bench line over the checker
+                parity = {"ok": False, "error": repr(ex)[:300]}
+            r["oracle"].close()
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = {}
+        for wl in ("C1", "C4", "C5"):
+            if wl == name:
+                continue
+            try:
+                extra[wl] = short_run(wl, local)
+            except Exception as ex:
+                extra[wl] = {"error": repr(ex)[:300]}
 
     if rank == 0:
         try:
@@ -389,7 +489,7 @@ def b200_arm(args):
             "config": {"workload": desc, "atoms": n_atoms, "rebuilds": rebuilds, "l2": "inputs larger than L2 (state + neighbour streams >> 126 MB), no flush",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "breakdown_ms_per_step": breakdown, "fp64_dfma_peak_tflops": dfma,
+            "breakdown_ms_per_step": breakdown, "fp64_dfma_peak_tflops": dfma, "parity": parity, "extra_workloads": extra,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -407,6 +507,8 @@ def main():
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed comparison of the CUDA path with the CPU oracle on the benchmark input")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE workloads (C1, C4, C5)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -17,7 +17,7 @@ SYMBOLS = [
     "xnb_create", "xnb_destroy", "xnb_last_error", "xnb_version", "xnb_set_domain", "xnb_init_rcb_grid", "xnb_set_nbh_dist",
     "xnb_set_type_mass", "xnb_set_sub_grid_density", "xnb_set_nccl_comm", "xnb_nccl_unique_id", "xnb_nccl_init_rank",
     "xnb_set_particles", "xnb_num_inner", "xnb_num_total", "xnb_get_particles", "xnb_upload_rv", "xnb_download_rvf",
-    "xnb_get_grid_info", "xnb_get_sweep_info", "xnb_get_cells", "xnb_move_particles", "xnb_rebuild_amr", "xnb_backup_r", "xnb_ghost_comm_scheme",
+    "xnb_get_grid_info", "xnb_get_sweep_info", "xnb_get_cells", "xnb_view_particles", "xnb_device_allocations", "xnb_move_particles", "xnb_rebuild_amr", "xnb_backup_r", "xnb_ghost_comm_scheme",
     "xnb_ghost_update_all", "xnb_ghost_update_r", "xnb_chunk_neighbors", "xnb_zero_particle_force", "xnb_set_pair_functor", "xnb_lennard_jones_force",
     "xnb_divide_force_by_mass", "xnb_set_chunk_neighbors_config", "xnb_lennard_jones_force_symmetric", "xnb_update_force_from_ghost", "xnb_push_f_v_r", "xnb_push_f_v", "xnb_particle_displ_over", "xnb_verlet_first_half",
     "xnb_read_displ_over", "xnb_force_and_second_half", "xnb_run_steps", "xnb_step_host", "xnb_first_iteration", "xnb_energy_virial",
@@ -35,6 +35,11 @@ class XnbGridInfo(C.Structure):
 class XnbSweepInfo(C.Structure):
     _fields_ = [("compiled", C.c_int32), ("ghost", C.c_int32), ("tile", C.c_int64 * 3), ("threads", C.c_int64), ("blocks", C.c_int64),
                 ("smem_bytes", C.c_int64), ("rows", C.c_int64), ("candidates", C.c_int64), ("interior_tiles", C.c_int64), ("boundary_tiles", C.c_int64)]
+
+
+class XnbParticleView(C.Structure):
+    _fields_ = [("n_inner", C.c_int64), ("n_total", C.c_int64), ("n_cells", C.c_int64)] + [(k, C.c_void_p) for k in
+                ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz", "id", "type", "cell_start", "cell_count", "particle_cell")]
 
 
 class XnbLatticeCfg(C.Structure):
@@ -75,6 +80,7 @@ def load():
         "xnb_set_particles": (I, [P, I64] + [P] * 8), "xnb_num_inner": (I64, [P]), "xnb_num_total": (I64, [P]),
         "xnb_get_particles": (I, [P, I64, I64] + [P] * 12), "xnb_upload_rv": (I, [P] * 8), "xnb_download_rvf": (I, [P] * 12),
         "xnb_get_grid_info": (I, [P, C.POINTER(XnbGridInfo)]), "xnb_get_sweep_info": (I, [P, C.POINTER(XnbSweepInfo)]), "xnb_get_cells": (I, [P, P, P]),
+        "xnb_view_particles": (I, [P, C.POINTER(XnbParticleView)]), "xnb_device_allocations": (I64, []),
         "xnb_move_particles": (I, [P, P]), "xnb_rebuild_amr": (I, [P, P]), "xnb_backup_r": (I, [P, P]), "xnb_ghost_comm_scheme": (I, [P, P]),
         "xnb_ghost_update_all": (I, [P, P]), "xnb_ghost_update_r": (I, [P, P]), "xnb_chunk_neighbors": (I, [P, P]),
         "xnb_zero_particle_force": (I, [P, I, P]), "xnb_set_pair_functor": (I, [P, I]), "xnb_lennard_jones_force": (I, [P, D, D, D, I, P]), "xnb_divide_force_by_mass": (I, [P, P]),
@@ -196,8 +202,16 @@ class Context:
     def sweep_info(self):
         si = XnbSweepInfo()
         self._ck(self.L.xnb_get_sweep_info(self.h, C.byref(si)))
-        return dict(compiled=bool(si.compiled), paired=(si.compiled == 2), ghost=bool(si.ghost), tile=tuple(si.tile[:]), threads=si.threads, blocks=si.blocks,
+        return dict(compiled=bool(si.compiled), ghost=bool(si.ghost), tile=tuple(si.tile[:]), threads=si.threads, blocks=si.blocks,
                     smem_bytes=si.smem_bytes, rows=si.rows, candidates=si.candidates, interior_tiles=si.interior_tiles, boundary_tiles=si.boundary_tiles)
+
+    def view_particles(self):
+        """device pointers of the SoA particle arrays and of the per-cell tables (xnb_particle_view); no copy, no synchronisation"""
+        v = XnbParticleView()
+        self._ck(self.L.xnb_view_particles(self.h, C.byref(v)))
+        return {k: getattr(v, k) for k, _ in XnbParticleView._fields_}
+
+    def device_allocations(self): return int(self.L.xnb_device_allocations())
 
     def cells(self):
         nc = self.grid_info()["n_cells"]

@@ -3,6 +3,7 @@
 #include "../../include/xnb_hotpath.h"
 #include "xnb_kernels.cuh"
 #include "xnb_sweep_cl.cuh"
+#include "xnb_nbh_bits.cuh"
 #include "xnb_host_decomp.hpp"
 
 #include <algorithm>
@@ -66,6 +67,7 @@ bool env_flag(const char* name) { const char* v = getenv(name); return v && *v &
 int env_int(const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; }
 
 constexpr int XNB_MAX_DEVICES = 64;
+long long g_device_allocs = 0;      // cudaMalloc calls (xnb_device_allocations)
 
 template <class T>
 struct DBuf
@@ -80,6 +82,7 @@ struct DBuf
     T* q = nullptr;
     cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
     if (e != cudaSuccess) return e;
+    g_device_allocs++;
     if (p && keep) { e = cudaMemcpy(q, p, std::min(keep, cap) * sizeof(T), cudaMemcpyDeviceToDevice); if (e != cudaSuccess) { cudaFree(q); return e; } }
     if (p) cudaFree(p);
     p = q; cap = ncap;
@@ -111,6 +114,7 @@ struct xnb_ctx
   int64_t n_inner = 0, n_total = 0;
   DBuf<uint32_t> atom_cell[2]; int cur_ac = 0;
   DBuf<uint32_t> key, rnk, perm, perm2, leave_list;
+  DBuf<unsigned long long> sort_keys; DBuf<uint32_t> sort_srcs;     // in-cell sort scratch for cells of more than CELLSORT_MAX particles
   DBuf<uint32_t> cell_start, cell_count;
   DBuf<uint32_t> backup;
   DBuf<double> mass; int n_types = 0;
@@ -135,10 +139,13 @@ struct xnb_ctx
   bool nbh_half_symmetric = false, nbh_skip_ghosts = false;       // ChunkNeighborsConfig (xnb_set_chunk_neighbors_config)
   int nbh_cap_l = 0; uint32_t nbh_slot_words = 0; bool nbh_full_cap = false;   // capacities of the tiled build (grow on demand)
   // ---- compiled lists of the pair sweep (xnb_sweep_cl.cuh): derived from the streams after every rebuild
-  struct ClCfg { bool valid = false, ghost = false, paired = false; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; int64_t candidates = 0;
+  struct ClCfg { bool valid = false, ghost = false; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; int64_t candidates = 0;
                  unsigned n_interior = 0, n_boundary = 0; };    // tiles whose halo box holds no ghost cell / the others (cl_tile_list: interior first)
   ClCfg cl;
-  DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0; DBuf<uint32_t> cl_tile_list; DBuf<uint16_t> cl_perm; double cl_union_per_pair = 0;
+  DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0; DBuf<uint32_t> cl_tile_list;
+  // ---- k_nbh_bits (xnb_nbh_bits.cuh): masks parked between its two phases, capacities that worked last time, lazily built ghost-cell lists
+  DBuf<uint32_t> nb_gmasks; int nb_cap_slots = 0; bool ghost_lists = false;       // ghost_lists: the streams of the ghost cells are current
+  struct NbGhostCfg { ClTileP tp{}; int cap_slots = 0; bool have = false; } nb_ghost;
   cudaStream_t st_comm = nullptr; cudaEvent_t ev_pos = nullptr, ev_ghost = nullptr;      // halo exchange overlapped with the interior tiles
   int64_t n_nonempty_inner = 0;
   int64_t pool_used = 0; uint32_t max_neighbors = 0, max_cell_count = 0, max_stream = 0; double avg_stream = 0; bool have_nbh = false;
@@ -146,7 +153,7 @@ struct xnb_ctx
   DBuf<unsigned long long> scan_tmp64; DBuf<uint32_t> scan_tmp32;
   DBuf<unsigned long long> d_scalars64;   // [0] displacement counter, [1] scan total
   DBuf<uint32_t> d_scalars32;             // [0] error word, [1] leave_count, [2] max_side, [3] max_nbh, [4] scan total, [8..8+64) migrate counts
-  DBuf<double> ev_partials;
+  DBuf<double> ev_partials, ev_scratch, ev_ekin;
   DBuf<int> d_blocks;
   DBuf<uint32_t> mig_rank, mig_pos, mig_base;
   // ---- xnb_step_host: positions (and ids) go back to the host on their own stream as soon as they are final
@@ -357,7 +364,7 @@ int check_device_errors(xnb_ctx* c, cudaStream_t st)
   if (e & DERR_LOST_PARTICLE) return c->fail(XNB_ERR_LOST_PARTICLE, "a particle left a non periodic domain (reference: stays in otb_particles)");
   if (e & DERR_CELL_OVERFLOW) return c->fail(XNB_ERR_CAPACITY, "more than 65535 particles in a cell (u16 stream index, chunk_neighbors_execute.h:229)");
   if (e & DERR_GROUP_OVERFLOW) return c->fail(XNB_ERR_CAPACITY, "u16 counter overflow in a neighbour stream (chunk_neighbors_execute.h:362,369)");
-  if (e & DERR_SORT_CAPACITY) return c->fail(XNB_ERR_CAPACITY, "more than 2048 particles in a cell: in-cell sort capacity exceeded");
+  if (e & DERR_SORT_CAPACITY) return c->fail(XNB_ERR_CAPACITY, "in-cell sort: no scratch for a cell of more than 2048 particles");
   if (e & DERR_ID_RANGE) return c->fail(XNB_ERR_CAPACITY, "particle id >= 2^52");
   if (e & DERR_TILE_CAPACITY) return c->fail(XNB_ERR_CAPACITY, "a tile exceeded its shared-memory staging capacity");
   return c->fail(XNB_ERR_INVALID, "device error word " + std::to_string(e));
@@ -595,7 +602,7 @@ int xnb_get_sweep_info(const xnb_ctx* c, xnb_sweep_info* out)
 {
   if (!c || !out) return XNB_ERR_INVALID;
   memset(out, 0, sizeof *out);
-  out->compiled = c->cl.valid ? (c->cl.paired ? 2 : 1) : 0;   // 2: pair-merged lists (two particles per sweep thread)
+  out->compiled = c->cl.valid ? 1 : 0;
   if (c->cl.valid)
   {
     out->tile[0] = c->cl.tp.ti; out->tile[1] = c->cl.tp.tj; out->tile[2] = c->cl.tp.tk;
@@ -695,8 +702,10 @@ int xnb_move_particles(xnb_ctx* c, void* stream)
   rc = scan_exclusive<uint32_t, uint32_t>(c, c->cell_count.p, c->cell_start.p, (size_t)g.n_cells, (uint32_t*)nullptr, c->scan_tmp32, st); if (rc) return rc;
   CK(cudaMemsetAsync(c->perm2.p, 0xFF, ((size_t)n_src + 16) * 4, st));      // sentinel: slots no kernel fills (error paths) are skipped by k_gather
   if (n_src) LAUNCH(k_bin_scatter, nblk(n_src, 256), 256, st, (int)n_src, c->key.p, c->rnk.p, c->cell_start.p, c->perm.p);
+  // cells beyond the shared-memory sort capacity rank through global scratch (12 bytes per particle)
+  CK(c->sort_keys.ensure((size_t)n_src + 16, 0, 1.2)); CK(c->sort_srcs.ensure((size_t)n_src + 16, 0, 1.2));
   LAUNCH((k_cell_sort<false>), (unsigned)g.n_cells, CELLSORT_THREADS, st, g, c->cell_start.p, c->cell_count.p, c->perm.p, c->perm2.p,
-         A.rx, A.ry, A.rz, A.id, c->side_lut.p, (const unsigned long long*)nullptr, (uint32_t*)nullptr, s32);
+         A.rx, A.ry, A.rz, A.id, c->side_lut.p, (const unsigned long long*)nullptr, (uint32_t*)nullptr, c->sort_keys.p, c->sort_srcs.p, s32);
   rc = ensure_particle_capacity(c, (size_t)std::max<int64_t>(n_new, 1), (size_t)n_src); if (rc) return rc;
   A = c->P(c->cur);
   ParticlesP B = c->P(1 - c->cur);
@@ -731,8 +740,9 @@ int xnb_rebuild_amr(xnb_ctx* c, void* stream)
   CK(c->perm.ensure((size_t)n + 16)); CK(c->perm2.ensure((size_t)n + 16));
   ParticlesP A = c->P(c->cur), B = c->P(1 - c->cur);
   LAUNCH(k_iota, nblk(n, 256), 256, st, (int)n, c->perm.p);
+  CK(c->sort_keys.ensure((size_t)n + 16, 0, 1.2)); CK(c->sort_srcs.ensure((size_t)n + 16, 0, 1.2));
   LAUNCH((k_cell_sort<true>), (unsigned)g.n_cells, CELLSORT_THREADS, st, g, c->cell_start.p, c->cell_count.p, c->perm.p, c->perm2.p,
-         A.rx, A.ry, A.rz, A.id, c->side_lut.p, c->sub_grid_start.p, c->sub_grid_cells.p, s32);
+         A.rx, A.ry, A.rz, A.id, c->side_lut.p, c->sub_grid_start.p, c->sub_grid_cells.p, c->sort_keys.p, c->sort_srcs.p, s32);
   LAUNCH(k_gather, nblk(n, 256), 256, st, (int)n, (uint32_t)n, c->perm2.p, A, B, c->atom_cell[c->cur_ac].p, c->atom_cell[1 - c->cur_ac].p);
   c->cur = 1 - c->cur; c->cur_ac = 1 - c->cur_ac;
   return XNB_OK;
@@ -854,75 +864,250 @@ int xnb_ghost_update_r(xnb_ctx* c, void* stream) { if (!c) return XNB_ERR_INVALI
 } // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------------------
-// compiled lists of the pair sweep: tile shape from the cell occupancy, then k_cl_compile (re-run with more room if a
-// capacity was too small).  Not finding a shape that fits is not an error: the sweep then reads the streams directly
-// (k_lj_sweep).
+// tiles of the pair sweep (and of the neighbour build, which works on the same tiles): candidate shapes ranked by the
+// occupancy they give the sweep kernel
+// ---------------------------------------------------------------------------------------------------------------------
+struct ClCand { int t[3]; int threads, var; size_t smem; int cap, nh, tc; double score; };
+static const size_t XNB_SM_BYTES = 227 * 1024;
+
+static std::vector<ClCand> cl_tile_candidates(const xnb_ctx* c, const int lo[3], const int hi[3], int gap)
+{
+  const GridP& g = c->g;
+  const int nc[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+  std::vector<ClCand> cands;
+  if (nc[0] <= 0 || nc[1] <= 0 || nc[2] <= 0) return cands;
+  const double ne = (double)std::max<int64_t>(c->n_nonempty_inner, 1);
+  const double avg = std::max((double)c->n_inner / ne, 1.0);
+  const double mx = (double)std::max<uint32_t>(c->max_cell_count, 1);
+  static const int shapes[][3] = {{4, 2, 2}, {4, 4, 1}, {2, 2, 2}, {4, 2, 1}, {3, 3, 2}, {4, 3, 1}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}, {4, 4, 2}, {3, 2, 2}, {8, 2, 1}, {8, 2, 2}};
+  int et[3] = {0, 0, 0};
+  if (const char* e = getenv("XNB_CL_TILE")) sscanf(e, "%d,%d,%d", &et[0], &et[1], &et[2]);
+  for (const auto& sh : shapes)
+  {
+    ClCand k{};
+    for (int d = 0; d < 3; d++) k.t[d] = std::min(sh[d], nc[d]);
+    if (et[0] > 0 && (k.t[0] != std::min(et[0], nc[0]) || k.t[1] != std::min(et[1], nc[1]) || k.t[2] != std::min(et[2], nc[2]))) continue;
+    k.tc = k.t[0] * k.t[1] * k.t[2];
+    if (k.tc > 32) continue;
+    bool dup = false; for (const ClCand& o : cands) dup |= (o.t[0] == k.t[0] && o.t[1] == k.t[1] && o.t[2] == k.t[2]);
+    if (dup) continue;
+    k.nh = std::min(k.t[0] + 2 * gap, g.dims[0]) * std::min(k.t[1] + 2 * gap, g.dims[1]) * std::min(k.t[2] + 2 * gap, g.dims[2]);
+    const double tile_avg = avg * k.tc;
+    k.threads = 32 * (int)std::ceil(std::min(mx * k.tc, tile_avg * 1.04 + 8.0) / 32.0);
+    if (k.threads > 1024) continue;
+    k.threads = std::max(k.threads, 64);
+    k.var = k.threads <= 576 ? 0 : 1;
+    const double capd = std::min(mx * k.nh, avg * k.nh * 1.08 + 64.0);
+    if (capd > 8191.0) continue;
+    k.cap = ((int)capd + 1) & ~1;
+    k.smem = cl_sweep_smem_bytes(k.nh, k.tc, k.cap, k.threads / 32);
+    if (k.smem + 1024 + 2048 > XNB_SM_BYTES) continue;
+    const int by_smem = (int)(XNB_SM_BYTES / (k.smem + 1024 + 256));
+    const int by_regs = 65536 / (k.threads * (k.var == 0 ? 56 : 64));
+    const int by_warps = 64 / (k.threads / 32);
+    const int resident = std::min(std::min(by_smem, by_regs), std::min(by_warps, 32));
+    if (resident < 1) continue;
+    const double useful = resident * (tile_avg / 32.0);               // useful resident warps per SM
+    k.score = std::min(useful, 36.0) - 0.25 * (double)k.nh / (double)k.tc;
+    cands.push_back(k);
+  }
+  std::stable_sort(cands.begin(), cands.end(), [](const ClCand& a, const ClCand& b) { return a.score > b.score; });
+  return cands;
+}
+
+static void cl_tile_grid(ClTileP& tp, const ClCand& k, const int lo[3], const int hi[3], int gap)
+{
+  tp.gap = gap;
+  for (int d = 0; d < 3; d++) { tp.lo[d] = lo[d]; tp.hi[d] = hi[d]; }
+  tp.ti = k.t[0]; tp.tj = k.t[1]; tp.tk = k.t[2];
+  tp.tiles_i = (hi[0] - lo[0] + tp.ti - 1) / tp.ti; tp.tiles_j = (hi[1] - lo[1] + tp.tj - 1) / tp.tj; tp.tiles_k = (hi[2] - lo[2] + tp.tk - 1) / tp.tk;
+  tp.nh_max = (tp.ti + 2 * gap) * (tp.tj + 2 * gap) * (tp.tk + 2 * gap); tp.tc_max = k.tc;
+  tp.cap = k.cap; tp.gmax = k.threads / 32;
+}
+
+// the sweep configuration once the compiled rows of tile grid `tp` exist (built by k_nbh_bits or by k_cl_compile)
+static int cl_finish(xnb_ctx* c, const ClTileP& tp, bool ghost, unsigned blocks, uint32_t rows, int64_t candidates, uint32_t max_groups, cudaStream_t st)
+{
+  const GridP& g = c->g;
+  const bool same_grid = c->cl.valid && c->cl.ghost == ghost && c->cl.blocks == blocks && c->cl.tp.ti == tp.ti && c->cl.tp.tj == tp.tj && c->cl.tp.tk == tp.tk &&
+                         c->cl.tp.tiles_i == tp.tiles_i && c->cl.tp.tiles_j == tp.tiles_j && c->cl.tp.tiles_k == tp.tiles_k;
+  c->cl.tp = tp; c->cl.ghost = ghost; c->cl.blocks = blocks; c->cl.rows = rows; c->cl.candidates = candidates;
+  // every tile is swept in one pass: one warp per group of the fullest tile
+  c->cl.threads = std::max(32 * (int)std::max<uint32_t>(max_groups, 1u), 64);
+  if (env_int("XNB_CL_THREADS") > 0) c->cl.threads = std::min(env_int("XNB_CL_THREADS") & ~31, 1024);
+  c->cl.var = c->cl.threads <= 576 ? 0 : 1;
+  if (getenv("XNB_CL_VAR")) { const int v = env_int("XNB_CL_VAR"); if ((v == 2 && c->cl.threads <= 288) || (v == 3 && c->cl.threads <= 576)) c->cl.var = v; }   // experiments: 2 = three blocks per SM (<= 72 registers), 3 = one block per SM
+  c->cl.smem = cl_sweep_smem_bytes(tp.nh_max, tp.tc_max, tp.cap, std::max(tp.gmax, c->cl.threads / 32));
+  if (!same_grid)
+  {
+    // interior tiles: the halo box touches no ghost cell, so they can be swept while the halo exchange is in flight
+    std::vector<uint32_t> inner, outer;
+    for (unsigned b = 0; b < blocks; b++)
+    {
+      const int t_i = (int)(b % tp.tiles_i), t_j = (int)((b / tp.tiles_i) % tp.tiles_j), t_k = (int)(b / ((unsigned)tp.tiles_i * tp.tiles_j));
+      const int c0[3] = {tp.lo[0] + t_i * tp.ti, tp.lo[1] + t_j * tp.tj, tp.lo[2] + t_k * tp.tk};
+      const int tc[3] = {std::min(tp.ti, tp.hi[0] - c0[0]), std::min(tp.tj, tp.hi[1] - c0[1]), std::min(tp.tk, tp.hi[2] - c0[2])};
+      bool in = !ghost;
+      for (int d = 0; d < 3; d++) in = in && c0[d] - tp.gap >= g.gl && c0[d] + tc[d] - 1 + tp.gap < g.dims[d] - g.gl;
+      (in ? inner : outer).push_back(b);
+    }
+    c->cl.n_interior = (unsigned)inner.size(); c->cl.n_boundary = (unsigned)outer.size();
+    inner.insert(inner.end(), outer.begin(), outer.end());
+    CK(c->cl_tile_list.ensure(inner.size() + 16));
+    // (pageable source: the call returns once the data sits in the driver's staging buffer, `inner` may go out of scope)
+    CK(cudaMemcpyAsync(c->cl_tile_list.p, inner.data(), inner.size() * 4, cudaMemcpyHostToDevice, st));
+  }
+  c->cl.valid = true;
+  if (getenv("XNB_TILE_DEBUG"))
+    fprintf(stderr, "[xnb] compiled lists: tiles %dx%dx%d threads %d var %d smem %zu cap %d gmax %d blocks %u rows %u\n", tp.ti, tp.tj, tp.tk,
+            c->cl.threads, c->cl.var, c->cl.smem, tp.cap, tp.gmax, blocks, rows);
+  return XNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// neighbour build on the tiles of the sweep: k_nbh_bits.  mode 0: lists of the inner cells + compiled rows of the sweep (what
+// the step loop needs); mode 1: lists of the ghost cells only, streams only -- built lazily, when somebody asks for them
+// (xnb_view_chunk_neighbors / xnb_get_streams / a sweep with ghost = true).  *done = false: no tile shape fits shared memory
+// (large cells) and the caller falls back to the per-particle two-pass kernels.
+// ---------------------------------------------------------------------------------------------------------------------
+static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
+{
+  *done = false;
+  const GridP& g = c->g;
+  const int gap = (int)std::ceil(c->nbh_dist / c->cs);
+  int lo[3], hi[3];
+  for (int d = 0; d < 3; d++) { lo[d] = mode == 0 ? g.gl : 0; hi[d] = mode == 0 ? g.dims[d] - g.gl : g.dims[d]; }
+  if (mode == 1 && g.gl == 0) { *done = true; return XNB_OK; }
+  ParticlesP A = c->P(c->cur);
+  const uint32_t mcc = std::max<uint32_t>(c->max_cell_count, 1);
+  const int nrows = (2 * gap + 1) * (2 * gap + 1);
+  const int nwarp = NBH_BITS_THREADS / 32;
+  // stream capacity per cell: first guess from the list radius (volume ratio of the sphere to the neighbourhood), grows on demand
+  if (c->nbh_slot_words == 0)
+  {
+    const double frac = std::min(1.0, 4.19 * c->nbh_dist * c->nbh_dist * c->nbh_dist / std::pow((2.0 * gap + 1.0) * c->cs, 3.0));
+    const double per = 1.0 + 2.0 * std::pow(2.0 * gap + 1.0, 3.0) * 0.6 + frac * std::pow(2.0 * gap + 1.0, 3.0) * (double)mcc * 1.3;
+    c->nbh_slot_words = (uint32_t)((size_t)(2 * (mcc + 1) + (double)mcc * per + 64 + 7) & ~(size_t)7);
+  }
+  std::vector<ClCand> cands = cl_tile_candidates(c, lo, hi, gap);
+  static bool attr_done_dev[XNB_MAX_DEVICES] = {};
+  if (!attr_done_dev[c->device % XNB_MAX_DEVICES])
+  {
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_nbh_bits));
+    CK(cudaFuncSetAttribute(k_nbh_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
+    attr_done_dev[c->device % XNB_MAX_DEVICES] = true;
+  }
+  uint32_t* counters = c->d_scalars32.p + 64;                  // NB_U32_COUNT u32
+  unsigned long long* totals = c->d_scalars64.p + 4;           // 3 u64
+  for (const ClCand& k : cands)
+  {
+    ClTileP tp{};
+    cl_tile_grid(tp, k, lo, hi, gap);
+    // slots: per row of the neighbourhood ceil(row candidates / 32) + 1 blocks
+    int cap_slots = nrows * ((int)(((2 * gap + 1) * mcc + 31) / 32) + 1);
+    const ClTileP& prev = mode == 0 ? c->cl.tp : c->nb_ghost.tp;
+    const bool have_prev = mode == 0 ? (c->cl.valid && !c->cl.ghost) : c->nb_ghost.have;
+    if (have_prev && prev.ti == tp.ti && prev.tj == tp.tj && prev.tk == tp.tk)
+    {
+      // same shape as last time: start from the capacities that worked
+      tp.gmax = std::max(tp.gmax, prev.gmax); tp.cap = std::max(tp.cap, prev.cap);
+      const int ps = mode == 0 ? c->nb_cap_slots : c->nb_ghost.cap_slots;      // slots the last build used, + slack
+      if (ps > 0) cap_slots = std::min(cap_slots, ps);
+    }
+    const unsigned blocks = (unsigned)((int64_t)tp.tiles_i * tp.tiles_j * tp.tiles_k);
+    bool ok = false, shape_fails = false;
+    for (int attempt = 0; attempt < 6; attempt++)
+    {
+      if (tp.cap > 8191 || tp.gmax > 32) { shape_fails = true; break; }
+      const size_t smem = nb_smem_bytes(tp.nh_max, tp.tc_max, tp.gmax, tp.cap, cap_slots, nwarp);
+      if (smem + 2048 > XNB_SM_BYTES) { shape_fails = true; break; }
+      if ((size_t)g.n_cells * c->nbh_slot_words > ((size_t)24 << 30)) return XNB_OK;      // streams would not fit: two-pass build with a compact pool
+      CK(c->pool.ensure((size_t)g.n_cells * c->nbh_slot_words + 64));
+      CK(c->nb_gmasks.ensure((size_t)blocks * tp.gmax * cap_slots * 32 + 64));
+      if (mode == 0)
+      {
+        if (c->cl_cap_rows == 0) c->cl_cap_rows = (uint32_t)std::min<double>(4.0e9, (double)c->n_inner * 24.0 / 32.0 * 1.10 + 4096.0);
+        CK(c->cl_rows.ensure((size_t)c->cl_cap_rows * 128 + 64));
+        CK(c->cl_groups.ensure((size_t)blocks * tp.gmax + 16));
+      }
+      CK(cudaMemsetAsync(counters, 0, NB_U32_COUNT * 4, st)); CK(cudaMemsetAsync(totals, 0, 3 * 8, st));
+      NbhBitsP bp{};
+      bp.cap_slots = cap_slots; bp.emit_rows = mode == 0 ? 1 : 0; bp.sel_mode = mode; bp.slot_words = (int)c->nbh_slot_words; bp.cap_rows = c->cl_cap_rows;
+      bp.lane_min = env_int("XNB_NBH_LANE_MIN") > 0 ? env_int("XNB_NBH_LANE_MIN") : 16; bp.max_dist2 = c->nbh_dist * c->nbh_dist;
+      NbhBitsOut o{c->pool.p, c->cell_stream.p, c->stream_size.p, c->cell_stream_bytes.p, c->stream_off.p, c->cl_groups.p, reinterpret_cast<uint2*>(c->cl_rows.p),
+                   c->nb_gmasks.p, counters, totals};
+      if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh_bits mode %d tiles %dx%dx%d cap %d gmax %d slots %d slot_words %u smem %zu blocks %u (max cell %u)\n", mode, tp.ti, tp.tj, tp.tk, tp.cap, tp.gmax, cap_slots, c->nbh_slot_words, smem, blocks, mcc);
+      k_nbh_bits<<<blocks, NBH_BITS_THREADS, smem, st>>>(g, tp, bp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
+      c->launches++; CK(cudaGetLastError());
+      uint32_t h[NB_U32_COUNT]; unsigned long long tot[3];
+      {
+        // one host synchronisation for the small results
+        char* hp = static_cast<char*>(c->h_pinned);
+        CK(cudaMemcpyAsync(hp, counters, NB_U32_COUNT * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hp + 64, totals, 3 * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(h, hp, NB_U32_COUNT * 4); memcpy(tot, hp + 64, 24);
+      }
+      bool again = false;
+      if ((int)h[NB_GMAX] > tp.gmax) { tp.gmax = (int)h[NB_GMAX]; again = true; }
+      if ((int)h[NB_CAP] > tp.cap) { tp.cap = ((int)h[NB_CAP] + 1) & ~1; again = true; }
+      if ((int)h[NB_SLOTS] > cap_slots) { cap_slots = (int)h[NB_SLOTS] + 1; again = true; }
+      if (h[NB_SLOT_WORDS] > c->nbh_slot_words) { c->nbh_slot_words = (uint32_t)(((size_t)(h[NB_SLOT_WORDS] * 1.12) + 64 + 7) & ~(size_t)7); again = true; }
+      if (mode == 0 && h[NB_ROWS] > c->cl_cap_rows) { c->cl_cap_rows = (uint32_t)((double)h[NB_ROWS] * 1.05) + 1024u; again = true; }
+      if (again || h[NB_OVERFLOW]) { if (!again) return c->fail(XNB_ERR_CAPACITY, "chunk_neighbors: tiled build reported an overflow it cannot size"); continue; }
+      if (mode == 0)
+      {
+        c->pool_used = (int64_t)tot[1]; c->max_neighbors = h[NB_MAX_NBH]; c->n_nonempty_inner = h[NB_NONEMPTY]; c->max_stream = h[NB_MAX_STREAM];
+        c->avg_stream = c->n_inner ? (double)tot[2] / (double)c->n_inner : 0.0;
+        c->nb_cap_slots = std::min(cap_slots, (int)h[NB_SLOTS] + 3);
+        c->have_nbh = true; c->ghost_lists = g.gl == 0;
+        int rc = cl_finish(c, tp, false, blocks, h[NB_ROWS], (int64_t)tot[0], h[NB_GMAX], st); if (rc) return rc;
+      }
+      else
+      {
+        c->pool_used += (int64_t)tot[1]; c->max_neighbors = std::max(c->max_neighbors, h[NB_MAX_NBH]); c->max_stream = std::max(c->max_stream, h[NB_MAX_STREAM]);
+        c->nb_ghost.tp = tp; c->nb_ghost.cap_slots = std::min(cap_slots, (int)h[NB_SLOTS] + 3); c->nb_ghost.have = true;
+        c->ghost_lists = true;
+      }
+      ok = true;
+      break;
+    }
+    if (ok) { *done = true; return XNB_OK; }
+    if (!shape_fails) return c->fail(XNB_ERR_CAPACITY, "chunk_neighbors: tiled build did not converge");
+  }
+  return XNB_OK;
+}
+
+// lists of the ghost-cell particles, on demand (the step loop with ghost = false never reads them)
+static int ensure_ghost_lists(xnb_ctx* c, cudaStream_t st)
+{
+  if (!c->have_nbh || c->ghost_lists) return XNB_OK;
+  bool done = false;
+  int rc = nbh_bits_run(c, 1, st, &done); if (rc) return rc;
+  if (!done) return c->fail(XNB_ERR_CAPACITY, "chunk_neighbors: the ghost-cell lists could not be built on tiles");
+  return check_device_errors(c, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// compiled lists derived from existing streams (k_cl_compile): for lists built by the two-pass kernels and for sweeps over
+// the ghost cells too (ghost = true).  Not finding a tile shape that fits is not an error: the sweep then reads the streams
+// directly (k_lj_sweep).
 // ---------------------------------------------------------------------------------------------------------------------
 static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
 {
   c->cl.valid = false;
   if (env_flag("XNB_SWEEP_STREAMS") || c->n_total == 0 || !c->have_nbh) return XNB_OK;
+  if (ghost) { int rc = ensure_ghost_lists(c, st); if (rc) return rc; }
   const GridP& g = c->g;
-  ClTileP tp{};
-  tp.gap = (int)std::ceil(c->nbh_dist / c->cs);
-  for (int d = 0; d < 3; d++) { tp.lo[d] = ghost ? 0 : g.gl; tp.hi[d] = ghost ? g.dims[d] : g.dims[d] - g.gl; }
-  const int nc[3] = {tp.hi[0] - tp.lo[0], tp.hi[1] - tp.lo[1], tp.hi[2] - tp.lo[2]};
-  if (nc[0] <= 0 || nc[1] <= 0 || nc[2] <= 0) return XNB_OK;
-  const double ne = (double)std::max<int64_t>(c->n_nonempty_inner, 1);
-  const double avg = std::max((double)c->n_inner / ne, 1.0);
-  const double mx = (double)std::max<uint32_t>(c->max_cell_count, 1);
-  const size_t SM_BYTES = 227 * 1024;
-  // pair-merged lists (xnb_sweep_cl.cuh): two tile particles per sweep thread, a group = 64 slots
-  const bool paired = env_flag("XNB_CL_PAIRED");
-  const int gsz = paired ? 64 : 32;
-  static const int shapes[][3] = {{4, 2, 2}, {4, 4, 1}, {2, 2, 2}, {4, 2, 1}, {3, 3, 2}, {4, 3, 1}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}, {4, 4, 2}, {3, 2, 2}, {8, 2, 1}, {8, 2, 2}};
-  int et[3] = {0, 0, 0};
-  if (const char* e = getenv("XNB_CL_TILE")) sscanf(e, "%d,%d,%d", &et[0], &et[1], &et[2]);
-  struct Cand { int t[3]; int threads, var; size_t smem; int cap, nh, tc; double score; };
-  std::vector<Cand> cands;
-  for (const auto& sh : shapes)
-  {
-    Cand k{};
-    for (int d = 0; d < 3; d++) k.t[d] = std::min(sh[d], nc[d]);
-    if (et[0] > 0 && (k.t[0] != std::min(et[0], nc[0]) || k.t[1] != std::min(et[1], nc[1]) || k.t[2] != std::min(et[2], nc[2]))) continue;
-    k.tc = k.t[0] * k.t[1] * k.t[2];
-    if (k.tc > 32) continue;
-    bool dup = false; for (const Cand& o : cands) dup |= (o.t[0] == k.t[0] && o.t[1] == k.t[1] && o.t[2] == k.t[2]);
-    if (dup) continue;
-    k.nh = std::min(k.t[0] + 2 * tp.gap, g.dims[0]) * std::min(k.t[1] + 2 * tp.gap, g.dims[1]) * std::min(k.t[2] + 2 * tp.gap, g.dims[2]);
-    const double tile_avg = avg * k.tc;
-    k.threads = 32 * (int)std::ceil(std::min(mx * k.tc, tile_avg * 1.04 + 8.0) / (double)gsz);
-    if (k.threads > (paired ? 576 : 1024)) continue;
-    k.threads = std::max(k.threads, 64);
-    k.var = paired ? (k.threads <= 288 ? 0 : 1) : (k.threads <= 576 ? 0 : 1);
-    const double capd = std::min(mx * k.nh, avg * k.nh * 1.08 + 64.0);
-    if (capd > 8191.0) continue;
-    k.cap = ((int)capd + 1) & ~1;
-    k.smem = cl_sweep_smem_bytes(k.nh, k.tc, k.cap, k.threads / 32);
-    if (k.smem + 1024 + 2048 > SM_BYTES) continue;
-    const int by_smem = (int)(SM_BYTES / (k.smem + 1024 + 256));
-    const int by_regs = 65536 / (k.threads * (paired ? 112 : k.var == 0 ? 56 : 64));
-    const int by_warps = 64 / (k.threads / 32);
-    const int resident = std::min(std::min(by_smem, by_regs), std::min(by_warps, 32));
-    if (resident < 1) continue;
-    const double useful = resident * (tile_avg / 32.0);               // useful resident warps per SM (paired: two particles per lane)
-    k.score = std::min(useful, 36.0) - 0.25 * (double)k.nh / (double)k.tc;
-    cands.push_back(k);
-  }
-  std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) { return a.score > b.score; });
+  const int gap = (int)std::ceil(c->nbh_dist / c->cs);
+  int lo[3], hi[3];
+  for (int d = 0; d < 3; d++) { lo[d] = ghost ? 0 : g.gl; hi[d] = ghost ? g.dims[d] : g.dims[d] - g.gl; }
+  std::vector<ClCand> cands = cl_tile_candidates(c, lo, hi, gap);
   uint32_t* counters = c->d_scalars32.p + 112;
-  for (const Cand& k : cands)
+  for (const ClCand& k : cands)
   {
-    tp.ti = k.t[0]; tp.tj = k.t[1]; tp.tk = k.t[2];
-    tp.tiles_i = (nc[0] + tp.ti - 1) / tp.ti; tp.tiles_j = (nc[1] + tp.tj - 1) / tp.tj; tp.tiles_k = (nc[2] + tp.tk - 1) / tp.tk;
-    tp.nh_max = (tp.ti + 2 * tp.gap) * (tp.tj + 2 * tp.gap) * (tp.tk + 2 * tp.gap); tp.tc_max = k.tc;
-    tp.cap = k.cap; tp.gmax = k.threads / 32;
-    if (c->cl.tp.ti == tp.ti && c->cl.tp.tj == tp.tj && c->cl.tp.tk == tp.tk && c->cl.ghost == ghost && c->cl.paired == paired)
-    {
-      // same shape as last time: start from the capacities that worked (no second compile pass per rebuild)
-      tp.gmax = std::max(tp.gmax, c->cl.tp.gmax);
-      if (c->cl.tp.cap > tp.cap && cl_sweep_smem_bytes(tp.nh_max, tp.tc_max, c->cl.tp.cap, tp.gmax) + 1024 + 2048 <= SM_BYTES) tp.cap = c->cl.tp.cap;
-    }
+    ClTileP tp{};
+    cl_tile_grid(tp, k, lo, hi, gap);
     const unsigned blocks = (unsigned)((int64_t)tp.tiles_i * tp.tiles_j * tp.tiles_k);
     size_t smem = cl_sweep_smem_bytes(tp.nh_max, tp.tc_max, tp.cap, tp.gmax);
     bool ok = false;
@@ -931,67 +1116,26 @@ static int cl_prepare(xnb_ctx* c, bool ghost, cudaStream_t st)
       if (c->cl_cap_rows == 0) c->cl_cap_rows = (uint32_t)std::min<double>(4.0e9, (double)c->pool_used / 128.0 * 1.10 + 4096.0);
       CK(c->cl_rows.ensure((size_t)c->cl_cap_rows * 128 + 64));
       CK(c->cl_groups.ensure((size_t)blocks * tp.gmax + 16));
-      CK(cudaMemsetAsync(counters, 0, 8 * 4, st));      // [0..2] u32 counters, [4..5] one u64 (8-byte aligned): list entries, [6..7] one u64: union entries (paired)
+      CK(cudaMemsetAsync(counters, 0, 8 * 4, st));      // [0..2] u32 counters, [4..5] one u64 (8-byte aligned): list entries
       const size_t tbytes = (((size_t)(2 * tp.nh_max + 2 * tp.tc_max + 2) * 4 + 15) & ~(size_t)15);
-      if (paired)
-      {
-        ParticlesP A = c->P(c->cur);
-        CK(c->cl_perm.ensure((size_t)blocks * tp.gmax * 64 + 64));
-        k_cl_compile_paired<<<blocks, 32 * std::min(2 * tp.gmax, 32), tbytes + (size_t)tp.gmax * 64 * 3, st>>>(g, tp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p,
-            (const uint16_t* const*)c->cell_stream.p, c->cl_groups.p, reinterpret_cast<uint2*>(c->cl_rows.p), c->cl_perm.p, c->cl_cap_rows, counters,
-            reinterpret_cast<unsigned long long*>(counters + 4));
-      }
-      else
       k_cl_compile<<<blocks, 32 * std::min(tp.gmax, 32), tbytes, st>>>(g, tp, c->cell_start.p, c->cell_count.p, (const uint16_t* const*)c->cell_stream.p, c->cl_groups.p,
                                                                      reinterpret_cast<uint2*>(c->cl_rows.p), c->cl_cap_rows, counters, reinterpret_cast<unsigned long long*>(counters + 4));
       c->launches++; CK(cudaGetLastError());
       uint32_t h[8]; int rc = read_back(c, counters, 8, h, st); if (rc) return rc;
       bool again = false;
-      if ((int)h[1] > tp.gmax) { if (h[1] * 32u > (paired ? 576u : 1024u)) break; tp.gmax = (int)h[1]; again = true; }
+      if ((int)h[1] > tp.gmax) { if (h[1] * 32u > 1024u) break; tp.gmax = (int)h[1]; again = true; }
       if ((int)h[2] > tp.cap) { tp.cap = ((int)h[2] + 1) & ~1; again = true; }
       smem = cl_sweep_smem_bytes(tp.nh_max, tp.tc_max, tp.cap, tp.gmax);
-      if (tp.cap > 8191 || smem + 1024 + 2048 > SM_BYTES) break;
+      if (tp.cap > 8191 || smem + 1024 + 2048 > XNB_SM_BYTES) break;
       if (!again && h[0] > c->cl_cap_rows) { c->cl_cap_rows = (uint32_t)((double)h[0] * 1.05) + 1024u; again = true; }
       if (again) continue;
-      // every tile is swept in one pass: one warp per group of the fullest tile
-      c->cl.tp = tp; c->cl.ghost = ghost; c->cl.paired = paired; c->cl.blocks = blocks; c->cl.smem = smem; c->cl.rows = h[0];
-      c->cl.candidates = (int64_t)(((unsigned long long)h[5] << 32) | h[4]);
-      c->cl_union_per_pair = (double)(((unsigned long long)h[7] << 32) | h[6]) / std::max(0.5 * (double)(ghost ? c->n_total : c->n_inner), 1.0);
-      c->cl.threads = std::max(32 * (int)std::max<uint32_t>(h[1], 1u), 64);
-      if (env_int("XNB_CL_THREADS") > 0) c->cl.threads = std::min(env_int("XNB_CL_THREADS") & ~31, 1024);
-      c->cl.var = paired ? (c->cl.threads <= 288 ? 0 : 1) : (c->cl.threads <= 576 ? 0 : 1);
-      if (!paired && getenv("XNB_CL_VAR")) { const int v = env_int("XNB_CL_VAR"); if ((v == 2 && c->cl.threads <= 288) || (v == 3 && c->cl.threads <= 576)) c->cl.var = v; }   // experiments: 2 = three blocks per SM (<= 72 registers), 3 = one block per SM
-      c->cl.smem = cl_sweep_smem_bytes(tp.nh_max, tp.tc_max, tp.cap, std::max(tp.gmax, c->cl.threads / 32));   // one ring of list rows per warp
-      {
-        // interior tiles: the halo box touches no ghost cell, so they can be swept while the halo exchange is in flight
-        std::vector<uint32_t> inner, outer;
-        for (unsigned b = 0; b < blocks; b++)
-        {
-          const int t_i = (int)(b % tp.tiles_i), t_j = (int)((b / tp.tiles_i) % tp.tiles_j), t_k = (int)(b / ((unsigned)tp.tiles_i * tp.tiles_j));
-          const int c0[3] = {tp.lo[0] + t_i * tp.ti, tp.lo[1] + t_j * tp.tj, tp.lo[2] + t_k * tp.tk};
-          const int tc[3] = {std::min(tp.ti, tp.hi[0] - c0[0]), std::min(tp.tj, tp.hi[1] - c0[1]), std::min(tp.tk, tp.hi[2] - c0[2])};
-          bool in = !ghost;
-          for (int d = 0; d < 3; d++) in = in && c0[d] - tp.gap >= g.gl && c0[d] + tc[d] - 1 + tp.gap < g.dims[d] - g.gl;
-          (in ? inner : outer).push_back(b);
-        }
-        c->cl.n_interior = (unsigned)inner.size(); c->cl.n_boundary = (unsigned)outer.size();
-        inner.insert(inner.end(), outer.begin(), outer.end());
-        CK(c->cl_tile_list.ensure(inner.size() + 16));
-        // (pageable source: the call returns once the data sits in the driver's staging buffer, `inner` may go out of scope)
-        CK(cudaMemcpyAsync(c->cl_tile_list.p, inner.data(), inner.size() * 4, cudaMemcpyHostToDevice, st));
-      }
+      rc = cl_finish(c, tp, ghost, blocks, h[0], (int64_t)(((unsigned long long)h[5] << 32) | h[4]), h[1], st); if (rc) return rc;
       ok = true;
       break;
     }
-    if (ok) { c->cl.valid = true; break; }
+    if (ok) break;
   }
-  if (getenv("XNB_TILE_DEBUG"))
-  {
-    if (c->cl.valid && c->cl.paired) fprintf(stderr, "[xnb] pair-merged lists: %.2f union entries per particle pair, %.2f list entries per particle\n", c->cl_union_per_pair, (double)c->cl.candidates / std::max<double>((double)c->n_inner, 1.0));
-    if (c->cl.valid) fprintf(stderr, "[xnb] compiled lists: tiles %dx%dx%d threads %d var %d smem %zu cap %d gmax %d blocks %u rows %u (avg %.1f max %.0f)\n", c->cl.tp.ti, c->cl.tp.tj, c->cl.tp.tk,
-                             c->cl.threads, c->cl.var, c->cl.smem, c->cl.tp.cap, c->cl.tp.gmax, c->cl.blocks, c->cl.rows, avg, mx);
-    else fprintf(stderr, "[xnb] compiled lists: no tile shape fits, sweeping the streams\n");
-  }
+  if (getenv("XNB_TILE_DEBUG") && !c->cl.valid) fprintf(stderr, "[xnb] compiled lists: no tile shape fits, sweeping the streams\n");
   return XNB_OK;
 }
 
@@ -1017,95 +1161,25 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
   if ((rc = t_begin(c, XNB_T_NBH, st))) return rc;
   NbhOut out{c->nb_len.p, c->nb_cnt.p, c->nb_off.p, c->cell_stream.p};
 
-  // ---- tiled single-kernel form (k_nbh_fused) when a tile fits shared memory, else the per-particle two-pass kernels
-  // (lists filtered by ChunkNeighborsConfig::half_symmetric / skip_ghosts are built by the two-pass kernels)
-  bool tiled = n > 0 && !env_flag("XNB_NBH_UNTILED") && !c->nbh_half_symmetric && !c->nbh_skip_ghosts;
-  if (tiled)
+  // ---- tiled form (k_nbh_bits, one kernel: streams of the inner cells + compiled rows of the sweep) when a tile fits shared
+  // memory, else the per-particle two-pass kernels.  Lists filtered by ChunkNeighborsConfig::half_symmetric / skip_ghosts are
+  // built by the two-pass kernels.
+  c->ghost_lists = false;
+  if (n > 0 && !env_flag("XNB_NBH_UNTILED") && !c->nbh_half_symmetric && !c->nbh_skip_ghosts)
   {
-    CK(cudaMemsetAsync(s32 + 5, 0, 4, st));
-    LAUNCH(k_max_u32, nblk(g.n_cells, 256), 256, st, g.n_cells, c->cell_count.p, s32 + 5);
-    uint32_t mcc = 0;
-    rc = read_back(c, s32 + 5, 1, &mcc, st); if (rc) return rc;
-    mcc = std::max<uint32_t>(mcc, 1);
-    const int nslot = (2 * gap + 1) * (2 * gap + 1) * (2 * gap + 1);
-    const bool u8 = mcc <= 127 && nslot <= 128 && !env_flag("XNB_NBH_U16");     // byte list areas (k_nbh_fused<true>)
-    const size_t SMEM_MAX = 200 * 1024;
-    if (mcc > 32u * NBH_MAX_CHUNKS) tiled = false;
-    if (c->nbh_cap_l == 0) c->nbh_cap_l = 160;
-    static const int shapes[][2] = {{4, 2}, {2, 2}, {2, 1}, {1, 1}};
-    int first_shape = env_int("XNB_NBH_TILE");      // tuning knobs: index into shapes[], warps per block
-    int nwarp = env_int("XNB_NBH_WARPS") > 0 ? std::min(env_int("XNB_NBH_WARPS"), 8) : 8;
-    for (int attempt = 0; attempt < 6 && tiled; attempt++)
+    // occupancy of the cells (tile shape and capacities follow from it)
+    CK(cudaMemsetAsync(s32 + 5, 0, 8, st));
+    LAUNCH(k_cell_stats, nblk(g.n_cells, 256), 256, st, g, c->cell_count.p, s32 + 5);
+    uint32_t cs[2] = {0, 0};
+    rc = read_back(c, s32 + 5, 2, cs, st); if (rc) return rc;
+    c->max_cell_count = std::max<uint32_t>(cs[0], 1); c->n_nonempty_inner = cs[1];
+    bool done = false;
+    rc = nbh_bits_run(c, 0, st, &done); if (rc) return rc;
+    if (done)
     {
-      NbhTileP tp{};
-      tp.gap = gap; tp.max_dist2 = md2; tp.cap_l = ((c->nbh_cap_l + 7) & ~7) + 4;      // cap_l / 4 odd: the 32 list areas of a warp start in 32 different banks
-      tp.tail = (1 + nslot * (2 + (int)mcc) + 15) & ~15;
-      if (c->nbh_slot_words == 0) c->nbh_slot_words = (uint32_t)((2 * (mcc + 1) + (size_t)mcc * tp.cap_l * 3 / 4 + 7) & ~(size_t)7);
-      tp.slot_words = (int)c->nbh_slot_words;
-      const size_t lists = (size_t)nwarp * (size_t)(31 * tp.cap_l + tp.tail) * (u8 ? 1 : 2);
-      int pick = -1; size_t smem = 0;
-      for (int q = std::max(first_shape, 0); q < 4; q++)
-      {
-        const int ti = std::min(shapes[q][0], g.dims[0]), tj = std::min(shapes[q][1], g.dims[1]);
-        const size_t nh = (size_t)std::min(ti + 2 * gap, g.dims[0]) * std::min(tj + 2 * gap, g.dims[1]) * std::min(2 * gap + 1, g.dims[2]);
-        if (nh > (size_t)NBH_MAX_HALO) continue;
-        // staging capacity: every halo cell at 85% of the fullest cell (a fuller tile makes the kernel report
-        // DERR_TILE_CAPACITY and the build is re-run with the exact bound, then with the next smaller tile shape)
-        // (cells are staged padded to multiples of 4)
-        const size_t cap = (size_t)std::ceil((double)nh * (double)((mcc + 3) & ~3u) * (c->nbh_full_cap ? 1.0 : 0.85)) + 3 * nh + 32;
-        smem = ((cap * 16 + 15) & ~(size_t)15) + lists;
-        if (smem <= SMEM_MAX) { pick = q; tp.ti = ti; tp.tj = tj; tp.cap = (int)cap; break; }
-      }
-      if (pick < 0 || (size_t)g.n_cells * c->nbh_slot_words > ((size_t)24 << 30)) { tiled = false; break; }
-      tp.tiles_i = (g.dims[0] + tp.ti - 1) / tp.ti; tp.tiles_j = (g.dims[1] + tp.tj - 1) / tp.tj;
-      CK(c->pool.ensure((size_t)g.n_cells * c->nbh_slot_words + 64));
-      uint32_t* stats = s32 + 96;
-      CK(cudaMemsetAsync(stats, 0, 6 * 4, st)); CK(cudaMemsetAsync(c->d_scalars64.p + 1, 0, 16, st));
-      NbhCellOut o{c->pool.p, c->cell_stream.p, c->stream_size.p, c->cell_stream_bytes.p, c->stream_off.p, stats, c->d_scalars64.p + 1};
-      static bool attr_done_dev[XNB_MAX_DEVICES] = {};      // function attributes are per device
-      bool& attr_done = attr_done_dev[c->device % XNB_MAX_DEVICES];
-      if (!attr_done)
-      {
-        CK(cudaFuncSetAttribute(k_nbh_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-        CK(cudaFuncSetAttribute(k_nbh_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-        attr_done = true;
-      }
-      const unsigned blocks = (unsigned)((int64_t)tp.tiles_i * tp.tiles_j * g.dims[2]);
-      if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh tiles %dx%d warps %d u8 %d cap %d cap_l %d slot %d smem %zu blocks %u (max cell %u)\n", tp.ti, tp.tj, nwarp, (int)u8, tp.cap, tp.cap_l, tp.slot_words, smem, blocks, mcc);
-      if (u8) k_nbh_fused<true><<<blocks, nwarp * 32, smem, st>>>(g, tp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, s32);
-      else    k_nbh_fused<false><<<blocks, nwarp * 32, smem, st>>>(g, tp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, s32);
-      c->launches++; CK(cudaGetLastError());
-      uint32_t hs[6]; unsigned long long tot2[2]; uint32_t e = 0;
-      {
-        // one host synchronisation for the three small results (statistics, totals, error word)
-        char* hp = static_cast<char*>(c->h_pinned);
-        CK(cudaMemcpyAsync(hp, stats, 6 * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(hp + 32, c->d_scalars64.p + 1, 2 * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(hp + 64, s32, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        memcpy(hs, hp, 24); memcpy(tot2, hp + 32, 16); memcpy(&e, hp + 64, 4);
-      }
-      bool again = false;
-      if (e & DERR_TILE_CAPACITY)
-      {
-        // this tile shape was too optimistic: clear the bit and retry with exact-capacity staging / a smaller tile
-        LAUNCH(k_clear_bits_u32, 1, 1, st, s32, (uint32_t)DERR_TILE_CAPACITY);
-        if (!c->nbh_full_cap) c->nbh_full_cap = true; else first_shape = pick + 1;
-        if (first_shape >= 4) { tiled = false; break; }
-        again = true;
-      }
-      if (hs[4] > (uint32_t)tp.cap_l) { c->nbh_cap_l = (int)(hs[4] * 1.15) + 8; again = true; }
-      if (hs[5] > c->nbh_slot_words) { c->nbh_slot_words = (uint32_t)(((size_t)(hs[5] * 1.12) + 64 + 7) & ~(size_t)7); again = true; }
-      else if (hs[4] > (uint32_t)tp.cap_l) { c->nbh_slot_words = (uint32_t)(((size_t)(c->nbh_slot_words * 1.25) + 7) & ~(size_t)7); }
-      if (again) continue;
-      c->pool_used = (int64_t)tot2[0]; c->max_neighbors = hs[0]; c->n_nonempty_inner = hs[1]; c->max_cell_count = hs[2]; c->max_stream = hs[3];
-      c->avg_stream = c->n_inner ? (double)tot2[1] / (double)c->n_inner : 0.0;
-      c->have_nbh = true;
-      if ((rc = cl_prepare(c, false, st))) return rc;
       if ((rc = t_end(c, XNB_T_NBH, st))) return rc;
       return check_device_errors(c, st);
     }
-    if (tiled) return c->fail(XNB_ERR_CAPACITY, "chunk_neighbors: tiled build did not converge");
   }
   // ---- per-particle two-pass form (count -> sizes -> scan -> fill)
   // the AMR tables prune whole sub-cells when they describe the current in-cell order (rebuild_amr ran after the last binning)
@@ -1131,7 +1205,7 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
   CK(c->pool.ensure((size_t)tot + 64, 0, 1.05));
   LAUNCH(k_nbh_pointers, nblk(g.n_cells, 256), 256, st, g.n_cells, c->pool.p, c->stream_off.p, c->stream_size.p, c->cell_stream.p, c->cell_stream_bytes.p);
   if (n) LAUNCH((k_nbh_build<true>), nblk(n, 128), 128, st, g, (int)n, gap, md2, (int)c->nbh_half_symmetric, (int)c->nbh_skip_ghosts, sgs_prune, sgc_prune, A.rx, A.ry, A.rz, c->atom_cell[c->cur_ac].p, c->cell_start.p, c->cell_count.p, out, s32);
-  c->have_nbh = true;
+  c->have_nbh = true; c->ghost_lists = true;          // the two-pass kernels build the lists of every cell
   if ((rc = cl_prepare(c, false, st))) return rc;
   if ((rc = t_end(c, XNB_T_NBH, st))) return rc;
   return check_device_errors(c, st);
@@ -1232,7 +1306,8 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
   // a full-list sweep over half_symmetric lists would apply every pair to one of its two particles only (the reference's operator
   // does exactly that, silently); here it is an error: use xnb_lennard_jones_force_symmetric + xnb_update_force_from_ghost
   if (c->nbh_half_symmetric) return c->fail(XNB_ERR_INVALID, "the full-list pair sweep needs full lists: chunk_neighbors was configured half_symmetric");
-  if (c->cl.ghost != ghost) { if ((rc = cl_prepare(c, ghost, st))) return rc; c->cl.ghost = ghost; }
+  if (ghost && (rc = ensure_ghost_lists(c, st))) return rc;
+  if (c->cl.ghost != ghost || (!c->cl.valid && !env_flag("XNB_SWEEP_STREAMS"))) { if ((rc = cl_prepare(c, ghost, st))) return rc; c->cl.ghost = ghost; }
   if (c->cl.valid)
   {
     const xnb_ctx::ClCfg& k = c->cl;
@@ -1251,22 +1326,8 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
     const unsigned nb = part == 0 ? k.blocks : part == 1 ? k.n_interior : k.n_boundary;
     const uint32_t* tl = part == 0 ? nullptr : part == 1 ? c->cl_tile_list.p : c->cl_tile_list.p + k.n_interior;
     if (nb == 0) return XNB_OK;
-    static bool cl2_attr_done_dev[XNB_MAX_DEVICES][2][2][2] = {};
-    auto& cl2_attr_done = cl2_attr_done_dev[c->device % XNB_MAX_DEVICES];
-#define XNB_CL2_LAUNCH(VAR) do { \
-      if (!cl2_attr_done[MODE][EV ? 1 : 0][VAR]) { \
-        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (k_lj_sweep_cl2<F, MODE, EV, VAR>))); \
-        CK(cudaFuncSetAttribute((k_lj_sweep_cl2<F, MODE, EV, VAR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes)); \
-        cl2_attr_done[MODE][EV ? 1 : 0][VAR] = true; } \
-      if (part == 0 && (rc = t_begin(c, XNB_T_FORCE, st))) return rc; \
-      k_lj_sweep_cl2<F, MODE, EV, VAR><<<nb, k.threads, k.smem, st>>>(c->g, k.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, \
-          fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, c->cl_groups.p, \
-          reinterpret_cast<const uint2*>(c->cl_rows.p), c->cl_perm.p, EV ? c->ev_partials.p : nullptr, c->d_scalars32.p, skip_if_nonzero, tl); } while (0)
-    if (k.paired) { if (k.var == 0) XNB_CL2_LAUNCH(0); else XNB_CL2_LAUNCH(1); }
-    else
     if (k.var == 0) XNB_CL_LAUNCH(0); else if (k.var == 1) XNB_CL_LAUNCH(1); else if (k.var == 2) XNB_CL_LAUNCH(2); else XNB_CL_LAUNCH(3);
 #undef XNB_CL_LAUNCH
-#undef XNB_CL2_LAUNCH
     c->launches++; CK(cudaGetLastError());
     return part == 0 ? t_end(c, XNB_T_FORCE, st) : XNB_OK;
   }
@@ -1639,8 +1700,8 @@ int xnb_energy_virial(xnb_ctx* c, double eps, double sig, double rcut, double* e
   const unsigned nb2 = nblk(n, 256);
   unsigned nb = 0; double* evp = nullptr;
   // MODE 0 accumulates into f: run it on a zeroed scratch copy of f so the state is untouched
-  DBuf<double> scratch; CK(scratch.ensure((size_t)c->n_total * 3 + 16));
-  DBuf<double> ekp; CK(ekp.ensure((size_t)nb2 + 16));
+  DBuf<double>& scratch = c->ev_scratch; CK(scratch.ensure((size_t)c->n_total * 3 + 16, 0, 1.1));
+  DBuf<double>& ekp = c->ev_ekin; CK(ekp.ensure((size_t)nb2 + 16, 0, 1.1));
   ParticlesP A = c->P(c->cur);
   CK(cudaMemsetAsync(scratch.p, 0, (size_t)c->n_total * 3 * 8, st));
   if (n)
@@ -1667,6 +1728,7 @@ int xnb_view_chunk_neighbors(xnb_ctx* c, const uint16_t* const** d_cell_stream, 
 {
   if (!c || !c->have_nbh) return XNB_ERR_INVALID;
   CK(cudaSetDevice(c->device));
+  { int rc = ensure_ghost_lists(c, nullptr); if (rc) return rc; }      // lists of the ghost cells are built on demand
   if (d_cell_stream) *d_cell_stream = (const uint16_t* const*)c->cell_stream.p;
   if (d_bytes) *d_bytes = c->cell_stream_bytes.p;
   if (max_neighbors) *max_neighbors = c->max_neighbors;
@@ -1679,6 +1741,8 @@ int xnb_get_streams(xnb_ctx* c, uint32_t* size_u16, uint16_t* data)
 {
   if (!c || !c->have_nbh) return XNB_ERR_INVALID;
   CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  { int rc = ensure_ghost_lists(c, nullptr); if (rc) return rc; }      // lists of the ghost cells are built on demand
   CK(cudaDeviceSynchronize());
   const size_t nc = (size_t)c->g.n_cells;
   std::vector<uint32_t> sz(nc); std::vector<unsigned long long> off(nc);
@@ -1723,6 +1787,19 @@ int xnb_get_backup(xnb_ctx* c, uint32_t* out)
   return XNB_OK;
 }
 
+int xnb_view_particles(xnb_ctx* c, xnb_particle_view* out)
+{
+  if (!c || !out) return XNB_ERR_INVALID;
+  int rc = ensure_grid(c); if (rc) return rc;
+  ParticlesP A = c->P(c->cur);
+  out->n_inner = c->n_inner; out->n_total = c->n_total; out->n_cells = c->g.n_cells;
+  out->rx = A.rx; out->ry = A.ry; out->rz = A.rz; out->vx = A.vx; out->vy = A.vy; out->vz = A.vz; out->fx = A.fx; out->fy = A.fy; out->fz = A.fz;
+  out->id = reinterpret_cast<uint64_t*>(A.id); out->type = A.type;
+  out->cell_start = c->cell_start.p; out->cell_count = c->cell_count.p; out->particle_cell = c->atom_cell[c->cur_ac].p;
+  return XNB_OK;
+}
+
+int64_t xnb_device_allocations(void) { return g_device_allocs; }
 int64_t xnb_rebuild_count(const xnb_ctx* c) { return c ? c->rebuilds : 0; }
 int64_t xnb_kernel_launches(const xnb_ctx* c) { return c ? c->launches : 0; }
 

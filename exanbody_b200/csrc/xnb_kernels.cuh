@@ -4,7 +4,8 @@
 //   K1c in-cell sub-grid : k_amr_sizes -> scan -> k_cell_sort<AMR> -> k_gather                    (rebuild_amr)
 //   K1e backup           : k_backup_r                                                             (backup_r)
 //   K6/7 ghosts          : k_ghost_count -> scan -> k_ghost_fill -> k_ghost_cells, k_ghost_pack   (ghost_comm_scheme, ghost_update_*)
-//   K2  neighbour build  : k_nbh_build<COUNT> -> k_nbh_cell_sizes -> scan -> k_nbh_build<FILL>    (chunk_neighbors)
+//   K2  neighbour build  : k_nbh_bits (xnb_nbh_bits.cuh); here the per-particle two-pass fallback
+//                          k_nbh_build<COUNT> -> k_nbh_cell_sizes -> scan -> k_nbh_build<FILL>    (chunk_neighbors)
 //   K3  pair sweep       : k_lj_force<...>                                                         (lennard_jones_force [+ fused epilogue])
 //   K4/5 integrate       : k_verlet_first_half, k_push_f_v_r, k_push_f_v, k_displ_over, ...
 //
@@ -171,9 +172,10 @@ XNB_DEVINL void cell_origin(const GridP& g, uint32_t c, double& ox, double& oy, 
 //   AMR=true  : (sub-cell index, particle id): the sub-cell grouping of project_particles_in_sub_grids
 //               (amr_grid_algorithm.h:188-299); sub_grid_cells[] gets the cumulative end offsets (:283-292)
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int CELLSORT_MAX = 2048;   // particles per cell the in-cell sort handles (reference hard limit: 65535)
+constexpr int CELLSORT_MAX = 2048;   // particles per cell sorted out of shared memory; larger cells (the format allows 65535) rank through global scratch
 constexpr int CELLSORT_THREADS = 128;
 
+// big_keys / big_srcs: global scratch of n_src entries for cells beyond CELLSORT_MAX (slices [cell_start, cell_start + n) are disjoint)
 template <bool AMR>
 __global__ void __launch_bounds__(CELLSORT_THREADS)
 k_cell_sort(GridP g, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
@@ -181,16 +183,20 @@ k_cell_sort(GridP g, const uint32_t* __restrict__ cell_start, const uint32_t* __
             const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
             const unsigned long long* __restrict__ id,
             const uint8_t* __restrict__ side_lut, const unsigned long long* __restrict__ sub_grid_start,
-            uint32_t* __restrict__ sub_grid_cells, uint32_t* __restrict__ err)
+            uint32_t* __restrict__ sub_grid_cells, unsigned long long* __restrict__ big_keys, uint32_t* __restrict__ big_srcs, uint32_t* __restrict__ err)
 {
-  __shared__ unsigned long long keys[CELLSORT_MAX];
-  __shared__ uint32_t srcs[CELLSORT_MAX];
+  __shared__ unsigned long long s_keys[CELLSORT_MAX];
+  __shared__ uint32_t s_srcs[CELLSORT_MAX];
   __shared__ uint32_t hist[AMR ? 4096 : 1];
   const int c = blockIdx.x;
   const int n = (int)cell_count[c];
   if (n == 0) return;
-  if (n > CELLSORT_MAX) { if (threadIdx.x == 0) atomicOr(err, DERR_SORT_CAPACITY); return; }
+  if (n > 65535) { if (threadIdx.x == 0) atomicOr(err, DERR_CELL_OVERFLOW); return; }
   const uint32_t s0 = cell_start[c];
+  const bool big = n > CELLSORT_MAX;
+  if (big && !big_keys) { if (threadIdx.x == 0) atomicOr(err, DERR_SORT_CAPACITY); return; }
+  unsigned long long* const keys = big ? big_keys + s0 : s_keys;
+  uint32_t* const srcs = big ? big_srcs + s0 : s_srcs;
   int side = 1;
   if (AMR)
   {
@@ -221,7 +227,7 @@ k_cell_sort(GridP g, const uint32_t* __restrict__ cell_start, const uint32_t* __
     srcs[t] = src;
   }
   __syncthreads();
-  // rank sort (n is small: 32..256 in the benchmark configs); ids are unique so ranks are a permutation
+  // rank sort (32..256 particles per cell in the benchmark configurations); ids are unique so the ranks are a permutation
   for (int t = threadIdx.x; t < n; t += blockDim.x)
   {
     const unsigned long long my = keys[t];
@@ -715,499 +721,24 @@ __global__ void k_nbh_pointers(int n_cells, uint16_t* __restrict__ pool, const u
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// K2 (tiled form): the whole chunk neighbour build in ONE kernel, k_nbh_fused.
-//
-// One block = one tile of ti x tj cells (same k) of the whole local grid (ghost cells included,
-// chunk_neighbors_execute.h:110).  The block stages the tile's halo box into shared memory as one float4 per particle,
-// q = (-2x', -2y', -2z', |x'|^2) with x' = x - O relative to the centre O of the box.  One warp owns one cell A
-// (lane = particle p_a, 32 at a time); every neighbour cell B is swept with ALL lanes reading the same q_j (one
-// broadcast LDS.128), so   d2 - |x_a'|^2 = q.w + x_a' q.x + y_a' q.y + z_a' q.z   costs three FFMA per candidate.
-// The fp32 value only CLASSIFIES: "surely in" (<= max_dist^2 - band), "surely out" (> max_dist^2 + band); the few
-// candidates inside the band (and, in the own cell, closer than the band to zero) are decided by the exact fp64 test of
-// the reference (dr = r_a - r_b, d2 = norm2(dr), d2 > 0 && d2 <= max_dist^2, :225-227) on the original coordinates, so
-// the lists are bit-identical to the all-fp64 form.  band is derived from the largest |x'| actually staged.
-// Accepted p_b are appended to the lane's list in shared memory in the reference's stream order (ascending cell code,
-// ascending p_b => already sorted and unique, :308-324); when the 32 lists of a chunk are complete the warp writes the
-// u32 offset-table entries and copies the lists, coalesced, into the cell's stream.
-// Streams live in fixed slots of the pool: cell c owns pool[c*slot_words, (c+1)*slot_words) (deterministic placement,
-// no allocator and no second pass; the reference uses a bump allocator, chunk_neighbors.h:70-96).  If a list or a cell
-// outgrows its capacity the kernel keeps counting, reports the size it needs, and the host re-runs it with more room.
-// ------------------------------------------------------------------------------------------------------------------
-struct NbhTileP
-{
-  int ti, tj;            // cells per tile along i, j
-  int tiles_i, tiles_j;  // tiles per k-plane (covering the whole local grid)
-  int gap;               // neighbour cell layers
-  int cap;               // staging capacity in particles
-  int cap_l;             // list capacity per particle (u16 words)
-  int tail;              // extra words behind the last lane's list area (overflow stays inside the block's memory)
-  int slot_words;        // stream capacity per cell (u16 words, multiple of 8)
-  double max_dist2;
-};
-
-struct NbhCellOut
-{
-  uint16_t* pool;
-  uint16_t** cell_stream;            // per cell stream pointer (nullptr for empty cells, host_write_accessor.h:47-52)
-  uint32_t* stream_size;             // u16 words
-  uint32_t* cell_stream_bytes;       // bytes (GridChunkNeighbors::m_cell_stream_size)
-  unsigned long long* stream_off;    // u16 offset of the stream in the pool
-  uint32_t* stats;                   // [0] max neighbours [1] non-empty inner cells [2] max cell count [3] max padded stream [4] needed cap_l [5] needed slot_words
-  unsigned long long* totals;        // [0] padded words of all cells [1] padded words of inner cells
-};
-
-XNB_DEVINL unsigned float_flip(float f) { return __float_as_uint(f); }   // for non-negative floats the bit pattern is monotone
-
-// exact decision for one ambiguous candidate (rare): the reference's test on the original fp64 coordinates
-__device__ __noinline__ bool nbh_exact_one(uint32_t self, uint32_t j, double max_dist2,
-                                           const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz)
-{
-  const double d2 = norm2_exact(__dadd_rn(rx[self], -rx[j]), __dadd_rn(ry[self], -ry[j]), __dadd_rn(rz[self], -rz[j]));
-  return j != self && d2 > 0.0 && d2 <= max_dist2;
-}
-
-// hot-loop step of the tiled build: if (t <= hi) { append v to the lane's list; mx = max(mx, t) } as four predicated
-// instructions on a shared-state-space address (no generic-address arithmetic in the loop)
-template <class LT>
-XNB_DEVINL void nbh_append(uint32_t& wa, float& mx, float t, float hi, uint32_t v)
-{
-  if (sizeof(LT) == 1)
-    asm volatile("{ .reg .pred p; setp.le.f32 p, %2, %3; @p st.shared.u8 [%0], %4; @p add.u32 %0, %0, 1; @p max.f32 %1, %1, %2; }"
-                 : "+r"(wa), "+f"(mx) : "f"(t), "f"(hi), "r"(v) : "memory");
-  else
-    asm volatile("{ .reg .pred p; setp.le.f32 p, %2, %3; @p st.shared.u16 [%0], %4; @p add.u32 %0, %0, 2; @p max.f32 %1, %1, %2; }"
-                 : "+r"(wa), "+f"(mx) : "f"(t), "f"(hi), "r"(v) : "memory");
-}
-template <class LT> XNB_DEVINL uint32_t nbh_lds(uint32_t a)
-{
-  uint32_t v;
-  if (sizeof(LT) == 1) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
-}
-template <class LT> XNB_DEVINL void nbh_sts(uint32_t a, uint32_t v)
-{
-  if (sizeof(LT) == 1) asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory");
-  else asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory");
-}
-
-constexpr int NBH_MAX_HALO = 1024;   // halo cells per tile the kernel supports ((ti+2gap)(tj+2gap)(2gap+1))
-constexpr uint32_t NBH_TRANSPOSE_MAX = 8;   // a trailing chunk of at most this many particles is built candidate-per-lane
-// lane-per-particle chunks of a cell of n particles: chunks of 32 until at most NBH_TRANSPOSE_MAX particles remain; those are
-// built candidate-per-lane by the warp that owns the last chunk
-XNB_DEVINL uint32_t nbh_full_chunks(uint32_t n) { return n == 0u ? 0u : (max(n, NBH_TRANSPOSE_MAX + 1u) - NBH_TRANSPOSE_MAX + 31u) >> 5; }
-constexpr int NBH_MAX_TCELLS = 8;    // cells per tile
-constexpr int NBH_MAX_CHUNKS = 32;   // 32-particle chunks per cell (cells of up to 1024 particles)
-
-// U8 = true: list areas hold bytes (p_b, counts < 128; group header = 0x80|slot, n), expanded to the u16 stream words
-// when the lists are copied out -- half the shared memory per warp, twice the resident warps.  Requires max cell count
-// <= 127 and (2gap+1)^3 <= 128.  U8 = false: list areas hold the final u16 words.
-template <bool U8>
-__global__ void __launch_bounds__(256, 2)   // two blocks per SM (shared memory allows no more): <= 128 registers, no spills in either form
-k_nbh_fused(GridP g, NbhTileP tp,
-            const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
-            const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
-            NbhCellOut out, uint32_t* __restrict__ err)
-{
-  typedef typename std::conditional<U8, uint8_t, uint16_t>::type LT;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t hstart[NBH_MAX_HALO + 1];   // staged index of each halo cell's first particle (cells padded to multiples of 4)
-  __shared__ uint32_t hfirst[NBH_MAX_HALO];       // global index of each halo cell's first particle
-  __shared__ uint16_t hcount[NBH_MAX_HALO];       // particles of each halo cell
-  __shared__ uint32_t s_scan[32];
-  __shared__ unsigned s_rmax;
-  __shared__ uint32_t s_stats[6];
-  __shared__ unsigned long long s_tot[2];
-  __shared__ uint32_t ustart[NBH_MAX_TCELLS + 1];
-  __shared__ uint32_t s_cum[NBH_MAX_TCELLS][NBH_MAX_CHUNKS + 1];   // list words of the cell before chunk ic (0xFFFFFFFF = not yet known)
-  __shared__ uint32_t s_next, s_done;
-  __shared__ uint16_t s_enc[128];
-  float4* S4 = reinterpret_cast<float4*>(smem_raw);
-  LT* LB = reinterpret_cast<LT*>(smem_raw + (size_t)tp.cap * 16);
-
-  int b = blockIdx.x;
-  const int t_i = b % tp.tiles_i; b /= tp.tiles_i;
-  const int t_j = b % tp.tiles_j; const int ck = b / tp.tiles_j;
-  const int ci0 = t_i * tp.ti, cj0 = t_j * tp.tj;
-  const int tci = min(tp.ti, g.dims[0] - ci0), tcj = min(tp.tj, g.dims[1] - cj0);
-  const int tcells = tci * tcj;
-  const int gap = tp.gap;
-  const int nslot1 = 2 * gap + 1;
-  const int bx0 = max(ci0 - gap, 0), bx1 = min(ci0 + tci - 1 + gap, g.dims[0] - 1);
-  const int by0 = max(cj0 - gap, 0), by1 = min(cj0 + tcj - 1 + gap, g.dims[1] - 1);
-  const int bz0 = max(ck - gap, 0), bz1 = min(ck + gap, g.dims[2] - 1);
-  const int HX = bx1 - bx0 + 1, HY = by1 - by0 + 1, HZ = bz1 - bz0 + 1;
-  const int NH = HX * HY * HZ;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-
-  // ---- prefix table of the halo cells
-  {
-    uint32_t carry = 0;
-    for (int base = 0; base < NH; base += blockDim.x)
-    {
-      const int h = base + threadIdx.x;
-      uint32_t cnt = 0;
-      if (h < NH)
-      {
-        const int hxq = h % HX, hyq = (h / HX) % HY, hzq = h / (HX * HY);
-        const int c = ijk_to_index(g.dims, bx0 + hxq, by0 + hyq, bz0 + hzq);
-        cnt = cell_count[c]; hfirst[h] = cell_start[c]; hcount[h] = (uint16_t)cnt;
-        cnt = (cnt + 3u) & ~3u;
-      }
-      uint32_t total;
-      const uint32_t off = block_exclusive_scan<uint32_t>(cnt, &total, s_scan);
-      if (h < NH) hstart[h] = carry + off;
-      carry += total;
-    }
-    if (threadIdx.x == 0) { hstart[NH] = carry; s_rmax = 0u; s_tot[0] = 0ull; s_tot[1] = 0ull; s_next = 0u; s_done = 0u; }
-    if (threadIdx.x < 6) s_stats[threadIdx.x] = 0u;
-    if (U8)
-      for (int sl = threadIdx.x; sl < nslot1 * nslot1 * nslot1; sl += blockDim.x)
-      {
-        // encode_cell_index (chunk_neighbors.h:137-150) of neighbour slot sl = ((rk+gap)*n + (rj+gap))*n + (ri+gap)
-        const int ri = sl % nslot1 - gap, rj = (sl / nslot1) % nslot1 - gap, rk = sl / (nslot1 * nslot1) - gap;
-        s_enc[sl] = (uint16_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint16_t)(ri + 16);
-      }
-  }
-  __syncthreads();
-  const uint32_t n_halo = hstart[NH];
-  if (n_halo > (uint32_t)tp.cap) { if (threadIdx.x == 0) atomicOr(err, DERR_TILE_CAPACITY); return; }
-
-  // ---- work units = (tile cell, 32-particle chunk), handed out in order through s_next; empty cells are closed here
-  if (threadIdx.x == 0)
-  {
-    uint32_t acc = 0;
-    for (int q = 0; q < tcells; q++)
-    {
-      const int hq = ((ck - bz0) * HY + (cj0 + q / tci - by0)) * HX + (ci0 + q % tci - bx0);
-      const uint32_t nq = hcount[hq];
-      // work units: chunks of 32 particles; a trailing chunk of <= NBH_TRANSPOSE_MAX particles is its own (cheap) unit
-      ustart[q] = acc; acc += nbh_full_chunks(nq);
-      s_cum[q][0] = 0u;
-      for (uint32_t ic = 1; ic <= ((nq + 31u) >> 5) && ic <= (uint32_t)NBH_MAX_CHUNKS; ic++) s_cum[q][ic] = 0xFFFFFFFFu;
-      if (nq == 0)
-      {
-        const int cq = ijk_to_index(g.dims, ci0 + q % tci, cj0 + q / tci, ck);
-        out.cell_stream[cq] = nullptr; out.stream_size[cq] = 0u; out.cell_stream_bytes[cq] = 0u;
-        out.stream_off[cq] = (unsigned long long)cq * (unsigned long long)tp.slot_words;
-      }
-    }
-    ustart[tcells] = acc;
-  }
-
-  // ---- stage q = (-2x', -2y', -2z', |x'|^2), one warp per halo cell;  O = centre of the tile (fp64)
-  const double ox = __dadd_rn(g.org[0], __dmul_rn((double)(g.off[0] + ci0) + 0.5 * (double)tci, g.cs));
-  const double oy = __dadd_rn(g.org[1], __dmul_rn((double)(g.off[1] + cj0) + 0.5 * (double)tcj, g.cs));
-  const double oz = __dadd_rn(g.org[2], __dmul_rn((double)(g.off[2] + ck) + 0.5, g.cs));
-  {
-    float rmax = 0.f;
-    // three halo cells per warp and trip, all loads issued before the first use (the loop is latency bound otherwise)
-    for (int h0 = warp; h0 < NH; h0 += 3 * nwarp)
-    {
-      double px[3], py[3], pz[3]; uint32_t d0[3], cnt[3], cnt4[3], s0[3];
-#pragma unroll
-      for (int u = 0; u < 3; u++)
-      {
-        const int h = h0 + u * nwarp;
-        d0[u] = cnt[u] = cnt4[u] = s0[u] = 0u; px[u] = py[u] = pz[u] = 0.;
-        if (h < NH)
-        {
-          d0[u] = hstart[h]; cnt[u] = hcount[h]; cnt4[u] = hstart[h + 1] - d0[u]; s0[u] = hfirst[h];
-          if ((uint32_t)lane < cnt[u]) { px[u] = rx[s0[u] + lane]; py[u] = ry[s0[u] + lane]; pz[u] = rz[s0[u] + lane]; }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 3; u++)
-      {
-        for (uint32_t p = lane; p < cnt4[u]; p += 32)
-        {
-          if (p < cnt[u])
-          {
-            const double xd = p < 32u ? px[u] : rx[s0[u] + p], yd = p < 32u ? py[u] : ry[s0[u] + p], zd = p < 32u ? pz[u] : rz[s0[u] + p];
-            const float x = (float)(xd - ox), y = (float)(yd - oy), z = (float)(zd - oz);
-            rmax = fmaxf(rmax, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
-            S4[d0[u] + p] = make_float4(-2.f * x, -2.f * y, -2.f * z, (float)((double)x * x + (double)y * y + (double)z * z));
-          }
-          else S4[d0[u] + p] = make_float4(0.f, 0.f, 0.f, INFINITY);     // pad: never within any distance
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-    if (lane == 0) atomicMax(&s_rmax, float_flip(rmax));
-  }
-  __syncthreads();
-  // classification band: |fp32 value - exact d2| <= 2^-24 (60 R^2 + 1.01 max_dist2), R = max |coordinate|;
-  // the band used is 2^-24 (128 R^2 + 4 max_dist2), more than twice that
-  const double R = (double)__uint_as_float(s_rmax);
-  const double band = 5.9604644775390625e-08 * (128.0 * R * R + 4.0 * tp.max_dist2);
-  const int cap_l = tp.cap_l;
-  LT* const Lw = LB + (size_t)warp * (size_t)(31 * cap_l + tp.tail);   // this warp's 32 list areas
-  LT* const L = Lw + (size_t)lane * cap_l;
-  const uint32_t n_units = ustart[tcells];
-
-  for (;;)
-  {
-    uint32_t u = 0;
-    if (lane == 0) u = atomicAdd(&s_next, 1u);
-    u = __shfl_sync(0xffffffffu, u, 0);
-    if (u >= n_units) break;
-    int q = 0;
-    while (q + 1 < tcells && u >= ustart[q + 1]) q++;
-    const uint32_t ic0 = u - ustart[q];
-    const int cia = ci0 + q % tci, cja = cj0 + q / tci;
-    const int ca = ijk_to_index(g.dims, cia, cja, ck);
-    const int hA = ((ck - bz0) * HY + (cja - by0)) * HX + (cia - bx0);
-    const uint32_t sA = hstart[hA], nA = hcount[hA], gA = hfirst[hA];
-    const unsigned long long slot_off = (unsigned long long)ca * (unsigned long long)tp.slot_words;
-    uint16_t* const base = out.pool + slot_off;
-    uint16_t* const lists = base + 2u * (nA + 1u);
-    const uint32_t nfull = nbh_full_chunks(nA);
-    // pass 0: this unit's lane-per-particle chunk; pass 1 (owner of the last chunk only): the trailing few particles
-    for (uint32_t pass = 0; pass < 2u; pass++)
-    {
-      const uint32_t ic = ic0 + pass;
-      const bool transposed = pass == 1u;
-      if (transposed && !(ic == nfull && nA > 32u * nfull)) break;
-      const uint32_t ia = ic * 32u + lane;
-      const bool active = ia < nA;
-      uint32_t cw = 1, groups = 0;                               // L[0] = group counter
-      if (!transposed)
-      {
-        // ---- lane = particle p_a; all lanes sweep neighbour cell B reading the same q_j (broadcast)
-        const float4 qa = S4[sA + (active ? ia : 0u)];
-        const float xi = -0.5f * qa.x, yi = -0.5f * qa.y, zi = -0.5f * qa.z;
-        const float lo = (float)(tp.max_dist2 - band - (double)qa.w);
-        const float hi = active ? (float)(tp.max_dist2 + band - (double)qa.w) : -INFINITY;   // idle lanes accept nothing
-        const float zlo = (float)(band - (double)qa.w);            // own cell only: d2 <= band is "ambiguous" (d2 > 0 test)
-        const uint32_t atom = gA + ia;
-        const uint32_t Lsh = (uint32_t)__cvta_generic_to_shared(L);
-        for (int rk = -gap; rk <= gap; rk++)
-        {
-          const int bk = ck + rk;
-          if (bk < 0 || bk >= g.dims[2]) continue;
-          for (int rj = -gap; rj <= gap; rj++)
-          {
-            const int bj = cja + rj;
-            if (bj < 0 || bj >= g.dims[1]) continue;
-            for (int ri = -gap; ri <= gap; ri++)
-            {
-              const int bi = cia + ri;
-              if (bi < 0 || bi >= g.dims[0]) continue;
-              const int hB = ((bk - bz0) * HY + (bj - by0)) * HX + (bi - bx0);
-              const uint32_t nB = hcount[hB];
-              if (nB == 0) continue;
-              const uint32_t gB = hfirst[hB];
-              const float4* __restrict__ Q = S4 + hstart[hB];
-              const uint32_t hdr = cw;
-              const uint32_t wa0 = Lsh + (cw + 2u) * (uint32_t)sizeof(LT);
-              uint32_t wa = wa0;
-              float mx = -INFINITY;                                // largest accepted fp32 value of this segment
-              // four candidates per trip (cells are staged padded to multiples of 4 with never-accepted entries):
-              // 4 x (LDS.128 broadcast, 3 FFMA, compare, predicated append)
-              for (uint32_t j = 0; j < nB; j += 4)
-              {
-                float t[4];
-#pragma unroll
-                for (int v = 0; v < 4; v++)
-                {
-                  const float4 qj = Q[j + v];
-                  t[v] = fmaf(zi, qj.z, fmaf(yi, qj.y, fmaf(xi, qj.x, qj.w)));
-                }
-#pragma unroll
-                for (int v = 0; v < 4; v++) nbh_append<LT>(wa, mx, t[v], hi, j + v);
-              }
-              const bool own = rk == 0 && rj == 0 && ri == 0;
-              if (own || mx > lo)
-              {
-                // some accepted candidate of this segment sits inside the band (or this is the own cell): re-walk the
-                // few accepted entries and decide the ambiguous ones with the exact fp64 test of the reference
-                uint32_t wr = wa0;
-                for (uint32_t rd = wa0; rd < wa; rd += (uint32_t)sizeof(LT))
-                {
-                  const uint32_t jj = nbh_lds<LT>(rd);
-                  const float4 qj = Q[jj];
-                  const float t = fmaf(zi, qj.z, fmaf(yi, qj.y, fmaf(xi, qj.x, qj.w)));
-                  bool keep = jj < nB && !(own && jj == ia);      // (jj >= nB: only in an overflowed list area; the build is re-run)
-                  // (cell_a,p_a) != (cell_b,p_b); d2 > 0 is decided exactly when the fp32 value is within the band of zero
-                  if (keep && (t > lo || (own && t <= zlo))) keep = nbh_exact_one(atom, gB + jj, tp.max_dist2, rx, ry, rz);
-                  if (keep) { nbh_sts<LT>(wr, jj); wr += (uint32_t)sizeof(LT); }
-                }
-                wa = wr;
-              }
-              const uint32_t n = (wa - wa0) / (uint32_t)sizeof(LT);
-              if (n)
-              {
-                const int slot = ((rk + gap) * nslot1 + (rj + gap)) * nslot1 + (ri + gap);
-                // encode_cell_index (chunk_neighbors.h:137-150); in byte mode the code is looked up at copy-out
-                L[hdr] = U8 ? (LT)(0x80 | slot) : (LT)((uint16_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint16_t)(ri + 16));
-                L[hdr + 1] = (LT)n;
-                cw = hdr + 2u + n; groups++;
-              }
-            }
-          }
-        }
-      }
-      else
-      {
-        // ---- trailing chunk of a few particles: one particle at a time, lane = candidate, accepted candidates appended
-        // in order with ballot + popc (a full lane-per-particle pass would cost as much as a 32-particle chunk)
-        const uint32_t nrem = nA - ic * 32u;
-        const uint32_t lt_mask = (1u << lane) - 1u;
-        for (uint32_t a = 0; a < nrem; a++)
-        {
-          const uint32_t iaa = ic * 32u + a;
-          const float4 qa = S4[sA + iaa];
-          const float xi = -0.5f * qa.x, yi = -0.5f * qa.y, zi = -0.5f * qa.z;
-          const float lo = (float)(tp.max_dist2 - band - (double)qa.w);
-          const float hi = (float)(tp.max_dist2 + band - (double)qa.w);
-          const float zlo = (float)(band - (double)qa.w);
-          const uint32_t atom = gA + iaa;
-          LT* const La = Lw + (size_t)a * cap_l;
-          uint32_t cwa = 1, ga = 0;
-          for (int rk = -gap; rk <= gap; rk++)
-          {
-            const int bk = ck + rk;
-            if (bk < 0 || bk >= g.dims[2]) continue;
-            for (int rj = -gap; rj <= gap; rj++)
-            {
-              const int bj = cja + rj;
-              if (bj < 0 || bj >= g.dims[1]) continue;
-              for (int ri = -gap; ri <= gap; ri++)
-              {
-                const int bi = cia + ri;
-                if (bi < 0 || bi >= g.dims[0]) continue;
-                const int hB = ((bk - bz0) * HY + (bj - by0)) * HX + (bi - bx0);
-                const uint32_t nB = hcount[hB];
-                if (nB == 0) continue;
-                const uint32_t gB = hfirst[hB];
-                const float4* __restrict__ Q = S4 + hstart[hB];
-                const bool own = rk == 0 && rj == 0 && ri == 0;
-                const uint32_t hdr = cwa;
-                uint32_t wi = cwa + 2u;
-                for (uint32_t j0 = 0; j0 < nB; j0 += 64u)
-                {
-                  // two candidates per lane (j, j + 32): most cells take a single trip
-                  const uint32_t j = j0 + lane, j2 = j + 32u;
-                  const bool valid = j < nB, valid2 = j2 < nB;
-                  const float4 qj = Q[valid ? j : 0u], qk = Q[valid2 ? j2 : 0u];
-                  const float t = fmaf(zi, qj.z, fmaf(yi, qj.y, fmaf(xi, qj.x, qj.w)));
-                  const float t2 = fmaf(zi, qk.z, fmaf(yi, qk.y, fmaf(xi, qk.x, qk.w)));
-                  bool acc = valid && t <= hi && !(own && j == iaa);
-                  bool acc2 = valid2 && t2 <= hi && !(own && j2 == iaa);
-                  if (acc && (t > lo || (own && t <= zlo))) acc = nbh_exact_one(atom, gB + j, tp.max_dist2, rx, ry, rz);
-                  if (acc2 && (t2 > lo || (own && t2 <= zlo))) acc2 = nbh_exact_one(atom, gB + j2, tp.max_dist2, rx, ry, rz);
-                  const uint32_t m = __ballot_sync(0xffffffffu, acc), m2 = __ballot_sync(0xffffffffu, acc2);
-                  if (acc) La[wi + (uint32_t)__popc(m & lt_mask)] = (LT)j;
-                  wi += (uint32_t)__popc(m);
-                  if (acc2) La[wi + (uint32_t)__popc(m2 & lt_mask)] = (LT)j2;
-                  wi += (uint32_t)__popc(m2);
-                }
-                const uint32_t n = wi - (hdr + 2u);
-                if (n)
-                {
-                  const int slot = ((rk + gap) * nslot1 + (rj + gap)) * nslot1 + (ri + gap);
-                  if (lane == 0)
-                  {
-                    La[hdr] = U8 ? (LT)(0x80 | slot) : (LT)((uint16_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint16_t)(ri + 16));
-                    La[hdr + 1] = (LT)n;
-                  }
-                  cwa = wi; ga++;
-                }
-              }
-            }
-          }
-          if (lane == a) { cw = cwa; groups = ga; }
-        }
-        __syncwarp();
-      }
-      L[0] = (LT)groups;
-      const uint32_t len = active ? cw : 0u;
-      const uint32_t ncand = active ? cw - 1u - 2u * groups : 0u;
-      if (active && (groups >= 65535u || ncand >= 65535u)) atomicOr(err, DERR_GROUP_OVERFLOW);
-      // warp statistics + exclusive scan of the list lengths
-      uint32_t x = len, mxl = len, mxc = ncand;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { mxl = max(mxl, __shfl_xor_sync(0xffffffffu, mxl, o)); mxc = max(mxc, __shfl_xor_sync(0xffffffffu, mxc, o)); }
-      const uint32_t chunk_total = __shfl_sync(0xffffffffu, x, 31);
-      // list words of this cell before this chunk: published by the warp that owns the previous chunk
-      uint32_t run = 0;
-      if (lane == 0)
-      {
-        volatile uint32_t* cum = &s_cum[q][0];
-        if (ic < (uint32_t)NBH_MAX_CHUNKS) { while ((run = cum[ic]) == 0xFFFFFFFFu) { __nanosleep(64); } cum[ic + 1] = run + chunk_total; }
-        atomicMax(&s_stats[0], mxc);
-        if (mxl > (uint32_t)cap_l) atomicMax(&s_stats[4], mxl);
-      }
-      run = __shfl_sync(0xffffffffu, run, 0);
-      const uint32_t off = run + x - len;
-      const bool ovf = mxl > (uint32_t)cap_l || 2u * (nA + 1u) + run + chunk_total > (uint32_t)tp.slot_words;
-      __syncwarp();
-      if (!ovf)
-      {
-        if (active)
-        {
-          // offset table entry (chunk_neighbors_execute.h:279-283) and closing entry (:390-398)
-          reinterpret_cast<uint32_t*>(base)[ia] = off + 1u;
-          if (ia == nA - 1u) reinterpret_cast<uint32_t*>(base)[nA] = off + len + 1u;
-        }
-        if (len)
-        {
-          // every lane copies its own list: 8-byte stores once the destination is 8-byte aligned (the 32 lists of a chunk are
-          // adjacent in the stream, so the partial sectors of neighbouring lanes merge in L2)
-          uint16_t* const dst = lists + off;
-          const uint32_t head = min(len, (uint32_t)(((8u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 7u)) & 7u) >> 1));
-          uint32_t v = 0;
-          for (; v < head; v++) dst[v] = (uint16_t)L[v];
-          for (; v + 4u <= len; v += 4u)
-          {
-            const uint32_t w0 = L[v], w1 = L[v + 1], w2 = L[v + 2], w3 = L[v + 3];
-            *reinterpret_cast<uint2*>(dst + v) = make_uint2(w0 | (w1 << 16), w2 | (w3 << 16));
-          }
-          for (; v < len; v++) dst[v] = (uint16_t)L[v];
-          if (U8)
-          {
-            // byte mode: the group headers hold 0x80|slot; hop over them and write the cell codes
-            uint32_t pos = 1;
-            for (uint32_t gq = 0; gq < groups; gq++) { const uint32_t code = L[pos], n = L[pos + 1]; dst[pos] = s_enc[code & 0x7fu]; pos += 2u + n; }
-          }
-        }
-      }
-      __syncwarp();
-      // ---- the warp that closes the cell's last chunk does the per cell bookkeeping
-      if (lane == 0 && (ic + 1u) * 32u >= nA)
-      {
-        const uint32_t sz = 2u * (nA + 1u) + run + chunk_total;
-        const uint32_t szp = (sz + 7u) & ~7u;
-        const bool fits = szp <= (uint32_t)tp.slot_words;
-        out.cell_stream[ca] = fits ? base : nullptr;
-        out.stream_size[ca] = sz;
-        out.cell_stream_bytes[ca] = sz * 2u;
-        out.stream_off[ca] = slot_off;
-        if (fits) for (uint32_t p = sz; p < szp; p++) base[p] = 0;   // deterministic padding
-        atomicMax(&s_stats[2], nA); atomicMax(&s_stats[3], szp); atomicMax(&s_stats[5], szp);
-        atomicAdd(&s_tot[0], (unsigned long long)szp);
-        const bool inner = cia >= g.gl && cia < g.dims[0] - g.gl && cja >= g.gl && cja < g.dims[1] - g.gl && ck >= g.gl && ck < g.dims[2] - g.gl;
-        if (inner) { atomicAdd(&s_tot[1], (unsigned long long)szp); atomicAdd(&s_stats[1], 1u); }
-      }
-    }
-  }
-  // ---- the last warp to run out of work flushes the block statistics (no block-wide barrier: warps retire independently)
-  uint32_t done = 0;
-  if (lane == 0) { __threadfence_block(); done = atomicAdd(&s_done, 1u); }
-  done = __shfl_sync(0xffffffffu, done, 0);
-  if (done == (uint32_t)nwarp - 1u)
-  {
-    __threadfence_block();
-    if (lane < 6 && s_stats[lane]) { if (lane == 1) atomicAdd(&out.stats[1], s_stats[1]); else atomicMax(&out.stats[lane], s_stats[lane]); }
-    if (lane < 2 && s_tot[lane]) atomicAdd(&out.totals[lane], s_tot[lane]);
-  }
-}
-
 __global__ void k_clear_bits_u32(uint32_t* p, uint32_t bits) { *p &= ~bits; }
+
+// occupancy of the local grid: out[0] = largest cell count (all cells), out[1] = non-empty inner cells
+__global__ void k_cell_stats(GridP g, const uint32_t* __restrict__ cell_count, uint32_t* __restrict__ out)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t v = 0; bool ne = false;
+  if (c < g.n_cells)
+  {
+    v = cell_count[c];
+    const int ci = c % g.dims[0], cj = (c / g.dims[0]) % g.dims[1], ck = c / (g.dims[0] * g.dims[1]);
+    ne = v > 0 && ci >= g.gl && ci < g.dims[0] - g.gl && cj >= g.gl && cj < g.dims[1] - g.gl && ck >= g.gl && ck < g.dims[2] - g.gl;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, ne);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) { if (v) atomicMax(out, v); if (m) atomicAdd(out + 1, (uint32_t)__popc(m)); }
+}
 
 // maximum of a u32 array (cell counts) -> *out (atomicMax)
 __global__ void k_max_u32(int n, const uint32_t* __restrict__ a, uint32_t* __restrict__ out)

@@ -72,8 +72,10 @@ XNB_DEVINL ClTables cl_tables(unsigned char* smem, const ClTileP& tp)
 }
 
 // block-cooperative; ends with a barrier.  Tile cells are numbered q = (kk * tcj + jj) * tci + ii.
+// sel_mode 1: only tile cells outside the inner range take part (their particles are the tile particles); the others are still
+// staged as candidates
 XNB_DEVINL void cl_setup(const GridP& g, const ClTile& T, const ClTables& tb, const uint32_t* __restrict__ cell_start,
-                         const uint32_t* __restrict__ cell_count, uint32_t* s_scan)
+                         const uint32_t* __restrict__ cell_count, uint32_t* s_scan, int sel_mode = 0)
 {
   const int HXY = T.HX * T.HY;
   uint32_t carry = 0;
@@ -103,6 +105,11 @@ XNB_DEVINL void cl_setup(const GridP& g, const ClTile& T, const ClTables& tb, co
       const int ii = q % T.tci, jj = (q / T.tci) % T.tcj, kk = q / (T.tci * T.tcj);
       h = ((T.ck0 + kk - T.bz0) * T.HY + (T.cj0 + jj - T.by0)) * T.HX + (T.ci0 + ii - T.bx0);
       cnt = tb.hstart[h + 1] - tb.hstart[h];
+      if (sel_mode == 1)
+      {
+        const int ci = T.ci0 + ii, cj = T.cj0 + jj, ck = T.ck0 + kk;
+        if (ci >= g.gl && ci < g.dims[0] - g.gl && cj >= g.gl && cj < g.dims[1] - g.gl && ck >= g.gl && ck < g.dims[2] - g.gl) cnt = 0;
+      }
     }
     uint32_t x = cnt;
 #pragma unroll
@@ -329,11 +336,7 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
     if (MODE == 1 && active) { m = mass[type[i]]; if (dth != 0.0) { ux = vx[i]; uy = vy[i]; uz = vz[i]; } }
     acc.ax = acc.ay = acc.az = 0.;
     const uint2 ge = gt[t >> 5];
-#if XNB_CL_ABL == 14      // EXPERIMENT (wrong forces): no pair loop at all -- prologue and epilogue only
-    const uint32_t trips = ge.y >> 10;
-#else
     const uint32_t trips = ge.y;
-#endif
     const uint2* R = rows + ((size_t)ge.x * 32u + (uint32_t)lane);
     // register prefetch ONE row ahead, issued at the very top of a trip and pinned there by a warp barrier.  (Written as a
     // two-rows-ahead rotation, ptxas sank the load to the bottom of the loop body; the six scoreboards of a warp are all needed by
@@ -348,17 +351,8 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
       if (k + CL_PREFETCH_ROWS < trips) asm volatile("prefetch.global.L2 [%0];" :: "l"(R + (size_t)(k + CL_PREFETCH_ROWS) * 32u));
       __syncwarp();
       // a list word is 8 x the staged index of the candidate: byte offset of its z, half the byte offset of its {x,y}
-#if XNB_CL_ABL == 11 || XNB_CL_ABL == 15      // EXPERIMENT (wrong forces): conflict-free gather addresses that do not depend on the list words
-      const uint32_t kk = 4u * k;
-      const uint32_t j[4] = {8u * (lane + 32u * (kk & 63u)), 8u * (lane + 32u * ((kk + 1u) & 63u)), 8u * (lane + 32u * ((kk + 2u) & 63u)), 8u * (lane + 32u * ((kk + 3u) & 63u))};
-#elif XNB_CL_ABL == 12    // EXPERIMENT (wrong forces): conflict-free gather addresses that depend on the list words
-      const uint32_t kk = 4u * k;
-      const uint32_t j[4] = {8u * (((w0.x >> 15) & 1u) + lane + 32u * (kk & 63u)), 8u * ((w0.x >> 31) + lane + 32u * ((kk + 1u) & 63u)),
-                             8u * (((w0.y >> 15) & 1u) + lane + 32u * ((kk + 2u) & 63u)), 8u * ((w0.y >> 31) + lane + 32u * ((kk + 3u) & 63u))};
-#else
       // (PRMT for the low halves: written as `& 0xffff` the compiler folds the mask into the scaled address and needs two more instructions)
       const uint32_t j[4] = {__byte_perm(w0.x, 0u, 0x4410), w0.x >> 16, __byte_perm(w0.y, 0u, 0x4410), w0.y >> 16};
-#endif
       double dx[4], dy[4], dz[4], d2[4]; bool ok[4];
 #pragma unroll
       for (int u = 0; u < 4; u++)
@@ -373,19 +367,10 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
       // -0; below 2^-1022 it counts as zero: DESIGN.md 4), so the test costs one integer and one FP64 compare
 #pragma unroll
       for (int u = 0; u < 4; u++) ok[u] = in_cut(d2[u], rc2);
-#if XNB_CL_ABL == 13 || XNB_CL_ABL == 15      // EXPERIMENT (wrong forces): real gathers, functor skipped
-#pragma unroll
-      for (int u = 0; u < 4; u++) if (ok[u]) { acc.ax += d2[u]; acc.ay += dx[u]; acc.az += dz[u] + dy[u]; }
-#else
       pair_apply4<EV>(lj, dx, dy, dz, d2, ok, j, acc);
-#endif
       w0 = w1;
     }
-#if XNB_CL_ABL >= 10     // EXPERIMENTS: results are never stored (all variants then see the same -- force-free -- dynamics)
-    if (active && acc.ax == 1234.56789)
-#else
     if (active)
-#endif
     {
       double ax = acc.ax, ay = acc.ay, az = acc.az;
       if (MODE == 0)
@@ -417,309 +402,6 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
   {
     __shared__ double red[7][32];
     double vals[7] = {acc.e, acc.wxx, acc.wyy, acc.wzz, acc.wxy, acc.wxz, acc.wyz};
-#pragma unroll
-    for (int q = 0; q < 7; q++)
-    {
-      double v = vals[q];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) red[q][warp] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 7)
-    {
-      double v = 0.;
-      for (int wq = 0; wq < nwarp; wq++) v += red[threadIdx.x][wq];
-      ev_partials[(size_t)blockIdx.x * 7 + threadIdx.x] = v;
-    }
-  }
-}
-
-// ==================================================================================================================
-// Pair-merged compiled lists (XNB_CL_PAIRED): one sweep thread owns TWO tile particles that lie close together and walks
-// the sorted UNION of their two lists.  A union entry is gathered from shared memory once and evaluated against both
-// particles; an entry that belongs to the other particle's list only lies beyond the list radius of this one, so this one's
-// cut test rejects it (contribution exactly zero) -- no masks.  Each particle still meets its own candidates in stream order
-// (both lists ascend in staged index, so does their merge): forces stay bit-identical to the stream sweep.  For two particles
-// 0.9 sigma apart the union is ~1.25 lists: 0.62 gathers per (particle, list entry) instead of 1.
-//   * slots: the particles of a tile cell are ordered by the Morton code of their position inside the cell (4x4x4 bins);
-//     slot s of the tile = (cell, rank in that order); lane l of group G owns slots 64G + 2l and 64G + 2l + 1;
-//     perm[tile][slot] = tile particle (numbered cell after cell in storage order, as in the unpaired layout)
-//   * pads / missing partners: the SENTINEL, staged index n_halo, a position 1e30 away from everything
-// ==================================================================================================================
-XNB_DEVINL uint32_t cl_morton6(uint32_t x, uint32_t y, uint32_t z)      // 2 bits per axis
-{
-  return (x & 1u) | ((y & 1u) << 1) | ((z & 1u) << 2) | ((x & 2u) << 2) | ((y & 2u) << 3) | ((z & 2u) << 4);
-}
-
-// iterator over the staged indices of one particle's list (reference-format stream: group = cell code, count, count x p_b)
-struct ClListIt
-{
-  const uint16_t* p; uint32_t groups, n, base;
-  XNB_DEVINL void open(const uint16_t* lst, uint32_t ngrp) { p = lst; groups = ngrp; n = 0u; base = 0u; }
-  XNB_DEVINL uint32_t next(const uint32_t* hstart, int hb2, int HXY, int HX)
-  {
-    if (n == 0u)
-    {
-      if (groups == 0u) return 0xFFFFFFFFu;
-      const uint32_t w = p[0]; n = p[1]; p += 2; groups--;
-      base = hstart[hb2 + (int)(w >> 10) * HXY + (int)((w >> 5) & 31u) * HX + (int)(w & 31u)];
-    }
-    n--;
-    return base + (uint32_t)(*p++);
-  }
-};
-
-// counters: [0] rows used (bump allocator) [1] max groups of a tile [2] max staged particles of a tile + 1 (sentinel) [3] unused;
-// *n_candidates += list entries (of the original lists); n_candidates[1] += union entries
-__global__ void __launch_bounds__(1024)
-k_cl_compile_paired(GridP g, ClTileP tp, const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
-                    const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
-                    const uint16_t* const* __restrict__ cell_stream, uint2* __restrict__ groups, uint2* __restrict__ rows, uint16_t* __restrict__ perm,
-                    uint32_t cap_rows, uint32_t* __restrict__ counters, unsigned long long* __restrict__ n_candidates)
-{
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t s_scan[32];
-  const ClTile T = cl_tile(g, tp, (int)blockIdx.x);
-  const ClTables tb = cl_tables(smem_raw, tp);
-  const int pmax = tp.gmax * 64;                                   // slots per tile
-  uint16_t* s_perm = reinterpret_cast<uint16_t*>(smem_raw + cl_tables_bytes(tp.nh_max, tp.tc_max));   // [pmax]
-  uint8_t* s_key = reinterpret_cast<uint8_t*>(s_perm + pmax);                                           // [pmax]
-  cl_setup(g, T, tb, cell_start, cell_count, s_scan);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const uint32_t n_tile = tb.tstart[T.tcells], n_halo = tb.hstart[T.NH];
-  const uint32_t ngroups = (n_tile + 63u) >> 6;
-  uint2* const gt = groups + (size_t)blockIdx.x * (size_t)tp.gmax;
-  if (threadIdx.x == 0) { atomicMax(&counters[1], ngroups); atomicMax(&counters[2], n_halo + 1u); }
-  for (uint32_t q = min(ngroups, (uint32_t)tp.gmax) + threadIdx.x; q < (uint32_t)tp.gmax; q += blockDim.x) gt[q] = make_uint2(0u, 0u);
-  if (ngroups > (uint32_t)tp.gmax || n_halo + 1u > (uint32_t)tp.cap) return;      // the host reads the counters and re-runs with more room
-  const int HXY = T.HX * T.HY;
-  const double inv_cs = 4.0 / g.cs;
-
-  // ---- Morton key of every tile particle, then its rank among the particles of its cell = its slot
-  for (uint32_t t = threadIdx.x; t < n_tile; t += blockDim.x)
-  {
-    const int q = cl_find_cell(tb.tstart, T.tcells, t);
-    const uint32_t i = tb.hfirst[tb.thalo[q]] + (t - tb.tstart[q]);
-    const int ii = q % T.tci, jj = (q / T.tci) % T.tcj, kk = q / (T.tci * T.tcj);
-    double ox, oy, oz;
-    cell_origin(g, (uint32_t)ijk_to_index(g.dims, T.ci0 + ii, T.cj0 + jj, T.ck0 + kk), ox, oy, oz);
-    const int bx = min(max((int)((rx[i] - ox) * inv_cs), 0), 3), by = min(max((int)((ry[i] - oy) * inv_cs), 0), 3), bz = min(max((int)((rz[i] - oz) * inv_cs), 0), 3);
-    s_key[t] = (uint8_t)cl_morton6((uint32_t)bx, (uint32_t)by, (uint32_t)bz);
-  }
-  __syncthreads();
-  for (uint32_t t = threadIdx.x; t < n_tile; t += blockDim.x)
-  {
-    const int q = cl_find_cell(tb.tstart, T.tcells, t);
-    const uint32_t t0 = tb.tstart[q], t1 = tb.tstart[q + 1], key = s_key[t];
-    uint32_t rank = 0;
-    for (uint32_t u = t0; u < t1; u++) { const uint32_t ku = s_key[u]; rank += (ku < key || (ku == key && u < t)) ? 1u : 0u; }
-    s_perm[t0 + rank] = (uint16_t)t;
-  }
-  __syncthreads();
-  for (uint32_t sl = threadIdx.x; sl < (uint32_t)pmax; sl += blockDim.x) perm[(size_t)blockIdx.x * (size_t)pmax + sl] = sl < n_tile ? s_perm[sl] : (uint16_t)0xFFFFu;
-
-  const uint32_t sentinel = n_halo << 3;
-  for (uint32_t grp = warp; grp < ngroups; grp += nwarp)
-  {
-    ClListIt it[2]; uint32_t ub = 0; int hb2[2] = {0, 0};
-#pragma unroll
-    for (int w = 0; w < 2; w++)
-    {
-      const uint32_t sl = grp * 64u + 2u * (uint32_t)lane + (uint32_t)w;
-      it[w].open(nullptr, 0u);
-      if (sl < n_tile)
-      {
-        const uint32_t t = s_perm[sl];
-        const int q = cl_find_cell(tb.tstart, T.tcells, t);
-        const uint32_t pa = t - tb.tstart[q], na = tb.tstart[q + 1] - tb.tstart[q];
-        const int hA = (int)tb.thalo[q];
-        const int ii = q % T.tci, jj = (q / T.tci) % T.tcj, kk = q / (T.tci * T.tcj);
-        const uint16_t* cs = cell_stream[ijk_to_index(g.dims, T.ci0 + ii, T.cj0 + jj, T.ck0 + kk)];
-        const uint32_t off0 = reinterpret_cast<const uint32_t*>(cs)[pa], off1 = reinterpret_cast<const uint32_t*>(cs)[pa + 1];
-        const uint16_t* lst = cs + 2u * (na + 1u) + off0;
-        const uint32_t ngrp = (uint32_t)lst[-1];
-        ub += (off1 - off0 - 1u) - 2u * ngrp;
-        it[w].open(lst, ngrp);
-        hb2[w] = hA - 16 * (HXY + T.HX + 1);
-      }
-    }
-    uint32_t trips_ub = (ub + 3u) >> 2, csum = ub;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { trips_ub = max(trips_ub, __shfl_xor_sync(0xffffffffu, trips_ub, o)); csum += __shfl_xor_sync(0xffffffffu, csum, o); }
-    uint32_t row0 = 0;
-    if (lane == 0) { row0 = atomicAdd(&counters[0], trips_ub); atomicAdd(n_candidates, (unsigned long long)csum); }
-    row0 = __shfl_sync(0xffffffffu, row0, 0);
-    const bool fits = row0 + trips_ub <= cap_rows;       // else: keep counting, write nothing
-    uint2* col = rows + ((size_t)row0 * 32u + (uint32_t)lane);
-    unsigned long long buf = 0ull;
-    uint32_t r = 0;
-    uint32_t a = it[0].next(tb.hstart, hb2[0], HXY, T.HX), b = it[1].next(tb.hstart, hb2[1], HXY, T.HX);
-    while ((a & b) != 0xFFFFFFFFu)
-    {
-      const uint32_t m = min(a, b);
-      buf = (buf >> 16) | ((unsigned long long)(m << 3) << 48);
-      r++;
-      if (fits && (r & 3u) == 0u) col[(size_t)((r >> 2) - 1u) * 32u] = make_uint2((uint32_t)buf, (uint32_t)(buf >> 32));
-      if (a == m) a = it[0].next(tb.hstart, hb2[0], HXY, T.HX);
-      if (b == m) b = it[1].next(tb.hstart, hb2[1], HXY, T.HX);
-    }
-    uint32_t trips = (r + 3u) >> 2, usum = r;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, o)); usum += __shfl_xor_sync(0xffffffffu, usum, o); }
-    if (lane == 0) { gt[grp] = make_uint2(row0, fits ? trips : 0u); atomicAdd(n_candidates + 1, (unsigned long long)usum); }
-    if (!fits) continue;
-    while (r < 4u * trips)
-    {
-      buf = (buf >> 16) | ((unsigned long long)sentinel << 48);
-      r++;
-      if ((r & 3u) == 0u) col[(size_t)((r >> 2) - 1u) * 32u] = make_uint2((uint32_t)buf, (uint32_t)(buf >> 32));
-    }
-  }
-}
-
-// the sweep over pair-merged lists: as k_lj_sweep_cl, two particles per thread
-// VAR 0: <= 288 threads (576 particles), two blocks per SM; VAR 1: <= 576 threads, one block per SM
-template <class F, int MODE, bool EV, int VAR>
-__global__ void __launch_bounds__(VAR == 0 ? 288 : 576, VAR == 0 ? 2 : 1)
-k_lj_sweep_cl2(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
-               const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
-               double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
-               double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
-               const uint8_t* __restrict__ type, const double* __restrict__ mass,
-               const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
-               const uint2* __restrict__ groups, const uint2* __restrict__ rows, const uint16_t* __restrict__ perm,
-               double* __restrict__ ev_partials /* [gridDim.x][7] */, uint32_t* __restrict__ err,
-               const unsigned long long* __restrict__ skip_if_nonzero, const uint32_t* __restrict__ tile_list)
-{
-  if (skip_if_nonzero && *skip_if_nonzero) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t s_scan[32];
-  const uint32_t tile = tile_list ? tile_list[blockIdx.x] : blockIdx.x;
-  const ClTile T = cl_tile(g, tp, (int)tile);
-  const ClTables tb = cl_tables(smem_raw, tp);
-  double2* XY = reinterpret_cast<double2*>(smem_raw + cl_tables_bytes(tp.nh_max, tp.tc_max));   // [cap]
-  double* Z = reinterpret_cast<double*>(XY + tp.cap);                                             // [cap]
-  cl_setup(g, T, tb, cell_start, cell_count, s_scan);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const uint32_t n_tile = tb.tstart[T.tcells], n_halo = tb.hstart[T.NH];
-  const uint32_t ngroups = (n_tile + 63u) >> 6;
-  const bool bad = ngroups > (uint32_t)tp.gmax || n_halo + 1u > (uint32_t)tp.cap;   // cannot happen after a successful compile
-  if (bad && threadIdx.x == 0) atomicOr(err, DERR_TILE_CAPACITY);
-  const uint2* const gt = groups + (size_t)tile * (size_t)tp.gmax;
-  const uint16_t* const pt = perm + (size_t)tile * (size_t)tp.gmax * 64u;
-  if (!bad && threadIdx.x < ngroups * 32u)
-  {
-    const uint2 ge = gt[threadIdx.x >> 5];
-    const uint2* R = rows + ((size_t)ge.x * 32u + (uint32_t)lane);
-    for (uint32_t k = 0; k < min(ge.y, CL_PREFETCH_ROWS); k++) asm volatile("prefetch.global.L2 [%0];" :: "l"(R + (size_t)k * 32u));
-  }
-  if (!bad && n_tile > 0)
-  {
-    for (int h = warp; h < T.NH; h += nwarp)
-    {
-      const uint32_t d0 = tb.hstart[h], cnt = tb.hstart[h + 1] - d0, s0 = tb.hfirst[h];
-      for (uint32_t p = lane; p < cnt; p += 32)
-      {
-        cp_async8(&XY[d0 + p].x, rx + s0 + p); cp_async8(&XY[d0 + p].y, ry + s0 + p); cp_async8(Z + d0 + p, rz + s0 + p);
-      }
-    }
-    if (threadIdx.x == 0) { XY[n_halo] = make_double2(1.0e30, 1.0e30); Z[n_halo] = 1.0e30; }      // the sentinel
-    cp_async_wait_all();
-  }
-  __syncthreads();
-
-  PairAcc acc[2];
-#pragma unroll
-  for (int w = 0; w < 2; w++) acc[w].e = acc[w].wxx = acc[w].wyy = acc[w].wzz = acc[w].wxy = acc[w].wxz = acc[w].wyz = 0.;
-  const double rc2 = lj.rcut2();
-  const uint32_t xyb = (uint32_t)__cvta_generic_to_shared(XY), zb = (uint32_t)__cvta_generic_to_shared(Z);
-
-  if (!bad)
-  for (uint32_t t = threadIdx.x; t < ngroups * 32u; t += blockDim.x)
-  {
-    // this thread's two particles (a missing partner stands on the sentinel: nothing is within its cut)
-    bool active[2]; uint32_t gi[2]; double xa[2], ya[2], za[2], m[2], ux[2], uy[2], uz[2];
-#pragma unroll
-    for (int w = 0; w < 2; w++)
-    {
-      const uint32_t sl = (t >> 5) * 64u + 2u * (uint32_t)lane + (uint32_t)w;
-      active[w] = sl < n_tile;
-      uint32_t self = n_halo; gi[w] = 0u;
-      if (active[w])
-      {
-        const uint32_t tp_ = pt[sl];
-        const int q = cl_find_cell(tb.tstart, T.tcells, tp_);
-        const uint32_t pa = tp_ - tb.tstart[q];
-        self = tb.hstart[tb.thalo[q]] + pa; gi[w] = tb.hfirst[tb.thalo[q]] + pa;
-      }
-      const double2 ra = XY[self];
-      xa[w] = ra.x; ya[w] = ra.y; za[w] = Z[self];
-      m[w] = 1.0; ux[w] = uy[w] = uz[w] = 0.;
-      if (MODE == 1 && active[w]) { m[w] = mass[type[gi[w]]]; if (dth != 0.0) { ux[w] = vx[gi[w]]; uy[w] = vy[gi[w]]; uz[w] = vz[gi[w]]; } }
-      acc[w].ax = acc[w].ay = acc[w].az = 0.;
-    }
-    const uint2 ge = gt[t >> 5];
-    const uint32_t trips = ge.y;
-    const uint2* R = rows + ((size_t)ge.x * 32u + (uint32_t)lane);
-    const uint32_t sw = (n_halo << 3) | (n_halo << 19);
-    uint2 w0 = make_uint2(sw, sw), w1 = w0;
-    if (trips > 0u) w0 = ld_stream8(R);
-    for (uint32_t k = 0; k < trips; k++)
-    {
-      if (k + 1u < trips) w1 = ld_stream8(R + (size_t)(k + 1u) * 32u);
-      if (k + CL_PREFETCH_ROWS < trips) asm volatile("prefetch.global.L2 [%0];" :: "l"(R + (size_t)(k + CL_PREFETCH_ROWS) * 32u));
-      __syncwarp();
-      const uint32_t j[4] = {__byte_perm(w0.x, 0u, 0x4410), w0.x >> 16, __byte_perm(w0.y, 0u, 0x4410), w0.y >> 16};
-      double px[4], py[4], pz[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) { lds_f64x2(xyb + j[u] + j[u], px[u], py[u]); lds_f64(zb + j[u], pz[u]); }
-#pragma unroll
-      for (int w = 0; w < 2; w++)
-      {
-        double dx[4], dy[4], dz[4], d2[4]; bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) { dx[u] = __dadd_rn(px[u], -xa[w]); dy[u] = __dadd_rn(py[u], -ya[w]); dz[u] = __dadd_rn(pz[u], -za[w]); }
-#pragma unroll
-        for (int u = 0; u < 4; u++) d2[u] = norm2_exact(dx[u], dy[u], dz[u]);
-#pragma unroll
-        for (int u = 0; u < 4; u++) ok[u] = in_cut(d2[u], rc2);
-        pair_apply4<EV>(lj, dx, dy, dz, d2, ok, j, acc[w]);
-      }
-      w0 = w1;
-    }
-#pragma unroll
-    for (int w = 0; w < 2; w++)
-      if (active[w])
-      {
-        const uint32_t i = gi[w];
-        double ax = acc[w].ax, ay = acc[w].ay, az = acc[w].az;
-        if (MODE == 0) { fx[i] += ax; fy[i] += ay; fz[i] += az; }
-        else
-        {
-          ax = __ddiv_rn(ax, m[w]); ay = __ddiv_rn(ay, m[w]); az = __ddiv_rn(az, m[w]);
-          fx[i] = ax; fy[i] = ay; fz[i] = az;
-          if (dth != 0.0)
-          {
-            vx[i] = __dadd_rn(ux[w], __dmul_rn(ax, dth));
-            vy[i] = __dadd_rn(uy[w], __dmul_rn(ay, dth));
-            vz[i] = __dadd_rn(uz[w], __dmul_rn(az, dth));
-          }
-        }
-      }
-  }
-  if (MODE == 1)
-  {
-    const int ng = n_total - n_inner;
-    const int per = (ng + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int g0 = n_inner + (int)blockIdx.x * per, g1 = min(g0 + per, n_total);
-    for (int i = g0 + (int)threadIdx.x; i < g1; i += blockDim.x) { fx[i] = 0.; fy[i] = 0.; fz[i] = 0.; }
-  }
-  if (EV)
-  {
-    __shared__ double red[7][32];
-    double vals[7] = {acc[0].e + acc[1].e, acc[0].wxx + acc[1].wxx, acc[0].wyy + acc[1].wyy, acc[0].wzz + acc[1].wzz,
-                      acc[0].wxy + acc[1].wxy, acc[0].wxz + acc[1].wxz, acc[0].wyz + acc[1].wyz};
 #pragma unroll
     for (int q = 0; q < 7; q++)
     {

@@ -93,7 +93,7 @@ int xnb_get_grid_info(const xnb_ctx*, xnb_grid_info* out);
    fits shared memory and the sweep reads the streams.                                                             */
 typedef struct xnb_sweep_info
 {
-  int32_t compiled;       /* 1 if the sweep runs over compiled lists, 2: pair-merged lists (XNB_CL_PAIRED) */
+  int32_t compiled;       /* 1 if the sweep runs over compiled lists                                      */
   int32_t ghost;          /* lists compiled for ghost cells too (lennard_jones_force ghost=true)       */
   int64_t tile[3];        /* cells per tile (= per thread block)                                       */
   int64_t threads;        /* threads per block                                                         */
@@ -107,6 +107,23 @@ typedef struct xnb_sweep_info
 int xnb_get_sweep_info(const xnb_ctx*, xnb_sweep_info* out);
 /* per-cell particle count and start index into the flat arrays (the per-cell SoA views of CellParticles)        */
 int xnb_get_cells(xnb_ctx*, uint32_t* cell_start /* n_cells */, uint32_t* cell_count /* n_cells */);
+/* DEVICE view of the grid: what the reference hands its operators as cells[c][field] (src/core/include/exanb/core/grid.h:70-71,
+   678: per-cell SoA pointers).  Field f of particle p of cell c is f[cell_start[c] + p], p < cell_count[c]; inner particles
+   are [0, n_inner) sorted by cell, ghosts follow.  All pointers are device pointers owned by the ctx; they stay valid until
+   the next xnb_move_particles / xnb_rebuild_amr / xnb_ghost_comm_scheme (binning gathers into the other buffer, ghost creation
+   may grow the arrays): take the view again after those.  Does not synchronise: work enqueued on the caller's stream is
+   ordered with the kernels that produce these arrays.                                                                */
+typedef struct xnb_particle_view
+{
+  int64_t n_inner, n_total, n_cells;
+  double *rx, *ry, *rz, *vx, *vy, *vz, *fx, *fy, *fz;
+  uint64_t* id;
+  uint8_t* type;
+  const uint32_t* cell_start;      /* n_cells */
+  const uint32_t* cell_count;      /* n_cells */
+  const uint32_t* particle_cell;   /* n_total: local cell index of every particle */
+} xnb_particle_view;
+int xnb_view_particles(xnb_ctx*, xnb_particle_view* out);
 
 /* ---- operators of the hot path (asynchronous on `stream`) --------------------------------------------------- */
 /* op `move_particles` : src/grid_cell_particles/include/exanb/grid_cell_particles/move_particles_across_cells.h:78-235
@@ -209,6 +226,7 @@ int xnb_get_backup(xnb_ctx*, uint32_t* out /* 3*n_inner */);
 /* counters */
 int64_t xnb_rebuild_count(const xnb_ctx*);
 int64_t xnb_kernel_launches(const xnb_ctx*);    /* number of kernels this ctx has launched so far                */
+int64_t xnb_device_allocations(void);           /* cudaMalloc calls of the library so far (process-wide): constant over steady-state steps */
 /* device time per kernel group since the last reset: CUDA event pairs recorded on the launching stream around each
    group, never synchronising inside the timed region; xnb_timing_read waits for the recorded events and sums them. */
 #define XNB_T_FORCE 0        /* pair sweep (K3)                                  */

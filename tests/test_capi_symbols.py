@@ -35,13 +35,15 @@ def test_header_is_plain_c_and_structs_match_the_ctypes_mirror(tmp_path):
     import subprocess
     src = tmp_path / "probe.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "xnb_hotpath.h"\n'
-                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(xnb_grid_info), sizeof(xnb_sweep_info), sizeof(xnb_lattice_cfg),'
-                   ' offsetof(xnb_sweep_info, tile), offsetof(xnb_sweep_info, candidates), offsetof(xnb_grid_info, block_end)); return 0; }\n')
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(xnb_grid_info), sizeof(xnb_sweep_info), sizeof(xnb_lattice_cfg),'
+                   ' offsetof(xnb_sweep_info, tile), offsetof(xnb_sweep_info, candidates), offsetof(xnb_grid_info, block_end),'
+                   ' sizeof(xnb_particle_view), offsetof(xnb_particle_view, particle_cell)); return 0; }\n')
     exe = tmp_path / "probe"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
     got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     want = [ctypes.sizeof(capi.XnbGridInfo), ctypes.sizeof(capi.XnbSweepInfo), ctypes.sizeof(capi.XnbLatticeCfg),
-            capi.XnbSweepInfo.tile.offset, capi.XnbSweepInfo.candidates.offset, capi.XnbGridInfo.block_end.offset]
+            capi.XnbSweepInfo.tile.offset, capi.XnbSweepInfo.candidates.offset, capi.XnbGridInfo.block_end.offset,
+            ctypes.sizeof(capi.XnbParticleView), capi.XnbParticleView.particle_cell.offset]
     assert got == want, (got, want)
 
 

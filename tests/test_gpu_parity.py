@@ -43,8 +43,8 @@ def setup_pair(kw):
 @pytest.mark.parametrize("nbh_kernels", ["tiled", "untiled"])
 @pytest.mark.parametrize("case", list(CASES))
 def test_rebuild_pipeline_bit_exact(case, nbh_kernels, monkeypatch):
-    # "tiled": k_nbh_masks (fp32 classification + exact fp64 decision inside the band) + k_nbh_emit;
-    # "untiled": the per-particle all-fp64 kernels kept as the fallback for tiles that do not fit shared memory
+    # "tiled": k_nbh_bits (fp32 classification into accept bits + exact fp64 decision inside the band; streams of the ghost cells
+    # built on demand); "untiled": the per-particle all-fp64 kernels kept as the fallback for tiles that do not fit shared memory
     if nbh_kernels == "untiled":
         monkeypatch.setenv("XNB_NBH_UNTILED", "1")
     else:
@@ -217,29 +217,6 @@ def test_compiled_lists_sweep_equals_stream_sweep(case, tile, monkeypatch):
         assert np.array_equal(pga[k], pgb[k]), k
     # energy / virial: per-tile partial sums, so only the summation order differs
     assert abs(eva[0] - evb[0]) <= 1e-12 * abs(eva[0]) and np.abs(eva[1] - evb[1]).max() <= 1e-12 * np.abs(eva[1]).max()
-
-
-@pytest.mark.parametrize("case", ["ni16k", "lj2k", "lj_voids"])
-def test_pair_merged_lists_sweep_equals_stream_sweep(case, monkeypatch):
-    """XNB_CL_PAIRED=1 (experiment): two nearby particles per sweep thread walking the sorted union of their lists.
-    A candidate of the partner's list lies outside this particle's cut and contributes exactly zero, and every particle still meets
-    its own candidates in stream order: forces are bit-identical to the stream sweep"""
-    kw = CASES[case]
-    eps, sig, rc = kw["epsilon"], kw["sigma"], kw["rcut"]
-    out = {}
-    for mode in ("paired", "streams"):
-        monkeypatch.delenv("XNB_CL_PAIRED", raising=False); monkeypatch.delenv("XNB_SWEEP_STREAMS", raising=False)
-        monkeypatch.setenv("XNB_CL_PAIRED" if mode == "paired" else "XNB_SWEEP_STREAMS", "1")
-        _, ctx = setup_pair(kw)
-        ctx.first_iteration(eps, sig, rc)
-        si = ctx.sweep_info()
-        assert si["paired"] == (mode == "paired") and si["compiled"] == (mode == "paired")
-        ctx.run_steps(12, kw["dt"], eps, sig, rc)
-        out[mode] = (ctx.get_particles(0, ctx.n_inner), ctx.energy_virial(eps, sig, rc))
-    (pa, ea), (pb, eb) = out["paired"], out["streams"]
-    for k in ("id", "rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
-        assert np.array_equal(pa[k], pb[k]), k
-    assert abs(ea[0] - eb[0]) <= 1e-12 * abs(eb[0])
 
 
 @pytest.mark.parametrize("case", ["ni16k", "lj2k", "lj_gap2", "lj_voids"])
