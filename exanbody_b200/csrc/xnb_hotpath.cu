@@ -144,8 +144,8 @@ struct xnb_ctx
   ClCfg cl;
   DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0; DBuf<uint32_t> cl_tile_list;
   // ---- k_nbh_bits (xnb_nbh_bits.cuh): masks parked between its two phases, capacities that worked last time, lazily built ghost-cell lists
-  DBuf<uint32_t> nb_gmasks; int nb_cap_slots = 0; bool ghost_lists = false;       // ghost_lists: the streams of the ghost cells are current
-  struct NbGhostCfg { ClTileP tp{}; int cap_slots = 0; bool have = false; } nb_ghost;
+  int nb_cap_l = 0, nb_cap_trips = 0; bool ghost_lists = false;       // ghost_lists: the streams of the ghost cells are current
+  struct NbGhostCfg { ClTileP tp{}; int cap_l = 0; bool have = false; } nb_ghost;
   cudaStream_t st_comm = nullptr; cudaEvent_t ev_pos = nullptr, ev_ghost = nullptr;      // halo exchange overlapped with the interior tiles
   int64_t n_nonempty_inner = 0;
   int64_t pool_used = 0; uint32_t max_neighbors = 0, max_cell_count = 0, max_stream = 0; double avg_stream = 0; bool have_nbh = false;
@@ -380,12 +380,6 @@ int read_back(xnb_ctx* c, const T* d, size_t n, T* out, cudaStream_t st)
   return 0;
 }
 
-int require_binned(xnb_ctx* c)
-{
-  int rc = ensure_grid(c);
-  if (rc) return rc;
-  return 0;
-}
 
 } // namespace
 
@@ -980,7 +974,6 @@ static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
   if (mode == 1 && g.gl == 0) { *done = true; return XNB_OK; }
   ParticlesP A = c->P(c->cur);
   const uint32_t mcc = std::max<uint32_t>(c->max_cell_count, 1);
-  const int nrows = (2 * gap + 1) * (2 * gap + 1);
   const int nwarp = NBH_BITS_THREADS / 32;
   // stream capacity per cell: first guess from the list radius (volume ratio of the sphere to the neighbourhood), grows on demand
   if (c->nbh_slot_words == 0)
@@ -990,54 +983,60 @@ static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
     c->nbh_slot_words = (uint32_t)((size_t)(2 * (mcc + 1) + (double)mcc * per + 64 + 7) & ~(size_t)7);
   }
   std::vector<ClCand> cands = cl_tile_candidates(c, lo, hi, gap);
+  const int n1 = 2 * gap + 1;
+  const bool u8 = mcc <= 255 && n1 * n1 * n1 <= 128 && !env_flag("XNB_NBH_U16");      // byte list areas
+  if (mcc + 3u > 32u * NBH_CELL_BLOCKS && !env_flag("XNB_NBH_FORCE_BITS")) return XNB_OK;   // a neighbour cell would need more accept masks than the kernel keeps in registers
   static bool attr_done_dev[XNB_MAX_DEVICES] = {};
   if (!attr_done_dev[c->device % XNB_MAX_DEVICES])
   {
-    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_nbh_bits));
-    CK(cudaFuncSetAttribute(k_nbh_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_nbh_bits<true>));
+    CK(cudaFuncSetAttribute(k_nbh_bits<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
+    CK(cudaFuncSetAttribute(k_nbh_bits<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
     attr_done_dev[c->device % XNB_MAX_DEVICES] = true;
   }
   uint32_t* counters = c->d_scalars32.p + 64;                  // NB_U32_COUNT u32
   unsigned long long* totals = c->d_scalars64.p + 4;           // 3 u64
+  // list capacity per particle: first guess from the list radius, then what the last build needed
+  const double frac = std::min(1.0, 4.19 * c->nbh_dist * c->nbh_dist * c->nbh_dist / std::pow((double)n1 * c->cs, 3.0));
+  int& cap_l_state = mode == 0 ? c->nb_cap_l : c->nb_ghost.cap_l;
+  if (cap_l_state == 0) cap_l_state = (int)(1.0 + 2.0 * std::min(27.0, (double)n1 * n1 * n1) + frac * (double)(n1 * n1 * n1) * (double)std::max(mcc, 8u) * 1.25 + 16.0);
   for (const ClCand& k : cands)
   {
     ClTileP tp{};
     cl_tile_grid(tp, k, lo, hi, gap);
-    // slots: per row of the neighbourhood ceil(row candidates / 32) + 1 blocks
-    int cap_slots = nrows * ((int)(((2 * gap + 1) * mcc + 31) / 32) + 1);
     const ClTileP& prev = mode == 0 ? c->cl.tp : c->nb_ghost.tp;
     const bool have_prev = mode == 0 ? (c->cl.valid && !c->cl.ghost) : c->nb_ghost.have;
     if (have_prev && prev.ti == tp.ti && prev.tj == tp.tj && prev.tk == tp.tk)
     {
       // same shape as last time: start from the capacities that worked
       tp.gmax = std::max(tp.gmax, prev.gmax); tp.cap = std::max(tp.cap, prev.cap);
-      const int ps = mode == 0 ? c->nb_cap_slots : c->nb_ghost.cap_slots;      // slots the last build used, + slack
-      if (ps > 0) cap_slots = std::min(cap_slots, ps);
     }
     const unsigned blocks = (unsigned)((int64_t)tp.tiles_i * tp.tiles_j * tp.tiles_k);
     bool ok = false, shape_fails = false;
     for (int attempt = 0; attempt < 6; attempt++)
     {
       if (tp.cap > 8191 || tp.gmax > 32) { shape_fails = true; break; }
-      const size_t smem = nb_smem_bytes(tp.nh_max, tp.tc_max, tp.gmax, tp.cap, cap_slots, nwarp);
+      const int cap_l = ((cap_l_state + 7) & ~7) + 4;                  // cap_l / 4 odd: the 32 list areas of a warp start in 32 different banks
+      const size_t smem = nb_smem_bytes(tp.nh_max, tp.tc_max, tp.gmax, tp.cap, cap_l, u8 ? 1 : 2, nwarp);
       if (smem + 2048 > XNB_SM_BYTES) { shape_fails = true; break; }
       if ((size_t)g.n_cells * c->nbh_slot_words > ((size_t)24 << 30)) return XNB_OK;      // streams would not fit: two-pass build with a compact pool
       CK(c->pool.ensure((size_t)g.n_cells * c->nbh_slot_words + 64));
-      CK(c->nb_gmasks.ensure((size_t)blocks * tp.gmax * cap_slots * 32 + 64));
       if (mode == 0)
       {
-        if (c->cl_cap_rows == 0) c->cl_cap_rows = (uint32_t)std::min<double>(4.0e9, (double)c->n_inner * 24.0 / 32.0 * 1.10 + 4096.0);
-        CK(c->cl_rows.ensure((size_t)c->cl_cap_rows * 128 + 64));
+        // a group owns a fixed block of cap_trips rows (4 list entries per lane and row)
+        if (c->nb_cap_trips == 0) c->nb_cap_trips = c->max_neighbors ? (int)(c->max_neighbors / 4 + 4) : (cap_l_state + 3) / 4;
+        CK(c->cl_rows.ensure((size_t)blocks * tp.gmax * c->nb_cap_trips * 128 + 64, 0, 1.05));
         CK(c->cl_groups.ensure((size_t)blocks * tp.gmax + 16));
       }
       CK(cudaMemsetAsync(counters, 0, NB_U32_COUNT * 4, st)); CK(cudaMemsetAsync(totals, 0, 3 * 8, st));
       NbhBitsP bp{};
-      bp.cap_slots = cap_slots; bp.emit_rows = mode == 0 ? 1 : 0; bp.sel_mode = mode; bp.slot_words = (int)c->nbh_slot_words; bp.cap_rows = c->cl_cap_rows;
-      bp.lane_min = env_int("XNB_NBH_LANE_MIN") > 0 ? env_int("XNB_NBH_LANE_MIN") : 16; bp.max_dist2 = c->nbh_dist * c->nbh_dist;
+      bp.cap_l = cap_l; bp.emit_rows = mode == 0 ? 1 : 0; bp.sel_mode = mode; bp.slot_words = (int)c->nbh_slot_words; bp.cap_trips = c->nb_cap_trips;
+      bp.lane_min = env_int("XNB_NBH_LANE_MIN") > 0 ? env_int("XNB_NBH_LANE_MIN") : 5; bp.max_dist2 = c->nbh_dist * c->nbh_dist;
       NbhBitsOut o{c->pool.p, c->cell_stream.p, c->stream_size.p, c->cell_stream_bytes.p, c->stream_off.p, c->cl_groups.p, reinterpret_cast<uint2*>(c->cl_rows.p),
-                   c->nb_gmasks.p, counters, totals};
-      if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh_bits mode %d tiles %dx%dx%d cap %d gmax %d slots %d slot_words %u smem %zu blocks %u (max cell %u)\n", mode, tp.ti, tp.tj, tp.tk, tp.cap, tp.gmax, cap_slots, c->nbh_slot_words, smem, blocks, mcc);
-      k_nbh_bits<<<blocks, NBH_BITS_THREADS, smem, st>>>(g, tp, bp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
+                   counters, totals};
+      if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh_bits mode %d tiles %dx%dx%d cap %d gmax %d cap_l %d u8 %d trips %d slot_words %u smem %zu blocks %u (max cell %u)\n", mode, tp.ti, tp.tj, tp.tk, tp.cap, tp.gmax, cap_l, (int)u8, c->nb_cap_trips, c->nbh_slot_words, smem, blocks, mcc);
+      if (u8) k_nbh_bits<true><<<blocks, NBH_BITS_THREADS, smem, st>>>(g, tp, bp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
+      else    k_nbh_bits<false><<<blocks, NBH_BITS_THREADS, smem, st>>>(g, tp, bp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
       c->launches++; CK(cudaGetLastError());
       uint32_t h[NB_U32_COUNT]; unsigned long long tot[3];
       {
@@ -1048,25 +1047,27 @@ static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
         CK(cudaStreamSynchronize(st));
         memcpy(h, hp, NB_U32_COUNT * 4); memcpy(tot, hp + 64, 24);
       }
+      if (h[NB_OVERFLOW] & 4u) return XNB_OK;                      // a row needs more masks than the kernel holds: two-pass build
       bool again = false;
       if ((int)h[NB_GMAX] > tp.gmax) { tp.gmax = (int)h[NB_GMAX]; again = true; }
       if ((int)h[NB_CAP] > tp.cap) { tp.cap = ((int)h[NB_CAP] + 1) & ~1; again = true; }
-      if ((int)h[NB_SLOTS] > cap_slots) { cap_slots = (int)h[NB_SLOTS] + 1; again = true; }
+      if ((int)h[NB_SLOTS] > cap_l) { cap_l_state = (int)(h[NB_SLOTS] * 1.1) + 8; again = true; }
       if (h[NB_SLOT_WORDS] > c->nbh_slot_words) { c->nbh_slot_words = (uint32_t)(((size_t)(h[NB_SLOT_WORDS] * 1.12) + 64 + 7) & ~(size_t)7); again = true; }
-      if (mode == 0 && h[NB_ROWS] > c->cl_cap_rows) { c->cl_cap_rows = (uint32_t)((double)h[NB_ROWS] * 1.05) + 1024u; again = true; }
+      if (mode == 0 && (int)h[NB_TRIPS] > c->nb_cap_trips) { c->nb_cap_trips = (int)h[NB_TRIPS] + 3; again = true; }
       if (again || h[NB_OVERFLOW]) { if (!again) return c->fail(XNB_ERR_CAPACITY, "chunk_neighbors: tiled build reported an overflow it cannot size"); continue; }
+      cap_l_state = std::max(cap_l_state, std::min(cap_l, (int)(h[NB_SLOTS] * 1.08) + 8));     // keep some room for the next rebuild, no more
+      if ((int)(h[NB_SLOTS] * 1.08) + 8 < cap_l_state) cap_l_state = (int)(h[NB_SLOTS] * 1.08) + 8;
       if (mode == 0)
       {
         c->pool_used = (int64_t)tot[1]; c->max_neighbors = h[NB_MAX_NBH]; c->n_nonempty_inner = h[NB_NONEMPTY]; c->max_stream = h[NB_MAX_STREAM];
         c->avg_stream = c->n_inner ? (double)tot[2] / (double)c->n_inner : 0.0;
-        c->nb_cap_slots = std::min(cap_slots, (int)h[NB_SLOTS] + 3);
         c->have_nbh = true; c->ghost_lists = g.gl == 0;
         int rc = cl_finish(c, tp, false, blocks, h[NB_ROWS], (int64_t)tot[0], h[NB_GMAX], st); if (rc) return rc;
       }
       else
       {
         c->pool_used += (int64_t)tot[1]; c->max_neighbors = std::max(c->max_neighbors, h[NB_MAX_NBH]); c->max_stream = std::max(c->max_stream, h[NB_MAX_STREAM]);
-        c->nb_ghost.tp = tp; c->nb_ghost.cap_slots = std::min(cap_slots, (int)h[NB_SLOTS] + 3); c->nb_ghost.have = true;
+        c->nb_ghost.tp = tp; c->nb_ghost.have = true;
         c->ghost_lists = true;
       }
       ok = true;
