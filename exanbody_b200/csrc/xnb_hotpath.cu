@@ -974,7 +974,6 @@ static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
   if (mode == 1 && g.gl == 0) { *done = true; return XNB_OK; }
   ParticlesP A = c->P(c->cur);
   const uint32_t mcc = std::max<uint32_t>(c->max_cell_count, 1);
-  const int nwarp = NBH_BITS_THREADS / 32;
   // stream capacity per cell: first guess from the list radius (volume ratio of the sphere to the neighbourhood), grows on demand
   if (c->nbh_slot_words == 0)
   {
@@ -1017,6 +1016,9 @@ static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
     {
       if (tp.cap > 8191 || tp.gmax > 32) { shape_fails = true; break; }
       const int cap_l = ((cap_l_state + 7) & ~7) + 4;                  // cap_l / 4 odd: the 32 list areas of a warp start in 32 different banks
+      // one warp per group of 32 tile particles, the groups of a tile in even rounds over the warps
+      const int rounds = (tp.gmax + NBH_BITS_MAX_THREADS / 32 - 1) / (NBH_BITS_MAX_THREADS / 32);
+      const int nwarp = std::max(env_int("XNB_NBH_WARPS") > 0 ? std::min(env_int("XNB_NBH_WARPS"), NBH_BITS_MAX_THREADS / 32) : (tp.gmax + rounds - 1) / rounds, 2);
       const size_t smem = nb_smem_bytes(tp.nh_max, tp.tc_max, tp.gmax, tp.cap, cap_l, u8 ? 1 : 2, nwarp);
       if (smem + 2048 > XNB_SM_BYTES) { shape_fails = true; break; }
       if ((size_t)g.n_cells * c->nbh_slot_words > ((size_t)24 << 30)) return XNB_OK;      // streams would not fit: two-pass build with a compact pool
@@ -1031,12 +1033,12 @@ static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
       CK(cudaMemsetAsync(counters, 0, NB_U32_COUNT * 4, st)); CK(cudaMemsetAsync(totals, 0, 3 * 8, st));
       NbhBitsP bp{};
       bp.cap_l = cap_l; bp.emit_rows = mode == 0 ? 1 : 0; bp.sel_mode = mode; bp.slot_words = (int)c->nbh_slot_words; bp.cap_trips = c->nb_cap_trips;
-      bp.lane_min = env_int("XNB_NBH_LANE_MIN") > 0 ? env_int("XNB_NBH_LANE_MIN") : 5; bp.max_dist2 = c->nbh_dist * c->nbh_dist;
+      bp.max_dist2 = c->nbh_dist * c->nbh_dist;
       NbhBitsOut o{c->pool.p, c->cell_stream.p, c->stream_size.p, c->cell_stream_bytes.p, c->stream_off.p, c->cl_groups.p, reinterpret_cast<uint2*>(c->cl_rows.p),
                    counters, totals};
-      if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh_bits mode %d tiles %dx%dx%d cap %d gmax %d cap_l %d u8 %d trips %d slot_words %u smem %zu blocks %u (max cell %u)\n", mode, tp.ti, tp.tj, tp.tk, tp.cap, tp.gmax, cap_l, (int)u8, c->nb_cap_trips, c->nbh_slot_words, smem, blocks, mcc);
-      if (u8) k_nbh_bits<true><<<blocks, NBH_BITS_THREADS, smem, st>>>(g, tp, bp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
-      else    k_nbh_bits<false><<<blocks, NBH_BITS_THREADS, smem, st>>>(g, tp, bp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
+      if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh_bits mode %d tiles %dx%dx%d cap %d gmax %d cap_l %d u8 %d warps %d trips %d slot_words %u smem %zu blocks %u (max cell %u)\n", mode, tp.ti, tp.tj, tp.tk, tp.cap, tp.gmax, cap_l, (int)u8, nwarp, c->nb_cap_trips, c->nbh_slot_words, smem, blocks, mcc);
+      if (u8) k_nbh_bits<true><<<blocks, 32 * nwarp, smem, st>>>(g, tp, bp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
+      else    k_nbh_bits<false><<<blocks, 32 * nwarp, smem, st>>>(g, tp, bp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
       c->launches++; CK(cudaGetLastError());
       uint32_t h[NB_U32_COUNT]; unsigned long long tot[3];
       {
@@ -1062,6 +1064,7 @@ static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
         c->pool_used = (int64_t)tot[1]; c->max_neighbors = h[NB_MAX_NBH]; c->n_nonempty_inner = h[NB_NONEMPTY]; c->max_stream = h[NB_MAX_STREAM];
         c->avg_stream = c->n_inner ? (double)tot[2] / (double)c->n_inner : 0.0;
         c->have_nbh = true; c->ghost_lists = g.gl == 0;
+        c->nb_cap_trips = std::min(c->nb_cap_trips, (int)h[NB_TRIPS] + 4);       // rows of a group closer together next time
         int rc = cl_finish(c, tp, false, blocks, h[NB_ROWS], (int64_t)tot[0], h[NB_GMAX], st); if (rc) return rc;
       }
       else

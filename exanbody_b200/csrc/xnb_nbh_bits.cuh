@@ -39,7 +39,6 @@ struct NbhBitsP
   int sel_mode;          // 0: every tile cell is built; 1: only cells outside the inner range (ghost-cell lists, built lazily)
   int slot_words;        // stream capacity per cell (u16 words, multiple of 8)
   int cap_trips;         // rows per group in the compiled-list buffer (a group owns a fixed block of rows: no allocator)
-  int lane_min;          // segments of a group with at least this many particles of one cell are built lane-per-particle
   double max_dist2;
 };
 
@@ -154,12 +153,12 @@ struct NbhBitsOut
   uint32_t* counters; unsigned long long* totals;
 };
 
-constexpr int NBH_BITS_THREADS = 256;
-constexpr int NBH_CELL_BLOCKS = 3;      // accept masks (32 candidates each, the first one aligned to 4 below the cell's first particle) per
-                                        // neighbour cell in the lane-per-particle form: cells of up to 3 x 32 - 3 = 93 particles
-// staged candidates: every halo cell padded to a multiple of four, + slack for the 32-wide candidate-per-lane reads
-__host__ __device__ inline uint32_t nb_cap_pairs(int cap, int nh_max) { return ((((uint32_t)cap + 3u * (uint32_t)nh_max + 31u) & ~31u) >> 1) + 18u; }
-// dynamic shared memory of k_nbh_bits: tables | ncand[gmax * 32] u16 | hpad[nh_max + 1] | staged pairs | per-warp list areas
+constexpr int NBH_BITS_MAX_THREADS = 288;   // nine warps: the 17-18 groups of a 4x2x2 tile of 32-particle cells in two even rounds
+constexpr int NBH_CELL_BLOCKS = 3;      // accept masks (32 candidates each) per neighbour cell: cells of up to 96 staged (padded) particles
+constexpr uint32_t NBH_SLACK_PAIRS = 32u * NBH_CELL_BLOCKS / 2u + 4u;     // a lane of a smaller cell reads on to the warp's longest cell
+// staged candidates: every halo cell padded to a multiple of four, + slack
+__host__ __device__ inline uint32_t nb_cap_pairs(int cap, int nh_max) { return ((((uint32_t)cap + 3u * (uint32_t)nh_max + 31u) & ~31u) >> 1) + NBH_SLACK_PAIRS; }
+// dynamic shared memory of k_nbh_bits: tables | plen[gmax * 32] u16 | hpad[nh_max + 1] | staged pairs | per-warp list areas
 __host__ __device__ inline size_t nb_list_area_bytes(int cap_l, int elem) { return (((size_t)32 * cap_l + 64) * (size_t)elem + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t nb_smem_bytes(int nh_max, int tc_max, int gmax, int cap, int cap_l, int elem, int nwarp)
 {
@@ -177,7 +176,7 @@ template <class LT> XNB_DEVINL void nb_sts(uint32_t a, uint32_t v)
 // p_b and counts fit a byte, a group header is (0x80 | neighbour slot, n); else u16).  A list is kept in the reference's layout:
 // [groups][(cell slot, n, p_b x n) x groups].
 template <bool U8>
-__global__ void __launch_bounds__(NBH_BITS_THREADS, 2)
+__global__ void __launch_bounds__(NBH_BITS_MAX_THREADS, 2)
 k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
            const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
            const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
@@ -185,6 +184,7 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
 {
   typedef typename std::conditional<U8, uint8_t, uint16_t>::type LT;
   constexpr uint32_t ES = (uint32_t)sizeof(LT);
+  constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_scan[32];
   __shared__ uint32_t s_next, s_ovf;
@@ -193,24 +193,26 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
   __shared__ unsigned long long s_tot[3];
   __shared__ uint16_t s_enc[128];        // neighbour slot -> encoded cell index (chunk_neighbors.h:137-150)
   __shared__ int16_t s_dh[128];          // neighbour slot -> halo index relative to the cell's own
+  __shared__ uint32_t s_flag[32];        // group g: list lengths published
   const ClTile T = cl_tile(g, tp, (int)blockIdx.x);
   const ClTables tb = cl_tables(smem_raw, tp);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int gap = tp.gap, n1 = 2 * gap + 1;
   const size_t tbytes = cl_tables_bytes(tp.nh_max, tp.tc_max);
-  uint16_t* const pcand = reinterpret_cast<uint16_t*>(smem_raw + tbytes);             // list entries of every tile particle
-  const size_t pcand_bytes = (((size_t)tp.gmax * 64) + 15) & ~(size_t)15;
+  uint16_t* const plen = reinterpret_cast<uint16_t*>(smem_raw + tbytes);              // list length (stream words) of every tile particle
+  const size_t plen_bytes = (((size_t)tp.gmax * 64) + 15) & ~(size_t)15;
   const uint32_t cap_pairs = nb_cap_pairs(tp.cap, tp.nh_max);
-  uint32_t* const hpad = reinterpret_cast<uint32_t*>(smem_raw + tbytes + pcand_bytes);   // staged (padded) index of every halo cell's first particle
+  uint32_t* const hpad = reinterpret_cast<uint32_t*>(smem_raw + tbytes + plen_bytes);   // staged (padded) index of every halo cell's first particle
   const size_t hpad_bytes = (((size_t)tp.nh_max + 1) * 4 + 15) & ~(size_t)15;
-  NbPair* const S = reinterpret_cast<NbPair*>(smem_raw + tbytes + pcand_bytes + hpad_bytes);
+  NbPair* const S = reinterpret_cast<NbPair*>(smem_raw + tbytes + plen_bytes + hpad_bytes);
   const uint32_t cap_l = (uint32_t)bp.cap_l;
-  LT* const Lw = reinterpret_cast<LT*>(smem_raw + tbytes + pcand_bytes + hpad_bytes + (size_t)cap_pairs * sizeof(NbPair) + (size_t)warp * nb_list_area_bytes(bp.cap_l, (int)ES));
+  LT* const Lw = reinterpret_cast<LT*>(smem_raw + tbytes + plen_bytes + hpad_bytes + (size_t)cap_pairs * sizeof(NbPair) + (size_t)warp * nb_list_area_bytes(bp.cap_l, (int)ES));
   LT* const L = Lw + (size_t)lane * cap_l;                                             // this lane's list
 
   cl_setup(g, T, tb, cell_start, cell_count, s_scan, bp.sel_mode);
   if (threadIdx.x == 0) { s_next = 0u; s_ovf = 0u; s_rmax = 0u; s_tot[0] = s_tot[1] = s_tot[2] = 0ull; }
   if (threadIdx.x < NB_U32_COUNT) s_stat[threadIdx.x] = 0u;
+  if (threadIdx.x < 32) s_flag[threadIdx.x] = 0u;
   if (U8)
     for (int sl = threadIdx.x; sl < n1 * n1 * n1; sl += blockDim.x)
     {
@@ -227,6 +229,20 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
   {
     if (threadIdx.x == 0) atomicOr(&out.counters[NB_OVERFLOW], 1u);
     return;                                                                      // the host reads the counters and re-runs with more room
+  }
+  // empty tile cells: no stream
+  if ((int)threadIdx.x < T.tcells)
+  {
+    const int q = (int)threadIdx.x;
+    const int ii = q % T.tci, jj = (q / T.tci) % T.tcj, kk = q / (T.tci * T.tcj);
+    const int ci = T.ci0 + ii, cj = T.cj0 + jj, ck = T.ck0 + kk;
+    const int hq = (int)tb.thalo[q];
+    if (tb.hstart[hq + 1] == tb.hstart[hq] && !(bp.sel_mode == 1 && cl_cell_is_inner(g, ci, cj, ck)))
+    {
+      const int ca = ijk_to_index(g.dims, ci, cj, ck);
+      out.cell_stream[ca] = nullptr; out.stream_size[ca] = 0u; out.cell_stream_bytes[ca] = 0u;
+      out.stream_off[ca] = (unsigned long long)ca * (unsigned long long)bp.slot_words;
+    }
   }
   __syncthreads();
 
@@ -276,7 +292,7 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
       e[0] = 0.f; e[2] = 0.f; e[4] = 0.f; e[6] = INFINITY;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(FULL, rmax, o));
     if (lane == 0) atomicMax(&s_rmax, __float_as_uint(rmax));
   }
   __syncthreads();
@@ -284,300 +300,219 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
   const double Rm = (double)__uint_as_float(s_rmax);
   const double band = 5.9604644775390625e-08 * (192.0 * Rm * Rm + 12.0 * bp.max_dist2);
   const float band2 = (float)(2.0 * band);                 // accepted and t > -2 band: ambiguous
-  const float zc = (float)(bp.max_dist2);                  // t + zc < 0  <=>  fp32 d2 < band: inside the zero band (own cell row)
+  const float zc = (float)(bp.max_dist2);                  // t + zc < 0  <=>  fp32 d2 < band: inside the zero band (own cell)
   const uint32_t Lsh = (uint32_t)__cvta_generic_to_shared(L);
-  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int q_first = cl_find_cell(tb.tstart, T.tcells, 0u);                   // cell of tile particle 0 (idle lanes of the last group stand on it)
+  volatile uint32_t* const vflag = s_flag;
 
-  // ============ one warp per tile cell, 32 of its particles at a time: lists in shared memory, then both outputs from them ======
+  // ============ one warp per GROUP of the sweep (32 consecutive tile particles, lane = particle; the lanes of a group belong to one,
+  // two or -- small cells -- a few tile cells): lists in shared memory, then both outputs from them ======
   for (;;)
   {
-    uint32_t uq = 0;
-    if (lane == 0) uq = atomicAdd(&s_next, 1u);
-    const int q = (int)__shfl_sync(0xffffffffu, uq, 0);
-    if (q >= T.tcells) break;
+    uint32_t ug = 0;
+    if (lane == 0) ug = atomicAdd(&s_next, 1u);
+    const uint32_t grp = __shfl_sync(FULL, ug, 0);
+    if (grp >= ngroups) break;
+    const uint32_t t = grp * 32u + (uint32_t)lane;                             // tile particle: group t >> 5, lane t & 31 of the sweep
+    const bool active = t < n_tile;
+    const int q = active ? cl_find_cell(tb.tstart, T.tcells, t) : q_first;
     const int ii = q % T.tci, jj = (q / T.tci) % T.tcj, kk = q / (T.tci * T.tcj);
     const int cia = T.ci0 + ii, cja = T.cj0 + jj, cka = T.ck0 + kk;
-    if (bp.sel_mode == 1 && cl_cell_is_inner(g, cia, cja, cka)) continue;
     const int ca = ijk_to_index(g.dims, cia, cja, cka);
-    const uint32_t nA = tb.tstart[q + 1] - tb.tstart[q];
-    const unsigned long long slot_off = (unsigned long long)ca * (unsigned long long)bp.slot_words;
-    if (nA == 0u)
-    {
-      if (lane == 0) { out.cell_stream[ca] = nullptr; out.stream_size[ca] = 0u; out.cell_stream_bytes[ca] = 0u; out.stream_off[ca] = slot_off; }
-      continue;
-    }
+    const uint32_t tq = tb.tstart[q];
+    const uint32_t nA = tb.tstart[q + 1] - tq;
+    const uint32_t pa = active ? t - tq : 0u;
     const int hA = (int)tb.thalo[q];
-    uint16_t* const base = out.pool + slot_off;
-    uint16_t* const lists = base + 2u * (nA + 1u);
-    uint32_t run = 0;                                      // list words of the cell so far
-    bool cell_fits = true;
-    for (uint32_t pa0 = 0; pa0 < nA; pa0 += 32u)
+    const uint32_t self = tb.hstart[hA] + pa, gself = tb.hfirst[hA] + pa;          // index in the sweep's staged halo / in the flat arrays
+    NbSelf me;
     {
-      const uint32_t nact = min(32u, nA - pa0);
-      const bool active = (uint32_t)lane < nact;
-      const uint32_t pa = pa0 + (active ? (uint32_t)lane : 0u);
-      const uint32_t self = tb.hstart[hA] + pa, gself = tb.hfirst[hA] + pa;        // index in the sweep's staged halo / in the flat arrays
-      NbSelf me;
-      {
-        const float4 qa = nb_candidate(S, hpad[hA] + pa);
-        me.x = -0.5f * qa.x; me.y = -0.5f * qa.y; me.z = -0.5f * qa.z;
-        me.c = active ? (float)((double)qa.w - (bp.max_dist2 + band)) : INFINITY;      // idle lanes accept nothing
-      }
-      uint32_t w = 1u, ngrp = 0u, ncand = 0u;          // L[0] = group counter; w = elements of the list so far
-      if (nact >= (uint32_t)bp.lane_min)
-      {
-        // ---- lane = particle; every lane sweeps the same candidates (broadcast loads); the accept masks of a neighbour cell stay in
-        // registers and are expanded into the lane's list right away
-        for (int rk = -gap; rk <= gap; rk++)
-        {
-          const int bk = cka + rk;
-          if (bk < 0 || bk >= g.dims[2]) continue;
-          for (int rj = -gap; rj <= gap; rj++)
-          {
-            const int bj = cja + rj;
-            if (bj < 0 || bj >= g.dims[1]) continue;
-            const int hrow = ((bk - T.bz0) * T.HY + (bj - T.by0)) * T.HX - T.bx0;
-            for (int ri = -gap; ri <= gap; ri++)
-            {
-              const int bi = cia + ri;
-              if (bi < 0 || bi >= g.dims[0]) continue;
-              const int hB = hrow + bi;
-              const uint32_t hp = hpad[hB], nB4 = hpad[hB + 1] - hp;          // padded staged range of the cell
-              if (nB4 == 0u) continue;
-              const bool own = rk == 0 && rj == 0 && ri == 0;
-              if (nB4 > 32u * (uint32_t)NBH_CELL_BLOCKS) { if (lane == 0) { s_ovf = 1u; atomicOr(&out.counters[NB_OVERFLOW], 4u); } continue; }    // host: other kernels
-              // bit b of cw[i] = p_b 32 i + b of this cell accepted
-              uint32_t cw[NBH_CELL_BLOCKS], cnt = 0;
-#pragma unroll
-              for (int k = 0; k < NBH_CELL_BLOCKS; k++)
-              {
-                cw[k] = 0u;
-                if ((uint32_t)(32 * k) < nB4)
-                {
-                  const uint32_t bb = hp + (uint32_t)(32 * k), n4 = min(32u, nB4 - (uint32_t)(32 * k));
-                  int trk = 0x7fffffff; uint32_t zb = 0u, mk;
-                  if (own)
-                  {
-                    mk = nb_block_bits<true>(S, bb, n4, me, zc, trk, zb);
-                    const uint32_t sb = pa - (uint32_t)(32 * k);
-                    if (sb < 32u) { mk &= ~(1u << sb); zb &= ~(1u << sb); }      // never a neighbour of itself
-                    zb &= mk;
-                  }
-                  else mk = nb_block_bits<false>(S, bb, n4, me, zc, trk, zb);
-                  const bool amb = active && ((trk < 0 && __int_as_float(trk) > -band2) || zb != 0u);
-                  if (__any_sync(0xffffffffu, amb))
-                  {
-                    if (amb) { mk = nb_block_exact(S, tb.hfirst[hB], (uint32_t)(32 * k), bb, mk, zb, me, band2, gself, bp.max_dist2, rx, ry, rz); atomicAdd(&s_stat[NB_AMBIGUOUS], 1u); }
-                  }
-                  cw[k] = mk; cnt += (uint32_t)__popc(mk);
-                }
-              }
-              if (cnt == 0u) continue;
-              if (w + 2u + cnt <= cap_l)
-              {
-                // group header: neighbour slot (byte lists) or the encoded cell index (chunk_neighbors.h:137-150), then the count
-                nb_sts<LT>(Lsh + w * ES, U8 ? (0x80u | (uint32_t)(((rk + gap) * n1 + (rj + gap)) * n1 + (ri + gap))) : (uint32_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint32_t)(ri + 16));
-                nb_sts<LT>(Lsh + (w + 1u) * ES, cnt);
-                uint32_t wa = Lsh + (w + 2u) * ES;
-#pragma unroll
-                for (int i = 0; i < NBH_CELL_BLOCKS; i++)
-                {
-                  uint32_t x = cw[i];
-                  while (x) { const uint32_t b = (uint32_t)__ffs((int)x) - 1u; x &= x - 1u; nb_sts<LT>(wa, (uint32_t)(32 * i) + b); wa += ES; }
-                }
-              }
-              w += 2u + cnt; ngrp++; ncand += cnt;
-            }
-          }
-        }
-      }
-      else
-      {
-        // ---- a few particles (sparse cell, or the tail of a cell): one particle at a time, lane = candidate; a ballot gives the
-        // accept mask and the accepted lanes append their p_b side by side
-        for (uint32_t a = 0; a < nact; a++)
-        {
-          NbSelf pa_c;
-          pa_c.x = __shfl_sync(0xffffffffu, me.x, a); pa_c.y = __shfl_sync(0xffffffffu, me.y, a); pa_c.z = __shfl_sync(0xffffffffu, me.z, a); pa_c.c = __shfl_sync(0xffffffffu, me.c, a);
-          const uint32_t pa_a = pa0 + a, gself_a = __shfl_sync(0xffffffffu, gself, a);
-          const uint32_t La = (uint32_t)__cvta_generic_to_shared(Lw + (size_t)a * cap_l);
-          uint32_t wa = 1u, ga = 0u, na = 0u;
-          for (int rk = -gap; rk <= gap; rk++)
-          {
-            const int bk = cka + rk;
-            if (bk < 0 || bk >= g.dims[2]) continue;
-            for (int rj = -gap; rj <= gap; rj++)
-            {
-              const int bj = cja + rj;
-              if (bj < 0 || bj >= g.dims[1]) continue;
-              const int hrow = ((bk - T.bz0) * T.HY + (bj - T.by0)) * T.HX - T.bx0;
-              for (int ri = -gap; ri <= gap; ri++)
-              {
-                const int bi = cia + ri;
-                if (bi < 0 || bi >= g.dims[0]) continue;
-                const int hB = hrow + bi;
-                const uint32_t hp = hpad[hB], nB = tb.hstart[hB + 1] - tb.hstart[hB];
-                if (nB == 0u) continue;
-                const bool own = rk == 0 && rj == 0 && ri == 0;
-                const uint32_t hdr = wa;
-                uint32_t ccount = 0u;
-                for (uint32_t p0 = 0; p0 < nB; p0 += 32u)
-                {
-                  const uint32_t j = p0 + lane;                        // p_b of this lane's candidate
-                  const bool valid = j < nB;
-                  const float tv = nb_value(pa_c, nb_candidate(S, hp + (valid ? j : 0u)));
-                  bool acc = valid && tv < 0.f && !(own && j == pa_a);
-                  const bool amb = acc && (tv > -band2 || (own && tv + zc < 0.f));
-                  if (__any_sync(0xffffffffu, amb))
-                  {
-                    if (amb) { acc = nb_exact(gself_a, tb.hfirst[hB] + j, bp.max_dist2, rx, ry, rz); atomicAdd(&s_stat[NB_AMBIGUOUS], 1u); }
-                  }
-                  const uint32_t mb = __ballot_sync(0xffffffffu, acc);
-                  const uint32_t np = (uint32_t)__popc(mb);
-                  if (acc && hdr + 2u + ccount + np <= cap_l) nb_sts<LT>(La + (hdr + 2u + ccount + (uint32_t)__popc(mb & lt_mask)) * ES, j);
-                  ccount += np;
-                }
-                if (ccount == 0u) continue;
-                if (lane == 0 && hdr + 2u <= cap_l)
-                {
-                  nb_sts<LT>(La + hdr * ES, U8 ? (0x80u | (uint32_t)(((rk + gap) * n1 + (rj + gap)) * n1 + (ri + gap))) : (uint32_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint32_t)(ri + 16));
-                  nb_sts<LT>(La + (hdr + 1u) * ES, ccount);
-                }
-                wa = hdr + 2u + ccount; ga++; na += ccount;
-              }
-            }
-          }
-          if ((uint32_t)lane == a) { w = wa; ngrp = ga; ncand = na; }
-        }
-        __syncwarp();
-      }
-      const uint32_t len = active ? w : 0u;                 // = 1 + 2 groups + entries
-      // ---- capacities
-      uint32_t mxl = len;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mxl = max(mxl, __shfl_xor_sync(0xffffffffu, mxl, o));
-      if (mxl > cap_l)
-      {
-        if (lane == 0) { atomicMax(&s_stat[NB_SLOTS], mxl); s_ovf = 1u; }
-        cell_fits = false;
-        continue;                                                                // lists incomplete: the host re-runs with more room
-      }
-      if (active) nb_sts<LT>(Lsh, ngrp);
-      if (lane == 0) atomicMax(&s_stat[NB_SLOTS], mxl);
-      if (active && (ngrp >= 65535u || ncand >= 65535u)) atomicOr(err, DERR_GROUP_OVERFLOW);
-      const uint32_t t = tb.tstart[q] + pa;                                  // tile particle: group t >> 5, lane t & 31 of the sweep
-      if (active) pcand[t] = (uint16_t)ncand;
-      uint32_t x = len, mxc = active ? ncand : 0u, csum = active ? ncand : 0u;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { mxc = max(mxc, __shfl_xor_sync(0xffffffffu, mxc, o)); csum += __shfl_xor_sync(0xffffffffu, csum, o); }
-      const uint32_t chunk_total = __shfl_sync(0xffffffffu, x, 31);
-      const uint32_t off = run + x - len;
-      if (lane == 0) { atomicMax(&s_stat[NB_MAX_NBH], mxc); atomicAdd(&s_tot[0], (unsigned long long)csum); }
-      const bool fits = 2u * (nA + 1u) + run + chunk_total <= (uint32_t)bp.slot_words;
-      const uint32_t my_trips = (ncand + 3u) >> 2;
-      const bool rows_fit = !bp.emit_rows || my_trips <= (uint32_t)bp.cap_trips;
-      if (active && !rows_fit) atomicMax(&s_stat[NB_TRIPS], my_trips);
-      cell_fits = cell_fits && fits;
-      run += chunk_total;
-      __syncwarp();
-      if (fits && active)
-      {
-        // offset table entry (chunk_neighbors_execute.h:279-283) and closing entry (:390-398)
-        reinterpret_cast<uint32_t*>(base)[pa] = off + 1u;
-        if (pa == nA - 1u) reinterpret_cast<uint32_t*>(base)[nA] = off + len + 1u;
-        // ---- (a) the reference-format list: every lane copies its own list, 8-byte stores once the destination is aligned (the 32
-        // lists of a chunk are adjacent in the stream, partial sectors merge in L2)
-        {
-          uint16_t* const dst = lists + off;
-          const uint32_t head = min(len, (uint32_t)(((8u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 7u)) & 7u) >> 1));
-          uint32_t v = 0;
-          for (; v < head; v++) dst[v] = (uint16_t)L[v];
-          for (; v + 4u <= len; v += 4u)
-          {
-            const uint32_t w0 = L[v], w1 = L[v + 1], w2 = L[v + 2], w3 = L[v + 3];
-            *reinterpret_cast<uint2*>(dst + v) = make_uint2(w0 | (w1 << 16), w2 | (w3 << 16));
-          }
-          for (; v < len; v++) dst[v] = (uint16_t)L[v];
-          if (U8)
-          {
-            // byte lists: the group headers hold 0x80 | slot; hop over them and write the cell codes
-            uint32_t pos = 1;
-            for (uint32_t gq = 0; gq < ngrp; gq++) { const uint32_t code = L[pos], n = L[pos + 1]; dst[pos] = s_enc[code & 0x7fu]; pos += 2u + n; }
-          }
-        }
-        // ---- (b) the compiled-row words of this particle: 8 x staged index of every entry, four per 8-byte store, into its column of
-        // the group's row block
-        if (bp.emit_rows && rows_fit)
-        {
-          uint2* col = out.rows + (((size_t)blockIdx.x * (size_t)tp.gmax + (t >> 5)) * (size_t)bp.cap_trips) * 32u + (t & 31u);
-          uint32_t pos = 1u, rem = 0u, hs8 = 0u, left = ncand;
-          const uint32_t pad = self << 3;                                       // own staged index: d2 = 0 is never inside the cut
-          for (uint32_t k = 0; k < my_trips; k++)
-          {
-            uint32_t wv[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-            {
-              if (left == 0u) { wv[u] = pad; continue; }
-              if (rem == 0u)
-              {
-                // next group: staged index of its cell's first particle
-                const uint32_t code = L[pos]; rem = L[pos + 1u]; pos += 2u;
-                int dh;
-                if (U8) dh = (int)s_dh[code & 0x7fu];
-                else dh = (((int)(code >> 10) - 16) * T.HY + ((int)((code >> 5) & 31u) - 16)) * T.HX + ((int)(code & 31u) - 16);
-                hs8 = tb.hstart[hA + dh] << 3;
-              }
-              wv[u] = hs8 + ((uint32_t)L[pos] << 3); pos++; rem--; left--;
-            }
-            col[(size_t)k * 32u] = make_uint2(wv[0] | (wv[1] << 16), wv[2] | (wv[3] << 16));
-          }
-        }
-      }
-      __syncwarp();
+      const float4 qa = nb_candidate(S, hpad[hA] + pa);
+      me.x = -0.5f * qa.x; me.y = -0.5f * qa.y; me.z = -0.5f * qa.z;
+      me.c = active ? (float)((double)qa.w - (bp.max_dist2 + band)) : INFINITY;      // idle lanes accept nothing
     }
-    // ---- per cell bookkeeping
+    // compiled rows of this group: lane's column, four entries per 8-byte word (word k of the column = entries 4k .. 4k+3)
+    const uint32_t row0 = (uint32_t)(((size_t)blockIdx.x * (size_t)tp.gmax + grp) * (size_t)bp.cap_trips);
+    uint2* const col = out.rows + (size_t)row0 * 32u + (uint32_t)lane;
+    const uint32_t cap_e = bp.emit_rows ? 4u * (uint32_t)bp.cap_trips : 0u;       // entries the lane's column can take
+    uint32_t buf_lo = 0u, buf_hi = 0u;
+
+    uint32_t w = 1u, ngrp = 0u, ncand = 0u;          // L[0] = group counter; w = elements of the list so far
+    // ---- every lane sweeps the neighbourhood of ITS cell (lanes of one cell read the same candidates: broadcast loads); the accept
+    // masks of a neighbour cell stay in registers and are expanded into the lane's list and its column of the rows right away
+    for (int rk = -gap; rk <= gap; rk++)
+      for (int rj = -gap; rj <= gap; rj++)
+        for (int ri = -gap; ri <= gap; ri++)
+        {
+          const int bi = cia + ri, bj = cja + rj, bk = cka + rk;
+          const bool exist = bi >= 0 && bi < g.dims[0] && bj >= 0 && bj < g.dims[1] && bk >= 0 && bk < g.dims[2];
+          const int hB = exist ? hA + (rk * T.HY + rj) * T.HX + ri : 0;
+          const uint32_t hp = hpad[hB], nB4 = exist ? hpad[hB + 1] - hp : 0u;          // padded staged range of the cell
+          const uint32_t nmax = __reduce_max_sync(FULL, nB4);
+          if (nmax == 0u) continue;
+          if (nmax > 32u * (uint32_t)NBH_CELL_BLOCKS) { if (lane == 0) { s_ovf = 1u; atomicOr(&out.counters[NB_OVERFLOW], 4u); } continue; }    // host: other kernels
+          const bool own = rk == 0 && rj == 0 && ri == 0;
+          // bit b of cw[i] = p_b 32 i + b of this cell accepted
+          uint32_t cw[NBH_CELL_BLOCKS], cnt = 0;
+#pragma unroll
+          for (int k = 0; k < NBH_CELL_BLOCKS; k++)
+          {
+            cw[k] = 0u;
+            if ((uint32_t)(32 * k) < nmax)
+            {
+              const uint32_t bb = hp + (uint32_t)(32 * k), n4 = min(32u, nmax - (uint32_t)(32 * k));
+              // candidates of this lane's cell among the n4 (the others belong to the cells behind it in the staged order)
+              const uint32_t nv = nB4 > (uint32_t)(32 * k) ? min(32u, nB4 - (uint32_t)(32 * k)) : 0u;
+              const uint32_t valid = nv >= 32u ? FULL : ((1u << nv) - 1u);
+              int trk = 0x7fffffff; uint32_t zb = 0u, mk;
+              if (own)
+              {
+                mk = nb_block_bits<true>(S, bb, n4, me, zc, trk, zb) & valid;
+                const uint32_t sb = pa - (uint32_t)(32 * k);
+                if (sb < 32u) { mk &= ~(1u << sb); zb &= ~(1u << sb); }      // never a neighbour of itself
+                zb &= mk;
+              }
+              else mk = nb_block_bits<false>(S, bb, n4, me, zc, trk, zb) & valid;
+              const bool amb = mk != 0u && ((trk < 0 && __int_as_float(trk) > -band2) || zb != 0u);
+              if (__any_sync(FULL, amb))
+              {
+                if (amb) { mk = nb_block_exact(S, tb.hfirst[hB], (uint32_t)(32 * k), bb, mk, zb, me, band2, gself, bp.max_dist2, rx, ry, rz); atomicAdd(&s_stat[NB_AMBIGUOUS], 1u); }
+              }
+              cw[k] = mk; cnt += (uint32_t)__popc(mk);
+            }
+          }
+          if (cnt == 0u) continue;
+          if (w + 2u + cnt <= cap_l)
+          {
+            // group header: neighbour slot (byte lists) or the encoded cell index (chunk_neighbors.h:137-150), then the count
+            nb_sts<LT>(Lsh + w * ES, U8 ? (0x80u | (uint32_t)(((rk + gap) * n1 + (rj + gap)) * n1 + (ri + gap))) : (uint32_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint32_t)(ri + 16));
+            nb_sts<LT>(Lsh + (w + 1u) * ES, cnt);
+            uint32_t wa = Lsh + (w + 2u) * ES;
+            const uint32_t hs8 = tb.hstart[hB] << 3;                     // 8 x staged index (sweep) of the cell's first particle
+            uint32_t r = ncand;
+#pragma unroll
+            for (int i = 0; i < NBH_CELL_BLOCKS; i++)
+            {
+              uint32_t x = __brev(cw[i]);
+              const uint32_t pb0 = (uint32_t)(32 * i);
+              while (x)
+              {
+                const uint32_t b = (uint32_t)__clz((int)x);
+                x ^= 0x80000000u >> b;
+                const uint32_t pb = pb0 + b;
+                nb_sts<LT>(wa, pb); wa += ES;
+                // compiled-row entry: shifted into the lane's pending word, stored every fourth entry
+                const uint32_t rv = hs8 + (pb << 3);
+                buf_lo = __funnelshift_r(buf_lo, buf_hi, 16);
+                buf_hi = __byte_perm(buf_hi, rv, 0x5432);
+                r++;
+                if ((r & 3u) == 0u && r <= cap_e) col[(size_t)((r >> 2) - 1u) * 32u] = make_uint2(buf_lo, buf_hi);
+              }
+            }
+          }
+          w += 2u + cnt; ngrp++; ncand += cnt;
+        }
+    const uint32_t len = active ? w : 0u;                 // = 1 + 2 groups + entries
+    // ---- capacities
+    const uint32_t mxl = __reduce_max_sync(FULL, len);
+    const uint32_t my_trips = (ncand + 3u) >> 2;
+    const uint32_t trips = __reduce_max_sync(FULL, my_trips);
+    const uint32_t mxc = __reduce_max_sync(FULL, ncand), csum = __reduce_add_sync(FULL, ncand);
     if (lane == 0)
     {
-      const uint32_t sz = 2u * (nA + 1u) + run;
+      atomicMax(&s_stat[NB_SLOTS], mxl); atomicMax(&s_stat[NB_TRIPS], trips); atomicMax(&s_stat[NB_MAX_NBH], mxc);
+      atomicAdd(&s_tot[0], (unsigned long long)csum);
+    }
+    if (active && (ngrp >= 65535u || ncand >= 65535u || len >= 65535u)) atomicOr(err, DERR_GROUP_OVERFLOW);
+    const bool lists_ok = mxl <= cap_l;                  // else: lists incomplete, the host re-runs with more room
+    if (!lists_ok && lane == 0) s_ovf = 1u;
+    // ---- compiled rows: the pending word, then pads (the particle's own staged index: d2 = 0 is never inside the cut) up to the
+    // group's longest list
+    if (bp.emit_rows)
+    {
+      const uint32_t pad = self << 3, pw = pad | (pad << 16);
+      if (trips <= (uint32_t)bp.cap_trips && lists_ok)
+      {
+        uint32_t r = ncand;
+        while (r & 3u) { buf_lo = __funnelshift_r(buf_lo, buf_hi, 16); buf_hi = __byte_perm(buf_hi, pad, 0x5432); r++; if ((r & 3u) == 0u) col[(size_t)((r >> 2) - 1u) * 32u] = make_uint2(buf_lo, buf_hi); }
+        for (uint32_t k = my_trips; k < trips; k++) col[(size_t)k * 32u] = make_uint2(pw, pw);
+        if (lane == 0) { gt[grp] = make_uint2(row0, trips); atomicAdd(&s_stat[NB_ROWS], trips); }
+      }
+      else if (lane == 0) { gt[grp] = make_uint2(row0, 0u); s_ovf = 1u; }
+    }
+    // ---- position of every list in its cell's stream: lengths of the cell's particles in front of it.  Those inside this group come
+    // from a scan; the part of the group's first cell that lies in earlier groups is read from the lengths those groups published
+    if (active) { plen[t] = (uint16_t)len; if (lists_ok) nb_sts<LT>(Lsh, ngrp); }
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); vflag[grp] = 1u; }
+    uint32_t x = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
+    const uint32_t same = __match_any_sync(FULL, q);
+    const int first = __ffs((int)same) - 1;
+    const uint32_t ex = x - len;
+    uint32_t off = ex - __shfl_sync(FULL, ex, first);
+    const int q0 = __shfl_sync(FULL, q, 0);
+    const uint32_t t0 = __shfl_sync(FULL, tq, 0);
+    if (t0 < grp * 32u)
+    {
+      // wait for the groups that hold the front part of the cell (they were claimed earlier and never wait for this one)
+      const uint32_t g0 = t0 >> 5;
+      for (;;)
+      {
+        const uint32_t gi = g0 + (uint32_t)lane;
+        const bool ready = gi >= grp || vflag[gi] != 0u;
+        if (__all_sync(FULL, ready)) break;
+        __nanosleep(64);
+      }
+      __threadfence_block();
+      uint32_t carry = 0;
+      for (uint32_t u = t0 + (uint32_t)lane; u < grp * 32u; u += 32u) carry += (uint32_t)reinterpret_cast<volatile uint16_t*>(plen)[u];
+      carry = __reduce_add_sync(FULL, carry);
+      if (q == q0) off += carry;
+    }
+    const unsigned long long slot_off = (unsigned long long)ca * (unsigned long long)bp.slot_words;
+    uint16_t* const base = out.pool + slot_off;
+    uint16_t* const lists = base + 2u * (nA + 1u);
+    const bool fits = lists_ok && 2u * (nA + 1u) + off + len <= (uint32_t)bp.slot_words;
+    if (fits && active)
+    {
+      // offset table entry (chunk_neighbors_execute.h:279-283) and closing entry (:390-398)
+      reinterpret_cast<uint32_t*>(base)[pa] = off + 1u;
+      if (pa == nA - 1u) reinterpret_cast<uint32_t*>(base)[nA] = off + len + 1u;
+      // ---- the reference-format list: every lane copies its own list, 8-byte stores once the destination is aligned (the lists of a
+      // group are adjacent in the stream, partial sectors merge in L2)
+      uint16_t* const dst = lists + off;
+      const uint32_t head = min(len, (uint32_t)(((8u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 7u)) & 7u) >> 1));
+      uint32_t v = 0;
+      for (; v < head; v++) dst[v] = (uint16_t)L[v];
+      for (; v + 4u <= len; v += 4u)
+      {
+        const uint32_t w0 = L[v], w1 = L[v + 1], w2 = L[v + 2], w3 = L[v + 3];
+        *reinterpret_cast<uint2*>(dst + v) = make_uint2(w0 | (w1 << 16), w2 | (w3 << 16));
+      }
+      for (; v < len; v++) dst[v] = (uint16_t)L[v];
+      if (U8)
+      {
+        // byte lists: the group headers hold 0x80 | slot; hop over them and write the cell codes
+        uint32_t pos = 1;
+        for (uint32_t gq = 0; gq < ngrp; gq++) { const uint32_t code = L[pos], n = L[pos + 1]; dst[pos] = s_enc[code & 0x7fu]; pos += 2u + n; }
+      }
+    }
+    // ---- per cell bookkeeping, by the lane of the cell's last particle
+    if (active && pa == nA - 1u)
+    {
+      const uint32_t sz = 2u * (nA + 1u) + off + len;
       const uint32_t szp = (sz + 7u) & ~7u;
-      const bool fits = cell_fits && szp <= (uint32_t)bp.slot_words;
-      out.cell_stream[ca] = fits ? base : nullptr;
+      const bool cfits = lists_ok && szp <= (uint32_t)bp.slot_words;
+      out.cell_stream[ca] = cfits ? base : nullptr;
       out.stream_size[ca] = sz; out.cell_stream_bytes[ca] = sz * 2u; out.stream_off[ca] = slot_off;
-      if (fits) for (uint32_t p = sz; p < szp; p++) base[p] = 0;       // deterministic padding
+      if (cfits) for (uint32_t p = sz; p < szp; p++) base[p] = 0;       // deterministic padding
+      if (!cfits) s_ovf = 1u;
       atomicMax(&s_stat[NB_MAX_CELL], nA); atomicMax(&s_stat[NB_MAX_STREAM], szp); atomicMax(&s_stat[NB_SLOT_WORDS], szp);
       atomicAdd(&s_tot[1], (unsigned long long)szp);
       if (cl_cell_is_inner(g, cia, cja, cka)) { atomicAdd(&s_tot[2], (unsigned long long)szp); atomicAdd(&s_stat[NB_NONEMPTY], 1u); }
     }
-  }
-  __syncthreads();
-  // ---- compiled rows: every group is padded to its longest list (a group's lanes may come from different cells, i.e. warps)
-  if (bp.emit_rows && !s_ovf && s_stat[NB_TRIPS] == 0u)
-  {
-    const int q0 = cl_find_cell(tb.tstart, T.tcells, 0u);
-    const uint32_t pad0 = tb.hstart[tb.thalo[q0]] << 3;                        // idle lanes of the tile's last group stand on tile particle 0
-    for (uint32_t grp = warp; grp < ngroups; grp += nwarp)
-    {
-      const uint32_t t = grp * 32u + lane;
-      const bool active = t < n_tile;
-      const uint32_t nc = active ? (uint32_t)pcand[t] : 0u;
-      uint32_t trips = (nc + 3u) >> 2;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, o));
-      const uint32_t row0 = (uint32_t)(((size_t)blockIdx.x * (size_t)tp.gmax + grp) * (size_t)bp.cap_trips);
-      if (lane == 0) { gt[grp] = make_uint2(row0, trips); atomicAdd(&s_stat[NB_ROWS], trips); }
-      uint32_t pad = pad0;
-      if (active)
-      {
-        const int q = cl_find_cell(tb.tstart, T.tcells, t);
-        pad = (tb.hstart[tb.thalo[q]] + (t - tb.tstart[q])) << 3;
-      }
-      const uint32_t pw = pad | (pad << 16);
-      uint2* col = out.rows + (size_t)row0 * 32u + (uint32_t)lane;
-      for (uint32_t k = (nc + 3u) >> 2; k < trips; k++) col[(size_t)k * 32u] = make_uint2(pw, pw);
-    }
+    __syncwarp();
   }
   __syncthreads();
   if (threadIdx.x == 0)
