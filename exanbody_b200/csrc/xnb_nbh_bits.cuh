@@ -304,6 +304,8 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
   const uint32_t Lsh = (uint32_t)__cvta_generic_to_shared(L);
   const int q_first = cl_find_cell(tb.tstart, T.tcells, 0u);                   // cell of tile particle 0 (idle lanes of the last group stand on it)
   volatile uint32_t* const vflag = s_flag;
+  // every neighbour cell of every tile cell lies inside the grid unless the halo box was clipped
+  const bool all_exist = T.HX == T.tci + 2 * gap && T.HY == T.tcj + 2 * gap && T.HZ == T.tck + 2 * gap;
 
   // ============ one warp per GROUP of the sweep (32 consecutive tile particles, lane = particle; the lanes of a group belong to one,
   // two or -- small cells -- a few tile cells): lists in shared memory, then both outputs from them ======
@@ -333,8 +335,11 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
     // compiled rows of this group: lane's column, four entries per 8-byte word (word k of the column = entries 4k .. 4k+3)
     const uint32_t row0 = (uint32_t)(((size_t)blockIdx.x * (size_t)tp.gmax + grp) * (size_t)bp.cap_trips);
     uint2* const col = out.rows + (size_t)row0 * 32u + (uint32_t)lane;
-    const uint32_t cap_e = bp.emit_rows ? 4u * (uint32_t)bp.cap_trips : 0u;       // entries the lane's column can take
-    uint32_t buf_lo = 0u, buf_hi = 0u;
+    uint2* colp = col;                                                             // where the lane's pending word goes
+    const uint32_t cap_e = bp.emit_rows ? 4u * (uint32_t)bp.cap_trips : 0xffffffffu;       // entries the lane's column can take
+    const uint32_t rows_on = bp.emit_rows ? 0u : 4u;                              // (r & 3) == 4 never holds: no rows
+    uint32_t buf_lo = 0u, buf_hi = 0u, r = 0u;
+    bool room = true;                                                              // the lane's list and column still take everything
 
     uint32_t w = 1u, ngrp = 0u, ncand = 0u;          // L[0] = group counter; w = elements of the list so far
     // ---- every lane sweeps the neighbourhood of ITS cell (lanes of one cell read the same candidates: broadcast loads); the accept
@@ -344,7 +349,7 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
         for (int ri = -gap; ri <= gap; ri++)
         {
           const int bi = cia + ri, bj = cja + rj, bk = cka + rk;
-          const bool exist = bi >= 0 && bi < g.dims[0] && bj >= 0 && bj < g.dims[1] && bk >= 0 && bk < g.dims[2];
+          const bool exist = all_exist || (bi >= 0 && bi < g.dims[0] && bj >= 0 && bj < g.dims[1] && bk >= 0 && bk < g.dims[2]);
           const int hB = exist ? hA + (rk * T.HY + rj) * T.HX + ri : 0;
           const uint32_t hp = hpad[hB], nB4 = exist ? hpad[hB + 1] - hp : 0u;          // padded staged range of the cell
           const uint32_t nmax = __reduce_max_sync(FULL, nB4);
@@ -381,31 +386,29 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
             }
           }
           if (cnt == 0u) continue;
-          if (w + 2u + cnt <= cap_l)
+          room = room && w + 2u + cnt <= cap_l && ncand + cnt <= cap_e;
+          if (room)
           {
             // group header: neighbour slot (byte lists) or the encoded cell index (chunk_neighbors.h:137-150), then the count
             nb_sts<LT>(Lsh + w * ES, U8 ? (0x80u | (uint32_t)(((rk + gap) * n1 + (rj + gap)) * n1 + (ri + gap))) : (uint32_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint32_t)(ri + 16));
             nb_sts<LT>(Lsh + (w + 1u) * ES, cnt);
             uint32_t wa = Lsh + (w + 2u) * ES;
             const uint32_t hs8 = tb.hstart[hB] << 3;                     // 8 x staged index (sweep) of the cell's first particle
-            uint32_t r = ncand;
 #pragma unroll
             for (int i = 0; i < NBH_CELL_BLOCKS; i++)
             {
               uint32_t x = __brev(cw[i]);
-              const uint32_t pb0 = (uint32_t)(32 * i);
+              const uint32_t hs8i = hs8 + (uint32_t)(256 * i);
               while (x)
               {
                 const uint32_t b = (uint32_t)__clz((int)x);
                 x ^= 0x80000000u >> b;
-                const uint32_t pb = pb0 + b;
-                nb_sts<LT>(wa, pb); wa += ES;
+                nb_sts<LT>(wa, (uint32_t)(32 * i) + b); wa += ES;
                 // compiled-row entry: shifted into the lane's pending word, stored every fourth entry
-                const uint32_t rv = hs8 + (pb << 3);
                 buf_lo = __funnelshift_r(buf_lo, buf_hi, 16);
-                buf_hi = __byte_perm(buf_hi, rv, 0x5432);
+                buf_hi = __byte_perm(buf_hi, hs8i + (b << 3), 0x5432);
                 r++;
-                if ((r & 3u) == 0u && r <= cap_e) col[(size_t)((r >> 2) - 1u) * 32u] = make_uint2(buf_lo, buf_hi);
+                if ((r & 3u) == rows_on) { *colp = make_uint2(buf_lo, buf_hi); colp += 32; }
               }
             }
           }
@@ -423,17 +426,16 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
       atomicAdd(&s_tot[0], (unsigned long long)csum);
     }
     if (active && (ngrp >= 65535u || ncand >= 65535u || len >= 65535u)) atomicOr(err, DERR_GROUP_OVERFLOW);
-    const bool lists_ok = mxl <= cap_l;                  // else: lists incomplete, the host re-runs with more room
+    const bool lists_ok = __all_sync(FULL, room);        // else: lists incomplete, the host re-runs with more room
     if (!lists_ok && lane == 0) s_ovf = 1u;
     // ---- compiled rows: the pending word, then pads (the particle's own staged index: d2 = 0 is never inside the cut) up to the
     // group's longest list
     if (bp.emit_rows)
     {
       const uint32_t pad = self << 3, pw = pad | (pad << 16);
-      if (trips <= (uint32_t)bp.cap_trips && lists_ok)
+      if (lists_ok)
       {
-        uint32_t r = ncand;
-        while (r & 3u) { buf_lo = __funnelshift_r(buf_lo, buf_hi, 16); buf_hi = __byte_perm(buf_hi, pad, 0x5432); r++; if ((r & 3u) == 0u) col[(size_t)((r >> 2) - 1u) * 32u] = make_uint2(buf_lo, buf_hi); }
+        while (r & 3u) { buf_lo = __funnelshift_r(buf_lo, buf_hi, 16); buf_hi = __byte_perm(buf_hi, pad, 0x5432); r++; if ((r & 3u) == 0u) *colp = make_uint2(buf_lo, buf_hi); }
         for (uint32_t k = my_trips; k < trips; k++) col[(size_t)k * 32u] = make_uint2(pw, pw);
         if (lane == 0) { gt[grp] = make_uint2(row0, trips); atomicAdd(&s_stat[NB_ROWS], trips); }
       }
