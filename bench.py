@@ -224,6 +224,7 @@ def parity_against_oracle(o, steps, rebuilds_oracle, kw, device):
         # single-step force parity on IDENTICAL positions: hand the GPU's state to the oracle and let it recompute lists and forces
         pcell, cnt = U.gpu_particles_cell_order(ctx)
         o.set_particles(cnt, pcell); o.build_neighbors(); o.compute_force()
+        ctx.chunk_neighbors()               # lists of the FINAL configuration on both sides (the step loop's lists date from its last rebuild)
         sz_o, data_o = o.streams(); sz_g, data_g = ctx.streams()
         out["streams_equal"] = bool(np.array_equal(sz_o, sz_g) and np.array_equal(data_o, data_g))
         out["stream_words"] = int(np.asarray(sz_g, np.int64).sum())

@@ -4,6 +4,7 @@
 #include "xnb_kernels.cuh"
 #include "xnb_sweep_cl.cuh"
 #include "xnb_nbh_bits.cuh"
+#include "xnb_pair_generic.cuh"
 #include "xnb_host_decomp.hpp"
 
 #include <algorithm>
@@ -1381,6 +1382,36 @@ int xnb_lennard_jones_force(xnb_ctx* c, double eps, double sig, double rcut, int
   if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "lennard_jones_force: no neighbour list (run xnb_chunk_neighbors)");
   c->rcut_max = std::max(c->rcut_max, rcut);    // lennard_jones.cu:193
   return launch_force<0, false>(c, ghost != 0, make_lj(eps, sig, rcut), 0.0, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+// op `gravitational_force` (contribs/pi/gravitational_force.cu:161-217): the second functor of the concept, with a per-neighbour
+// field (the neighbour's type -> mass).  Goes through the general sweep (xnb_pair_generic.cuh); buffer_form selects which of the two
+// call forms of the functor the sweep uses (0: buffer-less, 1: ComputePairBuffer2).  Accumulates into fx,fy,fz.
+int xnb_gravitational_force(xnb_ctx* c, double G, double rcut, int ghost, int buffer_form, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "gravitational_force: no neighbour list (run xnb_chunk_neighbors)");
+  if (c->nbh_half_symmetric) return c->fail(XNB_ERR_INVALID, "gravitational_force: the full-list pair sweep needs full lists");
+  if (ghost) return c->fail(XNB_ERR_INVALID, "gravitational_force: ghost = true is not offered by the general sweep");
+  if (!c->mass.p || c->n_types <= 0) return c->fail(XNB_ERR_INVALID, "gravitational_force: particle type property 'mass' is missing (xnb_set_type_mass)");
+  c->rcut_max = std::max(c->rcut_max, rcut);    // gravitational_force.cu:184
+  cudaStream_t st = (cudaStream_t)stream;
+  ParticlesP A = c->P(c->cur);
+  int rc;
+  if ((rc = t_begin(c, XNB_T_FORCE, st))) return rc;
+  if (c->n_inner)
+  {
+    const CellsView cells{c->cell_start.p, c->cell_count.p, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, A.id, A.type};
+    const GravitationalForceFunctor f{G, c->mass.p};
+    if (buffer_form)
+      LAUNCH((k_pair_sweep_generic<GravitationalForceFunctor, true>), nblk(c->n_inner, 128), 128, st, c->g, (int)c->n_inner, f, rcut * rcut, cells, A.fx, A.fy, A.fz,
+             c->atom_cell[c->cur_ac].p, (const uint16_t* const*)c->cell_stream.p, c->d_scalars32.p);
+    else
+      LAUNCH((k_pair_sweep_generic<GravitationalForceFunctor, false>), nblk(c->n_inner, 128), 128, st, c->g, (int)c->n_inner, f, rcut * rcut, cells, A.fx, A.fy, A.fz,
+             c->atom_cell[c->cur_ac].p, (const uint16_t* const*)c->cell_stream.p, c->d_scalars32.p);
+  }
+  return t_end(c, XNB_T_FORCE, st);
 }
 
 int xnb_set_chunk_neighbors_config(xnb_ctx* c, int half_symmetric, int skip_ghosts)

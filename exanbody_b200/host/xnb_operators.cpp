@@ -388,6 +388,34 @@ struct LennardJonesForce : OperatorNode     // contribs/md/lennard_jones/lennard
     else ck(grid->ctx, xnb_lennard_jones_force(grid->ctx, config->epsilon, config->sigma, *rcut, *ghost ? 1 : 0, stream), "lennard_jones_force");
   }
 };
+// a second functor of the pair-functor concept, with a per-neighbour field (the neighbour's type): runs through the general pair sweep
+struct GravitationalForce : OperatorNode    // contribs/pi/gravitational_force.cu:161-217
+{
+  ADD_SLOT(GravitationalParms, config, INPUT, REQUIRED, DocString{"gravitational constant G"});
+  ADD_SLOT(ParticleTypeProperties, particle_type_properties, INPUT, ParticleTypeProperties{});
+  ADD_SLOT(double, rcut, INPUT, 0.0, DocString{"Cutoff distance"});
+  ADD_SLOT(GridChunkNeighbors, chunk_neighbors, INPUT, GridChunkNeighbors{}, DocString{"neighbor list"});
+  ADD_SLOT(bool, ghost, INPUT, false, DocString{"Enables computation in ghost cells"});
+  ADD_SLOT(bool, compute_buffer, INPUT, false, DocString{"OURS: call the functor's ComputePairBuffer2 form instead of the buffer-less one"});
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED, DocString{"Simulation domain"});
+  ADD_SLOT(double, rcut_max, INPUT_OUTPUT, 0.0, DocString{"Updated max rcut"});
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT, DocString{"Local sub-domain particles grid"});
+  void yaml_initialize(const Params& p) override
+  {
+    if (p.has("config.G")) { if (!config.value) config.value = std::make_shared<GravitationalParms>(); config->G = p.quantity("config.G"); }
+    if (p.has("rcut")) { rcut.value = std::make_shared<double>(p.quantity("rcut")); }
+    XNB_PARAM_BOOL(p, ghost); XNB_PARAM_BOOL(p, compute_buffer);
+    *rcut_max = std::max(*rcut, *rcut_max);
+  }
+  void execute() override
+  {
+    *rcut_max = std::max(*rcut, *rcut_max);            // :184
+    if (grid->number_of_cells() == 0) return;
+    if (particle_type_properties->mass.empty()) fatal_error("particle type property 'mass' is missing");      // :187-190
+    ck(grid->ctx, xnb_set_type_mass(grid->ctx, particle_type_properties->mass.data(), (int)particle_type_properties->mass.size()), "particle masses");
+    ck(grid->ctx, xnb_gravitational_force(grid->ctx, config->G, *rcut, *ghost ? 1 : 0, *compute_buffer ? 1 : 0, stream), "gravitational_force");
+  }
+};
 struct UpdateForceFromGhost : OperatorNode  // mpi/update_force_from_ghost.cu:44 (UpdateFromGhosts<fx,fy,fz, UpdateValueAdd>)
 {
   ADD_SLOT(Grid, grid, INPUT_OUTPUT);
@@ -540,6 +568,7 @@ void register_hot_path_operators()
   f->register_factory("resize_particle_locks", make_simple_operator<Nop>());     // ComputePairOptionalLocks<false>: LJ takes no locks
   f->register_factory("zero_particle_force", make_simple_operator<ZeroParticleForce>());
   f->register_factory("lennard_jones_force", make_simple_operator<LennardJonesForce<false>>());
+  f->register_factory("gravitational_force", make_simple_operator<GravitationalForce>());
   f->register_factory("lennard_jones_force_symmetric", make_simple_operator<LennardJonesForce<true>>());
   f->register_factory("update_force_from_ghost", make_simple_operator<UpdateForceFromGhost>());   // adds zeros after a full-list sweep (ghost forces are 0 then)
   f->register_factory("divide_force_by_type_scalar", make_simple_operator<DivideForceByTypeScalar>());

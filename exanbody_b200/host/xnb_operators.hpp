@@ -44,6 +44,7 @@ struct Domain
   AABB bounds; double cell_size = 0; IJK grid_dims; bool periodic[3] = {true, true, true}; bool expandable = false;
 };
 struct LennardJonesParms { double epsilon = 0, sigma = 0; };                 // lennard_jones.cu:40-44
+struct GravitationalParms { double G = 0.0; };                              // contribs/pi/gravitational_force.cu:42-45
 struct ChunkNeighborsConfig                                                  // chunk_neighbors_config.h:27-39
 {
   bool free_scratch_memory = false, build_particle_offset = true, subcell_compaction = true, half_symmetric = false, skip_ghosts = false;

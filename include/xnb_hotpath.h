@@ -157,6 +157,15 @@ int xnb_set_pair_functor(xnb_ctx*, int functor);
    compute_cell_particle_pairs (src/compute/include/exanb/compute/compute_cell_particle_pairs.h:122-189).
    ACCUMULATES into fx,fy,fz like the reference (call xnb_zero_particle_force first).                            */
 int xnb_lennard_jones_force(xnb_ctx*, double epsilon, double sigma, double rcut, int ghost, void* stream);
+/* op `gravitational_force` : contribs/pi/gravitational_force.cu:161-217 (functor :48-132, traits :144-150) -- a second
+   functor of the concept, one that reads a PER-NEIGHBOUR field (the neighbour's type, for its mass; the reference passes
+   SimpleNbhComputeBuffer<FieldSet<type>>, :175).  It runs through the general pair sweep (csrc/xnb_pair_generic.cuh:
+   compute_cell_particle_pairs_impl_default.h:87-239 for any functor of the concept, reference-format streams, cells[c][field][p]
+   views).  buffer_form = 0: the buffer-less call `func(dr, d2, type_a, fx, fy, fz, cells, cell_b, p_b, weight)`
+   (impl_default.h:199-204); buffer_form = 1: the ComputePairBuffer2 call `func(n, buf, type_a, fx, fy, fz, cells)`
+   (impl_default.h:213-222, compute_pair_buffer.h:150-243; capacity 512 neighbours inside the cut, more is an error).
+   Masses: xnb_set_type_mass.  ACCUMULATES into fx,fy,fz.  ghost must be 0.                                         */
+int xnb_gravitational_force(xnb_ctx*, double G, double rcut, int ghost, int buffer_form, void* stream);
 /* ---- Newton-3 path ---------------------------------------------------------------------- */
 /* ChunkNeighborsConfig::half_symmetric / skip_ghosts of the chunk_neighbors operator (chunk_neighbors_config.h:35-36),
    i.e. NeighborFilterHalfSymGhost (neighbor_filter_func.h:36-52): half_symmetric keeps b only if cell_b < cell_a or

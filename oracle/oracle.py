@@ -44,9 +44,10 @@ def lib():
         L.xo_destroy.argtypes = [P]
         L.xo_last_error.restype = C.c_char_p
         for f in ("xo_init", "xo_generate", "xo_first_iteration", "xo_move_particles", "xo_update_particles_full", "xo_ghost_update_r", "xo_build_neighbors",
-                  "xo_compute_force", "xo_compute_force_symmetric", "xo_push_f_v_r", "xo_check_streams"):
+                  "xo_compute_force", "xo_compute_force_symmetric", "xo_push_f_v_r", "xo_check_streams", "xo_zero_force"):
             getattr(L, f).argtypes = [P]; getattr(L, f).restype = C.c_int
         L.xo_run.argtypes = [P, C.c_int]; L.xo_run.restype = C.c_int
+        L.xo_gravitational_force.argtypes = [P, C.c_double, C.c_double, P, C.c_int]; L.xo_gravitational_force.restype = C.c_int
         L.xo_push_f_v.argtypes = [P, C.c_double]; L.xo_push_f_v.restype = C.c_int
         for f in ("xo_displ_over", "xo_total_particles", "xo_inner_particles", "xo_stream_total_u16", "xo_max_neighbors",
                   "xo_rebuild_count"):
@@ -119,6 +120,10 @@ class Oracle:
     def build_neighbors(self): self._chk(self.L.xo_build_neighbors(self.h))
     def compute_force(self): self._chk(self.L.xo_compute_force(self.h))
     def compute_force_symmetric(self): self._chk(self.L.xo_compute_force_symmetric(self.h))
+    def zero_force(self): self._chk(self.L.xo_zero_force(self.h))
+    def gravitational_force(self, G, rcut, type_mass):
+        m = np.ascontiguousarray(type_mass, np.float64)
+        self._chk(self.L.xo_gravitational_force(self.h, float(G), float(rcut), m.ctypes.data_as(C.c_void_p), len(m)))
 
     def set_nbh_config(self, half_symmetric=False, skip_ghosts=False):
         self.L.xo_set_nbh_config(self.h, int(bool(half_symmetric)), int(bool(skip_ghosts)))

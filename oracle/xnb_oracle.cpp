@@ -848,6 +848,62 @@ static int compute_force(xo_sim& s, double* epot_out, double* vir_out)
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * gravitational_force (contribs/pi/gravitational_force.cu:161-217): compute_cell_particle_pairs over the inner cells with the
+ * functor of :48-85 (buffer-less form; CentralParticleFieldSet = type, fx, fy, fz; the neighbour's type is read through
+ * cells[cell_b][type][p_b] :76, masses through the type property 'mass' :75,77):
+ *   r = sqrt(d2); inv_r = 1/r; de = G ma mb inv_r inv_r; de *= w / r; f += de * dr          (:50-55, :78-84)
+ * ADDS to the force fields (no zeroing, no division by mass: neither is part of the operator).  Not pinned by any reference test.
+ * ---------------------------------------------------------------------------------------------- */
+static int gravitational_force(xo_sim& s, double G, double rcut, const double* type_mass, int n_types)
+{
+  Grid& g = s.grid;
+  const i64 gl = g.ghost_layers();
+  const double rcut2 = rcut * rcut;
+  int bad_type = 0;
+# pragma omp parallel for collapse(3) schedule(dynamic)
+  for (i64 k = gl; k < g.dims.k - gl; k++) for (i64 j = gl; j < g.dims.j - gl; j++) for (i64 i = gl; i < g.dims.i - gl; i++)
+  {
+    const i64 cell_a = ijk_to_index(g.dims, IJK{i, j, k});
+    Cell& A = g.cells[(size_t)cell_a];
+    const size_t na = A.size();
+    const StreamInfo si = stream_info(s.streams[(size_t)cell_a], na);
+    for (size_t pa = 0; pa < na; pa++)
+    {
+      const double xa = A.rx[pa], ya = A.ry[pa], za = A.rz[pa];
+      const int type_a = (int)A.type[pa];
+      if (type_a >= n_types) { bad_type = 1; continue; }
+      const double mass_a = type_mass[type_a];
+      double fx = A.fx[pa], fy = A.fy[pa], fz = A.fz[pa];
+      for_each_listed(s, cell_a, pa, si, [&](i64 cell_b, size_t pb) {
+        const Cell& B = g.cells[(size_t)cell_b];
+        const double dx = B.rx[pb] - xa, dy = B.ry[pb] - ya, dz = B.rz[pb] - za;
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 > 0.0 && d2 <= rcut2)
+        {
+          const int type_b = (int)B.type[pb];
+          if (type_b >= n_types) { bad_type = 1; return; }
+          const double mass_b = type_mass[type_b];
+          const double r = std::sqrt(d2);
+          const double inv_r = 1.0 / r;
+          double de = G * mass_a * mass_b * inv_r * inv_r;
+          de *= 1.0 / r;
+          fx += de * dx; fy += de * dy; fz += de * dz;
+        }
+      });
+      A.fx[pa] = fx; A.fy[pa] = fy; A.fz[pa] = fz;
+    }
+  }
+  if (bad_type) { g_err = "gravitational_force: particle type without a mass"; return 1; }
+  return 0;
+}
+
+/* zero_particle_force{ghost:true} alone (zero_particle_force.cu:15-46) */
+static void zero_force(xo_sim& s)
+{
+  for (Cell& c : s.grid.cells) { std::fill(c.fx.begin(), c.fx.end(), 0.); std::fill(c.fy.begin(), c.fy.end(), 0.); std::fill(c.fz.begin(), c.fz.end(), 0.); }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Symmetric (Newton-3) pair sweep over half_symmetric lists -- SURVEY 8(f) rank 2.  The reference has no symmetric LJ
  * operator; this restates what its machinery does for a symmetric pair functor:
  *   zero_particle_force{ghost:true}
@@ -1046,6 +1102,8 @@ int xo_ghost_update_r(xo_sim* s) { ghost_update(*s, false); return 0; }
 int xo_build_neighbors(xo_sim* s) { amr_grid_pairs(*s); chunk_neighbors(*s); return 0; }
 int xo_compute_force(xo_sim* s) { return compute_force(*s, nullptr, nullptr); }
 int xo_compute_force_symmetric(xo_sim* s) { return compute_force_symmetric(*s); }
+int xo_zero_force(xo_sim* s) { zero_force(*s); return 0; }
+int xo_gravitational_force(xo_sim* s, double G, double rcut, const double* type_mass, int n_types) { return gravitational_force(*s, G, rcut, type_mass, n_types); }
 void xo_set_nbh_config(xo_sim* s, int half_symmetric, int skip_ghosts) { s->nbh_half_symmetric = half_symmetric != 0; s->nbh_skip_ghosts = skip_ghosts != 0; }
 int xo_push_f_v_r(xo_sim* s) { push_f_v_r(*s); return 0; }
 int xo_push_f_v(xo_sim* s, double sc) { push_f_v(*s, sc); return 0; }

@@ -465,3 +465,38 @@ def test_error_behaviour():
     c4.set_particles(np.zeros(0), np.zeros(0), np.zeros(0))
     c4.first_iteration(1.0, 1.0, 1.5)
     assert c4.n_total == 0 and c4.run_steps(3, 0.005, 1.0, 1.0, 1.5) == 0
+
+
+@pytest.mark.parametrize("buffer_form", [False, True])
+@pytest.mark.parametrize("case", ["lj2k", "lj_gap2", "lj_voids", "ni16k"])
+def test_gravitational_force_second_functor(case, buffer_form):
+    """a second functor of the concept, one that reads a per-neighbour field -- gravitational_force
+    (contribs/pi/gravitational_force.cu): masses by particle TYPE of the central particle and of the neighbour, through both call forms
+    (buffer-less / ComputePairBuffer2) of the general pair sweep, against the oracle's restatement on the same lists.  Three types
+    with different masses; forces within 1e-10, the two call forms within rounding of each other."""
+    kw = CASES[case]
+    inp = U.generate_input(kw)
+    inp["type"] = (inp["id"] % 3).astype(np.uint8)
+    type_mass = np.array([1.0, 2.5, 0.125])
+    G, rcut = 0.75, kw["rcut"]
+    o = U.make_oracle(kw)
+    o.generate()
+    ctx = U.make_ctx(kw, particles=inp)
+    ctx.set_type_mass(type_mass)
+    ctx.move_particles(); ctx.update_particles_full()
+    # the oracle takes the GPU's grid content (in-cell order and types included), builds its own lists and sweeps them
+    o.move_particles(); o.update_particles_full()
+    pcell, cnt = U.gpu_particles_cell_order(ctx)
+    assert set(np.unique(pcell["type"])) == {0, 1, 2}
+    o.set_particles(cnt, pcell); o.build_neighbors()
+    o.zero_force(); o.gravitational_force(G, rcut, type_mass)
+    ctx.zero_particle_force(True); ctx.gravitational_force(G, rcut, buffer_form=buffer_form)
+    po = U.by_id(o.particles(), o.inner_mask()); pg = U.by_id(ctx.get_particles(0, ctx.n_inner))
+    assert np.array_equal(po["id"], pg["id"]) and np.array_equal(po["type"], pg["type"])
+    fo, fg = U.vec(po, ("fx", "fy", "fz")), U.vec(pg, ("fx", "fy", "fz"))
+    assert np.abs(fo).max() > 0
+    assert U.force_error(fg, fo) <= TOL
+    # ACCUMULATES like the reference operator: a second call doubles the forces
+    ctx.gravitational_force(G, rcut, buffer_form=not buffer_form)
+    pg2 = U.by_id(ctx.get_particles(0, ctx.n_inner))
+    assert U.force_error(U.vec(pg2, ("fx", "fy", "fz")), 2.0 * fo) <= TOL
