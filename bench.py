@@ -158,11 +158,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, workload_name="C2"):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture OF THE SAME WORKLOAD (null when there is none)"""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         try:
             e = json.load(open(p)).get(kernel)
+            if e and e.get("workload", "C2") != workload_name:
+                return None
             return float(e["dram_bytes_per_launch"]) if e else None      # bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)
         except Exception:
             return None
@@ -236,6 +239,73 @@ def parity_against_oracle(o, steps, rebuilds_oracle, kw, device):
         out["ok"] = False
     ctx.close()
     return out
+
+
+def parity_nranks(rank, world, local, dist):
+    """untimed, before the timed region of an N > 1 run: a small lattice case (12x8x8 cells, 24576 atoms, 20 steps) stepped by the N
+    ranks (spatial decomposition, NCCL halo, migration) and by the CPU ORACLE on rank 0: same atoms, same rebuild count, positions and
+    forces within tolerance.  (tests/test_gpu_multi.py compares N ranks with 1 rank of the CUDA path; this is the independent checker.)"""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity_util as U
+    from conftest import lj_reduced_kwargs
+    kw = dict(lj_reduced_kwargs(ncell_units=8, cell_units=2), bounds_max=tuple(A_FCC * n for n in (24, 16, 16)), grid_dims=(12, 8, 8))
+    eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
+    steps = 20
+    inp = U.generate_input(kw)
+    ctx = U.make_ctx(kw, rank=rank, nranks=world, device=local, particles=inp)
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.from_numpy(ctx.nccl_unique_id().copy())
+    uid = uid.cuda(); dist.broadcast(uid, 0); ctx.nccl_init_rank(uid.cpu().numpy(), rank, world)
+    ctx.first_iteration(eps, sig, rc)
+    rb = ctx.run_steps(steps, dt, eps, sig, rc)
+    mine = ctx.get_particles(0, ctx.n_inner)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, {k: mine[k] for k in ("id", "rx", "ry", "rz", "fx", "fy", "fz")})
+    ctx.close()
+    out = None
+    if rank == 0:
+        o = U.make_oracle(kw)
+        o.generate(); o.first_iteration()
+        rb_o = o.run(steps)
+        po = U.by_id(o.particles(), o.inner_mask())
+        pg = U.by_id({k: np.concatenate([e[k] for e in everyone]) for k in everyone[0]})
+        out = {"case": "LJ 24x16x16 unit cells, %d atoms, %d steps" % (len(po["id"]), steps), "ranks": world, "atoms_per_rank": [int(len(e["id"])) for e in everyone],
+               "atoms_equal": bool(np.array_equal(po["id"], pg["id"])), "rebuilds": [int(rb), int(rb_o)]}
+        if out["atoms_equal"]:
+            L = np.array(kw["bounds_max"])
+            dr = U.vec(pg, ("rx", "ry", "rz")) - U.vec(po, ("rx", "ry", "rz")); dr -= L * np.round(dr / L)
+            out["max_position_error_over_cell"] = float(np.abs(dr).max() / kw["cell_size"])
+            out["max_force_error"] = float(U.force_error(U.vec(pg, ("fx", "fy", "fz")), U.vec(po, ("fx", "fy", "fz"))))
+            out["ok"] = bool(rb == rb_o and out["max_position_error_over_cell"] < 1e-10 and out["max_force_error"] < 1e-8)
+        else:
+            out["ok"] = False
+        o.close()
+    dist.barrier()
+    return out
+
+
+def weak_base_run(local, steps, warmup):
+    """rank 0 alone, after the timed region of an N > 1 run: the SAME per-GPU workload (C3 block, 100^3 unit cells = 4 M atoms) on ONE GPU
+    (periodic self-images instead of NCCL partners): the like-for-like denominator of the weak-scaling efficiency"""
+    import torch
+    from exanbody_b200 import capi
+    kw, desc = workload("C3", 1)
+    eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity_util as U
+    ctx = U.make_ctx(kw, device=local)
+    sh = torch.cuda.current_stream().cuda_stream
+    ctx.first_iteration(eps, sig, rc, sh)
+    ctx.run_steps(warmup, dt, eps, sig, rc, sh)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(); rb = ctx.run_steps(steps, dt, eps, sig, rc, sh); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    n = ctx.n_inner
+    ctx.close()
+    return {"workload": desc, "atoms": int(n), "steps": steps, "rebuilds": int(rb), "value": n * steps / (ms * 1e-3), "ms_per_step": ms / steps}
 
 
 def short_run(name, device, steps=12, warmup=3):
@@ -317,6 +387,12 @@ def b200_arm(args):
     name = args.workload if args.workload != "auto" else ("C2" if world == 1 else "C3")
     kw, desc = workload(name, world)
     eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
+    par_n = None
+    if world > 1 and not args.no_parity:
+        try:
+            par_n = parity_nranks(rank, world, local, dist)
+        except Exception as ex:
+            par_n = {"ok": False, "error": repr(ex)[:300]}
 
     ctx = capi.Context(local)
     ctx.set_domain((0., 0., 0.), kw["bounds_max"], kw["cell_size"], kw["grid_dims"], (1, 1, 1))
@@ -397,7 +473,7 @@ def b200_arm(args):
     kname = "k_lj_sweep_cl" if si["compiled"] else "k_lj_sweep"
     n_list = si["candidates"] / max(n_atoms_local, 1) if si["compiled"] else None        # list entries per atom (78 on the perfect lattice)
     roofline = {"bound": "hbm", "kernel": kname + " (pair sweep + fused second half kick)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(kname), "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/ncu_traffic.json)",
+                "frac": achieved / peak, "traffic": ncu_traffic(kname, name), "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/ncu_traffic.json)",
                 "algorithmic_bytes_per_launch": force_bytes * n_atoms_local, "peak_source": peak_src,
                 "algorithmic_bytes_per_atom": force_bytes, "stream_bytes_per_atom": S, "kernel_ms": fk_ms,
                 "whole_step": {"algorithmic_bytes_per_atom": step_bytes, "achieved": step_bytes * value / world / 1e9, "frac": step_bytes * value / world / 1e9 / peak},
@@ -469,6 +545,15 @@ def b200_arm(args):
             except Exception as ex:
                 extra[wl] = {"error": repr(ex)[:300]}
 
+    weak_base = None
+    if world > 1 and name == "C3" and not args.no_extra:
+        if rank == 0:
+            try:
+                weak_base = weak_base_run(local, args.steps, args.warmup)
+                weak_base["efficiency_vs_weak_base"] = value / (world * weak_base["value"])
+            except Exception as ex:
+                weak_base = {"error": repr(ex)[:300]}
+        barrier()
     if rank == 0:
         try:
             dfma = capi.measure_dfma_peak(local)
@@ -490,7 +575,7 @@ def b200_arm(args):
             "config": {"workload": desc, "atoms": n_atoms, "rebuilds": rebuilds, "l2": "inputs larger than L2 (state + neighbour streams >> 126 MB), no flush",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "breakdown_ms_per_step": breakdown, "fp64_dfma_peak_tflops": dfma, "parity": parity, "extra_workloads": extra,
+            "breakdown_ms_per_step": breakdown, "fp64_dfma_peak_tflops": dfma, "parity": parity, "extra_workloads": extra, "parity_nranks": par_n, "weak_base": weak_base,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -130,8 +130,9 @@ struct xnb_ctx
   DBuf<double> it_outer;
   DBuf<uint32_t> rc_dst_cell, rc_count, rc_offset;
   DBuf<uint32_t> send_src; DBuf<uint16_t> send_flags;
-  DBuf<double> stage; DBuf<uint8_t> stage_type;
-  std::vector<uint32_t> h_send_base, h_recv_base;      // per partner particle offsets [nranks+1]
+  DBuf<double> stage, rstage; DBuf<uint8_t> stage_type;
+  DBuf<uint32_t> d_ghost_base;                          // device copy of h_send_base | h_recv_base (nranks + 1 entries each)
+  std::vector<uint32_t> h_send_base, h_recv_base, h_ghost_base;      // per partner particle offsets [nranks+1]; both, back to back
   int64_t n_send = 0, n_ghost = 0;
   // ---- neighbours
   DBuf<uint32_t> nb_len, nb_cnt, nb_off, stream_size, stream_size_padded, cell_stream_bytes;
@@ -801,6 +802,13 @@ int xnb_ghost_comm_scheme(xnb_ctx* c, void* stream)
   CK(cudaStreamSynchronize(st));
   for (int p = 0; p <= c->nranks; p++) { c->h_send_base[(size_t)p] = hso[(size_t)c->send_first[(size_t)p]]; c->h_recv_base[(size_t)p] = hro[(size_t)c->recv_first[(size_t)p]]; }
   c->n_send = hso[(size_t)ns]; c->n_ghost = hro[(size_t)nr];
+  {
+    // the pack / unpack kernels find an entry's partner in these (one slab per partner on the wire)
+    CK(c->d_ghost_base.ensure(2 * ((size_t)c->nranks + 1) + 4));
+    c->h_ghost_base.resize(2 * ((size_t)c->nranks + 1));
+    for (int p = 0; p <= c->nranks; p++) { c->h_ghost_base[(size_t)p] = c->h_send_base[(size_t)p]; c->h_ghost_base[(size_t)c->nranks + 1 + p] = c->h_recv_base[(size_t)p]; }
+    CK(cudaMemcpyAsync(c->d_ghost_base.p, c->h_ghost_base.data(), c->h_ghost_base.size() * 4, cudaMemcpyHostToDevice, st));
+  }
   CK(c->send_src.ensure((size_t)c->n_send + 16, 0, 1.2)); CK(c->send_flags.ensure((size_t)c->n_send + 16, 0, 1.2));
   if (ns) LAUNCH(k_ghost_fill, nblk((int64_t)ns * 32, 128), 128, st, g, it, c->cell_start.p, c->cell_count.p, A.rx, A.ry, A.rz, c->it_offset.p, c->send_src.p, c->send_flags.p);
   rc = ensure_particle_capacity(c, (size_t)(c->n_inner + c->n_ghost), (size_t)c->n_inner); if (rc) return rc;
@@ -819,35 +827,33 @@ static int ghost_update(xnb_ctx* c, bool all, cudaStream_t st)
   ParticlesP A = c->P(c->cur);
   const int self_first = (int)c->h_send_base[(size_t)c->rank], self_end = (int)c->h_send_base[(size_t)c->rank + 1];
   const uint32_t self_dst = (uint32_t)(c->n_inner + c->h_recv_base[(size_t)c->rank]);
-  const size_t ns = (size_t)c->n_send;
-  if (c->nranks > 1) { CK(c->stage.ensure(ns * (all ? 10 : 3) + 16, 0, 1.2)); if (all) CK(c->stage_type.ensure(ns + 16, 0, 1.2)); }
+  const size_t ns = (size_t)c->n_send, ng = (size_t)c->n_ghost;
+  const size_t nw = all ? GHOST_WORDS_ALL : GHOST_WORDS_R;          // 8-byte words per ghost on the wire
+  if (c->nranks > 1) { CK(c->stage.ensure(ns * nw + 16, 0, 1.2)); CK(c->rstage.ensure(ng * nw + 16, 0, 1.2)); }
   if (ns)
   {
-    if (all) LAUNCH((k_ghost_pack<true>), nblk((int64_t)ns, 256), 256, st, g, (int)ns, c->send_src.p, c->send_flags.p, A, self_first, self_end, self_dst, c->stage.p, c->stage_type.p);
-    else     LAUNCH((k_ghost_pack<false>), nblk((int64_t)ns, 256), 256, st, g, (int)ns, c->send_src.p, c->send_flags.p, A, self_first, self_end, self_dst, c->stage.p, c->stage_type.p);
+    if (all) LAUNCH((k_ghost_pack<true>), nblk((int64_t)ns, 256), 256, st, g, (int)ns, c->send_src.p, c->send_flags.p, A, self_first, self_end, self_dst, c->d_ghost_base.p, c->nranks, c->stage.p);
+    else     LAUNCH((k_ghost_pack<false>), nblk((int64_t)ns, 256), 256, st, g, (int)ns, c->send_src.p, c->send_flags.p, A, self_first, self_end, self_dst, c->d_ghost_base.p, c->nranks, c->stage.p);
   }
   if (c->nranks > 1)
   {
-    const int nf = all ? 9 : 3;
+    // one message per partner and direction (update_ghosts_comm_manager.h:267-281,390,436)
     NK(g_nccl.GroupStart());
     for (int p = 0; p < c->nranks; p++)
     {
       if (p == c->rank) continue;
       const size_t s0 = c->h_send_base[(size_t)p], sn = c->h_send_base[(size_t)p + 1] - s0;
       const size_t r0 = c->h_recv_base[(size_t)p], rn = c->h_recv_base[(size_t)p + 1] - r0;
-      if (sn)
-      {
-        for (int f = 0; f < nf; f++) NK(g_nccl.Send(c->stage.p + (size_t)f * ns + s0, sn, nccl_float64, p, c->comm, st));
-        if (all) { NK(g_nccl.Send(c->stage.p + (size_t)9 * ns + s0, sn, nccl_uint64, p, c->comm, st)); NK(g_nccl.Send(c->stage_type.p + s0, sn, nccl_uint8, p, c->comm, st)); }
-      }
-      if (rn)
-      {
-        const size_t d0 = (size_t)c->n_inner + r0;
-        for (int f = 0; f < nf; f++) NK(g_nccl.Recv(c->f64[c->cur][f].p + d0, rn, nccl_float64, p, c->comm, st));
-        if (all) { NK(g_nccl.Recv(c->idb[c->cur].p + d0, rn, nccl_uint64, p, c->comm, st)); NK(g_nccl.Recv(c->typeb[c->cur].p + d0, rn, nccl_uint8, p, c->comm, st)); }
-      }
+      if (sn) NK(g_nccl.Send(c->stage.p + nw * s0, nw * sn, nccl_float64, p, c->comm, st));
+      if (rn) NK(g_nccl.Recv(c->rstage.p + nw * r0, nw * rn, nccl_float64, p, c->comm, st));
     }
     NK(g_nccl.GroupEnd());
+    if (ng)
+    {
+      const uint32_t* rb = c->d_ghost_base.p + (size_t)c->nranks + 1;
+      if (all) LAUNCH((k_ghost_unpack<true>), nblk((int64_t)ng, 256), 256, st, (int)ng, (uint32_t)c->n_inner, A, rb, c->nranks, c->rank, c->rstage.p);
+      else     LAUNCH((k_ghost_unpack<false>), nblk((int64_t)ng, 256), 256, st, (int)ng, (uint32_t)c->n_inner, A, rb, c->nranks, c->rank, c->rstage.p);
+    }
   }
   return XNB_OK;
 }

@@ -494,11 +494,23 @@ __global__ void k_ghost_cells_clear(GridP g, uint32_t n_inner, uint32_t* __restr
 
 // pack: ghost g takes particle send_src[g] with the periodic shift applied (update_ghost_functors.h:41-67,172-217).
 // Sends to myself (periodic images, grid_update_ghosts.h:176-187) go straight into the ghost slots [self_dst ...);
-// the others go to the plane-major staging buffer handed to ncclSend.
+// the others go to the staging buffer, ONE CONTIGUOUS SLAB PER PARTNER (one message per partner, as the reference's
+// UpdateGhostsCommManager ships one buffer per partner: update_ghosts_comm_manager.h:63-75,267-281): partner p's send-list
+// entries [s0, s0 + sn) occupy 8-byte words [NW s0, NW (s0 + sn)), field-major inside the slab:
+//   x[sn] y[sn] z[sn]                                     (NW = 3,  ghost_update_r)
+//   x y z vx vy vz fx fy fz id type(one word each)        (NW = 11, ghost_update_all)
+constexpr int GHOST_WORDS_R = 3, GHOST_WORDS_ALL = 11;
+// partner whose range [base[p], base[p+1]) holds entry q (base has nranks + 1 entries)
+XNB_DEVINL int ghost_partner_of(const uint32_t* __restrict__ base, int nranks, uint32_t q)
+{
+  int lo = 0, hi = nranks - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (q >= base[mid]) lo = mid; else hi = mid - 1; }
+  return lo;
+}
 template <bool ALL_FIELDS>
 __global__ void k_ghost_pack(GridP g, int n_send, const uint32_t* __restrict__ send_src, const uint16_t* __restrict__ send_flags,
                              ParticlesP p, int self_first, int self_end, uint32_t self_dst,
-                             double* __restrict__ stage /* planes of n_send doubles: x y z [vx vy vz fx fy fz id] */, uint8_t* __restrict__ stage_type)
+                             const uint32_t* __restrict__ send_base, int nranks, double* __restrict__ stage)
 {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_send) return;
@@ -519,15 +531,40 @@ __global__ void k_ghost_pack(GridP g, int n_send, const uint32_t* __restrict__ s
   }
   else
   {
-    const size_t n = (size_t)n_send;
-    stage[q] = x; stage[n + q] = y; stage[2 * n + q] = z;
+    constexpr size_t NW = ALL_FIELDS ? GHOST_WORDS_ALL : GHOST_WORDS_R;
+    const int pr = ghost_partner_of(send_base, nranks, (uint32_t)q);
+    const size_t s0 = send_base[pr], n = send_base[pr + 1] - s0;
+    double* slab = stage + NW * s0 + ((size_t)q - s0);
+    slab[0] = x; slab[n] = y; slab[2 * n] = z;
     if (ALL_FIELDS)
     {
-      stage[3 * n + q] = p.vx[s]; stage[4 * n + q] = p.vy[s]; stage[5 * n + q] = p.vz[s];
-      stage[6 * n + q] = p.fx[s]; stage[7 * n + q] = p.fy[s]; stage[8 * n + q] = p.fz[s];
-      reinterpret_cast<unsigned long long*>(stage)[9 * n + q] = p.id[s];
-      stage_type[q] = p.type[s];
+      slab[3 * n] = p.vx[s]; slab[4 * n] = p.vy[s]; slab[5 * n] = p.vz[s];
+      slab[6 * n] = p.fx[s]; slab[7 * n] = p.fy[s]; slab[8 * n] = p.fz[s];
+      reinterpret_cast<unsigned long long*>(slab)[9 * n] = p.id[s];
+      reinterpret_cast<unsigned long long*>(slab)[10 * n] = (unsigned long long)p.type[s];
     }
+  }
+}
+// unpack (GhostReceiveUnpackFunctor, update_ghost_functors.h:369-452): ghost i of partner p's slab -> ghost slot n_inner + i
+template <bool ALL_FIELDS>
+__global__ void k_ghost_unpack(int n_ghost, uint32_t n_inner, ParticlesP p, const uint32_t* __restrict__ recv_base, int nranks, int self_rank,
+                               const double* __restrict__ rstage)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ghost) return;
+  const int pr = ghost_partner_of(recv_base, nranks, (uint32_t)i);
+  if (pr == self_rank) return;                       // my own periodic images were written in place by the pack kernel
+  constexpr size_t NW = ALL_FIELDS ? GHOST_WORDS_ALL : GHOST_WORDS_R;
+  const size_t r0 = recv_base[pr], n = recv_base[pr + 1] - r0;
+  const double* slab = rstage + NW * r0 + ((size_t)i - r0);
+  const uint32_t d = n_inner + (uint32_t)i;
+  p.rx[d] = slab[0]; p.ry[d] = slab[n]; p.rz[d] = slab[2 * n];
+  if (ALL_FIELDS)
+  {
+    p.vx[d] = slab[3 * n]; p.vy[d] = slab[4 * n]; p.vz[d] = slab[5 * n];
+    p.fx[d] = slab[6 * n]; p.fy[d] = slab[7 * n]; p.fz[d] = slab[8 * n];
+    p.id[d] = reinterpret_cast<const unsigned long long*>(slab)[9 * n];
+    p.type[d] = (uint8_t)reinterpret_cast<const unsigned long long*>(slab)[10 * n];
   }
 }
 
