@@ -545,6 +545,22 @@ def b200_arm(args):
             except Exception as ex:
                 extra[wl] = {"error": repr(ex)[:300]}
 
+    # ---- dynamic re-partition, on request: load_balance_rcb on the live contexts, then the same K steps again
+    lbal = None
+    if world > 1 and args.load_balance:
+        atoms_before = [None] * world
+        dist.all_gather_object(atoms_before, int(ctx.n_inner))
+        b, a = ctx.load_balance_rcb(stream=sh)
+        ctx.update_particles_full(sh)
+        ctx.run_steps(args.warmup, dt, eps, sig, rc, sh)
+        barrier()
+        e0.record(stream); rb2 = ctx.run_steps(args.steps, dt, eps, sig, rc, sh); e1.record(stream)
+        barrier()
+        ms2 = max_over_ranks(e0.elapsed_time(e1))
+        atoms_after = [None] * world
+        dist.all_gather_object(atoms_after, int(ctx.n_inner))
+        lbal = {"lb_inbalance": [b, a], "ms_per_step_before": ms / args.steps, "ms_per_step_after": ms2 / args.steps, "rebuilds_after": int(rb2),
+                "atoms_per_rank_before": atoms_before, "atoms_per_rank_after": atoms_after, "value_after": sum(atoms_after) * args.steps / (ms2 * 1e-3)}
     weak_base = None
     if world > 1 and name == "C3" and not args.no_extra:
         if rank == 0:
@@ -575,7 +591,7 @@ def b200_arm(args):
             "config": {"workload": desc, "atoms": n_atoms, "rebuilds": rebuilds, "l2": "inputs larger than L2 (state + neighbour streams >> 126 MB), no flush",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "breakdown_ms_per_step": breakdown, "fp64_dfma_peak_tflops": dfma, "parity": parity, "extra_workloads": extra, "parity_nranks": par_n, "weak_base": weak_base,
+            "breakdown_ms_per_step": breakdown, "fp64_dfma_peak_tflops": dfma, "parity": parity, "extra_workloads": extra, "parity_nranks": par_n, "weak_base": weak_base, "load_balance": lbal,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -594,6 +610,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed comparison of the CUDA path with the CPU oracle on the benchmark input")
+    ap.add_argument("--load-balance", action="store_true", help="N > 1: after the timed region re-partition with load_balance_rcb and time the same steps again")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE workloads (C1, C4, C5)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -18,7 +18,7 @@ SYMBOLS = [
     "xnb_set_type_mass", "xnb_set_sub_grid_density", "xnb_set_nccl_comm", "xnb_nccl_unique_id", "xnb_nccl_init_rank",
     "xnb_set_particles", "xnb_num_inner", "xnb_num_total", "xnb_get_particles", "xnb_upload_rv", "xnb_download_rvf",
     "xnb_get_grid_info", "xnb_get_sweep_info", "xnb_get_cells", "xnb_view_particles", "xnb_device_allocations", "xnb_move_particles", "xnb_rebuild_amr", "xnb_backup_r", "xnb_ghost_comm_scheme",
-    "xnb_ghost_update_all", "xnb_ghost_update_r", "xnb_chunk_neighbors", "xnb_zero_particle_force", "xnb_set_pair_functor", "xnb_lennard_jones_force", "xnb_gravitational_force",
+    "xnb_ghost_update_all", "xnb_ghost_update_r", "xnb_chunk_neighbors", "xnb_zero_particle_force", "xnb_set_pair_functor", "xnb_lennard_jones_force", "xnb_gravitational_force", "xnb_load_balance_rcb", "xnb_get_block",
     "xnb_divide_force_by_mass", "xnb_set_chunk_neighbors_config", "xnb_lennard_jones_force_symmetric", "xnb_update_force_from_ghost", "xnb_push_f_v_r", "xnb_push_f_v", "xnb_particle_displ_over", "xnb_verlet_first_half",
     "xnb_read_displ_over", "xnb_force_and_second_half", "xnb_run_steps", "xnb_step_host", "xnb_first_iteration", "xnb_energy_virial",
     "xnb_view_chunk_neighbors", "xnb_stream_pool_u16", "xnb_get_streams", "xnb_get_amr", "xnb_get_backup",
@@ -83,7 +83,7 @@ def load():
         "xnb_view_particles": (I, [P, C.POINTER(XnbParticleView)]), "xnb_device_allocations": (I64, []),
         "xnb_move_particles": (I, [P, P]), "xnb_rebuild_amr": (I, [P, P]), "xnb_backup_r": (I, [P, P]), "xnb_ghost_comm_scheme": (I, [P, P]),
         "xnb_ghost_update_all": (I, [P, P]), "xnb_ghost_update_r": (I, [P, P]), "xnb_chunk_neighbors": (I, [P, P]),
-        "xnb_zero_particle_force": (I, [P, I, P]), "xnb_set_pair_functor": (I, [P, I]), "xnb_lennard_jones_force": (I, [P, D, D, D, I, P]), "xnb_gravitational_force": (I, [P, D, D, I, I, P]), "xnb_divide_force_by_mass": (I, [P, P]),
+        "xnb_zero_particle_force": (I, [P, I, P]), "xnb_set_pair_functor": (I, [P, I]), "xnb_lennard_jones_force": (I, [P, D, D, D, I, P]), "xnb_gravitational_force": (I, [P, D, D, I, I, P]), "xnb_load_balance_rcb": (I, [P, P, P, P, P]), "xnb_get_block": (I, [P, I, P, P]), "xnb_divide_force_by_mass": (I, [P, P]),
         "xnb_set_chunk_neighbors_config": (I, [P, I, I]), "xnb_lennard_jones_force_symmetric": (I, [P, D, D, D, P]), "xnb_update_force_from_ghost": (I, [P, P]),
         "xnb_push_f_v_r": (I, [P, D, D, P]), "xnb_push_f_v": (I, [P, D, D, P]), "xnb_particle_displ_over": (I, [P, P, P]),
         "xnb_verlet_first_half": (I, [P, D, P]), "xnb_read_displ_over": (I, [P, P, P]), "xnb_force_and_second_half": (I, [P, D, D, D, D, P]),
@@ -286,6 +286,18 @@ class Context:
     def update_particles_full(self, stream=None):
         """parallel_update_particles of data/config/update-particles.msp:47-53 (after move_particles)"""
         self.rebuild_amr(stream); self.backup_r(stream); self.ghost_comm_scheme(stream); self.ghost_update_all(stream); self.chunk_neighbors(stream)
+
+    def load_balance_rcb(self, coefs=None, stream=None):
+        """op load_balance_rcb on the live context (collective): returns (lb_inbalance before, after); continue with update_particles_full()"""
+        b = C.c_double(); a = C.c_double()
+        k = None if coefs is None else np.ascontiguousarray(coefs, np.float64)
+        self._ck(self.L.xnb_load_balance_rcb(self.h, _p(k), C.addressof(b), C.addressof(a), _p(stream)))
+        return b.value, a.value
+
+    def block(self, rank):
+        s = np.zeros(3, np.int64); e = np.zeros(3, np.int64)
+        self._ck(self.L.xnb_get_block(self.h, int(rank), _p(s), _p(e)))
+        return s, e
 
     def energy_virial(self, epsilon, sigma, rcut, stream=None):
         e = C.c_double(); k = C.c_double(); w = np.zeros(6)

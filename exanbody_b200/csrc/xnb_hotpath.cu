@@ -130,7 +130,7 @@ struct xnb_ctx
   DBuf<double> it_outer;
   DBuf<uint32_t> rc_dst_cell, rc_count, rc_offset;
   DBuf<uint32_t> send_src; DBuf<uint16_t> send_flags;
-  DBuf<double> stage, rstage; DBuf<uint8_t> stage_type;
+  DBuf<double> stage, rstage, lb_costs; DBuf<uint8_t> stage_type;
   DBuf<uint32_t> d_ghost_base;                          // device copy of h_send_base | h_recv_base (nranks + 1 entries each)
   std::vector<uint32_t> h_send_base, h_recv_base, h_ghost_base;      // per partner particle offsets [nranks+1]; both, back to back
   int64_t n_send = 0, n_ghost = 0;
@@ -710,6 +710,69 @@ int xnb_move_particles(xnb_ctx* c, void* stream)
   c->n_inner = n_new; c->n_total = n_new; c->n_ghost = 0; c->have_nbh = false; c->amr_current = false;
   LAUNCH(k_ghost_cells_clear, nblk(g.n_cells, 256), 256, st, g, (uint32_t)n_new, c->cell_start.p, c->cell_count.p);
   return check_device_errors(c, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// op `load_balance_rcb` on a live context (src/mpi/load_balance_rcb.cpp:51-601 without Zoltan, cost model simple_cost_model.h:67-146,
+// followed by migrate_cell_particles.cpp:101-143): per-cell costs on the device -> sum over the ranks -> cost-weighted recursive
+// bisection (every rank computes the same table) -> the new block replaces the old one and xnb_move_particles' migration hand-off
+// carries every particle to its new owner.  Collective.  The caller continues with the rebuild chain (rebuild_amr ... chunk_neighbors).
+// ---------------------------------------------------------------------------------------------------------------------
+int xnb_load_balance_rcb(xnb_ctx* c, const double coefs[4], double* inbalance_before, double* inbalance_after, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_grid(c); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  static const double default_coefs[4] = {0.0, 0.0, 1.0, 0.0};
+  const double* k = coefs ? coefs : default_coefs;
+  const size_t nd = (size_t)c->ddims[0] * (size_t)c->ddims[1] * (size_t)c->ddims[2];
+  CK(c->lb_costs.ensure(nd + 8));
+  CK(cudaMemsetAsync(c->lb_costs.p, 0, nd * 8, st));
+  LAUNCH(k_cell_costs, nblk(c->g.n_cells, 256), 256, st, c->g, c->cell_count.p, k[0], k[1], k[2], k[3], c->lb_costs.p);
+  if (c->nranks > 1)
+  {
+    if (!c->comm) return c->fail(XNB_ERR_NCCL, "nranks > 1 needs an NCCL communicator");
+    NK(g_nccl.AllReduce(c->lb_costs.p, c->lb_costs.p, nd, nccl_float64, nccl_sum, c->comm, st));       // MPI_Allreduce(SUM), load_balance_rcb.cpp:270
+  }
+  std::vector<double> costs(nd);
+  CK(cudaMemcpyAsync(costs.data(), c->lb_costs.p, nd * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  auto block_cost = [&](const Block& b) {
+    double s = 0.0;
+    for (int64_t kk = b.s[2]; kk < b.e[2]; kk++) for (int64_t jj = b.s[1]; jj < b.e[1]; jj++) for (int64_t ii = b.s[0]; ii < b.e[0]; ii++)
+      s += costs[(size_t)((kk * c->ddims[1] + jj) * c->ddims[0] + ii)];
+    return s;
+  };
+  auto inbalance = [&](const std::vector<Block>& bl) {        // lb_inbalance = (max - avg) / avg (load_balance_rcb.cpp:443-452)
+    double mx = 0.0, sum = 0.0;
+    for (const Block& b : bl) { const double v = block_cost(b); mx = std::max(mx, v); sum += v; }
+    const double avg = sum / (double)bl.size();
+    return avg > 0.0 ? (mx - avg) / avg : 0.0;
+  };
+  std::vector<Block> nb((size_t)c->nranks);
+  for (int r = 0; r < c->nranks; r++)
+  {
+    nb[(size_t)r] = load_balance_rcb(c->ddims, costs.data(), (size_t)c->nranks, (size_t)r);
+    for (int d = 0; d < 3; d++) if (nb[(size_t)r].e[d] <= nb[(size_t)r].s[d]) return c->fail(XNB_ERR_INVALID, "load_balance_rcb: Assigned grid block is empty");      // :457
+  }
+  if (inbalance_before) *inbalance_before = inbalance(c->blocks);
+  if (inbalance_after) *inbalance_after = inbalance(nb);
+  bool same = true;
+  for (int r = 0; r < c->nranks; r++) for (int d = 0; d < 3; d++) same = same && nb[(size_t)r].s[d] == c->blocks[(size_t)r].s[d] && nb[(size_t)r].e[d] == c->blocks[(size_t)r].e[d];
+  if (same) return XNB_OK;
+  // the new decomposition: grid geometry, ghost items and the migration table are rebuilt; lists and tile shapes of the old grid are void
+  c->blocks = nb; c->grid_ready = false;
+  c->n_total = c->n_inner; c->n_ghost = 0; c->n_send = 0;
+  c->have_nbh = false; c->cl.valid = false; c->nb_ghost.have = false; c->ghost_lists = false; c->amr_current = false; c->nbh_slot_words = 0;
+  return xnb_move_particles(c, stream);
+}
+
+int xnb_get_block(const xnb_ctx* c, int rank, int64_t start[3], int64_t end[3])
+{
+  if (!c || !c->have_block || rank < 0 || rank >= c->nranks) return XNB_ERR_INVALID;
+  for (int d = 0; d < 3; d++) { start[d] = c->blocks[(size_t)rank].s[d]; end[d] = c->blocks[(size_t)rank].e[d]; }
+  return XNB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -1219,4 +1219,20 @@ __global__ void k_migrate_pack(int n_leave, const uint32_t* __restrict__ leave_l
   stage_type[k] = p.type[i];
 }
 
+// simple_cost_model (src/mpi/include/exanb/mpi/simple_cost_model.h:67-146) on the device: cost of every INNER cell of this rank's block
+// from its particle count, p = N / cell volume, cost = p d1 + p^2 d2 + p^3 d3 + c (ghost cells carry no cost, :103), written into the
+// cost array of the whole domain grid at the cell's domain index (the array all ranks then sum: load_balance_rcb.cpp:270)
+__global__ void k_cell_costs(GridP g, const uint32_t* __restrict__ cell_count, double d3, double d2, double d1, double cc, double* __restrict__ domain_costs)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.n_cells) return;
+  const int i = c % g.dims[0], j = (c / g.dims[0]) % g.dims[1], k = c / (g.dims[0] * g.dims[1]);
+  if (i < g.gl || i >= g.dims[0] - g.gl || j < g.gl || j >= g.dims[1] - g.gl || k < g.gl || k >= g.dims[2] - g.gl) return;
+  const double cell_volume = __dmul_rn(__dmul_rn(g.cs, g.cs), g.cs);
+  const double pvol = __ddiv_rn((double)cell_count[c], cell_volume);
+  const double cost = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(pvol, d1), __dmul_rn(__dmul_rn(pvol, pvol), d2)), __dmul_rn(__dmul_rn(__dmul_rn(pvol, pvol), pvol), d3)), cc);
+  const size_t di = (size_t)(g.off[0] + i), dj = (size_t)(g.off[1] + j), dk = (size_t)(g.off[2] + k);
+  domain_costs[(dk * (size_t)g.ddims[1] + dj) * (size_t)g.ddims[0] + di] = cost;
+}
+
 } // namespace xnb

@@ -416,6 +416,19 @@ struct GravitationalForce : OperatorNode    // contribs/pi/gravitational_force.c
     ck(grid->ctx, xnb_gravitational_force(grid->ctx, config->G, *rcut, *ghost ? 1 : 0, *compute_buffer ? 1 : 0, stream), "gravitational_force");
   }
 };
+// dynamic re-partition: cost model + cost-weighted RCB + migration in one collective call
+struct LoadBalanceRCB : OperatorNode        // mpi/load_balance_rcb.cpp:51-601 (+ simple_cost_model.h, migrate_cell_particles.cpp:101-143)
+{
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT);
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  ADD_SLOT(double, lb_inbalance, INPUT_OUTPUT, 0.0, DocString{"(max - avg) / avg of the block costs after the re-partition"});
+  void execute() override
+  {
+    double before = 0.0, after = 0.0;
+    ck(grid->ctx, xnb_load_balance_rcb(grid->ctx, nullptr, &before, &after, stream), "load_balance_rcb");
+    *lb_inbalance = after;
+  }
+};
 struct UpdateForceFromGhost : OperatorNode  // mpi/update_force_from_ghost.cu:44 (UpdateFromGhosts<fx,fy,fz, UpdateValueAdd>)
 {
   ADD_SLOT(Grid, grid, INPUT_OUTPUT);
@@ -568,6 +581,7 @@ void register_hot_path_operators()
   f->register_factory("resize_particle_locks", make_simple_operator<Nop>());     // ComputePairOptionalLocks<false>: LJ takes no locks
   f->register_factory("zero_particle_force", make_simple_operator<ZeroParticleForce>());
   f->register_factory("lennard_jones_force", make_simple_operator<LennardJonesForce<false>>());
+  f->register_factory("load_balance_rcb", make_simple_operator<LoadBalanceRCB>());
   f->register_factory("gravitational_force", make_simple_operator<GravitationalForce>());
   f->register_factory("lennard_jones_force_symmetric", make_simple_operator<LennardJonesForce<true>>());
   f->register_factory("update_force_from_ghost", make_simple_operator<UpdateForceFromGhost>());   // adds zeros after a full-list sweep (ghost forces are 0 then)

@@ -275,9 +275,19 @@ int xnb_host_simple_cost_model(int64_t n_cells, const uint32_t* cell_count, doub
    rank 1): cost-weighted recursive bisection of the domain cell grid.  cell_costs = the all-reduced cost of every domain
    cell, index (k*dj + j)*di + i (CellCosts, e.g. simple_cost_model).  Every rank calls it with the same costs and obtains
    its own block; *block_cost (may be NULL) = the cost inside it, from which lb_inbalance = (max - avg)/avg follows.
-   Applying a new block to a live xnb_ctx (re-partition + migration) is not implemented yet.                          */
+   xnb_load_balance_rcb (below) applies the result to a live xnb_ctx.                                               */
 int xnb_host_load_balance_rcb(const int64_t grid_dims[3], const double* cell_costs, int nranks, int rank,
                               int64_t start[3], int64_t end[3], double* block_cost);
+/* op `load_balance_rcb` on a live context, COLLECTIVE (src/mpi/load_balance_rcb.cpp:51-601 without Zoltan + simple_cost_model.h:67-146
+   + migrate_cell_particles.cpp:101-143): per-cell costs on the device from the current cell counts
+   (coefs as xnb_host_simple_cost_model, NULL = the reference's defaults {0,0,1,0}), summed over the ranks (ncclAllReduce),
+   cost-weighted recursive bisection (every rank derives the same table), then the new block replaces the old one and the
+   migration hand-off of xnb_move_particles carries every particle to its new owner (any rank).  lb_inbalance = (max - avg)/avg
+   of the block costs before / after (either may be NULL).  SYNCHRONISES the host.  Continue with the rebuild chain
+   (xnb_rebuild_amr ... xnb_chunk_neighbors); forces and velocities travel with the particles.                        */
+int xnb_load_balance_rcb(xnb_ctx*, const double coefs[4], double* lb_inbalance_before, double* lb_inbalance_after, void* stream);
+/* GridBlock [start, end) of `rank` in domain cells (this rank's own table: identical on every rank) */
+int xnb_get_block(const xnb_ctx*, int rank, int64_t start[3], int64_t end[3]);
 /* src/mpi/update_ghosts_comm_scheme.cpp:168-196,429-443: the cells rank `from` sends to rank `to` (sender local cell,
    receiver local ghost cell, GhostBoundaryModifier flags, ghosts_comm_scheme.h:46-81), in the reference's order.
    Returns the item count (arrays are filled when capacity suffices); -1 on invalid arguments.                     */

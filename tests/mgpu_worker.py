@@ -44,6 +44,18 @@ def main():
         eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
         ctx.first_iteration(eps, sig, rc)
         rb = ctx.run_steps(nsteps, dt, eps, sig, rc)
+        lb = None
+        if name == "lj_voids":
+            # load_balance_rcb on the live contexts (device cost model -> all-reduce -> cost-weighted RCB -> new blocks
+            # -> migration to the new owners), then the rebuild chain, then more steps.  Clusters + voids: the static blocks are badly
+            # balanced on purpose.  The single-rank reference below performs the same rebuild at the same step.
+            n_before = ctx.n_inner
+            lb = ctx.load_balance_rcb()
+            ctx.update_particles_full()
+            blocks = [tuple(map(tuple, ctx.block(r))) for r in range(world)]
+            counts = [None] * world
+            dist.all_gather_object(counts, (int(n_before), int(ctx.n_inner)))
+            rb += ctx.run_steps(nsteps // 2, dt, eps, sig, rc)
         if name.endswith("_overlap"):
             si = ctx.sweep_info()
             assert si["compiled"] and si["interior_tiles"] > 0 and si["boundary_tiles"] > 0, si
@@ -63,6 +75,14 @@ def main():
             ref = U.make_ctx(kw, device=local, particles=inp)
             ref.first_iteration(eps, sig, rc)
             rb_ref = ref.run_steps(nsteps, dt, eps, sig, rc)
+            if lb is not None:
+                ref.move_particles(); ref.update_particles_full()
+                rb_ref += ref.run_steps(nsteps // 2, dt, eps, sig, rc)
+                nb = [c[0] for c in counts]; na = [c[1] for c in counts]
+                imb = lambda v: (max(v) - sum(v) / len(v)) / (sum(v) / len(v))
+                assert sum(nb) == sum(na), "load_balance_rcb lost atoms: %s -> %s" % (nb, na)
+                assert lb[1] <= lb[0] + 1e-12 and imb(na) <= imb(nb) + 1e-12, (lb, nb, na)
+                print("load_balance_rcb: lb_inbalance %.3f -> %.3f, atoms per rank %s -> %s, blocks %s" % (lb[0], lb[1], nb, na, blocks), flush=True)
             pr = U.by_id(ref.get_particles(0, ref.n_inner))
             allp = U.by_id({k: np.concatenate([e[k] for e in everyone]) for k in everyone[0]})
             assert np.array_equal(allp["id"], pr["id"]), "%s: atoms lost or duplicated across ranks" % name
