@@ -4,6 +4,7 @@
 #include "xnb_kernels.cuh"
 #include "xnb_sweep_cl.cuh"
 #include "xnb_nbh_bits.cuh"
+#include "xnb_nbh_big.cuh"
 #include "xnb_pair_generic.cuh"
 #include "xnb_host_decomp.hpp"
 
@@ -147,7 +148,8 @@ struct xnb_ctx
   DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0; DBuf<uint32_t> cl_tile_list;
   // ---- k_nbh_bits (xnb_nbh_bits.cuh): masks parked between its two phases, capacities that worked last time, lazily built ghost-cell lists
   int nb_cap_l = 0, nb_cap_trips = 0; bool ghost_lists = false;       // ghost_lists: the streams of the ghost cells are current
-  struct NbGhostCfg { ClTileP tp{}; int cap_l = 0; bool have = false; } nb_ghost;
+  int nb_cap32 = 0;
+  struct NbGhostCfg { ClTileP tp{}; int cap_l = 0, cap32 = 0; bool have = false; } nb_ghost;
   cudaStream_t st_comm = nullptr; cudaEvent_t ev_pos = nullptr, ev_ghost = nullptr;      // halo exchange overlapped with the interior tiles
   int64_t n_nonempty_inner = 0;
   int64_t pool_used = 0; uint32_t max_neighbors = 0, max_cell_count = 0, max_stream = 0; double avg_stream = 0; bool have_nbh = false;
@@ -1034,6 +1036,109 @@ static int cl_finish(xnb_ctx* c, const ClTileP& tp, bool ghost, unsigned blocks,
 // (xnb_view_chunk_neighbors / xnb_get_streams / a sweep with ghost = true).  *done = false: no tile shape fits shared memory
 // (large cells) and the caller falls back to the per-particle two-pass kernels.
 // ---------------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------------
+// the same for LARGE cells (more than 32 * NBH_CELL_BLOCKS particles): k_nbh_big, one block per cell, sub-cell pruning through the
+// bounding boxes of 32-particle blocks, two passes (count / fill) instead of lists in shared memory
+// ---------------------------------------------------------------------------------------------------------------------
+static int nbh_big_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
+{
+  *done = false;
+  const GridP& g = c->g;
+  const int gap = (int)std::ceil(c->nbh_dist / c->cs);
+  const int n1 = 2 * gap + 1;
+  if (n1 * n1 * n1 > 125 || env_flag("XNB_NBH_NO_BIG")) return XNB_OK;
+  int lo[3], hi[3];
+  for (int d = 0; d < 3; d++) { lo[d] = mode == 0 ? g.gl : 0; hi[d] = mode == 0 ? g.dims[d] - g.gl : g.dims[d]; }
+  if (mode == 1 && g.gl == 0) { *done = true; return XNB_OK; }
+  ParticlesP A = c->P(c->cur);
+  const uint32_t mcc = std::max<uint32_t>(c->max_cell_count, 1);
+  if (c->nbh_slot_words == 0)
+  {
+    const double frac = std::min(1.0, 4.19 * c->nbh_dist * c->nbh_dist * c->nbh_dist / std::pow((2.0 * gap + 1.0) * c->cs, 3.0));
+    const double per = 1.0 + 2.0 * std::pow(2.0 * gap + 1.0, 3.0) * 0.6 + frac * std::pow(2.0 * gap + 1.0, 3.0) * (double)mcc * 1.3;
+    c->nbh_slot_words = (uint32_t)((size_t)(2 * (mcc + 1) + (double)mcc * per + 64 + 7) & ~(size_t)7);
+  }
+  // the sweep's tile for such cells: one cell
+  ClCand k{};
+  bool have = false;
+  for (const ClCand& q : cl_tile_candidates(c, lo, hi, gap)) if (q.t[0] == 1 && q.t[1] == 1 && q.t[2] == 1) { k = q; have = true; break; }
+  if (!have) return XNB_OK;
+  static bool attr_done_dev[XNB_MAX_DEVICES] = {};
+  if (!attr_done_dev[c->device % XNB_MAX_DEVICES])
+  {
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_nbh_big));
+    CK(cudaFuncSetAttribute(k_nbh_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
+    attr_done_dev[c->device % XNB_MAX_DEVICES] = true;
+  }
+  uint32_t* counters = c->d_scalars32.p + 64;
+  unsigned long long* totals = c->d_scalars64.p + 4;
+  ClTileP tp{};
+  cl_tile_grid(tp, k, lo, hi, gap);
+  const ClTileP& prev = mode == 0 ? c->cl.tp : c->nb_ghost.tp;
+  const bool have_prev = mode == 0 ? (c->cl.valid && !c->cl.ghost) : c->nb_ghost.have;
+  if (have_prev && prev.ti == 1 && prev.tj == 1 && prev.tk == 1) { tp.gmax = std::max(tp.gmax, prev.gmax); tp.cap = std::max(tp.cap, prev.cap); }
+  tp.gmax = std::max(tp.gmax, (int)((mcc + 31u) / 32u));
+  int& cap32 = mode == 0 ? c->nb_cap32 : c->nb_ghost.cap32;
+  // staged candidates of ONE plane of halo cells, every cell padded to a multiple of 32
+  if (cap32 == 0) cap32 = (int)std::min<double>((double)(n1 * n1) * (double)((mcc + 31u) & ~31u), (double)tp.cap / n1 * 1.10 + 32.0 * n1 * n1 + 31.0) & ~31;
+  const unsigned blocks = (unsigned)((int64_t)tp.tiles_i * tp.tiles_j * tp.tiles_k);
+  for (int attempt = 0; attempt < 6; attempt++)
+  {
+    if (tp.cap > 8191 || tp.gmax > NBH_BIG_MAX_THREADS / 32) return XNB_OK;          // one warp per group of the cell
+    const int nwarp = std::max(tp.gmax, 2);
+    const size_t smem = nbig_smem_bytes(tp.nh_max, tp.tc_max, tp.gmax, cap32, n1 * n1 * n1, nwarp);
+    if (smem + 2048 > XNB_SM_BYTES) return XNB_OK;
+    if ((size_t)g.n_cells * c->nbh_slot_words > ((size_t)24 << 30)) return XNB_OK;
+    CK(c->pool.ensure((size_t)g.n_cells * c->nbh_slot_words + 64));
+    if (mode == 0)
+    {
+      if (c->nb_cap_trips == 0) c->nb_cap_trips = c->max_neighbors ? (int)(c->max_neighbors / 4 + 8) : (int)(c->nbh_slot_words / mcc / 4 + 8);
+      CK(c->cl_rows.ensure((size_t)blocks * tp.gmax * c->nb_cap_trips * 128 + 64, 0, 1.05));
+      CK(c->cl_groups.ensure((size_t)blocks * tp.gmax + 16));
+    }
+    CK(cudaMemsetAsync(counters, 0, NB_U32_COUNT * 4, st)); CK(cudaMemsetAsync(totals, 0, 3 * 8, st));
+    NbhBitsP bp{};
+    bp.emit_rows = mode == 0 ? 1 : 0; bp.sel_mode = mode; bp.slot_words = (int)c->nbh_slot_words; bp.cap_trips = c->nb_cap_trips; bp.max_dist2 = c->nbh_dist * c->nbh_dist;
+    NbhBitsOut o{c->pool.p, c->cell_stream.p, c->stream_size.p, c->cell_stream_bytes.p, c->stream_off.p, c->cl_groups.p, reinterpret_cast<uint2*>(c->cl_rows.p), counters, totals};
+    if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh_big mode %d cap %d cap32 %d gmax %d trips %d slot_words %u smem %zu blocks %u (max cell %u)\n", mode, tp.cap, cap32, tp.gmax, c->nb_cap_trips, c->nbh_slot_words, smem, blocks, mcc);
+    k_nbh_big<<<blocks, 32 * nwarp, smem, st>>>(g, tp, bp, cap32, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
+    c->launches++; CK(cudaGetLastError());
+    uint32_t h[NB_U32_COUNT]; unsigned long long tot[3];
+    {
+      char* hp = static_cast<char*>(c->h_pinned);
+      CK(cudaMemcpyAsync(hp, counters, NB_U32_COUNT * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(hp + 64, totals, 3 * 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      memcpy(h, hp, NB_U32_COUNT * 4); memcpy(tot, hp + 64, 24);
+    }
+    bool again = false;
+    if ((int)h[NB_GMAX] > tp.gmax) { tp.gmax = (int)h[NB_GMAX]; again = true; }
+    if ((int)h[NB_CAP] > tp.cap) { tp.cap = ((int)h[NB_CAP] + 1) & ~1; again = true; }
+    if ((int)h[NB_SLOTS] > cap32) { cap32 = ((int)h[NB_SLOTS] + 31) & ~31; again = true; }
+    if (h[NB_SLOT_WORDS] > c->nbh_slot_words) { c->nbh_slot_words = (uint32_t)(((size_t)(h[NB_SLOT_WORDS] * 1.12) + 64 + 7) & ~(size_t)7); again = true; }
+    if (mode == 0 && (int)h[NB_TRIPS] > c->nb_cap_trips) { c->nb_cap_trips = (int)h[NB_TRIPS] + 6; again = true; }
+    if (h[NB_OVERFLOW] & 4u) return XNB_OK;
+    if (again || h[NB_OVERFLOW]) { if (!again) return c->fail(XNB_ERR_CAPACITY, "chunk_neighbors: large-cell build reported an overflow it cannot size"); continue; }
+    if (mode == 0)
+    {
+      c->pool_used = (int64_t)tot[1]; c->max_neighbors = h[NB_MAX_NBH]; c->n_nonempty_inner = h[NB_NONEMPTY]; c->max_stream = h[NB_MAX_STREAM];
+      c->avg_stream = c->n_inner ? (double)tot[2] / (double)c->n_inner : 0.0;
+      c->have_nbh = true; c->ghost_lists = g.gl == 0;
+      c->nb_cap_trips = std::min(c->nb_cap_trips, (int)h[NB_TRIPS] + 8);
+      int rc = cl_finish(c, tp, false, blocks, h[NB_ROWS], (int64_t)tot[0], h[NB_GMAX], st); if (rc) return rc;
+    }
+    else
+    {
+      c->pool_used += (int64_t)tot[1]; c->max_neighbors = std::max(c->max_neighbors, h[NB_MAX_NBH]); c->max_stream = std::max(c->max_stream, h[NB_MAX_STREAM]);
+      c->nb_ghost.tp = tp; c->nb_ghost.have = true;
+      c->ghost_lists = true;
+    }
+    *done = true;
+    return XNB_OK;
+  }
+  return c->fail(XNB_ERR_CAPACITY, "chunk_neighbors: large-cell build did not converge");
+}
+
 static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
 {
   *done = false;
@@ -1054,7 +1159,7 @@ static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
   std::vector<ClCand> cands = cl_tile_candidates(c, lo, hi, gap);
   const int n1 = 2 * gap + 1;
   const bool u8 = mcc <= 255 && n1 * n1 * n1 <= 128 && !env_flag("XNB_NBH_U16");      // byte list areas
-  if (mcc + 3u > 32u * NBH_CELL_BLOCKS && !env_flag("XNB_NBH_FORCE_BITS")) return XNB_OK;   // a neighbour cell would need more accept masks than the kernel keeps in registers
+  if (mcc + 3u > 32u * NBH_CELL_BLOCKS && !env_flag("XNB_NBH_FORCE_BITS")) return nbh_big_run(c, mode, st, done);   // a neighbour cell would need more accept masks than k_nbh_bits keeps in registers
   static bool attr_done_dev[XNB_MAX_DEVICES] = {};
   if (!attr_done_dev[c->device % XNB_MAX_DEVICES])
   {
