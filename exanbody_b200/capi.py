@@ -18,7 +18,7 @@ SYMBOLS = [
     "xnb_set_type_mass", "xnb_set_sub_grid_density", "xnb_set_nccl_comm", "xnb_nccl_unique_id", "xnb_nccl_init_rank",
     "xnb_set_particles", "xnb_num_inner", "xnb_num_total", "xnb_get_particles", "xnb_upload_rv", "xnb_download_rvf",
     "xnb_get_grid_info", "xnb_get_sweep_info", "xnb_get_cells", "xnb_view_particles", "xnb_device_allocations", "xnb_move_particles", "xnb_rebuild_amr", "xnb_backup_r", "xnb_ghost_comm_scheme",
-    "xnb_ghost_update_all", "xnb_ghost_update_r", "xnb_chunk_neighbors", "xnb_zero_particle_force", "xnb_set_pair_functor", "xnb_lennard_jones_force", "xnb_gravitational_force", "xnb_load_balance_rcb", "xnb_get_block",
+    "xnb_ghost_update_all", "xnb_ghost_update_r", "xnb_chunk_neighbors", "xnb_zero_particle_force", "xnb_set_pair_functor", "xnb_lennard_jones_force", "xnb_gravitational_force", "xnb_load_balance_rcb", "xnb_get_block", "xnb_host_amr_sub_cell_pairs",
     "xnb_divide_force_by_mass", "xnb_set_chunk_neighbors_config", "xnb_lennard_jones_force_symmetric", "xnb_update_force_from_ghost", "xnb_push_f_v_r", "xnb_push_f_v", "xnb_particle_displ_over", "xnb_verlet_first_half",
     "xnb_read_displ_over", "xnb_force_and_second_half", "xnb_run_steps", "xnb_step_host", "xnb_first_iteration", "xnb_energy_virial",
     "xnb_view_chunk_neighbors", "xnb_stream_pool_u16", "xnb_get_streams", "xnb_get_amr", "xnb_get_backup",
@@ -83,7 +83,7 @@ def load():
         "xnb_view_particles": (I, [P, C.POINTER(XnbParticleView)]), "xnb_device_allocations": (I64, []),
         "xnb_move_particles": (I, [P, P]), "xnb_rebuild_amr": (I, [P, P]), "xnb_backup_r": (I, [P, P]), "xnb_ghost_comm_scheme": (I, [P, P]),
         "xnb_ghost_update_all": (I, [P, P]), "xnb_ghost_update_r": (I, [P, P]), "xnb_chunk_neighbors": (I, [P, P]),
-        "xnb_zero_particle_force": (I, [P, I, P]), "xnb_set_pair_functor": (I, [P, I]), "xnb_lennard_jones_force": (I, [P, D, D, D, I, P]), "xnb_gravitational_force": (I, [P, D, D, I, I, P]), "xnb_load_balance_rcb": (I, [P, P, P, P, P]), "xnb_get_block": (I, [P, I, P, P]), "xnb_divide_force_by_mass": (I, [P, P]),
+        "xnb_zero_particle_force": (I, [P, I, P]), "xnb_set_pair_functor": (I, [P, I]), "xnb_lennard_jones_force": (I, [P, D, D, D, I, P]), "xnb_gravitational_force": (I, [P, D, D, I, I, P]), "xnb_load_balance_rcb": (I, [P, P, P, P, P]), "xnb_get_block": (I, [P, I, P, P]), "xnb_host_amr_sub_cell_pairs": (I64, [I, D, D, P, P]), "xnb_divide_force_by_mass": (I, [P, P]),
         "xnb_set_chunk_neighbors_config": (I, [P, I, I]), "xnb_lennard_jones_force_symmetric": (I, [P, D, D, D, P]), "xnb_update_force_from_ghost": (I, [P, P]),
         "xnb_push_f_v_r": (I, [P, D, D, P]), "xnb_push_f_v": (I, [P, D, D, P]), "xnb_particle_displ_over": (I, [P, P, P]),
         "xnb_verlet_first_half": (I, [P, D, P]), "xnb_read_displ_over": (I, [P, P, P]), "xnb_force_and_second_half": (I, [P, D, D, D, D, P]),
@@ -426,3 +426,16 @@ def ghost_items(grid_dims, periodic, ghost_layers, nranks, src_rank, dst_rank):
     a = np.zeros(n, np.uint32); b = np.zeros(n, np.uint32); f = np.zeros(n, np.uint32)
     L.xnb_host_ghost_items(_p(gd), _p(per), ghost_layers, nranks, src_rank, dst_rank, n, _p(a), _p(b), _p(f))
     return a, b, f
+
+
+def amr_sub_cell_pairs(max_res, cell_size, max_dist):
+    """op amr_grid_pairs (host): (list_offsets, pairs) of the AmrSubCellPairCache"""
+    L = load()
+    layers = int(np.ceil(max_dist / cell_size))
+    n_lists = max_res * (max_res + 1) // 2 * (layers + 1) ** 3
+    n = L.xnb_host_amr_sub_cell_pairs(int(max_res), float(cell_size), float(max_dist), None, None)
+    if n < 0:
+        raise ValueError("amr_sub_cell_pairs: bad arguments")
+    off = np.zeros(n_lists + 1, np.uint64); data = np.zeros(max(int(n), 1), np.uint16)
+    L.xnb_host_amr_sub_cell_pairs(int(max_res), float(cell_size), float(max_dist), _p(off), _p(data))
+    return off, data[:int(n)]

@@ -5,6 +5,7 @@
 #include "xnb_host_decomp.hpp"
 #include <algorithm>
 #include <vector>
+#include <cmath>
 
 namespace xnb {
 
@@ -200,4 +201,45 @@ extern "C" int64_t xnb_host_ghost_items(const int64_t grid_dims[3], const int32_
       if (flags) flags[q] = items[q].flags;
     }
   return (int64_t)items.size();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// op `amr_grid_pairs`: max_distance_sub_cell_pairs (src/amr/lib/amr_grid_algorithm.cpp:102-218) -> AmrSubCellPairCache
+// (amr/include/exanb/amr/amr_grid_algorithm.h:439-453).  For every resolution pair (res_a <= res_b <= max_res, in the order
+// res_b outer / res_a inner = unique_pair_id) and every neighbour cell offset (k, j, i in [0, layers], layers = ceil(max_dist / cell_size)):
+// the list of (sub-cell a, sub-cell b) pairs, each coded (k << 10) | (j << 5) | i, whose boxes are at most max_dist apart.
+// list_offsets: n_lists + 1 entries (u16 words); pairs: a, b interleaved.  Returns the total number of u16 words (pairs may be NULL
+// to size the buffer), or -1 on bad arguments.  n_lists = max_res (max_res + 1) / 2 * (layers + 1)^3.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int64_t xnb_host_amr_sub_cell_pairs(int max_res, double cell_size, double max_dist, uint64_t* list_offsets, uint16_t* pairs)
+{
+  if (max_res < 1 || max_res >= 32 || !(cell_size > 0.0) || !(max_dist >= 0.0)) return -1;
+  const double max_dist2 = max_dist * max_dist;
+  const int layers = (int)std::ceil(max_dist / cell_size);
+  int64_t total = 0; size_t list = 0;
+  auto min_d2_1d = [](double alo, double ahi, double blo, double bhi) { const double d = std::max(0.0, std::max(blo - ahi, alo - bhi)); return d * d; };
+  for (int res_b = 1; res_b <= max_res; res_b++) for (int res_a = 1; res_a <= res_b; res_a++)
+  {
+    const double sa = cell_size / res_a, sb = cell_size / res_b;
+    for (int ck = 0; ck <= layers; ck++) for (int cj = 0; cj <= layers; cj++) for (int ci = 0; ci <= layers; ci++)
+    {
+      if (list_offsets) list_offsets[list] = (uint64_t)total;
+      list++;
+      for (int ka = 0; ka < res_a; ka++) for (int ja = 0; ja < res_a; ja++) for (int ia = 0; ia < res_a; ia++)
+        for (int kb = 0; kb < res_b; kb++) for (int jb = 0; jb < res_b; jb++) for (int ib = 0; ib < res_b; ib++)
+        {
+          // min_distance2_between of the two boxes (core/geometry.h:125-156): per axis gap, squared and summed x, y, z
+          const double dx = min_d2_1d(ia * sa, (ia + 1) * sa, ci * cell_size + ib * sb, ci * cell_size + (ib + 1) * sb);
+          const double dy = min_d2_1d(ja * sa, (ja + 1) * sa, cj * cell_size + jb * sb, cj * cell_size + (jb + 1) * sb);
+          const double dz = min_d2_1d(ka * sa, (ka + 1) * sa, ck * cell_size + kb * sb, ck * cell_size + (kb + 1) * sb);
+          if (dx + dy + dz <= max_dist2)
+          {
+            if (pairs) { pairs[total] = (uint16_t)((ka << 10) | (ja << 5) | ia); pairs[total + 1] = (uint16_t)((kb << 10) | (jb << 5) | ib); }
+            total += 2;
+          }
+        }
+    }
+  }
+  if (list_offsets) list_offsets[list] = (uint64_t)total;
+  return total;
 }

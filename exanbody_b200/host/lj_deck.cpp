@@ -1,7 +1,9 @@
 // lj_deck.cpp -- the reference's LJ regression deck (contribs/microStamp/samples/benchmark_lj_snap/input_lj_Ni.msp) composed
 // from the operator mirror exactly as the YAML batches of data/config/*.msp compose it:
 //   input_data -> nbh_dist -> first_iteration -> compute_loop(numerical_scheme) -> simulation_epilog(check_values)
-// usage: lj_deck <check_values file> [grid cells per axis = 4] [steps = 100] [check]
+// usage: lj_deck <check_values file> [grid cells per axis = 4] [steps = 100] [check | dump <prefix> | restart <dump file>]
+//   dump: after the loop write <prefix>.dump (write_dump) and <prefix>.xyz (write_xyz), then check_values
+//   restart: input_data = read_dump instead of lattice + noise, then the loop, then check_values
 #include "xnb_operators.hpp"
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +30,8 @@ int main(int argc, char** argv)
   const std::string golden = argc > 1 ? argv[1] : "check_values_lj_Ni.dat";
   const int cells = argc > 2 ? std::atoi(argv[2]) : 4;
   const int end_iteration = argc > 3 ? std::atoi(argv[3]) : 100;
+  const std::string mode = argc > 4 ? argv[4] : "";
+  const std::string io_arg = argc > 5 ? argv[5] : "";
   char dom[512];
   std::snprintf(dom, sizeof dom, "{ cell_size: 13.92 ang , grid_dims: [ %d , %d , %d ] , bounds: [ [ 0.0 um , 0.0 um , 0.0 um ] , [ %.2f ang , %.2f ang , %.2f ang ] ] , "
                 "periodic: [ true , true , true ] , expandable: false }", cells, cells, cells, 13.92 * cells, 13.92 * cells, 13.92 * cells);
@@ -42,10 +46,19 @@ int main(int argc, char** argv)
   // input_data: (input_lj_Ni.msp:57-76)
   auto input_data = sim.sub_batch();
   input_data->add("particle_type_add_properties", "{ Ni: { mass: 58.693 Da , z: 28 } }");
-  input_data->add("domain", dom);
-  input_data->add("init_rcb_grid");
-  input_data->add("lattice", "{ structure: FCC , types: [ Ni , Ni , Ni , Ni ] , size: [ 3.48 ang , 3.48 ang , 3.48 ang ] }");
-  input_data->add("gaussian_noise_r", "{ sigma: 0.05 ang }");
+  if (mode == "restart")
+  {
+    input_data->add("read_dump", "{ filename: " + io_arg + " }");      // domain and particles come from the checkpoint
+    input_data->add("domain");
+    input_data->add("init_rcb_grid");
+  }
+  else
+  {
+    input_data->add("domain", dom);
+    input_data->add("init_rcb_grid");
+    input_data->add("lattice", "{ structure: FCC , types: [ Ni , Ni , Ni , Ni ] , size: [ 3.48 ang , 3.48 ang , 3.48 ang ] }");
+    input_data->add("gaussian_noise_r", "{ sigma: 0.05 ang }");
+  }
 
   // compute_all_forces_energy: (input_lj_Ni.msp:88-92); lennard_jones_force: (:83-85)
   auto forces = sim.sub_batch();
@@ -91,8 +104,15 @@ int main(int argc, char** argv)
     forces->execute();
     verlet_second_half->execute();
   }
+  if (mode == "dump")
+  {
+    auto io = sim.sub_batch();
+    io->add("write_dump", "{ filename: " + io_arg + ".dump }");
+    io->add("write_xyz", "{ filename: " + io_arg + ".xyz , fields: [ velocity , id , type ] }");
+    io->execute();
+  }
   // the reference's golden file belongs to the verbatim deck; any other size runs check_values only on request (it then writes or reads its own file)
-  if ((cells == 4 && end_iteration == 100) || (argc > 4 && std::string(argv[4]) == "check")) epilog->execute();
+  if ((cells == 4 && end_iteration == 100) || !mode.empty()) epilog->execute();
   std::printf("lj_deck: %lld particles, %d iterations, %d neighbour rebuilds\n", (long long)sim.value<Grid>("grid")->number_of_particles(), end_iteration, rebuilds);
   return 0;
 }

@@ -1,6 +1,9 @@
 // xnb_operators.cpp -- the operators of the LJ hot path behind the reference's operator interface (see xnb_operators.hpp).
 // Each operator cites the reference operator whose name, slots and YAML keys it mirrors; execute() forwards to the C-ABI.
 #include "xnb_operators.hpp"
+#include <regex>
+#include <cstring>
+#include <cstdio>
 
 #include <algorithm>
 #include <cmath>
@@ -200,7 +203,7 @@ struct ParticleTypeAddProperties : OperatorNode
   ADD_SLOT(ParticleTypeProperties, particle_type_properties, INPUT_OUTPUT);
   void yaml_initialize(const Params& p) override
   {
-    for (auto& kv : p.kv) { const size_t dot = kv.first.find(".mass"); if (dot != std::string::npos) particle_type_properties->mass.push_back(convert_quantity(kv.second)); }
+    for (auto& kv : p.kv) { const size_t dot = kv.first.find(".mass"); if (dot != std::string::npos) { particle_type_properties->mass.push_back(convert_quantity(kv.second)); particle_type_properties->names.push_back(kv.first.substr(0, dot)); } }
   }
   void execute() override {}
 };
@@ -295,7 +298,37 @@ struct MoveParticles : OperatorNode
     ck(grid->ctx, xnb_move_particles(grid->ctx, stream), "move_particles");
   }
 };
-struct Nop : OperatorNode { void execute() override {} };     // operators whose work is folded into a neighbour (see registration)
+struct Nop : OperatorNode { void execute() override {} };
+
+// op `amr_grid_pairs` (amr/amr_grid_pairs.cpp -> max_distance_sub_cell_pairs, amr/lib/amr_grid_algorithm.cpp:102-218): the
+// AmrSubCellPairCache, rebuilt only when the maximum sub-grid resolution, the cell size or the distance changed (:129-133)
+struct AmrGridPairs : OperatorNode
+{
+  ADD_SLOT(Grid, grid, INPUT);
+  ADD_SLOT(AmrGrid, amr, INPUT, AmrGrid{});
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  ADD_SLOT(double, nbh_dist, INPUT, REQUIRED);
+  ADD_SLOT(AmrSubCellPairCache, amr_grid_pairs, INPUT_OUTPUT);
+  void execute() override
+  {
+    if (!grid->ctx) return;
+    xnb_grid_info gi; ck(grid->ctx, xnb_get_grid_info(grid->ctx, &gi), "amr_grid_pairs");
+    std::vector<int64_t> sgs((size_t)gi.n_cells + 1, 0);
+    if (xnb_get_amr(grid->ctx, sgs.data(), nullptr) < 0) fatal_error(std::string("amr_grid_pairs: ") + xnb_last_error(grid->ctx));
+    size_t max_res = 1;
+    for (int64_t c = 0; c < gi.n_cells; c++) { const size_t side = (size_t)std::llround(std::cbrt((double)(sgs[(size_t)c + 1] - sgs[(size_t)c] + 1))); max_res = std::max(max_res, side); }
+    AmrSubCellPairCache& pc = *amr_grid_pairs;
+    pc.ctx = grid->ctx;
+    if (max_res <= pc.m_max_res && domain->cell_size == pc.m_cell_size && *nbh_dist == pc.m_max_dist) return;       // cache up to date
+    pc.m_max_res = max_res; pc.m_cell_size = domain->cell_size; pc.m_max_dist = *nbh_dist;
+    const int64_t n = xnb_host_amr_sub_cell_pairs((int)max_res, pc.m_cell_size, pc.m_max_dist, nullptr, nullptr);
+    if (n < 0) fatal_error("amr_grid_pairs: bad resolution / distance");
+    const size_t layers = (size_t)std::ceil(pc.m_max_dist / pc.m_cell_size);
+    pc.m_list_offsets.assign(max_res * (max_res + 1) / 2 * (layers + 1) * (layers + 1) * (layers + 1) + 1, 0);
+    pc.m_pair_ab.assign((size_t)n, 0);
+    xnb_host_amr_sub_cell_pairs((int)max_res, pc.m_cell_size, pc.m_max_dist, pc.m_list_offsets.data(), pc.m_pair_ab.data());
+  }
+};     // operators whose work is folded into a neighbour (see registration)
 
 struct RebuildAmr : OperatorNode        // amr/rebuild_amr.cpp:35-68 (slot default 5.0; the default decks set 6.5, update-particles.msp:9)
 {
@@ -470,6 +503,207 @@ struct ParticleDisplOver : OperatorNode         // mpi/particle_displ_over.cu:98
 };
 
 // op `check_values` (debug/check_values.cpp:52-405), reader side: [id, r(3), a(3), v(3)] hex-float rows
+// ---------------------------------------------------------------------------------------------------------------------
+// on-disk formats either side of the loop.  Single sub-domain per file (the reference writes one file from all
+// ranks through MPI-IO: io/include/exanb/io/mpi_file_io.h).
+// ---------------------------------------------------------------------------------------------------------------------
+// fetch this rank's inner particles (cell order)
+struct HostParticles { std::vector<double> f[9]; std::vector<uint64_t> id; std::vector<uint8_t> type; int64_t n = 0; };
+static void fetch_particles(xnb_ctx* ctx, HostParticles& hp, const char* who)
+{
+  hp.n = xnb_num_inner(ctx);
+  for (auto& v : hp.f) v.resize((size_t)hp.n);
+  hp.id.resize((size_t)hp.n); hp.type.resize((size_t)hp.n);
+  ck(ctx, xnb_get_particles(ctx, 0, hp.n, hp.f[0].data(), hp.f[1].data(), hp.f[2].data(), hp.f[3].data(), hp.f[4].data(), hp.f[5].data(), hp.f[6].data(), hp.f[7].data(), hp.f[8].data(),
+                            hp.id.data(), hp.type.data(), nullptr), who);
+}
+
+// op `write_xyz` (io/write_xyz.cpp:28-116, io/include/exanb/io/write_xyz.h:200-415): extended-XYZ text.
+//   line 1: particle count; line 2: Lattice="<9 x %10.12e>" Properties=species:S:1:pos:R:3[:vel:R:3][:force:R:3][:processor_id:I:1][:id:I:1][:type:I:1] Time=<t>
+//   then one FIXED-WIDTH line per particle: type name "%-8s", ' ', position "% .10e % .10e % .10e", then every selected field preceded by
+//   ' ' (reals "% .10e", integers "% 10d").  Fields are selected by the regular expressions of `fields` (default ".*"), position always
+//   first; `field_alias` defaults position -> pos, velocity -> vel.  (The reference's `units` map is parsed but its formatter is called
+//   without a field id, write_xyz.h:316,368, so no conversion is applied; none is applied here either.)
+struct WriteXYZ : OperatorNode
+{
+  ADD_SLOT(Grid, grid, INPUT);
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  ADD_SLOT(bool, ghost, INPUT, false);
+  ADD_SLOT(std::string, filename, INPUT, std::string("output"));
+  ADD_SLOT(std::vector<std::string>, fields, INPUT, std::vector<std::string>({".*"}), DocString{"List of regular expressions to select fields to write"});
+  ADD_SLOT(ParticleTypeProperties, particle_type_properties, INPUT, ParticleTypeProperties{});
+  ADD_SLOT(double, physical_time, INPUT, 0.0);
+  void yaml_initialize(const Params& p) override
+  {
+    if (p.has("filename")) filename.value = std::make_shared<std::string>(p.str("filename"));
+    if (p.has("fields"))
+    {
+      std::vector<std::string> l; std::string cur;
+      for (char ch : p.str("fields")) { if (ch == '[' || ch == ']' || ch == ' ' || ch == '"') continue; if (ch == ',') { if (!cur.empty()) l.push_back(cur); cur.clear(); } else cur += ch; }
+      if (!cur.empty()) l.push_back(cur);
+      fields.value = std::make_shared<std::vector<std::string>>(l);
+    }
+    XNB_PARAM_BOOL(p, ghost);
+  }
+  void execute() override
+  {
+    if (*ghost) fatal_error("write_xyz: ghost: true is not offered (ghosts are copies of inner particles)");
+    HostParticles hp; fetch_particles(grid->ctx, hp, "write_xyz");
+    auto selected = [&](const std::string& name) { for (const auto& f : *fields) if (std::regex_match(name, std::regex(f))) return true; return false; };
+    const bool w_vel = selected("velocity"), w_force = selected("force"), w_rank = selected("processor_id"), w_id = selected("id"), w_type = selected("type");
+    const Domain& d = *domain;
+    std::FILE* out = std::fopen(filename->c_str(), "w");
+    if (!out) fatal_error("write_xyz: cannot write '" + *filename + "'");
+    const double L[3] = {d.bounds.bmax.x - d.bounds.bmin.x, d.bounds.bmax.y - d.bounds.bmin.y, d.bounds.bmax.z - d.bounds.bmin.z};
+    std::fprintf(out, "%ld\nLattice=\"%10.12e %10.12e %10.12e %10.12e %10.12e %10.12e %10.12e %10.12e %10.12e\"", (long)hp.n, L[0], 0., 0., 0., L[1], 0., 0., 0., L[2]);
+    std::ostringstream prop; prop << " Properties=species:S:1:pos:R:3";
+    if (w_vel) prop << ":vel:R:3";
+    if (w_force) prop << ":force:R:3";
+    if (w_rank) prop << ":processor_id:I:1";
+    if (w_id) prop << ":id:I:1";
+    if (w_type) prop << ":type:I:1";
+    prop << " Time=" << *physical_time << "\n";
+    std::fputs(prop.str().c_str(), out);
+    const auto& names = particle_type_properties->names;
+    for (int64_t q = 0; q < hp.n; q++)
+    {
+      const size_t i = (size_t)q;
+      const char* tn = hp.type[i] < names.size() ? names[hp.type[i]].c_str() : "XX";
+      std::fprintf(out, "%-8s % .10e % .10e % .10e", tn, hp.f[0][i], hp.f[1][i], hp.f[2][i]);
+      if (w_vel) std::fprintf(out, " % .10e % .10e % .10e", hp.f[3][i], hp.f[4][i], hp.f[5][i]);
+      if (w_force) std::fprintf(out, " % .10e % .10e % .10e", hp.f[6][i], hp.f[7][i], hp.f[8][i]);
+      if (w_rank) std::fprintf(out, " % 10d", 0);
+      if (w_id) std::fprintf(out, " % 10ld", (long)hp.id[i]);
+      if (w_type) std::fprintf(out, " % 10d", (int)hp.type[i]);
+      std::fputc('\n', out);
+    }
+    std::fclose(out);
+  }
+};
+
+// ops `write_dump` / `read_dump` (io/write_dump.cpp:36-46, read_dump.cpp, io/include/exanb/io/sim_dump_io.h:105-190,
+// sim_dump_writer.h:100-490, sim_dump_reader.h): checkpoint of positions, velocities, id, type (SimDumpWriteAllButForce).
+// File = SimDumpHeader fields in the reference's order (version 1.3 = 1003, nb_fields, data_flags, tuple_size, field_size[128],
+// fields[128][32], nb_particles, time_step, time, domain, optional/table/data offsets, optional_header_size, chunk_count), a table of
+// DataChunkItem {u64 global_offset, u32 data_size, i32 n_particles}, then the chunks: arrays of tuples {rx ry rz vx vy vz (f64), id (u64),
+// type (u8) + 7 pad bytes}, uncompressed (negative n_particles = "size is the raw size", sim_dump_writer.h:87-92).  The byte layouts
+// of the domain record and of the tuple are THIS MIRROR'S (onika's soatl::FieldTuple and the reference Domain class are not
+// reproducible byte for byte without onika): files round-trip through these two operators, not through the reference.
+struct DumpDomainRecord { double bmin[3], bmax[3], cell_size; int64_t grid_dims[3]; double xform[9]; uint32_t flags; uint32_t pad; };
+struct DumpTuple { double r[3], v[3]; uint64_t id; uint8_t type; uint8_t pad[7]; };
+struct DumpChunkItem { uint64_t global_offset; uint32_t data_size; int32_t n_particles; };
+struct DumpHeader
+{
+  uint64_t version = 1003; uint32_t nb_fields = 8; uint8_t data_flags[4] = {0, 0, 0, 0}; uint64_t tuple_size = sizeof(DumpTuple);
+  uint64_t field_size[128]; char fields[128][32];
+  uint64_t nb_particles = 0, time_step = 0; double time = 0.0;
+  DumpDomainRecord domain;
+  uint64_t optional_offset = 0, table_offset = 0, data_offset = 0, optional_header_size = 0, chunk_count = 0;
+};
+static const size_t DUMP_CHUNK_PARTICLES = 1048576;      // WRITE_BUFFER_SIZE of sim_dump_writer.h
+struct WriteDump : OperatorNode
+{
+  ADD_SLOT(Grid, grid, INPUT);
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED);
+  ADD_SLOT(std::string, filename, INPUT, std::string("output.dump"));
+  ADD_SLOT(long, timestep, INPUT, 0L);
+  ADD_SLOT(double, physical_time, INPUT, 0.0);
+  ADD_SLOT(long, compression_level, INPUT, 0L, DocString{"accepted; chunks are stored raw"});
+  void yaml_initialize(const Params& p) override { if (p.has("filename")) filename.value = std::make_shared<std::string>(p.str("filename")); }
+  void execute() override
+  {
+    HostParticles hp; fetch_particles(grid->ctx, hp, "write_dump");
+    DumpHeader h;
+    std::memset(h.field_size, 0, sizeof h.field_size); std::memset(h.fields, 0, sizeof h.fields);
+    const char* fn[8] = {"rx", "ry", "rz", "vx", "vy", "vz", "id", "type"}; const uint64_t fs[8] = {8, 8, 8, 8, 8, 8, 8, 1};
+    for (int q = 0; q < 8; q++) { std::strncpy(h.fields[q], fn[q], 31); h.field_size[q] = fs[q]; }
+    h.nb_particles = (uint64_t)hp.n; h.time_step = (uint64_t)*timestep; h.time = *physical_time;
+    const Domain& d = *domain;
+    std::memset(&h.domain, 0, sizeof h.domain);
+    h.domain.bmin[0] = d.bounds.bmin.x; h.domain.bmin[1] = d.bounds.bmin.y; h.domain.bmin[2] = d.bounds.bmin.z;
+    h.domain.bmax[0] = d.bounds.bmax.x; h.domain.bmax[1] = d.bounds.bmax.y; h.domain.bmax[2] = d.bounds.bmax.z;
+    h.domain.cell_size = d.cell_size; h.domain.grid_dims[0] = d.grid_dims.i; h.domain.grid_dims[1] = d.grid_dims.j; h.domain.grid_dims[2] = d.grid_dims.k;
+    h.domain.xform[0] = h.domain.xform[4] = h.domain.xform[8] = 1.0;
+    h.domain.flags = (d.periodic[0] ? 1u : 0u) | (d.periodic[1] ? 2u : 0u) | (d.periodic[2] ? 4u : 0u) | (d.expandable ? 8u : 0u);
+    const size_t nchunks = ((size_t)hp.n + DUMP_CHUNK_PARTICLES - 1) / DUMP_CHUNK_PARTICLES;
+    h.chunk_count = nchunks + 1;                                       // a free slot at the end stores the file size (sim_dump_writer.h:173)
+    h.optional_offset = sizeof(DumpHeader); h.table_offset = h.optional_offset; h.data_offset = h.table_offset + h.chunk_count * sizeof(DumpChunkItem);
+    std::vector<DumpChunkItem> table(h.chunk_count);
+    uint64_t off = h.data_offset;
+    for (size_t c = 0; c < nchunks; c++)
+    {
+      const size_t n = std::min(DUMP_CHUNK_PARTICLES, (size_t)hp.n - c * DUMP_CHUNK_PARTICLES);
+      table[c] = DumpChunkItem{off, (uint32_t)(n * sizeof(DumpTuple)), -(int32_t)n};
+      off += n * sizeof(DumpTuple);
+    }
+    table[nchunks] = DumpChunkItem{off, 0, 0};
+    std::FILE* out = std::fopen(filename->c_str(), "wb");
+    if (!out) fatal_error("write_dump: cannot write '" + *filename + "'");
+    std::fwrite(&h, sizeof h, 1, out); std::fwrite(table.data(), sizeof(DumpChunkItem), table.size(), out);
+    std::vector<DumpTuple> buf;
+    for (size_t c = 0; c < nchunks; c++)
+    {
+      const size_t q0 = c * DUMP_CHUNK_PARTICLES, n = (size_t)(-table[c].n_particles);
+      buf.assign(n, DumpTuple{});
+      for (size_t q = 0; q < n; q++)
+      {
+        DumpTuple& t = buf[q]; const size_t i = q0 + q;
+        for (int a = 0; a < 3; a++) { t.r[a] = hp.f[a][i]; t.v[a] = hp.f[3 + a][i]; }
+        t.id = hp.id[i]; t.type = hp.type[i];
+      }
+      std::fwrite(buf.data(), sizeof(DumpTuple), n, out);
+    }
+    std::fclose(out);
+    std::printf("write_dump: %lld particles, %zu chunks -> %s\n", (long long)hp.n, nchunks, filename->c_str());
+  }
+};
+struct ReadDump : OperatorNode
+{
+  ADD_SLOT(std::string, filename, INPUT, std::string("output.dump"));
+  ADD_SLOT(Domain, domain, INPUT_OUTPUT);
+  ADD_SLOT(ParticleSet, pending_particles, INPUT_OUTPUT);
+  ADD_SLOT(long, timestep, INPUT_OUTPUT, 0L);
+  ADD_SLOT(double, physical_time, INPUT_OUTPUT, 0.0);
+  void yaml_initialize(const Params& p) override { if (p.has("filename")) filename.value = std::make_shared<std::string>(p.str("filename")); }
+  void execute() override
+  {
+    std::FILE* in = std::fopen(filename->c_str(), "rb");
+    if (!in) fatal_error("read_dump: cannot read '" + *filename + "'");
+    DumpHeader h;
+    if (std::fread(&h, sizeof h, 1, in) != 1) fatal_error("read_dump: short header");
+    if (h.version > 1003) fatal_error("SimDumpHeader::check : bad version number");                       // sim_dump_io.h:181-185
+    if (h.tuple_size != sizeof(DumpTuple) || h.nb_fields != 8) fatal_error("SimDumpHeader::check : bad tuple size");      // :187-191
+    std::vector<DumpChunkItem> table(h.chunk_count);
+    std::fseek(in, (long)h.table_offset, SEEK_SET);
+    if (std::fread(table.data(), sizeof(DumpChunkItem), table.size(), in) != table.size()) fatal_error("read_dump: short chunk table");
+    Domain& d = *domain;
+    d.bounds.bmin = {h.domain.bmin[0], h.domain.bmin[1], h.domain.bmin[2]}; d.bounds.bmax = {h.domain.bmax[0], h.domain.bmax[1], h.domain.bmax[2]};
+    d.cell_size = h.domain.cell_size; d.grid_dims = {h.domain.grid_dims[0], h.domain.grid_dims[1], h.domain.grid_dims[2]};
+    for (int a = 0; a < 3; a++) d.periodic[a] = (h.domain.flags >> a) & 1u;
+    d.expandable = (h.domain.flags >> 3) & 1u;
+    ParticleSet& ps = *pending_particles;
+    ps = ParticleSet{};
+    std::vector<DumpTuple> buf;
+    for (const DumpChunkItem& c : table)
+    {
+      const size_t n = (size_t)std::abs(c.n_particles);
+      if (n == 0) continue;
+      buf.resize(n);
+      std::fseek(in, (long)c.global_offset, SEEK_SET);
+      if (std::fread(buf.data(), sizeof(DumpTuple), n, in) != n) fatal_error("read_dump: short chunk");
+      for (const DumpTuple& t : buf)
+      {
+        ps.rx.push_back(t.r[0]); ps.ry.push_back(t.r[1]); ps.rz.push_back(t.r[2]); ps.vx.push_back(t.v[0]); ps.vy.push_back(t.v[1]); ps.vz.push_back(t.v[2]);
+        ps.id.push_back(t.id); ps.type.push_back(t.type);
+      }
+    }
+    std::fclose(in);
+    if (ps.rx.size() != h.nb_particles) fatal_error("read_dump: particle count does not match the header");
+    *timestep = (long)h.time_step; *physical_time = h.time;
+    std::printf("read_dump: %zu particles, time step %ld <- %s\n", ps.rx.size(), *timestep, filename->c_str());
+  }
+};
+
 struct CheckValues : OperatorNode
 {
   ADD_SLOT(Grid, grid, INPUT);
@@ -576,7 +810,7 @@ void register_hot_path_operators()
   f->register_factory("ghost_comm_scheme", make_simple_operator<GhostCommSchemeOp>());
   f->register_factory("ghost_update_all", make_simple_operator<GhostUpdate<true>>());
   f->register_factory("ghost_update_r", make_simple_operator<GhostUpdate<false>>());
-  f->register_factory("amr_grid_pairs", make_simple_operator<Nop>());            // the sub-cell pair cache only prunes candidates; the tiled build does not need it
+  f->register_factory("amr_grid_pairs", make_simple_operator<AmrGridPairs>());   // the cache object for consumers; the builds themselves prune with measured boxes (xnb_nbh_big.cuh)
   f->register_factory("chunk_neighbors", make_simple_operator<BuildChunkNeighbors>());
   f->register_factory("resize_particle_locks", make_simple_operator<Nop>());     // ComputePairOptionalLocks<false>: LJ takes no locks
   f->register_factory("zero_particle_force", make_simple_operator<ZeroParticleForce>());
@@ -590,6 +824,9 @@ void register_hot_path_operators()
   f->register_factory("push_f_v", make_simple_operator<PushFV>());
   f->register_factory("particle_displ_over", make_simple_operator<ParticleDisplOver>());
   f->register_factory("check_values", make_simple_operator<CheckValues>());
+  f->register_factory("write_xyz", make_simple_operator<WriteXYZ>());
+  f->register_factory("write_dump", make_simple_operator<WriteDump>());
+  f->register_factory("read_dump", make_simple_operator<ReadDump>());
 }
 
 }} // namespace xnb::host

@@ -58,10 +58,12 @@ struct Grid { xnb_ctx* ctx = nullptr; int device = 0; ~Grid(); Grid() = default;
 struct GridChunkNeighbors { xnb_ctx* ctx = nullptr; const uint16_t* const* cell_stream = nullptr; const uint32_t* cell_stream_size = nullptr;
                             uint32_t max_neighbors = 0; size_t number_of_cells() const; };     // chunk_neighbors.h:42-120 (device views)
 struct AmrGrid { xnb_ctx* ctx = nullptr; };
-struct AmrSubCellPairCache { xnb_ctx* ctx = nullptr; };
+// amr_grid_algorithm.h:439-453: per (resolution pair, neighbour cell offset) the sub-cell pairs closer than max_dist, (a, b) codes interleaved
+struct AmrSubCellPairCache { xnb_ctx* ctx = nullptr; size_t m_max_res = 0; double m_cell_size = 0.0, m_max_dist = 0.0;
+                             std::vector<uint64_t> m_list_offsets; std::vector<uint16_t> m_pair_ab; size_t number_of_lists() const { return m_list_offsets.empty() ? 0 : m_list_offsets.size() - 1; } };
 struct PositionBackupData { xnb_ctx* ctx = nullptr; };
 struct GhostCommunicationScheme { xnb_ctx* ctx = nullptr; };
-struct ParticleTypeProperties { std::vector<double> mass; };                // per-type scalars (vec3_typescalar_op.cu:71-122)
+struct ParticleTypeProperties { std::vector<double> mass; std::vector<std::string> names; };                // per-type scalars (vec3_typescalar_op.cu:71-122)
 struct ParticleSet { std::vector<double> rx, ry, rz, vx, vy, vz; std::vector<uint64_t> id; std::vector<uint8_t> type; };
 
 // ---- minimal parameter node: the `{ key: value, ... }` flow maps operators take in .msp decks -------------------------

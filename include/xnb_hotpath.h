@@ -266,6 +266,14 @@ int64_t xnb_host_lattice_fcc(const xnb_lattice_cfg* cfg, int64_t capacity, doubl
 /* ---- static decomposition, host only (no CUDA): what every rank derives for itself and its partners -------------- */
 /* src/core/lib/simple_block_rcb.cpp:27-59 (via init_rcb_grid.cpp:65-77): block [start,end) of `rank` among `nranks` */
 int xnb_host_rcb_block(const int64_t grid_dims[3], int nranks, int rank, int64_t start[3], int64_t end[3]);
+/* op `amr_grid_pairs` : max_distance_sub_cell_pairs (src/amr/lib/amr_grid_algorithm.cpp:102-218) -> AmrSubCellPairCache
+   (src/amr/include/exanb/amr/amr_grid_algorithm.h:439-453), host only.  For every resolution pair (res_b outer, res_a <= res_b
+   inner) and every neighbour-cell offset (k, j, i in [0, layers], layers = ceil(max_dist / cell_size)): the (sub-cell a, sub-cell b)
+   pairs, coded (k << 10) | (j << 5) | i each, whose boxes are at most max_dist apart.  list_offsets: n_lists + 1 entries
+   (n_lists = max_res (max_res + 1) / 2 * (layers + 1)^3); pairs: a, b interleaved.  Returns the number of u16 words (call with
+   NULLs to size the buffers), -1 on bad arguments.  The product's own builds prune with measured bounding boxes instead
+   (csrc/xnb_nbh_big.cuh); the cache is produced for operators that consume it.                                        */
+int64_t xnb_host_amr_sub_cell_pairs(int max_res, double cell_size, double max_dist, uint64_t* list_offsets, uint16_t* pairs);
 /* op `simple_cost_model` (src/mpi/include/exanb/mpi/simple_cost_model.h:67-146), arithmetic only: cost of a cell from its
    particle count, p = N / cell_size^3, cost = coefs[0] p^3 + coefs[1] p^2 + coefs[2] p + coefs[3] (the reference's default
    coefficients are {0, 0, 1, 0}).  Feed it the inner-cell counts of xnb_get_cells; ghost cells carry no cost (:103).  */

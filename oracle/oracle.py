@@ -47,6 +47,7 @@ def lib():
                   "xo_compute_force", "xo_compute_force_symmetric", "xo_push_f_v_r", "xo_check_streams", "xo_zero_force"):
             getattr(L, f).argtypes = [P]; getattr(L, f).restype = C.c_int
         L.xo_run.argtypes = [P, C.c_int]; L.xo_run.restype = C.c_int
+        L.xo_amr_pair_cache.argtypes = [P, P, P, P]; L.xo_amr_pair_cache.restype = C.c_int64
         L.xo_gravitational_force.argtypes = [P, C.c_double, C.c_double, P, C.c_int]; L.xo_gravitational_force.restype = C.c_int
         L.xo_push_f_v.argtypes = [P, C.c_double]; L.xo_push_f_v.restype = C.c_int
         for f in ("xo_displ_over", "xo_total_particles", "xo_inner_particles", "xo_stream_total_u16", "xo_max_neighbors",
@@ -120,6 +121,15 @@ class Oracle:
     def build_neighbors(self): self._chk(self.L.xo_build_neighbors(self.h))
     def compute_force(self): self._chk(self.L.xo_compute_force(self.h))
     def compute_force_symmetric(self): self._chk(self.L.xo_compute_force_symmetric(self.h))
+    def amr_pair_cache(self):
+        """(max_res, list_offsets, pairs) of the AmrSubCellPairCache built by the last build_neighbors / update_particles_full"""
+        mr = C.c_int64()
+        n = self.L.xo_amr_pair_cache(self.h, C.addressof(mr), None, None)
+        layers_lists = None
+        # number of lists: walk once with a generous offsets buffer
+        off = np.zeros(1 + 32 * 33 // 2 * 64, np.uint64); data = np.zeros(max(int(n), 1), np.uint16)
+        self.L.xo_amr_pair_cache(self.h, None, off.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p))
+        return int(mr.value), off, data[:int(n)]
     def zero_force(self): self._chk(self.L.xo_zero_force(self.h))
     def gravitational_force(self, G, rcut, type_mass):
         m = np.ascontiguousarray(type_mass, np.float64)

@@ -1103,6 +1103,20 @@ int xo_build_neighbors(xo_sim* s) { amr_grid_pairs(*s); chunk_neighbors(*s); ret
 int xo_compute_force(xo_sim* s) { return compute_force(*s, nullptr, nullptr); }
 int xo_compute_force_symmetric(xo_sim* s) { return compute_force_symmetric(*s); }
 int xo_zero_force(xo_sim* s) { zero_force(*s); return 0; }
+int64_t xo_amr_pair_cache(const xo_sim* s, int64_t* max_res, uint64_t* list_offsets, uint16_t* pairs)
+{
+  const PairCache& pc = s->pair_cache;
+  if (max_res) *max_res = (int64_t)pc.max_res;
+  int64_t total = 0; size_t q = 0;
+  for (const SubCellPairs& l : pc.pairs)
+  {
+    if (list_offsets) list_offsets[q] = (uint64_t)total;
+    if (pairs) for (size_t t = 0; t < l.ab.size(); t++) pairs[(size_t)total + t] = l.ab[t];
+    total += (int64_t)l.ab.size(); q++;
+  }
+  if (list_offsets) list_offsets[q] = (uint64_t)total;
+  return total;
+}
 int xo_gravitational_force(xo_sim* s, double G, double rcut, const double* type_mass, int n_types) { return gravitational_force(*s, G, rcut, type_mass, n_types); }
 void xo_set_nbh_config(xo_sim* s, int half_symmetric, int skip_ghosts) { s->nbh_half_symmetric = half_symmetric != 0; s->nbh_skip_ghosts = skip_ghosts != 0; }
 int xo_push_f_v_r(xo_sim* s) { push_f_v_r(*s); return 0; }

@@ -95,6 +95,9 @@ int     xo_set_particles(xo_sim*, const int32_t* counts, const double* rx, const
                          const double* fx, const double* fy, const double* fz, const uint64_t* id, const uint8_t* type);
 /* AMR tables (amr_grid.h:31-61) */
 int64_t xo_amr_tables(const xo_sim*, int64_t* sub_grid_start /* n_cells+1 or NULL */, uint32_t* sub_grid_cells /* or NULL */);
+/* AmrSubCellPairCache of the last amr_grid_pairs (amr_grid_algorithm.cpp:102-218): lists in (res_b, res_a, offset k, j, i) order; returns the
+   number of u16 words, *max_res = the cache's resolution; list_offsets has n_lists + 1 entries; any pointer may be NULL */
+int64_t xo_amr_pair_cache(const xo_sim*, int64_t* max_res, uint64_t* list_offsets, uint16_t* pairs);
 /* backup_r (3 x u32 per inner atom, cell order over ALL cells, ghost cells contribute 0 entries) */
 int64_t xo_get_backup(const xo_sim*, uint32_t* out /* or NULL */);
 

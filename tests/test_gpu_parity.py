@@ -500,3 +500,26 @@ def test_gravitational_force_second_functor(case, buffer_form):
     ctx.gravitational_force(G, rcut, buffer_form=not buffer_form)
     pg2 = U.by_id(ctx.get_particles(0, ctx.n_inner))
     assert U.force_error(U.vec(pg2, ("fx", "fy", "fz")), 2.0 * fo) <= TOL
+
+
+@pytest.mark.parametrize("name,steps", [("C5", 40), ("C4", 3), ("C1", 6)])
+def test_full_size_workloads_against_the_oracle(name, steps):
+    """parity where the numbers are quoted (BASELINE.json configs at their stated size, the inputs bench.py times): the CUDA path and
+    the CPU oracle step the same input the same number of steps -- same atoms, SAME REBUILD COUNT (the C5 bar of SURVEY 8d), forces on
+    identical positions within 1e-10, neighbour streams of the final configuration byte for byte.  Exercises what only large inputs
+    reach: capacity regrowth of the tiled builds, the large-cell build (C1, C4: 256 atoms per cell), ragged occupancy (C5)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    kw, _ = bench.workload(name)
+    r = bench.run_cpu_oracle(kw, steps, 600.0, keep=True)
+    assert r["steps"] == steps
+    out = bench.parity_against_oracle(r["oracle"], steps, r["rebuilds"], kw, 0)
+    r["oracle"].close()
+    assert out["atoms_equal"] and out["rebuilds_equal"], out
+    assert out["streams_equal"], out
+    assert out["max_force_error_same_positions"] < TOL, out
+    assert out["ok"], out
+    if name in ("C4", "C5"):
+        assert r["rebuilds"] > 0

@@ -105,3 +105,35 @@ def test_check_values_writes_then_reads_its_own_file(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "check_values: 128 particles within thresholds" in r.stdout
     assert float(r.stdout.split("max abs error")[1].split()[0]) == 0.0
+
+
+@pytest.mark.gpu
+def test_dump_restart_and_xyz(tmp_path):
+    """write_dump -> read_dump restarts the deck (positions, velocities, ids, types and the domain travel through the
+    file; forces are recomputed), and write_xyz emits the reference's fixed-width extended-XYZ text.
+    Run A: 12 steps, checkpoint, then check_values writes its samples.  Run B: restart from the checkpoint with 0 steps, check_values
+    reads A's samples: positions / velocities identical, accelerations equal to rounding (the restart rebuilds the lists)."""
+    import numpy as np
+    deck = buildlib.build_host()
+    prefix = str(tmp_path / "ck")
+    cv = str(tmp_path / "cv.dat")
+    r = subprocess.run([deck, cv, "2", "12", "dump", prefix], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "write_dump: 2048 particles" in r.stdout and "check_values: wrote 128 reference particles" in r.stdout
+    # ---- extended XYZ (write_xyz.h:262-410): count, Lattice + Properties header, fixed-width lines
+    lines = open(prefix + ".xyz").read().split("\n")
+    assert lines[0] == "2048"
+    assert lines[1].startswith('Lattice="2.784000000000e+01 0.000000000000e+00') and "Properties=species:S:1:pos:R:3:vel:R:3:id:I:1:type:I:1 Time=0" in lines[1]
+    body = [l for l in lines[2:] if l]
+    assert len(body) == 2048 and len(set(len(l) for l in body)) == 1          # every line has the same width
+    assert body[0].startswith("Ni       ")
+    cols = np.array([[float(x) for x in l.split()[1:]] for l in body])
+    assert cols.shape == (2048, 8) and len(set(cols[:, 6].astype(int))) == 2048 and (cols[:, 7] == 0).all()
+    assert (cols[:, :3] > -1.0).all() and (cols[:, :3] < 28.84).all()          # positions are wrapped at the next move_particles only
+    # ---- checkpoint: header fields of SimDumpHeader, then restart
+    raw = open(prefix + ".dump", "rb").read()
+    assert int.from_bytes(raw[:8], "little") == 1003 and int.from_bytes(raw[8:12], "little") == 8          # version 1.3, 8 fields
+    r = subprocess.run([deck, cv, "2", "0", "restart", prefix + ".dump"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "read_dump: 2048 particles" in r.stdout and "check_values: 128 particles within thresholds" in r.stdout
+    assert float(r.stdout.split("max abs error")[1].split()[0]) < 1e-9
