@@ -124,7 +124,7 @@ k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32,
   const double oz = __dadd_rn(g.org[2], __dmul_rn((double)(g.off[2] + T.bz0) + 0.5 * (double)T.HZ, g.cs));
   // classification band from a bound on |r - O|: half the box (+ the epsilon a particle may stick out of its cell)
   const double Rm = 0.5 * (double)max(T.HX, max(T.HY, T.HZ)) * g.cs * (1.0 + 1e-9);
-  const double band = 5.9604644775390625e-08 * (192.0 * Rm * Rm + 12.0 * bp.max_dist2);
+  const double band = 5.9604644775390625e-08 * (128.0 * Rm * Rm + 4.0 * bp.max_dist2);
   const float band2 = (float)(2.0 * band);
   const float zc = (float)(bp.max_dist2);
   const float prune2 = (float)(bp.max_dist2 + 4.0 * band + 1e-6 * bp.max_dist2);          // boxes farther apart than this hold no pair

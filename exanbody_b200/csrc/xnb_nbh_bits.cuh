@@ -298,7 +298,7 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
   __syncthreads();
   // classification band: |fp32 value - exact| <= 2^-24 (81 R^2 + 5 max_dist2); the band used is more than twice that
   const double Rm = (double)__uint_as_float(s_rmax);
-  const double band = 5.9604644775390625e-08 * (192.0 * Rm * Rm + 12.0 * bp.max_dist2);
+  const double band = 5.9604644775390625e-08 * (128.0 * Rm * Rm + 4.0 * bp.max_dist2);
   const float band2 = (float)(2.0 * band);                 // accepted and t > -2 band: ambiguous
   const float zc = (float)(bp.max_dist2);                  // t + zc < 0  <=>  fp32 d2 < band: inside the zero band (own cell)
   const uint32_t Lsh = (uint32_t)__cvta_generic_to_shared(L);

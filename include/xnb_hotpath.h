@@ -7,6 +7,12 @@
  * cudaStream_t (passed as void*, NULL = default stream) and do not synchronise unless stated.  There is NO CPU
  * fallback: every entry point returns XNB_ERR_NO_DEVICE when no CUDA device is usable.
  *
+ * Entry points that BLOCK THE HOST (they wait on the stream for small results that size the next launch; marked
+ * "[host sync]" below): xnb_move_particles, xnb_rebuild_amr, xnb_ghost_comm_scheme, xnb_chunk_neighbors,
+ * xnb_load_balance_rcb, xnb_read_displ_over / xnb_particle_displ_over, xnb_run_steps (one event wait per step, after the
+ * fast path has been enqueued), xnb_step_host, xnb_first_iteration, xnb_energy_virial, and every xnb_get_* / xnb_download_*.
+ * The others only enqueue.  Device buffers grow geometrically on demand (xnb_device_allocations() counts the calls).
+ *
  * Return value: 0 = ok, otherwise an XNB_ERR_* code; xnb_last_error() gives the message
  * (the reference aborts through fatal_error(); the C++ shim in exanbody_b200/host maps non-zero to the same abort).
  *
@@ -129,19 +135,19 @@ int xnb_view_particles(xnb_ctx*, xnb_particle_view* out);
 /* op `move_particles` : src/grid_cell_particles/include/exanb/grid_cell_particles/move_particles_across_cells.h:78-235
    periodic wrap + cell location + re-binning of all inner particles (K1).  Multi-GPU: also performs the
    `migrate_cell_particles` hand-off of particles that left the block (src/mpi/migrate_cell_particles.cpp:101-143). */
-int xnb_move_particles(xnb_ctx*, void* stream);
+int xnb_move_particles(xnb_ctx*, void* stream);   /* [host sync] */
 /* op `rebuild_amr` : src/amr/rebuild_amr.cpp:35-62, amr_grid_algorithm.h:66-78,112-434 (in-cell sub-grid sort + tables) */
-int xnb_rebuild_amr(xnb_ctx*, void* stream);
+int xnb_rebuild_amr(xnb_ctx*, void* stream);   /* [host sync] */
 /* op `backup_r` : src/io/backup_r.cpp:36-78, src/core/include/exanb/core/backup_r.h:31-51                       */
 int xnb_backup_r(xnb_ctx*, void* stream);
 /* op `ghost_comm_scheme` : src/mpi/update_ghosts_comm_scheme.cpp:84-489 (who sends which particles of which cell) */
-int xnb_ghost_comm_scheme(xnb_ctx*, void* stream);
+int xnb_ghost_comm_scheme(xnb_ctx*, void* stream);   /* [host sync] */
 /* ops `ghost_update_all` / `ghost_update_r` : src/mpi/update_ghosts.cu:45-64, include/exanb/mpi/grid_update_ghosts.h:63-202 */
 int xnb_ghost_update_all(xnb_ctx*, void* stream);
 int xnb_ghost_update_r(xnb_ctx*, void* stream);
 /* ops `amr_grid_pairs` + `chunk_neighbors` : src/particle_neighbors/chunk_neighbors.cpp:48-74,
    include/exanb/particle_neighbors/chunk_neighbors_execute.h:40-423 (K2).  Config = build_particle_offset, chunk 1. */
-int xnb_chunk_neighbors(xnb_ctx*, void* stream);
+int xnb_chunk_neighbors(xnb_ctx*, void* stream);   /* [host sync] (an overflowing build is re-run with more room) */
 /* op `zero_particle_force` : src/compute/zero_particle_force.cu:15-53                                           */
 int xnb_zero_particle_force(xnb_ctx*, int ghost, void* stream);
 /* The functor the pair sweeps are instantiated with (the functor concept: compute_pair_traits.h:24-74, restated in
@@ -194,13 +200,13 @@ int xnb_particle_displ_over(xnb_ctx*, uint64_t* count_out, void* stream);
 /* verlet_first_half + trigger_move_particles (numerical-scheme.msp:13-15, update-particles.msp:1-6) in one kernel (K4);
    the displacement count stays on the device until xnb_read_displ_over().                                       */
 int xnb_verlet_first_half(xnb_ctx*, double dt, void* stream);
-int xnb_read_displ_over(xnb_ctx*, uint64_t* count_out, void* stream);
+int xnb_read_displ_over(xnb_ctx*, uint64_t* count_out, void* stream);   /* [host sync] */
 /* compute_all_forces_energy of the LJ deck (input_lj_Ni.msp:88-92) + verlet_second_half in one kernel (K3):
    f = LJ(r) (written, not accumulated), a = f/m[type], v += a*dt/2.  dt_half_kick = 0 skips the kick.           */
 int xnb_force_and_second_half(xnb_ctx*, double epsilon, double sigma, double rcut, double dt_half_kick, void* stream);
 /* whole `numerical_scheme` loop (numerical-scheme.msp:21-25 + check_and_update_particles): nsteps iterations.
    Synchronises once per step to read the rebuild trigger (the reference does an MPI_Allreduce there).           */
-int xnb_run_steps(xnb_ctx*, int nsteps, double dt, double epsilon, double sigma, double rcut, void* stream, int* rebuilds_out);
+int xnb_run_steps(xnb_ctx*, int nsteps, double dt, double epsilon, double sigma, double rcut, void* stream, int* rebuilds_out);   /* [host sync] once per step */
 /* one iteration of the same loop for a caller whose particles live in HOST memory, as the reference's Grid does
    (core/grid.h:57-688, host / managed allocations): uploads r,v of the inner particles (current device order; NULL
    = keep the device copy), runs one step exactly as xnb_run_steps(1) does, and returns r,v,f (NULL = not wanted).
@@ -218,7 +224,7 @@ int xnb_first_iteration(xnb_ctx*, double epsilon, double sigma, double rcut, voi
 /* ---- oracle-defined observables (unpinned by the reference) ---------------------------------- */
 /* E = 1/2 sum_ij e_ij (un-shifted lj_compute_energy, lennard_jones.cu:46-56), W = -1/2 sum dr (x) f, inner atoms;
    ekin = sum 1/2 m v^2.  Synchronous, local to this rank.                                                       */
-int xnb_energy_virial(xnb_ctx*, double epsilon, double sigma, double rcut, double* epot, double virial[6], double* ekin, void* stream);
+int xnb_energy_virial(xnb_ctx*, double epsilon, double sigma, double rcut, double* epot, double virial[6], double* ekin, void* stream);   /* [host sync] */
 
 /* ---- views / downloads of derived data -------------------------------------------------------------------- */
 /* GridChunkNeighbors (src/particle_neighbors/include/exanb/particle_neighbors/chunk_neighbors.h:40-120):
