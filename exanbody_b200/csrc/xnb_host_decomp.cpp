@@ -166,7 +166,12 @@ extern "C" int xnb_host_load_balance_rcb(const int64_t grid_dims[3], const doubl
                                          double* block_cost)
 {
   if (!grid_dims || !cell_costs || !start || !end || nranks < 1 || rank < 0 || rank >= nranks || grid_dims[0] < 1 || grid_dims[1] < 1 || grid_dims[2] < 1) return XNB_ERR_INVALID;
+  // costs must be finite and non-negative (a NaN would poison every comparison of the bisection)
+  const int64_t nd = grid_dims[0] * grid_dims[1] * grid_dims[2];
+  for (int64_t q = 0; q < nd; q++) if (!(cell_costs[q] >= 0.0) || !std::isfinite(cell_costs[q])) return XNB_ERR_INVALID;
   const xnb::Block b = xnb::load_balance_rcb(grid_dims, cell_costs, (size_t)nranks, (size_t)rank);
+  // "Assigned grid block is empty" is a fatal error of the reference (load_balance_rcb.cpp:410-411,457): more ranks than cells along the cuts
+  for (int d = 0; d < 3; d++) if (b.e[d] <= b.s[d]) return XNB_ERR_INVALID;
   double cost = 0.0;
   for (int64_t k = b.s[2]; k < b.e[2]; k++) for (int64_t j = b.s[1]; j < b.e[1]; j++) for (int64_t i = b.s[0]; i < b.e[0]; i++) cost += cell_costs[(k * grid_dims[1] + j) * grid_dims[0] + i];
   for (int d = 0; d < 3; d++) { start[d] = b.s[d]; end[d] = b.e[d]; }

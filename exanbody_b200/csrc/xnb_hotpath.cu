@@ -292,6 +292,7 @@ int ensure_grid(xnb_ctx* c)
   const int gap = (int)std::ceil(c->nbh_dist / c->cs);           // amr_grid_algorithm.h:451
   if (gap > 15) return c->fail(XNB_ERR_CAPACITY, "neighbour cell offset beyond +-15 cells (chunk_neighbors.h:140-142)");
   const Block& b = c->blocks[(size_t)c->rank];
+  for (int d = 0; d < 3; d++) if (b.e[d] <= b.s[d]) return c->fail(XNB_ERR_INVALID, "Assigned grid block is empty (more ranks than cells along a cut)");
   int64_t ncell = 1;
   for (int d = 0; d < 3; d++)
   {
@@ -1689,10 +1690,12 @@ int xnb_read_displ_over(xnb_ctx* c, uint64_t* count_out, void* stream)
   if (!c) return XNB_ERR_INVALID;
   CK(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
-  // MPI_Allreduce(SUM, 1 x u64) of particle_displ_over.cu:174
-  if (c->nranks > 1) { if (!c->comm) return c->fail(XNB_ERR_NCCL, "no communicator"); NK(g_nccl.AllReduce(c->d_scalars64.p, c->d_scalars64.p, 1, nccl_uint64, nccl_sum, c->comm, st)); }
+  // MPI_Allreduce(SUM, 1 x u64) of particle_displ_over.cu:174, into a slot of its own: the local count stays intact, so calling this twice
+  // after one xnb_verlet_first_half returns the same number
+  const unsigned long long* src = c->d_scalars64.p;
+  if (c->nranks > 1) { if (!c->comm) return c->fail(XNB_ERR_NCCL, "no communicator"); NK(g_nccl.AllReduce(c->d_scalars64.p, c->d_scalars64.p + 7, 1, nccl_uint64, nccl_sum, c->comm, st)); src = c->d_scalars64.p + 7; }
   unsigned long long v = 0;
-  int rc = read_back(c, c->d_scalars64.p, 1, &v, st); if (rc) return rc;
+  int rc = read_back(c, src, 1, &v, st); if (rc) return rc;
   if (count_out) *count_out = v;
   return XNB_OK;
 }

@@ -188,3 +188,25 @@ def test_simple_cost_model_and_the_chain_to_blocks():
         static.append(c3[s[2]:e[2], s[1]:e[1], s[0]:e[0]].sum())
     static = np.array(static)
     assert (static.max() - static.mean()) / static.mean() > 0.5                                 # the cost-blind blocks do not
+
+
+def test_bad_costs_and_empty_blocks_are_errors():
+    """the reference aborts with 'Assigned grid block is empty' (load_balance_rcb.cpp:410-411,457); NaN / negative costs would poison the bisection"""
+    import pytest
+    def n_errors(dims, n):
+        bad = 0
+        for r in range(n):
+            try:
+                capi.load_balance_rcb(dims, np.ones(int(np.prod(dims))), n, r)
+            except Exception:
+                bad += 1
+        return bad
+    assert n_errors((1, 1, 1), 2) == 1              # more ranks than cells: the rank left without a cell gets an error, not an empty block
+    assert n_errors((3, 3, 3), 64) >= 64 - 27
+    assert n_errors((4, 4, 4), 8) == 0
+    bad = np.ones(64); bad[5] = np.nan
+    with pytest.raises(Exception):
+        capi.load_balance_rcb((4, 4, 4), bad, 2, 0)
+    bad[5] = -1.0
+    with pytest.raises(Exception):
+        capi.load_balance_rcb((4, 4, 4), bad, 2, 0)
