@@ -1159,14 +1159,14 @@ static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
   }
   std::vector<ClCand> cands = cl_tile_candidates(c, lo, hi, gap);
   const int n1 = 2 * gap + 1;
-  const bool u8 = mcc <= 255 && n1 * n1 * n1 <= 128 && !env_flag("XNB_NBH_U16");      // byte list areas
+  if (n1 * n1 * n1 > 128) return XNB_OK;                    // byte lists: a group header holds 0x80 | neighbour slot -> two-pass build
+  const bool u8 = true;
   if (mcc + 3u > 32u * NBH_CELL_BLOCKS && !env_flag("XNB_NBH_FORCE_BITS")) return nbh_big_run(c, mode, st, done);   // a neighbour cell would need more accept masks than k_nbh_bits keeps in registers
   static bool attr_done_dev[XNB_MAX_DEVICES] = {};
   if (!attr_done_dev[c->device % XNB_MAX_DEVICES])
   {
-    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_nbh_bits<true>));
-    CK(cudaFuncSetAttribute(k_nbh_bits<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
-    CK(cudaFuncSetAttribute(k_nbh_bits<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_nbh_bits));
+    CK(cudaFuncSetAttribute(k_nbh_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
     attr_done_dev[c->device % XNB_MAX_DEVICES] = true;
   }
   uint32_t* counters = c->d_scalars32.p + 64;                  // NB_U32_COUNT u32
@@ -1213,8 +1213,7 @@ static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
       NbhBitsOut o{c->pool.p, c->cell_stream.p, c->stream_size.p, c->cell_stream_bytes.p, c->stream_off.p, c->cl_groups.p, reinterpret_cast<uint2*>(c->cl_rows.p),
                    counters, totals};
       if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh_bits mode %d tiles %dx%dx%d cap %d gmax %d cap_l %d u8 %d warps %d trips %d slot_words %u smem %zu blocks %u (max cell %u)\n", mode, tp.ti, tp.tj, tp.tk, tp.cap, tp.gmax, cap_l, (int)u8, nwarp, c->nb_cap_trips, c->nbh_slot_words, smem, blocks, mcc);
-      if (u8) k_nbh_bits<true><<<blocks, 32 * nwarp, smem, st>>>(g, tp, bp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
-      else    k_nbh_bits<false><<<blocks, 32 * nwarp, smem, st>>>(g, tp, bp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
+      k_nbh_bits<<<blocks, 32 * nwarp, smem, st>>>(g, tp, bp, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
       c->launches++; CK(cudaGetLastError());
       uint32_t h[NB_U32_COUNT]; unsigned long long tot[3];
       {

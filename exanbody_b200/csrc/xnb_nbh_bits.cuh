@@ -175,14 +175,14 @@ template <class LT> XNB_DEVINL void nb_sts(uint32_t a, uint32_t v)
 // List areas: one per lane, cap_l elements of LT (u8 when cells hold < 256 particles and the neighbourhood has < 128 cells:
 // p_b and counts fit a byte, a group header is (0x80 | neighbour slot, n); else u16).  A list is kept in the reference's layout:
 // [groups][(cell slot, n, p_b x n) x groups].
-template <bool U8>
 __global__ void __launch_bounds__(NBH_BITS_MAX_THREADS, 2)
 k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
            const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
            const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
            NbhBitsOut out, uint32_t* __restrict__ err)
 {
-  typedef typename std::conditional<U8, uint8_t, uint16_t>::type LT;
+  typedef uint8_t LT;               // byte lists: p_b, counts (cells of < 96 staged particles) and slots (< 128 neighbour cells) fit a byte
+  constexpr bool U8 = true;
   constexpr uint32_t ES = (uint32_t)sizeof(LT);
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -192,7 +192,6 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
   __shared__ uint32_t s_stat[NB_U32_COUNT];
   __shared__ unsigned long long s_tot[3];
   __shared__ uint16_t s_enc[128];        // neighbour slot -> encoded cell index (chunk_neighbors.h:137-150)
-  __shared__ int16_t s_dh[128];          // neighbour slot -> halo index relative to the cell's own
   __shared__ uint32_t s_flag[32];        // group g: list lengths published
   const ClTile T = cl_tile(g, tp, (int)blockIdx.x);
   const ClTables tb = cl_tables(smem_raw, tp);
@@ -218,7 +217,6 @@ k_nbh_bits(GridP g, ClTileP tp, NbhBitsP bp,
     {
       const int ri = sl % n1 - gap, rj = (sl / n1) % n1 - gap, rk = sl / (n1 * n1) - gap;
       s_enc[sl] = (uint16_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint16_t)(ri + 16);
-      s_dh[sl] = (int16_t)((rk * T.HY + rj) * T.HX + ri);
     }
   const uint32_t n_tile = tb.tstart[T.tcells], n_halo = tb.hstart[T.NH];
   const uint32_t ngroups = (n_tile + 31u) >> 5;
