@@ -148,7 +148,7 @@ struct xnb_ctx
   DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0; DBuf<uint32_t> cl_tile_list;
   // ---- k_nbh_bits (xnb_nbh_bits.cuh): masks parked between its two phases, capacities that worked last time, lazily built ghost-cell lists
   int nb_cap_l = 0, nb_cap_trips = 0; bool ghost_lists = false;       // ghost_lists: the streams of the ghost cells are current
-  int nb_cap32 = 0;
+  int nb_cap32 = 0; DBuf<uint32_t> nb_scratch;          // k_nbh_big: accept masks parked between its count and fill passes
   struct NbGhostCfg { ClTileP tp{}; int cap_l = 0, cap32 = 0; bool have = false; } nb_ghost;
   cudaStream_t st_comm = nullptr; cudaEvent_t ev_pos = nullptr, ev_ghost = nullptr;      // halo exchange overlapped with the interior tiles
   int64_t n_nonempty_inner = 0;
@@ -1081,7 +1081,7 @@ static int nbh_big_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
   tp.gmax = std::max(tp.gmax, (int)((mcc + 31u) / 32u));
   int& cap32 = mode == 0 ? c->nb_cap32 : c->nb_ghost.cap32;
   // staged candidates of ONE plane of halo cells, every cell padded to a multiple of 32
-  if (cap32 == 0) cap32 = (int)std::min<double>((double)(n1 * n1) * (double)((mcc + 31u) & ~31u), (double)tp.cap / n1 * 1.10 + 32.0 * n1 * n1 + 31.0) & ~31;
+  cap32 = std::max(cap32, (int)std::min<double>((double)(n1 * n1) * (double)((mcc + 31u) & ~31u), (double)tp.cap / n1 * 1.10 + 32.0 * n1 * n1 + 31.0) & ~31);
   const unsigned blocks = (unsigned)((int64_t)tp.tiles_i * tp.tiles_j * tp.tiles_k);
   for (int attempt = 0; attempt < 6; attempt++)
   {
@@ -1102,7 +1102,11 @@ static int nbh_big_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
     bp.emit_rows = mode == 0 ? 1 : 0; bp.sel_mode = mode; bp.slot_words = (int)c->nbh_slot_words; bp.cap_trips = c->nb_cap_trips; bp.max_dist2 = c->nbh_dist * c->nbh_dist;
     NbhBitsOut o{c->pool.p, c->cell_stream.p, c->stream_size.p, c->cell_stream_bytes.p, c->stream_off.p, c->cl_groups.p, reinterpret_cast<uint2*>(c->cl_rows.p), counters, totals};
     if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh_big mode %d cap %d cap32 %d gmax %d trips %d slot_words %u smem %zu blocks %u (max cell %u)\n", mode, tp.cap, cap32, tp.gmax, c->nb_cap_trips, c->nbh_slot_words, smem, blocks, mcc);
-    k_nbh_big<<<blocks, 32 * nwarp, smem, st>>>(g, tp, bp, cap32, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
+    // scratch rows per group: every 32-candidate block of the neighbourhood could survive
+    const int scratch_rows = n1 * n1 * n1 * (int)((mcc + 31u) / 32u + 1u);
+    if (n1 * n1 * n1 * 16 > (1 << 20) || (mcc + 31u) / 32u + 1u > 16u) return XNB_OK;      // tag = slot * 16 + block
+    CK(c->nb_scratch.ensure((size_t)blocks * tp.gmax * scratch_rows * 33 + 64, 0, 1.05));
+    k_nbh_big<<<blocks, 32 * nwarp, smem, st>>>(g, tp, bp, cap32, c->nb_scratch.p, scratch_rows, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
     c->launches++; CK(cudaGetLastError());
     uint32_t h[NB_U32_COUNT]; unsigned long long tot[3];
     {
@@ -1125,7 +1129,7 @@ static int nbh_big_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
       c->pool_used = (int64_t)tot[1]; c->max_neighbors = h[NB_MAX_NBH]; c->n_nonempty_inner = h[NB_NONEMPTY]; c->max_stream = h[NB_MAX_STREAM];
       c->avg_stream = c->n_inner ? (double)tot[2] / (double)c->n_inner : 0.0;
       c->have_nbh = true; c->ghost_lists = g.gl == 0;
-      c->nb_cap_trips = std::min(c->nb_cap_trips, (int)h[NB_TRIPS] + 8);
+      c->nb_cap_trips = std::min(c->nb_cap_trips, (int)(h[NB_TRIPS] * 1.15) + 8);      // room for the next rebuild's longest list: a launch that overflows is run twice
       int rc = cl_finish(c, tp, false, blocks, h[NB_ROWS], (int64_t)tot[0], h[NB_GMAX], st); if (rc) return rc;
     }
     else
@@ -1239,7 +1243,7 @@ static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
         c->pool_used = (int64_t)tot[1]; c->max_neighbors = h[NB_MAX_NBH]; c->n_nonempty_inner = h[NB_NONEMPTY]; c->max_stream = h[NB_MAX_STREAM];
         c->avg_stream = c->n_inner ? (double)tot[2] / (double)c->n_inner : 0.0;
         c->have_nbh = true; c->ghost_lists = g.gl == 0;
-        c->nb_cap_trips = std::min(c->nb_cap_trips, (int)h[NB_TRIPS] + 4);       // rows of a group closer together next time
+        c->nb_cap_trips = std::min(c->nb_cap_trips, (int)(h[NB_TRIPS] * 1.1) + 4);       // rows of a group closer together next time, with room for the next rebuild
         int rc = cl_finish(c, tp, false, blocks, h[NB_ROWS], (int64_t)tot[0], h[NB_GMAX], st); if (rc) return rc;
       }
       else

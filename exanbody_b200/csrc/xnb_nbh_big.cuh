@@ -15,9 +15,10 @@
 //     space.  Every block gets its bounding box at staging; a group of 32 tile particles (one warp, lane = particle) skips the blocks
 //     whose box is farther than the list radius from the group's own box -- the job the reference gives its sub-cell pair cache.  (With
 //     an arbitrary in-cell order the boxes are large and nothing is skipped: correct, just slower.)
-//   * two passes over the surviving blocks instead of a list in shared memory: COUNT (accept bits -> per neighbour cell counts, list
-//     length), positions of the lists in the cell's stream (scan + the lengths earlier groups published), FILL (the same
-//     classification again, bits expanded straight into the stream and into the lane's column of the compiled rows).
+//   * two passes instead of a list in shared memory: COUNT (accept bits -> per neighbour cell counts, list length; the masks of the
+//     blocks that accept anything are parked in L2-resident scratch, 128 bytes per block and group), positions of the lists in the
+//     cell's stream (scan + the lengths of the groups in front), FILL (the parked masks expanded straight into the stream and into
+//     the lane's column of the compiled rows: no second staging, no second classification).
 #pragma once
 #include "xnb_nbh_bits.cuh"
 
@@ -30,6 +31,38 @@ __host__ __device__ inline size_t nbig_smem_bytes(int nh_max, int tc_max, int gm
   return (((size_t)(2 * nh_max + 2 * tc_max + 2) * 4 + 15) & ~(size_t)15) + ((((size_t)gmax * 64) + 15) & ~(size_t)15) + ((((size_t)nh_max + 1) * 4 + 15) & ~(size_t)15) +
          (size_t)(cap32 / 32) * 32 + (size_t)nwarp * (size_t)nslots * 64 + (size_t)cap32 * 16 + 64;
 }
+
+// u16 words of one particle's list, written in order through a 64-bit register: aligned 8-byte stores for everything but the words
+// that share an 8-byte line with a neighbouring list (first and last line: 2-byte stores).  A quarter of the store requests of
+// word-by-word writing, which is what bounds the fill pass (234 M list words per build at C4).
+struct NbStreamWriter
+{
+  uint2* sp; uint32_t lo, hi, sfill, a0; bool first;
+  XNB_DEVINL void begin(uint16_t* dst)
+  {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+    a0 = (uint32_t)((a >> 1) & 3u); sp = reinterpret_cast<uint2*>(a & ~(uintptr_t)7); lo = hi = 0u; sfill = a0; first = true;
+  }
+  XNB_DEVINL void push(uint32_t w)
+  {
+    lo = __funnelshift_r(lo, hi, 16); hi = __byte_perm(hi, w, 0x5432); sfill++;
+    if ((sfill & 3u) == 0u)
+    {
+      if (first) { uint16_t* p = reinterpret_cast<uint16_t*>(sp); const unsigned long long v = ((unsigned long long)hi << 32) | lo; for (uint32_t q = a0; q < 4u; q++) p[q] = (uint16_t)(v >> (16u * q)); first = false; }
+      else *sp = make_uint2(lo, hi);
+      sp++;
+    }
+  }
+  XNB_DEVINL void end()
+  {
+    const uint32_t rem = sfill & 3u, base = first ? a0 : 0u;
+    if (rem <= base) return;
+    const uint32_t npend = rem - base;
+    const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+    uint16_t* p = reinterpret_cast<uint16_t*>(sp);
+    for (uint32_t i = 0; i < npend; i++) p[base + i] = (uint16_t)(v >> (16u * (4u - npend + i)));
+  }
+};
 
 // accept bits of lane's particle against the 32 staged candidates of block `bb` (staged index of its first candidate), ambiguity resolved
 XNB_DEVINL uint32_t nbig_classify(const NbPair* __restrict__ S, uint32_t bb, const NbSelf& me, bool own, uint32_t pa, uint32_t pb0, float zc, float band2,
@@ -54,7 +87,7 @@ XNB_DEVINL uint32_t nbig_classify(const NbPair* __restrict__ S, uint32_t bb, con
 }
 
 __global__ void __launch_bounds__(NBH_BIG_MAX_THREADS, 2)
-k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32,
+k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32, uint32_t* __restrict__ scratch, int scratch_rows,
           const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
           const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
           NbhBitsOut out, uint32_t* __restrict__ err)
@@ -190,8 +223,12 @@ k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32,
     __syncthreads();
   };
 
-  // ---- COUNT pass, plane by plane
-  uint32_t ngrp = 0u, ncand = 0u;
+  // ---- COUNT pass, plane by plane.  The accept masks of the surviving blocks are parked in this group's scratch rows (row n = the 32
+  // lanes' masks of the n-th surviving block, one coalesced 128-byte store; tag = slot * 16 + block index behind the rows): the FILL
+  // pass reads them back from L2 instead of staging and classifying everything again
+  uint32_t ngrp = 0u, ncand = 0u, n_surv = 0u;
+  uint32_t* const my_rows = scratch + ((size_t)blockIdx.x * (size_t)tp.gmax + (size_t)min(warp, tp.gmax - 1)) * (size_t)scratch_rows * 33u;
+  uint32_t* const my_tags = my_rows + (size_t)scratch_rows * 32u;
   for (int rk = -gap; rk <= gap; rk++)
   {
     const int bk = ck0 + rk;
@@ -216,6 +253,9 @@ k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32,
           if (far_block((hp >> 5) + k)) continue;
           const uint32_t mk = nbig_classify(S, hp + 32u * k, me, own, pa, 32u * k, zc, band2, gfirst, gself, bp.max_dist2, rx, ry, rz, &s_stat[NB_AMBIGUOUS]);
           cntc += (uint32_t)__popc(mk);
+          if (!__any_sync(FULL, mk != 0u)) continue;                 // nobody accepts anything of this block
+          if (n_surv < (uint32_t)scratch_rows) { my_rows[n_surv * 32u + (uint32_t)lane] = mk; if (lane == 0) my_tags[n_surv] = (uint32_t)slot * 16u + k; }
+          n_surv++;
         }
       }
       cnts[slot * 32] = (uint16_t)cntc;
@@ -247,55 +287,54 @@ k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32,
     for (uint32_t u = (uint32_t)lane; u < grp * 32u; u += 32u) carry += (uint32_t)plen[u];
     off = x - len + __reduce_add_sync(FULL, carry);
     const bool fits = 2u * (nA + 1u) + off + len <= (uint32_t)bp.slot_words;
-    const bool rows_ok = !bp.emit_rows || trips <= (uint32_t)bp.cap_trips;
+    const bool rows_ok = (!bp.emit_rows || trips <= (uint32_t)bp.cap_trips) && n_surv <= (uint32_t)scratch_rows;
+    if (n_surv > (uint32_t)scratch_rows && lane == 0) atomicOr(&out.counters[NB_OVERFLOW], 8u);
     fill = __all_sync(FULL, fits || !active) && rows_ok;
     if (!fill && lane == 0) { s_ovf = 1u; if (bp.emit_rows) gt[grp] = make_uint2(row0, 0u); }
   }
-  // ---- FILL pass: the same planes, the same blocks, the same bits; straight into the stream and the lane's column of the rows
+  // ---- FILL pass: the parked masks, block by block; bits expanded straight into the stream and the lane's column of the rows
   uint16_t* dst = lists + off;
   uint2* colp = col;
   uint32_t buf_lo = 0u, buf_hi = 0u, r = 0u;
   const uint32_t rows_on = bp.emit_rows ? 0u : 4u;
-  if (fill && active) { reinterpret_cast<uint32_t*>(base)[pa] = off + 1u; if (pa == nA - 1u) reinterpret_cast<uint32_t*>(base)[nA] = off + len + 1u; *dst = (uint16_t)ngrp; }
-  dst++;
-  for (int rk = -gap; rk <= gap; rk++)
+  NbStreamWriter sw; sw.begin(dst);
+  if (fill && active) { reinterpret_cast<uint32_t*>(base)[pa] = off + 1u; if (pa == nA - 1u) reinterpret_cast<uint32_t*>(base)[nA] = off + len + 1u; sw.push(ngrp); }
+  if (fill)
   {
-    const int bk = ck0 + rk;
-    if (bk < 0 || bk >= g.dims[2]) continue;
-    const int z = bk - T.bz0;
-    stage_plane(z);
-    if (!fill) continue;
-    const uint32_t pl0 = hpad[z * HXY];
-    int slot = (rk + gap) * n1 * n1;
-    for (int rj = -gap; rj <= gap; rj++) for (int ri = -gap; ri <= gap; ri++, slot++)
+    int prev_slot = -1; uint32_t hs8 = 0u;
+    // tags 32 at a time (one coalesced load, then shuffles); the masks one block ahead of the expansion
+    uint32_t tagv = 0u, mk_next = n_surv ? my_rows[(uint32_t)lane] : 0u;
+    for (uint32_t n = 0; n < n_surv; n++)
     {
-      const int bi = ci0 + ri, bj = cj0 + rj;
-      if (!(bi >= 0 && bi < g.dims[0] && bj >= 0 && bj < g.dims[1])) continue;
-      const uint32_t cntc = cnts[slot * 32];
-      if (!__any_sync(FULL, cntc != 0u)) continue;
-      if (cntc) { dst[0] = (uint16_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint16_t)(ri + 16); dst[1] = (uint16_t)cntc; dst += 2; }
-      const int hB = hA + (rk * T.HY + rj) * T.HX + ri;
-      const uint32_t hp = hpad[hB] - pl0, nblk = (hpad[hB + 1] - hpad[hB]) >> 5;
-      const bool own = rk == 0 && rj == 0 && ri == 0;
-      const uint32_t gfirst = tb.hfirst[hB], hs8 = tb.hstart[hB] << 3;
-      for (uint32_t k = 0; k < nblk; k++)
+      if ((n & 31u) == 0u) tagv = n + (uint32_t)lane < n_surv ? my_tags[n + (uint32_t)lane] : 0u;
+      const uint32_t tag = __shfl_sync(FULL, tagv, (int)(n & 31u));
+      const uint32_t mk_cur = mk_next;
+      if (n + 1u < n_surv) mk_next = my_rows[(n + 1u) * 32u + (uint32_t)lane];
+      const int slot = (int)(tag >> 4); const uint32_t k = tag & 15u;
+      if (slot != prev_slot)
       {
-        if (far_block((hp >> 5) + k)) continue;
-        uint32_t xm = __brev(nbig_classify(S, hp + 32u * k, me, own, pa, 32u * k, zc, band2, gfirst, gself, bp.max_dist2, rx, ry, rz, nullptr));
-        const uint32_t pb0 = 32u * k, hs8k = hs8 + 256u * k;
-        while (xm)
-        {
-          const uint32_t b = (uint32_t)__clz((int)xm);
-          xm ^= 0x80000000u >> b;
-          *dst++ = (uint16_t)(pb0 + b);
-          buf_lo = __funnelshift_r(buf_lo, buf_hi, 16);
-          buf_hi = __byte_perm(buf_hi, hs8k + (b << 3), 0x5432);
-          r++;
-          if ((r & 3u) == rows_on) { *colp = make_uint2(buf_lo, buf_hi); colp += 32; }
-        }
+        // next neighbour cell: its header (cell code, count) for the lanes that list something of it
+        prev_slot = slot;
+        const int ri = slot % n1 - gap, rj = (slot / n1) % n1 - gap, rk = slot / (n1 * n1) - gap;
+        const uint32_t cntc = cnts[slot * 32];
+        if (cntc) { sw.push((uint32_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint32_t)(ri + 16)); sw.push(cntc); }
+        hs8 = tb.hstart[hA + (rk * T.HY + rj) * T.HX + ri] << 3;
+      }
+      uint32_t xm = __brev(mk_cur);
+      const uint32_t pb0 = 32u * k, hs8k = hs8 + 256u * k;
+      while (xm)
+      {
+        const uint32_t b = (uint32_t)__clz((int)xm);
+        xm ^= 0x80000000u >> b;
+        sw.push(pb0 + b);
+        buf_lo = __funnelshift_r(buf_lo, buf_hi, 16);
+        buf_hi = __byte_perm(buf_hi, hs8k + (b << 3), 0x5432);
+        r++;
+        if ((r & 3u) == rows_on) { *colp = make_uint2(buf_lo, buf_hi); colp += 32; }
       }
     }
   }
+  if (fill && active) sw.end();
   if (fill && bp.emit_rows)
   {
     const uint32_t pad = self << 3, pw = pad | (pad << 16);
