@@ -1078,7 +1078,7 @@ static int nbh_big_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
   const ClTileP& prev = mode == 0 ? c->cl.tp : c->nb_ghost.tp;
   const bool have_prev = mode == 0 ? (c->cl.valid && !c->cl.ghost) : c->nb_ghost.have;
   if (have_prev && prev.ti == 1 && prev.tj == 1 && prev.tk == 1) { tp.gmax = std::max(tp.gmax, prev.gmax); tp.cap = std::max(tp.cap, prev.cap); }
-  tp.gmax = std::max(tp.gmax, (int)((mcc + 31u) / 32u));
+  tp.gmax = std::max(tp.gmax, (int)((mcc + 63u) / 32u));      // one group of slack (see scratch_rows)
   int& cap32 = mode == 0 ? c->nb_cap32 : c->nb_ghost.cap32;
   // staged candidates of ONE plane of halo cells, every cell padded to a multiple of 32
   cap32 = std::max(cap32, (int)std::min<double>((double)(n1 * n1) * (double)((mcc + 31u) & ~31u), (double)tp.cap / n1 * 1.10 + 32.0 * n1 * n1 + 31.0) & ~31);
@@ -1103,8 +1103,9 @@ static int nbh_big_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
     NbhBitsOut o{c->pool.p, c->cell_stream.p, c->stream_size.p, c->cell_stream_bytes.p, c->stream_off.p, c->cl_groups.p, reinterpret_cast<uint2*>(c->cl_rows.p), counters, totals};
     if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh_big mode %d cap %d cap32 %d gmax %d trips %d slot_words %u smem %zu blocks %u (max cell %u)\n", mode, tp.cap, cap32, tp.gmax, c->nb_cap_trips, c->nbh_slot_words, smem, blocks, mcc);
     // scratch rows per group: every 32-candidate block of the neighbourhood could survive
-    const int scratch_rows = n1 * n1 * n1 * (int)((mcc + 31u) / 32u + 1u);
-    if (n1 * n1 * n1 * 16 > (1 << 20) || (mcc + 31u) / 32u + 1u > 16u) return XNB_OK;      // tag = slot * 16 + block
+    // (two blocks of slack per cell: the occupancy of the fullest cell changes from rebuild to rebuild and a reallocation costs milliseconds)
+    const int scratch_rows = n1 * n1 * n1 * (int)std::min<uint32_t>((mcc + 95u) / 32u + 1u, 16u);
+    if ((mcc + 31u) / 32u > 16u) return XNB_OK;      // tag = slot * 16 + block
     CK(c->nb_scratch.ensure((size_t)blocks * tp.gmax * scratch_rows * 33 + 64, 0, 1.05));
     k_nbh_big<<<blocks, 32 * nwarp, smem, st>>>(g, tp, bp, cap32, c->nb_scratch.p, scratch_rows, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
     c->launches++; CK(cudaGetLastError());
