@@ -5,6 +5,7 @@
 #include "xnb_sweep_cl.cuh"
 #include "xnb_nbh_bits.cuh"
 #include "xnb_nbh_big.cuh"
+#include "xnb_sweep_pl.cuh"
 #include "xnb_pair_generic.cuh"
 #include "xnb_host_decomp.hpp"
 
@@ -142,13 +143,14 @@ struct xnb_ctx
   bool nbh_half_symmetric = false, nbh_skip_ghosts = false;       // ChunkNeighborsConfig (xnb_set_chunk_neighbors_config)
   int nbh_cap_l = 0; uint32_t nbh_slot_words = 0; bool nbh_full_cap = false;   // capacities of the tiled build (grow on demand)
   // ---- compiled lists of the pair sweep (xnb_sweep_cl.cuh): derived from the streams after every rebuild
-  struct ClCfg { bool valid = false, ghost = false; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; int64_t candidates = 0;
+  struct ClCfg { bool valid = false, ghost = false; int planes = 0, cap_pl = 0; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; int64_t candidates = 0;
                  unsigned n_interior = 0, n_boundary = 0; };    // tiles whose halo box holds no ghost cell / the others (cl_tile_list: interior first)
   ClCfg cl;
   DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0; DBuf<uint32_t> cl_tile_list;
   // ---- k_nbh_bits (xnb_nbh_bits.cuh): masks parked between its two phases, capacities that worked last time, lazily built ghost-cell lists
   int nb_cap_l = 0, nb_cap_trips = 0; bool ghost_lists = false;       // ghost_lists: the streams of the ghost cells are current
-  int nb_cap32 = 0; DBuf<uint32_t> nb_scratch;          // k_nbh_big: accept masks parked between its count and fill passes
+  int nb_cap32 = 0, nb_scratch_rows = 0; DBuf<uint32_t> nb_scratch;
+  int64_t nbh_builds = 0, steps_since_nbh = 0, last_nbh_interval = -1;   // first-half kicks since the last neighbour build / between the last two builds (-1: unknown)          // k_nbh_big: accept masks parked between its count and fill passes
   struct NbGhostCfg { ClTileP tp{}; int cap_l = 0, cap32 = 0; bool have = false; } nb_ghost;
   cudaStream_t st_comm = nullptr; cudaEvent_t ev_pos = nullptr, ev_ghost = nullptr;      // halo exchange overlapped with the interior tiles
   int64_t n_nonempty_inner = 0;
@@ -993,7 +995,7 @@ static void cl_tile_grid(ClTileP& tp, const ClCand& k, const int lo[3], const in
 }
 
 // the sweep configuration once the compiled rows of tile grid `tp` exist (built by k_nbh_bits or by k_cl_compile)
-static int cl_finish(xnb_ctx* c, const ClTileP& tp, bool ghost, unsigned blocks, uint32_t rows, int64_t candidates, uint32_t max_groups, cudaStream_t st)
+static int cl_finish(xnb_ctx* c, const ClTileP& tp, bool ghost, unsigned blocks, uint32_t rows, int64_t candidates, uint32_t max_groups, cudaStream_t st, int planes = 0, int cap_pl = 0)
 {
   const GridP& g = c->g;
   const bool same_grid = c->cl.valid && c->cl.ghost == ghost && c->cl.blocks == blocks && c->cl.tp.ti == tp.ti && c->cl.tp.tj == tp.tj && c->cl.tp.tk == tp.tk &&
@@ -1005,6 +1007,8 @@ static int cl_finish(xnb_ctx* c, const ClTileP& tp, bool ghost, unsigned blocks,
   c->cl.var = c->cl.threads <= 576 ? 0 : 1;
   if (getenv("XNB_CL_VAR")) { const int v = env_int("XNB_CL_VAR"); if ((v == 2 && c->cl.threads <= 288) || (v == 3 && c->cl.threads <= 576)) c->cl.var = v; }   // experiments: 2 = three blocks per SM (<= 72 registers), 3 = one block per SM
   c->cl.smem = cl_sweep_smem_bytes(tp.nh_max, tp.tc_max, tp.cap, std::max(tp.gmax, c->cl.threads / 32));
+  c->cl.planes = planes; c->cl.cap_pl = cap_pl;
+  if (planes) { c->cl.threads = std::max(32 * (int)std::max<uint32_t>(max_groups, 1u), 64); c->cl.smem = pl_sweep_smem_bytes(tp.nh_max, tp.tc_max, cap_pl); }      // k_lj_sweep_pl: one warp per group, one plane of the halo staged at a time
   if (!same_grid)
   {
     // interior tiles: the halo box touches no ghost cell, so they can be swept while the halo exchange is in flight
@@ -1078,7 +1082,7 @@ static int nbh_big_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
   const ClTileP& prev = mode == 0 ? c->cl.tp : c->nb_ghost.tp;
   const bool have_prev = mode == 0 ? (c->cl.valid && !c->cl.ghost) : c->nb_ghost.have;
   if (have_prev && prev.ti == 1 && prev.tj == 1 && prev.tk == 1) { tp.gmax = std::max(tp.gmax, prev.gmax); tp.cap = std::max(tp.cap, prev.cap); }
-  tp.gmax = std::max(tp.gmax, (int)((mcc + 63u) / 32u));      // one group of slack (see scratch_rows)
+  tp.gmax = std::max(tp.gmax, (int)((mcc + 31u) / 32u));
   int& cap32 = mode == 0 ? c->nb_cap32 : c->nb_ghost.cap32;
   // staged candidates of ONE plane of halo cells, every cell padded to a multiple of 32
   cap32 = std::max(cap32, (int)std::min<double>((double)(n1 * n1) * (double)((mcc + 31u) & ~31u), (double)tp.cap / n1 * 1.10 + 32.0 * n1 * n1 + 31.0) & ~31);
@@ -1094,19 +1098,29 @@ static int nbh_big_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
     if (mode == 0)
     {
       if (c->nb_cap_trips == 0) c->nb_cap_trips = c->max_neighbors ? (int)(c->max_neighbors / 4 + 8) : (int)(c->nbh_slot_words / mcc / 4 + 8);
-      CK(c->cl_rows.ensure((size_t)blocks * tp.gmax * c->nb_cap_trips * 128 + 64, 0, 1.05));
-      CK(c->cl_groups.ensure((size_t)blocks * tp.gmax + 16));
+      CK(c->cl_rows.ensure((size_t)blocks * tp.gmax * c->nb_cap_trips * 128 + 64, 0, 1.3));
+      CK(c->cl_groups.ensure((size_t)blocks * tp.gmax + 16, 0, 1.3));
     }
     CK(cudaMemsetAsync(counters, 0, NB_U32_COUNT * 4, st)); CK(cudaMemsetAsync(totals, 0, 3 * 8, st));
     NbhBitsP bp{};
     bp.emit_rows = mode == 0 ? 1 : 0; bp.sel_mode = mode; bp.slot_words = (int)c->nbh_slot_words; bp.cap_trips = c->nb_cap_trips; bp.max_dist2 = c->nbh_dist * c->nbh_dist;
+    // compiled rows in one segment per z-plane of halo cells: the sweep then stages a third of the halo at a time (k_lj_sweep_pl)
+    // (plane segments are padded per plane: about a third more rows and a slower build; that pays when a list is swept several times,
+    // not when the system rebuilds on every step)
+    const bool planes = mode == 0 && gap == 1 && tp.gmax <= SWEEP_PL_MAX_THREADS / 32 && cap32 <= 8190 && !env_flag("XNB_CL_NO_PLANES") &&
+                        (c->last_nbh_interval < 0 || c->last_nbh_interval >= 4 || env_flag("XNB_CL_PLANES"));
+    bp.planes = planes ? 1 : 0; bp.cap_pl = cap32;
     NbhBitsOut o{c->pool.p, c->cell_stream.p, c->stream_size.p, c->cell_stream_bytes.p, c->stream_off.p, c->cl_groups.p, reinterpret_cast<uint2*>(c->cl_rows.p), counters, totals};
     if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh_big mode %d cap %d cap32 %d gmax %d trips %d slot_words %u smem %zu blocks %u (max cell %u)\n", mode, tp.cap, cap32, tp.gmax, c->nb_cap_trips, c->nbh_slot_words, smem, blocks, mcc);
     // scratch rows per group: every 32-candidate block of the neighbourhood could survive
     // (two blocks of slack per cell: the occupancy of the fullest cell changes from rebuild to rebuild and a reallocation costs milliseconds)
-    const int scratch_rows = n1 * n1 * n1 * (int)std::min<uint32_t>((mcc + 95u) / 32u + 1u, 16u);
+    // first build: every block of the neighbourhood could accept something; afterwards what the last build needed + 30 % (the rows of all
+    // resident groups should stay in L2: 128 bytes per row)
+    const int scratch_full = n1 * n1 * n1 * (int)std::min<uint32_t>((mcc + 95u) / 32u + 1u, 16u);
+    if (c->nb_scratch_rows == 0 || c->nb_scratch_rows > scratch_full) c->nb_scratch_rows = scratch_full;
+    const int scratch_rows = c->nb_scratch_rows;
     if ((mcc + 31u) / 32u > 16u) return XNB_OK;      // tag = slot * 16 + block
-    CK(c->nb_scratch.ensure((size_t)blocks * tp.gmax * scratch_rows * 33 + 64, 0, 1.05));
+    CK(c->nb_scratch.ensure((size_t)blocks * tp.gmax * scratch_rows * 33 + 64, 0, 1.3));
     k_nbh_big<<<blocks, 32 * nwarp, smem, st>>>(g, tp, bp, cap32, c->nb_scratch.p, scratch_rows, A.rx, A.ry, A.rz, c->cell_start.p, c->cell_count.p, o, c->d_scalars32.p);
     c->launches++; CK(cudaGetLastError());
     uint32_t h[NB_U32_COUNT]; unsigned long long tot[3];
@@ -1122,16 +1136,18 @@ static int nbh_big_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
     if ((int)h[NB_CAP] > tp.cap) { tp.cap = ((int)h[NB_CAP] + 1) & ~1; again = true; }
     if ((int)h[NB_SLOTS] > cap32) { cap32 = ((int)h[NB_SLOTS] + 31) & ~31; again = true; }
     if (h[NB_SLOT_WORDS] > c->nbh_slot_words) { c->nbh_slot_words = (uint32_t)(((size_t)(h[NB_SLOT_WORDS] * 1.12) + 64 + 7) & ~(size_t)7); again = true; }
-    if (mode == 0 && (int)h[NB_TRIPS] > c->nb_cap_trips) { c->nb_cap_trips = (int)h[NB_TRIPS] + 6; again = true; }
+    if (mode == 0 && (int)h[NB_TRIPS] > c->nb_cap_trips) { c->nb_cap_trips = (int)(h[NB_TRIPS] * 1.25) + 8; again = true; }      // lists that grow from rebuild to rebuild (a heating system) must not overflow every time
     if (h[NB_OVERFLOW] & 4u) return XNB_OK;
+    if ((int)h[NB_SURV] > scratch_rows) { c->nb_scratch_rows = (int)(h[NB_SURV] * 1.3) + 8; again = true; }
     if (again || h[NB_OVERFLOW]) { if (!again) return c->fail(XNB_ERR_CAPACITY, "chunk_neighbors: large-cell build reported an overflow it cannot size"); continue; }
+    c->nb_scratch_rows = std::min(scratch_rows, (int)(h[NB_SURV] * 1.3) + 8);
     if (mode == 0)
     {
       c->pool_used = (int64_t)tot[1]; c->max_neighbors = h[NB_MAX_NBH]; c->n_nonempty_inner = h[NB_NONEMPTY]; c->max_stream = h[NB_MAX_STREAM];
       c->avg_stream = c->n_inner ? (double)tot[2] / (double)c->n_inner : 0.0;
       c->have_nbh = true; c->ghost_lists = g.gl == 0;
       c->nb_cap_trips = std::min(c->nb_cap_trips, (int)(h[NB_TRIPS] * 1.15) + 8);      // room for the next rebuild's longest list: a launch that overflows is run twice
-      int rc = cl_finish(c, tp, false, blocks, h[NB_ROWS], (int64_t)tot[0], h[NB_GMAX], st); if (rc) return rc;
+      int rc = cl_finish(c, tp, false, blocks, h[NB_ROWS], (int64_t)tot[0], h[NB_GMAX], st, planes ? 1 : 0, cap32); if (rc) return rc;
     }
     else
     {
@@ -1345,6 +1361,8 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
   if ((rc = t_begin(c, XNB_T_NBH, st))) return rc;
   NbhOut out{c->nb_len.p, c->nb_cnt.p, c->nb_off.p, c->cell_stream.p};
 
+  if (c->nbh_builds > 0) c->last_nbh_interval = c->steps_since_nbh;      // (have_nbh is already false here: ghost_comm_scheme voided the lists)
+  c->steps_since_nbh = 0; c->nbh_builds++;
   // ---- tiled form (k_nbh_bits, one kernel: streams of the inner cells + compiled rows of the sweep) when a tile fits shared
   // memory, else the per-particle two-pass kernels.  Lists filtered by ChunkNeighborsConfig::half_symmetric / skip_ghosts are
   // built by the two-pass kernels.
@@ -1510,6 +1528,24 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
     const unsigned nb = part == 0 ? k.blocks : part == 1 ? k.n_interior : k.n_boundary;
     const uint32_t* tl = part == 0 ? nullptr : part == 1 ? c->cl_tile_list.p : c->cl_tile_list.p + k.n_interior;
     if (nb == 0) return XNB_OK;
+    if (k.planes)
+    {
+      // large cells: rows in plane segments, one plane of the halo staged at a time (xnb_sweep_pl.cuh)
+      static bool pl_attr_done_dev[XNB_MAX_DEVICES][2][2] = {};
+      auto& pl_attr_done = pl_attr_done_dev[c->device % XNB_MAX_DEVICES];
+      if (!pl_attr_done[MODE][EV ? 1 : 0])
+      {
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, (k_lj_sweep_pl<F, MODE, EV>)));
+        CK(cudaFuncSetAttribute((k_lj_sweep_pl<F, MODE, EV>), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes));
+        pl_attr_done[MODE][EV ? 1 : 0] = true;
+      }
+      if (part == 0 && (rc = t_begin(c, XNB_T_FORCE, st))) return rc;
+      k_lj_sweep_pl<F, MODE, EV><<<nb, k.threads, k.smem, st>>>(c->g, k.tp, k.cap_pl, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
+          fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, c->cl_groups.p,
+          reinterpret_cast<const uint2*>(c->cl_rows.p), EV ? c->ev_partials.p : nullptr, c->d_scalars32.p, skip_if_nonzero, tl);
+      c->launches++; CK(cudaGetLastError());
+      return part == 0 ? t_end(c, XNB_T_FORCE, st) : XNB_OK;
+    }
     if (k.var == 0) XNB_CL_LAUNCH(0); else if (k.var == 1) XNB_CL_LAUNCH(1); else if (k.var == 2) XNB_CL_LAUNCH(2); else XNB_CL_LAUNCH(3);
 #undef XNB_CL_LAUNCH
     c->launches++; CK(cudaGetLastError());
@@ -1721,6 +1757,7 @@ int xnb_verlet_first_half(xnb_ctx* c, double dt, void* stream)
   if (!c) return XNB_ERR_INVALID;
   CK(cudaSetDevice(c->device));
   c->amr_current = false;      // positions change: the sub-cell tables no longer bound them
+  c->steps_since_nbh++;
   cudaStream_t st = (cudaStream_t)stream;
   ParticlesP A = c->P(c->cur);
   int rc;

@@ -227,6 +227,7 @@ k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32, uint32_t* __restrict__ sc
   // lanes' masks of the n-th surviving block, one coalesced 128-byte store; tag = slot * 16 + block index behind the rows): the FILL
   // pass reads them back from L2 instead of staging and classifying everything again
   uint32_t ngrp = 0u, ncand = 0u, n_surv = 0u;
+  uint32_t ncand_pl[3] = {0u, 0u, 0u};                 // planes mode: list entries per z-plane of the halo (T.HZ <= 3: one neighbour layer)
   uint32_t* const my_rows = scratch + ((size_t)blockIdx.x * (size_t)tp.gmax + (size_t)min(warp, tp.gmax - 1)) * (size_t)scratch_rows * 33u;
   uint32_t* const my_tags = my_rows + (size_t)scratch_rows * 32u;
   for (int rk = -gap; rk <= gap; rk++)
@@ -260,11 +261,15 @@ k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32, uint32_t* __restrict__ sc
       }
       cnts[slot * 32] = (uint16_t)cntc;
       if (cntc) { ngrp++; ncand += cntc; }
+      if (bp.planes) { if (z == 0) ncand_pl[0] += cntc; else if (z == 1) ncand_pl[1] += cntc; else ncand_pl[2] += cntc; }
     }
   }
   const uint32_t len = active ? 1u + 2u * ngrp + ncand : 0u;
+  // rows of the group: one segment, or (planes) one segment per halo plane, each as long as its longest lane
+  uint32_t trips_pl[3] = {0u, 0u, 0u};
+  if (bp.planes) for (int q = 0; q < 3; q++) trips_pl[q] = __reduce_max_sync(FULL, (ncand_pl[q] + 3u) >> 2);
   const uint32_t my_trips = (ncand + 3u) >> 2;
-  const uint32_t trips = __reduce_max_sync(FULL, my_trips);
+  const uint32_t trips = bp.planes ? trips_pl[0] + trips_pl[1] + trips_pl[2] : __reduce_max_sync(FULL, my_trips);
   if (have_group)
   {
     const uint32_t mxc = __reduce_max_sync(FULL, ncand), csum = __reduce_add_sync(FULL, ncand);
@@ -288,6 +293,7 @@ k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32, uint32_t* __restrict__ sc
     off = x - len + __reduce_add_sync(FULL, carry);
     const bool fits = 2u * (nA + 1u) + off + len <= (uint32_t)bp.slot_words;
     const bool rows_ok = (!bp.emit_rows || trips <= (uint32_t)bp.cap_trips) && n_surv <= (uint32_t)scratch_rows;
+    if (lane == 0) atomicMax(&s_stat[NB_SURV], n_surv);
     if (n_surv > (uint32_t)scratch_rows && lane == 0) atomicOr(&out.counters[NB_OVERFLOW], 8u);
     fill = __all_sync(FULL, fits || !active) && rows_ok;
     if (!fill && lane == 0) { s_ovf = 1u; if (bp.emit_rows) gt[grp] = make_uint2(row0, 0u); }
@@ -301,7 +307,14 @@ k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32, uint32_t* __restrict__ sc
   if (fill && active) { reinterpret_cast<uint32_t*>(base)[pa] = off + 1u; if (pa == nA - 1u) reinterpret_cast<uint32_t*>(base)[nA] = off + len + 1u; sw.push(ngrp); }
   if (fill)
   {
-    int prev_slot = -1; uint32_t hs8 = 0u;
+    int prev_slot = -1, cur_z = 0; uint32_t hs8 = 0u, seg_row = 0u;
+    const uint32_t pad_pl = (uint32_t)bp.cap_pl << 3, pw_pl = pad_pl | (pad_pl << 16);
+    // planes: close the segment of plane cur_z (pending word, then sentinel pads up to the group's trip count of that plane)
+    auto close_plane = [&]() {
+      while (r & 3u) { buf_lo = __funnelshift_r(buf_lo, buf_hi, 16); buf_hi = __byte_perm(buf_hi, pad_pl, 0x5432); r++; if ((r & 3u) == 0u) { *colp = make_uint2(buf_lo, buf_hi); colp += 32; } }
+      for (uint32_t kq = r >> 2; kq < trips_pl[cur_z]; kq++) { *colp = make_uint2(pw_pl, pw_pl); colp += 32; }
+      seg_row += trips_pl[cur_z]; colp = col + (size_t)seg_row * 32u; r = 0u; cur_z++;
+    };
     // tags 32 at a time (one coalesced load, then shuffles); the masks one block ahead of the expansion
     uint32_t tagv = 0u, mk_next = n_surv ? my_rows[(uint32_t)lane] : 0u;
     for (uint32_t n = 0; n < n_surv; n++)
@@ -319,6 +332,12 @@ k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32, uint32_t* __restrict__ sc
         const uint32_t cntc = cnts[slot * 32];
         if (cntc) { sw.push((uint32_t)((((rk + 16) << 5) + (rj + 16)) << 5) + (uint32_t)(ri + 16)); sw.push(cntc); }
         hs8 = tb.hstart[hA + (rk * T.HY + rj) * T.HX + ri] << 3;
+        if (bp.planes)
+        {
+          const int z = ck0 + rk - T.bz0;
+          if (bp.emit_rows) while (cur_z < z) close_plane();
+          hs8 -= tb.hstart[z * HXY] << 3;                      // indices relative to the plane's first particle
+        }
       }
       uint32_t xm = __brev(mk_cur);
       const uint32_t pb0 = 32u * k, hs8k = hs8 + 256u * k;
@@ -333,9 +352,14 @@ k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32, uint32_t* __restrict__ sc
         if ((r & 3u) == rows_on) { *colp = make_uint2(buf_lo, buf_hi); colp += 32; }
       }
     }
+    if (bp.planes && bp.emit_rows)
+    {
+      while (cur_z < T.HZ) close_plane();                    // the open segment and the planes behind it
+      if (lane == 0) { gt[grp] = make_uint2(row0, trips_pl[0] | (trips_pl[1] << 10) | (trips_pl[2] << 20)); atomicAdd(&s_stat[NB_ROWS], trips); }
+    }
   }
   if (fill && active) sw.end();
-  if (fill && bp.emit_rows)
+  if (fill && bp.emit_rows && !bp.planes)
   {
     const uint32_t pad = self << 3, pw = pad | (pad << 16);
     while (r & 3u) { buf_lo = __funnelshift_r(buf_lo, buf_hi, 16); buf_hi = __byte_perm(buf_hi, pad, 0x5432); r++; if ((r & 3u) == 0u) *colp = make_uint2(buf_lo, buf_hi); }
@@ -364,6 +388,7 @@ k_nbh_big(GridP g, ClTileP tp, NbhBitsP bp, int cap32, uint32_t* __restrict__ sc
     atomicMax(&out.counters[NB_MAX_NBH], s_stat[NB_MAX_NBH]); atomicAdd(&out.counters[NB_NONEMPTY], s_stat[NB_NONEMPTY]);
     atomicMax(&out.counters[NB_MAX_CELL], s_stat[NB_MAX_CELL]); atomicMax(&out.counters[NB_MAX_STREAM], s_stat[NB_MAX_STREAM]);
     atomicMax(&out.counters[NB_TRIPS], s_stat[NB_TRIPS]); atomicAdd(&out.counters[NB_ROWS], s_stat[NB_ROWS]);
+    atomicMax(&out.counters[NB_SURV], s_stat[NB_SURV]);
     if (s_stat[NB_AMBIGUOUS]) atomicAdd(&out.counters[NB_AMBIGUOUS], s_stat[NB_AMBIGUOUS]);
     for (int q = 0; q < 3; q++) if (s_tot[q]) atomicAdd(&out.totals[q], s_tot[q]);
   }

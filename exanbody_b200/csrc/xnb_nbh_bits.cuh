@@ -39,12 +39,14 @@ struct NbhBitsP
   int sel_mode;          // 0: every tile cell is built; 1: only cells outside the inner range (ghost-cell lists, built lazily)
   int slot_words;        // stream capacity per cell (u16 words, multiple of 8)
   int cap_trips;         // rows per group in the compiled-list buffer (a group owns a fixed block of rows: no allocator)
+  int planes;            // k_nbh_big: 1 = the compiled rows of a group come in one segment per z-plane of halo cells (k_lj_sweep_pl)
+  int cap_pl;            // planes: the sentinel slot pads point at (= staging capacity of a plane in the sweep)
   double max_dist2;
 };
 
 // counters written by k_nbh_bits (u32): what it used and what it would have needed
 enum { NB_ROWS = 0, NB_GMAX = 1, NB_CAP = 2, NB_SLOTS = 3, NB_SLOT_WORDS = 4, NB_MAX_NBH = 5, NB_NONEMPTY = 6, NB_MAX_CELL = 7, NB_MAX_STREAM = 8,
-       NB_OVERFLOW = 9, NB_AMBIGUOUS = 10, NB_TRIPS = 11, NB_U32_COUNT = 12 };
+       NB_OVERFLOW = 9, NB_AMBIGUOUS = 10, NB_TRIPS = 11, NB_SURV = 12, NB_U32_COUNT = 13 };      // NB_SURV: k_nbh_big, most scratch rows a group needed
 // u64 totals: [0] list entries of the built particles [1] padded stream words of all built cells [2] of the inner cells among them
 
 XNB_DEVINL bool cl_cell_is_inner(const GridP& g, int ci, int cj, int ck)
