@@ -603,8 +603,9 @@ int xnb_get_sweep_info(const xnb_ctx* c, xnb_sweep_info* out)
 {
   if (!c || !out) return XNB_ERR_INVALID;
   memset(out, 0, sizeof *out);
-  out->compiled = c->cl.valid ? 1 : 0;
-  if (c->cl.valid)
+  const bool compiled = c->cl.valid && !env_flag("XNB_SWEEP_STREAMS");
+  out->compiled = compiled ? 1 : 0;
+  if (compiled)
   {
     out->tile[0] = c->cl.tp.ti; out->tile[1] = c->cl.tp.tj; out->tile[2] = c->cl.tp.tk;
     out->threads = c->cl.threads; out->blocks = c->cl.blocks; out->smem_bytes = (int64_t)c->cl.smem;
@@ -1509,8 +1510,9 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
   // does exactly that, silently); here it is an error: use xnb_lennard_jones_force_symmetric + xnb_update_force_from_ghost
   if (c->nbh_half_symmetric) return c->fail(XNB_ERR_INVALID, "the full-list pair sweep needs full lists: chunk_neighbors was configured half_symmetric");
   if (ghost && (rc = ensure_ghost_lists(c, st))) return rc;
-  if (c->cl.ghost != ghost || (!c->cl.valid && !env_flag("XNB_SWEEP_STREAMS"))) { if ((rc = cl_prepare(c, ghost, st))) return rc; c->cl.ghost = ghost; }
-  if (c->cl.valid)
+  const bool sweep_streams = env_flag("XNB_SWEEP_STREAMS");         // diagnostic: sweep the reference-format streams directly (k_lj_sweep)
+  if (!sweep_streams && (c->cl.ghost != ghost || !c->cl.valid)) { if ((rc = cl_prepare(c, ghost, st))) return rc; c->cl.ghost = ghost; }
+  if (c->cl.valid && !sweep_streams)
   {
     const xnb_ctx::ClCfg& k = c->cl;
     if (EV) { CK(c->ev_partials.ensure((size_t)k.blocks * 7 + 16)); if (evp_out) *evp_out = c->ev_partials.p; if (nblocks_out) *nblocks_out = k.blocks; }
@@ -1843,7 +1845,7 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
     CK(cudaMemcpyAsync(const_cast<unsigned long long*>(h_flag), c->d_scalars64.p, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(c->ev_flag, st));
     size_t force_scopes = c->tpool[XNB_T_FORCE].used;
-    const bool overlap = speculate && c->nranks > 1 && c->cl.valid && !c->cl.ghost && c->cl.n_interior > 0 && c->cl.n_boundary > 0 && !env_flag("XNB_NO_OVERLAP");
+    const bool overlap = speculate && c->nranks > 1 && c->cl.valid && !c->cl.ghost && c->cl.n_interior > 0 && c->cl.n_boundary > 0 && !env_flag("XNB_NO_OVERLAP") && !env_flag("XNB_SWEEP_STREAMS");
     if (overlap)
     {
       // halo exchange (pack kernel + NCCL send/recv) on its own stream while the interior tiles are swept; the boundary tiles

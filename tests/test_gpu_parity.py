@@ -523,3 +523,28 @@ def test_full_size_workloads_against_the_oracle(name, steps):
     assert out["ok"], out
     if name in ("C4", "C5"):
         assert r["rebuilds"] > 0
+
+
+@pytest.mark.parametrize("planes", ["XNB_CL_PLANES", "XNB_CL_NO_PLANES"])
+@pytest.mark.parametrize("case", ["ni16k", "lj_dense"])
+def test_large_cell_sweeps_equal_the_stream_sweep(case, planes, monkeypatch):
+    """large cells (256 per cell): k_nbh_big emits the compiled rows either in one segment (swept by k_lj_sweep_cl, whole halo staged) or in
+    one segment per z-plane of halo cells (k_lj_sweep_pl, a third of the halo staged at a time).  Both hold the stream's candidates in
+    the stream's order: trajectories (several rebuilds), forces, energy and virial bit-identical to the sweep over the streams."""
+    kw = CASES[case]
+    eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
+    res = []
+    for streams in (True, False):
+        monkeypatch.delenv("XNB_SWEEP_STREAMS", raising=False); monkeypatch.delenv("XNB_CL_PLANES", raising=False); monkeypatch.delenv("XNB_CL_NO_PLANES", raising=False)
+        monkeypatch.setenv("XNB_SWEEP_STREAMS" if streams else planes, "1")
+        _, ctx = setup_pair(kw)
+        ctx.first_iteration(eps, sig, rc)
+        rb = ctx.run_steps(12, dt, eps, sig, rc)
+        si = ctx.sweep_info()
+        assert bool(si["compiled"]) == (not streams)
+        res.append((ctx.get_particles(0, ctx.n_inner), ctx.energy_virial(eps, sig, rc), rb))
+    (pa, eva, ra), (pb, evb, rbb) = res
+    assert ra == rbb
+    for k in ("id", "rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
+        assert np.array_equal(pa[k], pb[k]), k
+    assert abs(eva[0] - evb[0]) <= 1e-12 * abs(eva[0]) and np.abs(eva[1] - evb[1]).max() <= 1e-12 * np.abs(eva[1]).max()
