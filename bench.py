@@ -299,13 +299,16 @@ def weak_base_run(local, steps, warmup):
     sh = torch.cuda.current_stream().cuda_stream
     ctx.first_iteration(eps, sig, rc, sh)
     ctx.run_steps(warmup, dt, eps, sig, rc, sh)
+    ctx.timing_enable(True); ctx.timing_read(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record(); rb = ctx.run_steps(steps, dt, eps, sig, rc, sh); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    tim = ctx.timing_read(reset=True); ctx.timing_enable(False)
     n = ctx.n_inner
     ctx.close()
-    return {"workload": desc, "atoms": int(n), "steps": steps, "rebuilds": int(rb), "value": n * steps / (ms * 1e-3), "ms_per_step": ms / steps}
+    return {"workload": desc, "atoms": int(n), "steps": steps, "rebuilds": int(rb), "value": n * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+            "breakdown_ms_per_step": {k: v["ms"] / steps for k, v in tim.items()}}
 
 
 def short_run(name, device, steps=12, warmup=3):
@@ -589,7 +592,8 @@ def b200_arm(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "atoms": n_atoms, "rebuilds": rebuilds, "l2": "inputs larger than L2 (state + neighbour streams >> 126 MB), no flush",
-                       "timing": "CUDA events on the launching stream, max over ranks"},
+                       "timing": "CUDA events on the launching stream, max over ranks",
+                       "ghost_transport": (ctx.ghost_transport() if world > 1 else None)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "breakdown_ms_per_step": breakdown, "fp64_dfma_peak_tflops": dfma, "parity": parity, "extra_workloads": extra, "parity_nranks": par_n, "weak_base": weak_base, "load_balance": lbal,
         }

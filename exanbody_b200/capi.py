@@ -18,7 +18,7 @@ SYMBOLS = [
     "xnb_set_type_mass", "xnb_set_sub_grid_density", "xnb_set_nccl_comm", "xnb_nccl_unique_id", "xnb_nccl_init_rank",
     "xnb_set_particles", "xnb_num_inner", "xnb_num_total", "xnb_get_particles", "xnb_upload_rv", "xnb_download_rvf",
     "xnb_get_grid_info", "xnb_get_sweep_info", "xnb_get_cells", "xnb_view_particles", "xnb_device_allocations", "xnb_move_particles", "xnb_rebuild_amr", "xnb_backup_r", "xnb_ghost_comm_scheme",
-    "xnb_ghost_update_all", "xnb_ghost_update_r", "xnb_chunk_neighbors", "xnb_zero_particle_force", "xnb_set_pair_functor", "xnb_lennard_jones_force", "xnb_gravitational_force", "xnb_load_balance_rcb", "xnb_get_block", "xnb_host_amr_sub_cell_pairs",
+    "xnb_ghost_update_all", "xnb_ghost_update_r", "xnb_ghost_transport", "xnb_chunk_neighbors", "xnb_zero_particle_force", "xnb_set_pair_functor", "xnb_lennard_jones_force", "xnb_gravitational_force", "xnb_average_neighbors", "xnb_get_generic_field", "xnb_load_balance_rcb", "xnb_get_block", "xnb_host_amr_sub_cell_pairs",
     "xnb_divide_force_by_mass", "xnb_set_chunk_neighbors_config", "xnb_lennard_jones_force_symmetric", "xnb_update_force_from_ghost", "xnb_push_f_v_r", "xnb_push_f_v", "xnb_particle_displ_over", "xnb_verlet_first_half",
     "xnb_read_displ_over", "xnb_force_and_second_half", "xnb_run_steps", "xnb_step_host", "xnb_first_iteration", "xnb_energy_virial",
     "xnb_view_chunk_neighbors", "xnb_stream_pool_u16", "xnb_get_streams", "xnb_get_amr", "xnb_get_backup",
@@ -83,7 +83,7 @@ def load():
         "xnb_view_particles": (I, [P, C.POINTER(XnbParticleView)]), "xnb_device_allocations": (I64, []),
         "xnb_move_particles": (I, [P, P]), "xnb_rebuild_amr": (I, [P, P]), "xnb_backup_r": (I, [P, P]), "xnb_ghost_comm_scheme": (I, [P, P]),
         "xnb_ghost_update_all": (I, [P, P]), "xnb_ghost_update_r": (I, [P, P]), "xnb_chunk_neighbors": (I, [P, P]),
-        "xnb_zero_particle_force": (I, [P, I, P]), "xnb_set_pair_functor": (I, [P, I]), "xnb_lennard_jones_force": (I, [P, D, D, D, I, P]), "xnb_gravitational_force": (I, [P, D, D, I, I, P]), "xnb_load_balance_rcb": (I, [P, P, P, P, P]), "xnb_get_block": (I, [P, I, P, P]), "xnb_host_amr_sub_cell_pairs": (I64, [I, D, D, P, P]), "xnb_divide_force_by_mass": (I, [P, P]),
+        "xnb_zero_particle_force": (I, [P, I, P]), "xnb_set_pair_functor": (I, [P, I]), "xnb_lennard_jones_force": (I, [P, D, D, D, I, P]), "xnb_gravitational_force": (I, [P, D, D, I, I, P]), "xnb_average_neighbors": (I, [P, D, P, I, P]), "xnb_ghost_transport": (I, [P]), "xnb_get_generic_field": (I, [P, P]), "xnb_load_balance_rcb": (I, [P, P, P, P, P]), "xnb_get_block": (I, [P, I, P, P]), "xnb_host_amr_sub_cell_pairs": (I64, [I, D, D, P, P]), "xnb_divide_force_by_mass": (I, [P, P]),
         "xnb_set_chunk_neighbors_config": (I, [P, I, I]), "xnb_lennard_jones_force_symmetric": (I, [P, D, D, D, P]), "xnb_update_force_from_ghost": (I, [P, P]),
         "xnb_push_f_v_r": (I, [P, D, D, P]), "xnb_push_f_v": (I, [P, D, D, P]), "xnb_particle_displ_over": (I, [P, P, P]),
         "xnb_verlet_first_half": (I, [P, D, P]), "xnb_read_displ_over": (I, [P, P, P]), "xnb_force_and_second_half": (I, [P, D, D, D, D, P]),
@@ -233,6 +233,20 @@ class Context:
         self._ck(self.L.xnb_set_pair_functor(self.h, int(functor)))
     def lennard_jones_force(self, epsilon, sigma, rcut, ghost=False, stream=None):
         self._ck(self.L.xnb_lennard_jones_force(self.h, epsilon, sigma, rcut, int(ghost), _p(stream)))
+    def ghost_transport(self):
+        """'peer' (NVLink peer-memory mailboxes) or 'nccl' (send / recv per partner)"""
+        return "peer" if self.L.xnb_ghost_transport(self.h) == 1 else "nccl"
+
+    FIELDS = {"rx": 0, "ry": 1, "rz": 2, "vx": 3, "vy": 4, "vz": 5, "fx": 6, "fy": 7, "fz": 8, "id": 9, "type": 10}
+
+    def average_neighbors(self, rcut, nbh_field, weight_function=None, stream=None):
+        """op average_neighbors_scalar (src/compute/average_neighbors.cu): returns the averaged field of the inner particles (current order)"""
+        w = None if weight_function is None else np.ascontiguousarray(list(weight_function) + [0.0] * (4 - len(weight_function)), np.float64)
+        self._ck(self.L.xnb_average_neighbors(self.h, rcut, _p(w), self.FIELDS[nbh_field], _p(stream)))
+        out = np.zeros(self.n_inner)
+        self._ck(self.L.xnb_get_generic_field(self.h, _p(out)))
+        return out
+
     def gravitational_force(self, G, rcut, ghost=False, buffer_form=False, stream=None):
         """op gravitational_force (contribs/pi/gravitational_force.cu) through the general pair sweep"""
         self._ck(self.L.xnb_gravitational_force(self.h, G, rcut, int(ghost), int(buffer_form), _p(stream)))

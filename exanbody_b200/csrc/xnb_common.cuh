@@ -49,7 +49,8 @@ enum : uint32_t
   DERR_FAR_MIGRATION = 1u << 3,   // particle jumped to a rank that is not a ghost partner
   DERR_SORT_CAPACITY = 1u << 4,   // cell too large for the in-cell sort
   DERR_ID_RANGE = 1u << 5,        // particle id >= 2^52
-  DERR_TILE_CAPACITY = 1u << 6    // a tile did not fit its shared-memory staging capacity (host falls back to the untiled kernels)
+  DERR_TILE_CAPACITY = 1u << 6,   // a tile did not fit its shared-memory staging capacity (host falls back to the untiled kernels)
+  DERR_PEER_TIMEOUT = 1u << 7     // a partner's halo slab / displacement count never arrived in my mailbox (xnb_peer_halo.cuh)
 };
 
 #define XNB_DEVINL __device__ __forceinline__

@@ -7,6 +7,7 @@
 #include "xnb_nbh_big.cuh"
 #include "xnb_sweep_pl.cuh"
 #include "xnb_pair_generic.cuh"
+#include "xnb_peer_halo.cuh"
 #include "xnb_host_decomp.hpp"
 
 #include <algorithm>
@@ -132,7 +133,7 @@ struct xnb_ctx
   DBuf<double> it_outer;
   DBuf<uint32_t> rc_dst_cell, rc_count, rc_offset;
   DBuf<uint32_t> send_src; DBuf<uint16_t> send_flags;
-  DBuf<double> stage, rstage, lb_costs; DBuf<uint8_t> stage_type;
+  DBuf<double> stage, rstage, lb_costs, generic_field; int64_t generic_field_n = -1; DBuf<uint8_t> stage_type;
   DBuf<uint32_t> d_ghost_base;                          // device copy of h_send_base | h_recv_base (nranks + 1 entries each)
   std::vector<uint32_t> h_send_base, h_recv_base, h_ghost_base;      // per partner particle offsets [nranks+1]; both, back to back
   int64_t n_send = 0, n_ghost = 0;
@@ -169,6 +170,18 @@ struct xnb_ctx
   cudaEvent_t ev_flag = nullptr;
   // ---- NCCL
   ncclComm_t comm = nullptr; bool own_comm = false;
+  // ---- halo over NVLink peer memory (xnb_peer_halo.cuh): my mailbox, the partners' mailboxes mapped here, exchange counters
+  struct PeerHalo
+  {
+    bool tried = false, enabled = false;
+    void* box = nullptr; size_t cap_words = 0; unsigned long long gen = 0;   // my mailbox: header + 2 halves of cap_words words
+    std::vector<void*> retired;                                             // outgrown mailboxes (partners may still have them mapped)
+    std::vector<void*> peer_ptr; std::vector<unsigned long long> peer_gen;   // partner mailboxes as mapped in this process
+    DBuf<PeerSlot> d_slots; DBuf<unsigned char> d_rec;                      // device table for the kernels; all-gather scratch
+    std::vector<PeerSlot> h_slots;                                          // source of the asynchronous upload of d_slots
+    unsigned long long epoch = 0, epoch_over = 0;                           // exchanges done (halo / displacement sum): same on every rank
+  };
+  PeerHalo peer;
   // ---- counters
   int64_t launches = 0, rebuilds = 0;
   int pair_functor = XNB_FUNCTOR_LJ;   // xnb_set_pair_functor
@@ -307,7 +320,7 @@ int ensure_grid(xnb_ctx* c)
   if (ncell > 0x7fffffff) return c->fail(XNB_ERR_CAPACITY, "too many cells");
   g.cs = c->cs; g.gl = gl; g.n_cells = (int)ncell;
   CK(c->cell_start.ensure((size_t)ncell)); CK(c->cell_count.ensure((size_t)ncell));
-  CK(c->d_scalars64.ensure(8)); CK(c->d_scalars32.ensure(128));
+  CK(c->d_scalars64.ensure(16)); CK(c->d_scalars32.ensure(128));
   CK(cudaMemset(c->d_scalars64.p, 0, 8 * 8)); CK(cudaMemset(c->d_scalars32.p, 0, 128 * 4));
   CK(cudaMemset(c->cell_count.p, 0, (size_t)ncell * 4)); CK(cudaMemset(c->cell_start.p, 0, (size_t)ncell * 4));
   if (!c->h_pinned) CK(cudaMallocHost(&c->h_pinned, 4096));
@@ -374,6 +387,7 @@ int check_device_errors(xnb_ctx* c, cudaStream_t st)
   if (e & DERR_SORT_CAPACITY) return c->fail(XNB_ERR_CAPACITY, "in-cell sort: no scratch for a cell of more than 2048 particles");
   if (e & DERR_ID_RANGE) return c->fail(XNB_ERR_CAPACITY, "particle id >= 2^52");
   if (e & DERR_TILE_CAPACITY) return c->fail(XNB_ERR_CAPACITY, "a tile exceeded its shared-memory staging capacity");
+  if (e & DERR_PEER_TIMEOUT) return c->fail(XNB_ERR_NCCL, "peer-memory halo: a partner's data did not arrive within 20 s");
   return c->fail(XNB_ERR_INVALID, "device error word " + std::to_string(e));
 }
 
@@ -432,6 +446,9 @@ void xnb_destroy(xnb_ctx* c)
   if (c->ev_d2h_go) cudaEventDestroy(c->ev_d2h_go);
   if (c->ev_d2h_done) cudaEventDestroy(c->ev_d2h_done);
   if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
+  for (size_t p = 0; p < c->peer.peer_ptr.size(); p++) if (c->peer.peer_ptr[p] && (int)p != c->rank) cudaIpcCloseMemHandle(c->peer.peer_ptr[p]);
+  if (c->peer.box) cudaFree(c->peer.box);
+  for (void* q : c->peer.retired) cudaFree(q);
   if (c->comm && c->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   delete c;
 }
@@ -825,6 +842,111 @@ int xnb_backup_r(xnb_ctx* c, void* stream)
   return XNB_OK;
 }
 
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// halo over peer memory: mailbox management (xnb_peer_halo.cuh).  Called from xnb_ghost_comm_scheme, i.e. collectively and once per
+// rebuild: the per-step path (ghost_update_r, the displacement sum) then runs without any host-side communication call.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct PeerRecord                      // what every rank tells every other rank at a rebuild (all-gathered, 512 bytes)
+{
+  cudaIpcMemHandle_t handle; unsigned long long gen, cap_words; uint32_t ok, pad; uint32_t recv_base[PEER_MAX_RANKS + 1];
+  unsigned char fill[512 - sizeof(cudaIpcMemHandle_t) - 16 - 8 - 4 * (PEER_MAX_RANKS + 1)];
+};
+static_assert(sizeof(PeerRecord) == 512, "PeerRecord");
+
+// my mailbox holds two halves of at least need_words words
+int peer_ensure_box(xnb_ctx* c, size_t need_words, cudaStream_t st)
+{
+  xnb_ctx::PeerHalo& P = c->peer;
+  if (P.box && need_words <= P.cap_words) return 0;
+  const size_t cap = std::max<size_t>((size_t)((double)need_words * 1.5), (size_t)1 << 16);
+  void* q = nullptr;
+  CK(cudaMalloc(&q, PEER_HDR_BYTES + 2 * cap * 8));
+  g_device_allocs++;
+  CK(cudaMemsetAsync(q, 0, PEER_HDR_BYTES, st));
+  if (P.box) P.retired.push_back(P.box);
+  P.box = q; P.cap_words = cap; P.gen++;
+  return 0;
+}
+
+// all-gather the records, map what changed, refresh the device table.  *all_ok = every rank could do it.
+int peer_exchange(xnb_ctx* c, bool my_ok, bool* all_ok, cudaStream_t st)
+{
+  xnb_ctx::PeerHalo& P = c->peer;
+  const size_t n = (size_t)c->nranks;
+  PeerRecord mine; memset(&mine, 0, sizeof(mine));
+  mine.ok = my_ok ? 1u : 0u;
+  if (my_ok)
+  {
+    if (cudaIpcGetMemHandle(&mine.handle, P.box) != cudaSuccess) { cudaGetLastError(); mine.ok = 0u; }
+    mine.gen = P.gen; mine.cap_words = P.cap_words;
+    for (size_t p = 0; p <= n; p++) mine.recv_base[p] = c->h_recv_base.size() > p ? c->h_recv_base[p] : 0u;
+  }
+  CK(P.d_rec.ensure((n + 1) * sizeof(PeerRecord)));
+  CK(cudaMemcpyAsync(P.d_rec.p + n * sizeof(PeerRecord), &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  NK(g_nccl.AllGather(P.d_rec.p + n * sizeof(PeerRecord), P.d_rec.p, sizeof(PeerRecord), nccl_uint8, c->comm, st));
+  std::vector<PeerRecord> all(n);
+  CK(cudaMemcpyAsync(all.data(), P.d_rec.p, n * sizeof(PeerRecord), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  bool ok = true;
+  for (size_t p = 0; p < n; p++) ok = ok && all[p].ok != 0u;
+  *all_ok = ok;
+  if (!ok) return 0;
+  P.peer_ptr.resize(n, nullptr); P.peer_gen.resize(n, 0);
+  std::vector<PeerSlot>& slots = P.h_slots; slots.resize(n);
+  for (size_t p = 0; p < n; p++)
+  {
+    if ((int)p == c->rank) P.peer_ptr[p] = P.box;
+    else if (P.peer_gen[p] != all[p].gen || !P.peer_ptr[p])
+    {
+      if (P.peer_ptr[p]) cudaIpcCloseMemHandle(P.peer_ptr[p]);
+      P.peer_ptr[p] = nullptr;
+      if (cudaIpcOpenMemHandle(&P.peer_ptr[p], all[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); P.peer_ptr[p] = nullptr; *all_ok = false; }
+    }
+    P.peer_gen[p] = all[p].gen;
+    slots[p] = PeerSlot{(unsigned long long)(uintptr_t)P.peer_ptr[p], all[p].cap_words, all[p].recv_base[(size_t)c->rank], 0u};
+  }
+  CK(P.d_slots.ensure(n + 1));
+  CK(cudaMemcpyAsync(P.d_slots.p, slots.data(), n * sizeof(PeerSlot), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+// every rebuild (from xnb_ghost_comm_scheme, after the receive layout is known).  The first call decides, for all ranks alike, whether
+// the peer path is usable (same node, IPC permitted, XNB_GHOST_NCCL unset); afterwards a failure is an error.
+int peer_refresh(xnb_ctx* c, cudaStream_t st)
+{
+  xnb_ctx::PeerHalo& P = c->peer;
+  if (c->nranks < 2 || (P.tried && !P.enabled)) return 0;
+  const bool first = !P.tried;
+  P.tried = true;
+  bool my_ok = c->nranks <= PEER_MAX_RANKS && !(first && env_flag("XNB_GHOST_NCCL"));
+  if (my_ok)
+  {
+    const int rc = peer_ensure_box(c, (size_t)c->n_ghost * GHOST_WORDS_ALL + 16, st);
+    if (rc) { if (!first) return rc; my_ok = false; cudaGetLastError(); }
+  }
+  bool all_ok = false;
+  int rc = peer_exchange(c, my_ok, &all_ok, st); if (rc) return rc;
+  if (first)
+  {
+    // opening a handle may have failed on some rank only: agree once more
+    unsigned long long* flag = c->d_scalars64.p + 8;
+    const unsigned long long mine = all_ok ? 0ull : 1ull;
+    CK(cudaMemcpyAsync(flag, &mine, 8, cudaMemcpyHostToDevice, st));
+    NK(g_nccl.AllReduce(flag, flag, 1, nccl_uint64, nccl_sum, c->comm, st));
+    unsigned long long bad = 0;
+    rc = read_back(c, flag, 1, &bad, st); if (rc) return rc;
+    P.enabled = bad == 0;
+    return 0;
+  }
+  if (!all_ok) return c->fail(XNB_ERR_NCCL, "peer-memory halo: a partner's mailbox could not be mapped");
+  return 0;
+}
+} // namespace
+
+extern "C" {
 // ---------------------------------------------------------------------------------------------------------------------
 // ghosts
 // ---------------------------------------------------------------------------------------------------------------------
@@ -878,6 +1000,7 @@ int xnb_ghost_comm_scheme(xnb_ctx* c, void* stream)
     for (int p = 0; p <= c->nranks; p++) { c->h_ghost_base[(size_t)p] = c->h_send_base[(size_t)p]; c->h_ghost_base[(size_t)c->nranks + 1 + p] = c->h_recv_base[(size_t)p]; }
     CK(cudaMemcpyAsync(c->d_ghost_base.p, c->h_ghost_base.data(), c->h_ghost_base.size() * 4, cudaMemcpyHostToDevice, st));
   }
+  if (c->nranks > 1) { rc = peer_refresh(c, st); if (rc) return rc; }
   CK(c->send_src.ensure((size_t)c->n_send + 16, 0, 1.2)); CK(c->send_flags.ensure((size_t)c->n_send + 16, 0, 1.2));
   if (ns) LAUNCH(k_ghost_fill, nblk((int64_t)ns * 32, 128), 128, st, g, it, c->cell_start.p, c->cell_count.p, A.rx, A.ry, A.rz, c->it_offset.p, c->send_src.p, c->send_flags.p);
   rc = ensure_particle_capacity(c, (size_t)(c->n_inner + c->n_ghost), (size_t)c->n_inner); if (rc) return rc;
@@ -898,6 +1021,29 @@ static int ghost_update(xnb_ctx* c, bool all, cudaStream_t st)
   const uint32_t self_dst = (uint32_t)(c->n_inner + c->h_recv_base[(size_t)c->rank]);
   const size_t ns = (size_t)c->n_send, ng = (size_t)c->n_ghost;
   const size_t nw = all ? GHOST_WORDS_ALL : GHOST_WORDS_R;          // 8-byte words per ghost on the wire
+  if (c->nranks > 1 && c->peer.enabled)
+  {
+    // pack + NVLink stores + flag in one kernel, unpack waits on the flags: no host-side communication call on this path
+    xnb_ctx::PeerHalo& P = c->peer;
+    const unsigned long long epoch = ++P.epoch;
+    PeerHdr* hdr = static_cast<PeerHdr*>(P.box);
+    const unsigned grid_cap = 2u * 148u;
+    if (ns)
+    {
+      const unsigned nb = std::min(nblk((int64_t)ns, 256), grid_cap);
+      if (all) LAUNCH((k_ghost_push<true>), nb, 256, st, g, (int)ns, c->send_src.p, c->send_flags.p, A, self_first, self_end, self_dst, c->d_ghost_base.p, c->nranks, c->rank, P.d_slots.p, epoch, hdr);
+      else     LAUNCH((k_ghost_push<false>), nb, 256, st, g, (int)ns, c->send_src.p, c->send_flags.p, A, self_first, self_end, self_dst, c->d_ghost_base.p, c->nranks, c->rank, P.d_slots.p, epoch, hdr);
+    }
+    if (ng)
+    {
+      const unsigned nb = std::min(nblk((int64_t)ng, 256), grid_cap);
+      const uint32_t* rb = c->d_ghost_base.p + (size_t)c->nranks + 1;
+      const double* half = reinterpret_cast<const double*>(static_cast<const char*>(P.box) + PEER_HDR_BYTES) + (epoch & 1ull) * P.cap_words;
+      if (all) LAUNCH((k_ghost_pull<true>), nb, 256, st, (int)ng, (uint32_t)c->n_inner, A, rb, c->nranks, c->rank, hdr, half, epoch, c->d_scalars32.p);
+      else     LAUNCH((k_ghost_pull<false>), nb, 256, st, (int)ng, (uint32_t)c->n_inner, A, rb, c->nranks, c->rank, hdr, half, epoch, c->d_scalars32.p);
+    }
+    return XNB_OK;
+  }
   if (c->nranks > 1) { CK(c->stage.ensure(ns * nw + 16, 0, 1.2)); CK(c->rstage.ensure(ng * nw + 16, 0, 1.2)); }
   if (ns)
   {
@@ -928,6 +1074,8 @@ static int ghost_update(xnb_ctx* c, bool all, cudaStream_t st)
 }
 
 extern "C" {
+// 0: NCCL send / recv per partner; 1: NVLink peer-memory mailboxes (xnb_peer_halo.cuh); decided at the first xnb_ghost_comm_scheme
+int xnb_ghost_transport(const xnb_ctx* c) { return c && c->peer.enabled ? 1 : 0; }
 int xnb_ghost_update_all(xnb_ctx* c, void* stream) { if (!c) return XNB_ERR_INVALID; CK(cudaSetDevice(c->device)); return ghost_update(c, true, (cudaStream_t)stream); }
 int xnb_ghost_update_r(xnb_ctx* c, void* stream) { if (!c) return XNB_ERR_INVALID; CK(cudaSetDevice(c->device)); return ghost_update(c, false, (cudaStream_t)stream); }
 
@@ -1631,6 +1779,45 @@ int xnb_gravitational_force(xnb_ctx* c, double G, double rcut, int ghost, int bu
   return t_end(c, XNB_T_FORCE, st);
 }
 
+// op `average_neighbors_scalar` (src/compute/average_neighbors.cu:102-215): a functor with a per-neighbour scalar field and a particle
+// context (start / pair / stop), through the general sweep.  nbh_field: XNB_FIELD_*.  The result lives in a ctx-owned generic real
+// field (one double per particle, current particle order): xnb_get_generic_field / xnb_view_generic_field.
+int xnb_average_neighbors(xnb_ctx* c, double rcut, const double weight_function[4], int nbh_field, void* stream)
+{
+  if (!c) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "average_neighbors: no neighbour list (run xnb_chunk_neighbors)");
+  if (c->nbh_half_symmetric) return c->fail(XNB_ERR_INVALID, "average_neighbors: needs full lists");
+  if (nbh_field < 0 || nbh_field > XNB_FIELD_TYPE) return c->fail(XNB_ERR_INVALID, "average_neighbors: unknown nbh_field");
+  c->rcut_max = std::max(c->rcut_max, rcut);
+  cudaStream_t st = (cudaStream_t)stream;
+  ParticlesP A = c->P(c->cur);
+  CK(c->generic_field.ensure((size_t)c->n_total + 16, 0, 1.2));
+  CK(cudaMemsetAsync(c->generic_field.p, 0, (size_t)c->n_total * 8, st));
+  if (c->n_inner)
+  {
+    const CellsView cells{c->cell_start.p, c->cell_count.p, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, A.id, A.type};
+    const double* f64[9] = {A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, A.fx, A.fy, A.fz};
+    AverageNeighborsFunctor f{rcut * rcut, weight_function ? weight_function[0] : 1.0, weight_function ? weight_function[1] : 0.0, weight_function ? weight_function[2] : 0.0,
+                              weight_function ? weight_function[3] : 0.0, c->generic_field.p, nbh_field <= XNB_FIELD_FZ ? f64[nbh_field] : nullptr,
+                              nbh_field == XNB_FIELD_ID ? A.id : nullptr, nbh_field == XNB_FIELD_TYPE ? A.type : nullptr};
+    LAUNCH((k_pair_sweep_context<AverageNeighborsFunctor>), nblk(c->n_inner, 128), 128, st, c->g, (int)c->n_inner, f, rcut * rcut, cells, c->atom_cell[c->cur_ac].p,
+           (const uint16_t* const*)c->cell_stream.p);
+  }
+  c->generic_field_n = c->n_inner;
+  return XNB_OK;
+}
+
+int xnb_get_generic_field(xnb_ctx* c, double* out)
+{
+  if (!c || !out) return XNB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  if (!c->generic_field.p || c->generic_field_n != c->n_inner) return c->fail(XNB_ERR_INVALID, "no generic field for the current particle set");
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, c->generic_field.p, (size_t)c->n_inner * 8, cudaMemcpyDeviceToHost));
+  return XNB_OK;
+}
+
 int xnb_set_chunk_neighbors_config(xnb_ctx* c, int half_symmetric, int skip_ghosts)
 {
   if (!c) return XNB_ERR_INVALID;
@@ -1841,7 +2028,13 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
     // host reads the count.  The fast path (ghost_update_r + sweep) is enqueued BEFORE the host waits for that count, so the GPU
     // never idles on the host round trip; the sweep reads the same counter on the device and returns at once if a rebuild is due
     // (ghost_update_r before a rebuild is harmless: the rebuild recreates every ghost).
-    if (c->nranks > 1) { if (!c->comm) return c->fail(XNB_ERR_NCCL, "no communicator"); NK(g_nccl.AllReduce(c->d_scalars64.p, c->d_scalars64.p, 1, nccl_uint64, nccl_sum, c->comm, st)); }
+    if (c->nranks > 1)
+    {
+      if (!c->comm) return c->fail(XNB_ERR_NCCL, "no communicator");
+      if (c->peer.enabled)
+        LAUNCH(k_peer_allsum, 1, PEER_MAX_RANKS, st, c->nranks, c->rank, c->peer.d_slots.p, static_cast<const PeerHdr*>(c->peer.box), ++c->peer.epoch_over, c->d_scalars64.p, c->d_scalars32.p);
+      else NK(g_nccl.AllReduce(c->d_scalars64.p, c->d_scalars64.p, 1, nccl_uint64, nccl_sum, c->comm, st));
+    }
     CK(cudaMemcpyAsync(const_cast<unsigned long long*>(h_flag), c->d_scalars64.p, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(c->ev_flag, st));
     size_t force_scopes = c->tpool[XNB_T_FORCE].used;
@@ -1863,11 +2056,15 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
       if ((rc = t_begin(c, XNB_T_GHOST_UPDATE, c->st_comm))) return rc;
       if ((rc = xnb_ghost_update_r(c, c->st_comm))) return rc;
       if ((rc = t_end(c, XNB_T_GHOST_UPDATE, c->st_comm))) return rc;
+      // the boundary tiles follow the halo on ITS stream: they start the moment the ghosts are in, alongside whatever is left of
+      // the interior sweep (one tail instead of two), and the main stream joins at the end
+      const bool boundary_on_comm = !env_flag("XNB_BOUNDARY_ON_MAIN");
+      if (boundary_on_comm && (rc = launch_force<1, false>(c, false, lj, dt * 0.5, nullptr, nullptr, nullptr, nullptr, nullptr, c->st_comm, c->d_scalars64.p, 2))) return rc;
       CK(cudaEventRecord(c->ev_ghost, c->st_comm));
       if ((rc = t_begin(c, XNB_T_FORCE, st))) return rc;
       if ((rc = launch_force<1, false>(c, false, lj, dt * 0.5, nullptr, nullptr, nullptr, nullptr, nullptr, st, c->d_scalars64.p, 1))) return rc;
       CK(cudaStreamWaitEvent(st, c->ev_ghost, 0));
-      if ((rc = launch_force<1, false>(c, false, lj, dt * 0.5, nullptr, nullptr, nullptr, nullptr, nullptr, st, c->d_scalars64.p, 2))) return rc;
+      if (!boundary_on_comm && (rc = launch_force<1, false>(c, false, lj, dt * 0.5, nullptr, nullptr, nullptr, nullptr, nullptr, st, c->d_scalars64.p, 2))) return rc;
       if ((rc = t_end(c, XNB_T_FORCE, st))) return rc;
     }
     else if (speculate)

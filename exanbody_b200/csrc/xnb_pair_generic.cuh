@@ -163,4 +163,82 @@ k_pair_sweep_generic(GridP g, int n_inner, F func, double rcut2, CellsView cells
   fx[i] = ax; fy[i] = ay; fz[i] = az;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Particle-context call form (compute_pair_traits.h: HasParticleContextStart / HasParticleContext / HasParticleContextStop;
+// impl_default.h:152,199-204,224): the sweep owns a per-particle context (ComputeContextNoBuffer<ExtStorage>), calls
+// func(ctx, cells, cell_a, p_a, Start{}) before the particle's first neighbour, func(ctx, dr, d2, cells, cell_b, p_b, weight) per pair
+// and func(ctx, cells, cell_a, p_a, Stop{}) after the last.
+// ------------------------------------------------------------------------------------------------------------------
+struct ComputePairParticleContextStart {};
+struct ComputePairParticleContextStop {};
+template <class Ext> struct ComputeContextNoBuffer { Ext ext; };        // compute_pair_buffer.h:143-148
+
+// AverageNeighborsFunctor (src/compute/average_neighbors.cu:38-100): avg_field[a] = sum_b w(d) nbh_field[b] / sum_b w(d) over the
+// neighbours within rcut, w = a0 + a1 d + a2 d^2 + a3 d^3; a third kind of functor: per-neighbour SCALAR FIELD + particle context
+struct AverageNeighborsExtStorage
+{
+  double m_sum, m_weight_sum;
+  XNB_DEVINL void reset() { m_sum = 0.0; m_weight_sum = 0.0; }
+  XNB_DEVINL double avg() const { return (m_weight_sum > 0.0) ? (m_sum / m_weight_sum) : (m_sum / 1.0); }
+};
+struct AverageNeighborsFunctor
+{
+  double m_rcut_sq, a0, a1, a2, a3;
+  double* m_avg_field;                 // flat array of the averaged field (cells[c][avg_field][p] = m_avg_field[cell_start[c] + p])
+  const double* m_nbh_field_f64;       // the neighbours' field: one of the f64 particle arrays ...
+  const unsigned long long* m_nbh_field_u64; const uint8_t* m_nbh_field_u8;      // ... or id / type (anything convertible to double, :143)
+  typedef ComputeContextNoBuffer<AverageNeighborsExtStorage> Context;
+  XNB_DEVINL double nbh_value(uint32_t j) const { return m_nbh_field_f64 ? m_nbh_field_f64[j] : m_nbh_field_u64 ? (double)m_nbh_field_u64[j] : (double)m_nbh_field_u8[j]; }
+  XNB_DEVINL void operator()(Context& ctx, const CellsView&, size_t, size_t, ComputePairParticleContextStart) const { ctx.ext.reset(); }
+  XNB_DEVINL void operator()(Context& ctx, const CellsView& cells, size_t cell_a, size_t p_a, ComputePairParticleContextStop) const { m_avg_field[cells.flat(cell_a, p_a)] = ctx.ext.avg(); }
+  XNB_DEVINL void operator()(Context& ctx, double3, double d2, const CellsView& cells, size_t cell_b, size_t p_b, double) const
+  {
+    if (d2 <= m_rcut_sq)
+    {
+      double w = a0 + a2 * d2;
+      if (a1 != 0.0 || a3 != 0.0) { const double d = sqrt(d2); w += a1 * d + a3 * d2 * d; }
+      ctx.ext.m_sum += w * nbh_value(cells.flat(cell_b, p_b));
+      ctx.ext.m_weight_sum += w;
+    }
+  }
+};
+
+// k_pair_sweep_context<F>: compute_cell_particle_pairs for functors with a particle context (no central fields, no buffer)
+template <class F>
+__global__ void __launch_bounds__(128)
+k_pair_sweep_context(GridP g, int n_inner, F func, double rcut2, CellsView cells, const uint32_t* __restrict__ atom_cell,
+                     const uint16_t* const* __restrict__ cell_stream)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inner) return;
+  const uint32_t ca = atom_cell[i];
+  const uint32_t na = cells.cell_count[ca], pa = (uint32_t)i - cells.cell_start[ca];
+  typename F::Context ctx;
+  func(ctx, cells, (size_t)ca, (size_t)pa, ComputePairParticleContextStart{});
+  const uint16_t* cs = cell_stream[ca];
+  if (cs)
+  {
+    const uint32_t off0 = reinterpret_cast<const uint32_t*>(cs)[pa];
+    const uint16_t* lst = cs + 2u * (na + 1u) + off0;
+    uint32_t ngrp = (uint32_t)lst[-1];
+    const double xa = cells.rx[i], ya = cells.ry[i], za = cells.rz[i];
+    const int dxy = g.dims[0] * g.dims[1];
+    for (; ngrp > 0u; ngrp--)
+    {
+      const uint32_t code = *lst++; uint32_t n = *lst++;
+      const int cb = (int)ca + ((int)(code >> 10) - 16) * dxy + ((int)((code >> 5) & 31u) - 16) * g.dims[0] + ((int)(code & 31u) - 16);
+      const uint32_t sb = cells.cell_start[cb];
+      for (; n > 0u; n--)
+      {
+        const uint32_t pb = *lst++;
+        const uint32_t j = sb + pb;
+        const double dx = __dadd_rn(cells.rx[j], -xa), dy = __dadd_rn(cells.ry[j], -ya), dz = __dadd_rn(cells.rz[j], -za);
+        const double d2 = norm2_exact(dx, dy, dz);
+        if (d2 > 0.0 && d2 <= rcut2) func(ctx, make_double3(dx, dy, dz), d2, cells, (size_t)cb, (size_t)pb, 1.0);
+      }
+    }
+  }
+  func(ctx, cells, (size_t)ca, (size_t)pa, ComputePairParticleContextStop{});
+}
+
 } // namespace xnb

@@ -449,6 +449,40 @@ struct GravitationalForce : OperatorNode    // contribs/pi/gravitational_force.c
     ck(grid->ctx, xnb_gravitational_force(grid->ctx, config->G, *rcut, *ghost ? 1 : 0, *compute_buffer ? 1 : 0, stream), "gravitational_force");
   }
 };
+// a third functor: per-neighbour scalar field + particle context (start / pair / stop), through the general pair sweep
+struct AverageNeighborsScalar : OperatorNode    // src/compute/average_neighbors.cu:114-215
+{
+  ADD_SLOT(double, rcut, INPUT, 0.0, DocString{"Cutoff distance for average operation."});
+  ADD_SLOT(std::vector<double>, weight_function, INPUT, std::vector<double>{1.0}, DocString{"[a0,...,an] coefficients of the polynomial distance weighting function"});
+  ADD_SLOT(GridChunkNeighbors, chunk_neighbors, INPUT, GridChunkNeighbors{}, DocString{"neighbor list"});
+  ADD_SLOT(Domain, domain, INPUT, REQUIRED, DocString{"Simulation domain"});
+  ADD_SLOT(ParticleTypeProperties, particle_type_properties, INPUT, ParticleTypeProperties{});
+  ADD_SLOT(std::string, avg_field, INPUT, REQUIRED, DocString{"Name of the resulting averaged field."});
+  ADD_SLOT(std::string, nbh_field, INPUT, REQUIRED, DocString{"Name of the neighbors field to be averaged."});
+  ADD_SLOT(double, rcut_max, INPUT_OUTPUT, 0.0, DocString{"Updated max rcut"});
+  ADD_SLOT(Grid, grid, INPUT_OUTPUT, DocString{"Local sub-domain particles grid"});
+  void yaml_initialize(const Params& p) override
+  {
+    if (p.has("rcut")) rcut.value = std::make_shared<double>(p.quantity("rcut"));
+    if (p.has("weight_function")) weight_function.value = std::make_shared<std::vector<double>>(p.quantities("weight_function"));
+    if (p.has("avg_field")) avg_field.value = std::make_shared<std::string>(p.str("avg_field"));
+    if (p.has("nbh_field")) nbh_field.value = std::make_shared<std::string>(p.str("nbh_field"));
+  }
+  void execute() override
+  {
+    *rcut_max = std::max(*rcut, *rcut_max);            // :197
+    if (grid->number_of_cells() == 0) return;
+    if (weight_function->size() > 4) fatal_error("weighting function polynomial has a maximum degree of 3 (maximum 4 coefficients)");   // :199-202
+    static const char* names[] = {"rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz", "id", "type"};
+    int field = -1;
+    for (int i = 0; i <= XNB_FIELD_TYPE; i++) if (*nbh_field == names[i]) field = i;
+    if (field < 0) return;                             // like the reference (:133): no grid field of that name, nothing is computed
+    double coefs[4] = {1.0, 0.0, 0.0, 0.0};
+    for (size_t i = 0; i < weight_function->size(); i++) coefs[i] = (*weight_function)[i];
+    ck(grid->ctx, xnb_average_neighbors(grid->ctx, *rcut, coefs, field, stream), "average_neighbors_scalar");
+    grid->generic_real_field = *avg_field;             // field::mk_generic_real(avg_field): the ctx holds one generic real field
+  }
+};
 // dynamic re-partition: cost model + cost-weighted RCB + migration in one collective call
 struct LoadBalanceRCB : OperatorNode        // mpi/load_balance_rcb.cpp:51-601 (+ simple_cost_model.h, migrate_cell_particles.cpp:101-143)
 {
@@ -817,6 +851,7 @@ void register_hot_path_operators()
   f->register_factory("lennard_jones_force", make_simple_operator<LennardJonesForce<false>>());
   f->register_factory("load_balance_rcb", make_simple_operator<LoadBalanceRCB>());
   f->register_factory("gravitational_force", make_simple_operator<GravitationalForce>());
+  f->register_factory("average_neighbors_scalar", make_simple_operator<AverageNeighborsScalar>());
   f->register_factory("lennard_jones_force_symmetric", make_simple_operator<LennardJonesForce<true>>());
   f->register_factory("update_force_from_ghost", make_simple_operator<UpdateForceFromGhost>());   // adds zeros after a full-list sweep (ghost forces are 0 then)
   f->register_factory("divide_force_by_type_scalar", make_simple_operator<DivideForceByTypeScalar>());

@@ -54,7 +54,8 @@ struct UpdateGhostConfig { bool gpu_buffer_pack = true, staging_buffer = false; 
 // The grid and everything derived from it live in one xnb_ctx (one sub-domain on one GPU); the slot types below are
 // views on it, so that operators keep the reference's slot signature.
 struct Grid { xnb_ctx* ctx = nullptr; int device = 0; ~Grid(); Grid() = default; Grid(const Grid&) = delete; Grid& operator=(const Grid&) = delete;
-              int64_t number_of_particles() const; int64_t number_of_cells() const; };
+              int64_t number_of_particles() const; int64_t number_of_cells() const;
+              std::string generic_real_field; /* name of the generic real field the ctx holds (field::mk_generic_real) */ };
 struct GridChunkNeighbors { xnb_ctx* ctx = nullptr; const uint16_t* const* cell_stream = nullptr; const uint32_t* cell_stream_size = nullptr;
                             uint32_t max_neighbors = 0; size_t number_of_cells() const; };     // chunk_neighbors.h:42-120 (device views)
 struct AmrGrid { xnb_ctx* ctx = nullptr; };

@@ -145,6 +145,12 @@ int xnb_ghost_comm_scheme(xnb_ctx*, void* stream);   /* [host sync] */
 /* ops `ghost_update_all` / `ghost_update_r` : src/mpi/update_ghosts.cu:45-64, include/exanb/mpi/grid_update_ghosts.h:63-202 */
 int xnb_ghost_update_all(xnb_ctx*, void* stream);
 int xnb_ghost_update_r(xnb_ctx*, void* stream);
+/* how the halo travels between ranks (the role of the reference's MPI_Isend / MPI_Irecv per partner,
+   update_ghosts_comm_manager.h:390,436): 1 = NVLink peer-memory mailboxes -- the pack kernel stores straight into the partner's
+   HBM and raises a flag, the unpack kernel waits on it, and the per-step displacement all-reduce (particle_displ_over.cu:174) is
+   a peer-store kernel too, so the step path has no host-side communication call; 0 = one ncclSend / ncclRecv per partner (ranks on
+   different nodes, IPC not permitted, or XNB_GHOST_NCCL=1).  Decided collectively at the first xnb_ghost_comm_scheme.          */
+int xnb_ghost_transport(const xnb_ctx*);
 /* ops `amr_grid_pairs` + `chunk_neighbors` : src/particle_neighbors/chunk_neighbors.cpp:48-74,
    include/exanb/particle_neighbors/chunk_neighbors_execute.h:40-423 (K2).  Config = build_particle_offset, chunk 1. */
 int xnb_chunk_neighbors(xnb_ctx*, void* stream);   /* [host sync] (an overflowing build is re-run with more room) */
@@ -172,6 +178,25 @@ int xnb_lennard_jones_force(xnb_ctx*, double epsilon, double sigma, double rcut,
    (impl_default.h:213-222, compute_pair_buffer.h:150-243; capacity 512 neighbours inside the cut, more is an error).
    Masses: xnb_set_type_mass.  ACCUMULATES into fx,fy,fz.  ghost must be 0.                                         */
 int xnb_gravitational_force(xnb_ctx*, double G, double rcut, int ghost, int buffer_form, void* stream);
+/* op `average_neighbors_scalar` : src/compute/average_neighbors.cu:102-215 (functor :60-100, traits :104-113) -- a third kind of
+   functor of the concept: a per-neighbour SCALAR FIELD and a PARTICLE CONTEXT (HasParticleContextStart / HasParticleContext /
+   HasParticleContextStop: func(ctx, cells, cell_a, p_a, Start{}), func(ctx, dr, d2, cells, cell_b, p_b, w), func(..., Stop{});
+   impl_default.h:152,199-204,224).  avg_field[a] = sum_b w(d) nbh_field[b] / sum_b w(d) over the listed neighbours with
+   0 < d <= rcut, w(d) = a0 + a1 d + a2 d^2 + a3 d^3 (weight_function, NULL = {1,0,0,0}); nbh_field = XNB_FIELD_*.  The result is
+   a ctx-owned generic real field, one double per inner particle in the current particle order.                         */
+#define XNB_FIELD_RX 0
+#define XNB_FIELD_RY 1
+#define XNB_FIELD_RZ 2
+#define XNB_FIELD_VX 3
+#define XNB_FIELD_VY 4
+#define XNB_FIELD_VZ 5
+#define XNB_FIELD_FX 6
+#define XNB_FIELD_FY 7
+#define XNB_FIELD_FZ 8
+#define XNB_FIELD_ID 9
+#define XNB_FIELD_TYPE 10
+int xnb_average_neighbors(xnb_ctx*, double rcut, const double weight_function[4], int nbh_field, void* stream);
+int xnb_get_generic_field(xnb_ctx*, double* out /* n_inner */);   /* [host sync] */
 /* ---- Newton-3 path ---------------------------------------------------------------------- */
 /* ChunkNeighborsConfig::half_symmetric / skip_ghosts of the chunk_neighbors operator (chunk_neighbors_config.h:35-36),
    i.e. NeighborFilterHalfSymGhost (neighbor_filter_func.h:36-52): half_symmetric keeps b only if cell_b < cell_a or

@@ -48,6 +48,7 @@ def lib():
             getattr(L, f).argtypes = [P]; getattr(L, f).restype = C.c_int
         L.xo_run.argtypes = [P, C.c_int]; L.xo_run.restype = C.c_int
         L.xo_amr_pair_cache.argtypes = [P, P, P, P]; L.xo_amr_pair_cache.restype = C.c_int64
+        L.xo_average_neighbors.argtypes = [P, C.c_double, P, C.c_int, P]; L.xo_average_neighbors.restype = C.c_int
         L.xo_gravitational_force.argtypes = [P, C.c_double, C.c_double, P, C.c_int]; L.xo_gravitational_force.restype = C.c_int
         L.xo_push_f_v.argtypes = [P, C.c_double]; L.xo_push_f_v.restype = C.c_int
         for f in ("xo_displ_over", "xo_total_particles", "xo_inner_particles", "xo_stream_total_u16", "xo_max_neighbors",
@@ -131,6 +132,12 @@ class Oracle:
         self.L.xo_amr_pair_cache(self.h, None, off.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p))
         return int(mr.value), off, data[:int(n)]
     def zero_force(self): self._chk(self.L.xo_zero_force(self.h))
+    FIELDS = {"rx": 0, "ry": 1, "rz": 2, "vx": 3, "vy": 4, "vz": 5, "fx": 6, "fy": 7, "fz": 8, "id": 9, "type": 10}
+    def average_neighbors(self, rcut, nbh_field, weight_function=(1.0, 0.0, 0.0, 0.0)):
+        w = np.ascontiguousarray(list(weight_function) + [0.0] * (4 - len(weight_function)), np.float64)
+        out = np.zeros(self.n_total())
+        self._chk(self.L.xo_average_neighbors(self.h, float(rcut), _p(w), self.FIELDS[nbh_field], _p(out)))
+        return out
     def gravitational_force(self, G, rcut, type_mass):
         m = np.ascontiguousarray(type_mass, np.float64)
         self._chk(self.L.xo_gravitational_force(self.h, float(G), float(rcut), m.ctypes.data_as(C.c_void_p), len(m)))

@@ -897,6 +897,60 @@ static int gravitational_force(xo_sim& s, double G, double rcut, const double* t
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * average_neighbors_scalar (src/compute/average_neighbors.cu:38-100 functor, :123-175 operator): compute_cell_particle_pairs over
+ * the inner cells with a functor that has a PARTICLE CONTEXT: Start resets (m_sum, m_weight_sum) (:41-45), every neighbour with
+ * d2 <= rcut^2 adds w * nbh_field[b] and w, w = a0 + a1 d + a2 d^2 + a3 d^3 (:85-99), Stop writes sum / weight_sum (:47-51,73-77).
+ * nbh_field: 0..8 = rx ry rz vx vy vz fx fy fz, 9 = id, 10 = type.  out = all particles in cell order, ghost cells untouched (0).
+ * Parity unpinned by the reference's tests (it ships none for this operator); pinned here by a brute-force all-pairs evaluation
+ * in tests/test_gpu_parity.py.
+ * ------------------------------------------------------------------------------------------------ */
+static int average_neighbors(xo_sim& s, double rcut, const double wf[4], int nbh_field, double* out)
+{
+  Grid& g = s.grid;
+  if (nbh_field < 0 || nbh_field > 10) { g_err = "average_neighbors: unknown field"; return 1; }
+  const i64 gl = g.ghost_layers();
+  const double rcut2 = rcut * rcut;
+  std::vector<size_t> first(g.cells.size() + 1, 0);
+  for (size_t c = 0; c < g.cells.size(); c++) first[c + 1] = first[c] + g.cells[c].size();
+  std::fill(out, out + first.back(), 0.0);
+  auto value = [&](const Cell& B, size_t p) -> double {
+    switch (nbh_field) {
+      case 0: return B.rx[p]; case 1: return B.ry[p]; case 2: return B.rz[p];
+      case 3: return B.vx[p]; case 4: return B.vy[p]; case 5: return B.vz[p];
+      case 6: return B.fx[p]; case 7: return B.fy[p]; case 8: return B.fz[p];
+      case 9: return (double)B.id[p]; default: return (double)B.type[p];
+    }
+  };
+# pragma omp parallel for collapse(3) schedule(dynamic)
+  for (i64 k = gl; k < g.dims.k - gl; k++) for (i64 j = gl; j < g.dims.j - gl; j++) for (i64 i = gl; i < g.dims.i - gl; i++)
+  {
+    const i64 cell_a = ijk_to_index(g.dims, IJK{i, j, k});
+    const Cell& A = g.cells[(size_t)cell_a];
+    const size_t na = A.size();
+    const StreamInfo si = stream_info(s.streams[(size_t)cell_a], na);
+    for (size_t pa = 0; pa < na; pa++)
+    {
+      const double xa = A.rx[pa], ya = A.ry[pa], za = A.rz[pa];
+      double sum = 0.0, wsum = 0.0;
+      for_each_listed(s, cell_a, pa, si, [&](i64 cell_b, size_t pb) {
+        const Cell& B = g.cells[(size_t)cell_b];
+        const double dx = B.rx[pb] - xa, dy = B.ry[pb] - ya, dz = B.rz[pb] - za;
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 > 0.0 && d2 <= rcut2)
+        {
+          double w = wf[0] + wf[2] * d2;
+          if (wf[1] != 0.0 || wf[3] != 0.0) { const double d = std::sqrt(d2); w += wf[1] * d + wf[3] * d2 * d; }
+          sum += w * value(B, pb);
+          wsum += w;
+        }
+      });
+      out[first[(size_t)cell_a] + pa] = (wsum > 0.0) ? sum / wsum : sum;
+    }
+  }
+  return 0;
+}
+
 /* zero_particle_force{ghost:true} alone (zero_particle_force.cu:15-46) */
 static void zero_force(xo_sim& s)
 {
@@ -1117,6 +1171,7 @@ int64_t xo_amr_pair_cache(const xo_sim* s, int64_t* max_res, uint64_t* list_offs
   if (list_offsets) list_offsets[q] = (uint64_t)total;
   return total;
 }
+int xo_average_neighbors(xo_sim* s, double rcut, const double wf[4], int nbh_field, double* out) { return average_neighbors(*s, rcut, wf, nbh_field, out); }
 int xo_gravitational_force(xo_sim* s, double G, double rcut, const double* type_mass, int n_types) { return gravitational_force(*s, G, rcut, type_mass, n_types); }
 void xo_set_nbh_config(xo_sim* s, int half_symmetric, int skip_ghosts) { s->nbh_half_symmetric = half_symmetric != 0; s->nbh_skip_ghosts = skip_ghosts != 0; }
 int xo_push_f_v_r(xo_sim* s) { push_f_v_r(*s); return 0; }

@@ -76,6 +76,8 @@ int xo_compute_force_symmetric(xo_sim*);
 /* zero_particle_force{ghost:true}; gravitational_force (contribs/pi/gravitational_force.cu): ADDS G ma mb / r^2 pair forces, masses by type */
 int xo_zero_force(xo_sim*);
 int xo_gravitational_force(xo_sim*, double G, double rcut, const double* type_mass, int n_types);
+/* average_neighbors_scalar (src/compute/average_neighbors.cu): out[all particles, cell order]; field 0..8 = r v f, 9 = id, 10 = type */
+int xo_average_neighbors(xo_sim*, double rcut, const double weight_function[4], int nbh_field, double* out);
 int xo_push_f_v_r(xo_sim*);               /* push_vec3_2nd_order.h */
 int xo_push_f_v(xo_sim*, double dt_scale);/* push_vec3_1st_order.h */
 int64_t xo_displ_over(xo_sim*);           /* particle_displ_over.cu: count of atoms over threshold */

@@ -44,6 +44,9 @@ def main():
         eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
         ctx.first_iteration(eps, sig, rc)
         rb = ctx.run_steps(nsteps, dt, eps, sig, rc)
+        transport = ctx.ghost_transport()
+        expect = os.environ.get("XNB_EXPECT_TRANSPORT")
+        assert expect is None or transport == expect, "halo transport is %s, expected %s" % (transport, expect)
         lb = None
         if name == "lj_voids":
             # load_balance_rcb on the live contexts (device cost model -> all-reduce -> cost-weighted RCB -> new blocks
@@ -91,7 +94,7 @@ def main():
                 assert min(len(e["id"]) for e in everyone) > 0
             for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
                 assert np.array_equal(allp[k], pr[k]), "%s: %s differs between %d ranks and 1 rank (max %g)" % (name, k, world, np.abs(allp[k] - pr[k]).max())
-            print("mgpu parity ok: %s, %d ranks, %d atoms, %d steps, %d rebuilds, atoms per rank %s" % (name, world, len(pr["id"]), nsteps, rb, [len(e["id"]) for e in everyone]), flush=True)
+            print("mgpu parity ok: %s, %d ranks, transport %s, %d atoms, %d steps, %d rebuilds, atoms per rank %s" % (name, world, transport, len(pr["id"]), nsteps, rb, [len(e["id"]) for e in everyone]), flush=True)
             ref.close()
         ctx.close()
         dist.barrier()

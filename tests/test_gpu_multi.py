@@ -9,16 +9,23 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_decomposed_run_is_bit_identical_to_single_gpu(world):
+@pytest.mark.parametrize("world,transport", [(2, "peer"), (2, "nccl"), (4, "peer"), (8, "peer")])
+def test_decomposed_run_is_bit_identical_to_single_gpu(world, transport):
+    """transport: how the halo travels -- NVLink peer-memory mailboxes (xnb_peer_halo.cuh, the default on one node) or one
+    ncclSend / ncclRecv per partner (XNB_GHOST_NCCL=1); the worker asserts which one ran"""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+           "--master-port", str(29500 + world + (16 if transport == "nccl" else 0)), os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    env = dict(os.environ, XNB_EXPECT_TRANSPORT=transport)
+    env.pop("XNB_GHOST_NCCL", None)
+    if transport == "nccl":
+        env["XNB_GHOST_NCCL"] = "1"
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("mgpu parity ok") == 3, r.stdout[-2000:]
+    assert r.stdout.count("transport %s" % transport) == 3, r.stdout[-2000:]
 
 
 def test_two_contexts_on_two_devices_in_one_process():

@@ -502,6 +502,52 @@ def test_gravitational_force_second_functor(case, buffer_form):
     assert U.force_error(U.vec(pg2, ("fx", "fy", "fz")), 2.0 * fo) <= TOL
 
 
+@pytest.mark.parametrize("field,weights", [("vx", None), ("id", (1.0, 0.0, -0.05, 0.0)), ("type", (2.0, -0.3, 0.0, 0.01)), ("rz", (0.0, 1.0))])
+@pytest.mark.parametrize("case", ["lj2k", "lj_voids"])
+def test_average_neighbors_third_functor(case, field, weights):
+    """SURVEY 8(f) rank 3, the remaining call form of the functor concept: a PARTICLE CONTEXT (Start / per pair / Stop) and a per-neighbour
+    scalar field -- average_neighbors_scalar (src/compute/average_neighbors.cu:38-175): avg[a] = sum w(d) field[b] / sum w(d) over the
+    listed neighbours within rcut, w a cubic in d.  Against the oracle's restatement on the same lists (same summation order: equal to
+    rounding of the final division), and -- to pin the oracle itself -- against a brute-force evaluation over ALL particle pairs."""
+    from scipy.spatial import cKDTree
+    kw = CASES[case]
+    inp = U.generate_input(kw)
+    inp["type"] = (inp["id"] % 3).astype(np.uint8)
+    rcut = kw["rcut"]
+    o = U.make_oracle(kw)
+    o.generate()
+    ctx = U.make_ctx(kw, particles=inp)
+    ctx.move_particles(); ctx.update_particles_full()
+    o.move_particles(); o.update_particles_full()
+    pcell, cnt = U.gpu_particles_cell_order(ctx)
+    o.set_particles(cnt, pcell); o.build_neighbors()
+    w4 = (1.0, 0.0, 0.0, 0.0) if weights is None else tuple(weights) + (0.0,) * (4 - len(weights))
+    avg_o = o.average_neighbors(rcut, field, w4)
+    avg_g = ctx.average_neighbors(rcut, field, weights)
+    allo = o.particles(); mask = o.inner_mask()
+    po = U.by_id(dict(allo, avg=avg_o), mask)
+    pg = U.by_id(dict(ctx.get_particles(0, ctx.n_inner), avg=avg_g))
+    assert np.array_equal(po["id"], pg["id"])
+    scale = max(np.abs(po["avg"]).max(), 1e-300)
+    assert scale > 0 and np.abs(pg["avg"] - po["avg"]).max() <= 1e-13 * scale
+    # brute force over every particle (ghost images stand for the periodic copies)
+    pa = ctx.get_particles(0, ctx.n_total)
+    xyz = np.stack([pa["rx"], pa["ry"], pa["rz"]], 1)
+    val = pa[field].astype(np.float64)
+    tree = cKDTree(xyz)
+    ni = ctx.n_inner
+    ref = np.zeros(ni)
+    for a, nb in enumerate(tree.query_ball_point(xyz[:ni], rcut * (1 + 1e-9))):
+        nb = np.asarray(nb, np.int64)
+        d2 = ((xyz[nb] - xyz[a]) ** 2).sum(1)
+        nb = nb[(d2 > 0) & (d2 <= rcut * rcut)]; d2 = ((xyz[nb] - xyz[a]) ** 2).sum(1)
+        d = np.sqrt(d2)
+        w = w4[0] + w4[1] * d + w4[2] * d2 + w4[3] * d2 * d
+        ref[a] = (w * val[nb]).sum() / w.sum() if w.sum() > 0 else (w * val[nb]).sum()
+    assert np.abs(ref - avg_g).max() <= 1e-10 * scale
+    o.close(); ctx.close()
+
+
 @pytest.mark.parametrize("name,steps", [("C5", 40), ("C4", 3), ("C1", 6)])
 def test_full_size_workloads_against_the_oracle(name, steps):
     """parity where the numbers are quoted (BASELINE.json configs at their stated size, the inputs bench.py times): the CUDA path and

@@ -33,6 +33,10 @@ REFERENCE_SLOTS = {
     # src/mpi/particle_displ_over.cu:101-109 (the MPI communicator and the async request live in the ctx)
     "particle_displ_over": [("grid", "INPUT", False), ("domain", "INPUT", False), ("backup_r", "INPUT", False), ("threshold", "INPUT", False),
                             ("threshold_lab", "INPUT", False), ("async", "INPUT", False), ("result", "OUTPUT", False)],
+    # src/compute/average_neighbors.cu:119-131
+    "average_neighbors_scalar": [("rcut", "INPUT", False), ("weight_function", "INPUT", False), ("chunk_neighbors", "INPUT", False), ("domain", "INPUT", True),
+                                 ("particle_type_properties", "INPUT", False), ("avg_field", "INPUT", True), ("nbh_field", "INPUT", True),
+                                 ("rcut_max", "INPUT_OUTPUT", False), ("grid", "INPUT_OUTPUT", False)],
 }
 HOT_PATH_OPERATORS = ["domain", "init_rcb_grid", "lattice", "gaussian_noise_r", "nbh_dist", "move_particles", "migrate_cell_particles",
                       "rebuild_amr", "backup_r", "ghost_comm_scheme", "ghost_update_all", "ghost_update_r", "amr_grid_pairs", "chunk_neighbors",

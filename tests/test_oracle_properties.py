@@ -100,3 +100,33 @@ def test_half_symmetric_lists_and_newton3_sweep(case):
     assert o.stream_total_u16() < n_full
     o.set_nbh_config(); o.build_neighbors()
     assert o.stream_total_u16() == n_full
+
+
+@pytest.mark.parametrize("field,weights", [("vx", (1.0,)), ("id", (1.0, 0.0, -0.05)), ("rz", (2.0, -0.3, 0.0, 0.01))])
+@pytest.mark.parametrize("case", ["lj2k", "lj_voids"])
+def test_average_neighbors_against_brute_force(case, field, weights):
+    """average_neighbors_scalar (src/compute/average_neighbors.cu:38-100): the reference ships no test for it; the restatement is pinned
+    by an all-pairs evaluation with minimum-image distances (position fields: of the listed image, i.e. unwrapped relative to a)"""
+    kw = CASES[case]
+    o = O.Oracle(O.make_config(**kw))
+    o.init()
+    rcut = kw["rcut"]
+    w4 = tuple(weights) + (0.0,) * (4 - len(weights))
+    avg = o.average_neighbors(rcut, field, w4)
+    p = o.particles(); m = o.inner_mask()
+    L = np.array(kw["bounds_max"]); r = np.stack([p["rx"][m], p["ry"][m], p["rz"][m]], 1)
+    val = p[field][m].astype(np.float64); got = avg[m]
+    assert np.all(avg[~m] == 0.0)
+    n = len(val)
+    ref = np.zeros(n)
+    for a in range(n):
+        d = r - r[a]; sh = L * np.round(d / L); d -= sh
+        d2 = (d ** 2).sum(1)
+        sel = (d2 > 0) & (d2 <= rcut * rcut)
+        dd = np.sqrt(d2[sel])
+        w = w4[0] + w4[1] * dd + w4[2] * d2[sel] + w4[3] * d2[sel] * dd
+        v = val[sel] - (sh[sel, 2] if field == "rz" else 0.0)       # a ghost image carries the shifted coordinate
+        ref[a] = (w * v).sum() / w.sum() if w.sum() > 0 else (w * v).sum()
+    scale = max(np.abs(ref).max(), 1e-300)
+    assert np.abs(ref - got).max() <= 1e-11 * scale
+    o.close()
