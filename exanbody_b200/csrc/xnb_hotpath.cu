@@ -133,7 +133,7 @@ struct xnb_ctx
   DBuf<double> it_outer;
   DBuf<uint32_t> rc_dst_cell, rc_count, rc_offset;
   DBuf<uint32_t> send_src; DBuf<uint16_t> send_flags;
-  DBuf<double> stage, rstage, lb_costs, generic_field; int64_t generic_field_n = -1; DBuf<uint8_t> stage_type;
+  DBuf<double> stage, rstage, lb_costs, generic_field; int64_t generic_field_n = -1;
   DBuf<uint32_t> d_ghost_base;                          // device copy of h_send_base | h_recv_base (nranks + 1 entries each)
   std::vector<uint32_t> h_send_base, h_recv_base, h_ghost_base;      // per partner particle offsets [nranks+1]; both, back to back
   int64_t n_send = 0, n_ghost = 0;
@@ -162,7 +162,7 @@ struct xnb_ctx
   DBuf<uint32_t> d_scalars32;             // [0] error word, [1] leave_count, [2] max_side, [3] max_nbh, [4] scan total, [8..8+64) migrate counts
   DBuf<double> ev_partials, ev_scratch, ev_ekin;
   DBuf<int> d_blocks;
-  DBuf<uint32_t> mig_rank, mig_pos, mig_base;
+  DBuf<uint32_t> mig_rank, mig_pos, mig_base; std::vector<uint32_t> h_mig_base;     // mig_base: per destination send offsets | per source receive offsets (nranks + 1 each)
   // ---- xnb_step_host: positions (and ids) go back to the host on their own stream as soon as they are final
   struct HostOut { bool active = false, issued = false, id_always = false, id_copied = false; double* r[3] = {nullptr, nullptr, nullptr}; uint64_t* id = nullptr; };
   HostOut hout; cudaStream_t st_d2h = nullptr; cudaEvent_t ev_d2h_go = nullptr, ev_d2h_done = nullptr;
@@ -671,7 +671,7 @@ int xnb_move_particles(xnb_ctx* c, void* stream)
     // destination ranks and per-destination counts
     uint32_t* d_cnt = s32 + 8;
     CK(cudaMemsetAsync(d_cnt, 0, 64 * 4, st));
-    CK(c->mig_rank.ensure((size_t)n_leave + 16)); CK(c->mig_pos.ensure((size_t)n_leave + 16)); CK(c->mig_base.ensure(64));
+    CK(c->mig_rank.ensure((size_t)n_leave + 16)); CK(c->mig_pos.ensure((size_t)n_leave + 16));
     if (c->nranks > 64) return c->fail(XNB_ERR_INVALID, "more than 64 ranks not supported");
     if (n_leave) LAUNCH(k_migrate_dest, nblk(n_leave, 128), 128, st, g, (int)n_leave, c->leave_list.p, A.rx, A.ry, A.rz, c->d_blocks.p, c->nranks,
                         c->mig_rank.p, c->mig_pos.p, d_cnt, s32);
@@ -686,9 +686,12 @@ int xnb_move_particles(xnb_ctx* c, void* stream)
     for (int p = 0; p < c->nranks; p++) { sbase[(size_t)p + 1] = sbase[(size_t)p] + hmat[(size_t)c->rank * 64 + p]; rbase[(size_t)p + 1] = rbase[(size_t)p] + hmat[(size_t)p * 64 + c->rank]; }
     n_arrive = rbase[(size_t)c->nranks];
     if ((int64_t)sbase[(size_t)c->nranks] != n_leave) return c->fail(XNB_ERR_LOST_PARTICLE, "migration: particles without owner");
-    CK(cudaMemcpyAsync(c->mig_base.p, sbase.data(), (size_t)c->nranks * 4, cudaMemcpyHostToDevice, st));
-    CK(c->stage.ensure((size_t)n_leave * 10 + 16, 0, 1.5)); CK(c->stage_type.ensure((size_t)n_leave + 16, 0, 1.5));
-    if (n_leave) LAUNCH(k_migrate_pack, nblk(n_leave, 128), 128, st, (int)n_leave, c->leave_list.p, c->mig_rank.p, c->mig_pos.p, c->mig_base.p, A, c->stage.p, c->stage_type.p);
+    // one message per partner and direction (like the halo): slabs of GHOST_WORDS_ALL words per particle, scattered by k_ghost_unpack
+    c->h_mig_base.assign(sbase.begin(), sbase.end()); c->h_mig_base.insert(c->h_mig_base.end(), rbase.begin(), rbase.end());
+    CK(c->mig_base.ensure(2 * ((size_t)c->nranks + 1) + 4));
+    CK(cudaMemcpyAsync(c->mig_base.p, c->h_mig_base.data(), c->h_mig_base.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(c->stage.ensure((size_t)n_leave * GHOST_WORDS_ALL + 16, 0, 1.5)); CK(c->rstage.ensure((size_t)n_arrive * GHOST_WORDS_ALL + 16, 0, 1.5));
+    if (n_leave) LAUNCH(k_migrate_pack, nblk(n_leave, 128), 128, st, (int)n_leave, c->leave_list.p, c->mig_rank.p, c->mig_pos.p, c->mig_base.p, A, c->stage.p);
     rc = ensure_particle_capacity(c, (size_t)(n + n_arrive), (size_t)n); if (rc) return rc;
     A = c->P(c->cur);
     CK(c->key.ensure((size_t)(n + n_arrive) + 16, (size_t)n, 1.2)); CK(c->rnk.ensure((size_t)(n + n_arrive) + 16, (size_t)n, 1.2));
@@ -697,20 +700,11 @@ int xnb_move_particles(xnb_ctx* c, void* stream)
     {
       const size_t ns = sbase[(size_t)p + 1] - sbase[(size_t)p], nr = rbase[(size_t)p + 1] - rbase[(size_t)p];
       if (p == c->rank) continue;
-      if (ns)
-      {
-        for (int f = 0; f < 9; f++) NK(g_nccl.Send(c->stage.p + (size_t)f * n_leave + sbase[(size_t)p], ns, nccl_float64, p, c->comm, st));
-        NK(g_nccl.Send(c->stage.p + (size_t)9 * n_leave + sbase[(size_t)p], ns, nccl_uint64, p, c->comm, st));
-        NK(g_nccl.Send(c->stage_type.p + sbase[(size_t)p], ns, nccl_uint8, p, c->comm, st));
-      }
-      if (nr)
-      {
-        for (int f = 0; f < 9; f++) NK(g_nccl.Recv(c->f64[c->cur][f].p + n + rbase[(size_t)p], nr, nccl_float64, p, c->comm, st));
-        NK(g_nccl.Recv(c->idb[c->cur].p + n + rbase[(size_t)p], nr, nccl_uint64, p, c->comm, st));
-        NK(g_nccl.Recv(c->typeb[c->cur].p + n + rbase[(size_t)p], nr, nccl_uint8, p, c->comm, st));
-      }
+      if (ns) NK(g_nccl.Send(c->stage.p + (size_t)GHOST_WORDS_ALL * sbase[(size_t)p], (size_t)GHOST_WORDS_ALL * ns, nccl_float64, p, c->comm, st));
+      if (nr) NK(g_nccl.Recv(c->rstage.p + (size_t)GHOST_WORDS_ALL * rbase[(size_t)p], (size_t)GHOST_WORDS_ALL * nr, nccl_float64, p, c->comm, st));
     }
     NK(g_nccl.GroupEnd());
+    if (n_arrive) LAUNCH((k_ghost_unpack<true>), nblk(n_arrive, 256), 256, st, (int)n_arrive, (uint32_t)n, A, c->mig_base.p + (size_t)c->nranks + 1, c->nranks, -1, c->rstage.p);
     // locate the arrivals (they are inside my block by construction)
     if (n_arrive) LAUNCH(k_bin_locate, nblk(n_arrive, 256), 256, st, g, (int)n_arrive, A.rx + n, A.ry + n, A.rz + n, c->key.p + n, c->rnk.p + n, c->cell_count.p,
                          (uint32_t*)nullptr, s32 + 1, s32);
@@ -1015,7 +1009,8 @@ int xnb_ghost_comm_scheme(xnb_ctx* c, void* stream)
 static int ghost_update(xnb_ctx* c, bool all, cudaStream_t st)
 {
   const GridP& g = c->g;
-  if (c->n_send == 0 && c->n_ghost == 0) return XNB_OK;
+  // (the exchange counter of the peer transport advances on every rank alike, also on one that has nothing to send or receive)
+  if (c->n_send == 0 && c->n_ghost == 0 && !(c->nranks > 1 && c->peer.enabled)) return XNB_OK;
   ParticlesP A = c->P(c->cur);
   const int self_first = (int)c->h_send_base[(size_t)c->rank], self_end = (int)c->h_send_base[(size_t)c->rank + 1];
   const uint32_t self_dst = (uint32_t)(c->n_inner + c->h_recv_base[(size_t)c->rank]);

@@ -1201,22 +1201,25 @@ __global__ void k_migrate_dest(GridP g, int n_leave, const uint32_t* __restrict_
   dest_pos[q] = atomicAdd(&dest_count[owner], 1u);
 }
 
-// stage = 10 planes of n_leave 8-byte words (rx ry rz vx vy vz fx fy fz id) + one byte plane (type); slot = base[rank]+pos
+// migrating particles travel like ghosts with all fields: ONE contiguous slab per destination rank, field-major, 8-byte words
+// (x y z vx vy vz fx fy fz id type); destination r's entries [base[r], base[r+1]) occupy words [11 base[r], 11 base[r+1]) and the
+// receiver scatters them with k_ghost_unpack<true> (same layout on the wire).
 __global__ void k_migrate_pack(int n_leave, const uint32_t* __restrict__ leave_list, const uint32_t* __restrict__ dest_rank,
-                               const uint32_t* __restrict__ dest_pos, const uint32_t* __restrict__ dest_base, ParticlesP p,
-                               double* __restrict__ stage, uint8_t* __restrict__ stage_type)
+                               const uint32_t* __restrict__ dest_pos, const uint32_t* __restrict__ dest_base /* nranks + 1 */, ParticlesP p,
+                               double* __restrict__ stage)
 {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_leave) return;
   const uint32_t r = dest_rank[q];
   if (r == 0xFFFFFFFFu) return;
   const uint32_t i = leave_list[q];
-  const size_t n = (size_t)n_leave, k = (size_t)dest_base[r] + dest_pos[q];
-  stage[k] = p.rx[i]; stage[n + k] = p.ry[i]; stage[2 * n + k] = p.rz[i];
-  stage[3 * n + k] = p.vx[i]; stage[4 * n + k] = p.vy[i]; stage[5 * n + k] = p.vz[i];
-  stage[6 * n + k] = p.fx[i]; stage[7 * n + k] = p.fy[i]; stage[8 * n + k] = p.fz[i];
-  reinterpret_cast<unsigned long long*>(stage)[9 * n + k] = p.id[i];
-  stage_type[k] = p.type[i];
+  const size_t s0 = dest_base[r], n = dest_base[r + 1] - s0;
+  double* slab = stage + (size_t)GHOST_WORDS_ALL * s0 + dest_pos[q];
+  slab[0] = p.rx[i]; slab[n] = p.ry[i]; slab[2 * n] = p.rz[i];
+  slab[3 * n] = p.vx[i]; slab[4 * n] = p.vy[i]; slab[5 * n] = p.vz[i];
+  slab[6 * n] = p.fx[i]; slab[7 * n] = p.fy[i]; slab[8 * n] = p.fz[i];
+  reinterpret_cast<unsigned long long*>(slab)[9 * n] = p.id[i];
+  reinterpret_cast<unsigned long long*>(slab)[10 * n] = (unsigned long long)p.type[i];
 }
 
 // simple_cost_model (src/mpi/include/exanb/mpi/simple_cost_model.h:67-146) on the device: cost of every INNER cell of this rank's block
