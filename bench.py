@@ -468,6 +468,10 @@ def b200_arm(args):
     inner = ((i >= gl) & (i < d[0] - gl) & (j >= gl) & (j < d[1] - gl) & (k >= gl) & (k < d[2] - gl)).ravel()
     S = 2.0 * float(sz[inner].sum()) / max(n_atoms_local, 1)          # stream bytes per inner atom (reference u16 format)
     force_bytes = 97.0 + S                                            # R r 24 + R stream S + W f 24 + R v 24 + R type 1 + W v 24
+    # inside xnb_run_steps the sweep of step k also performs the first half of step k + 1 (k_lj_sweep_cl MODE 2): + W r' 24 + R backup 12
+    # on those launches (all steps but the last of the call; the stand-alone first-half kernel then does not run)
+    fused_frac = max(0.0, 1.0 - tim["first_half"]["n"] / float(max(args.steps, 1)))
+    force_bytes += 36.0 * fused_frac
     step_bytes = 253.0 + S                                            # minimal fused traffic of a steady step
     peak, peak_src = measured_peaks()
     fk_ms = tim["force"]["ms"] / max(tim["force"]["n"], 1)
@@ -478,14 +482,14 @@ def b200_arm(args):
     roofline = {"bound": "hbm", "kernel": kname + " (pair sweep + fused second half kick)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(kname, name), "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/ncu_traffic.json)",
                 "algorithmic_bytes_per_launch": force_bytes * n_atoms_local, "peak_source": peak_src,
-                "algorithmic_bytes_per_atom": force_bytes, "stream_bytes_per_atom": S, "kernel_ms": fk_ms,
+                "algorithmic_bytes_per_atom": force_bytes, "stream_bytes_per_atom": S, "kernel_ms": fk_ms, "fused_next_first_half_fraction": fused_frac,
                 "whole_step": {"algorithmic_bytes_per_atom": step_bytes, "achieved": step_bytes * value / world / 1e9, "frac": step_bytes * value / world / 1e9 / peak},
                 "sweep": {"compiled_lists": si["compiled"], "tile_cells": si["tile"], "threads": si["threads"], "blocks": si["blocks"], "smem_bytes": si["smem_bytes"],
                           "list_entries_per_atom": n_list, "compiled_list_bytes_per_atom": (si["rows"] * 256.0 / max(n_atoms_local, 1)) if si["compiled"] else None}}
     breakdown = {k2: (v["ms"] / args.steps) for k2, v in tim.items()}
     dom = max(breakdown, key=lambda k2: breakdown[k2]) if breakdown else None
     roofline["dominant_by_time"] = {"group": dom, "ms_per_step": breakdown.get(dom), "share_of_step": (breakdown.get(dom, 0.0) / (ms / args.steps)) if ms > 0 else None,
-                                    "groups": "force = pair sweep, nbh = chunk_neighbors (k_nbh_bits), first_half = verlet_first_half + displacement test, "
+                                    "groups": "force = pair sweep (+ second half kick, + the next step's first half when fused), nbh = chunk_neighbors (k_nbh_bits), first_half = verlet_first_half + displacement test, "
                                               "bin = move_particles + rebuild_amr + backup_r, ghost_scheme / ghost_update = halo"}
 
     # ---- end to end through the C-ABI with host buffers -----------------------------------------------------------------

@@ -147,6 +147,7 @@ struct xnb_ctx
   struct ClCfg { bool valid = false, ghost = false; int planes = 0, cap_pl = 0; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; int64_t candidates = 0;
                  unsigned n_interior = 0, n_boundary = 0; };    // tiles whose halo box holds no ghost cell / the others (cl_tile_list: interior first)
   ClCfg cl;
+  NextHalfP next_half{};                   // operands of a MODE 2 sweep (xnb_run_steps sets them right before the launch)
   DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0; DBuf<uint32_t> cl_tile_list;
   // ---- k_nbh_bits (xnb_nbh_bits.cuh): masks parked between its two phases, capacities that worked last time, lazily built ghost-cell lists
   int nb_cap_l = 0, nb_cap_trips = 0; bool ghost_lists = false;       // ghost_lists: the streams of the ghost cells are current
@@ -206,6 +207,7 @@ struct xnb_ctx
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return c->fail(XNB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
 #define NK(call) do { ncclResult_t r__ = (call); if (r__ != 0) return c->fail(XNB_ERR_NCCL, std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error")); } while (0)
 // timing scope helpers: record an event pair around a group of launches (no host synchronisation)
+static int verlet_first_half(xnb_ctx* c, double dt, cudaStream_t st, unsigned long long* counter);
 static int t_begin(xnb_ctx* c, int cat, cudaStream_t st);
 static int t_end(xnb_ctx* c, int cat, cudaStream_t st);
 #define LAUNCH(kernel, grid, block, stream, ...) do { kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); c->launches++; CK(cudaGetLastError()); } while (0)
@@ -1659,7 +1661,7 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
   {
     const xnb_ctx::ClCfg& k = c->cl;
     if (EV) { CK(c->ev_partials.ensure((size_t)k.blocks * 7 + 16)); if (evp_out) *evp_out = c->ev_partials.p; if (nblocks_out) *nblocks_out = k.blocks; }
-    static bool cl_attr_done_dev[XNB_MAX_DEVICES][2][2][4] = {};
+    static bool cl_attr_done_dev[XNB_MAX_DEVICES][3][2][4] = {};
     auto& cl_attr_done = cl_attr_done_dev[c->device % XNB_MAX_DEVICES];
 #define XNB_CL_LAUNCH(VAR) do { \
       if (!cl_attr_done[MODE][EV ? 1 : 0][VAR]) { \
@@ -1667,7 +1669,7 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
         CK(cudaFuncSetAttribute((k_lj_sweep_cl<F, MODE, EV, VAR>), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024 - (int)fa.sharedSizeBytes)); \
         cl_attr_done[MODE][EV ? 1 : 0][VAR] = true; } \
       if (part == 0 && (rc = t_begin(c, XNB_T_FORCE, st))) return rc; \
-      k_lj_sweep_cl<F, MODE, EV, VAR><<<nb, k.threads, k.smem, st>>>(c->g, k.tp, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, \
+      k_lj_sweep_cl<F, MODE, EV, VAR><<<nb, k.threads, k.smem, st>>>(c->g, k.tp, (int)c->n_inner, (int)c->n_total, lj, dth, c->next_half, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz, \
           fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, c->cl_groups.p, \
           reinterpret_cast<const uint2*>(c->cl_rows.p), EV ? c->ev_partials.p : nullptr, c->d_scalars32.p, skip_if_nonzero, tl); } while (0)
     const unsigned nb = part == 0 ? k.blocks : part == 1 ? k.n_interior : k.n_boundary;
@@ -1675,6 +1677,8 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
     if (nb == 0) return XNB_OK;
     if (k.planes)
     {
+      if constexpr (MODE == 2) return c->fail(XNB_ERR_INVALID, "fused next first half: not offered by the plane-staged sweep");
+      else {
       // large cells: rows in plane segments, one plane of the halo staged at a time (xnb_sweep_pl.cuh)
       static bool pl_attr_done_dev[XNB_MAX_DEVICES][2][2] = {};
       auto& pl_attr_done = pl_attr_done_dev[c->device % XNB_MAX_DEVICES];
@@ -1690,12 +1694,15 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
           reinterpret_cast<const uint2*>(c->cl_rows.p), EV ? c->ev_partials.p : nullptr, c->d_scalars32.p, skip_if_nonzero, tl);
       c->launches++; CK(cudaGetLastError());
       return part == 0 ? t_end(c, XNB_T_FORCE, st) : XNB_OK;
+      }
     }
     if (k.var == 0) XNB_CL_LAUNCH(0); else if (k.var == 1) XNB_CL_LAUNCH(1); else if (k.var == 2) XNB_CL_LAUNCH(2); else XNB_CL_LAUNCH(3);
 #undef XNB_CL_LAUNCH
     c->launches++; CK(cudaGetLastError());
     return part == 0 ? t_end(c, XNB_T_FORCE, st) : XNB_OK;
   }
+  if constexpr (MODE == 2) return c->fail(XNB_ERR_INVALID, "fused next first half: needs the compiled lists");
+  else {
   const TileCfg t = make_tiles(c, ghost);
   if (t.blocks == 0) return XNB_OK;
   if (EV) { CK(c->ev_partials.ensure((size_t)t.blocks * 7 + 16)); if (evp_out) *evp_out = c->ev_partials.p; if (nblocks_out) *nblocks_out = t.blocks; }
@@ -1713,6 +1720,7 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
       c->stream_size.p, EV ? c->ev_partials.p : nullptr, skip_if_nonzero);
   c->launches++; CK(cudaGetLastError());
   return t_end(c, XNB_T_FORCE, st);
+  }
 }
 
 // the functor the sweeps are instantiated with: the restated LJ functor (four-candidate hook) or the literal reference form
@@ -1940,16 +1948,7 @@ int xnb_verlet_first_half(xnb_ctx* c, double dt, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;
   CK(cudaSetDevice(c->device));
-  c->amr_current = false;      // positions change: the sub-cell tables no longer bound them
-  c->steps_since_nbh++;
-  cudaStream_t st = (cudaStream_t)stream;
-  ParticlesP A = c->P(c->cur);
-  int rc;
-  if ((rc = t_begin(c, XNB_T_FIRST_HALF, st))) return rc;
-  CK(cudaMemsetAsync(c->d_scalars64.p, 0, 8, st));
-  if (c->n_inner) LAUNCH(k_verlet_first_half, nblk(c->n_inner, 256), 256, st, c->g, (int)c->n_inner, dt, dt * dt * 0.5, dt * 0.5, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
-                         A.fx, A.fy, A.fz, c->atom_cell[c->cur_ac].p, c->backup.p, c->max_displ * c->max_displ, c->d_scalars64.p);
-  return t_end(c, XNB_T_FIRST_HALF, st);
+  return verlet_first_half(c, dt, (cudaStream_t)stream, c->d_scalars64.p);
 }
 
 int xnb_force_and_second_half(xnb_ctx* c, double eps, double sig, double rcut, double dth, void* stream)
@@ -2006,6 +2005,28 @@ int xnb_first_iteration(xnb_ctx* c, double eps, double sig, double rcut, void* s
   return xnb_force_and_second_half(c, eps, sig, rcut, 0.0, stream);
 }
 
+} // extern "C"
+// the first half kick with its displacement count going to `counter` (xnb_verlet_first_half: slot 0 of d_scalars64)
+static int verlet_first_half(xnb_ctx* c, double dt, cudaStream_t st, unsigned long long* counter)
+{
+  c->amr_current = false;      // positions change: the sub-cell tables no longer bound them
+  c->steps_since_nbh++;
+  ParticlesP A = c->P(c->cur);
+  int rc;
+  if ((rc = t_begin(c, XNB_T_FIRST_HALF, st))) return rc;
+  CK(cudaMemsetAsync(counter, 0, 8, st));
+  if (c->n_inner) LAUNCH(k_verlet_first_half, nblk(c->n_inner, 256), 256, st, c->g, (int)c->n_inner, dt, dt * dt * 0.5, dt * 0.5, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
+                         A.fx, A.fy, A.fz, c->atom_cell[c->cur_ac].p, c->backup.p, c->max_displ * c->max_displ, counter);
+  return t_end(c, XNB_T_FIRST_HALF, st);
+}
+// sweep + second half kick; fused: + the first half of the NEXT step in the sweep's epilogue (k_lj_sweep_cl MODE 2)
+static int sweep_step(xnb_ctx* c, bool fused, const LJP& lj, double dth, cudaStream_t st, const unsigned long long* skip, int part)
+{
+  return fused ? launch_force<2, false>(c, false, lj, dth, nullptr, nullptr, nullptr, nullptr, nullptr, st, skip, part)
+               : launch_force<1, false>(c, false, lj, dth, nullptr, nullptr, nullptr, nullptr, nullptr, st, skip, part);
+}
+extern "C" {
+
 int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, double rcut, void* stream, int* rebuilds_out)
 {
   if (!c) return XNB_ERR_INVALID;
@@ -2016,9 +2037,27 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
   if (!c->ev_flag) CK(cudaEventCreateWithFlags(&c->ev_flag, cudaEventDisableTiming));
   volatile unsigned long long* h_flag = reinterpret_cast<volatile unsigned long long*>(static_cast<char*>(c->h_pinned) + 1024);
   const bool speculate = !env_flag("XNB_NO_SPECULATION");
+  const LJP lj = make_lj(eps, sig, rcut);
+  // Between two steps of this loop nothing observes the state, so the sweep of step k also performs the first half of step k + 1 in its
+  // epilogue (MODE 2): a and the kicked v are in registers there.  The new positions go to the other position buffer (other blocks still
+  // stage the old ones) and the two buffers trade places afterwards; the displacement count of step k + 1 goes to the counter slot step k
+  // is not using.  The last step of the call is a plain MODE 1 sweep, so the state a caller sees is the usual one.
+  const bool fuse_ok = speculate && !env_flag("XNB_NO_FUSED_FIRST_HALF") && !c->hout.active;
+  auto can_fuse = [&](int it) { return fuse_ok && it + 1 < nsteps && c->cl.valid && !c->cl.ghost && !c->cl.planes && !env_flag("XNB_SWEEP_STREAMS") && c->n_inner > 0; };
+  auto arm_next_half = [&](unsigned long long* counter) -> int {
+    ParticlesP B = c->P(1 - c->cur);
+    CK(cudaMemsetAsync(counter, 0, 8, st));
+    c->next_half = NextHalfP{dt, dt * dt * 0.5, c->max_displ * c->max_displ, B.rx, B.ry, B.rz, c->atom_cell[c->cur_ac].p, c->backup.p, counter};
+    return 0;
+  };
+  bool pending = false;        // this step's first half was done by the previous sweep
+  int par = 0;                 // which counter slot holds this step's displacement count
   for (int it = 0; it < nsteps; it++)
   {
-    if ((rc = xnb_verlet_first_half(c, dt, stream))) return rc;
+    unsigned long long* const cnt = c->d_scalars64.p + (par ? 9 : 0);
+    unsigned long long* const next_cnt = c->d_scalars64.p + (par ? 0 : 9);
+    if (!pending) { if ((rc = verlet_first_half(c, dt, st, cnt))) return rc; }
+    else { c->amr_current = false; c->steps_since_nbh++; }
     // trigger_move_particles (update-particles.msp:1-6): MPI_Allreduce(SUM, 1 x u64) of particle_displ_over.cu:174, then the
     // host reads the count.  The fast path (ghost_update_r + sweep) is enqueued BEFORE the host waits for that count, so the GPU
     // never idles on the host round trip; the sweep reads the same counter on the device and returns at once if a rebuild is due
@@ -2027,25 +2066,27 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
     {
       if (!c->comm) return c->fail(XNB_ERR_NCCL, "no communicator");
       if (c->peer.enabled)
-        LAUNCH(k_peer_allsum, 1, PEER_MAX_RANKS, st, c->nranks, c->rank, c->peer.d_slots.p, static_cast<const PeerHdr*>(c->peer.box), ++c->peer.epoch_over, c->d_scalars64.p, c->d_scalars32.p);
-      else NK(g_nccl.AllReduce(c->d_scalars64.p, c->d_scalars64.p, 1, nccl_uint64, nccl_sum, c->comm, st));
+        LAUNCH(k_peer_allsum, 1, PEER_MAX_RANKS, st, c->nranks, c->rank, c->peer.d_slots.p, static_cast<const PeerHdr*>(c->peer.box), ++c->peer.epoch_over, cnt, c->d_scalars32.p);
+      else NK(g_nccl.AllReduce(cnt, cnt, 1, nccl_uint64, nccl_sum, c->comm, st));
     }
-    CK(cudaMemcpyAsync(const_cast<unsigned long long*>(h_flag), c->d_scalars64.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(const_cast<unsigned long long*>(h_flag), cnt, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(c->ev_flag, st));
     size_t force_scopes = c->tpool[XNB_T_FORCE].used;
+    bool fused = false;        // the sweep enqueued for this step carries the next first half
     const bool overlap = speculate && c->nranks > 1 && c->cl.valid && !c->cl.ghost && c->cl.n_interior > 0 && c->cl.n_boundary > 0 && !env_flag("XNB_NO_OVERLAP") && !env_flag("XNB_SWEEP_STREAMS");
     if (overlap)
     {
-      // halo exchange (pack kernel + NCCL send/recv) on its own stream while the interior tiles are swept; the boundary tiles
-      // wait for it.  One timing scope spans both sweep launches.
+      // halo exchange on its own stream while the interior tiles are swept; the boundary tiles wait for it.  One timing scope spans
+      // both sweep launches.
       if (!c->st_comm)
       {
-        // highest priority: the pack kernel and the NCCL kernels must get SMs while the interior sweep fills the GPU
+        // highest priority: the exchange kernels must get SMs while the interior sweep fills the GPU
         int prio_lo = 0, prio_hi = 0; CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CK(cudaStreamCreateWithPriority(&c->st_comm, cudaStreamNonBlocking, prio_hi));
         CK(cudaEventCreateWithFlags(&c->ev_pos, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_ghost, cudaEventDisableTiming));
       }
-      const LJP lj = make_lj(eps, sig, rcut);
+      fused = can_fuse(it);
+      if (fused && (rc = arm_next_half(next_cnt))) return rc;
       CK(cudaEventRecord(c->ev_pos, st));
       CK(cudaStreamWaitEvent(c->st_comm, c->ev_pos, 0));
       if ((rc = t_begin(c, XNB_T_GHOST_UPDATE, c->st_comm))) return rc;
@@ -2054,12 +2095,12 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
       // the boundary tiles follow the halo on ITS stream: they start the moment the ghosts are in, alongside whatever is left of
       // the interior sweep (one tail instead of two), and the main stream joins at the end
       const bool boundary_on_comm = !env_flag("XNB_BOUNDARY_ON_MAIN");
-      if (boundary_on_comm && (rc = launch_force<1, false>(c, false, lj, dt * 0.5, nullptr, nullptr, nullptr, nullptr, nullptr, c->st_comm, c->d_scalars64.p, 2))) return rc;
+      if (boundary_on_comm && (rc = sweep_step(c, fused, lj, dt * 0.5, c->st_comm, cnt, 2))) return rc;
       CK(cudaEventRecord(c->ev_ghost, c->st_comm));
       if ((rc = t_begin(c, XNB_T_FORCE, st))) return rc;
-      if ((rc = launch_force<1, false>(c, false, lj, dt * 0.5, nullptr, nullptr, nullptr, nullptr, nullptr, st, c->d_scalars64.p, 1))) return rc;
+      if ((rc = sweep_step(c, fused, lj, dt * 0.5, st, cnt, 1))) return rc;
       CK(cudaStreamWaitEvent(st, c->ev_ghost, 0));
-      if (!boundary_on_comm && (rc = launch_force<1, false>(c, false, lj, dt * 0.5, nullptr, nullptr, nullptr, nullptr, nullptr, st, c->d_scalars64.p, 2))) return rc;
+      if (!boundary_on_comm && (rc = sweep_step(c, fused, lj, dt * 0.5, st, cnt, 2))) return rc;
       if ((rc = t_end(c, XNB_T_FORCE, st))) return rc;
     }
     else if (speculate)
@@ -2067,7 +2108,9 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
       if ((rc = t_begin(c, XNB_T_GHOST_UPDATE, st))) return rc;
       if ((rc = xnb_ghost_update_r(c, stream))) return rc;
       if ((rc = t_end(c, XNB_T_GHOST_UPDATE, st))) return rc;
-      if ((rc = launch_force<1, false>(c, false, make_lj(eps, sig, rcut), dt * 0.5, nullptr, nullptr, nullptr, nullptr, nullptr, st, c->d_scalars64.p))) return rc;
+      fused = can_fuse(it);
+      if (fused && (rc = arm_next_half(next_cnt))) return rc;
+      if ((rc = sweep_step(c, fused, lj, dt * 0.5, st, cnt, 0))) return rc;
     }
     CK(cudaEventSynchronize(c->ev_flag));
     const unsigned long long over = *h_flag;
@@ -2076,7 +2119,9 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
       if (speculate && c->timing && c->tpool[XNB_T_FORCE].used == force_scopes + 1) c->tpool[XNB_T_FORCE].used = force_scopes;   // the void launch is not a sweep
       if ((rc = move_and_update_full(c, stream))) return rc;
       rebuilds++;
-      if ((rc = xnb_force_and_second_half(c, eps, sig, rcut, dt * 0.5, stream))) return rc;
+      fused = can_fuse(it);                       // the void launch did nothing; the sweep after the rebuild may carry the next first half
+      if (fused && (rc = arm_next_half(next_cnt))) return rc;
+      if ((rc = sweep_step(c, fused, lj, dt * 0.5, st, nullptr, 0))) return rc;
     }
     else if ((rc = host_out_positions(c, c->ev_flag, false))) return rc;     // no rebuild: positions are final since the first half
     if (over == 0 && !speculate)
@@ -2085,6 +2130,14 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
       if ((rc = xnb_ghost_update_r(c, stream))) return rc;
       if ((rc = t_end(c, XNB_T_GHOST_UPDATE, st))) return rc;
       if ((rc = xnb_force_and_second_half(c, eps, sig, rcut, dt * 0.5, stream))) return rc;
+    }
+    pending = fused;
+    if (fused)
+    {
+      // the sweep wrote the next positions into the other buffer: the two trade places (pointers and capacities; the ghost slots of
+      // the new current buffer are stale until the next ghost_update_r / rebuild, which always comes first)
+      for (int f = 0; f < 3; f++) { std::swap(c->f64[c->cur][f].p, c->f64[1 - c->cur][f].p); std::swap(c->f64[c->cur][f].cap, c->f64[1 - c->cur][f].cap); }
+      par ^= 1;
     }
   }
   if (rebuilds_out) *rebuilds_out = rebuilds;

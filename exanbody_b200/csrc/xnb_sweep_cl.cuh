@@ -264,9 +264,19 @@ XNB_DEVINL bool in_cut(double d2, double rc2)
       : "=r"(r) : "d"(d2), "d"(rc2));
   return r != 0u;
 }
+// MODE 2 = MODE 1 + the FIRST HALF OF THE NEXT STEP in the same epilogue (xnb_run_steps): with a and the kicked v in registers,
+//   r' = r + (v dt + a dt^2/2), v' = v + a dt/2, displacement test of r' against the backup (k_verlet_first_half's arithmetic, same
+// operations in the same order), r' written to the OTHER position buffer (other blocks still stage r), the count added to `counter`.
+struct NextHalfP
+{
+  double dt, dt2, thr2;
+  double *nrx, *nry, *nrz;
+  const uint32_t* atom_cell; const uint32_t* backup;
+  unsigned long long* counter;
+};
 template <class F, int MODE, bool EV, int VAR>
 __global__ void __launch_bounds__(VAR == 0 ? 576 : VAR == 1 ? 1024 : VAR == 2 ? 288 : 576, VAR == 0 ? 2 : VAR == 1 ? 1 : VAR == 2 ? 3 : 1)
-k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
+k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth, NextHalfP nh,
               const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
               double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
               double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
@@ -370,6 +380,7 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
       pair_apply4<EV>(lj, dx, dy, dz, d2, ok, j, acc);
       w0 = w1;
     }
+    bool over = false;
     if (active)
     {
       double ax = acc.ax, ay = acc.ay, az = acc.az;
@@ -379,9 +390,23 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
       }
       else
       {
+        if (MODE == 2) { m = mass[type[i]]; ux = vx[i]; uy = vy[i]; uz = vz[i]; }      // (MODE 2 has no register to park them in during the loop)
         ax = __ddiv_rn(ax, m); ay = __ddiv_rn(ay, m); az = __ddiv_rn(az, m);
         fx[i] = ax; fy[i] = ay; fz[i] = az;
-        if (dth != 0.0)
+        if (MODE == 2)
+        {
+          // second half of this step, then the first half of the next (push_f_v{0.5}; push_f_v_r{1.0}; push_f_v{0.5})
+          ux = __dadd_rn(ux, __dmul_rn(ax, dth)); uy = __dadd_rn(uy, __dmul_rn(ay, dth)); uz = __dadd_rn(uz, __dmul_rn(az, dth));
+          const double x = __dadd_rn(xa, __dadd_rn(__dmul_rn(ux, nh.dt), __dmul_rn(ax, nh.dt2)));
+          const double y = __dadd_rn(ya, __dadd_rn(__dmul_rn(uy, nh.dt), __dmul_rn(ay, nh.dt2)));
+          const double z = __dadd_rn(za, __dadd_rn(__dmul_rn(uz, nh.dt), __dmul_rn(az, nh.dt2)));
+          nh.nrx[i] = x; nh.nry[i] = y; nh.nrz[i] = z;
+          vx[i] = __dadd_rn(ux, __dmul_rn(ax, dth));
+          vy[i] = __dadd_rn(uy, __dmul_rn(ay, dth));
+          vz[i] = __dadd_rn(uz, __dmul_rn(az, dth));
+          over = displ_over_test(g, nh.atom_cell[i], nh.backup + 3 * (size_t)i, x, y, z, nh.thr2);
+        }
+        else if (dth != 0.0)
         {
           vx[i] = __dadd_rn(ux, __dmul_rn(ax, dth));
           vy[i] = __dadd_rn(uy, __dmul_rn(ay, dth));
@@ -389,8 +414,9 @@ k_lj_sweep_cl(GridP g, ClTileP tp, int n_inner, int n_total, F lj, double dth,
         }
       }
     }
+    if (MODE == 2) block_count_add(over, nh.counter);
   }
-  if (MODE == 1)
+  if (MODE != 0)
   {
     // zero_particle_force{ghost:true}: ghost particles keep f = 0 (each block clears its slice of the ghost range)
     const int ng = n_total - n_inner;

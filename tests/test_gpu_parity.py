@@ -289,6 +289,37 @@ def test_speculative_fast_path_changes_nothing(monkeypatch):
         assert np.array_equal(pa[k], pb[k]), k
 
 
+@pytest.mark.parametrize("case", ["lj2k", "lj_voids", "lj_gap2", "ni16k"])
+def test_fused_next_first_half_changes_nothing(case, monkeypatch):
+    """inside one xnb_run_steps call the sweep of step k also performs the first half of step k + 1 (k_lj_sweep_cl MODE 2: positions
+    into the other buffer, displacement count into the other counter slot).  Same rebuild steps and bit-identical state as the loop
+    with a stand-alone first-half kernel and as thirty single-step calls, also across two consecutive calls"""
+    kw = CASES[case]
+    eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
+    out = []
+    for mode in ("fused", "plain", "single"):
+        if mode == "plain":
+            monkeypatch.setenv("XNB_NO_FUSED_FIRST_HALF", "1")
+        else:
+            monkeypatch.delenv("XNB_NO_FUSED_FIRST_HALF", raising=False)
+        _, ctx = setup_pair(kw)
+        ctx.first_iteration(eps, sig, rc)
+        l0 = ctx.kernel_launches()
+        if mode == "single":
+            rb = sum(ctx.run_steps(1, dt, eps, sig, rc) for _ in range(30))
+        else:
+            rb = ctx.run_steps(23, dt, eps, sig, rc) + ctx.run_steps(7, dt, eps, sig, rc)
+        out.append((rb, ctx.get_particles(0, ctx.n_inner), ctx.kernel_launches() - l0, ctx.energy_virial(eps, sig, rc)))
+        ctx.close()
+    assert out[0][0] == out[1][0] == out[2][0] and (out[0][0] > 0 or case == "ni16k")      # (the Ni deck does not rebuild within 30 steps)
+    for other in (1, 2):
+        for k in ("id", "rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
+            assert np.array_equal(out[0][1][k], out[other][1][k]), (k, other)
+        assert all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(out[0][3], out[other][3]))
+    if case != "ni16k":                      # (large cells: the plane-staged sweep has no fused form)
+        assert out[0][2] < out[1][2]         # the fused loop launches fewer kernels
+
+
 @pytest.mark.parametrize("case", ["ni16k", "lj2k", "lj_gap2", "lj_voids"])
 def test_newton3_path(case):
     """SURVEY 8f rank 2: chunk_neighbors with ChunkNeighborsConfig::half_symmetric / skip_ghosts (neighbor_filter_func.h:36-52)
