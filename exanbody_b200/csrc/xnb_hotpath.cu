@@ -147,6 +147,8 @@ struct xnb_ctx
   struct ClCfg { bool valid = false, ghost = false; int planes = 0, cap_pl = 0; ClTileP tp{}; int threads = 0, var = 0; size_t smem = 0; unsigned blocks = 0; uint32_t rows = 0; int64_t candidates = 0;
                  unsigned n_interior = 0, n_boundary = 0; };    // tiles whose halo box holds no ghost cell / the others (cl_tile_list: interior first)
   ClCfg cl;
+  bool in_rebuild_chain = false;           // move_and_update_full: the operators' small read-backs are merged (one host wait each for binning, ghosts, lists)
+  bool cell_stats_valid = false;           // max_cell_count / n_nonempty_inner describe the current cell counts (ghost cells included)
   NextHalfP next_half{};                   // operands of a MODE 2 sweep (xnb_run_steps sets them right before the launch)
   DBuf<uint2> cl_groups; DBuf<uint16_t> cl_rows; uint32_t cl_cap_rows = 0; DBuf<uint32_t> cl_tile_list;
   // ---- k_nbh_bits (xnb_nbh_bits.cuh): masks parked between its two phases, capacities that worked last time, lazily built ghost-cell lists
@@ -375,12 +377,9 @@ int ensure_grid(xnb_ctx* c)
   return 0;
 }
 
-int check_device_errors(xnb_ctx* c, cudaStream_t st)
+// what the device error word says (and clear it)
+int decode_device_errors(xnb_ctx* c, uint32_t e, cudaStream_t st)
 {
-  uint32_t* h = (uint32_t*)c->h_pinned;
-  CK(cudaMemcpyAsync(h, c->d_scalars32.p, 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  const uint32_t e = h[0];
   if (!e) return 0;
   CK(cudaMemsetAsync(c->d_scalars32.p, 0, 4, st));
   if (e & DERR_LOST_PARTICLE) return c->fail(XNB_ERR_LOST_PARTICLE, "a particle left a non periodic domain (reference: stays in otb_particles)");
@@ -391,6 +390,14 @@ int check_device_errors(xnb_ctx* c, cudaStream_t st)
   if (e & DERR_TILE_CAPACITY) return c->fail(XNB_ERR_CAPACITY, "a tile exceeded its shared-memory staging capacity");
   if (e & DERR_PEER_TIMEOUT) return c->fail(XNB_ERR_NCCL, "peer-memory halo: a partner's data did not arrive within 20 s");
   return c->fail(XNB_ERR_INVALID, "device error word " + std::to_string(e));
+}
+
+int check_device_errors(xnb_ctx* c, cudaStream_t st)
+{
+  uint32_t* h = (uint32_t*)c->h_pinned;
+  CK(cudaMemcpyAsync(h, c->d_scalars32.p, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return decode_device_errors(c, h[0], st);
 }
 
 // small synchronous read-back through the pinned scratch page
@@ -719,6 +726,10 @@ int xnb_move_particles(xnb_ctx* c, void* stream)
   if (n_src) LAUNCH(k_bin_scatter, nblk(n_src, 256), 256, st, (int)n_src, c->key.p, c->rnk.p, c->cell_start.p, c->perm.p);
   // cells beyond the shared-memory sort capacity rank through global scratch (12 bytes per particle)
   CK(c->sort_keys.ensure((size_t)n_src + 16, 0, 1.2)); CK(c->sort_srcs.ensure((size_t)n_src + 16, 0, 1.2));
+  // the fullest cell at the last neighbour build tells which kernel suits (either one is correct for any occupancy)
+  if ((c->max_cell_count > 0 && c->max_cell_count <= 32 && !env_flag("XNB_CELLSORT_BLOCK")) || env_flag("XNB_CELLSORT_WARP"))
+    LAUNCH(k_cell_sort_warp, std::min(nblk(g.n_cells, 8), 148u * 16u), 256, st, g.n_cells, c->cell_start.p, c->cell_count.p, c->perm.p, c->perm2.p, A.id, c->sort_keys.p, c->sort_srcs.p, s32);
+  else
   LAUNCH((k_cell_sort<false>), (unsigned)g.n_cells, CELLSORT_THREADS, st, g, c->cell_start.p, c->cell_count.p, c->perm.p, c->perm2.p,
          A.rx, A.ry, A.rz, A.id, c->side_lut.p, (const unsigned long long*)nullptr, (uint32_t*)nullptr, c->sort_keys.p, c->sort_srcs.p, s32);
   rc = ensure_particle_capacity(c, (size_t)std::max<int64_t>(n_new, 1), (size_t)n_src); if (rc) return rc;
@@ -728,6 +739,8 @@ int xnb_move_particles(xnb_ctx* c, void* stream)
   c->cur = 1 - c->cur; c->cur_ac = 1 - c->cur_ac;
   c->n_inner = n_new; c->n_total = n_new; c->n_ghost = 0; c->have_nbh = false; c->amr_current = false;
   LAUNCH(k_ghost_cells_clear, nblk(g.n_cells, 256), 256, st, g, (uint32_t)n_new, c->cell_start.p, c->cell_count.p);
+  c->cell_stats_valid = false;
+  if (c->in_rebuild_chain) return XNB_OK;          // rebuild_amr, next in the chain, reads the error word with its own results
   return check_device_errors(c, st);
 }
 
@@ -809,8 +822,16 @@ int xnb_rebuild_amr(xnb_ctx* c, void* stream)
   LAUNCH(k_amr_sizes, nblk(g.n_cells, 256), 256, st, g, c->cell_count.p, c->side_lut.p, c->sg_size.p, s32 + 2);
   rc = scan_exclusive<uint32_t, unsigned long long>(c, c->sg_size.p, c->sub_grid_start.p, (size_t)g.n_cells + 1, c->d_scalars64.p + 1, c->scan_tmp64, st); if (rc) return rc;
   uint32_t ms = 0; unsigned long long tot = 0;
-  rc = read_back(c, s32 + 2, 1, &ms, st); if (rc) return rc;
-  rc = read_back(c, c->d_scalars64.p + 1, 1, &tot, st); if (rc) return rc;
+  {
+    // one host wait: error word (binning before me may have deferred its check), largest sub-grid side, sub-grid cell total
+    char* hp = static_cast<char*>(c->h_pinned);
+    CK(cudaMemcpyAsync(hp + 256, s32, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hp + 288, c->d_scalars64.p + 1, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint32_t w[4]; memcpy(w, hp + 256, 16); memcpy(&tot, hp + 288, 8);
+    if ((rc = decode_device_errors(c, w[0], st))) return rc;
+    ms = w[2];
+  }
   c->max_side = std::max(ms, 1u); c->n_sub_grid_cells = (int64_t)tot; c->amr_current = true;
   if (ms <= 1) return XNB_OK;          // every cell has a 1x1x1 sub grid: nothing to reorder (C2/C3)
   const int64_t n = c->n_inner;
@@ -986,7 +1007,15 @@ int xnb_ghost_comm_scheme(xnb_ctx* c, void* stream)
   std::vector<uint32_t> hso((size_t)ns + 1), hro((size_t)nr + 1);
   CK(cudaMemcpyAsync(hso.data(), c->it_offset.p, ((size_t)ns + 1) * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(hro.data(), c->rc_offset.p, ((size_t)nr + 1) * 4, cudaMemcpyDeviceToHost, st));
+  // occupancy of the grid for the neighbour build that follows (its tile shape and capacities), read in the same host wait: the inner
+  // cells as binned, the ghost cells from the receive counts (one receive item per ghost cell)
+  uint32_t cstats[2] = {0, 0};
+  CK(cudaMemsetAsync(c->d_scalars32.p + 5, 0, 8, st));
+  LAUNCH(k_cell_stats, nblk(g.n_cells, 256), 256, st, g, c->cell_count.p, c->d_scalars32.p + 5);
+  if (nr) LAUNCH(k_max_u32, nblk(nr, 256), 256, st, nr, c->rc_count.p, c->d_scalars32.p + 5);
+  CK(cudaMemcpyAsync(cstats, c->d_scalars32.p + 5, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  c->max_cell_count = std::max<uint32_t>(cstats[0], 1); c->n_nonempty_inner = cstats[1]; c->cell_stats_valid = true;
   for (int p = 0; p <= c->nranks; p++) { c->h_send_base[(size_t)p] = hso[(size_t)c->send_first[(size_t)p]]; c->h_recv_base[(size_t)p] = hro[(size_t)c->recv_first[(size_t)p]]; }
   c->n_send = hso[(size_t)ns]; c->n_ghost = hro[(size_t)nr];
   {
@@ -1274,8 +1303,11 @@ static int nbh_big_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
       char* hp = static_cast<char*>(c->h_pinned);
       CK(cudaMemcpyAsync(hp, counters, NB_U32_COUNT * 4, cudaMemcpyDeviceToHost, st));
       CK(cudaMemcpyAsync(hp + 64, totals, 3 * 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(hp + 96, c->d_scalars32.p, 4, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       memcpy(h, hp, NB_U32_COUNT * 4); memcpy(tot, hp + 64, 24);
+      uint32_t e; memcpy(&e, hp + 96, 4);
+      if (e) { const int rce = decode_device_errors(c, e, st); if (rce) return rce; }
     }
     bool again = false;
     if ((int)h[NB_GMAX] > tp.gmax) { tp.gmax = (int)h[NB_GMAX]; again = true; }
@@ -1388,8 +1420,11 @@ static int nbh_bits_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
         char* hp = static_cast<char*>(c->h_pinned);
         CK(cudaMemcpyAsync(hp, counters, NB_U32_COUNT * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(hp + 64, totals, 3 * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hp + 96, c->d_scalars32.p, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         memcpy(h, hp, NB_U32_COUNT * 4); memcpy(tot, hp + 64, 24);
+        uint32_t e; memcpy(&e, hp + 96, 4);
+        if (e) { const int rce = decode_device_errors(c, e, st); if (rce) return rce; }
       }
       if (h[NB_OVERFLOW] & 4u) return XNB_OK;                      // a row needs more masks than the kernel holds: two-pass build
       bool again = false;
@@ -1515,19 +1550,18 @@ int xnb_chunk_neighbors(xnb_ctx* c, void* stream)
   c->ghost_lists = false;
   if (n > 0 && !env_flag("XNB_NBH_UNTILED") && !c->nbh_half_symmetric && !c->nbh_skip_ghosts)
   {
-    // occupancy of the cells (tile shape and capacities follow from it)
-    CK(cudaMemsetAsync(s32 + 5, 0, 8, st));
-    LAUNCH(k_cell_stats, nblk(g.n_cells, 256), 256, st, g, c->cell_count.p, s32 + 5);
-    uint32_t cs[2] = {0, 0};
-    rc = read_back(c, s32 + 5, 2, cs, st); if (rc) return rc;
-    c->max_cell_count = std::max<uint32_t>(cs[0], 1); c->n_nonempty_inner = cs[1];
+    // occupancy of the cells (tile shape and capacities follow from it); ghost_comm_scheme has usually read it already
+    if (!c->cell_stats_valid)
+    {
+      CK(cudaMemsetAsync(s32 + 5, 0, 8, st));
+      LAUNCH(k_cell_stats, nblk(g.n_cells, 256), 256, st, g, c->cell_count.p, s32 + 5);
+      uint32_t cs[2] = {0, 0};
+      rc = read_back(c, s32 + 5, 2, cs, st); if (rc) return rc;
+      c->max_cell_count = std::max<uint32_t>(cs[0], 1); c->n_nonempty_inner = cs[1]; c->cell_stats_valid = true;
+    }
     bool done = false;
     rc = nbh_bits_run(c, 0, st, &done); if (rc) return rc;
-    if (done)
-    {
-      if ((rc = t_end(c, XNB_T_NBH, st))) return rc;
-      return check_device_errors(c, st);
-    }
+    if (done) return t_end(c, XNB_T_NBH, st);       // (the build's own host wait read the device error word too)
   }
   // ---- per-particle two-pass form (count -> sizes -> scan -> fill)
   // the AMR tables prune whole sub-cells when they describe the current in-cell order (rebuild_amr ran after the last binning)
@@ -1981,7 +2015,10 @@ static int move_and_update_full(xnb_ctx* c, void* stream)
   int rc;
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = t_begin(c, XNB_T_BIN, st))) return rc;
-  if ((rc = xnb_move_particles(c, stream))) return rc;
+  c->in_rebuild_chain = true;
+  rc = xnb_move_particles(c, stream);
+  c->in_rebuild_chain = false;
+  if (rc) return rc;
   if ((rc = xnb_rebuild_amr(c, stream))) return rc;
   if ((rc = xnb_backup_r(c, stream))) return rc;
   if ((rc = t_end(c, XNB_T_BIN, st))) return rc;

@@ -176,6 +176,55 @@ constexpr int CELLSORT_MAX = 2048;   // particles per cell sorted out of shared 
 constexpr int CELLSORT_THREADS = 128;
 
 // big_keys / big_srcs: global scratch of n_src entries for cells beyond CELLSORT_MAX (slices [cell_start, cell_start + n) are disjoint)
+// k_cell_sort for cells of at most 32 particles (C2, C3, C5: the usual case), one WARP per cell: keys in registers, rank by 32
+// shuffles.  A fuller cell (the occupancy may have changed since the host last looked) is still sorted correctly, by the same warp
+// through the global scratch (slow, rare).  In-cell order = ascending particle id, as k_cell_sort<false>.
+__global__ void __launch_bounds__(256)
+k_cell_sort_warp(int n_cells, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
+                 const uint32_t* __restrict__ perm_in, uint32_t* __restrict__ perm_out, const unsigned long long* __restrict__ id,
+                 unsigned long long* __restrict__ big_keys, uint32_t* __restrict__ big_srcs, uint32_t* __restrict__ err)
+{
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < n_cells; c += gridDim.x * wpb)
+  {
+    const int n = (int)cell_count[c];
+    if (n == 0) continue;
+    if (n > 65535) { if (lane == 0) atomicOr(err, DERR_CELL_OVERFLOW); continue; }
+    const uint32_t s0 = cell_start[c];
+    if (n <= 32)
+    {
+      uint32_t src = 0; unsigned long long key = ~0ull;
+      if (lane < n)
+      {
+        src = perm_in[s0 + lane];
+        const unsigned long long pid = id[src];
+        if (pid >> 52) atomicOr(err, DERR_ID_RANGE);
+        key = pid & ((1ull << 52) - 1ull);
+      }
+      int r = 0;
+      for (int u = 0; u < n; u++) r += (__shfl_sync(0xffffffffu, key, u) < key) ? 1 : 0;
+      if (lane < n) perm_out[s0 + r] = src;
+      continue;
+    }
+    for (int t = lane; t < n; t += 32)
+    {
+      const uint32_t src = perm_in[s0 + t];
+      const unsigned long long pid = id[src];
+      if (pid >> 52) atomicOr(err, DERR_ID_RANGE);
+      big_keys[s0 + t] = pid & ((1ull << 52) - 1ull); big_srcs[s0 + t] = src;
+    }
+    __syncwarp();
+    for (int t = lane; t < n; t += 32)
+    {
+      const unsigned long long my = big_keys[s0 + t];
+      int r = 0;
+      for (int u = 0; u < n; u++) r += (big_keys[s0 + u] < my) ? 1 : 0;
+      perm_out[s0 + r] = big_srcs[s0 + t];
+    }
+  }
+}
+
 template <bool AMR>
 __global__ void __launch_bounds__(CELLSORT_THREADS)
 k_cell_sort(GridP g, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,

@@ -289,6 +289,27 @@ def test_speculative_fast_path_changes_nothing(monkeypatch):
         assert np.array_equal(pa[k], pb[k]), k
 
 
+@pytest.mark.parametrize("case", ["lj2k", "lj_voids", "ni16k"])
+def test_in_cell_sort_kernels_agree(case, monkeypatch):
+    """binning sorts every cell by particle id with one warp per cell (cells of up to 32 particles: keys in registers; fuller cells
+    through global scratch) or one block per cell: same particle order, hence bit-identical runs"""
+    kw = CASES[case]
+    eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
+    out = []
+    for var in ("XNB_CELLSORT_WARP", "XNB_CELLSORT_BLOCK"):
+        monkeypatch.delenv("XNB_CELLSORT_WARP", raising=False); monkeypatch.delenv("XNB_CELLSORT_BLOCK", raising=False)
+        monkeypatch.setenv(var, "1")
+        _, ctx = setup_pair(kw)
+        ctx.first_iteration(eps, sig, rc)
+        order0 = ctx.get_particles(0, ctx.n_inner, fields=("id",))["id"].copy()
+        rb = ctx.run_steps(25, dt, eps, sig, rc)
+        out.append((order0, rb, ctx.get_particles(0, ctx.n_inner)))
+        ctx.close()
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+    for k in ("id", "rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
+        assert np.array_equal(out[0][2][k], out[1][2][k]), k
+
+
 @pytest.mark.parametrize("case", ["lj2k", "lj_voids", "lj_gap2", "ni16k"])
 def test_fused_next_first_half_changes_nothing(case, monkeypatch):
     """inside one xnb_run_steps call the sweep of step k also performs the first half of step k + 1 (k_lj_sweep_cl MODE 2: positions
