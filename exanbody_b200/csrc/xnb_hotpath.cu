@@ -727,7 +727,7 @@ int xnb_move_particles(xnb_ctx* c, void* stream)
   // cells beyond the shared-memory sort capacity rank through global scratch (12 bytes per particle)
   CK(c->sort_keys.ensure((size_t)n_src + 16, 0, 1.2)); CK(c->sort_srcs.ensure((size_t)n_src + 16, 0, 1.2));
   // the fullest cell at the last neighbour build tells which kernel suits (either one is correct for any occupancy)
-  if ((c->max_cell_count > 0 && c->max_cell_count <= 32 && !env_flag("XNB_CELLSORT_BLOCK")) || env_flag("XNB_CELLSORT_WARP"))
+  if ((c->max_cell_count > 0 && c->max_cell_count <= 56 && !env_flag("XNB_CELLSORT_BLOCK")) || env_flag("XNB_CELLSORT_WARP"))
     LAUNCH(k_cell_sort_warp, std::min(nblk(g.n_cells, 8), 148u * 16u), 256, st, g.n_cells, c->cell_start.p, c->cell_count.p, c->perm.p, c->perm2.p, A.id, c->sort_keys.p, c->sort_srcs.p, s32);
   else
   LAUNCH((k_cell_sort<false>), (unsigned)g.n_cells, CELLSORT_THREADS, st, g, c->cell_start.p, c->cell_count.p, c->perm.p, c->perm2.p,

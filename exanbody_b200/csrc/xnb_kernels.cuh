@@ -176,8 +176,8 @@ constexpr int CELLSORT_MAX = 2048;   // particles per cell sorted out of shared 
 constexpr int CELLSORT_THREADS = 128;
 
 // big_keys / big_srcs: global scratch of n_src entries for cells beyond CELLSORT_MAX (slices [cell_start, cell_start + n) are disjoint)
-// k_cell_sort for cells of at most 32 particles (C2, C3, C5: the usual case), one WARP per cell: keys in registers, rank by 32
-// shuffles.  A fuller cell (the occupancy may have changed since the host last looked) is still sorted correctly, by the same warp
+// k_cell_sort for cells of at most 64 particles (C2, C3, C5: the usual case), one WARP per cell: two keys per lane in registers,
+// rank by shuffles.  A fuller cell (the occupancy may have changed since the host last looked) is still sorted correctly, by the same warp
 // through the global scratch (slow, rare).  In-cell order = ascending particle id, as k_cell_sort<false>.
 __global__ void __launch_bounds__(256)
 k_cell_sort_warp(int n_cells, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_count,
@@ -192,19 +192,30 @@ k_cell_sort_warp(int n_cells, const uint32_t* __restrict__ cell_start, const uin
     if (n == 0) continue;
     if (n > 65535) { if (lane == 0) atomicOr(err, DERR_CELL_OVERFLOW); continue; }
     const uint32_t s0 = cell_start[c];
-    if (n <= 32)
+    if (n <= 64)
     {
-      uint32_t src = 0; unsigned long long key = ~0ull;
+      // two keys per lane (particles lane and lane + 32); rank = number of smaller keys among the n
+      uint32_t src0 = 0, src1 = 0; unsigned long long key0 = ~0ull, key1 = ~0ull;
       if (lane < n)
       {
-        src = perm_in[s0 + lane];
-        const unsigned long long pid = id[src];
+        src0 = perm_in[s0 + lane];
+        const unsigned long long pid = id[src0];
         if (pid >> 52) atomicOr(err, DERR_ID_RANGE);
-        key = pid & ((1ull << 52) - 1ull);
+        key0 = pid & ((1ull << 52) - 1ull);
       }
-      int r = 0;
-      for (int u = 0; u < n; u++) r += (__shfl_sync(0xffffffffu, key, u) < key) ? 1 : 0;
-      if (lane < n) perm_out[s0 + r] = src;
+      if (lane + 32 < n)
+      {
+        src1 = perm_in[s0 + lane + 32];
+        const unsigned long long pid = id[src1];
+        if (pid >> 52) atomicOr(err, DERR_ID_RANGE);
+        key1 = pid & ((1ull << 52) - 1ull);
+      }
+      int r0 = 0, r1 = 0;
+      const int na = min(n, 32);
+      for (int u = 0; u < na; u++) { const unsigned long long k = __shfl_sync(0xffffffffu, key0, u); r0 += (k < key0) ? 1 : 0; r1 += (k < key1) ? 1 : 0; }
+      for (int u = 32; u < n; u++) { const unsigned long long k = __shfl_sync(0xffffffffu, key1, u - 32); r0 += (k < key0) ? 1 : 0; r1 += (k < key1) ? 1 : 0; }
+      if (lane < n) perm_out[s0 + r0] = src0;
+      if (lane + 32 < n) perm_out[s0 + r1] = src1;
       continue;
     }
     for (int t = lane; t < n; t += 32)

@@ -291,7 +291,7 @@ def test_speculative_fast_path_changes_nothing(monkeypatch):
 
 @pytest.mark.parametrize("case", ["lj2k", "lj_voids", "ni16k"])
 def test_in_cell_sort_kernels_agree(case, monkeypatch):
-    """binning sorts every cell by particle id with one warp per cell (cells of up to 32 particles: keys in registers; fuller cells
+    """binning sorts every cell by particle id with one warp per cell (cells of up to 64 particles: keys in registers; fuller cells
     through global scratch) or one block per cell: same particle order, hence bit-identical runs"""
     kw = CASES[case]
     eps, sig, rc, dt = kw["epsilon"], kw["sigma"], kw["rcut"], kw["dt"]
