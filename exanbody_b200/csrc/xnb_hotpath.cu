@@ -1711,10 +1711,9 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
     if (nb == 0) return XNB_OK;
     if (k.planes)
     {
-      if constexpr (MODE == 2) return c->fail(XNB_ERR_INVALID, "fused next first half: not offered by the plane-staged sweep");
-      else {
+      {
       // large cells: rows in plane segments, one plane of the halo staged at a time (xnb_sweep_pl.cuh)
-      static bool pl_attr_done_dev[XNB_MAX_DEVICES][2][2] = {};
+      static bool pl_attr_done_dev[XNB_MAX_DEVICES][3][2] = {};
       auto& pl_attr_done = pl_attr_done_dev[c->device % XNB_MAX_DEVICES];
       if (!pl_attr_done[MODE][EV ? 1 : 0])
       {
@@ -1723,7 +1722,7 @@ static int launch_force_f(xnb_ctx* c, bool ghost, const F& lj, double dth, doubl
         pl_attr_done[MODE][EV ? 1 : 0] = true;
       }
       if (part == 0 && (rc = t_begin(c, XNB_T_FORCE, st))) return rc;
-      k_lj_sweep_pl<F, MODE, EV><<<nb, k.threads, k.smem, st>>>(c->g, k.tp, k.cap_pl, (int)c->n_inner, (int)c->n_total, lj, dth, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
+      k_lj_sweep_pl<F, MODE, EV><<<nb, k.threads, k.smem, st>>>(c->g, k.tp, k.cap_pl, (int)c->n_inner, (int)c->n_total, lj, dth, c->next_half, A.rx, A.ry, A.rz, A.vx, A.vy, A.vz,
           fxo ? fxo : A.fx, fyo ? fyo : A.fy, fzo ? fzo : A.fz, A.type, c->mass.p, c->cell_start.p, c->cell_count.p, c->cl_groups.p,
           reinterpret_cast<const uint2*>(c->cl_rows.p), EV ? c->ev_partials.p : nullptr, c->d_scalars32.p, skip_if_nonzero, tl);
       c->launches++; CK(cudaGetLastError());
@@ -2080,7 +2079,7 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
   // stage the old ones) and the two buffers trade places afterwards; the displacement count of step k + 1 goes to the counter slot step k
   // is not using.  The last step of the call is a plain MODE 1 sweep, so the state a caller sees is the usual one.
   const bool fuse_ok = speculate && !env_flag("XNB_NO_FUSED_FIRST_HALF") && !c->hout.active;
-  auto can_fuse = [&](int it) { return fuse_ok && it + 1 < nsteps && c->cl.valid && !c->cl.ghost && !c->cl.planes && !env_flag("XNB_SWEEP_STREAMS") && c->n_inner > 0; };
+  auto can_fuse = [&](int it) { return fuse_ok && it + 1 < nsteps && c->cl.valid && !c->cl.ghost && !env_flag("XNB_SWEEP_STREAMS") && c->n_inner > 0; };
   auto arm_next_half = [&](unsigned long long* counter) -> int {
     ParticlesP B = c->P(1 - c->cur);
     CK(cudaMemsetAsync(counter, 0, 8, st));

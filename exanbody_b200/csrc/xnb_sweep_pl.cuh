@@ -26,7 +26,7 @@ __host__ __device__ inline size_t pl_sweep_smem_bytes(int nh_max, int tc_max, in
 
 template <class F, int MODE, bool EV>
 __global__ void __launch_bounds__(SWEEP_PL_MAX_THREADS, 2)
-k_lj_sweep_pl(GridP g, ClTileP tp, int cap_pl, int n_inner, int n_total, F lj, double dth,
+k_lj_sweep_pl(GridP g, ClTileP tp, int cap_pl, int n_inner, int n_total, F lj, double dth, NextHalfP nh,
               const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
               double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
               double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
@@ -117,15 +117,30 @@ k_lj_sweep_pl(GridP g, ClTileP tp, int cap_pl, int n_inner, int n_total, F lj, d
     }
     R += (size_t)trips * 32u;
   }
+  bool over = false;
   if (active)
   {
     double ax = acc.ax, ay = acc.ay, az = acc.az;
     if (MODE == 0) { fx[i] += ax; fy[i] += ay; fz[i] += az; }
     else
     {
+      if (MODE == 2) { m = mass[type[i]]; ux = vx[i]; uy = vy[i]; uz = vz[i]; }
       ax = __ddiv_rn(ax, m); ay = __ddiv_rn(ay, m); az = __ddiv_rn(az, m);
       fx[i] = ax; fy[i] = ay; fz[i] = az;
-      if (dth != 0.0)
+      if (MODE == 2)
+      {
+        // second half of this step, then the first half of the next (as k_lj_sweep_cl MODE 2)
+        ux = __dadd_rn(ux, __dmul_rn(ax, dth)); uy = __dadd_rn(uy, __dmul_rn(ay, dth)); uz = __dadd_rn(uz, __dmul_rn(az, dth));
+        const double x = __dadd_rn(xa, __dadd_rn(__dmul_rn(ux, nh.dt), __dmul_rn(ax, nh.dt2)));
+        const double y = __dadd_rn(ya, __dadd_rn(__dmul_rn(uy, nh.dt), __dmul_rn(ay, nh.dt2)));
+        const double z = __dadd_rn(za, __dadd_rn(__dmul_rn(uz, nh.dt), __dmul_rn(az, nh.dt2)));
+        nh.nrx[i] = x; nh.nry[i] = y; nh.nrz[i] = z;
+        vx[i] = __dadd_rn(ux, __dmul_rn(ax, dth));
+        vy[i] = __dadd_rn(uy, __dmul_rn(ay, dth));
+        vz[i] = __dadd_rn(uz, __dmul_rn(az, dth));
+        over = displ_over_test(g, nh.atom_cell[i], nh.backup + 3 * (size_t)i, x, y, z, nh.thr2);
+      }
+      else if (dth != 0.0)
       {
         vx[i] = __dadd_rn(ux, __dmul_rn(ax, dth));
         vy[i] = __dadd_rn(uy, __dmul_rn(ay, dth));
@@ -133,7 +148,8 @@ k_lj_sweep_pl(GridP g, ClTileP tp, int cap_pl, int n_inner, int n_total, F lj, d
       }
     }
   }
-  if (MODE == 1)
+  if (MODE == 2) block_count_add(over, nh.counter);
+  if (MODE != 0)
   {
     // zero_particle_force{ghost:true}: ghost particles keep f = 0 (each block clears its slice of the ghost range)
     const int ng = n_total - n_inner;
