@@ -117,7 +117,8 @@ int xnb_get_cells(xnb_ctx*, uint32_t* cell_start /* n_cells */, uint32_t* cell_c
    678: per-cell SoA pointers).  Field f of particle p of cell c is f[cell_start[c] + p], p < cell_count[c]; inner particles
    are [0, n_inner) sorted by cell, ghosts follow.  All pointers are device pointers owned by the ctx; they stay valid until
    the next xnb_move_particles / xnb_rebuild_amr / xnb_ghost_comm_scheme (binning gathers into the other buffer, ghost creation
-   may grow the arrays): take the view again after those.  Does not synchronise: work enqueued on the caller's stream is
+   may grow the arrays) and the next xnb_run_steps of more than one step (its sweeps write the next positions into the other position
+   buffer and the two trade places): take the view again after those.  Does not synchronise: work enqueued on the caller's stream is
    ordered with the kernels that produce these arrays.                                                                */
 typedef struct xnb_particle_view
 {
