@@ -183,6 +183,7 @@ struct xnb_ctx
     DBuf<PeerSlot> d_slots; DBuf<unsigned char> d_rec;                      // device table for the kernels; all-gather scratch
     std::vector<PeerSlot> h_slots;                                          // source of the asynchronous upload of d_slots
     unsigned long long epoch = 0, epoch_over = 0;                           // exchanges done (halo / displacement sum): same on every rank
+    unsigned long long timeout_ns = PEER_TIMEOUT_NS;
   };
   PeerHalo peer;
   // ---- counters
@@ -388,7 +389,7 @@ int decode_device_errors(xnb_ctx* c, uint32_t e, cudaStream_t st)
   if (e & DERR_SORT_CAPACITY) return c->fail(XNB_ERR_CAPACITY, "in-cell sort: no scratch for a cell of more than 2048 particles");
   if (e & DERR_ID_RANGE) return c->fail(XNB_ERR_CAPACITY, "particle id >= 2^52");
   if (e & DERR_TILE_CAPACITY) return c->fail(XNB_ERR_CAPACITY, "a tile exceeded its shared-memory staging capacity");
-  if (e & DERR_PEER_TIMEOUT) return c->fail(XNB_ERR_NCCL, "peer-memory halo: a partner's data did not arrive within 20 s");
+  if (e & DERR_PEER_TIMEOUT) return c->fail(XNB_ERR_NCCL, "peer-memory halo: a partner's data did not arrive in time (XNB_PEER_TIMEOUT_MS, default 20 s)");
   return c->fail(XNB_ERR_INVALID, "device error word " + std::to_string(e));
 }
 
@@ -938,6 +939,7 @@ int peer_refresh(xnb_ctx* c, cudaStream_t st)
   if (c->nranks < 2 || (P.tried && !P.enabled)) return 0;
   const bool first = !P.tried;
   P.tried = true;
+  if (first && env_int("XNB_PEER_TIMEOUT_MS") > 0) P.timeout_ns = (unsigned long long)env_int("XNB_PEER_TIMEOUT_MS") * 1000000ull;
   bool my_ok = c->nranks <= PEER_MAX_RANKS && !(first && env_flag("XNB_GHOST_NCCL"));
   if (my_ok)
   {
@@ -1065,8 +1067,8 @@ static int ghost_update(xnb_ctx* c, bool all, cudaStream_t st)
       const unsigned nb = std::min(nblk((int64_t)ng, 256), grid_cap);
       const uint32_t* rb = c->d_ghost_base.p + (size_t)c->nranks + 1;
       const double* half = reinterpret_cast<const double*>(static_cast<const char*>(P.box) + PEER_HDR_BYTES) + (epoch & 1ull) * P.cap_words;
-      if (all) LAUNCH((k_ghost_pull<true>), nb, 256, st, (int)ng, (uint32_t)c->n_inner, A, rb, c->nranks, c->rank, hdr, half, epoch, c->d_scalars32.p);
-      else     LAUNCH((k_ghost_pull<false>), nb, 256, st, (int)ng, (uint32_t)c->n_inner, A, rb, c->nranks, c->rank, hdr, half, epoch, c->d_scalars32.p);
+      if (all) LAUNCH((k_ghost_pull<true>), nb, 256, st, (int)ng, (uint32_t)c->n_inner, A, rb, c->nranks, c->rank, hdr, half, epoch, c->d_scalars32.p, P.timeout_ns);
+      else     LAUNCH((k_ghost_pull<false>), nb, 256, st, (int)ng, (uint32_t)c->n_inner, A, rb, c->nranks, c->rank, hdr, half, epoch, c->d_scalars32.p, P.timeout_ns);
     }
     return XNB_OK;
   }
@@ -2102,7 +2104,7 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
     {
       if (!c->comm) return c->fail(XNB_ERR_NCCL, "no communicator");
       if (c->peer.enabled)
-        LAUNCH(k_peer_allsum, 1, PEER_MAX_RANKS, st, c->nranks, c->rank, c->peer.d_slots.p, static_cast<const PeerHdr*>(c->peer.box), ++c->peer.epoch_over, cnt, c->d_scalars32.p);
+        LAUNCH(k_peer_allsum, 1, PEER_MAX_RANKS, st, c->nranks, c->rank, c->peer.d_slots.p, static_cast<const PeerHdr*>(c->peer.box), ++c->peer.epoch_over, cnt, c->d_scalars32.p, c->peer.timeout_ns);
       else NK(g_nccl.AllReduce(cnt, cnt, 1, nccl_uint64, nccl_sum, c->comm, st));
     }
     CK(cudaMemcpyAsync(const_cast<unsigned long long*>(h_flag), cnt, 8, cudaMemcpyDeviceToHost, st));
@@ -2153,6 +2155,9 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
     if (over > 0)
     {
       if (speculate && c->timing && c->tpool[XNB_T_FORCE].used == force_scopes + 1) c->tpool[XNB_T_FORCE].used = force_scopes;   // the void launch is not a sweep
+      // peer transport: a partner whose count never arrived also lands here (k_peer_allsum forces the rebuild path on a timeout) --
+      // report it before the rebuild's NCCL exchanges would wait for that partner
+      if (c->nranks > 1 && c->peer.enabled && (rc = check_device_errors(c, st))) return rc;
       if ((rc = move_and_update_full(c, stream))) return rc;
       rebuilds++;
       fused = can_fuse(it);                       // the void launch did nothing; the sweep after the rebuild may carry the next first half

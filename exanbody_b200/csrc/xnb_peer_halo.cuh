@@ -26,7 +26,7 @@ namespace xnb {
 
 constexpr int PEER_MAX_RANKS = 64;
 constexpr size_t PEER_HDR_BYTES = 4096;
-constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;      // default; XNB_PEER_TIMEOUT_MS overrides (tests)
 struct PeerHdr
 {
   unsigned long long over[2][PEER_MAX_RANKS];
@@ -45,7 +45,7 @@ XNB_DEVINL void st_release_sys(unsigned long long* p, unsigned long long v) { as
 XNB_DEVINL unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // spin until *p >= want (MATCH: until the high 32 bits equal want); false on timeout
 template <bool MATCH>
-XNB_DEVINL bool peer_wait(const unsigned long long* p, unsigned long long want, unsigned long long* got)
+XNB_DEVINL bool peer_wait(const unsigned long long* p, unsigned long long want, unsigned long long* got, unsigned long long timeout_ns)
 {
   unsigned long long t0 = 0; unsigned int spins = 0;
   for (;;)
@@ -55,7 +55,7 @@ XNB_DEVINL bool peer_wait(const unsigned long long* p, unsigned long long want, 
     if (++spins > 64u)
     {
       __nanosleep(200);
-      if ((spins & 1023u) == 0u) { const unsigned long long t = global_timer_ns(); if (t0 == 0) t0 = t; else if (t - t0 > PEER_TIMEOUT_NS) return false; }
+      if ((spins & 255u) == 0u) { const unsigned long long t = global_timer_ns(); if (t0 == 0) t0 = t; else if (t - t0 > timeout_ns) return false; }
     }
   }
 }
@@ -117,7 +117,7 @@ k_ghost_push(GridP g, int n_send, const uint32_t* __restrict__ send_src, const u
 template <bool ALL_FIELDS>
 __global__ void __launch_bounds__(256)
 k_ghost_pull(int n_ghost, uint32_t n_inner, ParticlesP p, const uint32_t* __restrict__ recv_base, int nranks, int self_rank,
-             const PeerHdr* my_hdr, const double* half, unsigned long long epoch, uint32_t* __restrict__ err)
+             const PeerHdr* my_hdr, const double* half, unsigned long long epoch, uint32_t* __restrict__ err, unsigned long long timeout_ns)
 {
   constexpr size_t NW = ALL_FIELDS ? GHOST_WORDS_ALL : GHOST_WORDS_R;
   __shared__ int s_lo, s_hi; __shared__ bool s_ok;
@@ -133,7 +133,7 @@ k_ghost_pull(int n_ghost, uint32_t n_inner, ParticlesP p, const uint32_t* __rest
       for (int pr = lo; pr <= hi && s_ok; pr++)
       {
         if (pr == self_rank || recv_base[pr + 1] == recv_base[pr] || (pr >= seen_lo && pr <= seen_hi)) continue;
-        if (!peer_wait<false>(&my_hdr->flag[pr], epoch, nullptr)) { s_ok = false; atomicOr(err, DERR_PEER_TIMEOUT); }
+        if (!peer_wait<false>(&my_hdr->flag[pr], epoch, nullptr, timeout_ns)) { s_ok = false; atomicOr(err, DERR_PEER_TIMEOUT); }
       }
       if (seen_hi < seen_lo) seen_lo = lo;
       seen_hi = hi;
@@ -163,7 +163,7 @@ k_ghost_pull(int n_ghost, uint32_t n_inner, ParticlesP p, const uint32_t* __rest
 // sum over ranks of value[0] (in place).  One block, one thread per rank (nranks <= PEER_MAX_RANKS).
 __global__ void __launch_bounds__(PEER_MAX_RANKS)
 k_peer_allsum(int nranks, int me, const PeerSlot* __restrict__ peers, const PeerHdr* my_hdr, unsigned long long epoch, unsigned long long* value,
-              uint32_t* __restrict__ err)
+              uint32_t* __restrict__ err, unsigned long long timeout_ns)
 {
   __shared__ unsigned long long s_part[PEER_MAX_RANKS];
   const int t = threadIdx.x;
@@ -173,7 +173,7 @@ k_peer_allsum(int nranks, int me, const PeerSlot* __restrict__ peers, const Peer
   if (t < nranks)
   {
     st_release_sys(&reinterpret_cast<PeerHdr*>(peers[t].base)->over[epoch & 1ull][me], (e32 << 32) | mine);
-    if (!peer_wait<true>(&my_hdr->over[epoch & 1ull][t], e32, &got)) { atomicOr(err, DERR_PEER_TIMEOUT); got = 1; }     // a timeout forces the rebuild path
+    if (!peer_wait<true>(&my_hdr->over[epoch & 1ull][t], e32, &got, timeout_ns)) { atomicOr(err, DERR_PEER_TIMEOUT); got = 1; }     // a timeout forces the rebuild path
   }
   s_part[t] = (t < nranks) ? (got & 0xffffffffull) : 0ull;
   __syncthreads();

@@ -28,6 +28,21 @@ def test_decomposed_run_is_bit_identical_to_single_gpu(world, transport):
     assert r.stdout.count("transport %s" % transport) == 3, r.stdout[-2000:]
 
 
+def test_a_silent_partner_is_an_error_not_a_hang():
+    """peer-memory halo: the waits inside k_peer_allsum / k_ghost_pull give up after XNB_PEER_TIMEOUT_MS (default 20 s) and the step
+    loop returns XNB_ERR_NCCL before it would enter the rebuild's NCCL exchanges"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_dead_partner.py")]
+    env = dict(os.environ, XNB_PEER_TIMEOUT_MS="500")
+    env.pop("XNB_GHOST_NCCL", None)
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "silent partner reported" in r.stdout, r.stdout[-2000:]
+
+
 def test_two_contexts_on_two_devices_in_one_process():
     """one process may hold sub-domains on several GPUs (kernel attributes and the current device are handled per context):
     the same input stepped alternately on cuda:0 and cuda:1 gives bit-identical results"""
