@@ -345,6 +345,17 @@ def short_run(name, device, steps=12, warmup=3):
            "list_entries_per_atom": si["candidates"] / max(n, 1) if si["compiled"] else None,
            "whole_step_hbm_frac": (253.0 + S) * value / 1e9 / peak}
     ctx.close()
+    if si["compiled"] and fk > 0:
+        # F_alg = 8 N_list + 19 N_cut (+ 30 integrate) flop per atom-step, N_cut from N_list by the volume ratio; against the
+        # DFMA rate measured now (C4 is the FP64-bound configuration: rc = 5 sigma, 530 list entries per atom)
+        try:
+            dfma = capi.measure_dfma_peak(device)
+            n_list = si["candidates"] / max(n, 1)
+            f_sweep = 8.0 * n_list + 19.0 * n_list * (rc / (rc + kw["rcut_inc"])) ** 3
+            out["sweep_fp64_frac"] = f_sweep * n / (fk * 1e-3) / 1e12 / dfma
+            out["whole_step_fp64_frac"] = (f_sweep + 30.0) * value / 1e12 / dfma
+        except Exception:
+            pass
     return out
 
 

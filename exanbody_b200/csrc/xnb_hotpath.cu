@@ -1282,10 +1282,9 @@ static int nbh_big_run(xnb_ctx* c, int mode, cudaStream_t st, bool* done)
     NbhBitsP bp{};
     bp.emit_rows = mode == 0 ? 1 : 0; bp.sel_mode = mode; bp.slot_words = (int)c->nbh_slot_words; bp.cap_trips = c->nb_cap_trips; bp.max_dist2 = c->nbh_dist * c->nbh_dist;
     // compiled rows in one segment per z-plane of halo cells: the sweep then stages a third of the halo at a time (k_lj_sweep_pl)
-    // (plane segments are padded per plane: about a third more rows and a slower build; that pays when a list is swept several times,
-    // not when the system rebuilds on every step)
-    const bool planes = mode == 0 && gap == 1 && tp.gmax <= SWEEP_PL_MAX_THREADS / 32 && cap32 <= 8190 && !env_flag("XNB_CL_NO_PLANES") &&
-                        (c->last_nbh_interval < 0 || c->last_nbh_interval >= 4 || env_flag("XNB_CL_PLANES"));
+    // (plane segments are padded per plane: about a third more rows.  Measured at C4, which rebuilds on every step: build 2.97 -> 3.03 ms,
+    // sweep 0.816 -> 0.644 ms, step 4.19 -> 4.08 ms -- it pays even when a list is swept once.)
+    const bool planes = mode == 0 && gap == 1 && tp.gmax <= SWEEP_PL_MAX_THREADS / 32 && cap32 <= 8190 && !env_flag("XNB_CL_NO_PLANES");
     bp.planes = planes ? 1 : 0; bp.cap_pl = cap32;
     NbhBitsOut o{c->pool.p, c->cell_stream.p, c->stream_size.p, c->cell_stream_bytes.p, c->stream_off.p, c->cl_groups.p, reinterpret_cast<uint2*>(c->cl_rows.p), counters, totals};
     if (getenv("XNB_TILE_DEBUG")) fprintf(stderr, "[xnb] nbh_big mode %d cap %d cap32 %d gmax %d trips %d slot_words %u smem %zu blocks %u (max cell %u)\n", mode, tp.cap, cap32, tp.gmax, c->nb_cap_trips, c->nbh_slot_words, smem, blocks, mcc);
