@@ -245,7 +245,10 @@ k_cl_compile(GridP g, ClTileP tp, const uint32_t* __restrict__ cell_start, const
 // independent FP64 chains.  Arithmetic identical to k_lj_sweep.
 // VAR 0: <= 576 threads, two blocks per SM (<= 56 registers); VAR 1: <= 1024 threads.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t CL_PREFETCH_ROWS = 8;
+#ifndef XNB_CL_PREFETCH_ROWS
+#define XNB_CL_PREFETCH_ROWS 8
+#endif
+constexpr uint32_t CL_PREFETCH_ROWS = XNB_CL_PREFETCH_ROWS;      // rows pulled towards L2 ahead of the trip that needs them (4 and 16 measured: no better)
 
 XNB_DEVINL uint2 ld_stream8(const uint2* p)
 {
