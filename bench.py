@@ -5,11 +5,12 @@
 
 One "step" = one MD time step (numerical_scheme of data/config/numerical-scheme.msp:21-25) of the named workload, neighbour
 rebuilds included whenever the displacement trigger fires.  N=1 runs C2 (2 048 000 atoms); N>1 runs C3 (4 000 000 atoms per
-GPU, spatial decomposition, NCCL halo) under torchrun.  Prints ONE JSON line (rank 0).
+GPU, spatial decomposition, halo over NVLink peer memory) under torchrun.  Prints ONE JSON line (rank 0).
 
   value     device-resident rate: atoms(all ranks) * K / max-over-ranks CUDA-event time of the K steps
   e2e       the same steps driven through the C-ABI with HOST buffers (one xnb_step_host call per step): r,v go up from pinned
-            host memory, the step runs, r,v,f come back (ids too on the steps that rebuild) -- copies inside the timed region
+            host memory, the step runs, r,v,f come back (ids too on the steps that rebuild) -- copies inside the timed region;
+            with several ranks xnb_step_host_n on every rank (atoms migrate at rebuilds: the call returns the rank's new particle count)
   roofline  the dominant kernel (pair sweep k_lj_sweep_cl): algorithmic bytes per launch / its mean CUDA-event duration
   cpu_baseline  the CPU oracle (oracle/, the OpenMP restatement of the reference) on a bounded sample of the same workload
 
@@ -521,7 +522,40 @@ def b200_arm(args):
         assert ctx.n_inner == n
 
     e2e = None
-    if world == 1 and not args.no_e2e:       # with several ranks atoms migrate between ranks, so host buffers change size: e2e is defined at N=1
+    if world > 1 and not args.no_e2e:
+        # several ranks: xnb_step_host_n -- atoms migrate at a rebuild, so the host arrays have room to spare and the call says how many
+        # particles the rank owns afterwards; every step still uploads r, v and brings back r, v, f (+ ids when the step rebuilt)
+        cap = int(n * 1.25) + 4096
+        hbn = {k2: torch.empty(cap, dtype=torch.float64).pin_memory() for k2 in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz")}
+        hidn = torch.empty(cap, dtype=torch.int64).pin_memory()
+        pn = {k2: v.data_ptr() for k2, v in hbn.items()}
+        ctx.download_rvf(pn["rx"], pn["ry"], pn["rz"], pn["vx"], pn["vy"], pn["vz"], pn["fx"], pn["fy"], pn["fz"], hidn.data_ptr(), sh)
+        state = {"n": int(n), "rebuilds": 0, "h2d": 0, "d2h": 0}
+
+        def e2e_step_n():
+            n_in = state["n"]
+            rbs, n_new = ctx.step_host_n(dt, eps, sig, rc, cap, in_r=(pn["rx"], pn["ry"], pn["rz"]), in_v=(pn["vx"], pn["vy"], pn["vz"]),
+                                         out_r=(pn["rx"], pn["ry"], pn["rz"]), out_v=(pn["vx"], pn["vy"], pn["vz"]),
+                                         out_f=(pn["fx"], pn["fy"], pn["fz"]), out_id=hidn.data_ptr(), stream=sh)
+            state["n"] = n_new; state["rebuilds"] += rbs; state["h2d"] += 48 * n_in; state["d2h"] += 72 * n_new + 8 * n_new * rbs
+
+        e2e_steps = max(3, min(args.steps, 20))
+        for _ in range(3):
+            e2e_step_n()
+        barrier()
+        state.update(rebuilds=0, h2d=0, d2h=0)
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            e2e_step_n()
+        e1.record(stream)
+        barrier()
+        ems = max_over_ranks(e0.elapsed_time(e1))
+        h2d_all = sum_over_ranks(float(state["h2d"])); d2h_all = sum_over_ranks(float(state["d2h"]))
+        e2e = {"value": n_atoms * e2e_steps / (ems * 1e-3), "unit": "atom-timesteps/s", "h2d_bytes_per_step": h2d_all / e2e_steps,
+               "d2h_bytes_per_step": d2h_all / e2e_steps, "steps": e2e_steps, "rebuilds": state["rebuilds"], "ms_per_step": ems / e2e_steps,
+               "what": "per step one xnb_step_host_n call on every rank: r,v of the rank's atoms from pinned host memory -> one step (halo over peer "
+                       "memory, migration at rebuilds) -> r,v,f back (ids too on the steps that rebuild); bytes summed over the ranks, time = max over ranks"}
+    if world == 1 and not args.no_e2e:       # (N = 1: xnb_step_host, the arrays keep their size)
         e2e_steps = max(3, min(args.steps, 20))
         for _ in range(3):
             e2e_step()

@@ -20,7 +20,7 @@ SYMBOLS = [
     "xnb_get_grid_info", "xnb_get_sweep_info", "xnb_get_cells", "xnb_view_particles", "xnb_device_allocations", "xnb_move_particles", "xnb_rebuild_amr", "xnb_backup_r", "xnb_ghost_comm_scheme",
     "xnb_ghost_update_all", "xnb_ghost_update_r", "xnb_ghost_transport", "xnb_chunk_neighbors", "xnb_zero_particle_force", "xnb_set_pair_functor", "xnb_lennard_jones_force", "xnb_gravitational_force", "xnb_average_neighbors", "xnb_get_generic_field", "xnb_load_balance_rcb", "xnb_get_block", "xnb_host_amr_sub_cell_pairs",
     "xnb_divide_force_by_mass", "xnb_set_chunk_neighbors_config", "xnb_lennard_jones_force_symmetric", "xnb_update_force_from_ghost", "xnb_push_f_v_r", "xnb_push_f_v", "xnb_particle_displ_over", "xnb_verlet_first_half",
-    "xnb_read_displ_over", "xnb_force_and_second_half", "xnb_run_steps", "xnb_step_host", "xnb_first_iteration", "xnb_energy_virial",
+    "xnb_read_displ_over", "xnb_force_and_second_half", "xnb_run_steps", "xnb_step_host", "xnb_step_host_n", "xnb_first_iteration", "xnb_energy_virial",
     "xnb_view_chunk_neighbors", "xnb_stream_pool_u16", "xnb_get_streams", "xnb_get_amr", "xnb_get_backup",
     "xnb_rebuild_count", "xnb_kernel_launches", "xnb_timing_enable", "xnb_timing_read", "xnb_measure_dfma_peak",
     "xnb_host_lattice_fcc", "xnb_host_rcb_block", "xnb_host_load_balance_rcb", "xnb_host_simple_cost_model", "xnb_host_ghost_items",
@@ -87,7 +87,7 @@ def load():
         "xnb_set_chunk_neighbors_config": (I, [P, I, I]), "xnb_lennard_jones_force_symmetric": (I, [P, D, D, D, P]), "xnb_update_force_from_ghost": (I, [P, P]),
         "xnb_push_f_v_r": (I, [P, D, D, P]), "xnb_push_f_v": (I, [P, D, D, P]), "xnb_particle_displ_over": (I, [P, P, P]),
         "xnb_verlet_first_half": (I, [P, D, P]), "xnb_read_displ_over": (I, [P, P, P]), "xnb_force_and_second_half": (I, [P, D, D, D, D, P]),
-        "xnb_run_steps": (I, [P, I, D, D, D, D, P, P]), "xnb_step_host": (I, [P, D, D, D, D, P, P, P, P, P, P, I, P, P]), "xnb_first_iteration": (I, [P, D, D, D, P]),
+        "xnb_run_steps": (I, [P, I, D, D, D, D, P, P]), "xnb_step_host": (I, [P, D, D, D, D, P, P, P, P, P, P, I, P, P]), "xnb_step_host_n": (I, [P, D, D, D, D, P, P, P, P, P, P, I64, P, P, P]), "xnb_first_iteration": (I, [P, D, D, D, P]),
         "xnb_energy_virial": (I, [P, D, D, D, P, P, P, P]),
         "xnb_view_chunk_neighbors": (I, [P, P, P, P]), "xnb_stream_pool_u16": (I64, [P]), "xnb_get_streams": (I, [P, P, P]),
         "xnb_get_amr": (I64, [P, P, P]), "xnb_get_backup": (I, [P, P]), "xnb_rebuild_count": (I64, [P]), "xnb_kernel_launches": (I64, [P]),
@@ -294,6 +294,16 @@ class Context:
         self._ck(self.L.xnb_step_host(self.h, dt, epsilon, sigma, rcut, *[C.cast(k, C.c_void_p) if k is not None else None for k in keep],
                                       _p(out_id), int(bool(id_always)), _p(stream), C.addressof(r)))
         return r.value
+
+    def step_host_n(self, dt, epsilon, sigma, rcut, capacity, in_r=None, in_v=None, out_r=None, out_v=None, out_f=None, out_id=None, stream=None):
+        """xnb_step_host_n (several sub-domains): returns (rebuilds, particles this rank owns after the step)"""
+        def trip(t):
+            return None if t is None else (C.c_void_p * 3)(*[_p(x) for x in t])
+        keep = [trip(t) for t in (in_r, in_v, out_r, out_v, out_f)]
+        r = C.c_int(); n = C.c_int64()
+        self._ck(self.L.xnb_step_host_n(self.h, dt, epsilon, sigma, rcut, *[C.cast(k, C.c_void_p) if k is not None else None for k in keep],
+                                        _p(out_id), int(capacity), C.addressof(n), _p(stream), C.addressof(r)))
+        return r.value, n.value
 
     def first_iteration(self, epsilon, sigma, rcut, stream=None): self._ck(self.L.xnb_first_iteration(self.h, epsilon, sigma, rcut, _p(stream)))
 

@@ -167,7 +167,7 @@ struct xnb_ctx
   DBuf<int> d_blocks;
   DBuf<uint32_t> mig_rank, mig_pos, mig_base; std::vector<uint32_t> h_mig_base;     // mig_base: per destination send offsets | per source receive offsets (nranks + 1 each)
   // ---- xnb_step_host: positions (and ids) go back to the host on their own stream as soon as they are final
-  struct HostOut { bool active = false, issued = false, id_always = false, id_copied = false; double* r[3] = {nullptr, nullptr, nullptr}; uint64_t* id = nullptr; };
+  struct HostOut { bool active = false, issued = false, id_always = false, id_copied = false, overflow = false; double* r[3] = {nullptr, nullptr, nullptr}; uint64_t* id = nullptr; size_t capacity = 0; };
   HostOut hout; cudaStream_t st_d2h = nullptr; cudaEvent_t ev_d2h_go = nullptr, ev_d2h_done = nullptr;
   void* h_pinned = nullptr;               // 4 KB pinned scratch for small read-backs ([1024..1032): displacement count of xnb_run_steps)
   cudaEvent_t ev_flag = nullptr;
@@ -2003,6 +2003,7 @@ static int host_out_positions(xnb_ctx* c, cudaEvent_t after, bool rebuilt)
   h.issued = true;
   CK(cudaStreamWaitEvent(c->st_d2h, after, 0));
   const size_t n = (size_t)c->n_inner;
+  if (n > h.capacity) { h.overflow = true; return XNB_OK; }       // (several ranks: migration brought in more particles than the caller's arrays hold)
   for (int f = 0; f < 3; f++) if (h.r[f] && n) CK(cudaMemcpyAsync(h.r[f], c->f64[c->cur][f].p, n * 8, cudaMemcpyDeviceToHost, c->st_d2h));
   h.id_copied = h.id && (rebuilt || h.id_always);
   if (h.id_copied && n) CK(cudaMemcpyAsync(h.id, c->idb[c->cur].p, n * 8, cudaMemcpyDeviceToHost, c->st_d2h));
@@ -2184,13 +2185,35 @@ int xnb_run_steps(xnb_ctx* c, int nsteps, double dt, double eps, double sig, dou
   return XNB_OK;
 }
 
+} // extern "C"
+static int step_host_impl(xnb_ctx* c, double dt, double eps, double sig, double rcut,
+                          const double* const in_r[3], const double* const in_v[3],
+                          double* const out_r[3], double* const out_v[3], double* const out_f[3], uint64_t* out_id, int id_always,
+                          int64_t capacity, int64_t* n_out, void* stream, int* rebuilt_out);
+extern "C" {
 int xnb_step_host(xnb_ctx* c, double dt, double eps, double sig, double rcut,
                   const double* const in_r[3], const double* const in_v[3],
                   double* const out_r[3], double* const out_v[3], double* const out_f[3], uint64_t* out_id, int id_always,
                   void* stream, int* rebuilt_out)
 {
   if (!c) return XNB_ERR_INVALID;
-  if (c->nranks != 1) return c->fail(XNB_ERR_INVALID, "xnb_step_host: host-resident stepping is defined for a single sub-domain (particles migrate between ranks otherwise)");
+  if (c->nranks != 1) return c->fail(XNB_ERR_INVALID, "xnb_step_host: single sub-domain only (particles migrate between ranks otherwise: xnb_step_host_n)");
+  return step_host_impl(c, dt, eps, sig, rcut, in_r, in_v, out_r, out_v, out_f, out_id, id_always, -1, nullptr, stream, rebuilt_out);
+}
+int xnb_step_host_n(xnb_ctx* c, double dt, double eps, double sig, double rcut,
+                    const double* const in_r[3], const double* const in_v[3],
+                    double* const out_r[3], double* const out_v[3], double* const out_f[3], uint64_t* out_id,
+                    int64_t capacity, int64_t* n_out, void* stream, int* rebuilt_out)
+{
+  if (!c || capacity < 0 || !n_out) return XNB_ERR_INVALID;
+  return step_host_impl(c, dt, eps, sig, rcut, in_r, in_v, out_r, out_v, out_f, out_id, 0, capacity, n_out, stream, rebuilt_out);
+}
+} // extern "C"
+static int step_host_impl(xnb_ctx* c, double dt, double eps, double sig, double rcut,
+                          const double* const in_r[3], const double* const in_v[3],
+                          double* const out_r[3], double* const out_v[3], double* const out_f[3], uint64_t* out_id, int id_always,
+                          int64_t capacity, int64_t* n_out, void* stream, int* rebuilt_out)
+{
   if (!c->have_nbh) return c->fail(XNB_ERR_INVALID, "no neighbour list (run xnb_first_iteration)");
   CK(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -2209,19 +2232,23 @@ int xnb_step_host(xnb_ctx* c, double dt, double eps, double sig, double rcut,
   xnb_ctx::HostOut& h = c->hout;
   h = xnb_ctx::HostOut();
   h.active = true; h.id_always = id_always != 0; h.id = out_id;
+  h.capacity = capacity < 0 ? n : (size_t)capacity;
   for (int f = 0; f < 3; f++) h.r[f] = out_r ? out_r[f] : nullptr;
   int rebuilds = 0;
   int rc = xnb_run_steps(c, 1, dt, eps, sig, rcut, stream, &rebuilds);
-  const bool issued = h.issued;
+  const bool issued = h.issued, overflow = h.overflow;
   h.active = false;
   if (rc) { cudaStreamSynchronize(c->st_d2h); return rc; }
   if (!issued) return c->fail(XNB_ERR_INVALID, "xnb_step_host: internal error (positions never became final)");
-  if ((size_t)c->n_inner != n) { cudaStreamSynchronize(c->st_d2h); return c->fail(XNB_ERR_INVALID, "xnb_step_host: the number of particles changed (a particle left a non-periodic domain)"); }
+  const size_t n_now = (size_t)c->n_inner;
+  if (n_out) *n_out = (int64_t)n_now;
+  if (capacity < 0 && n_now != n) { cudaStreamSynchronize(c->st_d2h); return c->fail(XNB_ERR_INVALID, "xnb_step_host: the number of particles changed (a particle left a non-periodic domain)"); }
+  if (overflow || n_now > h.capacity) { cudaStreamSynchronize(c->st_d2h); return c->fail(XNB_ERR_CAPACITY, "xnb_step_host_n: this rank now owns more particles than the caller's arrays hold (the device state is intact: enlarge and xnb_download_rvf)"); }
   // v and f are final after the sweep's epilogue
   for (int f = 0; f < 3; f++)
   {
-    if (out_v && out_v[f] && n) CK(cudaMemcpyAsync(out_v[f], c->f64[c->cur][3 + f].p, n * 8, cudaMemcpyDeviceToHost, st));
-    if (out_f && out_f[f] && n) CK(cudaMemcpyAsync(out_f[f], c->f64[c->cur][6 + f].p, n * 8, cudaMemcpyDeviceToHost, st));
+    if (out_v && out_v[f] && n_now) CK(cudaMemcpyAsync(out_v[f], c->f64[c->cur][3 + f].p, n_now * 8, cudaMemcpyDeviceToHost, st));
+    if (out_f && out_f[f] && n_now) CK(cudaMemcpyAsync(out_f[f], c->f64[c->cur][6 + f].p, n_now * 8, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaEventRecord(c->ev_d2h_done, c->st_d2h));
   CK(cudaStreamWaitEvent(st, c->ev_d2h_done, 0));
@@ -2230,6 +2257,7 @@ int xnb_step_host(xnb_ctx* c, double dt, double eps, double sig, double rcut,
   return XNB_OK;
 }
 
+extern "C" {
 int xnb_energy_virial(xnb_ctx* c, double eps, double sig, double rcut, double* epot, double virial[6], double* ekin, void* stream)
 {
   if (!c) return XNB_ERR_INVALID;

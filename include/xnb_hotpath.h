@@ -244,6 +244,15 @@ int xnb_step_host(xnb_ctx*, double dt, double epsilon, double sigma, double rcut
                   const double* const in_r[3], const double* const in_v[3],
                   double* const out_r[3], double* const out_v[3], double* const out_f[3], uint64_t* out_id, int id_always,
                   void* stream, int* rebuilt_out);
+/* the same with SEVERAL sub-domains (collective, like xnb_run_steps): when the step rebuilds, particles migrate between the ranks
+   (mpi/migrate_cell_particles.cpp:101-143) and this rank then owns *n_out particles, possibly more or fewer than it uploaded.  The out
+   arrays hold `capacity` elements each; r, v, f and ids of the rank's particles after the step are written (ids whenever the step
+   rebuilt); the next call uploads *n_out elements.  XNB_ERR_CAPACITY if *n_out > capacity: the device state is intact, enlarge the
+   arrays and fetch it with xnb_download_rvf.                                                                                   */
+int xnb_step_host_n(xnb_ctx*, double dt, double epsilon, double sigma, double rcut,
+                    const double* const in_r[3], const double* const in_v[3],
+                    double* const out_r[3], double* const out_v[3], double* const out_f[3], uint64_t* out_id,
+                    int64_t capacity, int64_t* n_out, void* stream, int* rebuilt_out);   /* [host sync] */
 /* init_particles + first force (update-particles.msp:55-60, compute-loop.msp:1-7)                               */
 int xnb_first_iteration(xnb_ctx*, double epsilon, double sigma, double rcut, void* stream);
 

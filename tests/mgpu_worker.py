@@ -65,6 +65,30 @@ def main():
         mine = ctx.get_particles(0, ctx.n_inner)
         everyone = [None] * world
         dist.all_gather_object(everyone, {k: mine[k] for k in ("id", "rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz")})
+        if name == "lj_12x8x8":
+            # host-resident particles with several ranks (xnb_step_host_n): every step uploads r, v from host arrays and brings r, v, f
+            # (and the ids after a rebuild: atoms migrate between the ranks) back; same trajectory as the device-resident loop
+            ctx2 = U.make_ctx(kw, rank=rank, nranks=world, device=local, particles=inp)
+            uid2 = [ctx2.nccl_unique_id().copy() if rank == 0 else None]
+            dist.broadcast_object_list(uid2, 0)
+            ctx2.nccl_init_rank(uid2[0], rank, world)
+            ctx2.first_iteration(eps, sig, rc)
+            cap = int(ctx2.n_inner * 1.5) + 1024
+            hb = {k: np.zeros(cap) for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz")}
+            hid = np.zeros(cap, np.uint64)
+            ctx2.download_rvf(hb["rx"], hb["ry"], hb["rz"], hb["vx"], hb["vy"], hb["vz"], hb["fx"], hb["fy"], hb["fz"], hid)
+            n2, rb2, counts2 = ctx2.n_inner, 0, set()
+            for _ in range(nsteps):
+                r_, n2 = ctx2.step_host_n(dt, eps, sig, rc, cap, in_r=(hb["rx"], hb["ry"], hb["rz"]), in_v=(hb["vx"], hb["vy"], hb["vz"]),
+                                          out_r=(hb["rx"], hb["ry"], hb["rz"]), out_v=(hb["vx"], hb["vy"], hb["vz"]), out_f=(hb["fx"], hb["fy"], hb["fz"]), out_id=hid)
+                rb2 += r_; counts2.add(n2)
+            assert rb2 == rb and n2 == ctx2.n_inner == ctx.n_inner, (rb2, rb, n2, ctx.n_inner)
+            assert np.array_equal(hid[:n2], mine["id"]), "host-resident stepping: ids differ from the device-resident run"
+            for k in ("rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz"):
+                assert np.array_equal(hb[k][:n2], mine[k]), "host-resident stepping: %s differs from the device-resident run" % k
+            if rank == 0:
+                print("step_host_n ok: %d ranks, %d steps, %d rebuilds, particle counts seen on rank 0: %s" % (world, nsteps, rb2, sorted(counts2)), flush=True)
+            ctx2.close()
         # Newton-3 path on the final configuration: half_symmetric lists, symmetric sweep, and the ghost
         # exchange run backwards (update_force_from_ghost over NCCL) must reproduce the full-list forces (= a, mass 1 here)
         ctx.set_chunk_neighbors_config(half_symmetric=True); ctx.chunk_neighbors()
