@@ -688,10 +688,25 @@ int xnb_move_particles(xnb_ctx* c, void* stream)
     // all ranks learn the full count matrix
     DBuf<uint32_t>& mat = c->scan_tmp32;
     CK(mat.ensure((size_t)c->nranks * 64 + 64));
+    // the diagonal of the matrix is free (nobody migrates to itself): it carries every rank's device error word, so that an error one
+    // rank ran into (a particle left a non periodic domain, jumped further than a neighbour block ...) ends the call on ALL ranks here,
+    // before the exchange below would wait for the rank that gave up (the reference's fatal_error aborts every rank)
+    CK(cudaMemcpyAsync(d_cnt + c->rank, s32, 4, cudaMemcpyDeviceToDevice, st));
     NK(g_nccl.AllGather(d_cnt, mat.p, 64, nccl_uint32, c->comm, st));
     std::vector<uint32_t> hmat((size_t)c->nranks * 64);
     CK(cudaMemcpyAsync(hmat.data(), mat.p, hmat.size() * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    {
+      int bad_rank = -1;
+      for (int p = 0; p < c->nranks; p++) { if (hmat[(size_t)p * 64 + p] && bad_rank < 0) bad_rank = p; }
+      if (bad_rank >= 0)
+      {
+        const uint32_t mine = hmat[(size_t)c->rank * 64 + c->rank];
+        if (mine) return decode_device_errors(c, mine, st);
+        CK(cudaMemsetAsync(s32, 0, 4, st));
+        return c->fail(XNB_ERR_INVALID, "rank " + std::to_string(bad_rank) + " reported a device error (word " + std::to_string(hmat[(size_t)bad_rank * 64 + bad_rank]) + ") while binning: the step is abandoned on every rank");
+      }
+    }
     std::vector<uint32_t> sbase((size_t)c->nranks + 1, 0), rbase((size_t)c->nranks + 1, 0);
     for (int p = 0; p < c->nranks; p++) { sbase[(size_t)p + 1] = sbase[(size_t)p] + hmat[(size_t)c->rank * 64 + p]; rbase[(size_t)p + 1] = rbase[(size_t)p] + hmat[(size_t)p * 64 + c->rank]; }
     n_arrive = rbase[(size_t)c->nranks];

@@ -43,6 +43,20 @@ def test_a_silent_partner_is_an_error_not_a_hang():
     assert "silent partner reported" in r.stdout, r.stdout[-2000:]
 
 
+def test_an_error_on_one_rank_ends_the_step_on_every_rank():
+    """a particle leaves a non periodic domain on one rank: that rank reports it, and the other rank returns from the same call with an
+    error too (the migration's count matrix carries the error words) -- the reference's fatal_error aborts every rank"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "tests", "mgpu_lost_particle.py")]
+    env = dict(os.environ, XNB_PEER_TIMEOUT_MS="2000")
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "collective error ok" in r.stdout, r.stdout[-2000:]
+
+
 def test_two_contexts_on_two_devices_in_one_process():
     """one process may hold sub-domains on several GPUs (kernel attributes and the current device are handled per context):
     the same input stepped alternately on cuda:0 and cuda:1 gives bit-identical results"""
